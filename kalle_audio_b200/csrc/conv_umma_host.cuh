@@ -1,0 +1,268 @@
+// Host side of the tcgen05 convolution: tap tables (how Conv1d / strided Conv1d /
+// ConvTranspose1d decompose into (input phase, row shift, weight slab) contributions),
+// TMA tensor maps over the channels-last activations and the packed weights, launch.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "conv_umma.cuh"
+
+namespace kvae {
+
+enum ConvKind { kConv = 0, kConvT = 1 };
+
+// Geometry of one weight-normalised convolution layer of the Oobleck stack.
+struct ConvGeom {
+  int kind;      // kConv: nn.Conv1d ; kConvT: nn.ConvTranspose1d
+  int Cin, Cout, K, stride, dilation, pad;
+  int out_len(int T_in) const {
+    if (kind == kConv) return (T_in + 2 * pad - dilation * (K - 1) - 1) / stride + 1;
+    return (T_in - 1) * stride - 2 * pad + dilation * (K - 1) + 1;
+  }
+};
+
+inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+inline int posmod(int a, int b) { int r = a % b; return r < 0 ? r + b : r; }
+
+struct TapPlan {
+  int P_in = 1;    // input phases (strided Conv1d views x as [T/s, s, C])
+  int P_out = 1;   // output phases (ConvTranspose1d stride)
+  int span = 0;    // max over slabs of (max shift - min shift)
+  int tap_begin[kMaxPhases + 1] = {0};
+  std::vector<Tap> taps;
+};
+
+// per_tap_slab = true stages one A slab per tap (no row-shifted descriptors); used by the probe.
+inline bool build_taps(const ConvGeom& g, bool per_tap_slab, TapPlan& tp, std::string& err) {
+  tp = TapPlan();
+  struct Raw { int a_phase, delta, w; };
+  std::vector<std::vector<Raw>> by_out_phase;
+  if (g.kind == kConv) {
+    tp.P_in = g.stride;
+    tp.P_out = 1;
+    if (g.stride > 1 && g.dilation != 1) { err = "strided conv with dilation unsupported"; return false; }
+    std::vector<Raw> v;
+    for (int k = 0; k < g.K; ++k) {
+      const int off = k * g.dilation - g.pad;          // input row = t*stride + off
+      v.push_back({posmod(off, g.stride), floordiv(off, g.stride), k});
+    }
+    by_out_phase.push_back(v);
+  } else {
+    if (g.dilation != 1) { err = "dilated transposed conv unsupported"; return false; }
+    tp.P_in = 1;
+    tp.P_out = g.stride;
+    for (int phi = 0; phi < g.stride; ++phi) {
+      std::vector<Raw> v;
+      for (int k = 0; k < g.K; ++k)
+        if (posmod(phi + g.pad - k, g.stride) == 0)     // t_out = q*s+phi = t_in*s - pad + k
+          v.push_back({0, floordiv(phi + g.pad - k, g.stride), k});
+      by_out_phase.push_back(v);
+    }
+  }
+  if (tp.P_out > kMaxPhases) { err = "too many output phases"; return false; }
+  for (int phi = 0; phi < tp.P_out; ++phi) {
+    tp.tap_begin[phi] = static_cast<int>(tp.taps.size());
+    auto& v = by_out_phase[phi];
+    // group by input phase; a group shares one staged slab
+    std::stable_sort(v.begin(), v.end(), [](const Raw& a, const Raw& b) { return a.a_phase < b.a_phase; });
+    size_t i = 0;
+    while (i < v.size()) {
+      size_t j = i;
+      int dmin = v[i].delta, dmax = v[i].delta;
+      while (j < v.size() && v[j].a_phase == v[i].a_phase) {
+        dmin = std::min(dmin, v[j].delta);
+        dmax = std::max(dmax, v[j].delta);
+        ++j;
+      }
+      if (!per_tap_slab) tp.span = std::max(tp.span, dmax - dmin);
+      for (size_t t = i; t < j; ++t) {
+        Tap tap;
+        tap.a_phase = static_cast<int16_t>(v[t].a_phase);
+        tap.w_slab = static_cast<int16_t>(v[t].w);
+        if (per_tap_slab) {
+          tap.a_row = static_cast<int16_t>(v[t].delta);
+          tap.shift = 0;
+          tap.first = 1;
+          tap.last = 1;
+        } else {
+          tap.a_row = static_cast<int16_t>(dmin);
+          tap.shift = static_cast<int16_t>(v[t].delta - dmin);
+          tap.first = (t == i) ? 1 : 0;
+          tap.last = (t + 1 == j) ? 1 : 0;
+        }
+        tp.taps.push_back(tap);
+      }
+      i = j;
+    }
+  }
+  tp.tap_begin[tp.P_out] = static_cast<int>(tp.taps.size());
+  for (int phi = tp.P_out + 1; phi <= kMaxPhases; ++phi) tp.tap_begin[phi] = tp.tap_begin[tp.P_out];
+  if (static_cast<int>(tp.taps.size()) > kMaxTaps) { err = "too many taps"; return false; }
+  return true;
+}
+
+// ------------------------------------------------------------------ tensor maps
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                        const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_tmapEncodeTiled tmap_encoder() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+// Activations x: [B, T, C] bf16 viewed as [B, T/P, P, C]; box = {64 ch, 1 phase, RB rows, 1}.
+inline bool make_act_tmap(CUtensorMap* m, const void* x, int B, int T, int C, int P, int RB,
+                          std::string& err) {
+  auto enc = tmap_encoder();
+  if (!enc) { err = "cuTensorMapEncodeTiled unavailable"; return false; }
+  if (T % P) { err = "input length not divisible by stride"; return false; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)P, (cuuint64_t)(T / P), (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)P * C * 2, (cuuint64_t)T * C * 2};
+  cuuint32_t box[4] = {64, 1, (cuuint32_t)RB, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(act) failed: " + std::to_string((int)r); return false; }
+  return true;
+}
+
+// Packed weights: [nslab, Cout, Cin] bf16; box = {64 ch, NT out-channels, 1 slab}.
+inline bool make_w_tmap(CUtensorMap* m, const void* w, int nslab, int Cout, int Cin, int NT,
+                        std::string& err) {
+  auto enc = tmap_encoder();
+  if (!enc) { err = "cuTensorMapEncodeTiled unavailable"; return false; }
+  cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)nslab};
+  cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)NT, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(w), dims, strides, box,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(w) failed: " + std::to_string((int)r); return false; }
+  return true;
+}
+
+// ------------------------------------------------------------------ launch
+struct ConvEpilogue {
+  const float* bias = nullptr;
+  const void* residual = nullptr;
+  int residual_f32 = 0;
+  void* out_raw = nullptr;
+  int out_raw_f32 = 0;
+  __nv_bfloat16* out_act = nullptr;
+  const float* snake_a = nullptr;
+  const float* snake_inv_b = nullptr;
+};
+
+struct ConvTuning {
+  int MT = 0;             // 0 = auto
+  int NT = 0;             // 0 = auto
+  int desc_mode = 0;
+  bool per_tap_slab = false;
+};
+
+inline bool umma_supported(const ConvGeom& g) {
+  return g.Cin % 64 == 0 && g.Cout % 64 == 0 && g.Cout >= 64;
+}
+
+inline int pick_nt(int Cout) {
+  if (Cout % 256 == 0) return 256;
+  if (Cout % 128 == 0) return 128;
+  return 64;
+}
+
+// A prepared launch: everything that depends on (layer, B, T, pointers) but not on the data.
+struct ConvLaunch {
+  CUtensorMap tmA, tmW;
+  ConvParams p;
+  dim3 grid;
+  size_t smem = 0;
+  int T_out = 0;
+};
+
+inline bool prepare_conv_umma(const ConvGeom& g, const __nv_bfloat16* x, int B, int T_in,
+                              const __nv_bfloat16* wpacked, const ConvEpilogue& ep,
+                              const ConvTuning& tune, ConvLaunch& L, std::string& err) {
+  if (!umma_supported(g)) { err = "channel counts not multiples of 64"; return false; }
+  TapPlan tp;
+  if (!build_taps(g, tune.per_tap_slab, tp, err)) return false;
+  const int T_out = g.out_len(T_in);
+  if (T_out <= 0 || T_out % tp.P_out) { err = "bad output length"; return false; }
+  ConvParams& p = L.p;
+  std::memset(&p, 0, sizeof(p));
+  p.B = B;
+  p.P_out = tp.P_out;
+  p.Tq_out = T_out / tp.P_out;
+  p.Cout = g.Cout;
+  p.n_chunks = g.Cin / 64;
+  p.NT = tune.NT ? tune.NT : pick_nt(g.Cout);
+  if (g.Cout % p.NT || p.NT % 16 || p.NT > 256) { err = "bad NT"; return false; }
+  int MT = tune.MT ? tune.MT : (p.Tq_out > 128 ? 2 : 1);
+  if (MT * p.NT > 512) MT = 1;
+  p.MT = MT;
+  const int rows = 128 * MT + tp.span;
+  p.nbox = (rows + 255) / 256;
+  p.RB = (((rows + p.nbox - 1) / p.nbox) + 7) & ~7;
+  if (p.RB > 256) { err = "slab box too tall"; return false; }
+  p.desc_mode = tune.desc_mode;
+  int cols = 32;
+  while (cols < MT * p.NT) cols <<= 1;
+  p.tmem_cols = cols;
+  for (int i = 0; i <= kMaxPhases; ++i) p.tap_begin[i] = tp.tap_begin[i];
+  for (size_t i = 0; i < tp.taps.size(); ++i) p.taps[i] = tp.taps[i];
+  // ring depths from the 227 KB budget
+  const size_t budget = 227 * 1024 - 2048;
+  const size_t a_bytes = static_cast<size_t>(p.nbox) * p.RB * 128, b_bytes = static_cast<size_t>(p.NT) * 128;
+  p.SA = 2;
+  if (2 * a_bytes + 2 * b_bytes > budget) p.SA = 1;
+  if (p.SA * a_bytes + 2 * b_bytes > budget) { err = "tile does not fit shared memory"; return false; }
+  p.SB = static_cast<int>(std::min<size_t>(8, (budget - p.SA * a_bytes) / b_bytes));
+  // spend what is left on a deeper A ring (strided convs stage `stride` slabs per chunk)
+  while (p.SA < 4 && (p.SA + 1) * a_bytes + p.SB * b_bytes <= budget) ++p.SA;
+  p.bias = ep.bias;
+  p.residual = ep.residual;
+  p.residual_f32 = ep.residual_f32;
+  p.out_raw = ep.out_raw;
+  p.out_raw_f32 = ep.out_raw_f32;
+  p.out_act = ep.out_act;
+  p.snake_a = ep.snake_a;
+  p.snake_inv_b = ep.snake_inv_b;
+  if (!make_act_tmap(&L.tmA, x, B, T_in, g.Cin, tp.P_in, p.RB, err)) return false;
+  if (!make_w_tmap(&L.tmW, wpacked, g.K, g.Cout, g.Cin, p.NT, err)) return false;
+  const int q_tiles = (p.Tq_out + 128 * MT - 1) / (128 * MT);
+  L.grid = dim3(q_tiles * tp.P_out, g.Cout / p.NT, B);
+  L.smem = conv_umma_smem_bytes(p);
+  L.T_out = T_out;
+  return true;
+}
+
+inline cudaError_t launch_conv_umma(const ConvLaunch& L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  conv_umma_kernel<<<L.grid, 256, L.smem, stream>>>(L.tmA, L.tmW, L.p);
+  return cudaGetLastError();
+}
+
+}  // namespace kvae

@@ -1,0 +1,283 @@
+// Stand-alone probe for the tcgen05 convolution kernel (kalle_audio_b200/csrc/conv_umma.cuh).
+// Each invocation runs ONE case so a trap in one case cannot poison the others:
+//   umma_probe <case> <variant>     variant 0: one A slab per tap (no shifted descriptors)
+//                                   variant 1: shared slab, descriptor base_offset = 0
+//                                   variant 2: shared slab, base_offset = (addr >> 7) & 7
+//   umma_probe perf <idx>           timing of full-size layers (no CPU check)
+// The check is a double-precision channels-last convolution over the same bf16-rounded operands.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+#include <vector>
+
+#include "../kalle_audio_b200/csrc/conv_umma_host.cuh"
+
+using namespace kvae;
+
+#define CK(x)                                                                          \
+  do {                                                                                 \
+    cudaError_t e_ = (x);                                                              \
+    if (e_ != cudaSuccess) {                                                           \
+      printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__);  \
+      exit(2);                                                                         \
+    }                                                                                  \
+  } while (0)
+
+static float bf16r(float f) { return __bfloat162float(__float2bfloat16(f)); }
+
+struct Case {
+  const char* name;
+  ConvGeom g;
+  int B, T;
+  int MT, NT;
+  bool epi;  // exercise bias + residual + raw + snake outputs
+};
+
+static const Case kCases[] = {
+    {"k1_c64_128_T128", {kConv, 64, 128, 1, 1, 1, 0}, 1, 128, 1, 128, false},
+    {"k1_c256_256_T300", {kConv, 256, 256, 1, 1, 1, 0}, 2, 300, 2, 256, false},
+    {"k7d1_c128", {kConv, 128, 128, 7, 1, 1, 3}, 2, 1000, 2, 128, false},
+    {"k7d3_c128", {kConv, 128, 128, 7, 1, 3, 9}, 2, 1000, 2, 128, false},
+    {"k7d9_c256", {kConv, 256, 256, 7, 1, 9, 27}, 1, 700, 2, 128, true},
+    {"convT_s8_k16", {kConvT, 256, 128, 16, 8, 1, 4}, 2, 150, 2, 128, false},
+    {"convT_s5_k11", {kConvT, 128, 64, 11, 5, 1, 3}, 1, 333, 2, 64, true},
+    {"convT_s2_k4", {kConvT, 128, 128, 4, 2, 1, 1}, 1, 257, 2, 128, false},
+    {"down_s4_k8", {kConv, 128, 256, 8, 4, 1, 2}, 2, 1024, 2, 256, false},
+    {"down_s5_k10", {kConv, 64, 128, 10, 5, 1, 3}, 1, 1500, 1, 128, true},
+    {"down_s8_k16", {kConv, 128, 128, 16, 8, 1, 4}, 1, 4096, 2, 128, false},
+    {"k3_c512_128", {kConv, 512, 128, 3, 1, 1, 1}, 1, 216, 1, 128, false},
+    {"k7_c64_2048", {kConv, 64, 2048, 7, 1, 1, 3}, 1, 216, 2, 256, true},
+};
+static const int kNumCases = sizeof(kCases) / sizeof(kCases[0]);
+
+// packed weights [k][co][ci]
+static void cpu_conv(const Case& c, const std::vector<float>& x, const std::vector<float>& w,
+                     std::vector<double>& y, int T_out) {
+  const ConvGeom& g = c.g;
+  y.assign((size_t)c.B * T_out * g.Cout, 0.0);
+  for (int b = 0; b < c.B; ++b)
+    for (int k = 0; k < g.K; ++k) {
+      if (g.kind == kConv) {
+        for (int t = 0; t < T_out; ++t) {
+          int ti = t * g.stride + k * g.dilation - g.pad;
+          if (ti < 0 || ti >= c.T) continue;
+          const float* xr = &x[((size_t)b * c.T + ti) * g.Cin];
+          for (int co = 0; co < g.Cout; ++co) {
+            const float* wr = &w[((size_t)k * g.Cout + co) * g.Cin];
+            double s = 0;
+            for (int ci = 0; ci < g.Cin; ++ci) s += (double)xr[ci] * wr[ci];
+            y[((size_t)b * T_out + t) * g.Cout + co] += s;
+          }
+        }
+      } else {
+        for (int ti = 0; ti < c.T; ++ti) {
+          int t = ti * g.stride - g.pad + k;
+          if (t < 0 || t >= T_out) continue;
+          const float* xr = &x[((size_t)b * c.T + ti) * g.Cin];
+          for (int co = 0; co < g.Cout; ++co) {
+            const float* wr = &w[((size_t)k * g.Cout + co) * g.Cin];
+            double s = 0;
+            for (int ci = 0; ci < g.Cin; ++ci) s += (double)xr[ci] * wr[ci];
+            y[((size_t)b * T_out + t) * g.Cout + co] += s;
+          }
+        }
+      }
+    }
+}
+
+static int run_case(int idx, int variant) {
+  const Case& c = kCases[idx];
+  const ConvGeom& g = c.g;
+  const int T_out = g.out_len(c.T);
+  std::mt19937 rng(1234 + idx);
+  std::normal_distribution<float> nd(0.f, 1.f);
+  std::vector<float> x((size_t)c.B * c.T * g.Cin), w((size_t)g.K * g.Cout * g.Cin);
+  for (auto& v : x) v = bf16r(nd(rng));
+  const float ws = 1.0f / std::sqrt((float)(g.Cin * (g.kind == kConv ? g.K : (g.K + g.stride - 1) / g.stride)));
+  for (auto& v : w) v = bf16r(nd(rng) * ws);
+  std::vector<float> bias(g.Cout), sa(g.Cout), sib(g.Cout), res((size_t)c.B * T_out * g.Cout);
+  for (int i = 0; i < g.Cout; ++i) {
+    bias[i] = nd(rng) * 0.1f;
+    sa[i] = std::exp(nd(rng) * 0.3f);
+    sib[i] = 1.0f / (std::exp(nd(rng) * 0.3f) + 1e-9f);
+  }
+  for (auto& v : res) v = nd(rng);
+  std::vector<double> ref;
+  cpu_conv(c, x, w, ref, T_out);
+
+  std::vector<__nv_bfloat16> xb(x.size()), wb(w.size());
+  for (size_t i = 0; i < x.size(); ++i) xb[i] = __float2bfloat16(x[i]);
+  for (size_t i = 0; i < w.size(); ++i) wb[i] = __float2bfloat16(w[i]);
+  __nv_bfloat16 *dx, *dw, *dact;
+  float *dbias, *dsa, *dsib, *dres, *draw;
+  const size_t nout = (size_t)c.B * T_out * g.Cout;
+  CK(cudaMalloc(&dx, xb.size() * 2));
+  CK(cudaMalloc(&dw, wb.size() * 2));
+  CK(cudaMalloc(&dact, nout * 2));
+  CK(cudaMalloc(&draw, nout * 4));
+  CK(cudaMalloc(&dres, nout * 4));
+  CK(cudaMalloc(&dbias, g.Cout * 4));
+  CK(cudaMalloc(&dsa, g.Cout * 4));
+  CK(cudaMalloc(&dsib, g.Cout * 4));
+  CK(cudaMemcpy(dx, xb.data(), xb.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dw, wb.data(), wb.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dres, res.data(), nout * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dbias, bias.data(), g.Cout * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dsa, sa.data(), g.Cout * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dsib, sib.data(), g.Cout * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(draw, 0xff, nout * 4));
+  CK(cudaMemset(dact, 0xff, nout * 2));
+
+  ConvEpilogue ep;
+  ep.out_raw = draw;
+  ep.out_raw_f32 = 1;
+  if (c.epi) {
+    ep.bias = dbias;
+    ep.residual = dres;
+    ep.residual_f32 = 1;
+    ep.out_act = dact;
+    ep.snake_a = dsa;
+    ep.snake_inv_b = dsib;
+  }
+  ConvTuning tune;
+  tune.MT = c.MT;
+  tune.NT = c.NT;
+  tune.per_tap_slab = (variant == 0);
+  tune.desc_mode = (variant == 2) ? 1 : 0;
+  ConvLaunch L;
+  std::string err;
+  if (!prepare_conv_umma(g, dx, c.B, c.T, dw, ep, tune, L, err)) {
+    printf("CASE %d %s variant %d: prepare failed: %s\n", idx, c.name, variant, err.c_str());
+    return 3;
+  }
+  printf("CASE %d %s variant %d: grid (%d,%d,%d) smem %zu MT %d NT %d RB %d nbox %d SA %d SB %d tmem %d taps %d\n",
+         idx, c.name, variant, L.grid.x, L.grid.y, L.grid.z, L.smem, L.p.MT, L.p.NT, L.p.RB, L.p.nbox,
+         L.p.SA, L.p.SB, L.p.tmem_cols, L.p.tap_begin[L.p.P_out]);
+  fflush(stdout);
+  CK(launch_conv_umma(L, 0));
+  CK(cudaDeviceSynchronize());
+  std::vector<float> raw(nout);
+  std::vector<__nv_bfloat16> act(nout);
+  CK(cudaMemcpy(raw.data(), draw, nout * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(act.data(), dact, nout * 2, cudaMemcpyDeviceToHost));
+  double max_err = 0, max_ref = 0, max_err_act = 0;
+  size_t bad = 0, first_bad = (size_t)-1;
+  for (size_t i = 0; i < nout; ++i) {
+    double r = ref[i];
+    if (c.epi) r += bias[i % g.Cout] + res[i];
+    double e = std::fabs((double)raw[i] - r);
+    if (!(e <= 1e30)) e = 1e30;  // NaN
+    max_err = std::max(max_err, e);
+    max_ref = std::max(max_ref, std::fabs(r));
+    if (e > 2e-2) { if (!bad) first_bad = i; ++bad; }
+    if (c.epi) {
+      double s = std::sin(r * sa[i % g.Cout]);
+      double a = r + sib[i % g.Cout] * s * s;
+      double ea = std::fabs((double)__bfloat162float(act[i]) - a);
+      if (!(ea <= 1e30)) ea = 1e30;
+      max_err_act = std::max(max_err_act, ea / (1.0 + std::fabs(a)));
+    }
+  }
+  const bool ok = bad == 0 && (!c.epi || max_err_act < 1e-2);
+  printf("RESULT case %d %s variant %d: %s max_err %.3e max_ref %.3e bad %zu/%zu act_rel_err %.3e\n", idx,
+         c.name, variant, ok ? "PASS" : "FAIL", max_err, max_ref, bad, nout, max_err_act);
+  if (bad) {
+    size_t i = first_bad;
+    size_t co = i % g.Cout, t = (i / g.Cout) % T_out, b = i / ((size_t)g.Cout * T_out);
+    printf("  first bad at b=%zu t=%zu co=%zu got %.5f want %.5f\n", b, t, co, raw[i],
+           ref[i] + (c.epi ? bias[co] + res[i] : 0.0));
+    // error map over (t mod 16) to expose row-shift / swizzle mistakes
+    std::vector<size_t> by_row(16, 0);
+    for (size_t j = 0; j < nout; ++j) {
+      double r = ref[j] + (c.epi ? bias[j % g.Cout] + res[j] : 0.0);
+      if (!(std::fabs((double)raw[j] - r) <= 2e-2)) by_row[(j / g.Cout) % T_out % 16]++;
+    }
+    printf("  bad count by t%%16:");
+    for (int j = 0; j < 16; ++j) printf(" %zu", by_row[j]);
+    printf("\n");
+  }
+  return ok ? 0 : 1;
+}
+
+struct Perf {
+  const char* name;
+  ConvGeom g;
+  int B, T, MT, NT;
+};
+static const Perf kPerf[] = {
+    {"sao_s5_k7_c128", {kConv, 128, 128, 7, 1, 1, 3}, 4, 442368, 2, 128},
+    {"sao_s5_k1_c128", {kConv, 128, 128, 1, 1, 1, 0}, 4, 442368, 2, 128},
+    {"sao_s4_k7_c256", {kConv, 256, 256, 7, 1, 3, 9}, 4, 221184, 2, 256},
+    {"sao_s4_k7_c256_nt128", {kConv, 256, 256, 7, 1, 3, 9}, 4, 221184, 2, 128},
+    {"sao_s3_k7_c512", {kConv, 512, 512, 7, 1, 9, 27}, 4, 55296, 2, 256},
+    {"sao_s1_k7_c2048", {kConv, 2048, 2048, 7, 1, 1, 3}, 16, 1728, 2, 256},
+    {"sao_convT_s8_1024_512", {kConvT, 1024, 512, 16, 8, 1, 4}, 16, 1728, 2, 256},
+    {"sao_convT_s2_128_128", {kConvT, 128, 128, 4, 2, 1, 1}, 4, 221184, 2, 128},
+};
+static const int kNumPerf = sizeof(kPerf) / sizeof(kPerf[0]);
+
+static int run_perf(int idx) {
+  const Perf& c = kPerf[idx];
+  const ConvGeom& g = c.g;
+  const int T_out = g.out_len(c.T);
+  const size_t nin = (size_t)c.B * c.T * g.Cin, nw = (size_t)g.K * g.Cout * g.Cin,
+               nout = (size_t)c.B * T_out * g.Cout;
+  __nv_bfloat16 *dx, *dw, *dact;
+  CK(cudaMalloc(&dx, nin * 2));
+  CK(cudaMalloc(&dw, nw * 2));
+  CK(cudaMalloc(&dact, nout * 2));
+  CK(cudaMemset(dx, 0, nin * 2));
+  CK(cudaMemset(dw, 0, nw * 2));
+  ConvEpilogue ep;
+  ep.out_act = dact;
+  ConvTuning tune;
+  tune.MT = c.MT;
+  tune.NT = c.NT;
+  ConvLaunch L;
+  std::string err;
+  if (!prepare_conv_umma(g, dx, c.B, c.T, dw, ep, tune, L, err)) {
+    printf("PERF %s: prepare failed: %s\n", c.name, err.c_str());
+    return 3;
+  }
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; ++i) CK(launch_conv_umma(L, 0));
+  CK(cudaDeviceSynchronize());
+  const int iters = 10;
+  CK(cudaEventRecord(e0));
+  for (int i = 0; i < iters; ++i) CK(launch_conv_umma(L, 0));
+  CK(cudaEventRecord(e1));
+  CK(cudaDeviceSynchronize());
+  float ms;
+  CK(cudaEventElapsedTime(&ms, e0, e1));
+  ms /= iters;
+  const double taps_eff = (g.kind == kConv) ? (double)g.K * T_out : (double)g.K * c.T;
+  const double flops = 2.0 * c.B * taps_eff * g.Cin * g.Cout;
+  const double bytes = (nin + nout) * 2.0;
+  printf("PERF %s: %.3f ms  %.1f TFLOP/s  %.1f GB/s (act in+out)  grid (%d,%d,%d) smem %zu SA %d SB %d\n",
+         c.name, ms, flops / ms * 1e-9, bytes / ms * 1e-6, L.grid.x, L.grid.y, L.grid.z, L.smem, L.p.SA,
+         L.p.SB);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc >= 3 && std::string(argv[1]) == "perf") {
+    int idx = atoi(argv[2]);
+    if (idx < 0 || idx >= kNumPerf) return 4;
+    return run_perf(idx);
+  }
+  if (argc >= 2 && std::string(argv[1]) == "count") {
+    printf("%d %d\n", kNumCases, kNumPerf);
+    return 0;
+  }
+  if (argc < 3) {
+    printf("usage: umma_probe <case 0..%d> <variant 0..2> | perf <0..%d> | count\n", kNumCases - 1,
+           kNumPerf - 1);
+    return 4;
+  }
+  int idx = atoi(argv[1]), variant = atoi(argv[2]);
+  if (idx < 0 || idx >= kNumCases) return 4;
+  return run_case(idx, variant);
+}
