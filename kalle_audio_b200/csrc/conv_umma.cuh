@@ -53,6 +53,7 @@ struct ConvParams {
   int residual_f32;         // residual element type: 1 fp32, 0 bf16
   void* out_raw;            // pre-activation output or nullptr
   int out_raw_f32;
+  int out_raw_cf;           // 1: out_raw is channels-first [B, Cout, T_out] (API layout), else [B, T_out, Cout]
   __nv_bfloat16* out_act;   // bf16 operand for the next conv (SnakeBeta applied if snake_a)
   const float* snake_a;     // exp(alpha)            [Cout] or nullptr (plain cast)
   const float* snake_inv_b; // 1/(exp(beta) + 1e-9)  [Cout]
@@ -231,7 +232,20 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
-        if (p.out_raw) {
+        if (p.out_raw && p.out_raw_cf) {
+          // channels-first store: lanes hold consecutive time steps -> 128 B (fp32) per channel
+          const size_t t_out = static_cast<size_t>(q) * p.P_out + phi;
+          const size_t o0 = (static_cast<size_t>(b) * p.Cout + cbase) * T_out + t_out;
+          if (p.out_raw_f32) {
+            float* op = static_cast<float*>(p.out_raw) + o0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) op[static_cast<size_t>(j) * T_out] = v[j];
+          } else {
+            __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.out_raw) + o0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) op[static_cast<size_t>(j) * T_out] = __float2bfloat16(v[j]);
+          }
+        } else if (p.out_raw) {
           if (p.out_raw_f32) {
             float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out_raw) + orow + cbase);
 #pragma unroll

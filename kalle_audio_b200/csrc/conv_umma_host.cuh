@@ -166,6 +166,7 @@ struct ConvEpilogue {
   int residual_f32 = 0;
   void* out_raw = nullptr;
   int out_raw_f32 = 0;
+  int out_raw_cf = 0;
   __nv_bfloat16* out_act = nullptr;
   const float* snake_a = nullptr;
   const float* snake_inv_b = nullptr;
@@ -241,6 +242,7 @@ inline bool prepare_conv_umma(const ConvGeom& g, const __nv_bfloat16* x, int B, 
   p.residual_f32 = ep.residual_f32;
   p.out_raw = ep.out_raw;
   p.out_raw_f32 = ep.out_raw_f32;
+  p.out_raw_cf = ep.out_raw_cf;
   p.out_act = ep.out_act;
   p.snake_a = ep.snake_a;
   p.snake_inv_b = ep.snake_inv_b;

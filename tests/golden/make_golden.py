@@ -1,0 +1,219 @@
+"""Generates the golden fixtures in this directory by running the REFERENCE's own modules.
+
+Run in the build container only (needs /root/reference, which does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference imports un-vendored third-party packages; they are stubbed exactly as SURVEY.md
+section 8c describes: ``dac.nn.layers.WNConv1d/WNConvTranspose1d`` are the published two-liners
+(old-style ``torch.nn.utils.weight_norm`` over ``nn.Conv1d`` / ``nn.ConvTranspose1d``), everything
+else on the import path that the hot path never executes is a MagicMock.
+
+Fixtures (all float32, little-endian .npz):
+  tiny_ae.npz       self-contained: state_dicts + inputs + outputs of a 3-stage Oobleck at C=8
+  mid_ae.npz        C=64 three-stage model (tensor-core path shapes); outputs + param checksums
+  sao_full.npz      Stable-Audio-Open-shape model, [1,64,216] <-> [1,2,442368]; output slices
+  o12_d512.npz      12.5 Hz shape (strides 2,4,4,5,8), latent 512, [1,512,16] -> [1,1,20480]
+  chunked.npz       decode_audio / encode_audio with chunked=True on the tiny model
+  sampling.npz      vae_sample (bottleneck.py:51) and sample() (model_sigmaVAE.py:187) outputs
+Weights of the larger models are NOT stored: they are re-created from the recorded seed by the
+same construction order (nn.Conv1d / nn.ConvTranspose1d default init), and the fixture carries a
+float64 checksum of every parameter so a mismatch is detected rather than silently compared.
+"""
+import io
+import os
+import sys
+import types
+import warnings
+from contextlib import redirect_stdout
+from unittest.mock import MagicMock
+
+import numpy as np
+import torch
+from torch import nn
+from torch.nn.utils import weight_norm
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference"
+
+
+def import_reference():
+    warnings.filterwarnings("ignore")
+    sys.path.insert(0, REF)
+    dac = types.ModuleType("dac")
+    dac_nn = types.ModuleType("dac.nn")
+    layers = types.ModuleType("dac.nn.layers")
+    layers.WNConv1d = lambda *a, **k: weight_norm(nn.Conv1d(*a, **k))
+    layers.WNConvTranspose1d = lambda *a, **k: weight_norm(nn.ConvTranspose1d(*a, **k))
+    layers.Snake1d = MagicMock()
+    sys.modules.update({"dac": dac, "dac.nn": dac_nn, "dac.nn.layers": layers})
+    for m in ["dac.nn.quantize", "dac.model", "dac.model.dac", "dac.model.discriminator", "alias_free_torch",
+              "vector_quantize_pytorch", "k_diffusion", "x_transformers", "einops_exts", "audiotools",
+              "encodec", "pywt"]:
+        sys.modules[m] = MagicMock()
+    from stable_audio_tools.models import autoencoders, bottleneck
+    return autoencoders, bottleneck
+
+
+def ae_config(channels, c_mults, strides, enc_latent, dec_latent, io_channels, sample_rate):
+    ratio = int(np.prod(strides))
+    return {
+        "model_type": "autoencoder",
+        "sample_rate": sample_rate,
+        "model": {
+            "encoder": {"type": "oobleck", "config": {"in_channels": io_channels, "channels": channels,
+                                                      "c_mults": list(c_mults), "strides": list(strides),
+                                                      "latent_dim": enc_latent, "use_snake": True}},
+            "decoder": {"type": "oobleck", "config": {"out_channels": io_channels, "channels": channels,
+                                                      "c_mults": list(c_mults), "strides": list(strides),
+                                                      "latent_dim": dec_latent, "use_snake": True,
+                                                      "final_tanh": False}},
+            "bottleneck": {"type": "vae"},
+            "latent_dim": dec_latent,
+            "downsampling_ratio": ratio,
+            "io_channels": io_channels,
+        },
+    }
+
+
+CONFIGS = {
+    "tiny": ae_config(8, [1, 2, 4], [2, 4, 5], 8, 4, 2, 16000),
+    # encode_audio(chunked=True) pastes encoder output into a [B, latent_dim, T] buffer, so it only
+    # runs when the encoder emits latent_dim channels (autoencoders.py:471,496)
+    "tiny_sym": ae_config(8, [1, 2, 4], [2, 4, 5], 4, 4, 2, 16000),
+    "mid": ae_config(64, [1, 2, 4], [2, 4, 5], 128, 64, 2, 16000),
+    "sao": ae_config(128, [1, 2, 4, 8, 16], [2, 4, 4, 8, 8], 128, 64, 2, 44100),
+    "o12_d512": ae_config(128, [1, 2, 4, 8, 16], [2, 4, 4, 5, 8], 1024, 512, 1, 16000),
+}
+
+
+def checksums(sd):
+    return {k: float(v.double().abs().sum()) for k, v in sd.items()}
+
+
+def randomize_snake(model, seed):
+    """alpha/beta are zero at init (exp -> 1); perturb them so the fixture exercises the per-channel
+    parameters.  Deterministic given the seed; the product tests apply the same perturbation."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if name.endswith(".alpha") or name.endswith(".beta"):
+                p.copy_(0.3 * torch.randn(p.shape, generator=g))
+
+
+def build(ae_mod, name, seed=0, snake_seed=None):
+    torch.manual_seed(seed)
+    m = ae_mod.create_autoencoder_from_config(CONFIGS[name]).eval()
+    if snake_seed is not None:
+        randomize_snake(m, snake_seed)
+    return m
+
+
+def main():
+    ae_mod, bn_mod = import_reference()
+    torch.set_grad_enabled(False)
+
+    # ---- tiny: self-contained
+    m = build(ae_mod, "tiny", 0, snake_seed=7)
+    z = torch.randn(2, 4, 13, generator=torch.Generator().manual_seed(1))
+    x = 0.1 * torch.randn(2, 2, 40 * 9, generator=torch.Generator().manual_seed(2))
+    out = {"z": z, "x": x, "dec_out": m.decode(z), "enc_out": m.encode(x)}
+    # per-layer activations of the decoder (layer-level parity)
+    h = z
+    for i, layer in enumerate(m.decoder.layers):
+        h = layer(h)
+        out[f"dec_layer{i}"] = h
+    for k, v in m.state_dict().items():
+        out["sd." + k] = v
+    np.savez_compressed(os.path.join(HERE, "tiny_ae.npz"), **{k: v.numpy() for k, v in out.items()})
+
+    # ---- chunked on the tiny model
+    zc = torch.randn(1, 4, 300, generator=torch.Generator().manual_seed(11))
+    xc = 0.1 * torch.randn(1, 2, 40 * 300, generator=torch.Generator().manual_seed(12))
+    ms = build(ae_mod, "tiny_sym", 5, snake_seed=9)
+    ch = {"z": zc, "x": xc,
+          "dec_chunked": m.decode_audio(zc, chunked=True, overlap=32, chunk_size=128),
+          "dec_full": m.decode_audio(zc, chunked=False),
+          "dec_chunked_64_16": m.decode_audio(zc, chunked=True, overlap=16, chunk_size=64),
+          "enc_chunked": ms.encode_audio(xc, chunked=True, overlap=32, chunk_size=128),
+          "enc_full": ms.encode_audio(xc, chunked=False)}
+    for k, v in ms.state_dict().items():
+        ch["sym_sd." + k] = v
+    np.savez_compressed(os.path.join(HERE, "chunked.npz"), **{k: v.numpy() for k, v in ch.items()})
+
+    # ---- mid
+    m = build(ae_mod, "mid", 0, snake_seed=7)
+    z = torch.randn(2, 64, 24, generator=torch.Generator().manual_seed(1))
+    x = 0.1 * torch.randn(2, 2, 40 * 24, generator=torch.Generator().manual_seed(2))
+    out = {"z": z, "x": x, "dec_out": m.decode(z), "enc_out": m.encode(x)}
+    cs = checksums(m.state_dict())
+    out["cs_keys"] = np.array(list(cs.keys()))
+    out["cs_vals"] = np.array(list(cs.values()), dtype=np.float64)
+    np.savez_compressed(os.path.join(HERE, "mid_ae.npz"),
+                        **{k: (v.numpy() if torch.is_tensor(v) else v) for k, v in out.items()})
+
+    # ---- SAO full size (BASELINE config 1 input shape)
+    m = build(ae_mod, "sao", 0)
+    z = torch.randn(1, 64, 216, generator=torch.Generator().manual_seed(1))
+    y = m.decode(z)
+    x = 0.1 * torch.randn(1, 2, 442368, generator=torch.Generator().manual_seed(2))
+    e = m.encode(x)
+    idx = torch.cat([torch.arange(0, 4096), torch.arange(221184 - 2048, 221184 + 2048),
+                     torch.arange(442368 - 4096, 442368), torch.arange(0, 442368, 97)]).unique()
+    cs = checksums(m.state_dict())
+    np.savez_compressed(os.path.join(HERE, "sao_full.npz"), dec_idx=idx.numpy(), dec_out_at_idx=y[:, :, idx].numpy(),
+                        dec_abs_max=float(y.abs().max()), dec_sum=float(y.double().sum()),
+                        dec_sq_sum=float((y.double() ** 2).sum()), enc_out=e.numpy(),
+                        cs_keys=np.array(list(cs.keys())), cs_vals=np.array(list(cs.values()), dtype=np.float64))
+
+    # ---- O12 latent 512
+    m = build(ae_mod, "o12_d512", 0)
+    z = torch.randn(1, 512, 16, generator=torch.Generator().manual_seed(1))
+    y = m.decode(z)
+    x = 0.1 * torch.randn(1, 1, 1280 * 16, generator=torch.Generator().manual_seed(2))
+    e = m.encode(x)
+    cs = checksums(m.state_dict())
+    np.savez_compressed(os.path.join(HERE, "o12_d512.npz"), dec_out=y.numpy(), enc_out=e.numpy(),
+                        cs_keys=np.array(list(cs.keys())), cs_vals=np.array(list(cs.values()), dtype=np.float64))
+
+    # ---- sampling
+    sys.path.insert(0, REF)
+    mean = torch.randn(3, 64, 50, generator=torch.Generator().manual_seed(21))
+    scale = torch.randn(3, 64, 50, generator=torch.Generator().manual_seed(22))
+    torch.manual_seed(3)
+    noise = torch.randn_like(mean)
+    torch.manual_seed(3)
+    with redirect_stdout(io.StringIO()):
+        lat, kl = bn_mod.vae_sample(mean, scale)
+    # model_sigmaVAE.py imports transformers' Llama at module import; the free function sample() at
+    # :187-213 is self-contained, so execute just that function's source.
+    src = open(os.path.join(REF, "model_sigmaVAE.py")).read()
+    start = src.index("\ndef sample(mean, dist_type='fix'):")
+    ns = {"torch": torch}
+    exec(src[start:], ns)
+    sample = ns["sample"]
+    torch.manual_seed(3)
+    fix = sample(mean, "fix")
+    torch.manual_seed(3)
+    std_noise = torch.randn(3)
+    noise_g = torch.randn_like(mean)
+    torch.manual_seed(3)
+    gau = sample(mean, "gaussian")
+    mean_bf = mean.bfloat16()
+    torch.manual_seed(3)
+    noise_bf = torch.randn_like(mean_bf)
+    torch.manual_seed(3)
+    fix_bf = sample(mean_bf, "fix")
+    np.savez_compressed(os.path.join(HERE, "sampling.npz"), mean=mean.numpy(), scale=scale.numpy(),
+                        noise=noise.numpy(), vae_latents=lat.numpy(), vae_kl=float(kl), fix=fix.numpy(),
+                        std_noise=std_noise.numpy(), noise_g=noise_g.numpy(), gaussian=gau.numpy(),
+                        noise_bf=noise_bf.float().numpy(), fix_bf=fix_bf.float().numpy(),
+                        none=sample(mean, "other").numpy())
+    print("golden fixtures written to", HERE)
+    for f in sorted(os.listdir(HERE)):
+        if f.endswith(".npz"):
+            print(f"  {f}: {os.path.getsize(os.path.join(HERE, f)) / 1024:.1f} KiB")
+
+
+if __name__ == "__main__":
+    main()
