@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the sigmaVAE / Oobleck hot path on N B200s of one node.
+
+    python bench.py --gpus 1 --steps K --warmup W                      (this repo's CUDA path)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                               (the reference's CPU arithmetic, host cores)
+
+Workload (BASELINE.json configs[1]): SAO-shape autoencoder (channels 128, c_mults 1/2/4/8/16, strides
+2/4/4/8/8, 44.1 kHz stereo, random init, synthetic audio), one step = encode -> split mean/scale ->
+sample('fix') -> decode of 16 clips x 10.03 s per GPU in bf16 mode.  Batch items are independent, so N GPUs
+run N independent shards with no data-path collective (weak scaling: 16 clips per GPU).
+
+The JSON line:
+  value        audio-seconds round-tripped per second, whole job, inputs resident in HBM
+  e2e          same through the public module API with pinned HOST buffers: H2D of the audio and D2H of the
+               decoded waveform inside the timed region
+  decode_only  decode leg alone (the metric's name), same batch
+  roofline     tensor-core roofline of the dominant kernel (conv_umma_kernel): algorithmic FLOPs of its
+               launches / their CUDA-event time, against MEASURED_PEAKS.json (sustained figure: the kernel is
+               timed inside a long step)
+  cpu_baseline oracle port of the reference arithmetic on the host cores, bounded sample (rank 0, N=1 only)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+SAO = dict(channels=128, c_mults=[1, 2, 4, 8, 16], strides=[2, 4, 4, 8, 8], enc_latent=128, dec_latent=64,
+           io_channels=2, sample_rate=44100)
+CLIP_FRAMES = 216                     # 216 latent frames = 442368 samples = 10.031 s
+BATCH_PER_GPU = 16
+METRIC = "vae_decode_audio_sec_per_sec"
+UNIT = "audio-s/s"
+
+
+def sao_config():
+    import helpers as H
+    return H.ae_config(SAO["channels"], SAO["c_mults"], SAO["strides"], SAO["enc_latent"], SAO["dec_latent"],
+                       SAO["io_channels"], SAO["sample_rate"])
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"source": "measured", "hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"])}
+    return {"source": "fallback", "hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2])); power.append(float(r[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_roundtrip_sample(frames):
+    """Oracle port of the reference arithmetic (fp32, torch CPU kernels -- the same library calls the
+    reference's nn.Modules make) on a bounded sample: 1 clip x `frames` latent frames, encode -> sample ->
+    decode.  Returns (audio_seconds, seconds, threads)."""
+    import torch
+    import helpers as H
+    from oracle import oobleck_oracle as O
+    torch.set_grad_enabled(False)
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(0)
+    import kalle_audio_b200 as k
+    m = k.create_autoencoder_from_config(sao_config()).eval()     # parameter container only (CPU, same init)
+    sd = m.state_dict()
+    enc_sd, dec_sd = H.split_sd(sd, "encoder."), H.split_sd(sd, "decoder.")
+    L = frames * 2048
+    x = 0.1 * torch.randn(1, 2, L, generator=torch.Generator().manual_seed(2))
+    noise = torch.randn(1, 64, frames, generator=torch.Generator().manual_seed(3))
+
+    def step():
+        t0 = time.perf_counter()
+        e = O.oobleck_encoder(enc_sd, x, SAO["strides"])
+        mean, _ = e.chunk(2, dim=1)
+        z = O.sigma_sample(mean, noise, "fix")
+        y = O.oobleck_decoder(dec_sd, z, SAO["strides"])
+        assert y.shape == x.shape
+        return time.perf_counter() - t0
+
+    return L / SAO["sample_rate"], step, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    frames = 54
+    audio_s, step, threads = cpu_roundtrip_sample(frames)
+    for _ in range(args.warmup):
+        step()
+    times = [step() for _ in range(args.steps)]
+    total = sum(times)
+    value = audio_s * args.steps / total
+    sample = f"1 clip x {frames} latent frames ({audio_s:.2f} s audio) round trip per step, fp32, oracle port"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "BASELINE configs[1]: SAO-shape sigmaVAE encode -> sample('fix') -> decode round trip, "
+                        f"{BATCH_PER_GPU} clips x 10.03 s per GPU, bf16 tensor-core mode, fp32 I/O",
+            "arch": "oobleck channels=128 c_mults=[1,2,4,8,16] strides=[2,4,4,8,8] latent 128/64 stereo 44.1k",
+            "clips_per_gpu": BATCH_PER_GPU, "clip_seconds": CLIP_FRAMES * 2048 / SAO["sample_rate"],
+            "sharding": f"batch-sharded x{n_gpus}, no collective on the data path",
+            "l2": "per-step working set (>10 GB of activations) is far larger than the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------ CUDA arm
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+    import kalle_audio_b200 as k
+    from kalle_audio_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: there is no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.set_grad_enabled(False)
+
+    torch.manual_seed(0)
+    ae = k.create_autoencoder_from_config(sao_config()).eval().to(dev).set_precision("bf16")
+    B, L = BATCH_PER_GPU, CLIP_FRAMES * 2048
+    gen = torch.Generator().manual_seed(2 + rank)
+    x_host = (0.1 * torch.randn(B, 2, L, generator=gen)).pin_memory()
+    y_host = torch.empty(B, 2, L).pin_memory()
+    x_dev = x_host.to(dev)
+    audio_s_per_step = B * L / SAO["sample_rate"]
+
+    def roundtrip(x):
+        e = ae.encode(x)
+        mean, _scale = e.chunk(2, dim=1)
+        z = k.sample(mean.contiguous(), "fix")
+        return ae.decode(z), z
+
+    def step_resident():
+        y, _ = roundtrip(x_dev)
+        return y
+
+    def step_e2e():
+        x = x_host.to(dev, non_blocking=True)
+        y, _ = roundtrip(x)
+        y_host.copy_(y, non_blocking=True)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps, sampler=None):
+        barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), clocks
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    # roofline leg: per-step CUDA events inside the library, on the launching stream
+    enc_r, dec_r = ae.encoder.runner(dev), ae.decoder.runner(dev)
+    enc_r.set_profiling(True); dec_r.set_profiling(True)
+    _lib.lib().kvae_launch_count(1)
+    sampler = ClockSampler(local)
+    total_ms, clocks = timed(step_resident, args.steps, sampler)
+    launches = int(_lib.lib().kvae_launch_count(0))
+    prof = enc_r.step_profile() + dec_r.step_profile()          # last step of the timed region
+    enc_r.set_profiling(False); dec_r.set_profiling(False)
+
+    _, z_dev = roundtrip(x_dev)
+    for _ in range(2):
+        ae.decode(z_dev)
+    dec_ms, _ = timed(lambda: ae.decode(z_dev), args.steps)
+    for _ in range(2):
+        step_e2e()
+    e2e_ms, _ = timed(step_e2e, args.steps)
+
+    if rank == 0:
+        peaks = measured_peaks()
+        tc = [(ms, fl) for ms, fl, on_tc in prof if on_tc]
+        tc_ms, tc_fl = sum(m for m, _ in tc), sum(f for _, f in tc)
+        other_ms = sum(ms for ms, _, on_tc in prof if not on_tc)
+        achieved = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+        step_fl = enc_r.flops(B, L) + dec_r.flops(B, CLIP_FRAMES)
+        ms_per_step = total_ms / args.steps
+        value = world * audio_s_per_step * args.steps / (total_ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(world),
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": world * audio_s_per_step * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4},
+            "decode_only": {"value": world * audio_s_per_step * args.steps / (dec_ms * 1e-3), "unit": UNIT,
+                            "ms_per_step": dec_ms / args.steps,
+                            "tflops": dec_r.flops(B, CLIP_FRAMES) / (dec_ms / args.steps * 1e-3) / 1e12},
+            "roofline": {"bound": "tensor", "kernel": "conv_umma_kernel", "achieved": achieved,
+                         "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
+                         "peak_source": peaks["source"] + " (sustained; burst %.1f)" % peaks["bf16_tflops"],
+                         "launches_per_step": len(tc), "kernel_ms_per_step": tc_ms,
+                         "other_kernels_ms_per_step": other_ms,
+                         "whole_step_tflops": step_fl / (ms_per_step * 1e-3) / 1e12,
+                         "whole_step_frac": step_fl / (ms_per_step * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            frames = 54
+            audio_s, step, threads = cpu_roundtrip_sample(frames)
+            step()
+            t = min(step() for _ in range(2))
+            line["cpu_baseline"] = {"value": audio_s / t, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": f"1 clip x {frames} latent frames ({audio_s:.2f} s audio) round trip, "
+                                              "fp32 oracle port, warm-up 1 + best of 2"}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["cuda", "reference"], default="cuda")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

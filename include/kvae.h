@@ -1,0 +1,128 @@
+/* kvae.h -- C ABI of libkvae.so, the B200 (sm_100a) implementation of kalle-audio's
+ * sigmaVAE / Oobleck autoencoder hot path.
+ *
+ * The reference (18281818221/kalle-audio) is pure Python and has no FFI of its own; its boundary for
+ * this path is the nn.Module surface of stable_audio_tools/models/autoencoders.py.  Each entry point
+ * below names the reference interface it stands in for; kalle_audio_b200/ (Python, ctypes) mirrors the
+ * module surface on top of these calls.  INTEGRATION.md shows the binding a maintainer would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch); the library owns only opaque
+ *     plan handles (packed weights, per-shape launch descriptors);
+ *   - tensors cross the boundary in the reference's layout: [B, C, T], T contiguous; `dtype` is
+ *     KVAE_F32 or KVAE_BF16;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy stream);
+ *   - return 0 on success, negative on error; kvae_last_error() returns the message for this thread;
+ *   - a plan is not thread-safe: one plan per module instance per device (the reference's callers are
+ *     single-threaded).
+ *   - there is no CPU path: with no sm_100 device every compute entry point fails with an error.
+ */
+#ifndef KVAE_H_
+#define KVAE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KVAE_F32 0
+#define KVAE_BF16 1
+
+#define KVAE_ENCODER 0
+#define KVAE_DECODER 1
+
+/* precision of the convolution arithmetic inside a plan */
+#define KVAE_PREC_BF16 0 /* bf16 tensor-core operands, fp32 accumulation, fp32 residual stream  (<= 1e-3) */
+#define KVAE_PREC_F32 1  /* fp32 CUDA-core arithmetic throughout                                 (<= 1e-5) */
+
+#define KVAE_MAX_STAGES 8
+
+/* Architecture of one OobleckEncoder / OobleckDecoder: the constructor arguments of
+ * autoencoders.py:117-125 (encoder) and :151-160 (decoder).  use_snake must be true and
+ * antialias_activation / use_nearest_upsample false (the only combination the reference's configs
+ * use); the Python layer raises NotImplementedError for the others. */
+typedef struct kvae_arch {
+  int io_channels;                /* in_channels (encoder) / out_channels (decoder)            */
+  int channels;                   /* base width, 128                                           */
+  int latent_dim;                 /* encoder: channels emitted; decoder: channels consumed     */
+  int n_stages;                   /* len(c_mults) == len(strides)                              */
+  int c_mults[KVAE_MAX_STAGES];   /* as passed to the constructor (without the implicit 1)     */
+  int strides[KVAE_MAX_STAGES];
+  int final_tanh;                 /* decoder only                                              */
+} kvae_arch;
+
+typedef struct kvae_plan kvae_plan;
+
+int kvae_version(void);
+const char* kvae_last_error(void);
+/* number of CUDA devices with compute capability 10.x visible to the library (0 => no compute). */
+int kvae_device_count(void);
+/* kernels launched by this thread through the library since the last reset (bench.py's gpu_launches). */
+long long kvae_launch_count(int reset);
+
+/* ---- plans: replace OobleckEncoder.__init__/forward (:116-147) and OobleckDecoder (:150-191) ---- */
+int kvae_plan_create(const kvae_arch* arch, int direction, int precision, int device, kvae_plan** out);
+void kvae_plan_destroy(kvae_plan* plan);
+/* Layers are indexed in the reference's module (= state_dict) order. */
+int kvae_plan_num_convs(const kvae_plan* plan);
+int kvae_plan_num_snakes(const kvae_plan* plan);
+/* shape of conv `idx`: kind (0 Conv1d / 1 ConvTranspose1d), Cin, Cout, K, stride, dilation, padding, has_bias */
+int kvae_plan_conv_info(const kvae_plan* plan, int idx, int info[8]);
+int kvae_plan_snake_channels(const kvae_plan* plan, int idx);
+/* Folded (weight-norm removed) fp32 weight in torch layout -- Conv1d [Cout,Cin,K], ConvTranspose1d
+ * [Cin,Cout,K] -- and optional bias [Cout].  Replaces the per-forward torch._weight_norm hook of
+ * dac.nn.layers.WNConv1d / WNConvTranspose1d (call sites autoencoders.py:49,52,76,98,133,141,168,184):
+ * the fold happens once at load time and the library re-packs for its kernels. */
+int kvae_plan_set_conv(kvae_plan* plan, int idx, const float* w_folded, const float* bias, void* stream);
+/* SnakeBeta parameters (blocks.py:313-329): alpha, beta [C] fp32; logscale as in the module. */
+int kvae_plan_set_snake(kvae_plan* plan, int idx, const float* alpha, const float* beta, int logscale,
+                        void* stream);
+
+/* Scratch the caller must provide for a (B, T) problem; T is the INPUT length (latent frames for a
+ * decoder, audio samples for an encoder). */
+size_t kvae_workspace_bytes(kvae_plan* plan, int B, long long T);
+/* OobleckDecoder.forward (:190): z [B, latent_dim, T] -> wav [B, io_channels, T*prod(strides)]. */
+int kvae_decode(kvae_plan* plan, const void* z, int z_dtype, void* wav, int wav_dtype, int B, long long T,
+                void* workspace, size_t workspace_bytes, void* stream);
+/* OobleckEncoder.forward (:146): wav [B, io_channels, L] -> lat [B, latent_dim, L/prod(strides)]. */
+int kvae_encode(kvae_plan* plan, const void* wav, int wav_dtype, void* lat, int lat_dtype, int B, long long L,
+                void* workspace, size_t workspace_bytes, void* stream);
+/* algorithmic FLOPs of one pass (2*MACs of every conv, all taps counted) */
+double kvae_plan_flops(const kvae_plan* plan, int B, long long T);
+
+/* Per-step device timing for the roofline report: after kvae_plan_profile(plan, 1) every run records a CUDA
+ * event between steps on the launching stream; kvae_plan_step_profile waits for the last recorded run and
+ * returns, per convolution step, its duration (ms), algorithmic FLOPs and whether it ran on tcgen05.
+ * Returns the number of steps (> 0) or a negative error. */
+int kvae_plan_profile(kvae_plan* plan, int enable);
+int kvae_plan_step_profile(kvae_plan* plan, float* ms, double* flops, int* tensor_core, int max_steps);
+
+/* ---- layer-level entry points (module-level drop-ins and tests) ---- */
+/* SnakeBeta.forward (blocks.py:331-339) on [B, C, T]. */
+int kvae_snake_fwd(const void* x, void* y, const float* alpha, const float* beta, int logscale, int B, int C,
+                   long long T, int dtype, void* stream);
+/* torch.nn.utils.weight_norm fold, dim=0: w[i,:] = v[i,:] * g[i] / ||v[i,:]||  (fp32). */
+int kvae_weight_norm_fold(const float* v, const float* g, float* w, int dim0, int inner, void* stream);
+/* WNConv1d.forward / WNConvTranspose1d.forward on [B, Cin, T] with a folded fp32 weight in torch
+ * layout; fp32 arithmetic; x and y of `dtype`.  transposed = 1 selects ConvTranspose1d. */
+int kvae_conv1d_fwd(const void* x, void* y, const float* w_folded, const float* bias, int transposed, int B,
+                    int Cin, int Cout, long long T, int K, int stride, int dilation, int padding, int dtype,
+                    void* scratch, size_t scratch_bytes, void* stream);
+size_t kvae_conv1d_scratch_bytes(int Cin, int Cout, int K);
+
+/* ---- latent sampling ---- */
+/* sample(mean,'fix') of model_sigmaVAE.py:153-178 / 187-213: out = mean + std*noise, rounded exactly as
+ * torch does (mul, then add).  std_noise != NULL selects 'gaussian': per-item std_b = std_noise[b]*value. */
+int kvae_sigma_sample(const void* mean, const void* noise, void* out, size_t n, int dtype, float std,
+                      const void* std_noise, float value, size_t per_batch, void* stream);
+/* vae_sample of bottleneck.py:51-62 (as edited in the reference): out = noise*scale + mean; *kl (device
+ * fp32 scalar) = (mean^2 + var - log var - 1).sum(1).mean().  scratch: >= 8*1024 bytes. */
+int kvae_vae_sample(const void* mean, const void* scale, const void* noise, void* out, float* kl, int B, int D,
+                    long long T, int dtype, void* scratch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KVAE_H_ */

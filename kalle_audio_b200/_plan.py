@@ -1,0 +1,154 @@
+"""Host side of a fused encoder / decoder plan: creates the libkvae plan for an Oobleck module,
+keeps its packed weights in sync with the module's parameters, owns the workspace and issues
+``kvae_encode`` / ``kvae_decode`` on the caller's current CUDA stream."""
+from __future__ import annotations
+
+import ctypes as C
+import weakref
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import _lib
+from .layers import SnakeBeta, _WNConvBase
+
+
+class PlanRunner:
+    def __init__(self, module: torch.nn.Module, direction: int, arch: _lib.KvaeArch, precision: int,
+                 device: torch.device):
+        self.module_ref = weakref.ref(module)
+        self.direction = direction
+        self.precision = precision
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.KvaeError("plans exist on CUDA devices only (no CPU path)")
+        self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        L = _lib.lib()
+        handle = C.c_void_p()
+        _lib.check(L.kvae_plan_create(C.byref(arch), direction, precision, self.index, C.byref(handle)))
+        self.handle = handle
+        self._finalizer = weakref.finalize(self, L.kvae_plan_destroy, handle)
+        self.convs: List[_WNConvBase] = [m for m in module.modules() if isinstance(m, _WNConvBase)]
+        self.snakes: List[SnakeBeta] = [m for m in module.modules() if isinstance(m, SnakeBeta)]
+        if len(self.convs) != L.kvae_plan_num_convs(handle) or len(self.snakes) != L.kvae_plan_num_snakes(handle):
+            raise _lib.KvaeError("module tree does not match the plan built from its constructor arguments")
+        info = (C.c_int * 8)()
+        for i, m in enumerate(self.convs):
+            _lib.check(L.kvae_plan_conv_info(handle, i, C.byref(info)))
+            want = (int(m.transposed), m.in_channels, m.out_channels, m.kernel_size[0], m.stride[0], m.dilation[0],
+                    m.padding[0], int(m.bias is not None))
+            if tuple(info) != want:
+                raise _lib.KvaeError(f"conv {i}: module {want} does not match plan {tuple(info)}")
+        for i, m in enumerate(self.snakes):
+            if L.kvae_plan_snake_channels(handle, i) != m.in_features:
+                raise _lib.KvaeError(f"SnakeBeta {i}: channel count mismatch")
+        self._fingerprint: Optional[Tuple] = None
+        self._workspace: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------ weights
+    def _params(self):
+        for m in self.convs:
+            yield from m.parameters(recurse=False)
+        for m in self.snakes:
+            yield m.alpha
+            yield m.beta
+
+    def sync_weights(self) -> None:
+        """Re-folds weight norm (fp32) and re-packs when any parameter changed (in-place update, load_state_dict,
+        .to()).  Load-time cost only; the steady state is a tuple comparison."""
+        fp = tuple((p.data_ptr(), p._version) for p in self._params())
+        if fp == self._fingerprint:
+            return
+        L = _lib.lib()
+        st = _lib.stream_ptr(self.device)
+        for i, m in enumerate(self.convs):
+            if next(m.parameters(recurse=False)).device != self.device:
+                raise _lib.KvaeError("module parameters moved to another device; plan is stale")
+            w = m.folded_weight()
+            b = None if m.bias is None else m.bias.detach().float().contiguous()
+            _lib.check(L.kvae_plan_set_conv(self.handle, i, w.data_ptr(), _lib.ptr(b), st))
+        for i, m in enumerate(self.snakes):
+            a = m.alpha.detach().float().contiguous()
+            b = m.beta.detach().float().contiguous()
+            _lib.check(L.kvae_plan_set_snake(self.handle, i, a.data_ptr(), b.data_ptr(), int(m.alpha_logscale), st))
+        self._fingerprint = fp
+
+    # ------------------------------------------------------------------ run
+    def _get_workspace(self, B: int, T: int) -> torch.Tensor:
+        need = _lib.lib().kvae_workspace_bytes(self.handle, B, T)
+        if need == 0:
+            raise _lib.KvaeError(_lib.lib().kvae_last_error().decode())
+        if self._workspace is None or self._workspace.numel() < need:
+            self._workspace = None  # release before growing
+            self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    def out_length(self, T: int, ratio: int) -> int:
+        return T * ratio if self.direction == _lib.KVAE_DECODER else T // ratio
+
+    def run(self, x: torch.Tensor, out_channels: int, ratio: int, out_dtype: torch.dtype) -> torch.Tensor:
+        _lib.require_cuda(x, "fused plan")
+        if x.device != self.device:
+            raise _lib.KvaeError(f"input on {x.device}, plan on {self.device}")
+        if x.dim() != 3:
+            raise ValueError("expected [B, C, T]")
+        B, _, T = x.shape
+        if B == 0 or T == 0:
+            raise ValueError("empty input")
+        self.sync_weights()
+        xin = x if x.dtype in (torch.float32, torch.bfloat16) else x.float()
+        xin = xin.contiguous()
+        kdtype = out_dtype if out_dtype in (torch.float32, torch.bfloat16) else torch.float32
+        if self.direction == _lib.KVAE_ENCODER and T % ratio:
+            raise ValueError(f"audio length {T} is not a multiple of the downsampling ratio {ratio} "
+                             "(use preprocess_audio_for_encoder)")
+        out = torch.empty((B, out_channels, self.out_length(T, ratio)), dtype=kdtype, device=self.device)
+        ws = self._get_workspace(B, T)
+        L = _lib.lib()
+        fn = L.kvae_decode if self.direction == _lib.KVAE_DECODER else L.kvae_encode
+        _lib.check(fn(self.handle, xin.data_ptr(), _lib.dtype_code(xin.dtype), out.data_ptr(), _lib.dtype_code(kdtype),
+                      B, T, ws.data_ptr(), ws.numel(), _lib.stream_ptr(self.device)))
+        return out if out.dtype == out_dtype else out.to(out_dtype)
+
+    def set_profiling(self, enable: bool) -> None:
+        _lib.check(_lib.lib().kvae_plan_profile(self.handle, int(enable)))
+
+    def step_profile(self):
+        """[(ms, flops, on_tensor_cores)] per convolution step of the last profiled run (synchronises)."""
+        n = 256
+        ms, fl, tc = (C.c_float * n)(), (C.c_double * n)(), (C.c_int * n)()
+        got = _lib.lib().kvae_plan_step_profile(self.handle, ms, fl, tc, n)
+        if got < 0:
+            raise _lib.KvaeError(_lib.lib().kvae_last_error().decode())
+        return [(float(ms[i]), float(fl[i]), bool(tc[i])) for i in range(got)]
+
+    def flops(self, B: int, T: int) -> float:
+        return float(_lib.lib().kvae_plan_flops(self.handle, B, T))
+
+
+class PlanCache:
+    """Per-module cache of runners keyed by (device, precision)."""
+
+    def __init__(self):
+        self.runners: Dict[Tuple[str, int], PlanRunner] = {}
+
+    def get(self, module, direction, arch, precision, device) -> PlanRunner:
+        key = (str(device), precision)
+        r = self.runners.get(key)
+        if r is None:
+            r = PlanRunner(module, direction, arch, precision, device)
+            self.runners[key] = r
+        return r
+
+    def clear(self):
+        self.runners.clear()
+
+    # plans hold device handles: a copied / pickled module starts with an empty cache and rebuilds lazily
+    def __deepcopy__(self, memo):
+        return PlanCache()
+
+    def __getstate__(self):
+        return {}
+
+    def __setstate__(self, state):
+        self.runners = {}

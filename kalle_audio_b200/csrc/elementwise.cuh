@@ -1,0 +1,172 @@
+// HBM-bound helper kernels: SnakeBeta on the API layout, layout changes at the model boundary,
+// weight-norm folding and weight packing at load time, and the latent sampling steps.
+#pragma once
+#include <cuda_bf16.h>
+#include <cstdint>
+
+#include "conv_umma.cuh"  // snake_beta
+
+namespace kvae {
+
+__device__ __forceinline__ float ld_elem(const void* p, size_t i, int f32) {
+  return f32 ? static_cast<const float*>(p)[i] : __bfloat162float(static_cast<const __nv_bfloat16*>(p)[i]);
+}
+__device__ __forceinline__ void st_elem(void* p, size_t i, int f32, float v) {
+  if (f32) static_cast<float*>(p)[i] = v;
+  else static_cast<__nv_bfloat16*>(p)[i] = __float2bfloat16(v);
+}
+
+// ---------------------------------------------------------------- SnakeBeta, [B, C, T] layout
+// reference blocks.py:301-339: alpha' = exp(alpha), beta' = exp(beta) when logscale;
+// y = x + 1/(beta' + 1e-9) * sin(x*alpha')^2.   grid: (ceil(T/ (256*4)), B*C)
+__global__ void snake_cf_kernel(const void* x, void* y, const float* alpha, const float* beta,
+                                int logscale, int C, long long T, int f32) {
+  const int c = blockIdx.y % C;
+  float a = alpha[c], bt = beta[c];
+  if (logscale) { a = expf(a); bt = expf(bt); }
+  const float inv_b = 1.0f / (bt + 1e-9f);
+  const size_t row = static_cast<size_t>(blockIdx.y) * T;
+  const long long t0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long t = t0 + i;
+    if (t < T) {
+      const float v = ld_elem(x, row + t, f32);
+      const float s = sinf(v * a);
+      st_elem(y, row + t, f32, v + inv_b * (s * s));
+    }
+  }
+}
+
+// a = exp(alpha) (or alpha), inv_b = 1/(exp(beta)+1e-9): per-channel constants used by the fused
+// prologues/epilogues.
+__global__ void snake_params_kernel(const float* alpha, const float* beta, int logscale, int C, float* a,
+                                    float* inv_b) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) {
+    float av = alpha[c], bv = beta[c];
+    if (logscale) { av = expf(av); bv = expf(bv); }
+    a[c] = av;
+    inv_b[c] = 1.0f / (bv + 1e-9f);
+  }
+}
+
+// ---------------------------------------------------------------- [B, C, T] -> [B, T, C] bf16
+// 32x32 shared-memory tile transpose.  grid: (ceil(T/32), ceil(C/32), B), block (32, 8)
+__global__ void cf_to_cl_bf16_kernel(const void* x, int f32, __nv_bfloat16* y, int C, int T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t < T) ? ld_elem(x, (static_cast<size_t>(b) * C + c) * T + t, f32) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (c < C && t < T) y[(static_cast<size_t>(b) * T + t) * C + c] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+
+// ---------------------------------------------------------------- weight norm fold
+// w[i, :] = v[i, :] * (g[i] / ||v[i, :]||_2)   (old-style torch weight_norm, dim=0).  One block per i.
+__global__ void weight_norm_fold_kernel(const float* v, const float* g, float* w, int inner) {
+  __shared__ float red[32];
+  const size_t base = static_cast<size_t>(blockIdx.x) * inner;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) { const float x = v[base + i]; s = fmaf(x, x, s); }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) red[0] = t;
+  }
+  __syncthreads();
+  const float scale = g[blockIdx.x] / sqrtf(red[0]);
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) w[base + i] = v[base + i] * scale;
+}
+
+// ---------------------------------------------------------------- weight packing
+// torch Conv1d weight [Cout][Cin][K] (transposed=0) or ConvTranspose1d weight [Cin][Cout][K]
+// (transposed=1) -> tensor-core operand [K][Cout][Cin] bf16 and CUDA-core operand [K][Cin][Cout] fp32.
+__global__ void pack_weights_kernel(const float* w, int transposed, int Cout, int Cin, int K,
+                                    __nv_bfloat16* w_umma, float* w_direct) {
+  const size_t n = static_cast<size_t>(Cout) * Cin * K;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % K);
+    const size_t r = i / K;
+    int co, ci;
+    if (transposed) { co = static_cast<int>(r % Cout); ci = static_cast<int>(r / Cout); }
+    else { ci = static_cast<int>(r % Cin); co = static_cast<int>(r / Cin); }
+    const float v = w[i];
+    if (w_umma) w_umma[(static_cast<size_t>(k) * Cout + co) * Cin + ci] = __float2bfloat16(v);
+    if (w_direct) w_direct[(static_cast<size_t>(k) * Cin + ci) * Cout + co] = v;
+  }
+}
+
+// ---------------------------------------------------------------- latent sampling
+// sample(mean, 'fix') of model_sigmaVAE.py:153-178,187-213: mean + std * noise, evaluated as torch
+// does -- two separately rounded operations (mul then add), never an FMA -- so the result is
+// bit-identical to the reference given the same noise tensor.  per_batch_std != nullptr is the
+// 'gaussian' branch: std_b = std_noise[b] * (0.5 / 0.8), broadcast over the other dims.
+__global__ void sigma_sample_kernel(const void* mean, const void* noise, void* out, size_t n, int f32, float std,
+                                    const void* std_noise, float value, size_t per_batch) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float s = std;
+    if (std_noise) {
+      s = __fmul_rn(ld_elem(std_noise, i / per_batch, f32), value);
+      if (!f32) s = __bfloat162float(__float2bfloat16(s));
+    }
+    float t = __fmul_rn(s, ld_elem(noise, i, f32));
+    if (!f32) t = __bfloat162float(__float2bfloat16(t));
+    st_elem(out, i, f32, __fadd_rn(ld_elem(mean, i, f32), t));
+  }
+}
+
+// vae_sample of bottleneck.py:51-62 (as edited in the reference): latents = noise*scale + mean with
+// the two roundings of torch; kl = (mean^2 + var - log var - 1).sum(1).mean() with
+// stdev = softplus(scale) + 1e-4.  Per-block partial sums of the KL terms go to kl_partial
+// (deterministic two-pass reduction; kvae_vae_sample finishes it).
+__global__ void vae_sample_kernel(const void* mean, const void* scale, const void* noise, void* out, size_t n,
+                                  int f32, double* kl_partial) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float m = ld_elem(mean, i, f32), sc = ld_elem(scale, i, f32);
+    float t = __fmul_rn(ld_elem(noise, i, f32), sc);
+    if (!f32) t = __bfloat162float(__float2bfloat16(t));
+    st_elem(out, i, f32, __fadd_rn(t, m));
+    const float sp = (sc > 20.f) ? sc : log1pf(expf(sc));
+    const float stdev = sp + 1e-4f;
+    const float var = stdev * stdev;
+    acc += static_cast<double>(m * m + var - logf(var) - 1.f);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) kl_partial[blockIdx.x] = t;
+  }
+}
+__global__ void kl_finish_kernel(const double* partial, int n, double denom, float* kl) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += red[i];
+    *kl = static_cast<float>(t / denom);
+  }
+}
+
+}  // namespace kvae

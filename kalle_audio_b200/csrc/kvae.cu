@@ -1,0 +1,807 @@
+// libkvae.so: plan construction, workspace layout, launch sequencing and the C ABI (include/kvae.h).
+//
+// A plan turns the constructor arguments of OobleckEncoder / OobleckDecoder
+// (stable_audio_tools/models/autoencoders.py:116-191 of the reference) into a linear list of
+// convolution steps.  SnakeBeta never runs as its own kernel inside a plan: it is folded into the
+// epilogue of the producing convolution (which then emits the bf16 tensor-core operand of the next
+// convolution) or into the prologue of a CUDA-core convolution.  Residual adds are folded into the
+// epilogue of the k=1 convolution of each ResidualUnit (:47-62); the residual stream stays fp32.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/kvae.h"
+#include "conv_direct.cuh"
+#include "conv_umma_host.cuh"
+#include "elementwise.cuh"
+
+using namespace kvae;
+
+namespace {
+
+thread_local std::string g_err;
+thread_local long long g_launches = 0;
+
+int fail(const std::string& m) {
+  g_err = m;
+  return -1;
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  g_err = std::string(what) + ": " + cudaGetErrorString(e);
+  return -2;
+}
+#define KV_CUDA(x)                                  \
+  do {                                              \
+    cudaError_t e_ = (x);                           \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #x); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+struct ConvLayer {
+  ConvGeom g;
+  bool has_bias = true;
+  bool umma = false;
+  __nv_bfloat16* w_umma = nullptr;
+  float* w_direct = nullptr;
+  float* bias = nullptr;
+  bool set = false;
+};
+
+struct SnakeLayer {
+  int C = 0;
+  float* a = nullptr;
+  float* inv_b = nullptr;
+  bool set = false;
+};
+
+// one convolution of the chain, with its fused prologue / epilogue
+struct Step {
+  int conv = -1;
+  int pre_snake = -1;      // SnakeBeta applied to this conv's input (module order index) or -1
+  int residual_from = -1;  // step whose output is added in the epilogue (ResidualUnit skip) or -1
+  int len_num = 1, len_den = 1;  // output length = T * len_num / len_den
+  // resolved by finalize():
+  bool needs_raw = false, needs_act = false;
+  int epi_snake = -1;      // SnakeBeta folded into the epilogue for the next (tensor-core) conv
+};
+
+struct Tensor {
+  size_t bytes = 0;
+  int first = 0, last = 0;
+  size_t offset = 0;
+};
+
+struct Layout {
+  // tensors: index 0 = channels-last bf16 copy of the external input (if step 0 is tensor-core),
+  //          1 + 2*k = raw (fp32) output of step k, 2 + 2*k = activated bf16 output of step k
+  std::vector<Tensor> t;
+  size_t total = 0;
+};
+
+struct PreparedRun {
+  std::vector<ConvLaunch> umma;     // per step (valid when that step is tensor-core)
+  std::vector<DirectParams> direct; // per step (valid otherwise)
+  std::vector<dim3> direct_grid;
+  std::vector<int> direct_cfg;      // 0: 32x64 tile, 1: 128x4 tile
+  std::vector<size_t> direct_smem;
+  Layout layout;
+};
+
+}  // namespace
+
+struct kvae_plan {
+  kvae_arch arch;
+  int direction = KVAE_DECODER;
+  int precision = KVAE_PREC_BF16;
+  int device = 0;
+  std::vector<ConvLayer> convs;
+  std::vector<SnakeLayer> snakes;
+  std::vector<Step> steps;
+  int ratio = 1;
+  std::map<std::tuple<int, long long, void*>, std::unique_ptr<PreparedRun>> runs;
+  // optional per-step CUDA-event timing (bench.py's roofline leg)
+  bool profile = false;
+  std::vector<cudaEvent_t> events;
+  int prof_B = 0;
+  long long prof_T = 0;
+  bool prof_valid = false;
+};
+
+namespace {
+
+int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+void add_conv(kvae_plan* p, int kind, int Cin, int Cout, int K, int stride, int dil, int pad, bool bias) {
+  ConvLayer c;
+  c.g = ConvGeom{kind, Cin, Cout, K, stride, dil, pad};
+  c.has_bias = bias;
+  c.umma = (p->precision == KVAE_PREC_BF16) && umma_supported(c.g);
+  p->convs.push_back(c);
+}
+int add_snake(kvae_plan* p, int C) {
+  SnakeLayer s;
+  s.C = C;
+  p->snakes.push_back(s);
+  return static_cast<int>(p->snakes.size()) - 1;
+}
+
+// ResidualUnit (autoencoders.py:39-62): snake -> conv k7 dil d -> snake -> conv k1 -> + x
+void add_residual_unit(kvae_plan* p, int C, int d, int num, int den) {
+  const int input_step = static_cast<int>(p->steps.size()) - 1;
+  const int s0 = add_snake(p, C);
+  add_conv(p, kConv, C, C, 7, 1, d, 3 * d, true);
+  Step a;
+  a.conv = static_cast<int>(p->convs.size()) - 1;
+  a.pre_snake = s0;
+  a.len_num = num; a.len_den = den;
+  p->steps.push_back(a);
+  const int s1 = add_snake(p, C);
+  add_conv(p, kConv, C, C, 1, 1, 1, 0, true);
+  Step b;
+  b.conv = static_cast<int>(p->convs.size()) - 1;
+  b.pre_snake = s1;
+  b.residual_from = input_step;
+  b.len_num = num; b.len_den = den;
+  p->steps.push_back(b);
+}
+
+void build_decoder(kvae_plan* p) {
+  const kvae_arch& a = p->arch;
+  const int n = a.n_stages;
+  std::vector<int> cm(n + 1, 1);
+  for (int i = 0; i < n; ++i) cm[i + 1] = a.c_mults[i];
+  // layers.0: WNConv1d(latent -> c_mults[-1]*channels, k7, pad 3)                         (:168)
+  add_conv(p, kConv, a.latent_dim, cm[n] * a.channels, 7, 1, 1, 3, true);
+  Step s;
+  s.conv = 0;
+  p->steps.push_back(s);
+  int num = 1;
+  for (int i = n; i >= 1; --i) {            // DecoderBlock (:83-114), strides walked in reverse (:171-180)
+    const int cin = cm[i] * a.channels, cout = cm[i - 1] * a.channels, st = a.strides[i - 1];
+    const int sn = add_snake(p, cin);
+    add_conv(p, kConvT, cin, cout, 2 * st + st % 2, st, 1, ceil_div(st, 2), true);
+    num *= st;
+    Step u;
+    u.conv = static_cast<int>(p->convs.size()) - 1;
+    u.pre_snake = sn;
+    u.len_num = num;
+    p->steps.push_back(u);
+    for (int d : {1, 3, 9}) add_residual_unit(p, cout, d, num, 1);
+  }
+  const int sn = add_snake(p, cm[0] * a.channels);
+  add_conv(p, kConv, cm[0] * a.channels, a.io_channels, 7, 1, 1, 3, false);   // bias=False (:184)
+  Step f;
+  f.conv = static_cast<int>(p->convs.size()) - 1;
+  f.pre_snake = sn;
+  f.len_num = num;
+  p->steps.push_back(f);
+  p->ratio = num;
+}
+
+void build_encoder(kvae_plan* p) {
+  const kvae_arch& a = p->arch;
+  const int n = a.n_stages;
+  std::vector<int> cm(n + 1, 1);
+  for (int i = 0; i < n; ++i) cm[i + 1] = a.c_mults[i];
+  add_conv(p, kConv, a.io_channels, cm[0] * a.channels, 7, 1, 1, 3, true);      // (:133)
+  Step s;
+  s.conv = 0;
+  p->steps.push_back(s);
+  int den = 1;
+  for (int i = 0; i < n; ++i) {             // EncoderBlock (:64-81)
+    const int cin = cm[i] * a.channels, cout = cm[i + 1] * a.channels, st = a.strides[i];
+    for (int d : {1, 3, 9}) add_residual_unit(p, cin, d, 1, den);
+    const int sn = add_snake(p, cin);
+    add_conv(p, kConv, cin, cout, 2 * st, st, 1, ceil_div(st, 2), true);
+    den *= st;
+    Step u;
+    u.conv = static_cast<int>(p->convs.size()) - 1;
+    u.pre_snake = sn;
+    u.len_den = den;
+    p->steps.push_back(u);
+  }
+  const int sn = add_snake(p, cm[n] * a.channels);
+  add_conv(p, kConv, cm[n] * a.channels, a.latent_dim, 3, 1, 1, 1, true);        // (:141)
+  Step f;
+  f.conv = static_cast<int>(p->convs.size()) - 1;
+  f.pre_snake = sn;
+  f.len_den = den;
+  p->steps.push_back(f);
+  p->ratio = den;
+}
+
+void finalize_steps(kvae_plan* p) {
+  const int n = static_cast<int>(p->steps.size());
+  for (int k = 0; k < n; ++k) {
+    Step& s = p->steps[k];
+    const bool last = (k == n - 1);
+    const bool next_umma = !last && p->convs[p->steps[k + 1].conv].umma;
+    s.needs_act = next_umma;
+    s.epi_snake = next_umma ? p->steps[k + 1].pre_snake : -1;
+    s.needs_raw = last || (!last && !next_umma);
+    for (int j = k + 1; j < n; ++j)
+      if (p->steps[j].residual_from == k) s.needs_raw = true;
+  }
+}
+
+long long step_len(const Step& s, long long T) { return T * s.len_num / s.len_den; }
+
+size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Interval allocation of the intermediate tensors inside one workspace.
+bool make_layout(const kvae_plan* p, int B, long long T, Layout& L, std::string& err) {
+  const int n = static_cast<int>(p->steps.size());
+  L.t.assign(1 + 2 * n, Tensor());
+  const ConvLayer& c0 = p->convs[p->steps[0].conv];
+  if (c0.umma) {
+    L.t[0].bytes = static_cast<size_t>(B) * T * c0.g.Cin * 2;
+    L.t[0].first = 0;
+    L.t[0].last = 0;
+  }
+  for (int k = 0; k < n; ++k) {
+    const Step& s = p->steps[k];
+    const ConvLayer& c = p->convs[s.conv];
+    const long long len = step_len(s, T);
+    if (len <= 0) { err = "input too short for this architecture"; return false; }
+    int last_use = k;
+    if (k + 1 < n) last_use = k + 1;
+    for (int j = k + 1; j < n; ++j)
+      if (p->steps[j].residual_from == k) last_use = std::max(last_use, j);
+    if (s.needs_raw && k != n - 1) {
+      Tensor& t = L.t[1 + 2 * k];
+      t.bytes = static_cast<size_t>(B) * len * c.g.Cout * 4;
+      t.first = k;
+      t.last = last_use;
+    }
+    if (s.needs_act) {
+      Tensor& t = L.t[2 + 2 * k];
+      t.bytes = static_cast<size_t>(B) * len * c.g.Cout * 2;
+      t.first = k;
+      t.last = k + 1;
+    }
+  }
+  // first-fit over live intervals, in order of first use
+  struct Live { size_t off, size; int last; };
+  std::vector<Live> live;
+  size_t total = 0;
+  auto place = [&](Tensor& t) {
+    if (!t.bytes) return;
+    const size_t sz = align_up(t.bytes, 1024);
+    std::sort(live.begin(), live.end(), [](const Live& a, const Live& b) { return a.off < b.off; });
+    size_t off = 0;
+    for (const Live& l : live) {
+      if (off + sz <= l.off) break;
+      off = std::max(off, l.off + l.size);
+    }
+    t.offset = off;
+    live.push_back({off, sz, t.last});
+    total = std::max(total, off + sz);
+  };
+  place(L.t[0]);
+  for (int k = 0; k < n; ++k) {
+    std::vector<Live> keep;
+    for (const Live& l : live)
+      if (l.last >= k) keep.push_back(l);
+    live.swap(keep);
+    place(L.t[1 + 2 * k]);
+    place(L.t[2 + 2 * k]);
+  }
+  L.total = std::max<size_t>(total, 1024);
+  return true;
+}
+
+bool prepare_run(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R, std::string& err) {
+  const int n = static_cast<int>(p->steps.size());
+  if (!make_layout(p, B, T, R.layout, err)) return false;
+  R.umma.resize(n);
+  R.direct.resize(n);
+  R.direct_grid.resize(n);
+  R.direct_cfg.assign(n, 0);
+  R.direct_smem.assign(n, 0);
+  uint8_t* base = static_cast<uint8_t*>(ws);
+  auto tptr = [&](int id) -> void* { return R.layout.t[id].bytes ? base + R.layout.t[id].offset : nullptr; };
+  for (int k = 0; k < n; ++k) {
+    const Step& s = p->steps[k];
+    const ConvLayer& c = p->convs[s.conv];
+    const long long T_in = (k == 0) ? T : step_len(p->steps[k - 1], T);
+    const long long T_out = step_len(s, T);
+    if (c.g.out_len(static_cast<int>(T_in)) != T_out) {
+      err = "length bookkeeping mismatch at step " + std::to_string(k) + " (input length must be a multiple of the stride product)";
+      return false;
+    }
+    const bool last = (k == n - 1);
+    void* raw = (s.needs_raw && !last) ? tptr(1 + 2 * k) : nullptr;
+    void* act = s.needs_act ? tptr(2 + 2 * k) : nullptr;
+    const void* res = (s.residual_from >= 0) ? tptr(1 + 2 * s.residual_from) : nullptr;
+    if (s.residual_from >= 0 && !res) { err = "internal: residual tensor missing"; return false; }
+    if (c.umma) {
+      const void* in = (k == 0) ? tptr(0) : tptr(2 + 2 * (k - 1));
+      if (!in) { err = "internal: tensor-core operand missing"; return false; }
+      ConvEpilogue ep;
+      ep.bias = c.has_bias ? c.bias : nullptr;
+      ep.residual = res;
+      ep.residual_f32 = 1;
+      ep.out_raw = raw;            // external output patched at call time when last
+      ep.out_raw_f32 = 1;
+      ep.out_raw_cf = last ? 1 : 0;
+      if (last) ep.out_raw = reinterpret_cast<void*>(0x1);  // placeholder, patched per call
+      ep.out_act = static_cast<__nv_bfloat16*>(act);
+      if (s.epi_snake >= 0) {
+        ep.snake_a = p->snakes[s.epi_snake].a;
+        ep.snake_inv_b = p->snakes[s.epi_snake].inv_b;
+      }
+      ConvTuning tune;
+      if (!prepare_conv_umma(c.g, static_cast<const __nv_bfloat16*>(in), B, static_cast<int>(T_in), c.w_umma, ep,
+                             tune, R.umma[k], err))
+        return false;
+    } else {
+      DirectParams& d = R.direct[k];
+      std::memset(&d, 0, sizeof(d));
+      TapPlan tp;
+      if (!build_taps(c.g, false, tp, err)) return false;
+      d.B = B;
+      d.P_out = tp.P_out;
+      d.P_in = tp.P_in;
+      d.Tq_out = static_cast<int>((T_out + tp.P_out - 1) / tp.P_out);
+      d.T_out = static_cast<int>(T_out);
+      d.T_in = static_cast<int>(T_in);
+      d.Cin = c.g.Cin;
+      d.Cout = c.g.Cout;
+      d.span = tp.span;
+      for (int i = 0; i <= kMaxPhases; ++i) d.tap_begin[i] = tp.tap_begin[i];
+      for (size_t i = 0; i < tp.taps.size(); ++i) d.taps[i] = tp.taps[i];
+      if (k == 0) {  // external input, API layout [B, C, T]; pointer / dtype patched per call
+        d.x = nullptr;
+        d.x_sB = static_cast<long long>(c.g.Cin) * T_in;
+        d.x_sT = 1;
+        d.x_sC = T_in;
+      } else {
+        const Step& prev = p->steps[k - 1];
+        d.x = tptr(1 + 2 * (k - 1));
+        if (!prev.needs_raw || !d.x) { err = "internal: raw input missing"; return false; }
+        d.x_f32 = 1;
+        d.x_sB = T_in * c.g.Cin;
+        d.x_sT = c.g.Cin;
+        d.x_sC = 1;
+      }
+      if (s.pre_snake >= 0) {
+        d.pro_a = p->snakes[s.pre_snake].a;
+        d.pro_inv_b = p->snakes[s.pre_snake].inv_b;
+      }
+      d.w = c.w_direct;
+      d.bias = c.has_bias ? c.bias : nullptr;
+      d.residual = res;
+      d.residual_f32 = 1;
+      if (last) {  // external output, API layout; pointer / dtype patched per call
+        d.out_raw = nullptr;
+        d.o_sB = static_cast<long long>(c.g.Cout) * T_out;
+        d.o_sT = 1;
+        d.o_sC = T_out;
+        d.tanh_out = (p->direction == KVAE_DECODER && p->arch.final_tanh) ? 1 : 0;
+      } else {
+        d.out_raw = raw;
+        d.out_raw_f32 = 1;
+        d.o_sB = T_out * c.g.Cout;
+        d.o_sT = c.g.Cout;
+        d.o_sC = 1;
+      }
+      d.out_act = static_cast<__nv_bfloat16*>(act);
+      if (s.epi_snake >= 0) {
+        d.snake_a = p->snakes[s.epi_snake].a;
+        d.snake_inv_b = p->snakes[s.epi_snake].inv_b;
+      }
+      const int cfg = (c.g.Cout <= 4) ? 1 : 0;
+      const int BT = cfg ? 128 : 32, BN = cfg ? 4 : 64;
+      R.direct_cfg[k] = cfg;
+      R.direct_grid[k] = dim3(ceil_div(d.Tq_out, BT) * tp.P_out, ceil_div(c.g.Cout, BN), B);
+      R.direct_smem[k] = (static_cast<size_t>(BT + tp.span) * (kDirectKC + 1) + kDirectKC * BN) * sizeof(float);
+    }
+  }
+  return true;
+}
+
+cudaError_t launch_direct(const DirectParams& d, dim3 grid, int cfg, size_t smem, cudaStream_t st) {
+  if (cfg == 1) conv_direct_kernel<128, 4, 1, 4><<<grid, 128, smem, st>>>(d);
+  else conv_direct_kernel<32, 64, 4, 4><<<grid, 128, smem, st>>>(d);
+  return cudaGetLastError();
+}
+
+int run_plan(kvae_plan* p, const void* in, int in_dtype, void* out, int out_dtype, int B, long long T, void* ws,
+             size_t ws_bytes, cudaStream_t st) {
+  if (!p) return fail("null plan");
+  if (B <= 0 || T <= 0) return fail("empty batch or zero length input");
+  if (T > (1ll << 30)) return fail("input too long");
+  for (const ConvLayer& c : p->convs)
+    if (!c.set) return fail("plan weights not set (kvae_plan_set_conv)");
+  for (const SnakeLayer& s : p->snakes)
+    if (!s.set) return fail("plan SnakeBeta parameters not set (kvae_plan_set_snake)");
+  DeviceGuard guard(p->device);
+  if (!guard.ok) return fail("cannot select device");
+  const int n = static_cast<int>(p->steps.size());
+  const Step& lastst = p->steps[n - 1];
+  if (p->direction == KVAE_ENCODER && T % p->ratio) return fail("audio length must be a multiple of the downsampling ratio");
+  auto key = std::make_tuple(B, T, ws);
+  auto it = p->runs.find(key);
+  if (it == p->runs.end()) {
+    auto R = std::make_unique<PreparedRun>();
+    std::string err;
+    if (!prepare_run(p, B, T, ws, *R, err)) return fail(err);
+    if (p->runs.size() > 64) p->runs.clear();
+    it = p->runs.emplace(key, std::move(R)).first;
+  }
+  PreparedRun& R = *it->second;
+  if (ws_bytes < R.layout.total) return fail("workspace too small");
+  if (R.layout.total > 1024 && !ws) return fail("null workspace");
+  (void)lastst;
+  // boundary layout change for a tensor-core first layer
+  const ConvLayer& c0 = p->convs[p->steps[0].conv];
+  if (c0.umma) {
+    dim3 grid(ceil_div(static_cast<int>(T), 32), ceil_div(c0.g.Cin, 32), B), block(32, 8);
+    cf_to_cl_bf16_kernel<<<grid, block, 0, st>>>(in, in_dtype == KVAE_F32,
+                                                 reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(ws) + R.layout.t[0].offset),
+                                                 c0.g.Cin, static_cast<int>(T));
+    KV_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
+  if (p->profile) {
+    while (static_cast<int>(p->events.size()) < n + 1) {
+      cudaEvent_t e;
+      KV_CUDA(cudaEventCreate(&e));
+      p->events.push_back(e);
+    }
+    KV_CUDA(cudaEventRecord(p->events[0], st));
+    p->prof_B = B;
+    p->prof_T = T;
+    p->prof_valid = true;
+  }
+  for (int k = 0; k < n; ++k) {
+    const ConvLayer& c = p->convs[p->steps[k].conv];
+    if (c.umma) {
+      ConvLaunch& L = R.umma[k];
+      if (k == n - 1) {
+        L.p.out_raw = out;
+        L.p.out_raw_f32 = (out_dtype == KVAE_F32);
+        L.p.out_raw_cf = 1;
+      }
+      KV_CUDA(launch_conv_umma(L, st));
+    } else {
+      DirectParams& d = R.direct[k];
+      if (k == 0) { d.x = in; d.x_f32 = (in_dtype == KVAE_F32); }
+      if (k == n - 1) { d.out_raw = out; d.out_raw_f32 = (out_dtype == KVAE_F32); }
+      KV_CUDA(launch_direct(d, R.direct_grid[k], R.direct_cfg[k], R.direct_smem[k], st));
+    }
+    ++g_launches;
+    if (p->profile) KV_CUDA(cudaEventRecord(p->events[k + 1], st));
+  }
+  return 0;
+}
+
+bool check_dtype(int d) { return d == KVAE_F32 || d == KVAE_BF16; }
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+int kvae_version(void) { return 100; }
+const char* kvae_last_error(void) { return g_err.c_str(); }
+
+int kvae_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    int major = 0;
+    if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ++ok;
+  }
+  return ok;
+}
+
+long long kvae_launch_count(int reset) {
+  const long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+int kvae_plan_create(const kvae_arch* arch, int direction, int precision, int device, kvae_plan** out) {
+  if (!arch || !out) return fail("null argument");
+  if (direction != KVAE_ENCODER && direction != KVAE_DECODER) return fail("bad direction");
+  if (precision != KVAE_PREC_BF16 && precision != KVAE_PREC_F32) return fail("bad precision");
+  if (arch->n_stages < 1 || arch->n_stages > KVAE_MAX_STAGES) return fail("n_stages out of range");
+  if (arch->io_channels < 1 || arch->channels < 1 || arch->latent_dim < 1) return fail("bad channel counts");
+  for (int i = 0; i < arch->n_stages; ++i) {
+    if (arch->strides[i] < 1 || arch->strides[i] > kMaxPhases) return fail("stride out of range (1..8)");
+    if (arch->c_mults[i] < 1) return fail("bad c_mult");
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail("no CUDA device: libkvae has no CPU path");
+  }
+  if (device < 0 || device >= ndev) return fail("bad device index");
+  int major = 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+  if (major != 10) return fail("device is not sm_100 (B200): libkvae is built for sm_100a only");
+  auto p = std::make_unique<kvae_plan>();
+  p->arch = *arch;
+  p->direction = direction;
+  p->precision = precision;
+  p->device = device;
+  if (direction == KVAE_DECODER) build_decoder(p.get());
+  else build_encoder(p.get());
+  finalize_steps(p.get());
+  if (direction == KVAE_DECODER && arch->final_tanh && p->convs.back().umma)
+    return fail("final_tanh with a tensor-core output conv is not supported");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail("cannot select device");
+  for (ConvLayer& c : p->convs) {
+    const size_t n = static_cast<size_t>(c.g.Cin) * c.g.Cout * c.g.K;
+    if (c.umma) KV_CUDA(cudaMalloc(&c.w_umma, n * 2));
+    else KV_CUDA(cudaMalloc(&c.w_direct, n * 4));
+    if (c.has_bias) KV_CUDA(cudaMalloc(&c.bias, c.g.Cout * 4));
+  }
+  for (SnakeLayer& s : p->snakes) {
+    KV_CUDA(cudaMalloc(&s.a, s.C * 4));
+    KV_CUDA(cudaMalloc(&s.inv_b, s.C * 4));
+  }
+  *out = p.release();
+  return 0;
+}
+
+void kvae_plan_destroy(kvae_plan* p) {
+  if (!p) return;
+  DeviceGuard guard(p->device);
+  for (cudaEvent_t e : p->events) cudaEventDestroy(e);
+  for (ConvLayer& c : p->convs) {
+    cudaFree(c.w_umma);
+    cudaFree(c.w_direct);
+    cudaFree(c.bias);
+  }
+  for (SnakeLayer& s : p->snakes) {
+    cudaFree(s.a);
+    cudaFree(s.inv_b);
+  }
+  delete p;
+}
+
+int kvae_plan_num_convs(const kvae_plan* p) { return p ? static_cast<int>(p->convs.size()) : fail("null plan"); }
+int kvae_plan_num_snakes(const kvae_plan* p) { return p ? static_cast<int>(p->snakes.size()) : fail("null plan"); }
+
+int kvae_plan_conv_info(const kvae_plan* p, int idx, int info[8]) {
+  if (!p || !info) return fail("null argument");
+  if (idx < 0 || idx >= static_cast<int>(p->convs.size())) return fail("conv index out of range");
+  const ConvLayer& c = p->convs[idx];
+  info[0] = c.g.kind; info[1] = c.g.Cin; info[2] = c.g.Cout; info[3] = c.g.K;
+  info[4] = c.g.stride; info[5] = c.g.dilation; info[6] = c.g.pad; info[7] = c.has_bias ? 1 : 0;
+  return 0;
+}
+int kvae_plan_snake_channels(const kvae_plan* p, int idx) {
+  if (!p) return fail("null plan");
+  if (idx < 0 || idx >= static_cast<int>(p->snakes.size())) return fail("snake index out of range");
+  return p->snakes[idx].C;
+}
+
+int kvae_plan_set_conv(kvae_plan* p, int idx, const float* w, const float* bias, void* stream) {
+  if (!p || !w) return fail("null argument");
+  if (idx < 0 || idx >= static_cast<int>(p->convs.size())) return fail("conv index out of range");
+  ConvLayer& c = p->convs[idx];
+  if (c.has_bias && !bias) return fail("this conv has a bias");
+  if (!c.has_bias && bias) return fail("this conv has no bias (bias=False in the reference)");
+  DeviceGuard guard(p->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t n = static_cast<size_t>(c.g.Cin) * c.g.Cout * c.g.K;
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 4096));
+  pack_weights_kernel<<<blocks, 256, 0, st>>>(w, c.g.kind == kConvT, c.g.Cout, c.g.Cin, c.g.K, c.w_umma, c.w_direct);
+  KV_CUDA(cudaGetLastError());
+  if (bias) KV_CUDA(cudaMemcpyAsync(c.bias, bias, c.g.Cout * 4, cudaMemcpyDeviceToDevice, st));
+  c.set = true;
+  return 0;
+}
+
+int kvae_plan_set_snake(kvae_plan* p, int idx, const float* alpha, const float* beta, int logscale, void* stream) {
+  if (!p || !alpha || !beta) return fail("null argument");
+  if (idx < 0 || idx >= static_cast<int>(p->snakes.size())) return fail("snake index out of range");
+  SnakeLayer& s = p->snakes[idx];
+  DeviceGuard guard(p->device);
+  snake_params_kernel<<<ceil_div(s.C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(alpha, beta, logscale, s.C,
+                                                                                        s.a, s.inv_b);
+  KV_CUDA(cudaGetLastError());
+  s.set = true;
+  return 0;
+}
+
+size_t kvae_workspace_bytes(kvae_plan* p, int B, long long T) {
+  if (!p || B <= 0 || T <= 0) { fail("bad argument"); return 0; }
+  Layout L;
+  std::string err;
+  if (!make_layout(p, B, T, L, err)) { fail(err); return 0; }
+  return L.total;
+}
+
+int kvae_decode(kvae_plan* p, const void* z, int z_dtype, void* wav, int wav_dtype, int B, long long T, void* ws,
+                size_t ws_bytes, void* stream) {
+  if (!p) return fail("null plan");
+  if (p->direction != KVAE_DECODER) return fail("plan is not a decoder");
+  if (!z || !wav) return fail("null tensor");
+  if (!check_dtype(z_dtype) || !check_dtype(wav_dtype)) return fail("bad dtype");
+  return run_plan(p, z, z_dtype, wav, wav_dtype, B, T, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int kvae_encode(kvae_plan* p, const void* wav, int wav_dtype, void* lat, int lat_dtype, int B, long long L, void* ws,
+                size_t ws_bytes, void* stream) {
+  if (!p) return fail("null plan");
+  if (p->direction != KVAE_ENCODER) return fail("plan is not an encoder");
+  if (!wav || !lat) return fail("null tensor");
+  if (!check_dtype(wav_dtype) || !check_dtype(lat_dtype)) return fail("bad dtype");
+  return run_plan(p, wav, wav_dtype, lat, lat_dtype, B, L, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+double kvae_plan_flops(const kvae_plan* p, int B, long long T) {
+  if (!p) return 0.0;
+  double f = 0.0;
+  for (size_t k = 0; k < p->steps.size(); ++k) {
+    const Step& s = p->steps[k];
+    const ConvGeom& g = p->convs[s.conv].g;
+    const double T_in = (k == 0) ? static_cast<double>(T) : static_cast<double>(step_len(p->steps[k - 1], T));
+    const double T_out = static_cast<double>(step_len(s, T));
+    const double rows = (g.kind == kConv) ? T_out : T_in;
+    f += 2.0 * B * rows * g.Cin * g.Cout * g.K;
+  }
+  return f;
+}
+
+static double step_flops(const kvae_plan* p, size_t k, int B, long long T) {
+  const Step& s = p->steps[k];
+  const ConvGeom& g = p->convs[s.conv].g;
+  const double T_in = (k == 0) ? static_cast<double>(T) : static_cast<double>(step_len(p->steps[k - 1], T));
+  const double T_out = static_cast<double>(step_len(s, T));
+  const double rows = (g.kind == kConv) ? T_out : T_in;
+  return 2.0 * B * rows * g.Cin * g.Cout * g.K;
+}
+
+int kvae_plan_profile(kvae_plan* p, int enable) {
+  if (!p) return fail("null plan");
+  p->profile = enable != 0;
+  p->prof_valid = false;
+  return 0;
+}
+
+int kvae_plan_step_profile(kvae_plan* p, float* ms, double* flops, int* tensor_core, int max_steps) {
+  if (!p || !ms || !flops || !tensor_core) return fail("null argument");
+  if (!p->prof_valid) return fail("no profiled run recorded (kvae_plan_profile(plan, 1), then run)");
+  const int n = static_cast<int>(p->steps.size());
+  if (max_steps < n) return fail("output arrays too small");
+  DeviceGuard guard(p->device);
+  KV_CUDA(cudaEventSynchronize(p->events[n]));
+  for (int k = 0; k < n; ++k) {
+    KV_CUDA(cudaEventElapsedTime(&ms[k], p->events[k], p->events[k + 1]));
+    flops[k] = step_flops(p, k, p->prof_B, p->prof_T);
+    tensor_core[k] = p->convs[p->steps[k].conv].umma ? 1 : 0;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------ layer level
+int kvae_snake_fwd(const void* x, void* y, const float* alpha, const float* beta, int logscale, int B, int C,
+                   long long T, int dtype, void* stream) {
+  if (!x || !y || !alpha || !beta) return fail("null argument");
+  if (!check_dtype(dtype)) return fail("bad dtype");
+  if (B <= 0 || C <= 0 || T <= 0) return 0;  // empty tensor: nothing to do
+  if (static_cast<long long>(B) * C > 65535) return fail("B*C too large");
+  dim3 grid(static_cast<unsigned>((T + 1023) / 1024), B * C);
+  snake_cf_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, alpha, beta, logscale, C, T,
+                                                                       dtype == KVAE_F32);
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int kvae_weight_norm_fold(const float* v, const float* g, float* w, int dim0, int inner, void* stream) {
+  if (!v || !g || !w) return fail("null argument");
+  if (dim0 <= 0 || inner <= 0) return 0;
+  weight_norm_fold_kernel<<<dim0, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, g, w, inner);
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+size_t kvae_conv1d_scratch_bytes(int Cin, int Cout, int K) {
+  return align_up(static_cast<size_t>(Cin) * Cout * K * 4, 1024);
+}
+
+int kvae_conv1d_fwd(const void* x, void* y, const float* w, const float* bias, int transposed, int B, int Cin,
+                    int Cout, long long T, int K, int stride, int dilation, int padding, int dtype, void* scratch,
+                    size_t scratch_bytes, void* stream) {
+  if (!x || !y || !w || !scratch) return fail("null argument");
+  if (!check_dtype(dtype)) return fail("bad dtype");
+  if (B <= 0 || Cin <= 0 || Cout <= 0 || K <= 0 || T <= 0) return fail("empty input");
+  if (stride < 1 || stride > kMaxPhases) return fail("stride out of range (1..8)");
+  if (scratch_bytes < kvae_conv1d_scratch_bytes(Cin, Cout, K)) return fail("scratch too small");
+  ConvGeom g{transposed ? kConvT : kConv, Cin, Cout, K, stride, dilation, padding};
+  const long long T_out = g.out_len(static_cast<int>(T));
+  if (T_out <= 0) return fail("input shorter than the kernel");
+  TapPlan tp;
+  std::string err;
+  if (!build_taps(g, false, tp, err)) return fail(err);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* wd = static_cast<float*>(scratch);
+  const size_t n = static_cast<size_t>(Cin) * Cout * K;
+  pack_weights_kernel<<<static_cast<int>(std::min<size_t>((n + 255) / 256, 4096)), 256, 0, st>>>(
+      w, transposed, Cout, Cin, K, nullptr, wd);
+  KV_CUDA(cudaGetLastError());
+  DirectParams d;
+  std::memset(&d, 0, sizeof(d));
+  d.B = B; d.P_out = tp.P_out; d.P_in = tp.P_in;
+  d.Tq_out = static_cast<int>((T_out + tp.P_out - 1) / tp.P_out); d.T_out = static_cast<int>(T_out);
+  d.T_in = static_cast<int>(T); d.Cin = Cin; d.Cout = Cout; d.span = tp.span;
+  for (int i = 0; i <= kMaxPhases; ++i) d.tap_begin[i] = tp.tap_begin[i];
+  for (size_t i = 0; i < tp.taps.size(); ++i) d.taps[i] = tp.taps[i];
+  d.x = x; d.x_f32 = (dtype == KVAE_F32);
+  d.x_sB = static_cast<long long>(Cin) * T; d.x_sT = 1; d.x_sC = T;
+  d.w = wd; d.bias = bias;
+  d.out_raw = y; d.out_raw_f32 = (dtype == KVAE_F32);
+  d.o_sB = static_cast<long long>(Cout) * T_out; d.o_sT = 1; d.o_sC = T_out;
+  const int cfg = (Cout <= 4) ? 1 : 0;
+  const int BT = cfg ? 128 : 32, BN = cfg ? 4 : 64;
+  dim3 grid(ceil_div(d.Tq_out, BT) * tp.P_out, ceil_div(Cout, BN), B);
+  const size_t smem = (static_cast<size_t>(BT + tp.span) * (kDirectKC + 1) + kDirectKC * BN) * sizeof(float);
+  KV_CUDA(launch_direct(d, grid, cfg, smem, st));
+  g_launches += 2;
+  return 0;
+}
+
+// ------------------------------------------------------------------ latent sampling
+int kvae_sigma_sample(const void* mean, const void* noise, void* out, size_t n, int dtype, float std,
+                      const void* std_noise, float value, size_t per_batch, void* stream) {
+  if (!mean || !noise || !out) return fail("null argument");
+  if (!check_dtype(dtype)) return fail("bad dtype");
+  if (n == 0) return 0;
+  if (std_noise && per_batch == 0) return fail("per_batch must be > 0");
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
+  sigma_sample_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(mean, noise, out, n, dtype == KVAE_F32,
+                                                                             std, std_noise, value, per_batch);
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int kvae_vae_sample(const void* mean, const void* scale, const void* noise, void* out, float* kl, int B, int D,
+                    long long T, int dtype, void* scratch, void* stream) {
+  if (!mean || !scale || !noise || !out || !kl || !scratch) return fail("null argument");
+  if (!check_dtype(dtype)) return fail("bad dtype");
+  const size_t n = static_cast<size_t>(B) * D * T;
+  if (n == 0) return fail("empty input");
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 1024));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  vae_sample_kernel<<<blocks, 256, 0, st>>>(mean, scale, noise, out, n, dtype == KVAE_F32,
+                                            static_cast<double*>(scratch));
+  KV_CUDA(cudaGetLastError());
+  kl_finish_kernel<<<1, 256, 0, st>>>(static_cast<const double*>(scratch), blocks,
+                                      static_cast<double>(B) * static_cast<double>(T), kl);
+  KV_CUDA(cudaGetLastError());
+  g_launches += 2;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,224 @@
+"""Drop-in modules for the leaves of the Oobleck stack: SnakeBeta, WNConv1d, WNConvTranspose1d.
+
+Same constructor arguments, attribute names, parameter names/shapes and ``state_dict`` keys as the
+reference:
+  * SnakeBeta                      stable_audio_tools/models/blocks.py:309-339
+  * WNConv1d / WNConvTranspose1d   dac.nn.layers (un-vendored): ``weight_norm(nn.Conv1d(...))`` /
+                                   ``weight_norm(nn.ConvTranspose1d(...))`` with old-style parameters
+                                   ``weight_g`` / ``weight_v`` (call sites autoencoders.py:49-53,76,98)
+Parameters are initialised through torch's own ``nn.Conv1d`` / ``nn.ConvTranspose1d`` constructors, so
+the same ``torch.manual_seed`` yields the same random-init ``state_dict`` as the reference.
+
+``forward`` of a leaf runs the layer-level C-ABI kernels (fp32 arithmetic).  The fast path is not here:
+``OobleckEncoder`` / ``OobleckDecoder`` hand the whole stack to a fused plan (see ``_plan.py``).
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import _lib
+
+
+class _NoBackward(torch.autograd.Function):
+    """Marks outputs as non-differentiable through this library: backward is not built yet, so a
+    training step fails loudly instead of silently producing zero gradients."""
+
+    @staticmethod
+    def forward(ctx, out, *params):
+        return out.view_as(out)
+
+    @staticmethod
+    def backward(ctx, grad):
+        raise NotImplementedError("kalle_audio_b200: backward (training step, BASELINE config 5) is not implemented "
+                                  "in this round; forward/inference only")
+
+
+def guard_grad(out: torch.Tensor, params) -> torch.Tensor:
+    if torch.is_grad_enabled():
+        ps = [p for p in params if p.requires_grad]
+        if ps:
+            return _NoBackward.apply(out, *ps)
+    return out
+
+
+def snake_beta(x, alpha, beta):
+    """Functional form of blocks.py:301-302 (alpha, beta already exponentiated, broadcast [1,C,1])."""
+    _lib.require_cuda(x, "snake_beta")
+    a = alpha.reshape(-1).float().contiguous()
+    b = beta.reshape(-1).float().contiguous()
+    return _snake_call(x, a, b, logscale=False)
+
+
+def _snake_call(x, alpha, beta, logscale):
+    if x.dim() != 3:
+        raise ValueError("SnakeBeta expects [B, C, T]")
+    B, Cc, T = x.shape
+    if alpha.numel() != Cc:
+        raise ValueError(f"SnakeBeta has {alpha.numel()} channels, input has {Cc}")
+    xin = x if x.dtype in (torch.float32, torch.bfloat16) else x.float()
+    xin = xin.contiguous()
+    y = torch.empty_like(xin)
+    if xin.numel():
+        _lib.check(_lib.lib().kvae_snake_fwd(xin.data_ptr(), y.data_ptr(), alpha.data_ptr(), beta.data_ptr(),
+                                             int(logscale), B, Cc, T, _lib.dtype_code(xin.dtype),
+                                             _lib.stream_ptr(x.device)))
+    return y if y.dtype == x.dtype else y.to(x.dtype)
+
+
+class SnakeBeta(nn.Module):
+    def __init__(self, in_features, alpha=1.0, alpha_trainable=True, alpha_logscale=True):
+        super().__init__()
+        self.in_features = in_features
+        self.alpha_logscale = alpha_logscale
+        if self.alpha_logscale:
+            self.alpha = nn.Parameter(torch.zeros(in_features) * alpha)
+            self.beta = nn.Parameter(torch.zeros(in_features) * alpha)
+        else:
+            self.alpha = nn.Parameter(torch.ones(in_features) * alpha)
+            self.beta = nn.Parameter(torch.ones(in_features) * alpha)
+        self.alpha.requires_grad = alpha_trainable
+        self.beta.requires_grad = alpha_trainable
+        self.no_div_by_zero = 0.000000001
+
+    def forward(self, x):
+        _lib.require_cuda(x, "SnakeBeta.forward")
+        y = _snake_call(x, self.alpha.detach().float().contiguous(), self.beta.detach().float().contiguous(),
+                        self.alpha_logscale)
+        return guard_grad(y, (self.alpha, self.beta))
+
+
+def _single(v):
+    if isinstance(v, (tuple, list)):
+        if len(v) != 1:
+            raise ValueError("1-D convolution arguments must be scalars or 1-tuples")
+        return int(v[0])
+    return int(v)
+
+
+class _WNConvBase(nn.Module):
+    transposed = False
+
+    def _init_from(self, conv: nn.Module):
+        # old-style weight_norm: bias stays first, then weight_g = ||v|| over all dims but 0, weight_v = v
+        w = conv.weight.detach()
+        if conv.bias is not None:
+            self.bias = nn.Parameter(conv.bias.detach().clone())
+        else:
+            self.register_parameter("bias", None)
+        self.weight_g = nn.Parameter(torch.norm_except_dim(w, 2, 0).clone())
+        self.weight_v = nn.Parameter(w.clone())
+
+    # --- weight-norm handling -------------------------------------------------------------------
+    @property
+    def has_weight_norm(self) -> bool:
+        return "weight_g" in self._parameters
+
+    def folded_weight(self) -> torch.Tensor:
+        """fp32 folded weight w = v * g/||v|| computed on the device by libkvae (fold in fp32, round once)."""
+        if not self.has_weight_norm:
+            return self._parameters["weight"].detach().float().contiguous()
+        v = self.weight_v.detach().float().contiguous()
+        g = self.weight_g.detach().float().contiguous()
+        _lib.require_cuda(v, "weight-norm fold")
+        w = torch.empty_like(v)
+        _lib.check(_lib.lib().kvae_weight_norm_fold(v.data_ptr(), g.data_ptr(), w.data_ptr(), v.shape[0],
+                                                    v[0].numel(), _lib.stream_ptr(v.device)))
+        return w
+
+    @property
+    def weight(self):
+        if not self.has_weight_norm:
+            return self._parameters["weight"]
+        return self.folded_weight().to(self.weight_v.dtype)
+
+    def remove_weight_norm(self):
+        """torch.nn.utils.remove_weight_norm equivalent (reference models/utils.py:14-20): replaces
+        weight_g / weight_v by a plain ``weight`` parameter."""
+        if not self.has_weight_norm:
+            raise ValueError("weight_norm already removed")
+        w = self.folded_weight().to(self.weight_v.dtype)
+        del self._parameters["weight_g"]
+        del self._parameters["weight_v"]
+        self.register_parameter("weight", nn.Parameter(w))
+        return self
+
+    def conv_params(self):
+        return [p for p in self.parameters(recurse=False)]
+
+    # --- layer-level forward -------------------------------------------------------------------
+    def forward(self, x):
+        _lib.require_cuda(x, type(self).__name__ + ".forward")
+        if x.dim() != 3 or x.shape[1] != self.in_channels:
+            raise ValueError(f"expected [B, {self.in_channels}, T], got {tuple(x.shape)}")
+        if x.shape[0] == 0 or x.shape[2] == 0:
+            raise ValueError("empty input")
+        xin = x if x.dtype in (torch.float32, torch.bfloat16) else x.float()
+        xin = xin.contiguous()
+        w = self.folded_weight()
+        bias = None if self.bias is None else self.bias.detach().float().contiguous()
+        B, _, T = xin.shape
+        K, s, d, p = self.kernel_size[0], self.stride[0], self.dilation[0], self.padding[0]
+        if self.transposed:
+            T_out = (T - 1) * s - 2 * p + d * (K - 1) + 1
+        else:
+            T_out = (T + 2 * p - d * (K - 1) - 1) // s + 1
+        if T_out <= 0:
+            raise RuntimeError("Kernel size can't be greater than actual input size")
+        L = _lib.lib()
+        y = torch.empty((B, self.out_channels, T_out), dtype=xin.dtype, device=x.device)
+        nscratch = L.kvae_conv1d_scratch_bytes(self.in_channels, self.out_channels, K)
+        scratch = torch.empty(nscratch, dtype=torch.uint8, device=x.device)
+        _lib.check(L.kvae_conv1d_fwd(xin.data_ptr(), y.data_ptr(), w.data_ptr(), _lib.ptr(bias), int(self.transposed),
+                                     B, self.in_channels, self.out_channels, T, K, s, d, p,
+                                     _lib.dtype_code(xin.dtype), scratch.data_ptr(), nscratch,
+                                     _lib.stream_ptr(x.device)))
+        y = y if y.dtype == x.dtype else y.to(x.dtype)
+        return guard_grad(y, self.conv_params())
+
+    def extra_repr(self):
+        return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, "
+                f"padding={self.padding}, dilation={self.dilation}, bias={self.bias is not None}")
+
+
+class WNConv1d(_WNConvBase):
+    """weight_norm(nn.Conv1d(...)): weight_v [Cout, Cin, K], weight_g [Cout, 1, 1] (norm per out-channel)."""
+    transposed = False
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 bias=True, padding_mode="zeros", device=None, dtype=None):
+        super().__init__()
+        if groups != 1 or padding_mode != "zeros" or isinstance(padding, str):
+            raise NotImplementedError("kalle_audio_b200.WNConv1d: groups=1, zero padding with an integer amount only "
+                                      "(the only form the Oobleck stack uses without use_nearest_upsample)")
+        conv = nn.Conv1d(in_channels, out_channels, kernel_size, stride=stride, padding=padding, dilation=dilation,
+                         bias=bias, device=device, dtype=dtype)
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size = (_single(kernel_size),)
+        self.stride = (_single(stride),)
+        self.padding = (_single(padding),)
+        self.dilation = (_single(dilation),)
+        self.groups = 1
+        self._init_from(conv)
+
+
+class WNConvTranspose1d(_WNConvBase):
+    """weight_norm(nn.ConvTranspose1d(...)): weight_v [Cin, Cout, K], weight_g [Cin, 1, 1] -- the norm is
+    taken per *in*-channel because dim 0 of a transposed-conv weight is Cin."""
+    transposed = True
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, output_padding=0, groups=1,
+                 bias=True, dilation=1, padding_mode="zeros", device=None, dtype=None):
+        super().__init__()
+        if groups != 1 or padding_mode != "zeros" or _single(output_padding) != 0 or _single(dilation) != 1:
+            raise NotImplementedError("kalle_audio_b200.WNConvTranspose1d: groups=1, output_padding=0, dilation=1 only")
+        conv = nn.ConvTranspose1d(in_channels, out_channels, kernel_size, stride=stride, padding=padding, bias=bias,
+                                  device=device, dtype=dtype)
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size = (_single(kernel_size),)
+        self.stride = (_single(stride),)
+        self.padding = (_single(padding),)
+        self.dilation = (1,)
+        self.output_padding = (0,)
+        self.groups = 1
+        self._init_from(conv)

@@ -1,0 +1,301 @@
+"""GPU parity: the CUDA path (through the Python drop-in modules and the C ABI) against the CPU oracle and
+the golden outputs of the reference's own modules.  Tolerances are BASELINE.json's: max-abs <= 1e-5 in fp32
+mode, <= 1e-3 in bf16 mode (both against the fp32 reference); latent sampling bit-exact."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+import kalle_audio_b200 as k
+from oracle import oobleck_oracle as O
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+TOL_F32 = 1e-5
+TOL_BF16 = 1e-3
+
+
+def _sd_from_golden(g, prefix="sd."):
+    return {kk[len(prefix):]: H.t(g[kk]) for kk in g.files if kk.startswith(prefix)}
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def maxerr(a, b):
+    return float((a.detach().float().cpu() - H.t(b).float()).abs().max())
+
+
+# --------------------------------------------------------------------------- leaves
+def test_snake_beta_module(dev):
+    torch.manual_seed(0)
+    m = k.SnakeBeta(37).to(dev)
+    with torch.no_grad():
+        m.alpha.copy_(0.4 * torch.randn(37)); m.beta.copy_(0.4 * torch.randn(37))
+    x = torch.randn(3, 37, 1001)
+    ref = O.snake_beta(x, m.alpha.cpu(), m.beta.cpu())
+    assert maxerr(m(x.to(dev)), ref) <= 2e-6
+    yb = m(x.to(dev).bfloat16())
+    assert yb.dtype == torch.bfloat16 and maxerr(yb, O.snake_beta(x.bfloat16().float(), m.alpha.cpu(), m.beta.cpu())) <= 4e-2
+    assert k.SnakeBeta(4).to(dev)(torch.zeros(2, 4, 0, device=dev)).shape == (2, 4, 0)    # empty input
+    f = k.snake_beta(x.to(dev), torch.exp(m.alpha).view(1, -1, 1), torch.exp(m.beta).view(1, -1, 1))
+    assert maxerr(f, ref) <= 2e-6
+
+
+@pytest.mark.parametrize("cin,cout,K,stride,dil,pad,T", [
+    (5, 7, 7, 1, 1, 3, 50), (16, 16, 7, 1, 9, 27, 300), (8, 16, 8, 4, 1, 2, 64), (8, 4, 10, 5, 1, 3, 45),
+    (128, 2, 7, 1, 1, 3, 777), (2, 128, 7, 1, 1, 3, 500), (6, 6, 1, 1, 1, 0, 33), (4, 4, 7, 1, 3, 9, 5), (3, 5, 3, 2, 1, 1, 17)])
+def test_wnconv1d_module(dev, cin, cout, K, stride, dil, pad, T):
+    torch.manual_seed(1)
+    m = k.WNConv1d(cin, cout, K, stride=stride, dilation=dil, padding=pad)
+    with torch.no_grad():
+        m.weight_g.mul_(1.0 + 0.2 * torch.randn_like(m.weight_g))
+    x = torch.randn(2, cin, T)
+    sd = {"c." + n: p for n, p in m.state_dict().items()}
+    ref = O._wn_conv1d(sd, "c", x, stride=stride, padding=pad, dilation=dil)
+    y = m.to(dev)(x.to(dev))
+    assert y.shape == ref.shape
+    assert maxerr(y, ref) <= 2e-5 * max(1.0, float(ref.abs().max()))
+    assert maxerr(m.weight, O.weight_norm_fold(sd["c.weight_v"], sd["c.weight_g"])) <= 1e-6
+
+
+@pytest.mark.parametrize("cin,cout,stride,T", [(8, 4, 2, 33), (16, 8, 4, 20), (6, 3, 5, 11), (8, 8, 8, 9), (128, 64, 4, 50)])
+def test_wnconvtranspose1d_module(dev, cin, cout, stride, T):
+    torch.manual_seed(2)
+    K, pad = 2 * stride + stride % 2, (stride + 1) // 2
+    m = k.WNConvTranspose1d(cin, cout, K, stride=stride, padding=pad)
+    with torch.no_grad():
+        m.weight_g.mul_(1.0 + 0.2 * torch.randn_like(m.weight_g))
+    x = torch.randn(2, cin, T)
+    sd = {"c." + n: p for n, p in m.state_dict().items()}
+    ref = O._wn_conv_transpose1d(sd, "c", x, stride=stride, padding=pad)
+    y = m.to(dev)(x.to(dev))
+    assert y.shape == ref.shape == (2, cout, T * stride)
+    assert maxerr(y, ref) <= 2e-5 * max(1.0, float(ref.abs().max()))
+
+
+def test_standalone_blocks_chain_leaf_kernels(dev):
+    torch.manual_seed(3)
+    ru = k.ResidualUnit(8, 8, dilation=3, use_snake=True)
+    db = k.DecoderBlock(16, 8, stride=4, use_snake=True)
+    eb = k.EncoderBlock(8, 16, stride=5, use_snake=True)
+    x = torch.randn(2, 8, 100)
+    ref = O.residual_unit({"r." + n: p for n, p in ru.state_dict().items()}, "r", x, 3)
+    assert maxerr(ru.to(dev)(x.to(dev)), ref) <= 2e-5
+    x16 = torch.randn(2, 16, 25)
+    assert maxerr(db.to(dev)(x16.to(dev)),
+                  O.decoder_block({"d." + n: p.cpu() for n, p in db.state_dict().items()}, "d", x16, 4)) <= 5e-5
+    assert maxerr(eb.to(dev)(x.to(dev)),
+                  O.encoder_block({"e." + n: p.cpu() for n, p in eb.state_dict().items()}, "e", x, 5)) <= 5e-5
+
+
+# --------------------------------------------------------------------------- fused plans, small models
+def test_tiny_model_fp32_mode_matches_reference(dev):
+    g = H.golden("tiny_ae")
+    m = H.build("tiny", 0, snake_seed=7)
+    m.load_state_dict(_sd_from_golden(g))
+    m.to(dev)
+    y = m.decode(H.t(g["z"]).to(dev))
+    e = m.encode(H.t(g["x"]).to(dev))
+    assert y.dtype == torch.float32 and y.shape == g["dec_out"].shape and e.shape == g["enc_out"].shape
+    assert maxerr(y, g["dec_out"]) <= TOL_F32
+    assert maxerr(e, g["enc_out"]) <= TOL_F32
+
+
+def test_mid_model_tensor_core_path(dev):
+    """C = 64/128/256 three-stage model: every inner conv runs on tcgen05 in bf16 mode."""
+    g = H.golden("mid_ae")
+    m = H.build("mid", 0, snake_seed=7)
+    H.check_checksums(m.state_dict(), g)
+    m.to(dev)
+    z, x = H.t(g["z"]).to(dev), H.t(g["x"]).to(dev)
+    y32, e32 = m.decode(z), m.encode(x)
+    assert maxerr(y32, g["dec_out"]) <= TOL_F32 and maxerr(e32, g["enc_out"]) <= TOL_F32
+    m.set_precision("bf16")
+    y16, e16 = m.decode(z), m.encode(x)
+    assert y16.dtype == torch.float32
+    assert maxerr(y16, g["dec_out"]) <= TOL_BF16
+    # encoder latents are O(1): the budget is relative to their scale
+    assert maxerr(e16, g["enc_out"]) <= TOL_BF16 * max(1.0, float(np.abs(g["enc_out"]).max()) / 0.1)
+    assert maxerr(y16, g["dec_out"]) > 0.0      # it really is the reduced-precision path
+    mb = H.build("mid", 0, snake_seed=7).to(dev).bfloat16()
+    yb = mb.decode(z.bfloat16())
+    assert yb.dtype == torch.bfloat16 and maxerr(yb, g["dec_out"]) <= 4e-3     # + one bf16 rounding of the output
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (1, 7), (3, 33), (2, 130), (5, 64)])
+def test_ragged_shapes_mid_decoder(dev, B, T):
+    m = H.build("mid", 0, snake_seed=7)
+    sd = H.split_sd(m.state_dict(), "decoder.")
+    z = torch.randn(B, 64, T, generator=torch.Generator().manual_seed(B * 100 + T))
+    ref = O.oobleck_decoder(sd, z, H.strides_of("mid"))
+    m.to(dev).set_precision("bf16")
+    assert maxerr(m.decode(z.to(dev)), ref) <= TOL_BF16
+    m.set_precision("fp32")
+    assert maxerr(m.decode(z.to(dev)), ref) <= TOL_F32
+
+
+def test_weight_update_is_picked_up(dev):
+    m = H.build("mid", 0).to(dev).set_precision("bf16")
+    z = torch.randn(1, 64, 8, device=dev)
+    y0 = m.decode(z)
+    with torch.no_grad():
+        m.decoder.layers[0].weight_g.mul_(1.5)
+    y1 = m.decode(z)
+    assert float((y1 - y0).abs().max()) > 1e-4
+    ref = O.oobleck_decoder(H.split_sd({n: p.cpu() for n, p in m.state_dict().items()}, "decoder."), z.cpu(),
+                            H.strides_of("mid"))
+    assert maxerr(y1, ref) <= TOL_BF16
+
+
+def test_errors(dev):
+    m = H.build("tiny", 0).to(dev)
+    with pytest.raises(ValueError):
+        m.encode(torch.randn(1, 2, 81, device=dev))          # not a multiple of the ratio
+    with pytest.raises(ValueError):
+        m.decode(torch.randn(0, 4, 8, device=dev))
+    with pytest.raises(k.KvaeError):
+        m.decode(torch.randn(1, 4, 8))                        # CPU tensor
+    p = list(m.parameters())[0]
+    p.requires_grad_(True)
+    with torch.enable_grad():
+        y = m.decode(torch.randn(1, 4, 8, device=dev))
+        with pytest.raises(NotImplementedError):
+            y.sum().backward()
+
+
+# --------------------------------------------------------------------------- full-size models
+def test_sao_full_size_decode_and_encode(dev):
+    """BASELINE configs 1/2 shapes: z [1,64,216] -> [1,2,442368] and back, against the reference's outputs."""
+    g = H.golden("sao_full")
+    m = H.build("sao", 0)
+    H.check_checksums(m.state_dict(), g)
+    m.to(dev).set_precision("bf16")
+    z = torch.randn(1, 64, 216, generator=torch.Generator().manual_seed(1)).to(dev)
+    x = (0.1 * torch.randn(1, 2, 442368, generator=torch.Generator().manual_seed(2))).to(dev)
+    y = m.decode(z)
+    assert y.shape == (1, 2, 442368)
+    idx = H.t(g["dec_idx"]).long()
+    err = maxerr(y[:, :, idx.to(dev)], g["dec_out_at_idx"])
+    print(f"SAO bf16 decode max-abs err {err:.3e} (abs max {float(g['dec_abs_max']):.3f})")
+    assert err <= TOL_BF16
+    assert abs(float((y.double() ** 2).sum()) - float(g["dec_sq_sum"])) <= 2e-2 * float(g["dec_sq_sum"])
+    e = m.encode(x)
+    scale = float(np.abs(g["enc_out"]).max())
+    erre = maxerr(e, g["enc_out"])
+    print(f"SAO bf16 encode max-abs err {erre:.3e} (abs max {scale:.3f})")
+    assert erre <= TOL_BF16 * max(1.0, scale / 0.1)
+
+
+def test_sao_fp32_mode_short_clip(dev):
+    m = H.build("sao", 0)
+    sd = H.split_sd(m.state_dict(), "decoder.")
+    z = torch.randn(1, 64, 6, generator=torch.Generator().manual_seed(5))
+    ref = O.oobleck_decoder(sd, z, H.strides_of("sao"))
+    m.to(dev)
+    assert maxerr(m.decode(z.to(dev)), ref) <= TOL_F32
+
+
+def test_o12_latent512_decode_encode(dev):
+    g = H.golden("o12_d512")
+    m = H.build("o12_d512", 0)
+    H.check_checksums(m.state_dict(), g)
+    m.to(dev).set_precision("bf16")
+    z = torch.randn(1, 512, 16, generator=torch.Generator().manual_seed(1)).to(dev)
+    x = (0.1 * torch.randn(1, 1, 1280 * 16, generator=torch.Generator().manual_seed(2))).to(dev)
+    y = m.decode(z)
+    assert y.shape == (1, 1, 20480) and maxerr(y, g["dec_out"]) <= TOL_BF16
+    e = m.encode(x)
+    assert e.shape == (1, 1024, 16)
+    assert maxerr(e, g["enc_out"]) <= TOL_BF16 * max(1.0, float(np.abs(g["enc_out"]).max()) / 0.1)
+
+
+def test_batch_items_are_independent(dev):
+    """Batch sharding relies on it: decoding a batch == decoding each clip alone (bit-identical)."""
+    m = H.build("mid", 0).to(dev).set_precision("bf16")
+    z = torch.randn(4, 64, 40, device=dev)
+    y = m.decode(z)
+    for i in range(4):
+        assert torch.equal(y[i:i + 1], m.decode(z[i:i + 1]))
+
+
+# --------------------------------------------------------------------------- chunked / pretransform
+def test_chunked_decode_encode_match_reference(dev):
+    g = H.golden("chunked")
+    tiny = H.golden("tiny_ae")
+    m = H.build("tiny", 0)
+    m.load_state_dict(_sd_from_golden(tiny))
+    m.to(dev)
+    z = H.t(g["z"]).to(dev)
+    y = m.decode_audio(z, chunked=True, overlap=32, chunk_size=128)
+    assert y.dtype == torch.float32 and maxerr(y, g["dec_chunked"]) <= TOL_F32
+    assert maxerr(m.decode_audio(z, chunked=True, overlap=16, chunk_size=64), g["dec_chunked_64_16"]) <= TOL_F32
+    assert maxerr(m.decode_audio(z), g["dec_full"]) <= TOL_F32
+    with pytest.raises(UnboundLocalError):
+        m.decode_audio(z[:, :, :100], chunked=True)
+    ms = H.build("tiny_sym", 5)
+    ms.load_state_dict({kk[len("sym_sd."):]: H.t(g[kk]) for kk in g.files if kk.startswith("sym_sd.")})
+    ms.to(dev)
+    e = ms.encode_audio(H.t(g["x"]).to(dev), chunked=True, overlap=32, chunk_size=128)
+    assert maxerr(e, g["enc_chunked"]) <= TOL_F32
+    with pytest.raises(RuntimeError):
+        m.encode_audio(H.t(g["x"]).to(dev), chunked=True)      # encoder emits 2*latent_dim: reference errors too
+
+
+def test_pretransform_scale_and_iterate_batch(dev):
+    tiny = H.golden("tiny_ae")
+    cfg = H.CONFIGS["tiny"]
+    pt = k.create_pretransform_from_config({"type": "autoencoder", "config": cfg["model"], "scale": 2.0,
+                                            "iterate_batch": True}, 16000)
+    pt.load_state_dict(_sd_from_golden(tiny))
+    pt.to(dev)
+    y = pt.decode(H.t(tiny["z"]).to(dev) / 2.0)
+    assert maxerr(y, tiny["dec_out"]) <= TOL_F32
+    e = pt.encode(H.t(tiny["x"]).to(dev))
+    assert maxerr(e * 2.0, tiny["enc_out"]) <= TOL_F32
+
+
+# --------------------------------------------------------------------------- latent sampling (bit exact)
+def test_sampling_bit_exact_vs_reference(dev):
+    g = H.golden("sampling")
+    mean, scale, noise = (H.t(g[n]).to(dev) for n in ("mean", "scale", "noise"))
+    lat, kl = k.vae_sample(mean, scale, noise)
+    assert torch.equal(lat.cpu(), H.t(g["vae_latents"]))
+    assert abs(float(kl) - float(g["vae_kl"])) <= 1e-5 * abs(float(g["vae_kl"]))
+    assert torch.equal(k.sample(mean, "fix", noise=noise).cpu(), H.t(g["fix"]))
+    gau = k.sample(mean, "gaussian", noise=H.t(g["noise_g"]).to(dev), std_noise=H.t(g["std_noise"]).to(dev))
+    assert torch.equal(gau.cpu(), H.t(g["gaussian"]))
+    assert k.sample(mean, "anything else") is mean
+    fb = k.sample(mean.bfloat16(), "fix", noise=H.t(g["noise_bf"]).to(dev).bfloat16())
+    assert fb.dtype == torch.bfloat16 and torch.equal(fb.float().cpu(), H.t(g["fix_bf"]))
+    # LM layout [B, T, D] (model_sigmaVAE.py:68) and RNG-stream parity with torch.randn_like
+    mt = mean.transpose(1, 2).contiguous()
+    torch.manual_seed(3)
+    a = k.sample(mt, "fix")
+    torch.manual_seed(3)
+    b = mt + torch.tensor(0.5).to(dev) * torch.randn_like(mt)
+    assert torch.equal(a, b)
+    torch.manual_seed(4)
+    a = k.sample(mt, "gaussian")
+    torch.manual_seed(4)
+    s = torch.randn(mt.size(0), device=dev, dtype=mt.dtype) * (torch.tensor(0.5) / 0.8).to(dev)
+    b = mt + s.view(-1, 1, 1) * torch.randn_like(mt)
+    assert torch.equal(a, b)
+
+
+def test_encode_sample_decode_roundtrip_config2_shape(dev):
+    """BASELINE config 2 data flow at reduced batch: encode -> chunk(2) -> sample('fix') -> decode."""
+    m = H.build("sao", 0).to(dev).set_precision("bf16")
+    x = 0.1 * torch.randn(2, 2, 2048 * 12, device=dev)
+    enc = m.encode(x)
+    mean, _ = enc.chunk(2, dim=1)
+    zl = k.sample(mean.contiguous(), "fix")
+    y = m.decode(zl)
+    assert enc.shape == (2, 128, 12) and y.shape == x.shape and bool(torch.isfinite(y).all())
+    sd = {n: p.cpu() for n, p in m.state_dict().items()}
+    ref = O.oobleck_decoder(H.split_sd(sd, "decoder."), zl.cpu(), H.strides_of("sao"))
+    assert maxerr(y, ref) <= TOL_BF16

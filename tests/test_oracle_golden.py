@@ -1,0 +1,131 @@
+"""Pins the CPU oracle (oracle/oobleck_oracle.py) against outputs of the reference's own modules
+(tests/golden/*.npz, produced by tests/golden/make_golden.py from /root/reference)."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from oracle import oobleck_oracle as O
+
+torch.set_grad_enabled(False)
+
+
+def _sd_from_golden(g, prefix="sd."):
+    return {k[len(prefix):]: H.t(g[k]) for k in g.files if k.startswith(prefix)}
+
+
+def test_tiny_decoder_encoder_match_reference():
+    g = H.golden("tiny_ae")
+    sd = _sd_from_golden(g)
+    st = H.strides_of("tiny")
+    y = O.oobleck_decoder(H.split_sd(sd, "decoder."), H.t(g["z"]), st)
+    e = O.oobleck_encoder(H.split_sd(sd, "encoder."), H.t(g["x"]), st)
+    assert y.shape == g["dec_out"].shape and e.shape == g["enc_out"].shape
+    assert np.abs(y.numpy() - g["dec_out"]).max() <= 2e-6
+    assert np.abs(e.numpy() - g["enc_out"]).max() <= 2e-6
+
+
+def test_tiny_decoder_layerwise():
+    g = H.golden("tiny_ae")
+    sd = H.split_sd(_sd_from_golden(g), "decoder.")
+    st = H.strides_of("tiny")
+    n = len(st)
+    h = O._wn_conv1d(sd, "layers.0", H.t(g["z"]), padding=3)
+    assert np.abs(h.numpy() - g["dec_layer0"]).max() <= 1e-6
+    for i in range(n):
+        h = O.decoder_block(sd, f"layers.{1 + i}", h, st[n - 1 - i])
+        ref = g[f"dec_layer{1 + i}"]
+        assert np.abs(h.numpy() - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
+    h = O._snake(sd, f"layers.{1 + n}", h)
+    assert np.abs(h.numpy() - g[f"dec_layer{1 + n}"]).max() <= 2e-6
+
+
+def test_weight_norm_fold_matches_torch():
+    v = torch.randn(6, 5, 7)
+    g = torch.rand(6, 1, 1) + 0.5
+    assert torch.allclose(O.weight_norm_fold(v, g), torch._weight_norm(v, g, 0), atol=1e-7)
+    vt = torch.randn(5, 6, 4)       # transposed conv: norm over dim 0 = in-channels
+    gt = torch.rand(5, 1, 1) + 0.5
+    assert torch.allclose(O.weight_norm_fold(vt, gt), torch._weight_norm(vt, gt, 0), atol=1e-7)
+
+
+def test_chunked_paths_match_reference():
+    g = H.golden("chunked")
+    tiny = H.golden("tiny_ae")
+    sd = H.split_sd(_sd_from_golden(tiny), "decoder.")
+    st = H.strides_of("tiny")
+    dec = lambda z: O.oobleck_decoder(sd, z, st)
+    y = O.decode_audio_chunked(dec, H.t(g["z"]), 40, 2, overlap=32, chunk_size=128)
+    assert np.abs(y.numpy() - g["dec_chunked"]).max() <= 2e-6
+    y2 = O.decode_audio_chunked(dec, H.t(g["z"]), 40, 2, overlap=16, chunk_size=64)
+    assert np.abs(y2.numpy() - g["dec_chunked_64_16"]).max() <= 2e-6
+    # receptive field +-10 frames < overlap/2 = 16: chunked == unchunked to fp32 noise
+    assert np.abs(g["dec_chunked"] - g["dec_full"]).max() <= 1e-5
+    sym = H.split_sd({k[len("sym_sd."):]: H.t(g[k]) for k in g.files if k.startswith("sym_sd.")}, "encoder.")
+    enc = lambda x: O.oobleck_encoder(sym, x, st)
+    e = O.encode_audio_chunked(enc, H.t(g["x"]), 40, 4, overlap=32, chunk_size=128)
+    assert np.abs(e.numpy() - g["enc_chunked"]).max() <= 2e-6
+    with pytest.raises(UnboundLocalError):
+        O.decode_audio_chunked(dec, H.t(g["z"])[:, :, :100], 40, 2)
+
+
+def test_sampling_bit_exact():
+    g = H.golden("sampling")
+    mean, scale, noise = H.t(g["mean"]), H.t(g["scale"]), H.t(g["noise"])
+    lat, kl = O.vae_sample(mean, scale, noise)
+    assert torch.equal(lat, H.t(g["vae_latents"]))
+    assert abs(float(kl) - float(g["vae_kl"])) <= 1e-4 * abs(float(g["vae_kl"]))
+    assert torch.equal(O.sigma_sample(mean, noise, "fix"), H.t(g["fix"]))
+    assert torch.equal(O.sigma_sample(mean, H.t(g["noise_g"]), "gaussian", H.t(g["std_noise"])), H.t(g["gaussian"]))
+    assert torch.equal(O.sigma_sample(mean, noise, "other"), H.t(g["none"]))
+    fb = O.sigma_sample(mean.bfloat16(), H.t(g["noise_bf"]).bfloat16(), "fix")
+    assert fb.dtype == torch.bfloat16 and torch.equal(fb.float(), H.t(g["fix_bf"]))
+
+
+def test_mid_model_same_seed_same_weights_and_outputs():
+    g = H.golden("mid_ae")
+    m = H.build("mid", 0, snake_seed=7)
+    sd = m.state_dict()
+    H.check_checksums(sd, g)
+    st = H.strides_of("mid")
+    y = O.oobleck_decoder(H.split_sd(sd, "decoder."), H.t(g["z"]), st)
+    e = O.oobleck_encoder(H.split_sd(sd, "encoder."), H.t(g["x"]), st)
+    assert np.abs(y.numpy() - g["dec_out"]).max() <= 5e-6
+    assert np.abs(e.numpy() - g["enc_out"]).max() <= 5e-6
+
+
+def test_o12_latent512_matches_reference():
+    g = H.golden("o12_d512")
+    m = H.build("o12_d512", 0)
+    sd = m.state_dict()
+    H.check_checksums(sd, g)
+    st = H.strides_of("o12_d512")
+    z = torch.randn(1, 512, 16, generator=torch.Generator().manual_seed(1))
+    y = O.oobleck_decoder(H.split_sd(sd, "decoder."), z, st)
+    assert y.shape == (1, 1, 1280 * 16)
+    assert np.abs(y.numpy() - g["dec_out"]).max() <= 5e-6
+
+
+def test_sao_full_size_decode_matches_reference():
+    """BASELINE config 1: SAO-shape decoder, z [1,64,216] -> [1,2,442368], fp32 CPU."""
+    g = H.golden("sao_full")
+    m = H.build("sao", 0)
+    sd = m.state_dict()
+    H.check_checksums(sd, g)
+    z = torch.randn(1, 64, 216, generator=torch.Generator().manual_seed(1))
+    y = O.oobleck_decoder(H.split_sd(sd, "decoder."), z, H.strides_of("sao"))
+    assert y.shape == (1, 2, 442368)
+    idx = H.t(g["dec_idx"]).long()
+    assert np.abs(y[:, :, idx].numpy() - g["dec_out_at_idx"]).max() <= 5e-6
+    assert abs(float(y.abs().max()) - float(g["dec_abs_max"])) <= 1e-5
+    assert abs(float((y.double() ** 2).sum()) - float(g["dec_sq_sum"])) <= 1e-4 * float(g["dec_sq_sum"])
+
+
+def test_flop_model_matches_survey():
+    # SAO decode 1089.145 GF, encode 1089.089 GF; O12 D=512 decode 1255.219 GF
+    f = O.conv_flops_decoder(64, 128, [1, 2, 4, 8, 16], [2, 4, 4, 8, 8], 2, 1, 216)
+    assert abs(f / 1e9 - 1089.145) < 0.01
+    f = O.conv_flops_encoder(128, 128, [1, 2, 4, 8, 16], [2, 4, 4, 8, 8], 2, 1, 442368)
+    assert abs(f / 1e9 - 1089.089) < 0.01
+    f = O.conv_flops_decoder(512, 128, [1, 2, 4, 8, 16], [2, 4, 4, 5, 8], 1, 1, 375)
+    assert abs(f / 1e9 - 1255.219) < 0.01
