@@ -21,6 +21,7 @@
 
 #include "../../include/kvae.h"
 #include "conv_direct.cuh"
+#include "conv_edge.cuh"
 #include "conv_umma_host.cuh"
 #include "elementwise.cuh"
 
@@ -105,6 +106,9 @@ struct PreparedRun {
   std::vector<dim3> direct_grid;
   std::vector<int> direct_cfg;      // 0: 32x64 tile, 1: 128x4 tile
   std::vector<size_t> direct_smem;
+  std::vector<int> kind;            // per step: 0 tensor-core, 1 generic, 2 waveform-in, 3 waveform-out
+  std::vector<WaveInParams> wave_in;
+  std::vector<WaveOutParams> wave_out;
   Layout layout;
 };
 
@@ -319,6 +323,9 @@ bool prepare_run(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R, std
   R.direct_grid.resize(n);
   R.direct_cfg.assign(n, 0);
   R.direct_smem.assign(n, 0);
+  R.kind.assign(n, 1);
+  R.wave_in.resize(n);
+  R.wave_out.resize(n);
   uint8_t* base = static_cast<uint8_t*>(ws);
   auto tptr = [&](int id) -> void* { return R.layout.t[id].bytes ? base + R.layout.t[id].offset : nullptr; };
   for (int k = 0; k < n; ++k) {
@@ -335,7 +342,46 @@ bool prepare_run(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R, std
     void* act = s.needs_act ? tptr(2 + 2 * k) : nullptr;
     const void* res = (s.residual_from >= 0) ? tptr(1 + 2 * s.residual_from) : nullptr;
     if (s.residual_from >= 0 && !res) { err = "internal: residual tensor missing"; return false; }
+    const bool k7same = c.g.kind == kConv && c.g.K == 7 && c.g.stride == 1 && c.g.dilation == 1 && c.g.pad == 3;
+    if (!c.umma && p->precision == KVAE_PREC_BF16 && k7same && last && k > 0 && c.g.Cout <= 2 && !c.has_bias &&
+        c.g.Cin % 32 == 0 && c.g.Cin <= 256 && s.pre_snake >= 0 && !res) {
+      // decoder tail (conv_edge.cuh)
+      WaveOutParams& w = R.wave_out[k];
+      w.x = static_cast<const float*>(tptr(1 + 2 * (k - 1)));
+      if (!w.x) { err = "internal: raw input missing"; return false; }
+      w.pro_a = p->snakes[s.pre_snake].a;
+      w.pro_inv_b = p->snakes[s.pre_snake].inv_b;
+      w.w = c.w_direct;
+      w.y = nullptr;  // patched per call
+      w.T = static_cast<int>(T_out);
+      w.Cin = c.g.Cin;
+      w.tanh_out = (p->direction == KVAE_DECODER && p->arch.final_tanh) ? 1 : 0;
+      R.kind[k] = 3;
+      continue;
+    }
+    if (!c.umma && p->precision == KVAE_PREC_BF16 && k7same && k == 0 && !last && c.g.Cin <= 2 && c.has_bias &&
+        c.g.Cout % 128 == 0 && s.pre_snake < 0 && !res) {
+      // encoder head (conv_edge.cuh)
+      WaveInParams& w = R.wave_in[k];
+      w.x = nullptr;  // patched per call
+      w.w = c.w_direct;
+      w.bias = c.bias;
+      w.out_raw = static_cast<float*>(raw);
+      w.out_act = static_cast<__nv_bfloat16*>(act);
+      if (s.epi_snake >= 0) {
+        w.snake_a = p->snakes[s.epi_snake].a;
+        w.snake_inv_b = p->snakes[s.epi_snake].inv_b;
+      } else {
+        w.snake_a = nullptr;
+        w.snake_inv_b = nullptr;
+      }
+      w.T = static_cast<int>(T_out);
+      w.Cout = c.g.Cout;
+      R.kind[k] = 2;
+      continue;
+    }
     if (c.umma) {
+      R.kind[k] = 0;
       const void* in = (k == 0) ? tptr(0) : tptr(2 + 2 * (k - 1));
       if (!in) { err = "internal: tensor-core operand missing"; return false; }
       ConvEpilogue ep;
@@ -421,6 +467,29 @@ bool prepare_run(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R, std
   return true;
 }
 
+cudaError_t launch_wave_out(const WaveOutParams& w, int Cout, int B, cudaStream_t st) {
+  const size_t smem = wave_out_smem(w.Cin, Cout);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wave_out_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_wave_out_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid((w.T + kWaveOutTile - 1) / kWaveOutTile, B);
+  if (Cout == 1) conv_wave_out_kernel<1><<<grid, 128, smem, st>>>(w);
+  else conv_wave_out_kernel<2><<<grid, 128, smem, st>>>(w);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wave_in(const WaveInParams& w, int Cin, int B, cudaStream_t st) {
+  dim3 grid((w.T + kWaveInTile - 1) / kWaveInTile, w.Cout / 128, B);
+  if (Cin == 1) conv_wave_in_kernel<1><<<grid, 128, 0, st>>>(w);
+  else conv_wave_in_kernel<2><<<grid, 128, 0, st>>>(w);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_direct(const DirectParams& d, dim3 grid, int cfg, size_t smem, cudaStream_t st) {
   if (cfg == 1) conv_direct_kernel<128, 4, 1, 4><<<grid, 128, smem, st>>>(d);
   else conv_direct_kernel<32, 64, 4, 4><<<grid, 128, smem, st>>>(d);
@@ -477,7 +546,17 @@ int run_plan(kvae_plan* p, const void* in, int in_dtype, void* out, int out_dtyp
   }
   for (int k = 0; k < n; ++k) {
     const ConvLayer& c = p->convs[p->steps[k].conv];
-    if (c.umma) {
+    if (R.kind[k] == 3) {
+      WaveOutParams& w = R.wave_out[k];
+      w.y = out;
+      w.y_f32 = (out_dtype == KVAE_F32);
+      KV_CUDA(launch_wave_out(w, c.g.Cout, B, st));
+    } else if (R.kind[k] == 2) {
+      WaveInParams& w = R.wave_in[k];
+      w.x = in;
+      w.x_f32 = (in_dtype == KVAE_F32);
+      KV_CUDA(launch_wave_in(w, c.g.Cin, B, st));
+    } else if (c.umma) {
       ConvLaunch& L = R.umma[k];
       if (k == n - 1) {
         L.p.out_raw = out;

