@@ -70,7 +70,7 @@ __host__ __device__ inline size_t conv_umma_smem_bytes(const ConvParams& p) {
 __device__ __forceinline__ float sin_fast(float x) {
   const float k = rintf(x * 0.15915494309189535f);
   float r = fmaf(-k, 6.2831854820251465f, x);       // 2*pi rounded to fp32
-  r = fmaf(-k, -1.7484555e-7f, r);                  // 2*pi - fp32(2*pi)
+  r = fmaf(-k, -1.7484556e-7f, r);                  // 2*pi - fp32(2*pi)
   return __sinf(r);
 }
 
@@ -191,100 +191,116 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
-    // TMEM lane = time row, so tcgen05.ld hands each thread one row x 32 channels.  Rows are Cout
-    // elements apart in HBM, so that mapping would touch 32 different lines per warp instruction.
-    // Each warp therefore transposes its 32x32 block through shared memory (the operand rings are
-    // idle once acc_full fires) into "8 lanes x 16 B = one 128-byte row segment", so every residual
-    // load and every output store is a fully used line.
     const int quad = warp & 3;
+    const int row = quad * 32 + lane;
     const int T_out = p.Tq_out * p.P_out;
-    float* stage = reinterpret_cast<float*>(a_ring) + quad * (32 * 33);
-    const int tr = lane >> 3;         // row within a group of 4
-    const int tc = (lane & 7) * 4;    // first of this lane's 4 channels inside the 32-channel block
     ptx::mbar_wait(acc_full, 0);
     ptx::tc_fence_after();
     for (int m = 0; m < p.MT; ++m) {
-      const int qw = q0 + m * 128 + quad * 32;   // first row of this warp's block
+      const int q = q0 + m * 128 + row;
+      const bool valid = q < p.Tq_out;
+      const size_t orow = (static_cast<size_t>(b) * T_out + static_cast<size_t>(q) * p.P_out + phi) *
+                          p.Cout;
       for (int c0 = 0; c0 < p.NT; c0 += 32) {
         uint32_t r[32];
-        __syncwarp();  // tcgen05.ld is .sync.aligned; also orders the previous block's stage reads
+        __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the predicated body
         ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + m * p.NT + c0, r);
         ptx::tmem_ld_wait();
+        if (valid) {
         const int cbase = n0 + c0;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+            v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+          }
+        }
+        if (p.residual) {
+          if (p.residual_f32) {
+            const float4* rp = reinterpret_cast<const float4*>(
+                static_cast<const float*>(p.residual) + orow + cbase);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 x = __ldg(rp + j);
+              v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+            }
+          } else {
+            const uint4* rp = reinterpret_cast<const uint4*>(
+                static_cast<const __nv_bfloat16*>(p.residual) + orow + cbase);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 x = __ldg(rp + j);
+              const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[8 * j + 2 * e] += __uint_as_float(w[e] << 16);
+                v[8 * j + 2 * e + 1] += __uint_as_float(w[e] & 0xffff0000u);
+              }
+            }
+          }
+        }
         if (p.out_raw && p.out_raw_cf) {
-          // channels-first API output (no residual / activation on this path): thread = time row,
-          // lanes hold consecutive time steps -> 128 B per channel per warp, already coalesced
-          const int q = qw + lane;
-          if (q < p.Tq_out) {
-            const size_t t_out = static_cast<size_t>(q) * p.P_out + phi;
-            const size_t o0 = (static_cast<size_t>(b) * p.Cout + cbase) * T_out + t_out;
-            if (p.out_raw_f32) {
-              float* op = static_cast<float*>(p.out_raw) + o0;
+          // channels-first store: lanes hold consecutive time steps -> 128 B (fp32) per channel
+          const size_t t_out = static_cast<size_t>(q) * p.P_out + phi;
+          const size_t o0 = (static_cast<size_t>(b) * p.Cout + cbase) * T_out + t_out;
+          if (p.out_raw_f32) {
+            float* op = static_cast<float*>(p.out_raw) + o0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float v = __uint_as_float(r[j]);
-                if (p.bias) v += __ldg(p.bias + cbase + j);
-                op[static_cast<size_t>(j) * T_out] = v;
+            for (int j = 0; j < 32; ++j) op[static_cast<size_t>(j) * T_out] = v[j];
+          } else {
+            __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.out_raw) + o0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) op[static_cast<size_t>(j) * T_out] = __float2bfloat16(v[j]);
+          }
+        } else if (p.out_raw) {
+          if (p.out_raw_f32) {
+            float4* op = reinterpret_cast<float4*>(static_cast<float*>(p.out_raw) + orow + cbase);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              op[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            uint4* op =
+                reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out_raw) + orow + cbase);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+                w[e] = *reinterpret_cast<uint32_t*>(&h);
               }
-            } else {
-              __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.out_raw) + o0;
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                float v = __uint_as_float(r[j]);
-                if (p.bias) v += __ldg(p.bias + cbase + j);
-                op[static_cast<size_t>(j) * T_out] = __float2bfloat16(v);
-              }
+              op[j] = make_uint4(w[0], w[1], w[2], w[3]);
             }
-          }
-          continue;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = __uint_as_float(r[j]);
-        __syncwarp();
-        float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f), sa4 = bias4, sib4 = bias4;
-        if (p.bias) bias4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + tc));
-        if (p.snake_a) {
-          sa4 = __ldg(reinterpret_cast<const float4*>(p.snake_a + cbase + tc));
-          sib4 = __ldg(reinterpret_cast<const float4*>(p.snake_inv_b + cbase + tc));
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = 4 * i + tr;
-          const int q = qw + rr;
-          if (q >= p.Tq_out) continue;
-          const size_t o = (static_cast<size_t>(b) * T_out + static_cast<size_t>(q) * p.P_out + phi) * p.Cout +
-                           cbase + tc;
-          float v0 = stage[rr * 33 + tc] + bias4.x, v1 = stage[rr * 33 + tc + 1] + bias4.y;
-          float v2 = stage[rr * 33 + tc + 2] + bias4.z, v3 = stage[rr * 33 + tc + 3] + bias4.w;
-          if (p.residual) {
-            if (p.residual_f32) {
-              const float4 x = __ldg(reinterpret_cast<const float4*>(static_cast<const float*>(p.residual) + o));
-              v0 += x.x; v1 += x.y; v2 += x.z; v3 += x.w;
-            } else {
-              const uint2 x = __ldg(reinterpret_cast<const uint2*>(static_cast<const __nv_bfloat16*>(p.residual) + o));
-              v0 += __uint_as_float(x.x << 16); v1 += __uint_as_float(x.x & 0xffff0000u);
-              v2 += __uint_as_float(x.y << 16); v3 += __uint_as_float(x.y & 0xffff0000u);
-            }
-          }
-          if (p.out_raw) {
-            if (p.out_raw_f32) {
-              *reinterpret_cast<float4*>(static_cast<float*>(p.out_raw) + o) = make_float4(v0, v1, v2, v3);
-            } else {
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
-              *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(p.out_raw) + o) =
-                  make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
-            }
-          }
-          if (p.out_act) {
-            if (p.snake_a) {
-              v0 = snake_beta<true>(v0, sa4.x, sib4.x); v1 = snake_beta<true>(v1, sa4.y, sib4.y);
-              v2 = snake_beta<true>(v2, sa4.z, sib4.z); v3 = snake_beta<true>(v3, sa4.w, sib4.w);
-            }
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
-            *reinterpret_cast<uint2*>(p.out_act + o) =
-                make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
           }
         }
+        if (p.out_act) {
+          if (p.snake_a) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(p.snake_a + cbase + j));
+              const float4 ib = __ldg(reinterpret_cast<const float4*>(p.snake_inv_b + cbase + j));
+              v[j] = snake_beta<true>(v[j], a.x, ib.x);
+              v[j + 1] = snake_beta<true>(v[j + 1], a.y, ib.y);
+              v[j + 2] = snake_beta<true>(v[j + 2], a.z, ib.z);
+              v[j + 3] = snake_beta<true>(v[j + 3], a.w, ib.w);
+            }
+          }
+          uint4* op = reinterpret_cast<uint4*>(p.out_act + orow + cbase);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+              w[e] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            op[j] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+        }  // valid
       }
     }
   }

@@ -1,0 +1,311 @@
+// conv_umma2: persistent, double-buffered version of the tcgen05 implicit-GEMM convolution.
+//
+// Same GEMM view and tap decomposition as conv_umma.cuh (see there).  What changes is the schedule:
+//   * one CTA per SM loops over output tiles (static round-robin), so operand loads of tile i+1 are
+//     in flight while tile i is still being multiplied / written out;
+//   * the accumulator lives in TMEM twice (2 x MT*NT columns) when that fits in 512 columns: the UMMA
+//     issuer starts tile i+1 as soon as its operands land while the epilogue drains tile i;
+//   * 8 epilogue warps (two warpgroups, each covering the 128 TMEM lanes) split a tile's 32-column
+//     blocks between them;
+//   * outputs leave through TMA stores: a thread writes its row of a block into a swizzled
+//     shared-memory tile (conflict-free), one elected thread issues cp.async.bulk.tensor stores, and
+//     the bulk-group mechanism recycles the two staging tiles -- every HBM write is a full line and no
+//     thread waits for it;
+//   * the ResidualUnit skip (fp32 stream) is fetched with batched 16-byte loads ahead of the math.
+//
+// Warp roles (384 threads): warp 0 TMA producer, warp 1 UMMA issuer, warp 2 TMEM allocator, warp 3 idle,
+// warps 4-11 epilogue.
+#pragma once
+#include <cuda_bf16.h>
+#include <cstdint>
+
+#include "conv_umma.cuh"
+#include "ptx.cuh"
+
+namespace kvae {
+
+struct ConvParams2 {
+  int B, Tq_out, P_out, Cout;
+  int n_chunks;
+  int MT, NT;
+  int RB, nbox;
+  int SA, SB;
+  int acc_stages;          // 1 or 2 accumulator buffers in TMEM
+  int tmem_cols;           // power of two >= acc_stages*MT*NT
+  int q_tiles, n_tiles, total_tiles;
+  int tap_begin[kMaxPhases + 1];
+  Tap taps[kMaxTaps];
+  // epilogue
+  const float* bias;
+  const float* residual;   // fp32 channels-last [B, T_out, Cout] or nullptr
+  int raw_mode;            // 0 none, 1 fp32 channels-last via TMA (tmR), 2 channels-first direct store
+  void* out_cf;            // raw_mode 2: [B, Cout, T_out]
+  int out_cf_f32;
+  int act_mode;            // 0 none, 1 bf16 channels-last via TMA (tmO)
+  const float* snake_a;    // SnakeBeta folded into the activated output (nullptr: plain cast)
+  const float* snake_inv_b;
+};
+
+constexpr int kRawTileBytes = 128 * 128;   // 128 rows x 32 fp32, SWIZZLE_128B
+constexpr int kActTileBytes = 128 * 64;    // 128 rows x 32 bf16, SWIZZLE_64B
+// per-warpgroup output staging, double-buffered; only the tiles a layer needs are carved out
+__host__ __device__ inline int conv_umma2_stage_bytes_per_wg(int raw_mode, int act_mode) {
+  return (raw_mode == 1 ? 2 * kRawTileBytes : 0) + (act_mode == 1 ? 2 * kActTileBytes : 0);
+}
+
+__host__ __device__ inline size_t conv_umma2_smem_bytes(const ConvParams2& p) {
+  return 1024 + 1024 + static_cast<size_t>(p.SA) * p.nbox * p.RB * 128 + static_cast<size_t>(p.SB) * p.NT * 128 +
+         2 * conv_umma2_stage_bytes_per_wg(p.raw_mode, p.act_mode);
+}
+
+__global__ void __launch_bounds__(384, 1)
+conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
+                  const __grid_constant__ ConvParams2 p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* a_empty = a_full + 8;
+  uint64_t* b_full = a_full + 16;
+  uint64_t* b_empty = a_full + 32;
+  uint64_t* t_full = a_full + 48;    // [2] accumulator ready
+  uint64_t* t_empty = a_full + 50;   // [2] accumulator drained (8 epilogue warps arrive)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 52);
+  uint8_t* a_ring = smem + 1024;
+  const uint32_t a_bytes = static_cast<uint32_t>(p.nbox) * p.RB * 128;
+  const uint32_t b_bytes = static_cast<uint32_t>(p.NT) * 128;
+  uint8_t* b_ring = a_ring + static_cast<size_t>(p.SA) * a_bytes;
+  uint8_t* stage_base = b_ring + static_cast<size_t>(p.SB) * b_bytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+    if (p.raw_mode == 1) ptx::prefetch_tmap(&tmR);
+    if (p.act_mode == 1) ptx::prefetch_tmap(&tmO);
+    for (int i = 0; i < p.SA; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < p.SB; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 8); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, p.tmem_cols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int acc_cols = p.MT * p.NT;
+
+  // tile id -> (batch, q tile, output phase, n tile); n fastest so CTAs sharing an A slab run together
+  auto decode = [&](int tile, int& b, int& q0, int& phi, int& n0) {
+    n0 = (tile % p.n_tiles) * p.NT;
+    int r = tile / p.n_tiles;
+    phi = r % p.P_out;
+    r /= p.P_out;
+    q0 = (r % p.q_tiles) * (128 * p.MT);
+    b = r / p.q_tiles;
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int b, q0, phi, n0;
+        decode(tile, b, q0, phi, n0);
+        const int t_lo = p.tap_begin[phi], t_hi = p.tap_begin[phi + 1];
+        for (int ch = 0; ch < p.n_chunks; ++ch) {
+          for (int t = t_lo; t < t_hi; ++t) {
+            const Tap tap = p.taps[t];
+            if (tap.first) {
+              ptx::mbar_wait(&a_empty[as], aph ^ 1u);
+              ptx::mbar_expect_tx(&a_full[as], a_bytes);
+              for (int bx = 0; bx < p.nbox; ++bx)
+                ptx::tma_load_4d(a_ring + static_cast<size_t>(as) * a_bytes + bx * p.RB * 128, &tmA, &a_full[as],
+                                 ch * 64, tap.a_phase, q0 + tap.a_row + bx * p.RB, b);
+              if (++as == p.SA) { as = 0; aph ^= 1u; }
+            }
+            ptx::mbar_wait(&b_empty[bs], bph ^ 1u);
+            ptx::mbar_expect_tx(&b_full[bs], b_bytes);
+            ptx::tma_load_3d(b_ring + static_cast<size_t>(bs) * b_bytes, &tmW, &b_full[bs], ch * 64, n0, tap.w_slab);
+            if (++bs == p.SB) { bs = 0; bph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ UMMA issuer
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::idesc_bf16_f32(128, p.NT);
+      const uint32_t a_base = ptx::smem_u32(a_ring);
+      const uint32_t b_base = ptx::smem_u32(b_ring);
+      int as = 0, bs = 0, cur = 0, acc = 0;
+      uint32_t aph = 0, bph = 0, accph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int phi = (tile / p.n_tiles) % p.P_out;
+        const int t_lo = p.tap_begin[phi], t_hi = p.tap_begin[phi + 1];
+        ptx::mbar_wait(&t_empty[acc], accph ^ 1u);   // epilogue has drained this accumulator buffer
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * acc_cols;
+        for (int ch = 0; ch < p.n_chunks; ++ch) {
+          for (int t = t_lo; t < t_hi; ++t) {
+            const Tap tap = p.taps[t];
+            if (tap.first) {
+              ptx::mbar_wait(&a_full[as], aph);
+              cur = as;
+              if (++as == p.SA) { as = 0; aph ^= 1u; }
+            }
+            ptx::mbar_wait(&b_full[bs], bph);
+            ptx::tc_fence_after();
+            const uint32_t fresh = (ch == 0 && t == t_lo) ? 1u : 0u;
+            for (int m = 0; m < p.MT; ++m) {
+              const uint32_t a_tile = a_base + cur * a_bytes + (tap.shift + 128 * m) * 128;
+              const uint32_t b_tile = b_base + bs * b_bytes;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                ptx::umma_f16(d_tmem + m * p.NT, ptx::smem_desc_sw128(a_tile + k * 32, 0),
+                              ptx::smem_desc_sw128(b_tile + k * 32, 0), idesc, (fresh && k == 0) ? 0u : 1u);
+            }
+            ptx::umma_commit(&b_empty[bs]);
+            if (tap.last) ptx::umma_commit(&a_empty[cur]);
+            if (++bs == p.SB) { bs = 0; bph ^= 1u; }
+          }
+        }
+        ptx::umma_commit(&t_full[acc]);
+        if (++acc == p.acc_stages) { acc = 0; accph ^= 1u; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue (2 warpgroups)
+    const int g = (warp - 4) >> 2;
+    const int quad = warp & 3;
+    const int row = quad * 32 + lane;
+    const int T_out = p.Tq_out * p.P_out;
+    const bool issuer = (quad == 0 && lane == 0);
+    uint8_t* raw_stage = stage_base + g * conv_umma2_stage_bytes_per_wg(p.raw_mode, p.act_mode);
+    uint8_t* act_stage = raw_stage + (p.raw_mode == 1 ? 2 * kRawTileBytes : 0);
+    const int items = p.MT * (p.NT >> 5);
+    int acc = 0, buf = 0;
+    uint32_t accph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int b, q0, phi, n0;
+      decode(tile, b, q0, phi, n0);
+      ptx::mbar_wait(&t_full[acc], accph);
+      ptx::tc_fence_after();
+      const uint32_t acc_tmem = tmem_base + acc * acc_cols + (static_cast<uint32_t>(quad * 32) << 16);
+      for (int item = g; item < items; item += 2) {
+        const int m = item / (p.NT >> 5);
+        const int c0 = (item % (p.NT >> 5)) * 32;
+        const int cbase = n0 + c0;
+        const int q = q0 + m * 128 + row;
+        const bool valid = q < p.Tq_out;
+        const size_t orow = (static_cast<size_t>(b) * T_out + static_cast<size_t>(q) * p.P_out + phi) * p.Cout + cbase;
+        // skip connection first: its HBM latency overlaps the TMEM load and the bias add
+        float4 res[8];
+        if (p.residual && valid) {
+          const float4* rp = reinterpret_cast<const float4*>(p.residual + orow);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) res[j] = __ldg(rp + j);
+        }
+        uint32_t r[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32(acc_tmem + m * p.NT + c0, r);
+        ptx::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+            v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+          }
+        }
+        if (p.residual && valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
+          }
+        }
+        if (p.raw_mode == 2) {
+          // channels-first API output: lanes hold consecutive time steps -> coalesced per channel
+          if (valid) {
+            const size_t t_out = static_cast<size_t>(q) * p.P_out + phi;
+            const size_t o0 = (static_cast<size_t>(b) * p.Cout + cbase) * T_out + t_out;
+            if (p.out_cf_f32) {
+              float* op = static_cast<float*>(p.out_cf) + o0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) op[static_cast<size_t>(j) * T_out] = v[j];
+            } else {
+              __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.out_cf) + o0;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) op[static_cast<size_t>(j) * T_out] = __float2bfloat16(v[j]);
+            }
+          }
+        }
+        if (p.raw_mode == 1 || p.act_mode == 1) {
+          // the staging tiles of `buf` were last handed to TMA two items ago
+          if (issuer) ptx::bulk_wait_read<1>();
+          ptx::named_bar_sync(1 + g, 128);
+          if (p.raw_mode == 1) {
+            uint8_t* rt = raw_stage + buf * kRawTileBytes + row * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(rt + ((j ^ (row & 7)) << 4)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (p.act_mode == 1) {
+            if (p.snake_a) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 a = __ldg(reinterpret_cast<const float4*>(p.snake_a + cbase + j));
+                const float4 ib = __ldg(reinterpret_cast<const float4*>(p.snake_inv_b + cbase + j));
+                v[j] = snake_beta<true>(v[j], a.x, ib.x);
+                v[j + 1] = snake_beta<true>(v[j + 1], a.y, ib.y);
+                v[j + 2] = snake_beta<true>(v[j + 2], a.z, ib.z);
+                v[j + 3] = snake_beta<true>(v[j + 3], a.w, ib.w);
+              }
+            }
+            uint8_t* at = act_stage + buf * kActTileBytes + row * 64;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
+                w[e] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(at + ((j ^ ((row >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          }
+          ptx::fence_proxy_async();
+          ptx::named_bar_sync(1 + g, 128);
+          if (issuer) {
+            if (p.raw_mode == 1) ptx::tma_store_4d(&tmR, raw_stage + buf * kRawTileBytes, cbase, phi, q0 + m * 128, b);
+            if (p.act_mode == 1) ptx::tma_store_4d(&tmO, act_stage + buf * kActTileBytes, cbase, phi, q0 + m * 128, b);
+            ptx::bulk_commit();
+          }
+          buf ^= 1;
+        }
+      }
+      // accumulator buffer fully read: hand it back to the UMMA issuer
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&t_empty[acc]);
+      if (++acc == p.acc_stages) { acc = 0; accph ^= 1u; }
+    }
+    if (issuer) ptx::bulk_wait<0>();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+}  // namespace kvae

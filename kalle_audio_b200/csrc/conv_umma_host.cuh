@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "conv_umma.cuh"
+#include "conv_umma2.cuh"
 
 namespace kvae {
 
@@ -159,6 +160,25 @@ inline bool make_w_tmap(CUtensorMap* m, const void* w, int nslab, int Cout, int 
   return true;
 }
 
+// Output tensor [B, T, C] viewed as [B, T/P, P, C] for TMA stores of 128-row x 32-channel blocks:
+// fp32 blocks are 128 B wide (SWIZZLE_128B), bf16 blocks 64 B (SWIZZLE_64B).
+inline bool make_out_tmap(CUtensorMap* m, const void* y, int B, int T, int C, int P, bool f32, std::string& err) {
+  auto enc = tmap_encoder();
+  if (!enc) { err = "cuTensorMapEncodeTiled unavailable"; return false; }
+  if (T % P) { err = "output length not divisible by stride"; return false; }
+  const cuuint64_t es = f32 ? 4 : 2;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)P, (cuuint64_t)(T / P), (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)P * C * es, (cuuint64_t)T * C * es};
+  cuuint32_t box[4] = {32, 1, 128, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                   const_cast<void*>(y), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { err = "cuTensorMapEncodeTiled(out) failed: " + std::to_string((int)r); return false; }
+  return true;
+}
+
 // ------------------------------------------------------------------ launch
 struct ConvEpilogue {
   const float* bias = nullptr;
@@ -253,6 +273,123 @@ inline bool prepare_conv_umma(const ConvGeom& g, const __nv_bfloat16* x, int B, 
   L.smem = conv_umma_smem_bytes(p);
   L.T_out = T_out;
   return true;
+}
+
+// ------------------------------------------------------------------ persistent kernel (conv_umma2.cuh)
+struct ConvLaunch2 {
+  CUtensorMap tmA, tmW, tmR, tmO;
+  ConvParams2 p;
+  int grid = 0;
+  size_t smem = 0;
+  int T_out = 0;
+};
+
+struct ConvTuning2 {
+  int MT = 0, NT = 0, acc_stages = 0;   // 0 = auto
+  int max_ctas = 0;                     // 0 = one per SM
+};
+
+inline int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ep.out_raw: fp32 channels-last via TMA unless ep.out_raw_cf (then channels-first direct, any dtype).
+// ep.residual must be fp32 channels-last.
+inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B, int T_in,
+                               const __nv_bfloat16* wpacked, const ConvEpilogue& ep, const ConvTuning2& tune,
+                               ConvLaunch2& L, std::string& err) {
+  if (!umma_supported(g)) { err = "channel counts not multiples of 64"; return false; }
+  if (ep.residual && !ep.residual_f32) { err = "residual must be fp32"; return false; }
+  if (ep.out_raw && !ep.out_raw_cf && !ep.out_raw_f32) { err = "channels-last raw output must be fp32"; return false; }
+  TapPlan tp;
+  if (!build_taps(g, false, tp, err)) return false;
+  const int T_out = g.out_len(T_in);
+  if (T_out <= 0 || T_out % tp.P_out) { err = "bad output length"; return false; }
+  ConvParams2& p = L.p;
+  std::memset(&p, 0, sizeof(p));
+  p.B = B;
+  p.P_out = tp.P_out;
+  p.Tq_out = T_out / tp.P_out;
+  p.Cout = g.Cout;
+  p.n_chunks = g.Cin / 64;
+  p.raw_mode = ep.out_raw ? (ep.out_raw_cf ? 2 : 1) : 0;
+  p.act_mode = ep.out_act ? 1 : 0;
+  const size_t stage = 2 * static_cast<size_t>(conv_umma2_stage_bytes_per_wg(p.raw_mode, p.act_mode));
+  const size_t budget = 227 * 1024 - 2048 - stage;
+  // candidate tilings, best first: double-buffered accumulators when they fit the 512 TMEM columns
+  struct Cand { int MT, NT, acc; };
+  std::vector<Cand> cands;
+  if (tune.MT || tune.NT || tune.acc_stages) {
+    const int NT = tune.NT ? tune.NT : pick_nt(g.Cout);
+    const int MT = tune.MT ? tune.MT : 2;
+    cands.push_back({MT, NT, tune.acc_stages ? tune.acc_stages : (2 * MT * NT <= 512 ? 2 : 1)});
+  } else {
+    const int mt = p.Tq_out > 128 ? 2 : 1;
+    if (g.Cout % 256 == 0 && g.Cout >= 512) cands.push_back({mt, 256, mt * 256 * 2 <= 512 ? 2 : 1});
+    if (g.Cout % 128 == 0) cands.push_back({mt, 128, 2});
+    if (g.Cout % 128 == 0) cands.push_back({1, 128, 2});
+    cands.push_back({mt, 64, 2});
+    cands.push_back({1, 64, 2});
+  }
+  bool ok = false;
+  for (const Cand& c : cands) {
+    if (g.Cout % c.NT || c.NT % 32 || c.NT > 256 || c.acc * c.MT * c.NT > 512) continue;
+    const int rows = 128 * c.MT + tp.span;
+    const int nbox = (rows + 255) / 256;
+    const int RB = (((rows + nbox - 1) / nbox) + 7) & ~7;
+    if (RB > 256) continue;
+    const size_t a_bytes = static_cast<size_t>(nbox) * RB * 128, b_bytes = static_cast<size_t>(c.NT) * 128;
+    if (2 * a_bytes + 2 * b_bytes > budget) continue;
+    p.MT = c.MT; p.NT = c.NT; p.acc_stages = c.acc; p.nbox = nbox; p.RB = RB;
+    p.SA = 2;
+    p.SB = static_cast<int>(std::min<size_t>(8, (budget - 2 * a_bytes) / b_bytes));
+    while (p.SA < 4 && (p.SA + 1) * a_bytes + p.SB * b_bytes <= budget) ++p.SA;
+    ok = true;
+    break;
+  }
+  if (!ok) { err = "no tiling fits shared memory"; return false; }
+  int cols = 32;
+  while (cols < p.acc_stages * p.MT * p.NT) cols <<= 1;
+  p.tmem_cols = cols;
+  for (int i = 0; i <= kMaxPhases; ++i) p.tap_begin[i] = tp.tap_begin[i];
+  for (size_t i = 0; i < tp.taps.size(); ++i) p.taps[i] = tp.taps[i];
+  p.q_tiles = (p.Tq_out + 128 * p.MT - 1) / (128 * p.MT);
+  p.n_tiles = g.Cout / p.NT;
+  p.total_tiles = p.q_tiles * p.n_tiles * tp.P_out * B;
+  p.bias = ep.bias;
+  p.residual = static_cast<const float*>(ep.residual);
+  p.out_cf = (p.raw_mode == 2) ? ep.out_raw : nullptr;
+  p.out_cf_f32 = ep.out_raw_f32;
+  p.snake_a = ep.snake_a;
+  p.snake_inv_b = ep.snake_inv_b;
+  if (!make_act_tmap(&L.tmA, x, B, T_in, g.Cin, tp.P_in, p.RB, err)) return false;
+  if (!make_w_tmap(&L.tmW, wpacked, g.K, g.Cout, g.Cin, p.NT, err)) return false;
+  if (p.raw_mode == 1) { if (!make_out_tmap(&L.tmR, ep.out_raw, B, T_out, g.Cout, tp.P_out, true, err)) return false; }
+  else L.tmR = L.tmA;
+  if (p.act_mode == 1) { if (!make_out_tmap(&L.tmO, ep.out_act, B, T_out, g.Cout, tp.P_out, false, err)) return false; }
+  else L.tmO = L.tmA;
+  const int ctas = tune.max_ctas ? tune.max_ctas : sm_count();
+  L.grid = std::min(p.total_tiles, ctas);
+  L.smem = conv_umma2_smem_bytes(p);
+  L.T_out = T_out;
+  return true;
+}
+
+inline cudaError_t launch_conv_umma2(const ConvLaunch2& L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  conv_umma2_kernel<<<L.grid, 384, L.smem, stream>>>(L.tmA, L.tmW, L.tmR, L.tmO, L.p);
+  return cudaGetLastError();
 }
 
 inline cudaError_t launch_conv_umma(const ConvLaunch& L, cudaStream_t stream) {

@@ -5,14 +5,17 @@ LOG=gpurun_out/probe.log
 : > $LOG
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv >> $LOG 2>&1
 read NC NP < <(./build/umma_probe count)
+VARIANTS=${VARIANTS:-"1 3 4 5"}
 for c in $(seq 0 $((NC-1))); do
-  for v in 0 1 2; do
+  for v in $VARIANTS; do
     timeout 60 ./build/umma_probe $c $v >> $LOG 2>&1
     echo "exit $? (case $c variant $v)" >> $LOG
   done
 done
-for p in $(seq 0 $((NP-1))); do
-  timeout 120 ./build/umma_probe perf $p >> $LOG 2>&1
-  echo "exit $? (perf $p)" >> $LOG
+# perf: <idx> <kernel version 1|2|3(v2, forced tile)> <epilogue 0 cast | 1 bias+snake | 2 +residual+raw>
+for spec in "0 1 1" "0 2 1" "1 1 2" "1 2 2" "2 1 1" "2 2 1" "2 3 1" "4 1 1" "4 2 1" "4 3 1" "5 1 1" "5 2 1" "5 3 1" \
+            "6 1 2" "6 2 2" "6 3 2" "7 1 2" "7 2 2"; do
+  timeout 120 ./build/umma_probe perf $spec >> $LOG 2>&1
+  echo "exit $? (perf $spec)" >> $LOG
 done
-grep -E "RESULT|PERF|exit [1-9]" $LOG | tail -80
+grep -E "RESULT|PERF|exit [1-9]|prepare failed|timeout|rror" $LOG | cut -c1-170 | tail -100

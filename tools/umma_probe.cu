@@ -140,13 +140,30 @@ static int run_case(int idx, int variant) {
     ep.snake_a = dsa;
     ep.snake_inv_b = dsib;
   }
+  std::string err;
+  if (variant >= 3) {
+    // persistent double-buffered kernel; variant 4 forces a tiny grid so every CTA loops over many tiles
+    ConvTuning2 tune2;
+    if (variant == 4) tune2.max_ctas = 3;
+    if (variant == 5) { tune2.MT = 1; tune2.NT = c.NT > 128 ? 128 : c.NT; }
+    ConvLaunch2 L2;
+    if (!prepare_conv_umma2(g, dx, c.B, c.T, dw, ep, tune2, L2, err)) {
+      printf("CASE %d %s variant %d: prepare failed: %s\n", idx, c.name, variant, err.c_str());
+      return 3;
+    }
+    printf("CASE %d %s variant %d: grid %d smem %zu MT %d NT %d acc %d RB %d nbox %d SA %d SB %d tmem %d tiles %d\n",
+           idx, c.name, variant, L2.grid, L2.smem, L2.p.MT, L2.p.NT, L2.p.acc_stages, L2.p.RB, L2.p.nbox, L2.p.SA,
+           L2.p.SB, L2.p.tmem_cols, L2.p.total_tiles);
+    fflush(stdout);
+    CK(launch_conv_umma2(L2, 0));
+    CK(cudaDeviceSynchronize());
+  } else {
   ConvTuning tune;
   tune.MT = c.MT;
   tune.NT = c.NT;
   tune.per_tap_slab = (variant == 0);
   tune.desc_mode = (variant == 2) ? 1 : 0;
   ConvLaunch L;
-  std::string err;
   if (!prepare_conv_umma(g, dx, c.B, c.T, dw, ep, tune, L, err)) {
     printf("CASE %d %s variant %d: prepare failed: %s\n", idx, c.name, variant, err.c_str());
     return 3;
@@ -157,6 +174,7 @@ static int run_case(int idx, int variant) {
   fflush(stdout);
   CK(launch_conv_umma(L, 0));
   CK(cudaDeviceSynchronize());
+  }
   std::vector<float> raw(nout);
   std::vector<__nv_bfloat16> act(nout);
   CK(cudaMemcpy(raw.data(), draw, nout * 4, cudaMemcpyDeviceToHost));
@@ -217,7 +235,7 @@ static const Perf kPerf[] = {
 };
 static const int kNumPerf = sizeof(kPerf) / sizeof(kPerf[0]);
 
-static int run_perf(int idx) {
+static int run_perf(int idx, int ver, int epi) {
   const Perf& c = kPerf[idx];
   const ConvGeom& g = c.g;
   const int T_out = g.out_len(c.T);
@@ -227,27 +245,64 @@ static int run_perf(int idx) {
   CK(cudaMalloc(&dx, nin * 2));
   CK(cudaMalloc(&dw, nw * 2));
   CK(cudaMalloc(&dact, nout * 2));
-  CK(cudaMemset(dx, 0, nin * 2));
-  CK(cudaMemset(dw, 0, nw * 2));
+  {  // realistic operand values (power draw and clocks depend on the data)
+    std::vector<__nv_bfloat16> h(1 << 20);
+    std::mt19937 rng(7);
+    std::normal_distribution<float> nd(0.f, 1.f);
+    for (auto& v : h) v = __float2bfloat16(nd(rng));
+    for (size_t o = 0; o < nin; o += h.size())
+      CK(cudaMemcpy(dx + o, h.data(), std::min(h.size(), nin - o) * 2, cudaMemcpyHostToDevice));
+    for (auto& v : h) v = __float2bfloat16(nd(rng) * 0.03f);
+    for (size_t o = 0; o < nw; o += h.size())
+      CK(cudaMemcpy(dw + o, h.data(), std::min(h.size(), nw - o) * 2, cudaMemcpyHostToDevice));
+  }
+  float *dbias, *dsa, *dsib, *dres = nullptr, *draw = nullptr;
+  CK(cudaMalloc(&dbias, g.Cout * 4));
+  CK(cudaMalloc(&dsa, g.Cout * 4));
+  CK(cudaMalloc(&dsib, g.Cout * 4));
+  {
+    std::vector<float> ones(g.Cout, 1.0f), zeros(g.Cout, 0.01f);
+    CK(cudaMemcpy(dbias, zeros.data(), g.Cout * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dsa, ones.data(), g.Cout * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dsib, ones.data(), g.Cout * 4, cudaMemcpyHostToDevice));
+  }
   ConvEpilogue ep;
   ep.out_act = dact;
-  ConvTuning tune;
-  tune.MT = c.MT;
-  tune.NT = c.NT;
-  ConvLaunch L;
-  std::string err;
-  if (!prepare_conv_umma(g, dx, c.B, c.T, dw, ep, tune, L, err)) {
-    printf("PERF %s: prepare failed: %s\n", c.name, err.c_str());
-    return 3;
+  if (epi >= 1) { ep.bias = dbias; ep.snake_a = dsa; ep.snake_inv_b = dsib; }
+  if (epi >= 2) {
+    CK(cudaMalloc(&dres, nout * 4));
+    CK(cudaMalloc(&draw, nout * 4));
+    CK(cudaMemset(dres, 0, nout * 4));
+    ep.residual = dres; ep.residual_f32 = 1; ep.out_raw = draw; ep.out_raw_f32 = 1;
   }
+  std::string err;
+  ConvLaunch L;
+  ConvLaunch2 L2;
+  if (ver == 1) {
+    ConvTuning tune;
+    tune.MT = c.MT;
+    tune.NT = c.NT;
+    if (!prepare_conv_umma(g, dx, c.B, c.T, dw, ep, tune, L, err)) {
+      printf("PERF %s: prepare failed: %s\n", c.name, err.c_str());
+      return 3;
+    }
+  } else {
+    ConvTuning2 tune2;
+    if (ver == 3) { tune2.MT = c.MT; tune2.NT = c.NT; }
+    if (!prepare_conv_umma2(g, dx, c.B, c.T, dw, ep, tune2, L2, err)) {
+      printf("PERF %s: prepare failed: %s\n", c.name, err.c_str());
+      return 3;
+    }
+  }
+  auto launch = [&]() { return ver == 1 ? launch_conv_umma(L, 0) : launch_conv_umma2(L2, 0); };
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  for (int i = 0; i < 3; ++i) CK(launch_conv_umma(L, 0));
+  for (int i = 0; i < 3; ++i) CK(launch());
   CK(cudaDeviceSynchronize());
   const int iters = 10;
   CK(cudaEventRecord(e0));
-  for (int i = 0; i < iters; ++i) CK(launch_conv_umma(L, 0));
+  for (int i = 0; i < iters; ++i) CK(launch());
   CK(cudaEventRecord(e1));
   CK(cudaDeviceSynchronize());
   float ms;
@@ -255,10 +310,14 @@ static int run_perf(int idx) {
   ms /= iters;
   const double taps_eff = (g.kind == kConv) ? (double)g.K * T_out : (double)g.K * c.T;
   const double flops = 2.0 * c.B * taps_eff * g.Cin * g.Cout;
-  const double bytes = (nin + nout) * 2.0;
-  printf("PERF %s: %.3f ms  %.1f TFLOP/s  %.1f GB/s (act in+out)  grid (%d,%d,%d) smem %zu SA %d SB %d\n",
-         c.name, ms, flops / ms * 1e-9, bytes / ms * 1e-6, L.grid.x, L.grid.y, L.grid.z, L.smem, L.p.SA,
-         L.p.SB);
+  const double bytes = (nin + nout) * 2.0 + (epi >= 2 ? nout * 8.0 : 0.0);
+  if (ver == 1)
+    printf("PERF v1 epi%d %s: %.3f ms  %.1f TFLOP/s  %.1f GB/s  MT %d NT %d smem %zu SA %d SB %d\n", epi, c.name, ms,
+           flops / ms * 1e-9, bytes / ms * 1e-6, L.p.MT, L.p.NT, L.smem, L.p.SA, L.p.SB);
+  else
+    printf("PERF v%d epi%d %s: %.3f ms  %.1f TFLOP/s  %.1f GB/s  MT %d NT %d acc %d grid %d smem %zu SA %d SB %d\n", ver,
+           epi, c.name, ms, flops / ms * 1e-9, bytes / ms * 1e-6, L2.p.MT, L2.p.NT, L2.p.acc_stages, L2.grid, L2.smem,
+           L2.p.SA, L2.p.SB);
   return 0;
 }
 
@@ -266,7 +325,8 @@ int main(int argc, char** argv) {
   if (argc >= 3 && std::string(argv[1]) == "perf") {
     int idx = atoi(argv[2]);
     if (idx < 0 || idx >= kNumPerf) return 4;
-    return run_perf(idx);
+    const int ver = argc >= 4 ? atoi(argv[3]) : 1, epi = argc >= 5 ? atoi(argv[4]) : 0;
+    return run_perf(idx, ver, epi);
   }
   if (argc >= 2 && std::string(argv[1]) == "count") {
     printf("%d %d\n", kNumCases, kNumPerf);
