@@ -15,6 +15,7 @@
 
 #include "conv_umma.cuh"    // snake_beta
 #include "elementwise.cuh"  // ld_elem / st_elem
+#include "ptx.cuh"
 
 namespace kvae {
 
@@ -26,74 +27,144 @@ struct WaveOutParams {
   void* y;                // [B, COUT, T]
   int y_f32;
   int T, Cin, tanh_out;
+  int B, tiles_per_clip, total_tiles;
 };
 
-constexpr int kWaveOutTile = 128;
+constexpr int kWaveOutTile = 128;              // outputs per tile
+constexpr int kWaveOutRows = kWaveOutTile + 6; // staged input rows per tile
+constexpr int kWaveOutBufs = 3;
 
-// grid (ceil(T/128), B), block 128.  Shared: act[Cin][135] (+ weights [7][Cin][COUT], partials [4][128][COUT]).
-template <int COUT>
-__global__ void __launch_bounds__(128) conv_wave_out_kernel(const WaveOutParams p) {
-  constexpr int TT = kWaveOutTile, RS = TT + 6, RSP = RS + 1;   // 135: odd stride -> conflict-free both ways
-  extern __shared__ float sm_wo[];
-  float* act = sm_wo;                              // [Cin][RSP]
-  float* ws = act + p.Cin * RSP;                   // [7][Cin][COUT]
-  float* part = ws + 7 * p.Cin * COUT;             // [4][TT][COUT]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y;
-  const int t0 = blockIdx.x * TT;
-  for (int i = threadIdx.x; i < 7 * p.Cin * COUT; i += 128) ws[i] = p.w[i];
-  // stage SnakeBeta(x) for rows t0-3 .. t0+TT+2; lanes walk channels (coalesced 128 B per row segment)
-  for (int r = warp; r < RS; r += 4) {
-    const int t = t0 - 3 + r;
-    const bool in = (t >= 0 && t < p.T);
-    const float* xr = p.x + (static_cast<size_t>(b) * p.T + (in ? t : 0)) * p.Cin;
-    for (int ci = lane; ci < p.Cin; ci += 32) {
-      float v = 0.f;
-      if (in) v = snake_beta<true>(xr[ci], p.pro_a[ci], p.pro_inv_b[ci]);
-      act[ci * RSP + r] = v;
-    }
-  }
-  __syncthreads();
-  // each warp reduces a quarter of the channels for all 128 outputs; lane owns outputs lane + 32*j
-  float acc[4][COUT];
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int c = 0; c < COUT; ++c) acc[j][c] = 0.f;
-  const int cpw = p.Cin / 4;
-  for (int ci = warp * cpw; ci < (warp + 1) * cpw; ++ci) {
-    const float* a = act + ci * RSP + lane;
-#pragma unroll
-    for (int k = 0; k < 7; ++k) {
-      float wv[COUT];
-#pragma unroll
-      for (int c = 0; c < COUT; ++c) wv[c] = ws[(k * p.Cin + ci) * COUT + c];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float xv = a[32 * j + k];
-#pragma unroll
-        for (int c = 0; c < COUT; ++c) acc[j][c] = fmaf(xv, wv[c], acc[j][c]);
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int c = 0; c < COUT; ++c) part[(warp * TT + lane + 32 * j) * COUT + c] = acc[j][c];
-  __syncthreads();
-  for (int i = threadIdx.x; i < TT * COUT; i += 128) {
-    const int c = i / TT, tt = i % TT;            // consecutive threads -> consecutive time (coalesced store)
-    const int t = t0 + tt;
-    if (t >= p.T) continue;
-    float v = part[(0 * TT + tt) * COUT + c] + part[(1 * TT + tt) * COUT + c] + part[(2 * TT + tt) * COUT + c] +
-              part[(3 * TT + tt) * COUT + c];
-    if (p.tanh_out) v = tanhf(v);
-    st_elem(p.y, (static_cast<size_t>(b) * COUT + c) * p.T + t, p.y_f32, v);
-  }
+inline size_t wave_out_smem(int Cin) {
+  return 1024 + static_cast<size_t>(kWaveOutBufs) * kWaveOutRows * Cin * sizeof(float);
 }
 
-inline size_t wave_out_smem(int Cin, int Cout) {
-  return (static_cast<size_t>(Cin) * (kWaveOutTile + 7) + 7 * Cin * Cout + 4 * kWaveOutTile * Cout) * sizeof(float);
+// Persistent HBM-streaming kernel: one CTA per SM walks over 128-sample output tiles.  The 134 input rows a
+// tile needs are CONTIGUOUS in the channels-last stream, so a producer thread fetches them with bulk async
+// copies into a 3-deep shared-memory ring (mbarrier full/empty), keeping ~130 KB per SM in flight; 8 compute
+// warps each own 16 outputs: lane l holds channels 4l..4l+3 (one conflict-free 16-byte shared load per row),
+// keeps a 7-row register window with SnakeBeta applied once per loaded element, keeps its 7x4xCOUT weights in
+// registers, and the 32 lanes' partial sums are combined by a transposing butterfly (31 shuffles per 32 sums).
+// Requires Cin == 128.  grid = min(tiles, #SM), block = 288 (8 compute warps + 1 producer warp).
+template <int COUT>
+__global__ void __launch_bounds__(288, 1) conv_wave_out_kernel(const WaveOutParams p) {
+  constexpr int TT = kWaveOutTile, RS = kWaveOutRows, NB = kWaveOutBufs, CIN = 128;
+  extern __shared__ uint8_t sm_wo_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(sm_wo_raw);
+  uint8_t* smem = sm_wo_raw + (((raw_addr + 127u) & ~127u) - raw_addr);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + NB;
+  float* ring = reinterpret_cast<float*>(smem + 128);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NB; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 8); }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+
+  if (warp == 8) {
+    // ---------------------------------------------------------- producer
+    if (lane == 0) {
+      int buf = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int b = tile / p.tiles_per_clip;
+        const int t0 = (tile % p.tiles_per_clip) * TT;
+        const int r_lo = max(0, 3 - t0);                       // first staged row that exists
+        const int r_hi = min(RS, p.T - (t0 - 3));              // one past the last
+        ptx::mbar_wait(&empty[buf], ph ^ 1u);
+        ptx::mbar_expect_tx(&full[buf], static_cast<uint32_t>(r_hi - r_lo) * CIN * 4);
+        const float* src = p.x + (static_cast<size_t>(b) * p.T + (t0 - 3 + r_lo)) * CIN;
+        float* dst = ring + static_cast<size_t>(buf) * RS * CIN + r_lo * CIN;
+        for (int r = r_lo; r < r_hi; r += 32) {
+          const int n = min(32, r_hi - r);
+          ptx::bulk_load_1d(dst, src, static_cast<uint32_t>(n) * CIN * 4, &full[buf]);
+          dst += 32 * CIN;
+          src += 32 * CIN;
+        }
+        if (++buf == NB) { buf = 0; ph ^= 1u; }
+      }
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------ compute warps
+  float w[7][4][COUT];
+#pragma unroll
+  for (int k = 0; k < 7; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) w[k][e][c] = __ldg(p.w + (static_cast<size_t>(k) * CIN + 4 * lane + e) * COUT + c);
+  const float4 sa = __ldg(reinterpret_cast<const float4*>(p.pro_a + 4 * lane));
+  const float4 sib = __ldg(reinterpret_cast<const float4*>(p.pro_inv_b + 4 * lane));
+  int buf = 0;
+  uint32_t ph = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const int b = tile / p.tiles_per_clip;
+    const int t0 = (tile % p.tiles_per_clip) * TT;
+    ptx::mbar_wait(&full[buf], ph);
+    const float* tile_s = ring + static_cast<size_t>(buf) * RS * CIN + 4 * lane;
+    auto load_row = [&](int r) -> float4 {   // staged row r <-> time t0 - 3 + r; zero outside the clip (conv padding)
+      const int t = t0 - 3 + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t >= 0 && t < p.T) {
+        v = *reinterpret_cast<const float4*>(tile_s + r * CIN);
+        v.x = snake_beta<true>(v.x, sa.x, sib.x);
+        v.y = snake_beta<true>(v.y, sa.y, sib.y);
+        v.z = snake_beta<true>(v.z, sa.z, sib.z);
+        v.w = snake_beta<true>(v.w, sa.w, sib.w);
+      }
+      return v;
+    };
+    const int o0 = warp * 16;                 // this warp's first output inside the tile
+    float4 win[7];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) win[k + 1] = load_row(o0 + k);
+    float acc[16 * COUT];
+#pragma unroll
+    for (int o = 0; o < 16; ++o) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) win[k] = win[k + 1];
+      win[6] = load_row(o0 + o + 6);
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) {
+        float a = 0.f;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+          a = fmaf(win[k].x, w[k][0][c], a);
+          a = fmaf(win[k].y, w[k][1][c], a);
+          a = fmaf(win[k].z, w[k][2][c], a);
+          a = fmaf(win[k].w, w[k][3][c], a);
+        }
+        acc[c * 16 + o] = a;
+      }
+    }
+    // this warp no longer reads the staged tile
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&empty[buf]);
+    if (++buf == NB) { buf = 0; ph ^= 1u; }
+    // transposing butterfly: afterwards lane L holds the sum over all lanes of acc[L % (16*COUT)]
+    constexpr int NV = 16 * COUT;             // 16 or 32 values
+#pragma unroll
+    for (int s = NV / 2; s >= 1; s >>= 1) {
+#pragma unroll
+      for (int i = 0; i < s; ++i) {
+        const bool up = (lane & s) != 0;
+        const float send = up ? acc[i] : acc[i + s];
+        const float keep = up ? acc[i + s] : acc[i];
+        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+      }
+    }
+    float total = acc[0];
+    if (COUT == 1) total += __shfl_xor_sync(0xffffffffu, total, 16);   // 16 values: the two half-warps hold halves
+    const int idx = lane & (NV - 1);
+    const int c = idx / 16, o = idx % 16;
+    const int t = t0 + o0 + o;
+    if (t < p.T && (COUT == 2 || lane < 16)) {
+      if (p.tanh_out) total = tanhf(total);
+      st_elem(p.y, (static_cast<size_t>(b) * COUT + c) * p.T + t, p.y_f32, total);
+    }
+  }
 }
 
 struct WaveInParams {

@@ -12,6 +12,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -101,7 +102,9 @@ struct Layout {
 };
 
 struct PreparedRun {
-  std::vector<ConvLaunch> umma;     // per step (valid when that step is tensor-core)
+  std::vector<ConvLaunch> umma;     // per step (valid when that step is tensor-core, KVAE_CONV_V1=1)
+  std::vector<ConvLaunch2> umma2;   // per step (valid when that step is tensor-core; persistent kernel)
+  bool use_v1 = false;
   std::vector<DirectParams> direct; // per step (valid otherwise)
   std::vector<dim3> direct_grid;
   std::vector<int> direct_cfg;      // 0: 32x64 tile, 1: 128x4 tile
@@ -319,6 +322,11 @@ bool prepare_run(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R, std
   const int n = static_cast<int>(p->steps.size());
   if (!make_layout(p, B, T, R.layout, err)) return false;
   R.umma.resize(n);
+  R.umma2.resize(n);
+  {
+    const char* e = getenv("KVAE_CONV_V1");   // development switch: the non-persistent first-generation kernel
+    R.use_v1 = e && e[0] == '1';
+  }
   R.direct.resize(n);
   R.direct_grid.resize(n);
   R.direct_cfg.assign(n, 0);
@@ -344,7 +352,7 @@ bool prepare_run(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R, std
     if (s.residual_from >= 0 && !res) { err = "internal: residual tensor missing"; return false; }
     const bool k7same = c.g.kind == kConv && c.g.K == 7 && c.g.stride == 1 && c.g.dilation == 1 && c.g.pad == 3;
     if (!c.umma && p->precision == KVAE_PREC_BF16 && k7same && last && k > 0 && c.g.Cout <= 2 && !c.has_bias &&
-        c.g.Cin % 32 == 0 && c.g.Cin <= 256 && s.pre_snake >= 0 && !res) {
+        c.g.Cin == 128 && s.pre_snake >= 0 && !res) {
       // decoder tail (conv_edge.cuh)
       WaveOutParams& w = R.wave_out[k];
       w.x = static_cast<const float*>(tptr(1 + 2 * (k - 1)));
@@ -397,10 +405,17 @@ bool prepare_run(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R, std
         ep.snake_a = p->snakes[s.epi_snake].a;
         ep.snake_inv_b = p->snakes[s.epi_snake].inv_b;
       }
-      ConvTuning tune;
-      if (!prepare_conv_umma(c.g, static_cast<const __nv_bfloat16*>(in), B, static_cast<int>(T_in), c.w_umma, ep,
-                             tune, R.umma[k], err))
-        return false;
+      if (R.use_v1) {
+        ConvTuning tune;
+        if (!prepare_conv_umma(c.g, static_cast<const __nv_bfloat16*>(in), B, static_cast<int>(T_in), c.w_umma, ep,
+                               tune, R.umma[k], err))
+          return false;
+      } else {
+        ConvTuning2 tune;
+        if (!prepare_conv_umma2(c.g, static_cast<const __nv_bfloat16*>(in), B, static_cast<int>(T_in), c.w_umma, ep,
+                                tune, R.umma2[k], err))
+          return false;
+      }
     } else {
       DirectParams& d = R.direct[k];
       std::memset(&d, 0, sizeof(d));
@@ -467,19 +482,22 @@ bool prepare_run(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R, std
   return true;
 }
 
-cudaError_t launch_wave_out(const WaveOutParams& w, int Cout, int B, cudaStream_t st) {
-  const size_t smem = wave_out_smem(w.Cin, Cout);
+cudaError_t launch_wave_out(WaveOutParams& w, int Cout, int B, cudaStream_t st) {
+  const size_t smem = wave_out_smem(w.Cin);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wave_out_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_wave_out_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_wave_out_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      e = cudaFuncSetAttribute(conv_wave_out_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  dim3 grid((w.T + kWaveOutTile - 1) / kWaveOutTile, B);
-  if (Cout == 1) conv_wave_out_kernel<1><<<grid, 128, smem, st>>>(w);
-  else conv_wave_out_kernel<2><<<grid, 128, smem, st>>>(w);
+  w.B = B;
+  w.tiles_per_clip = (w.T + kWaveOutTile - 1) / kWaveOutTile;
+  w.total_tiles = w.tiles_per_clip * B;
+  const int grid = std::min(w.total_tiles, sm_count());
+  if (Cout == 1) conv_wave_out_kernel<1><<<grid, 288, smem, st>>>(w);
+  else conv_wave_out_kernel<2><<<grid, 288, smem, st>>>(w);
   return cudaGetLastError();
 }
 
@@ -556,6 +574,13 @@ int run_plan(kvae_plan* p, const void* in, int in_dtype, void* out, int out_dtyp
       w.x = in;
       w.x_f32 = (in_dtype == KVAE_F32);
       KV_CUDA(launch_wave_in(w, c.g.Cin, B, st));
+    } else if (c.umma && !R.use_v1) {
+      ConvLaunch2& L = R.umma2[k];
+      if (k == n - 1) {
+        L.p.out_cf = out;
+        L.p.out_cf_f32 = (out_dtype == KVAE_F32);
+      }
+      KV_CUDA(launch_conv_umma2(L, st));
     } else if (c.umma) {
       ConvLaunch& L = R.umma[k];
       if (k == n - 1) {
