@@ -7,11 +7,12 @@
 //     issuer starts tile i+1 as soon as its operands land while the epilogue drains tile i;
 //   * 8 epilogue warps (two warpgroups, each covering the 128 TMEM lanes) split a tile's 32-column
 //     blocks between them;
-//   * outputs leave through TMA stores: a thread writes its row of a block into a swizzled
-//     shared-memory tile (conflict-free), one elected thread issues cp.async.bulk.tensor stores, and
-//     the bulk-group mechanism recycles the two staging tiles -- every HBM write is a full line and no
-//     thread waits for it;
-//   * the ResidualUnit skip (fp32 stream) is fetched with batched 16-byte loads ahead of the math.
+//   * every epilogue warp runs its own little pipeline over 32-row x 32-channel blocks, with no
+//     block-level barrier: lane 0 prefetches the block's ResidualUnit skip (fp32 stream) with a TMA
+//     load one block ahead, every lane adds its row, writes the result IN PLACE into the same swizzled
+//     shared-memory block (conflict-free) plus the SnakeBeta-activated bf16 block, and lane 0 hands both
+//     to TMA stores; the bulk-group mechanism recycles the blocks.  Every HBM access is a full line
+//     and no thread waits on a store.
 //
 // Warp roles (384 threads): warp 0 TMA producer, warp 1 UMMA issuer, warp 2 TMEM allocator, warp 3 idle,
 // warps 4-11 epilogue.
@@ -46,22 +47,26 @@ struct ConvParams2 {
   const float* snake_inv_b;
 };
 
-constexpr int kRawTileBytes = 128 * 128;   // 128 rows x 32 fp32, SWIZZLE_128B
-constexpr int kActTileBytes = 128 * 64;    // 128 rows x 32 bf16, SWIZZLE_64B
-// per-warpgroup output staging, double-buffered; only the tiles a layer needs are carved out
-__host__ __device__ inline int conv_umma2_stage_bytes_per_wg(int raw_mode, int act_mode) {
-  return (raw_mode == 1 ? 2 * kRawTileBytes : 0) + (act_mode == 1 ? 2 * kActTileBytes : 0);
+constexpr int kRawBlkBytes = 32 * 128;   // 32 rows x 32 fp32, SWIZZLE_128B
+constexpr int kActBlkBytes = 32 * 64;    // 32 rows x 32 bf16, SWIZZLE_64B
+// per-epilogue-warp staging: a ring of fp32 blocks (3 deep when the skip connection is prefetched into
+// it, else 2) and two bf16 blocks; only what a layer needs is carved out
+__host__ __device__ inline int conv_umma2_raw_slots(int raw_mode, bool residual) {
+  return (raw_mode == 1 || residual) ? (residual ? 3 : 2) : 0;
+}
+__host__ __device__ inline int conv_umma2_stage_bytes_per_warp(int raw_mode, int act_mode, bool residual) {
+  return conv_umma2_raw_slots(raw_mode, residual) * kRawBlkBytes + (act_mode == 1 ? 2 * kActBlkBytes : 0);
 }
 
 __host__ __device__ inline size_t conv_umma2_smem_bytes(const ConvParams2& p) {
   return 1024 + 1024 + static_cast<size_t>(p.SA) * p.nbox * p.RB * 128 + static_cast<size_t>(p.SB) * p.NT * 128 +
-         2 * conv_umma2_stage_bytes_per_wg(p.raw_mode, p.act_mode);
+         8 * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, p.residual != nullptr);
 }
 
 __global__ void __launch_bounds__(384, 1)
 conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
-                  const __grid_constant__ ConvParams2 p) {
+                  const __grid_constant__ CUtensorMap tmX, const __grid_constant__ ConvParams2 p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -72,6 +77,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* t_full = a_full + 48;    // [2] accumulator ready
   uint64_t* t_empty = a_full + 50;   // [2] accumulator drained (8 epilogue warps arrive)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 52);
+  uint64_t* res_full = a_full + 56;  // [8 warps][3 slots] skip-connection block landed
   uint8_t* a_ring = smem + 1024;
   const uint32_t a_bytes = static_cast<uint32_t>(p.nbox) * p.RB * 128;
   const uint32_t b_bytes = static_cast<uint32_t>(p.NT) * 128;
@@ -89,6 +95,8 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int i = 0; i < p.SA; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.SB; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 8); }
+    for (int i = 0; i < 24; ++i) ptx::mbar_init(&res_full[i], 1);
+    if (p.residual) ptx::prefetch_tmap(&tmX);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -182,36 +190,59 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       }
     }
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue (2 warpgroups)
-    const int g = (warp - 4) >> 2;
-    const int quad = warp & 3;
-    const int row = quad * 32 + lane;
+    // ------------------------------------------------------------ epilogue: 8 independent warp pipelines
+    const int e = warp - 4;            // epilogue warp index
+    const int g = e >> 2;              // item parity handled by this warp
+    const int quad = warp & 3;         // TMEM lane quadrant = rows quad*32 .. +31 of a 128-row sub-tile
     const int T_out = p.Tq_out * p.P_out;
-    const bool issuer = (quad == 0 && lane == 0);
-    uint8_t* raw_stage = stage_base + g * conv_umma2_stage_bytes_per_wg(p.raw_mode, p.act_mode);
-    uint8_t* act_stage = raw_stage + (p.raw_mode == 1 ? 2 * kRawTileBytes : 0);
-    const int items = p.MT * (p.NT >> 5);
-    int acc = 0, buf = 0;
-    uint32_t accph = 0;
+    const bool has_res = p.residual != nullptr;
+    const int R = conv_umma2_raw_slots(p.raw_mode, has_res);
+    uint8_t* raw_ring = stage_base + e * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, has_res);
+    uint8_t* act_ring = raw_ring + R * kRawBlkBytes;
+    uint64_t* my_res_full = res_full + e * 3;
+    const int ipt = p.MT * (p.NT >> 5);      // items (32-column blocks) per tile
+    int acc = 0, jr = 0, ja = 0;
+    uint32_t accph = 0, res_ph = 0;          // res_ph: one parity bit per ring slot
+    // item -> block coordinates: (channel, phase, first row, batch)
+    auto coords = [&](int tile, int item, int& cb, int& ph, int& r0, int& bb) {
+      int q0, n0;
+      decode(tile, bb, q0, ph, n0);
+      cb = n0 + (item % (p.NT >> 5)) * 32;
+      r0 = q0 + (item / (p.NT >> 5)) * 128 + quad * 32;
+    };
+    if (has_res && lane == 0 && static_cast<int>(blockIdx.x) < p.total_tiles && g < ipt) {
+      int cb, ph, r0, bb;
+      coords(blockIdx.x, g, cb, ph, r0, bb);
+      ptx::mbar_expect_tx(&my_res_full[0], kRawBlkBytes);
+      ptx::tma_load_4d(raw_ring, &tmX, &my_res_full[0], cb, ph, r0, bb);
+    }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int b, q0, phi, n0;
       decode(tile, b, q0, phi, n0);
       ptx::mbar_wait(&t_full[acc], accph);
       ptx::tc_fence_after();
       const uint32_t acc_tmem = tmem_base + acc * acc_cols + (static_cast<uint32_t>(quad * 32) << 16);
-      for (int item = g; item < items; item += 2) {
+      for (int item = g; item < ipt; item += 2) {
         const int m = item / (p.NT >> 5);
         const int c0 = (item % (p.NT >> 5)) * 32;
         const int cbase = n0 + c0;
-        const int q = q0 + m * 128 + row;
-        const bool valid = q < p.Tq_out;
-        const size_t orow = (static_cast<size_t>(b) * T_out + static_cast<size_t>(q) * p.P_out + phi) * p.Cout + cbase;
-        // skip connection first: its HBM latency overlaps the TMEM load and the bias add
-        float4 res[8];
-        if (p.residual && valid) {
-          const float4* rp = reinterpret_cast<const float4*>(p.residual + orow);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) res[j] = __ldg(rp + j);
+        const int r0 = q0 + m * 128 + quad * 32;   // first row of this warp's block
+        // lane 0: recycle the oldest blocks, then prefetch the NEXT item's skip-connection block
+        if (lane == 0 && (R > 0 || p.act_mode == 1)) ptx::bulk_wait_read<1>();
+        if (has_res) {
+          if (lane == 0) {
+            int nt = tile, ni = item + 2;
+            if (ni >= ipt) { nt = tile + gridDim.x; ni = g; }
+            if (nt < p.total_tiles && ni < ipt) {
+              int cb, ph, rr, bb;
+              coords(nt, ni, cb, ph, rr, bb);
+              const int sn = (jr + 1) % 3;
+              ptx::mbar_expect_tx(&my_res_full[sn], kRawBlkBytes);
+              ptx::tma_load_4d(raw_ring + sn * kRawBlkBytes, &tmX, &my_res_full[sn], cb, ph, rr, bb);
+            }
+          }
+          ptx::mbar_wait(&my_res_full[jr], (res_ph >> jr) & 1u);
+          res_ph ^= (1u << jr);
         }
         uint32_t r[32];
         __syncwarp();
@@ -223,19 +254,22 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (p.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
-            v[j] += bb.x; v[j + 1] += bb.y; v[j + 2] += bb.z; v[j + 3] += bb.w;
+            const float4 bb4 = __ldg(reinterpret_cast<const float4*>(p.bias + cbase + j));
+            v[j] += bb4.x; v[j + 1] += bb4.y; v[j + 2] += bb4.z; v[j + 3] += bb4.w;
           }
         }
-        if (p.residual && valid) {
+        uint8_t* rt = raw_ring + jr * kRawBlkBytes + lane * 128;
+        if (has_res) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            v[4 * j] += res[j].x; v[4 * j + 1] += res[j].y; v[4 * j + 2] += res[j].z; v[4 * j + 3] += res[j].w;
+            const float4 x = *reinterpret_cast<const float4*>(rt + ((j ^ (lane & 7)) << 4));
+            v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
           }
         }
         if (p.raw_mode == 2) {
           // channels-first API output: lanes hold consecutive time steps -> coalesced per channel
-          if (valid) {
+          const int q = r0 + lane;
+          if (q < p.Tq_out) {
             const size_t t_out = static_cast<size_t>(q) * p.P_out + phi;
             const size_t o0 = (static_cast<size_t>(b) * p.Cout + cbase) * T_out + t_out;
             if (p.out_cf_f32) {
@@ -249,49 +283,46 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
         }
-        if (p.raw_mode == 1 || p.act_mode == 1) {
-          // the staging tiles of `buf` were last handed to TMA two items ago
-          if (issuer) ptx::bulk_wait_read<1>();
-          ptx::named_bar_sync(1 + g, 128);
-          if (p.raw_mode == 1) {
-            uint8_t* rt = raw_stage + buf * kRawTileBytes + row * 128;
+        if (p.raw_mode == 1) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(rt + ((j ^ (row & 7)) << 4)) =
-                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (p.act_mode == 1) {
-            if (p.snake_a) {
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(rt + ((j ^ (lane & 7)) << 4)) =
+                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (p.act_mode == 1) {
+          if (p.snake_a) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 a = __ldg(reinterpret_cast<const float4*>(p.snake_a + cbase + j));
-                const float4 ib = __ldg(reinterpret_cast<const float4*>(p.snake_inv_b + cbase + j));
-                v[j] = snake_beta<true>(v[j], a.x, ib.x);
-                v[j + 1] = snake_beta<true>(v[j + 1], a.y, ib.y);
-                v[j + 2] = snake_beta<true>(v[j + 2], a.z, ib.z);
-                v[j + 3] = snake_beta<true>(v[j + 3], a.w, ib.w);
-              }
-            }
-            uint8_t* at = act_stage + buf * kActTileBytes + row * 64;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t w[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * j + 2 * e], v[8 * j + 2 * e + 1]);
-                w[e] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              *reinterpret_cast<uint4*>(at + ((j ^ ((row >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(p.snake_a + cbase + j));
+              const float4 ib = __ldg(reinterpret_cast<const float4*>(p.snake_inv_b + cbase + j));
+              v[j] = snake_beta<true>(v[j], a.x, ib.x);
+              v[j + 1] = snake_beta<true>(v[j + 1], a.y, ib.y);
+              v[j + 2] = snake_beta<true>(v[j + 2], a.z, ib.z);
+              v[j + 3] = snake_beta<true>(v[j + 3], a.w, ib.w);
             }
           }
+          uint8_t* at = act_ring + ja * kActBlkBytes + lane * 64;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t w[4];
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * j + 2 * q4], v[8 * j + 2 * q4 + 1]);
+              w[q4] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(at + ((j ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+        if (R > 0 || p.act_mode == 1) {
           ptx::fence_proxy_async();
-          ptx::named_bar_sync(1 + g, 128);
-          if (issuer) {
-            if (p.raw_mode == 1) ptx::tma_store_4d(&tmR, raw_stage + buf * kRawTileBytes, cbase, phi, q0 + m * 128, b);
-            if (p.act_mode == 1) ptx::tma_store_4d(&tmO, act_stage + buf * kActTileBytes, cbase, phi, q0 + m * 128, b);
-            ptx::bulk_commit();
+          __syncwarp();
+          if (lane == 0) {
+            if (p.raw_mode == 1) ptx::tma_store_4d(&tmR, raw_ring + jr * kRawBlkBytes, cbase, phi, r0, b);
+            if (p.act_mode == 1) ptx::tma_store_4d(&tmO, act_ring + ja * kActBlkBytes, cbase, phi, r0, b);
+            ptx::bulk_commit();   // (an empty group when only the skip block was consumed keeps the count uniform)
           }
-          buf ^= 1;
+          if (R > 0) jr = (jr + 1 == R) ? 0 : jr + 1;
+          ja ^= 1;
         }
       }
       // accumulator buffer fully read: hand it back to the UMMA issuer
@@ -300,7 +331,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       if (lane == 0) ptx::mbar_arrive(&t_empty[acc]);
       if (++acc == p.acc_stages) { acc = 0; accph ^= 1u; }
     }
-    if (issuer) ptx::bulk_wait<0>();
+    if (lane == 0) ptx::bulk_wait<0>();
   }
 
   ptx::tc_fence_before();

@@ -160,7 +160,7 @@ inline bool make_w_tmap(CUtensorMap* m, const void* w, int nslab, int Cout, int 
   return true;
 }
 
-// Output tensor [B, T, C] viewed as [B, T/P, P, C] for TMA stores of 128-row x 32-channel blocks:
+// Output tensor [B, T, C] viewed as [B, T/P, P, C] for TMA transfers of 32-row x 32-channel blocks:
 // fp32 blocks are 128 B wide (SWIZZLE_128B), bf16 blocks 64 B (SWIZZLE_64B).
 inline bool make_out_tmap(CUtensorMap* m, const void* y, int B, int T, int C, int P, bool f32, std::string& err) {
   auto enc = tmap_encoder();
@@ -169,7 +169,7 @@ inline bool make_out_tmap(CUtensorMap* m, const void* y, int B, int T, int C, in
   const cuuint64_t es = f32 ? 4 : 2;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)P, (cuuint64_t)(T / P), (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)P * C * es, (cuuint64_t)T * C * es};
-  cuuint32_t box[4] = {32, 1, 128, 1};
+  cuuint32_t box[4] = {32, 1, 32, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                    const_cast<void*>(y), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -277,7 +277,7 @@ inline bool prepare_conv_umma(const ConvGeom& g, const __nv_bfloat16* x, int B, 
 
 // ------------------------------------------------------------------ persistent kernel (conv_umma2.cuh)
 struct ConvLaunch2 {
-  CUtensorMap tmA, tmW, tmR, tmO;
+  CUtensorMap tmA, tmW, tmR, tmO, tmX;
   ConvParams2 p;
   int grid = 0;
   size_t smem = 0;
@@ -320,7 +320,8 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
   p.n_chunks = g.Cin / 64;
   p.raw_mode = ep.out_raw ? (ep.out_raw_cf ? 2 : 1) : 0;
   p.act_mode = ep.out_act ? 1 : 0;
-  const size_t stage = 2 * static_cast<size_t>(conv_umma2_stage_bytes_per_wg(p.raw_mode, p.act_mode));
+  const size_t stage =
+      8 * static_cast<size_t>(conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, ep.residual != nullptr));
   const size_t budget = 227 * 1024 - 2048 - stage;
   // candidate tilings, best first: double-buffered accumulators when they fit the 512 TMEM columns
   struct Cand { int MT, NT, acc; };
@@ -374,6 +375,8 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
   else L.tmR = L.tmA;
   if (p.act_mode == 1) { if (!make_out_tmap(&L.tmO, ep.out_act, B, T_out, g.Cout, tp.P_out, false, err)) return false; }
   else L.tmO = L.tmA;
+  if (ep.residual) { if (!make_out_tmap(&L.tmX, ep.residual, B, T_out, g.Cout, tp.P_out, true, err)) return false; }
+  else L.tmX = L.tmA;
   const int ctas = tune.max_ctas ? tune.max_ctas : sm_count();
   L.grid = std::min(p.total_tiles, ctas);
   L.smem = conv_umma2_smem_bytes(p);
@@ -388,7 +391,7 @@ inline cudaError_t launch_conv_umma2(const ConvLaunch2& L, cudaStream_t stream) 
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  conv_umma2_kernel<<<L.grid, 384, L.smem, stream>>>(L.tmA, L.tmW, L.tmR, L.tmO, L.p);
+  conv_umma2_kernel<<<L.grid, 384, L.smem, stream>>>(L.tmA, L.tmW, L.tmR, L.tmO, L.tmX, L.p);
   return cudaGetLastError();
 }
 
