@@ -35,7 +35,11 @@ struct ConvParams2 {
   int tmem_cols;           // power of two >= acc_stages*MT*NT
   int q_tiles, n_tiles, total_tiles;
   int tap_begin[kMaxPhases + 1];
-  Tap taps[kMaxTaps];
+  // taps packed one word each so the single-thread producer / UMMA issue loops stay short:
+  //   tap_mma[t]: bits 0-15 (row shift * 128 B) >> 4, bit 16 first tap of a slab, bit 17 last tap of a slab
+  //   tap_ld[t] : bits 0-7 input phase, bits 8-15 weight slab, bits 16-31 slab start row (signed)
+  uint32_t tap_mma[kMaxTaps];
+  uint32_t tap_ld[kMaxTaps];
   // epilogue
   const float* bias;
   const float* residual;   // fp32 channels-last [B, T_out, Cout] or nullptr
@@ -130,18 +134,20 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int t_lo = p.tap_begin[phi], t_hi = p.tap_begin[phi + 1];
         for (int ch = 0; ch < p.n_chunks; ++ch) {
           for (int t = t_lo; t < t_hi; ++t) {
-            const Tap tap = p.taps[t];
-            if (tap.first) {
+            const uint32_t tl = p.tap_ld[t];
+            if (p.tap_mma[t] & 0x10000u) {
               ptx::mbar_wait(&a_empty[as], aph ^ 1u);
               ptx::mbar_expect_tx(&a_full[as], a_bytes);
+              const int row = q0 + (static_cast<int32_t>(tl) >> 16);
               for (int bx = 0; bx < p.nbox; ++bx)
                 ptx::tma_load_4d(a_ring + static_cast<size_t>(as) * a_bytes + bx * p.RB * 128, &tmA, &a_full[as],
-                                 ch * 64, tap.a_phase, q0 + tap.a_row + bx * p.RB, b);
+                                 ch * 64, tl & 0xff, row + bx * p.RB, b);
               if (++as == p.SA) { as = 0; aph ^= 1u; }
             }
             ptx::mbar_wait(&b_empty[bs], bph ^ 1u);
             ptx::mbar_expect_tx(&b_full[bs], b_bytes);
-            ptx::tma_load_3d(b_ring + static_cast<size_t>(bs) * b_bytes, &tmW, &b_full[bs], ch * 64, n0, tap.w_slab);
+            ptx::tma_load_3d(b_ring + static_cast<size_t>(bs) * b_bytes, &tmW, &b_full[bs], ch * 64, n0,
+                             (tl >> 8) & 0xff);
             if (++bs == p.SB) { bs = 0; bph ^= 1u; }
           }
         }
@@ -149,39 +155,52 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ UMMA issuer
+    // One thread feeds the tensor core; at N = 128 an MMA retires every 64 cycles, so this loop must stay
+    // a few dozen instructions per tap: descriptors are a constant high word plus a running low word.
     if (ptx::elect_one()) {
       const uint32_t idesc = ptx::idesc_bf16_f32(128, p.NT);
-      const uint32_t a_base = ptx::smem_u32(a_ring);
-      const uint32_t b_base = ptx::smem_u32(b_ring);
+      const uint64_t desc_hi = (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+      const uint32_t a_lo0 = ((ptx::smem_u32(a_ring) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t b_lo0 = ((ptx::smem_u32(b_ring) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t a_stage16 = a_bytes >> 4, b_stage16 = b_bytes >> 4;
+      const bool two = (p.MT == 2);
       int as = 0, bs = 0, cur = 0, acc = 0;
-      uint32_t aph = 0, bph = 0, accph = 0;
+      uint32_t aph = 0, bph = 0, accph = 0, cur_lo = a_lo0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int phi = (tile / p.n_tiles) % p.P_out;
         const int t_lo = p.tap_begin[phi], t_hi = p.tap_begin[phi + 1];
         ptx::mbar_wait(&t_empty[acc], accph ^ 1u);   // epilogue has drained this accumulator buffer
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * acc_cols;
+        const uint32_t d0 = tmem_base + acc * acc_cols;
+        const uint32_t d1 = d0 + p.NT;
+        uint32_t accum = 0;                          // first MMA of a tile overwrites the accumulator
         for (int ch = 0; ch < p.n_chunks; ++ch) {
           for (int t = t_lo; t < t_hi; ++t) {
-            const Tap tap = p.taps[t];
-            if (tap.first) {
+            const uint32_t tw = p.tap_mma[t];
+            if (tw & 0x10000u) {
               ptx::mbar_wait(&a_full[as], aph);
               cur = as;
+              cur_lo = a_lo0 + as * a_stage16;
               if (++as == p.SA) { as = 0; aph ^= 1u; }
             }
             ptx::mbar_wait(&b_full[bs], bph);
             ptx::tc_fence_after();
-            const uint32_t fresh = (ch == 0 && t == t_lo) ? 1u : 0u;
-            for (int m = 0; m < p.MT; ++m) {
-              const uint32_t a_tile = a_base + cur * a_bytes + (tap.shift + 128 * m) * 128;
-              const uint32_t b_tile = b_base + bs * b_bytes;
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                ptx::umma_f16(d_tmem + m * p.NT, ptx::smem_desc_sw128(a_tile + k * 32, 0),
-                              ptx::smem_desc_sw128(b_tile + k * 32, 0), idesc, (fresh && k == 0) ? 0u : 1u);
+            const uint32_t al = cur_lo + (tw & 0xffffu);
+            const uint32_t bl = b_lo0 + bs * b_stage16;
+            ptx::umma_f16(d0, desc_hi | al, desc_hi | bl, idesc, accum);
+            ptx::umma_f16(d0, desc_hi | (al + 2), desc_hi | (bl + 2), idesc, 1u);
+            ptx::umma_f16(d0, desc_hi | (al + 4), desc_hi | (bl + 4), idesc, 1u);
+            ptx::umma_f16(d0, desc_hi | (al + 6), desc_hi | (bl + 6), idesc, 1u);
+            if (two) {
+              const uint32_t al1 = al + 1024;        // second 128-row sub-tile: +128 rows * 128 B >> 4
+              ptx::umma_f16(d1, desc_hi | al1, desc_hi | bl, idesc, accum);
+              ptx::umma_f16(d1, desc_hi | (al1 + 2), desc_hi | (bl + 2), idesc, 1u);
+              ptx::umma_f16(d1, desc_hi | (al1 + 4), desc_hi | (bl + 4), idesc, 1u);
+              ptx::umma_f16(d1, desc_hi | (al1 + 6), desc_hi | (bl + 6), idesc, 1u);
             }
+            accum = 1u;
             ptx::umma_commit(&b_empty[bs]);
-            if (tap.last) ptx::umma_commit(&a_empty[cur]);
+            if (tw & 0x20000u) ptx::umma_commit(&a_empty[cur]);
             if (++bs == p.SB) { bs = 0; bph ^= 1u; }
           }
         }

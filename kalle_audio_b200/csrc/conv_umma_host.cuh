@@ -359,7 +359,13 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
   while (cols < p.acc_stages * p.MT * p.NT) cols <<= 1;
   p.tmem_cols = cols;
   for (int i = 0; i <= kMaxPhases; ++i) p.tap_begin[i] = tp.tap_begin[i];
-  for (size_t i = 0; i < tp.taps.size(); ++i) p.taps[i] = tp.taps[i];
+  for (size_t i = 0; i < tp.taps.size(); ++i) {
+    const Tap& t = tp.taps[i];
+    if (t.shift * 8 > 0xffff || t.a_phase > 255 || t.w_slab > 255) { err = "tap does not fit the packed table"; return false; }
+    p.tap_mma[i] = static_cast<uint32_t>(t.shift * 8) | (t.first ? 0x10000u : 0u) | (t.last ? 0x20000u : 0u);
+    p.tap_ld[i] = static_cast<uint32_t>(t.a_phase) | (static_cast<uint32_t>(t.w_slab) << 8) |
+                  (static_cast<uint32_t>(static_cast<uint16_t>(t.a_row)) << 16);
+  }
   p.q_tiles = (p.Tq_out + 128 * p.MT - 1) / (128 * p.MT);
   p.n_tiles = g.Cout / p.NT;
   p.total_tiles = p.q_tiles * p.n_tiles * tp.P_out * B;
