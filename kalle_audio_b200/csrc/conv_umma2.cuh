@@ -31,6 +31,7 @@ struct ConvParams2 {
   int MT, NT;
   int RB, nbox;
   int SA, SB;
+  int swap;                // 1: out-channels on the MMA M side (TMEM lanes), time on the N side (see kernel)
   int acc_stages;          // 1 or 2 accumulator buffers in TMEM
   int tmem_cols;           // power of two >= acc_stages*MT*NT
   int q_tiles, n_tiles, total_tiles;
@@ -111,7 +112,12 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int acc_cols = p.MT * p.NT;
+  // Two operand assignments.  swap = 0: M = 128 time rows (x MT sub-tiles), N = NT out-channels.
+  // swap = 1 (NT == 128): M = 128 out-channels, N = 128*MT time rows.  With N = 256 one instruction does the
+  // work of two, and per 128 cycles the tensor core reads 4 KB (weights) + 8 KB (activations) of shared
+  // memory instead of 2 x (4 + 4) KB -- at M = N = 128 the operand reads alone saturate the 128 B/cycle
+  // shared-memory port, which capped the C = 128 layers at ~55 % tensor utilisation.
+  const int acc_cols = p.swap ? 128 * p.MT : p.MT * p.NT;
 
   // tile id -> (batch, q tile, output phase, n tile); n fastest so CTAs sharing an A slab run together
   auto decode = [&](int tile, int& b, int& q0, int& phi, int& n0) {
@@ -159,6 +165,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // a few dozen instructions per tap: descriptors are a constant high word plus a running low word.
     if (ptx::elect_one()) {
       const uint32_t idesc = ptx::idesc_bf16_f32(128, p.NT);
+      const uint32_t idesc_swap = ptx::idesc_bf16_f32(128, 128 * p.MT);
       const uint64_t desc_hi = (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
       const uint32_t a_lo0 = ((ptx::smem_u32(a_ring) & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t b_lo0 = ((ptx::smem_u32(b_ring) & 0x3FFFFu) >> 4) | (1u << 16);
@@ -187,6 +194,12 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             ptx::tc_fence_after();
             const uint32_t al = cur_lo + (tw & 0xffffu);
             const uint32_t bl = b_lo0 + bs * b_stage16;
+            if (p.swap) {
+              ptx::umma_f16(d0, desc_hi | bl, desc_hi | al, idesc_swap, accum);
+              ptx::umma_f16(d0, desc_hi | (bl + 2), desc_hi | (al + 2), idesc_swap, 1u);
+              ptx::umma_f16(d0, desc_hi | (bl + 4), desc_hi | (al + 4), idesc_swap, 1u);
+              ptx::umma_f16(d0, desc_hi | (bl + 6), desc_hi | (al + 6), idesc_swap, 1u);
+            } else {
             ptx::umma_f16(d0, desc_hi | al, desc_hi | bl, idesc, accum);
             ptx::umma_f16(d0, desc_hi | (al + 2), desc_hi | (bl + 2), idesc, 1u);
             ptx::umma_f16(d0, desc_hi | (al + 4), desc_hi | (bl + 4), idesc, 1u);
@@ -197,6 +210,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               ptx::umma_f16(d1, desc_hi | (al1 + 2), desc_hi | (bl + 2), idesc, 1u);
               ptx::umma_f16(d1, desc_hi | (al1 + 4), desc_hi | (bl + 4), idesc, 1u);
               ptx::umma_f16(d1, desc_hi | (al1 + 6), desc_hi | (bl + 6), idesc, 1u);
+            }
             }
             accum = 1u;
             ptx::umma_commit(&b_empty[bs]);
@@ -219,15 +233,23 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint8_t* raw_ring = stage_base + e * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, has_res);
     uint8_t* act_ring = raw_ring + R * kRawBlkBytes;
     uint64_t* my_res_full = res_full + e * 3;
-    const int ipt = p.MT * (p.NT >> 5);      // items (32-column blocks) per tile
+    // An item is one 32-row x 32-channel output block.  swap = 0: TMEM lane = time row, so a thread owns one
+    // row x 32 channels (vector shared-memory accesses).  swap = 1: TMEM lane = channel, so a thread owns one
+    // channel x 32 rows (scalar accesses into the same swizzled blocks; per-channel constants live in registers).
+    const int ipt = p.swap ? 4 * p.MT : p.MT * (p.NT >> 5);
     int acc = 0, jr = 0, ja = 0;
     uint32_t accph = 0, res_ph = 0;          // res_ph: one parity bit per ring slot
     // item -> block coordinates: (channel, phase, first row, batch)
     auto coords = [&](int tile, int item, int& cb, int& ph, int& r0, int& bb) {
       int q0, n0;
       decode(tile, bb, q0, ph, n0);
-      cb = n0 + (item % (p.NT >> 5)) * 32;
-      r0 = q0 + (item / (p.NT >> 5)) * 128 + quad * 32;
+      if (p.swap) {
+        cb = n0 + quad * 32;
+        r0 = q0 + item * 32;
+      } else {
+        cb = n0 + (item % (p.NT >> 5)) * 32;
+        r0 = q0 + (item / (p.NT >> 5)) * 128 + quad * 32;
+      }
     };
     if (has_res && lane == 0 && static_cast<int>(blockIdx.x) < p.total_tiles && g < ipt) {
       int cb, ph, r0, bb;
@@ -238,14 +260,29 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int b, q0, phi, n0;
       decode(tile, b, q0, phi, n0);
+      // swap mode: this thread's channel and its constants
+      float bias_s = 0.f, sa_s = 1.f, sib_s = 0.f;
+      if (p.swap) {
+        const int c = n0 + quad * 32 + lane;
+        if (p.bias) bias_s = __ldg(p.bias + c);
+        if (p.snake_a) { sa_s = __ldg(p.snake_a + c); sib_s = __ldg(p.snake_inv_b + c); }
+      }
       ptx::mbar_wait(&t_full[acc], accph);
       ptx::tc_fence_after();
       const uint32_t acc_tmem = tmem_base + acc * acc_cols + (static_cast<uint32_t>(quad * 32) << 16);
       for (int item = g; item < ipt; item += 2) {
-        const int m = item / (p.NT >> 5);
-        const int c0 = (item % (p.NT >> 5)) * 32;
-        const int cbase = n0 + c0;
-        const int r0 = q0 + m * 128 + quad * 32;   // first row of this warp's block
+        int cbase, r0, tcol;
+        if (p.swap) {
+          cbase = n0 + quad * 32;
+          r0 = q0 + item * 32;
+          tcol = item * 32;
+        } else {
+          const int m = item / (p.NT >> 5);
+          const int c0 = (item % (p.NT >> 5)) * 32;
+          cbase = n0 + c0;
+          r0 = q0 + m * 128 + quad * 32;   // first row of this warp's block
+          tcol = m * p.NT + c0;
+        }
         // lane 0: recycle the oldest blocks, then prefetch the NEXT item's skip-connection block
         if (lane == 0 && (R > 0 || p.act_mode == 1)) ptx::bulk_wait_read<1>();
         if (has_res) {
@@ -265,11 +302,52 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         uint32_t r[32];
         __syncwarp();
-        ptx::tmem_ld_32x32(acc_tmem + m * p.NT + c0, r);
+        ptx::tmem_ld_32x32(acc_tmem + tcol, r);
         ptx::tmem_ld_wait();
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        uint8_t* const rblk = raw_ring + jr * kRawBlkBytes;
+        uint8_t* const ablk = act_ring + ja * kActBlkBytes;
+        if (p.swap) {
+          // ---- thread = channel (cbase + lane), v[j] = row r0 + j
+          // element (row j, channel lane) of a SWIZZLE_128B fp32 block / SWIZZLE_64B bf16 block
+          const uint32_t rcol = (lane & 3) * 4, rchunk = lane >> 2;
+          const uint32_t acol = (lane & 7) * 2, achunk = lane >> 3;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += bias_s;
+          if (has_res) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              v[j] += *reinterpret_cast<const float*>(rblk + j * 128 + ((rchunk ^ (j & 7)) << 4) + rcol);
+          }
+          if (p.raw_mode == 2) {
+            const int c = cbase + lane;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int q = r0 + j;
+              if (q < p.Tq_out) {
+                const size_t o = (static_cast<size_t>(b) * p.Cout + c) * T_out + static_cast<size_t>(q) * p.P_out + phi;
+                if (p.out_cf_f32) static_cast<float*>(p.out_cf)[o] = v[j];
+                else static_cast<__nv_bfloat16*>(p.out_cf)[o] = __float2bfloat16(v[j]);
+              }
+            }
+          }
+          if (p.raw_mode == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              *reinterpret_cast<float*>(rblk + j * 128 + ((rchunk ^ (j & 7)) << 4) + rcol) = v[j];
+          }
+          if (p.act_mode == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float a = p.snake_a ? snake_beta<true>(v[j], sa_s, sib_s) : v[j];
+              *reinterpret_cast<__nv_bfloat16*>(ablk + j * 64 + ((achunk ^ ((j >> 1) & 3)) << 4) + acol) =
+                  __float2bfloat16(a);
+            }
+          }
+        } else {
+        // ---- thread = time row (r0 + lane), v[j] = channel cbase + j
         if (p.bias) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -277,7 +355,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             v[j] += bb4.x; v[j + 1] += bb4.y; v[j + 2] += bb4.z; v[j + 3] += bb4.w;
           }
         }
-        uint8_t* rt = raw_ring + jr * kRawBlkBytes + lane * 128;
+        uint8_t* rt = rblk + lane * 128;
         if (has_res) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -320,7 +398,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               v[j + 3] = snake_beta<true>(v[j + 3], a.w, ib.w);
             }
           }
-          uint8_t* at = act_ring + ja * kActBlkBytes + lane * 64;
+          uint8_t* at = ablk + lane * 64;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint32_t w[4];
@@ -331,6 +409,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
             *reinterpret_cast<uint4*>(at + ((j ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
           }
+        }
         }
         if (R > 0 || p.act_mode == 1) {
           ptx::fence_proxy_async();

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -286,6 +287,7 @@ struct ConvLaunch2 {
 
 struct ConvTuning2 {
   int MT = 0, NT = 0, acc_stages = 0;   // 0 = auto
+  int swap = -1;                        // -1 = auto (swap whenever the tile is 128 out-channels wide)
   int max_ctas = 0;                     // 0 = one per SM
 };
 
@@ -348,9 +350,13 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
     const size_t a_bytes = static_cast<size_t>(nbox) * RB * 128, b_bytes = static_cast<size_t>(c.NT) * 128;
     if (2 * a_bytes + 2 * b_bytes > budget) continue;
     p.MT = c.MT; p.NT = c.NT; p.acc_stages = c.acc; p.nbox = nbox; p.RB = RB;
+    p.swap = (tune.swap >= 0) ? tune.swap : (c.NT == 128 ? 1 : 0);
+    if (p.swap && c.NT != 128) { err = "swap mode needs 128-channel tiles"; return false; }
     p.SA = 2;
     p.SB = static_cast<int>(std::min<size_t>(8, (budget - 2 * a_bytes) / b_bytes));
     while (p.SA < 4 && (p.SA + 1) * a_bytes + p.SB * b_bytes <= budget) ++p.SA;
+    if (const char* e = getenv("KVAE_SB")) p.SB = std::max(2, std::min(p.SB, atoi(e)));   // tuning experiments
+    if (const char* e = getenv("KVAE_SA")) p.SA = std::max(1, std::min(p.SA, atoi(e)));
     ok = true;
     break;
   }

@@ -13,8 +13,9 @@ for c in $(seq 0 $((NC-1))); do
   done
 done
 # perf: <idx> <kernel version 1|2|3(v2, forced tile)> <epilogue 0 cast | 1 bias+snake | 2 +residual+raw>
-for spec in "0 1 1" "0 2 1" "1 1 2" "1 2 2" "2 1 1" "2 2 1" "2 3 1" "4 1 1" "4 2 1" "4 3 1" "5 1 1" "5 2 1" "5 3 1" \
-            "6 1 2" "6 2 2" "6 3 2" "7 1 2" "7 2 2"; do
+# kernel version: 1 = first-generation kernel, 2 = persistent kernel (auto tiling), 3 = persistent with the
+# table's MT/NT, 4 = persistent with the operand swap disabled
+for spec in ${PERF_SPECS:-"0 2 1" "0 4 1" "0 2 0" "1 2 2" "1 4 2" "2 2 1" "2 4 1" "2 3 1" "4 2 1" "5 2 1" "6 2 1" "7 2 2" "7 4 2"}; do
   timeout 120 ./build/umma_probe perf $spec >> $LOG 2>&1
   echo "exit $? (perf $spec)" >> $LOG
 done

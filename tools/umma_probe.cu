@@ -146,6 +146,7 @@ static int run_case(int idx, int variant) {
     ConvTuning2 tune2;
     if (variant == 4) tune2.max_ctas = 3;
     if (variant == 5) { tune2.MT = 1; tune2.NT = c.NT > 128 ? 128 : c.NT; }
+    if (variant == 6) tune2.swap = 0;   // time rows on the M side even for 128-channel tiles
     ConvLaunch2 L2;
     if (!prepare_conv_umma2(g, dx, c.B, c.T, dw, ep, tune2, L2, err)) {
       printf("CASE %d %s variant %d: prepare failed: %s\n", idx, c.name, variant, err.c_str());
@@ -289,6 +290,7 @@ static int run_perf(int idx, int ver, int epi) {
   } else {
     ConvTuning2 tune2;
     if (ver == 3) { tune2.MT = c.MT; tune2.NT = c.NT; }
+    if (ver == 4) tune2.swap = 0;
     if (!prepare_conv_umma2(g, dx, c.B, c.T, dw, ep, tune2, L2, err)) {
       printf("PERF %s: prepare failed: %s\n", c.name, err.c_str());
       return 3;
@@ -315,9 +317,9 @@ static int run_perf(int idx, int ver, int epi) {
     printf("PERF v1 epi%d %s: %.3f ms  %.1f TFLOP/s  %.1f GB/s  MT %d NT %d smem %zu SA %d SB %d\n", epi, c.name, ms,
            flops / ms * 1e-9, bytes / ms * 1e-6, L.p.MT, L.p.NT, L.smem, L.p.SA, L.p.SB);
   else
-    printf("PERF v%d epi%d %s: %.3f ms  %.1f TFLOP/s  %.1f GB/s  MT %d NT %d acc %d grid %d smem %zu SA %d SB %d\n", ver,
-           epi, c.name, ms, flops / ms * 1e-9, bytes / ms * 1e-6, L2.p.MT, L2.p.NT, L2.p.acc_stages, L2.grid, L2.smem,
-           L2.p.SA, L2.p.SB);
+    printf("PERF v%d epi%d %s: %.3f ms  %.1f TFLOP/s  %.1f GB/s  MT %d NT %d swap %d acc %d grid %d smem %zu SA %d SB %d\n",
+           ver, epi, c.name, ms, flops / ms * 1e-9, bytes / ms * 1e-6, L2.p.MT, L2.p.NT, L2.p.swap, L2.p.acc_stages,
+           L2.grid, L2.smem, L2.p.SA, L2.p.SB);
   return 0;
 }
 
