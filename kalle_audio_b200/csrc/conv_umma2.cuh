@@ -316,10 +316,12 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           const uint32_t acol = (lane & 7) * 2, achunk = lane >> 3;
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += bias_s;
+          uint8_t* rbase[8];     // the 8 distinct swizzle phases of a SWIZZLE_128B block
+#pragma unroll
+          for (int c = 0; c < 8; ++c) rbase[c] = rblk + ((rchunk ^ c) << 4) + rcol;
           if (has_res) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              v[j] += *reinterpret_cast<const float*>(rblk + j * 128 + ((rchunk ^ (j & 7)) << 4) + rcol);
+            for (int j = 0; j < 32; ++j) v[j] += *reinterpret_cast<const float*>(rbase[j & 7] + j * 128);
           }
           if (p.raw_mode == 2) {
             const int c = cbase + lane;
@@ -335,16 +337,19 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           if (p.raw_mode == 1) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              *reinterpret_cast<float*>(rblk + j * 128 + ((rchunk ^ (j & 7)) << 4) + rcol) = v[j];
+            for (int j = 0; j < 32; ++j) *reinterpret_cast<float*>(rbase[j & 7] + j * 128) = v[j];
           }
           if (p.act_mode == 1) {
+            if (p.snake_a) {   // hoisted: a per-element test would put a branch between the 32 independent chains
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float a = p.snake_a ? snake_beta<true>(v[j], sa_s, sib_s) : v[j];
-              *reinterpret_cast<__nv_bfloat16*>(ablk + j * 64 + ((achunk ^ ((j >> 1) & 3)) << 4) + acol) =
-                  __float2bfloat16(a);
+              for (int j = 0; j < 32; ++j) v[j] = snake_beta<true>(v[j], sa_s, sib_s);
             }
+            uint8_t* abase[4];   // the 4 distinct swizzle phases of a SWIZZLE_64B block
+#pragma unroll
+            for (int c = 0; c < 4; ++c) abase[c] = ablk + ((achunk ^ c) << 4) + acol;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              *reinterpret_cast<__nv_bfloat16*>(abase[(j >> 1) & 3] + j * 64) = __float2bfloat16(v[j]);
           }
         } else {
         // ---- thread = time row (r0 + lane), v[j] = channel cbase + j
