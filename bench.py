@@ -301,6 +301,116 @@ def run_cuda(args):
         dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------ other BASELINE configs
+O12 = dict(channels=128, c_mults=[1, 2, 4, 8, 16], strides=[2, 4, 4, 5, 8], io_channels=1, sample_rate=16000)
+
+
+def run_extra(args):
+    """BASELINE configs[2] and [3] (not the driver's default line; same JSON keys where they apply).
+       o12_decode: vae_12_5_dim1024-shape decoder (latent 512), 64 clips x 30 s, batch-sharded over the ranks
+                   (strong scaling: 64 / N clips per GPU), decode only.
+       stream:     vae_12_5hz_dim2048-shape decoder (latent 1024), batch 1, decode_audio(chunked=True,
+                   chunk_size=128, overlap=32) semantics over T=375 -- first-chunk latency, per-chunk latency,
+                   real-time factor; CUDA-graph replay on."""
+    import torch
+    import torch.distributed as dist
+    import kalle_audio_b200 as k
+    from kalle_audio_b200.sharding import shard_bounds
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.set_grad_enabled(False)
+    torch.manual_seed(0)
+    latent = 512 if args.workload == "o12_decode" else 1024
+    dec = k.OobleckDecoder(out_channels=1, channels=O12["channels"], latent_dim=latent, c_mults=O12["c_mults"],
+                           strides=O12["strides"], use_snake=True, final_tanh=False).eval().to(dev)
+    dec.set_precision("bf16")
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    if args.workload == "o12_decode":
+        total_clips, T = 64, 375
+        lo, hi = shard_bounds(total_clips, world, rank)
+        z = torch.randn(hi - lo, latent, T, generator=torch.Generator().manual_seed(1 + rank)).to(dev)
+        mb = args.micro_batch or (hi - lo)
+
+        def step():
+            for i in range(0, hi - lo, mb):
+                dec(z[i:i + mb])
+
+        for _ in range(max(args.warmup, 3)):
+            step()
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            audio_s = total_clips * T * 1280 / O12["sample_rate"]
+            r = dec.runner(dev)
+            flops = r.flops(1, T) * total_clips
+            t = float(ms.item()) / args.steps * 1e-3
+            print(json.dumps({"metric": METRIC, "value": audio_s / t, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "warmup": max(args.warmup, 3), "ms_per_step": t * 1e3, "higher_is_better": True,
+                              "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                              "tflops_per_gpu": flops / t / 1e12 / world,
+                              "config": {"workload": "BASELINE configs[2]: O12 latent-512 (dim1024) decoder, 64 clips x 30 s, "
+                                                     f"batch-sharded {total_clips // world} per GPU, micro-batch {mb}, bf16 mode"}}),
+                  flush=True)
+    else:
+        T, chunk, overlap = 375, 128, 32
+        ae = k.AudioAutoencoder(None, dec, latent_dim=latent, downsampling_ratio=1280, sample_rate=16000, io_channels=1)
+        dec.enable_cuda_graphs(True)
+        z = torch.randn(1, latent, T, generator=torch.Generator().manual_seed(1)).to(dev)
+        for _ in range(max(args.warmup, 3)):
+            ae.decode_audio(z, chunked=True, overlap=overlap, chunk_size=chunk)
+            dec(z[:, :, :chunk])
+        sync()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        for _ in range(args.steps):
+            dec(z[:, :, :chunk])                      # one chunk, as a streaming caller would issue it
+        ev[1].record()
+        for _ in range(args.steps):
+            ae.decode_audio(z, chunked=True, overlap=overlap, chunk_size=chunk)   # all 4 windows in one batched call
+        ev[2].record()
+        sync()
+        t0 = time.perf_counter()
+        y = dec(z[:, :, :chunk])
+        y[0, 0, :8].cpu()
+        first_wall = time.perf_counter() - t0
+        if rank == 0:
+            chunk_ms = ev[0].elapsed_time(ev[1]) / args.steps
+            full_ms = ev[1].elapsed_time(ev[2]) / args.steps
+            audio_s = T * 1280 / 16000
+            print(json.dumps({"metric": METRIC, "value": audio_s / (full_ms * 1e-3), "unit": UNIT, "n_gpus": 1,
+                              "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": full_ms,
+                              "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                              "data": "synthetic", "per_chunk_ms": chunk_ms,
+                              "first_chunk_wall_ms_incl_d2h": first_wall * 1e3,
+                              "real_time_factor_per_chunk": (chunk - overlap) * 1280 / 16000 / (chunk_ms * 1e-3),
+                              "config": {"workload": "BASELINE configs[3]: O12 latent-1024 (dim2048) decoder, batch 1, "
+                                                     "chunked decode chunk 128 / overlap 32 over T=375 (4 windows), "
+                                                     "CUDA-graph replay, bf16 mode"}}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -308,9 +418,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["cuda", "reference"], default="cuda")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", choices=["roundtrip", "o12_decode", "stream"], default="roundtrip",
+                    help="roundtrip = BASELINE configs[1] (the driver's line); o12_decode = configs[2]; stream = configs[3]")
+    ap.add_argument("--micro-batch", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "roundtrip":
+        run_extra(args)
     else:
         run_cuda(args)
 

@@ -44,6 +44,9 @@ class PlanRunner:
                 raise _lib.KvaeError(f"SnakeBeta {i}: channel count mismatch")
         self._fingerprint: Optional[Tuple] = None
         self._workspace: Optional[torch.Tensor] = None
+        # optional CUDA-graph replay of the ~38 launches of one pass (small batches are launch-bound)
+        self.use_graphs = False
+        self._graphs: Dict[Tuple, Tuple] = {}
 
     # ------------------------------------------------------------------ weights
     def _params(self):
@@ -72,6 +75,7 @@ class PlanRunner:
             b = m.beta.detach().float().contiguous()
             _lib.check(L.kvae_plan_set_snake(self.handle, i, a.data_ptr(), b.data_ptr(), int(m.alpha_logscale), st))
         self._fingerprint = fp
+        self._graphs.clear()        # packed weights are rewritten in place, but keep capture state simple
 
     # ------------------------------------------------------------------ run
     def _get_workspace(self, B: int, T: int) -> torch.Tensor:
@@ -80,6 +84,7 @@ class PlanRunner:
             raise _lib.KvaeError(_lib.lib().kvae_last_error().decode())
         if self._workspace is None or self._workspace.numel() < need:
             self._workspace = None  # release before growing
+            self._graphs.clear()    # captured graphs point into the old workspace
             self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._workspace
 
@@ -102,12 +107,36 @@ class PlanRunner:
         if self.direction == _lib.KVAE_ENCODER and T % ratio:
             raise ValueError(f"audio length {T} is not a multiple of the downsampling ratio {ratio} "
                              "(use preprocess_audio_for_encoder)")
-        out = torch.empty((B, out_channels, self.out_length(T, ratio)), dtype=kdtype, device=self.device)
         ws = self._get_workspace(B, T)
         L = _lib.lib()
         fn = L.kvae_decode if self.direction == _lib.KVAE_DECODER else L.kvae_encode
-        _lib.check(fn(self.handle, xin.data_ptr(), _lib.dtype_code(xin.dtype), out.data_ptr(), _lib.dtype_code(kdtype),
-                      B, T, ws.data_ptr(), ws.numel(), _lib.stream_ptr(self.device)))
+        out_shape = (B, out_channels, self.out_length(T, ratio))
+
+        def launch(src, dst):
+            _lib.check(fn(self.handle, src.data_ptr(), _lib.dtype_code(src.dtype), dst.data_ptr(),
+                          _lib.dtype_code(kdtype), B, T, ws.data_ptr(), ws.numel(), _lib.stream_ptr(self.device)))
+
+        if self.use_graphs and not torch.cuda.is_current_stream_capturing():
+            key = (B, T, xin.dtype, kdtype)
+            entry = self._graphs.get(key)
+            if entry is None:
+                static_in = torch.empty_like(xin)
+                static_out = torch.empty(out_shape, dtype=kdtype, device=self.device)
+                static_in.copy_(xin)
+                launch(static_in, static_out)          # warm-up: builds descriptors, sets kernel attributes
+                torch.cuda.current_stream(self.device).synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    launch(static_in, static_out)
+                entry = (graph, static_in, static_out)
+                self._graphs[key] = entry
+            graph, static_in, static_out = entry
+            static_in.copy_(xin)
+            graph.replay()
+            out = static_out.clone()
+        else:
+            out = torch.empty(out_shape, dtype=kdtype, device=self.device)
+            launch(xin, out)
         return out if out.dtype == out_dtype else out.to(out_dtype)
 
     def set_profiling(self, enable: bool) -> None:

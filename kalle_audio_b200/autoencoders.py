@@ -143,8 +143,17 @@ class _OobleckBase(nn.Module):
             return torch.get_autocast_dtype("cuda")
         return next(self.parameters()).dtype
 
+    def enable_cuda_graphs(self, enable: bool = True):
+        """Replay each (batch, length) shape as one CUDA graph instead of ~38 launches (helps small batches)."""
+        self._use_graphs = bool(enable)
+        for r in self._plans.runners.values():
+            r.use_graphs = self._use_graphs
+        return self
+
     def runner(self, device):
-        return self._plans.get(self, self._direction, self._arch, self._resolve_precision(), device)
+        r = self._plans.get(self, self._direction, self._arch, self._resolve_precision(), device)
+        r.use_graphs = getattr(self, "_use_graphs", False)
+        return r
 
     def forward(self, x):
         _lib.require_cuda(x, type(self).__name__ + ".forward")
