@@ -117,26 +117,28 @@ __global__ void __launch_bounds__(288, 1) conv_wave_out_kernel(const WaveOutPara
       return v;
     };
     const int o0 = warp * 16;                 // this warp's first output inside the tile
-    float4 win[7];
-#pragma unroll
-    for (int k = 0; k < 6; ++k) win[k + 1] = load_row(o0 + k);
+    // Row-major accumulation: each staged row (SnakeBeta applied once) feeds the 7 outputs whose windows
+    // contain it, so the 56 FMAs per row go to 14 independent accumulators -- no long dependent chains.
     float acc[16 * COUT];
 #pragma unroll
-    for (int o = 0; o < 16; ++o) {
+    for (int i = 0; i < 16 * COUT; ++i) acc[i] = 0.f;
 #pragma unroll
-      for (int k = 0; k < 6; ++k) win[k] = win[k + 1];
-      win[6] = load_row(o0 + o + 6);
+    for (int r = 0; r < 22; ++r) {
+      const float4 x = load_row(o0 + r);
 #pragma unroll
-      for (int c = 0; c < COUT; ++c) {
-        float a = 0.f;
+      for (int k = 0; k < 7; ++k) {
+        const int o = r - k;                  // output (inside this warp's 16) whose tap k reads row r
+        if (o >= 0 && o < 16) {
 #pragma unroll
-        for (int k = 0; k < 7; ++k) {
-          a = fmaf(win[k].x, w[k][0][c], a);
-          a = fmaf(win[k].y, w[k][1][c], a);
-          a = fmaf(win[k].z, w[k][2][c], a);
-          a = fmaf(win[k].w, w[k][3][c], a);
+          for (int c = 0; c < COUT; ++c) {
+            float a = acc[c * 16 + o];
+            a = fmaf(x.x, w[k][0][c], a);
+            a = fmaf(x.y, w[k][1][c], a);
+            a = fmaf(x.z, w[k][2][c], a);
+            a = fmaf(x.w, w[k][3][c], a);
+            acc[c * 16 + o] = a;
+          }
         }
-        acc[c * 16 + o] = a;
       }
     }
     // this warp no longer reads the staged tile
