@@ -1,0 +1,342 @@
+// conv_ru: one-kernel ResidualUnit for 128-channel stages (reference autoencoders.py:39-62):
+//     x' = x + conv_k1( SnakeBeta2( conv_k7_dil_d( SnakeBeta1(x) ) ) )
+// The producer of x already wrote a = SnakeBeta1(x) (bf16 operand) and x (fp32 residual stream); this kernel
+// never materialises the intermediate h = SnakeBeta2(conv_k7(a)) in HBM.  Per output row it moves
+// 256 B (a) + 512 B (x) in and 512 B (x') + 256 B (a' = next layer's operand) out = 1536 B instead of the
+// 2048 B of the two-kernel form -- these stages are HBM-bound, so that is the speed-up.
+//
+// Orientation (see conv_umma2.cuh "swap"): out-channels on the MMA M side (TMEM lanes), 256 time rows on N.
+//   GEMM1  D1[co, t]  = sum_{tap,ci} W7[tap][co, ci] * a[t + shift(tap), ci]      (14 x 4 MMAs of 128x256x16)
+//   EPI1   h[t, c]    = bf16( SnakeBeta2( D1[c, t] + bias7[c] ) )  -> shared memory, K-major, 128-row halves
+//   GEMM2  D2[co2, t] = sum_c W1[co2, c] * h[t, c]                                 (2 halves x 2 x 4 MMAs of 128x128x16)
+//   EPI2   x'[t, c]   = D2[c, t] + bias1[c] + x[t, c]  -> fp32 stream (TMA store); a' = bf16(SnakeBeta_next(x')) (TMA store)
+// TMEM: D1 = columns [0,256), D2 = [256,512).  Warp roles (384 threads): 0 TMA producer, 1 UMMA issuer,
+// 2 TMEM allocator, 4-7 EPI1, 8-11 EPI2 (each EPI2 warp: skip-connection prefetch ring + in-place stores).
+// Shared memory (227 KB): activation slab ring 2 x <=40 KB, weight ring 3-4 x 16 KB (W7 taps, then the two W1
+// chunks of the tile), h half 32 KB, EPI2 staging 4 x <=16 KB.
+#pragma once
+#include <cuda_bf16.h>
+#include <cstdint>
+
+#include "conv_umma2.cuh"
+
+namespace kvae {
+
+struct RuParams {
+  int B, T;                 // rows per clip (stride-1 conv: T_in == T_out)
+  int RB, nbox;             // activation slab = nbox TMA boxes of RB rows (256 + 6*dilation rows)
+  int SA, SB;
+  int q_tiles, total_tiles; // 256-row tiles
+  uint32_t tap_shift16[7];  // (tap*dilation*128 B) >> 4
+  int slab_row0;            // slab start row relative to the tile's first row (= -3*dilation)
+  const float* bias7;       // [128]
+  const float* s2_a;        // SnakeBeta between the two convs
+  const float* s2_inv_b;
+  const float* bias1;       // [128]
+  int raw_out;              // 1: fp32 stream out via tmR
+  int act_out;              // 1: bf16 operand out via tmO
+  const float* sn_a;        // SnakeBeta folded into the operand output (nullptr: plain cast)
+  const float* sn_inv_b;
+};
+
+constexpr int kRuC = 128;
+constexpr int kRuHBytes = 2 * 128 * 128;   // h half: 2 K-chunks x [128 rows x 128 B]
+
+__host__ __device__ inline int ru_stage_bytes_per_warp(int act_out) { return 3 * kRawBlkBytes + (act_out ? 2 * kActBlkBytes : 0); }
+__host__ __device__ inline size_t ru_smem_bytes(const RuParams& p) {
+  return 1024 + 1024 + static_cast<size_t>(p.SA) * p.nbox * p.RB * 128 + static_cast<size_t>(p.SB) * kRuC * 128 +
+         kRuHBytes + 4 * ru_stage_bytes_per_warp(p.act_out);
+}
+
+__global__ void __launch_bounds__(384, 1)
+conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW7,
+               const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX,
+               const __grid_constant__ RuParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* a_empty = a_full + 8;
+  uint64_t* b_full = a_full + 16;
+  uint64_t* b_empty = a_full + 32;
+  uint64_t* d1_full = a_full + 48;
+  uint64_t* d1_empty = a_full + 49;
+  uint64_t* h_full = a_full + 50;
+  uint64_t* h_empty = a_full + 51;
+  uint64_t* d2_full = a_full + 52;
+  uint64_t* d2_empty = a_full + 53;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 54);
+  uint64_t* res_full = a_full + 56;   // [4 EPI2 warps][3 slots]
+  uint8_t* a_ring = smem + 1024;
+  const uint32_t a_bytes = static_cast<uint32_t>(p.nbox) * p.RB * 128;
+  constexpr uint32_t b_bytes = kRuC * 128;
+  uint8_t* b_ring = a_ring + static_cast<size_t>(p.SA) * a_bytes;
+  uint8_t* h_buf = b_ring + static_cast<size_t>(p.SB) * b_bytes;
+  uint8_t* stage_base = h_buf + kRuHBytes;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW7);
+    ptx::prefetch_tmap(&tmW1);
+    ptx::prefetch_tmap(&tmX);
+    if (p.raw_out) ptx::prefetch_tmap(&tmR);
+    if (p.act_out) ptx::prefetch_tmap(&tmO);
+    for (int i = 0; i < p.SA; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < p.SB; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
+    ptx::mbar_init(d1_full, 1);
+    ptx::mbar_init(d1_empty, 4);
+    ptx::mbar_init(h_full, 4);
+    ptx::mbar_init(h_empty, 1);
+    ptx::mbar_init(d2_full, 1);
+    ptx::mbar_init(d2_empty, 4);
+    for (int i = 0; i < 12; ++i) ptx::mbar_init(&res_full[i], 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t d1 = tmem_base, d2 = tmem_base + 256;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int b = tile / p.q_tiles;
+        const int q0 = (tile % p.q_tiles) * 256;
+        for (int ch = 0; ch < 2; ++ch) {
+          ptx::mbar_wait(&a_empty[as], aph ^ 1u);
+          ptx::mbar_expect_tx(&a_full[as], a_bytes);
+          for (int bx = 0; bx < p.nbox; ++bx)
+            ptx::tma_load_4d(a_ring + static_cast<size_t>(as) * a_bytes + bx * p.RB * 128, &tmA, &a_full[as], ch * 64, 0,
+                             q0 + p.slab_row0 + bx * p.RB, b);
+          if (++as == p.SA) { as = 0; aph ^= 1u; }
+          for (int t = 0; t < 7; ++t) {
+            ptx::mbar_wait(&b_empty[bs], bph ^ 1u);
+            ptx::mbar_expect_tx(&b_full[bs], b_bytes);
+            ptx::tma_load_3d(b_ring + static_cast<size_t>(bs) * b_bytes, &tmW7, &b_full[bs], ch * 64, 0, t);
+            if (++bs == p.SB) { bs = 0; bph ^= 1u; }
+          }
+        }
+        for (int kc = 0; kc < 2; ++kc) {   // the k=1 conv's weights ride the same ring
+          ptx::mbar_wait(&b_empty[bs], bph ^ 1u);
+          ptx::mbar_expect_tx(&b_full[bs], b_bytes);
+          ptx::tma_load_3d(b_ring + static_cast<size_t>(bs) * b_bytes, &tmW1, &b_full[bs], kc * 64, 0, 0);
+          if (++bs == p.SB) { bs = 0; bph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ UMMA issuer
+    if (ptx::elect_one()) {
+      const uint32_t idesc1 = ptx::idesc_bf16_f32(128, 256);
+      const uint32_t idesc2 = ptx::idesc_bf16_f32(128, 128);
+      const uint64_t desc_hi = (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+      const uint32_t a_lo0 = ((ptx::smem_u32(a_ring) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t b_lo0 = ((ptx::smem_u32(b_ring) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t h_lo0 = ((ptx::smem_u32(h_buf) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t a_stage16 = a_bytes >> 4, b_stage16 = b_bytes >> 4;
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0, d1e_ph = 0, d2e_ph = 0, hf_ph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        // ---- GEMM1 into D1
+        ptx::mbar_wait(d1_empty, d1e_ph ^ 1u);
+        d1e_ph ^= 1u;
+        ptx::tc_fence_after();
+        uint32_t accum = 0;
+        for (int ch = 0; ch < 2; ++ch) {
+          ptx::mbar_wait(&a_full[as], aph);
+          const int cur = as;
+          const uint32_t cur_lo = a_lo0 + as * a_stage16;
+          if (++as == p.SA) { as = 0; aph ^= 1u; }
+#pragma unroll 1
+          for (int t = 0; t < 7; ++t) {
+            ptx::mbar_wait(&b_full[bs], bph);
+            ptx::tc_fence_after();
+            const uint32_t al = cur_lo + p.tap_shift16[t];
+            const uint32_t bl = b_lo0 + bs * b_stage16;
+            ptx::umma_f16(d1, desc_hi | bl, desc_hi | al, idesc1, accum);
+            ptx::umma_f16(d1, desc_hi | (bl + 2), desc_hi | (al + 2), idesc1, 1u);
+            ptx::umma_f16(d1, desc_hi | (bl + 4), desc_hi | (al + 4), idesc1, 1u);
+            ptx::umma_f16(d1, desc_hi | (bl + 6), desc_hi | (al + 6), idesc1, 1u);
+            accum = 1u;
+            ptx::umma_commit(&b_empty[bs]);
+            if (++bs == p.SB) { bs = 0; bph ^= 1u; }
+          }
+          ptx::umma_commit(&a_empty[cur]);
+        }
+        ptx::umma_commit(d1_full);
+        // ---- GEMM2 into D2, one 128-row half at a time as EPI1 hands over h
+        const int s0 = bs;
+        const uint32_t ph0 = bph;
+        if (++bs == p.SB) { bs = 0; bph ^= 1u; }
+        const int s1 = bs;
+        const uint32_t ph1 = bph;
+        if (++bs == p.SB) { bs = 0; bph ^= 1u; }
+        ptx::mbar_wait(&b_full[s0], ph0);
+        ptx::mbar_wait(&b_full[s1], ph1);
+        ptx::mbar_wait(d2_empty, d2e_ph ^ 1u);
+        d2e_ph ^= 1u;
+        const uint32_t w_lo[2] = {b_lo0 + s0 * b_stage16, b_lo0 + s1 * b_stage16};
+        for (int half = 0; half < 2; ++half) {
+          ptx::mbar_wait(h_full, hf_ph);
+          hf_ph ^= 1u;
+          ptx::tc_fence_after();
+          const uint32_t dd = d2 + half * 128;
+#pragma unroll
+          for (int kc = 0; kc < 2; ++kc) {
+            const uint32_t hl = h_lo0 + kc * (16384 >> 4);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              ptx::umma_f16(dd, desc_hi | (w_lo[kc] + 2 * k), desc_hi | (hl + 2 * k), idesc2, (kc | k) ? 1u : 0u);
+          }
+          ptx::umma_commit(h_empty);
+        }
+        ptx::umma_commit(&b_empty[s0]);
+        ptx::umma_commit(&b_empty[s1]);
+        ptx::umma_commit(d2_full);
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ------------------------------------------------------------ EPI1: D1 -> bias, SnakeBeta -> h (shared memory)
+    const int quad = warp & 3;
+    const int c = quad * 32 + lane;                    // this thread's channel
+    const float bias = __ldg(p.bias7 + c);
+    const float sa = __ldg(p.s2_a + c), sib = __ldg(p.s2_inv_b + c);
+    // element (row r, channel c) of the K-major SWIZZLE_128B h tile: chunk tile c/64, 16-byte group (c%64)/8
+    uint8_t* hb[8];
+#pragma unroll
+    for (int x = 0; x < 8; ++x)
+      hb[x] = h_buf + (c >> 6) * 16384 + (((((c & 63) >> 3)) ^ x) << 4) + (c & 7) * 2;
+    uint32_t d1f_ph = 0, he_ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      ptx::mbar_wait(d1_full, d1f_ph);
+      d1f_ph ^= 1u;
+      ptx::tc_fence_after();
+      for (int half = 0; half < 2; ++half) {
+        ptx::mbar_wait(h_empty, he_ph ^ 1u);           // GEMM2 of the previous half has consumed h
+        he_ph ^= 1u;
+        for (int tb = 0; tb < 4; ++tb) {
+          uint32_t r[32];
+          __syncwarp();
+          ptx::tmem_ld_32x32(d1 + (static_cast<uint32_t>(quad * 32) << 16) + half * 128 + tb * 32, r);
+          ptx::tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = snake_beta<true>(__uint_as_float(r[j]) + bias, sa, sib);
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            *reinterpret_cast<__nv_bfloat16*>(hb[j & 7] + (tb * 32 + j) * 128) = __float2bfloat16(v[j]);
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(h_full);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(d1_empty);
+    }
+  } else if (warp >= 8) {
+    // ------------------------------------------------------------ EPI2: D2 -> bias, + skip -> stream / operand out
+    const int e = warp - 8;
+    const int quad = warp & 3;
+    const int c = quad * 32 + lane;
+    const int cbase = quad * 32;
+    const float bias = __ldg(p.bias1 + c);
+    float sa = 1.f, sib = 0.f;
+    if (p.sn_a) { sa = __ldg(p.sn_a + c); sib = __ldg(p.sn_inv_b + c); }
+    uint8_t* raw_ring = stage_base + e * ru_stage_bytes_per_warp(p.act_out);
+    uint8_t* act_ring = raw_ring + 3 * kRawBlkBytes;
+    uint64_t* my_res_full = res_full + e * 3;
+    const uint32_t rcol = (lane & 3) * 4, rchunk = lane >> 2;
+    const uint32_t acol = (lane & 7) * 2, achunk = lane >> 3;
+    int jr = 0, ja = 0;
+    uint32_t d2f_ph = 0, res_ph = 0;
+    if (lane == 0 && static_cast<int>(blockIdx.x) < p.total_tiles) {
+      const int b = blockIdx.x / p.q_tiles, q0 = (blockIdx.x % p.q_tiles) * 256;
+      ptx::mbar_expect_tx(&my_res_full[0], kRawBlkBytes);
+      ptx::tma_load_4d(raw_ring, &tmX, &my_res_full[0], cbase, 0, q0, b);
+    }
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int b = tile / p.q_tiles;
+      const int q0 = (tile % p.q_tiles) * 256;
+      ptx::mbar_wait(d2_full, d2f_ph);
+      d2f_ph ^= 1u;
+      ptx::tc_fence_after();
+      for (int item = 0; item < 8; ++item) {
+        const int r0 = q0 + item * 32;
+        if (lane == 0) {
+          ptx::bulk_wait_read<1>();
+          int nt = tile, ni = item + 1;
+          if (ni == 8) { nt = tile + gridDim.x; ni = 0; }
+          if (nt < p.total_tiles) {
+            const int sn = (jr + 1) % 3;
+            ptx::mbar_expect_tx(&my_res_full[sn], kRawBlkBytes);
+            ptx::tma_load_4d(raw_ring + sn * kRawBlkBytes, &tmX, &my_res_full[sn], cbase, 0,
+                             (nt % p.q_tiles) * 256 + ni * 32, nt / p.q_tiles);
+          }
+        }
+        ptx::mbar_wait(&my_res_full[jr], (res_ph >> jr) & 1u);
+        res_ph ^= (1u << jr);
+        uint32_t r[32];
+        __syncwarp();
+        ptx::tmem_ld_32x32(d2 + (static_cast<uint32_t>(quad * 32) << 16) + item * 32, r);
+        ptx::tmem_ld_wait();
+        uint8_t* const rblk = raw_ring + jr * kRawBlkBytes;
+        uint8_t* const ablk = act_ring + ja * kActBlkBytes;
+        uint8_t* rbase[8];
+#pragma unroll
+        for (int x = 0; x < 8; ++x) rbase[x] = rblk + ((rchunk ^ x) << 4) + rcol;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          v[j] = __uint_as_float(r[j]) + bias + *reinterpret_cast<const float*>(rbase[j & 7] + j * 128);
+        if (p.raw_out) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) *reinterpret_cast<float*>(rbase[j & 7] + j * 128) = v[j];
+        }
+        if (p.act_out) {
+          if (p.sn_a) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = snake_beta<true>(v[j], sa, sib);
+          }
+          uint8_t* abase[4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) abase[x] = ablk + ((achunk ^ x) << 4) + acol;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            *reinterpret_cast<__nv_bfloat16*>(abase[(j >> 1) & 3] + j * 64) = __float2bfloat16(v[j]);
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (p.raw_out) ptx::tma_store_4d(&tmR, rblk, cbase, 0, r0, b);
+          if (p.act_out) ptx::tma_store_4d(&tmO, ablk, cbase, 0, r0, b);
+          ptx::bulk_commit();
+        }
+        jr = (jr + 1 == 3) ? 0 : jr + 1;
+        ja ^= 1;
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(d2_empty);
+    }
+    if (lane == 0) ptx::bulk_wait<0>();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace kvae

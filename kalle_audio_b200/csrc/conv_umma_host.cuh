@@ -14,6 +14,7 @@
 
 #include "conv_umma.cuh"
 #include "conv_umma2.cuh"
+#include "conv_ru.cuh"
 
 namespace kvae {
 
@@ -404,6 +405,77 @@ inline cudaError_t launch_conv_umma2(const ConvLaunch2& L, cudaStream_t stream) 
     attr_set = true;
   }
   conv_umma2_kernel<<<L.grid, 384, L.smem, stream>>>(L.tmA, L.tmW, L.tmR, L.tmO, L.tmX, L.p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ fused ResidualUnit (conv_ru.cuh)
+struct RuLaunch {
+  CUtensorMap tmA, tmW7, tmW1, tmR, tmO, tmX;
+  RuParams p;
+  int grid = 0;
+  size_t smem = 0;
+};
+
+struct RuArgs {
+  const __nv_bfloat16* a = nullptr;       // SnakeBeta1(x), bf16 [B, T, 128]
+  const float* x = nullptr;               // residual stream, fp32 [B, T, 128]
+  const __nv_bfloat16* w7 = nullptr;      // packed [7][128][128]
+  const __nv_bfloat16* w1 = nullptr;      // packed [1][128][128]
+  const float* bias7 = nullptr;
+  const float* s2_a = nullptr;
+  const float* s2_inv_b = nullptr;
+  const float* bias1 = nullptr;
+  float* out_raw = nullptr;               // fp32 [B, T, 128] or nullptr
+  __nv_bfloat16* out_act = nullptr;       // bf16 [B, T, 128] or nullptr
+  const float* sn_a = nullptr;
+  const float* sn_inv_b = nullptr;
+};
+
+inline bool ru_supported(int C) { return C == kRuC; }
+
+inline bool prepare_conv_ru(const RuArgs& a, int B, int T, int dilation, RuLaunch& L, std::string& err) {
+  if (!a.a || !a.x || !a.w7 || !a.w1 || !a.bias7 || !a.bias1 || !a.s2_a || !a.s2_inv_b) { err = "fused RU: null argument"; return false; }
+  if (!a.out_raw && !a.out_act) { err = "fused RU: no output"; return false; }
+  RuParams& p = L.p;
+  std::memset(&p, 0, sizeof(p));
+  p.B = B;
+  p.T = T;
+  const int rows = 256 + 6 * dilation;
+  p.nbox = (rows + 255) / 256;
+  p.RB = (((rows + p.nbox - 1) / p.nbox) + 7) & ~7;
+  if (p.RB > 256) { err = "fused RU: dilation too large"; return false; }
+  p.slab_row0 = -3 * dilation;
+  for (int t = 0; t < 7; ++t) p.tap_shift16[t] = static_cast<uint32_t>(t * dilation * 8);
+  p.raw_out = a.out_raw ? 1 : 0;
+  p.act_out = a.out_act ? 1 : 0;
+  const size_t a_bytes = static_cast<size_t>(p.nbox) * p.RB * 128, b_bytes = kRuC * 128;
+  const size_t budget = 227 * 1024 - 2048 - kRuHBytes - 4 * static_cast<size_t>(ru_stage_bytes_per_warp(p.act_out));
+  p.SA = 2;
+  if (2 * a_bytes + 3 * b_bytes > budget) { err = "fused RU does not fit shared memory"; return false; }
+  p.SB = static_cast<int>(std::min<size_t>(8, (budget - 2 * a_bytes) / b_bytes));
+  p.q_tiles = (T + 255) / 256;
+  p.total_tiles = p.q_tiles * B;
+  p.bias7 = a.bias7; p.s2_a = a.s2_a; p.s2_inv_b = a.s2_inv_b; p.bias1 = a.bias1;
+  p.sn_a = a.sn_a; p.sn_inv_b = a.sn_inv_b;
+  if (!make_act_tmap(&L.tmA, a.a, B, T, kRuC, 1, p.RB, err)) return false;
+  if (!make_w_tmap(&L.tmW7, a.w7, 7, kRuC, kRuC, kRuC, err)) return false;
+  if (!make_w_tmap(&L.tmW1, a.w1, 1, kRuC, kRuC, kRuC, err)) return false;
+  if (!make_out_tmap(&L.tmX, a.x, B, T, kRuC, 1, true, err)) return false;
+  if (a.out_raw) { if (!make_out_tmap(&L.tmR, a.out_raw, B, T, kRuC, 1, true, err)) return false; } else L.tmR = L.tmX;
+  if (a.out_act) { if (!make_out_tmap(&L.tmO, a.out_act, B, T, kRuC, 1, false, err)) return false; } else L.tmO = L.tmX;
+  L.grid = std::min(p.total_tiles, sm_count());
+  L.smem = ru_smem_bytes(p);
+  return true;
+}
+
+inline cudaError_t launch_conv_ru(const RuLaunch& L, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_ru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  conv_ru_kernel<<<L.grid, 384, L.smem, stream>>>(L.tmA, L.tmW7, L.tmW1, L.tmR, L.tmO, L.tmX, L.p);
   return cudaGetLastError();
 }
 

@@ -323,7 +323,111 @@ static int run_perf(int idx, int ver, int epi) {
   return 0;
 }
 
+// Fused ResidualUnit check: x' = x + W1 * bf16(snake2(W7 (*) a + b7)) + b1 ; a' = bf16(snake_n(x'))
+static int run_ru(int dilation, int B, int T, int perf) {
+  const int C = 128;
+  std::mt19937 rng(99 + dilation);
+  std::normal_distribution<float> nd(0.f, 1.f);
+  const size_t n = (size_t)B * T * C;
+  std::vector<float> a(n), x(n), w7((size_t)7 * C * C), w1((size_t)C * C), b7(C), b1(C), s2a(C), s2ib(C), sna(C), snib(C);
+  for (auto& v : a) v = bf16r(nd(rng));
+  for (auto& v : x) v = nd(rng);
+  for (auto& v : w7) v = bf16r(nd(rng) / std::sqrt(7.f * C));
+  for (auto& v : w1) v = bf16r(nd(rng) / std::sqrt((float)C));
+  for (int i = 0; i < C; ++i) {
+    b7[i] = nd(rng) * 0.1f; b1[i] = nd(rng) * 0.1f;
+    s2a[i] = std::exp(nd(rng) * 0.3f); s2ib[i] = 1.f / (std::exp(nd(rng) * 0.3f) + 1e-9f);
+    sna[i] = std::exp(nd(rng) * 0.3f); snib[i] = 1.f / (std::exp(nd(rng) * 0.3f) + 1e-9f);
+  }
+  std::vector<__nv_bfloat16> ab(n), w7b(w7.size()), w1b(w1.size());
+  for (size_t i = 0; i < n; ++i) ab[i] = __float2bfloat16(a[i]);
+  for (size_t i = 0; i < w7.size(); ++i) w7b[i] = __float2bfloat16(w7[i]);
+  for (size_t i = 0; i < w1.size(); ++i) w1b[i] = __float2bfloat16(w1[i]);
+  __nv_bfloat16 *da, *dw7, *dw1, *dact;
+  float *dx, *draw, *db7, *db1, *ds2a, *ds2ib, *dsna, *dsnib;
+  CK(cudaMalloc(&da, n * 2)); CK(cudaMalloc(&dw7, w7.size() * 2)); CK(cudaMalloc(&dw1, w1.size() * 2));
+  CK(cudaMalloc(&dact, n * 2)); CK(cudaMalloc(&dx, n * 4)); CK(cudaMalloc(&draw, n * 4));
+  CK(cudaMalloc(&db7, C * 4)); CK(cudaMalloc(&db1, C * 4)); CK(cudaMalloc(&ds2a, C * 4)); CK(cudaMalloc(&ds2ib, C * 4));
+  CK(cudaMalloc(&dsna, C * 4)); CK(cudaMalloc(&dsnib, C * 4));
+  CK(cudaMemcpy(da, ab.data(), n * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dw7, w7b.data(), w7.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dw1, w1b.data(), w1.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dx, x.data(), n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(db7, b7.data(), C * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(db1, b1.data(), C * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(ds2a, s2a.data(), C * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(ds2ib, s2ib.data(), C * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dsna, sna.data(), C * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dsnib, snib.data(), C * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemset(draw, 0xff, n * 4)); CK(cudaMemset(dact, 0xff, n * 2));
+  RuArgs ra;
+  ra.a = da; ra.x = dx; ra.w7 = dw7; ra.w1 = dw1; ra.bias7 = db7; ra.s2_a = ds2a; ra.s2_inv_b = ds2ib; ra.bias1 = db1;
+  ra.out_raw = draw; ra.out_act = dact; ra.sn_a = dsna; ra.sn_inv_b = dsnib;
+  RuLaunch L;
+  std::string err;
+  if (!prepare_conv_ru(ra, B, T, dilation, L, err)) { printf("RU d=%d: prepare failed: %s\n", dilation, err.c_str()); return 3; }
+  printf("RU d=%d B=%d T=%d: grid %d smem %zu RB %d nbox %d SA %d SB %d tiles %d\n", dilation, B, T, L.grid, L.smem, L.p.RB,
+         L.p.nbox, L.p.SA, L.p.SB, L.p.total_tiles);
+  fflush(stdout);
+  CK(launch_conv_ru(L, 0));
+  CK(cudaDeviceSynchronize());
+  if (perf) {
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    for (int i = 0; i < 3; ++i) CK(launch_conv_ru(L, 0));
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < 10; ++i) CK(launch_conv_ru(L, 0));
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= 10;
+    const double flops = 2.0 * B * T * C * C * 8.0, bytes = (double)n * (2 + 4 + 4 + 2);
+    printf("PERF fused RU d=%d B=%d T=%d: %.3f ms  %.1f TFLOP/s  %.1f GB/s\n", dilation, B, T, ms, flops / ms * 1e-9, bytes / ms * 1e-6);
+    return 0;
+  }
+  std::vector<float> raw(n);
+  std::vector<__nv_bfloat16> act(n);
+  CK(cudaMemcpy(raw.data(), draw, n * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(act.data(), dact, n * 2, cudaMemcpyDeviceToHost));
+  double max_err = 0, max_err_act = 0, max_ref = 0; size_t bad = 0, first_bad = (size_t)-1;
+  std::vector<float> h((size_t)T * C);
+  for (int b = 0; b < B; ++b) {
+    for (int t = 0; t < T; ++t)
+      for (int co = 0; co < C; ++co) {
+        double s = b7[co];
+        for (int k = 0; k < 7; ++k) {
+          const int ti = t + (k - 3) * dilation;
+          if (ti < 0 || ti >= T) continue;
+          const float* ar = &a[((size_t)b * T + ti) * C];
+          const float* wr = &w7[((size_t)k * C + co) * C];
+          for (int ci = 0; ci < C; ++ci) s += (double)ar[ci] * wr[ci];
+        }
+        const double sn = std::sin(s * s2a[co]);
+        h[(size_t)t * C + co] = bf16r((float)(s + s2ib[co] * sn * sn));
+      }
+    for (int t = 0; t < T; ++t)
+      for (int co = 0; co < C; ++co) {
+        double s = b1[co] + x[((size_t)b * T + t) * C + co];
+        const float* wr = &w1[(size_t)co * C];
+        for (int ci = 0; ci < C; ++ci) s += (double)h[(size_t)t * C + ci] * wr[ci];
+        const size_t i = ((size_t)b * T + t) * C + co;
+        double e = std::fabs((double)raw[i] - s);
+        if (!(e <= 1e30)) e = 1e30;
+        max_err = std::max(max_err, e); max_ref = std::max(max_ref, std::fabs(s));
+        if (e > 3e-2) { if (!bad) first_bad = i; ++bad; }
+        const double sn = std::sin(s * sna[co]);
+        const double av = s + snib[co] * sn * sn;
+        double ea = std::fabs((double)__bfloat162float(act[i]) - av) / (1.0 + std::fabs(av));
+        if (!(ea <= 1e30)) ea = 1e30;
+        max_err_act = std::max(max_err_act, ea);
+      }
+  }
+  const bool ok = bad == 0 && max_err_act < 3e-2;
+  printf("RESULT fused RU d=%d B=%d T=%d: %s max_err %.3e max_ref %.3e bad %zu/%zu act_rel_err %.3e\n", dilation, B, T,
+         ok ? "PASS" : "FAIL", max_err, max_ref, bad, n, max_err_act);
+  if (bad) printf("  first bad at b=%zu t=%zu c=%zu got %.5f\n", first_bad / ((size_t)T * C), (first_bad / C) % T, first_bad % C, raw[first_bad]);
+  return ok ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
+  if (argc >= 5 && std::string(argv[1]) == "ru")
+    return run_ru(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), argc >= 6 ? atoi(argv[5]) : 0);
   if (argc >= 3 && std::string(argv[1]) == "perf") {
     int idx = atoi(argv[2]);
     if (idx < 0 || idx >= kNumPerf) return 4;
