@@ -10,10 +10,12 @@
 //   EPI1   h[t, c]    = bf16( SnakeBeta2( D1[c, t] + bias7[c] ) )  -> shared memory, K-major, 128-row halves
 //   GEMM2  D2[co2, t] = sum_c W1[co2, c] * h[t, c]                                 (2 halves x 2 x 4 MMAs of 128x128x16)
 //   EPI2   x'[t, c]   = D2[c, t] + bias1[c] + x[t, c]  -> fp32 stream (TMA store); a' = bf16(SnakeBeta_next(x')) (TMA store)
-// TMEM: D1 = columns [0,256), D2 = [256,512).  Warp roles (384 threads): 0 TMA producer, 1 UMMA issuer,
-// 2 TMEM allocator, 4-7 EPI1, 8-11 EPI2 (each EPI2 warp: skip-connection prefetch ring + in-place stores).
+// TMEM: D1 = columns [0,256), D2 = [256,512).  Warp roles (640 threads): 0 TMA producer, 1 UMMA issuer,
+// 2 TMEM allocator, 4-11 EPI1, 12-19 EPI2.  Both epilogues are instruction-latency bound per warp, so each gets
+// 8 warps (2 per TMEM lane quadrant) working on 32-channel x 16-row blocks; every EPI2 warp runs its own
+// skip-connection prefetch ring + in-place TMA stores.
 // Shared memory (227 KB): activation slab ring 2 x <=40 KB, weight ring 3-4 x 16 KB (W7 taps, then the two W1
-// chunks of the tile), h half 32 KB, EPI2 staging 4 x <=16 KB.
+// chunks of the tile), h half 32 KB, EPI2 staging 8 x <=8 KB.
 #pragma once
 #include <cuda_bf16.h>
 #include <cstdint>
@@ -42,13 +44,17 @@ struct RuParams {
 constexpr int kRuC = 128;
 constexpr int kRuHBytes = 2 * 128 * 128;   // h half: 2 K-chunks x [128 rows x 128 B]
 
-__host__ __device__ inline int ru_stage_bytes_per_warp(int act_out) { return 3 * kRawBlkBytes + (act_out ? 2 * kActBlkBytes : 0); }
+constexpr int kRuRawBlk = 16 * 128;        // 16 rows x 32 fp32, SWIZZLE_128B
+constexpr int kRuActBlk = 16 * 64;         // 16 rows x 32 bf16, SWIZZLE_64B
+constexpr int kRuThreads = 640;
+
+__host__ __device__ inline int ru_stage_bytes_per_warp(int act_out) { return 3 * kRuRawBlk + (act_out ? 2 * kRuActBlk : 0); }
 __host__ __device__ inline size_t ru_smem_bytes(const RuParams& p) {
   return 1024 + 1024 + static_cast<size_t>(p.SA) * p.nbox * p.RB * 128 + static_cast<size_t>(p.SB) * kRuC * 128 +
-         kRuHBytes + 4 * ru_stage_bytes_per_warp(p.act_out);
+         kRuHBytes + 8 * ru_stage_bytes_per_warp(p.act_out);
 }
 
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(kRuThreads, 1)
 conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW7,
                const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmR,
                const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmX,
@@ -67,7 +73,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* d2_full = a_full + 52;
   uint64_t* d2_empty = a_full + 53;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 54);
-  uint64_t* res_full = a_full + 56;   // [4 EPI2 warps][3 slots]
+  uint64_t* res_full = a_full + 56;   // [8 EPI2 warps][3 slots]
   uint8_t* a_ring = smem + 1024;
   const uint32_t a_bytes = static_cast<uint32_t>(p.nbox) * p.RB * 128;
   constexpr uint32_t b_bytes = kRuC * 128;
@@ -88,12 +94,12 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < p.SA; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.SB; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
     ptx::mbar_init(d1_full, 1);
-    ptx::mbar_init(d1_empty, 4);
-    ptx::mbar_init(h_full, 4);
+    ptx::mbar_init(d1_empty, 8);
+    ptx::mbar_init(h_full, 8);
     ptx::mbar_init(h_empty, 1);
     ptx::mbar_init(d2_full, 1);
-    ptx::mbar_init(d2_empty, 4);
-    for (int i = 0; i < 12; ++i) ptx::mbar_init(&res_full[i], 1);
+    ptx::mbar_init(d2_empty, 8);
+    for (int i = 0; i < 24; ++i) ptx::mbar_init(&res_full[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -207,9 +213,10 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::umma_commit(d2_full);
       }
     }
-  } else if (warp >= 4 && warp < 8) {
+  } else if (warp >= 4 && warp < 12) {
     // ------------------------------------------------------------ EPI1: D1 -> bias, SnakeBeta -> h (shared memory)
     const int quad = warp & 3;
+    const int sub = (warp - 4) >> 2;                   // which 16-column blocks of each 32 this warp takes
     const int c = quad * 32 + lane;                    // this thread's channel
     const float bias = __ldg(p.bias7 + c);
     const float sa = __ldg(p.s2_a + c), sib = __ldg(p.s2_inv_b + c);
@@ -226,17 +233,18 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int half = 0; half < 2; ++half) {
         ptx::mbar_wait(h_empty, he_ph ^ 1u);           // GEMM2 of the previous half has consumed h
         he_ph ^= 1u;
-        for (int tb = 0; tb < 4; ++tb) {
-          uint32_t r[32];
+#pragma unroll 1
+        for (int tb = sub; tb < 8; tb += 2) {          // 16-row blocks of this 128-row half
+          uint32_t r[16];
           __syncwarp();
-          ptx::tmem_ld_32x32(d1 + (static_cast<uint32_t>(quad * 32) << 16) + half * 128 + tb * 32, r);
+          ptx::tmem_ld_32x16(d1 + (static_cast<uint32_t>(quad * 32) << 16) + half * 128 + tb * 16, r);
           ptx::tmem_ld_wait();
-          float v[32];
+          float v[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = snake_beta<true>(__uint_as_float(r[j]) + bias, sa, sib);
+          for (int j = 0; j < 16; ++j) v[j] = snake_beta<true>(__uint_as_float(r[j]) + bias, sa, sib);
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            *reinterpret_cast<__nv_bfloat16*>(hb[j & 7] + (tb * 32 + j) * 128) = __float2bfloat16(v[j]);
+          for (int j = 0; j < 16; ++j)
+            *reinterpret_cast<__nv_bfloat16*>(hb[j & 7] + (tb * 16 + j) * 128) = __float2bfloat16(v[j]);
         }
         ptx::fence_proxy_async();
         __syncwarp();
@@ -246,26 +254,28 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(d1_empty);
     }
-  } else if (warp >= 8) {
+  } else if (warp >= 12) {
     // ------------------------------------------------------------ EPI2: D2 -> bias, + skip -> stream / operand out
-    const int e = warp - 8;
+    const int e = warp - 12;
     const int quad = warp & 3;
+    const int sub = e >> 2;
     const int c = quad * 32 + lane;
     const int cbase = quad * 32;
     const float bias = __ldg(p.bias1 + c);
     float sa = 1.f, sib = 0.f;
     if (p.sn_a) { sa = __ldg(p.sn_a + c); sib = __ldg(p.sn_inv_b + c); }
     uint8_t* raw_ring = stage_base + e * ru_stage_bytes_per_warp(p.act_out);
-    uint8_t* act_ring = raw_ring + 3 * kRawBlkBytes;
+    uint8_t* act_ring = raw_ring + 3 * kRuRawBlk;
     uint64_t* my_res_full = res_full + e * 3;
     const uint32_t rcol = (lane & 3) * 4, rchunk = lane >> 2;
     const uint32_t acol = (lane & 7) * 2, achunk = lane >> 3;
     int jr = 0, ja = 0;
     uint32_t d2f_ph = 0, res_ph = 0;
+    // items of this warp inside a tile: 16-row blocks sub, sub+2, ..., 14+sub
     if (lane == 0 && static_cast<int>(blockIdx.x) < p.total_tiles) {
       const int b = blockIdx.x / p.q_tiles, q0 = (blockIdx.x % p.q_tiles) * 256;
-      ptx::mbar_expect_tx(&my_res_full[0], kRawBlkBytes);
-      ptx::tma_load_4d(raw_ring, &tmX, &my_res_full[0], cbase, 0, q0, b);
+      ptx::mbar_expect_tx(&my_res_full[0], kRuRawBlk);
+      ptx::tma_load_4d(raw_ring, &tmX, &my_res_full[0], cbase, 0, q0 + sub * 16, b);
     }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / p.q_tiles;
@@ -273,48 +283,49 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       ptx::mbar_wait(d2_full, d2f_ph);
       d2f_ph ^= 1u;
       ptx::tc_fence_after();
-      for (int item = 0; item < 8; ++item) {
-        const int r0 = q0 + item * 32;
+#pragma unroll 1
+      for (int item = sub; item < 16; item += 2) {
+        const int r0 = q0 + item * 16;
         if (lane == 0) {
           ptx::bulk_wait_read<1>();
-          int nt = tile, ni = item + 1;
-          if (ni == 8) { nt = tile + gridDim.x; ni = 0; }
+          int nt = tile, ni = item + 2;
+          if (ni >= 16) { nt = tile + gridDim.x; ni = sub; }
           if (nt < p.total_tiles) {
             const int sn = (jr + 1) % 3;
-            ptx::mbar_expect_tx(&my_res_full[sn], kRawBlkBytes);
-            ptx::tma_load_4d(raw_ring + sn * kRawBlkBytes, &tmX, &my_res_full[sn], cbase, 0,
-                             (nt % p.q_tiles) * 256 + ni * 32, nt / p.q_tiles);
+            ptx::mbar_expect_tx(&my_res_full[sn], kRuRawBlk);
+            ptx::tma_load_4d(raw_ring + sn * kRuRawBlk, &tmX, &my_res_full[sn], cbase, 0,
+                             (nt % p.q_tiles) * 256 + ni * 16, nt / p.q_tiles);
           }
         }
         ptx::mbar_wait(&my_res_full[jr], (res_ph >> jr) & 1u);
         res_ph ^= (1u << jr);
-        uint32_t r[32];
+        uint32_t r[16];
         __syncwarp();
-        ptx::tmem_ld_32x32(d2 + (static_cast<uint32_t>(quad * 32) << 16) + item * 32, r);
+        ptx::tmem_ld_32x16(d2 + (static_cast<uint32_t>(quad * 32) << 16) + item * 16, r);
         ptx::tmem_ld_wait();
-        uint8_t* const rblk = raw_ring + jr * kRawBlkBytes;
-        uint8_t* const ablk = act_ring + ja * kActBlkBytes;
+        uint8_t* const rblk = raw_ring + jr * kRuRawBlk;
+        uint8_t* const ablk = act_ring + ja * kRuActBlk;
         uint8_t* rbase[8];
 #pragma unroll
         for (int x = 0; x < 8; ++x) rbase[x] = rblk + ((rchunk ^ x) << 4) + rcol;
-        float v[32];
+        float v[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
+        for (int j = 0; j < 16; ++j)
           v[j] = __uint_as_float(r[j]) + bias + *reinterpret_cast<const float*>(rbase[j & 7] + j * 128);
         if (p.raw_out) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) *reinterpret_cast<float*>(rbase[j & 7] + j * 128) = v[j];
+          for (int j = 0; j < 16; ++j) *reinterpret_cast<float*>(rbase[j & 7] + j * 128) = v[j];
         }
         if (p.act_out) {
           if (p.sn_a) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = snake_beta<true>(v[j], sa, sib);
+            for (int j = 0; j < 16; ++j) v[j] = snake_beta<true>(v[j], sa, sib);
           }
           uint8_t* abase[4];
 #pragma unroll
           for (int x = 0; x < 4; ++x) abase[x] = ablk + ((achunk ^ x) << 4) + acol;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
+          for (int j = 0; j < 16; ++j)
             *reinterpret_cast<__nv_bfloat16*>(abase[(j >> 1) & 3] + j * 64) = __float2bfloat16(v[j]);
         }
         ptx::fence_proxy_async();

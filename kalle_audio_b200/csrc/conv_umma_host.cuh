@@ -164,14 +164,15 @@ inline bool make_w_tmap(CUtensorMap* m, const void* w, int nslab, int Cout, int 
 
 // Output tensor [B, T, C] viewed as [B, T/P, P, C] for TMA transfers of 32-row x 32-channel blocks:
 // fp32 blocks are 128 B wide (SWIZZLE_128B), bf16 blocks 64 B (SWIZZLE_64B).
-inline bool make_out_tmap(CUtensorMap* m, const void* y, int B, int T, int C, int P, bool f32, std::string& err) {
+inline bool make_out_tmap(CUtensorMap* m, const void* y, int B, int T, int C, int P, bool f32, std::string& err,
+                          int box_rows = 32) {
   auto enc = tmap_encoder();
   if (!enc) { err = "cuTensorMapEncodeTiled unavailable"; return false; }
   if (T % P) { err = "output length not divisible by stride"; return false; }
   const cuuint64_t es = f32 ? 4 : 2;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)P, (cuuint64_t)(T / P), (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)P * C * es, (cuuint64_t)T * C * es};
-  cuuint32_t box[4] = {32, 1, 32, 1};
+  cuuint32_t box[4] = {32, 1, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
                    const_cast<void*>(y), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -449,7 +450,7 @@ inline bool prepare_conv_ru(const RuArgs& a, int B, int T, int dilation, RuLaunc
   p.raw_out = a.out_raw ? 1 : 0;
   p.act_out = a.out_act ? 1 : 0;
   const size_t a_bytes = static_cast<size_t>(p.nbox) * p.RB * 128, b_bytes = kRuC * 128;
-  const size_t budget = 227 * 1024 - 2048 - kRuHBytes - 4 * static_cast<size_t>(ru_stage_bytes_per_warp(p.act_out));
+  const size_t budget = 227 * 1024 - 2048 - kRuHBytes - 8 * static_cast<size_t>(ru_stage_bytes_per_warp(p.act_out));
   p.SA = 2;
   if (2 * a_bytes + 3 * b_bytes > budget) { err = "fused RU does not fit shared memory"; return false; }
   p.SB = static_cast<int>(std::min<size_t>(8, (budget - 2 * a_bytes) / b_bytes));
@@ -460,9 +461,9 @@ inline bool prepare_conv_ru(const RuArgs& a, int B, int T, int dilation, RuLaunc
   if (!make_act_tmap(&L.tmA, a.a, B, T, kRuC, 1, p.RB, err)) return false;
   if (!make_w_tmap(&L.tmW7, a.w7, 7, kRuC, kRuC, kRuC, err)) return false;
   if (!make_w_tmap(&L.tmW1, a.w1, 1, kRuC, kRuC, kRuC, err)) return false;
-  if (!make_out_tmap(&L.tmX, a.x, B, T, kRuC, 1, true, err)) return false;
-  if (a.out_raw) { if (!make_out_tmap(&L.tmR, a.out_raw, B, T, kRuC, 1, true, err)) return false; } else L.tmR = L.tmX;
-  if (a.out_act) { if (!make_out_tmap(&L.tmO, a.out_act, B, T, kRuC, 1, false, err)) return false; } else L.tmO = L.tmX;
+  if (!make_out_tmap(&L.tmX, a.x, B, T, kRuC, 1, true, err, 16)) return false;
+  if (a.out_raw) { if (!make_out_tmap(&L.tmR, a.out_raw, B, T, kRuC, 1, true, err, 16)) return false; } else L.tmR = L.tmX;
+  if (a.out_act) { if (!make_out_tmap(&L.tmO, a.out_act, B, T, kRuC, 1, false, err, 16)) return false; } else L.tmO = L.tmX;
   L.grid = std::min(p.total_tiles, sm_count());
   L.smem = ru_smem_bytes(p);
   return true;
@@ -475,7 +476,7 @@ inline cudaError_t launch_conv_ru(const RuLaunch& L, cudaStream_t stream) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  conv_ru_kernel<<<L.grid, 384, L.smem, stream>>>(L.tmA, L.tmW7, L.tmW1, L.tmR, L.tmO, L.tmX, L.p);
+  conv_ru_kernel<<<L.grid, kRuThreads, L.smem, stream>>>(L.tmA, L.tmW7, L.tmW1, L.tmR, L.tmO, L.tmX, L.p);
   return cudaGetLastError();
 }
 
