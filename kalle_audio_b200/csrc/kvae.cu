@@ -86,6 +86,7 @@ struct Step {
   // resolved by finalize():
   bool needs_raw = false, needs_act = false;
   int epi_snake = -1;      // SnakeBeta folded into the epilogue for the next (tensor-core) conv
+  int fuse = 0;            // 1: k7 conv of a ResidualUnit run by the fused kernel together with the next step (2)
 };
 
 struct Tensor {
@@ -109,7 +110,9 @@ struct PreparedRun {
   std::vector<dim3> direct_grid;
   std::vector<int> direct_cfg;      // 0: 32x64 tile, 1: 128x4 tile
   std::vector<size_t> direct_smem;
-  std::vector<int> kind;            // per step: 0 tensor-core, 1 generic, 2 waveform-in, 3 waveform-out
+  std::vector<int> kind;            // per step: 0 tensor-core, 1 generic, 2 waveform-in, 3 waveform-out,
+                                    //           4 fused ResidualUnit (this step + the next), 5 done by the previous step
+  std::vector<RuLaunch> ru;
   std::vector<WaveInParams> wave_in;
   std::vector<WaveOutParams> wave_out;
   Layout layout;
@@ -250,6 +253,28 @@ void finalize_steps(kvae_plan* p) {
     for (int j = k + 1; j < n; ++j)
       if (p->steps[j].residual_from == k) s.needs_raw = true;
   }
+  // ResidualUnits of 128-channel stages run as ONE kernel (conv_ru.cuh): k7 -> SnakeBeta -> k1 -> + skip
+  const char* nf = getenv("KVAE_NO_RU_FUSION");
+  const char* v1 = getenv("KVAE_CONV_V1");
+  if ((nf && nf[0] == '1') || (v1 && v1[0] == '1')) return;
+  for (int k = 1; k + 1 < n; ++k) {
+    Step& a = p->steps[k];
+    Step& b = p->steps[k + 1];
+    const ConvLayer& c7 = p->convs[a.conv];
+    const ConvLayer& c1 = p->convs[b.conv];
+    const bool shape = c7.umma && c1.umma && c7.g.kind == kConv && c1.g.kind == kConv && ru_supported(c7.g.Cin) &&
+                       c7.g.Cout == c7.g.Cin && c1.g.Cin == c7.g.Cin && c1.g.Cout == c7.g.Cin && c7.g.K == 7 &&
+                       c7.g.stride == 1 && c7.g.pad == 3 * c7.g.dilation && c1.g.K == 1 && c1.g.stride == 1 &&
+                       c1.g.pad == 0 && c7.has_bias && c1.has_bias;
+    const bool flow = b.residual_from == k - 1 && a.residual_from < 0 && !a.needs_raw && a.needs_act &&
+                      a.epi_snake >= 0 && p->steps[k - 1].needs_raw && p->steps[k - 1].needs_act && k + 1 < n - 1 + 1 &&
+                      (b.needs_raw || b.needs_act);
+    if (shape && flow && k + 1 != n - 1) {
+      a.fuse = 1;
+      b.fuse = 2;
+      ++k;
+    }
+  }
 }
 
 long long step_len(const Step& s, long long T) { return T * s.len_num / s.len_den; }
@@ -281,7 +306,7 @@ bool make_layout(const kvae_plan* p, int B, long long T, Layout& L, std::string&
       t.first = k;
       t.last = last_use;
     }
-    if (s.needs_act) {
+    if (s.needs_act && s.fuse != 1) {   // the fused ResidualUnit keeps its intermediate in shared memory
       Tensor& t = L.t[2 + 2 * k];
       t.bytes = static_cast<size_t>(B) * len * c.g.Cout * 2;
       t.first = k;
@@ -323,6 +348,7 @@ bool prepare_run(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R, std
   if (!make_layout(p, B, T, R.layout, err)) return false;
   R.umma.resize(n);
   R.umma2.resize(n);
+  R.ru.resize(n);
   {
     const char* e = getenv("KVAE_CONV_V1");   // development switch: the non-persistent first-generation kernel
     R.use_v1 = e && e[0] == '1';
@@ -350,6 +376,29 @@ bool prepare_run(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R, std
     void* act = s.needs_act ? tptr(2 + 2 * k) : nullptr;
     const void* res = (s.residual_from >= 0) ? tptr(1 + 2 * s.residual_from) : nullptr;
     if (s.residual_from >= 0 && !res) { err = "internal: residual tensor missing"; return false; }
+    if (s.fuse == 2 && !R.use_v1) { R.kind[k] = 5; continue; }
+    if (s.fuse == 1 && !R.use_v1) {
+      const Step& s1 = p->steps[k + 1];
+      const ConvLayer& c1 = p->convs[s1.conv];
+      RuArgs ra;
+      ra.a = static_cast<const __nv_bfloat16*>(tptr(2 + 2 * (k - 1)));
+      ra.x = static_cast<const float*>(tptr(1 + 2 * (k - 1)));
+      ra.w7 = c.w_umma;
+      ra.w1 = c1.w_umma;
+      ra.bias7 = c.bias;
+      ra.s2_a = p->snakes[s.epi_snake].a;
+      ra.s2_inv_b = p->snakes[s.epi_snake].inv_b;
+      ra.bias1 = c1.bias;
+      ra.out_raw = s1.needs_raw ? static_cast<float*>(tptr(1 + 2 * (k + 1))) : nullptr;
+      ra.out_act = s1.needs_act ? static_cast<__nv_bfloat16*>(tptr(2 + 2 * (k + 1))) : nullptr;
+      if (s1.epi_snake >= 0) {
+        ra.sn_a = p->snakes[s1.epi_snake].a;
+        ra.sn_inv_b = p->snakes[s1.epi_snake].inv_b;
+      }
+      if (!prepare_conv_ru(ra, B, static_cast<int>(T_out), c.g.dilation, R.ru[k], err)) return false;
+      R.kind[k] = 4;
+      continue;
+    }
     const bool k7same = c.g.kind == kConv && c.g.K == 7 && c.g.stride == 1 && c.g.dilation == 1 && c.g.pad == 3;
     if (!c.umma && p->precision == KVAE_PREC_BF16 && k7same && last && k > 0 && c.g.Cout <= 2 && !c.has_bias &&
         c.g.Cin == 128 && s.pre_snake >= 0 && !res) {
@@ -564,7 +613,11 @@ int run_plan(kvae_plan* p, const void* in, int in_dtype, void* out, int out_dtyp
   }
   for (int k = 0; k < n; ++k) {
     const ConvLayer& c = p->convs[p->steps[k].conv];
-    if (R.kind[k] == 3) {
+    if (R.kind[k] == 5) {
+      // computed by the fused ResidualUnit launch of the previous step
+    } else if (R.kind[k] == 4) {
+      KV_CUDA(launch_conv_ru(R.ru[k], st));
+    } else if (R.kind[k] == 3) {
       WaveOutParams& w = R.wave_out[k];
       w.y = out;
       w.y_f32 = (out_dtype == KVAE_F32);
@@ -595,7 +648,7 @@ int run_plan(kvae_plan* p, const void* in, int in_dtype, void* out, int out_dtyp
       if (k == n - 1) { d.out_raw = out; d.out_raw_f32 = (out_dtype == KVAE_F32); }
       KV_CUDA(launch_direct(d, R.direct_grid[k], R.direct_cfg[k], R.direct_smem[k], st));
     }
-    ++g_launches;
+    if (R.kind[k] != 5) ++g_launches;
     if (p->profile) KV_CUDA(cudaEventRecord(p->events[k + 1], st));
   }
   return 0;
