@@ -336,8 +336,15 @@ bool make_layout(const kvae_plan* p, int B, long long T, Layout& L, std::string&
     for (const Live& l : live)
       if (l.last >= k) keep.push_back(l);
     live.swap(keep);
+    if (p->steps[k].fuse == 2) continue;          // placed together with the fused head (below)
     place(L.t[1 + 2 * k]);
     place(L.t[2 + 2 * k]);
+    if (p->steps[k].fuse == 1) {
+      // the fused ResidualUnit kernel runs at step k and writes step k+1's tensors: they must not share
+      // memory with anything still live at step k (its own inputs included)
+      place(L.t[1 + 2 * (k + 1)]);
+      place(L.t[2 + 2 * (k + 1)]);
+    }
   }
   L.total = std::max<size_t>(total, 1024);
   return true;
