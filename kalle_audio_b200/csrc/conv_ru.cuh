@@ -227,11 +227,11 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       hb[x] = h_buf + (c >> 6) * 16384 + (((((c & 63) >> 3)) ^ x) << 4) + (c & 7) * 2;
     uint32_t d1f_ph = 0, he_ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      ptx::mbar_wait(d1_full, d1f_ph);
+      ptx::mbar_wait_relaxed(d1_full, d1f_ph);
       d1f_ph ^= 1u;
       ptx::tc_fence_after();
       for (int half = 0; half < 2; ++half) {
-        ptx::mbar_wait(h_empty, he_ph ^ 1u);           // GEMM2 of the previous half has consumed h
+        ptx::mbar_wait_relaxed(h_empty, he_ph ^ 1u);   // GEMM2 of the previous half has consumed h
         he_ph ^= 1u;
 #pragma unroll 1
         for (int tb = sub; tb < 8; tb += 2) {          // 16-row blocks of this 128-row half
@@ -280,7 +280,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / p.q_tiles;
       const int q0 = (tile % p.q_tiles) * 256;
-      ptx::mbar_wait(d2_full, d2f_ph);
+      ptx::mbar_wait_relaxed(d2_full, d2f_ph);
       d2f_ph ^= 1u;
       ptx::tc_fence_after();
 #pragma unroll 1
@@ -297,7 +297,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                              (nt % p.q_tiles) * 256 + ni * 16, nt / p.q_tiles);
           }
         }
-        ptx::mbar_wait(&my_res_full[jr], (res_ph >> jr) & 1u);
+        ptx::mbar_wait_relaxed(&my_res_full[jr], (res_ph >> jr) & 1u);
         res_ph ^= (1u << jr);
         uint32_t r[16];
         __syncwarp();
