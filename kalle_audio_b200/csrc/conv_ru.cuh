@@ -160,6 +160,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         d1e_ph ^= 1u;
         ptx::tc_fence_after();
         uint32_t accum = 0;
+        bool ready = false;
         for (int ch = 0; ch < 2; ++ch) {
           ptx::mbar_wait(&a_full[as], aph);
           const int cur = as;
@@ -167,17 +168,19 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (++as == p.SA) { as = 0; aph ^= 1u; }
 #pragma unroll 1
           for (int t = 0; t < 7; ++t) {
-            ptx::mbar_wait(&b_full[bs], bph);
+            if (!ready) ptx::mbar_wait(&b_full[bs], bph);
             ptx::tc_fence_after();
             const uint32_t al = cur_lo + p.tap_shift16[t];
             const uint32_t bl = b_lo0 + bs * b_stage16;
+            const int cb = bs;
+            if (++bs == p.SB) { bs = 0; bph ^= 1u; }
+            ready = ptx::mbar_try_wait(&b_full[bs], bph);      // poll the NEXT stage while this tap's MMAs issue
             ptx::umma_f16(d1, desc_hi | bl, desc_hi | al, idesc1, accum);
             ptx::umma_f16(d1, desc_hi | (bl + 2), desc_hi | (al + 2), idesc1, 1u);
             ptx::umma_f16(d1, desc_hi | (bl + 4), desc_hi | (al + 4), idesc1, 1u);
             ptx::umma_f16(d1, desc_hi | (bl + 6), desc_hi | (al + 6), idesc1, 1u);
             accum = 1u;
-            ptx::umma_commit(&b_empty[bs]);
-            if (++bs == p.SB) { bs = 0; bph ^= 1u; }
+            ptx::umma_commit(&b_empty[cb]);
           }
           ptx::umma_commit(&a_empty[cur]);
         }
@@ -227,11 +230,11 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       hb[x] = h_buf + (c >> 6) * 16384 + (((((c & 63) >> 3)) ^ x) << 4) + (c & 7) * 2;
     uint32_t d1f_ph = 0, he_ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      ptx::mbar_wait_relaxed(d1_full, d1f_ph);
+      ptx::mbar_wait(d1_full, d1f_ph);
       d1f_ph ^= 1u;
       ptx::tc_fence_after();
       for (int half = 0; half < 2; ++half) {
-        ptx::mbar_wait_relaxed(h_empty, he_ph ^ 1u);   // GEMM2 of the previous half has consumed h
+        ptx::mbar_wait(h_empty, he_ph ^ 1u);   // GEMM2 of the previous half has consumed h
         he_ph ^= 1u;
 #pragma unroll 1
         for (int tb = sub; tb < 8; tb += 2) {          // 16-row blocks of this 128-row half
@@ -280,7 +283,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       const int b = tile / p.q_tiles;
       const int q0 = (tile % p.q_tiles) * 256;
-      ptx::mbar_wait_relaxed(d2_full, d2f_ph);
+      ptx::mbar_wait(d2_full, d2f_ph);
       d2f_ph ^= 1u;
       ptx::tc_fence_after();
 #pragma unroll 1
@@ -297,7 +300,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                              (nt % p.q_tiles) * 256 + ni * 16, nt / p.q_tiles);
           }
         }
-        ptx::mbar_wait_relaxed(&my_res_full[jr], (res_ph >> jr) & 1u);
+        ptx::mbar_wait(&my_res_full[jr], (res_ph >> jr) & 1u);
         res_ph ^= (1u << jr);
         uint32_t r[16];
         __syncwarp();

@@ -64,14 +64,16 @@ __host__ __device__ inline size_t conv_umma_smem_bytes(const ConvParams& p) {
          static_cast<size_t>(p.SA) * p.nbox * p.RB * 128 + static_cast<size_t>(p.SB) * p.NT * 128;
 }
 
-// sin with a two-constant Cody-Waite reduction to [-pi, pi] in front of the MUFU approximation:
-// absolute error ~5e-7 for |x| up to ~1e4, at 4 extra FMA-pipe instructions (plain __sinf loses
-// accuracy quickly outside [-pi, pi]).
+// sin(x) through the MUFU approximation with an explicit range reduction in "revolutions":
+//   t = x/(2*pi);  f = t - round(t) in [-0.5, 0.5];  sin(x) = sin(2*pi*f).
+// round() uses the add-magic-constant trick (two FADDs) instead of FRND: FRND, MUFU.SIN and the bf16 convert all
+// issue on the 16-lane/clk XU pipe, and the fused epilogues were bound by exactly that pipe.
+// Absolute error ~1e-6 for |x| up to ~100 (plain __sinf degrades quickly outside [-pi, pi]).
 __device__ __forceinline__ float sin_fast(float x) {
-  const float k = rintf(x * 0.15915494309189535f);
-  float r = fmaf(-k, 6.2831854820251465f, x);       // 2*pi rounded to fp32
-  r = fmaf(-k, -1.7484556e-7f, r);                  // 2*pi - fp32(2*pi)
-  return __sinf(r);
+  const float t = x * 0.15915494309189535f;
+  const float k = __fadd_rn(__fadd_rn(t, 12582912.0f), -12582912.0f);   // nearest integer, valid for |t| < 2^22
+  const float f = t - k;
+  return __sinf(f * 6.283185307179586f);
 }
 
 template <bool kFastSin>

@@ -267,7 +267,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (p.bias) bias_s = __ldg(p.bias + c);
         if (p.snake_a) { sa_s = __ldg(p.snake_a + c); sib_s = __ldg(p.snake_inv_b + c); }
       }
-      ptx::mbar_wait_relaxed(&t_full[acc], accph);
+      ptx::mbar_wait(&t_full[acc], accph);
       ptx::tc_fence_after();
       const uint32_t acc_tmem = tmem_base + acc * acc_cols + (static_cast<uint32_t>(quad * 32) << 16);
       for (int item = g; item < ipt; item += 2) {
@@ -297,7 +297,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               ptx::tma_load_4d(raw_ring + sn * kRawBlkBytes, &tmX, &my_res_full[sn], cb, ph, rr, bb);
             }
           }
-          ptx::mbar_wait_relaxed(&my_res_full[jr], (res_ph >> jr) & 1u);
+          ptx::mbar_wait(&my_res_full[jr], (res_ph >> jr) & 1u);
           res_ph ^= (1u << jr);
         }
         uint32_t r[32];
