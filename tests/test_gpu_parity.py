@@ -337,3 +337,24 @@ def test_o12_full_length_batch_decode_properties(dev):
     d = (y2 - y).abs().amax(dim=(0, 1))
     assert float(d[: 1280 * 185].max()) == 0.0 and float(d[1280 * 215:].max()) == 0.0
     assert float(d[1280 * 195: 1280 * 206].max()) > 0.0
+
+
+def test_fused_residual_unit_matches_two_kernel_path(dev):
+    """The one-kernel ResidualUnit (conv_ru.cuh, 128-channel stages) against the k7 + k1 two-kernel path of the
+    same library (KVAE_NO_RU_FUSION=1) and against the oracle, incl. multi-tile persistence (T*40 rows)."""
+    import os
+    m = H.build("mid", 0, snake_seed=7)
+    sd = H.split_sd(m.state_dict(), "decoder.")
+    z = torch.randn(3, 64, 211, generator=torch.Generator().manual_seed(4))
+    ref = O.oobleck_decoder(sd, z, H.strides_of("mid"))
+    m.to(dev).set_precision("bf16")
+    y_fused = m.decode(z.to(dev))
+    os.environ["KVAE_NO_RU_FUSION"] = "1"
+    try:
+        m2 = H.build("mid", 0, snake_seed=7).to(dev).set_precision("bf16")
+        y_split = m2.decode(z.to(dev))
+    finally:
+        del os.environ["KVAE_NO_RU_FUSION"]
+    assert maxerr(y_fused, ref) <= bf16_tol(ref) and maxerr(y_split, ref) <= bf16_tol(ref)
+    # same arithmetic in both forms (bf16 operands, fp32 accumulation, same rounding points)
+    assert float((y_fused - y_split).abs().max()) <= 2e-5 * float(ref.abs().max())

@@ -60,6 +60,9 @@ try:
     profile(m.encoder.runner(dev), lambda: m.encode(x), "SAO encode B=1 L=442368 bf16")
     zb = torch.randn(8, 64, 216, device=dev)
     profile(m.decoder.runner(dev), lambda: m.decode(zb), "SAO decode B=8 T=216 bf16")
+    xb = 0.1 * torch.randn(8, 2, 442368, device=dev)
+    profile(m.encoder.runner(dev), lambda: m.encode(xb), "SAO encode B=8 L=442368 bf16")
+    del xb
     t0 = time.time()
     m.set_precision("fp32")
     z6 = z[:, :, :24].contiguous()
