@@ -64,17 +64,13 @@ __host__ __device__ inline size_t conv_umma_smem_bytes(const ConvParams& p) {
          static_cast<size_t>(p.SA) * p.nbox * p.RB * 128 + static_cast<size_t>(p.SB) * p.NT * 128;
 }
 
-// sin(x) through the MUFU approximation with an explicit range reduction in "revolutions":
-//   t = x/(2*pi);  f = t - round(t) in [-0.5, 0.5];  sin(x) = sin(2*pi*f).
-// round() uses the add-magic-constant trick (two FADDs) instead of FRND: FRND, MUFU.SIN and the bf16 convert all
-// issue on the 16-lane/clk XU pipe, and the fused epilogues were bound by exactly that pipe.
-// Absolute error ~1e-6 for |x| up to ~100 (plain __sinf degrades quickly outside [-pi, pi]).
-__device__ __forceinline__ float sin_fast(float x) {
-  const float t = x * 0.15915494309189535f;
-  const float k = __fadd_rn(__fadd_rn(t, 12582912.0f), -12582912.0f);   // nearest integer, valid for |t| < 2^22
-  const float f = t - k;
-  return __sinf(f * 6.283185307179586f);
-}
+// sin(x) for the bf16-mode epilogues: the MUFU approximation as is (one FMUL by 1/(2*pi) + MUFU.SIN; the unit
+// works on the fractional number of revolutions, so it is periodic by construction).  Its error is
+// ~4e-7 + |x| * 2^-24 (the rounding of x/(2*pi)), i.e. < 1e-5 for |x| < 100 -- far below the bf16 rounding
+// applied right after.  An explicit range reduction in front cost five more FMA-pipe instructions per
+// element, and the fused epilogues at C = 128 are bound by exactly that pipe (64 lanes/clk/SM), see
+// profiles/r01_conv_umma2_swap_k7_c128_B4.ncu-rep.
+__device__ __forceinline__ float sin_fast(float x) { return __sinf(x); }
 
 template <bool kFastSin>
 __device__ __forceinline__ float snake_beta(float v, float a, float inv_b) {
