@@ -15,7 +15,8 @@ The JSON line:
   e2e          same through the public module API with pinned HOST buffers: H2D of the audio and D2H of the
                decoded waveform inside the timed region
   decode_only  decode leg alone (the metric's name), same batch
-  roofline     tensor-core roofline of the dominant kernel (conv_umma_kernel): algorithmic FLOPs of its
+  roofline     tensor-core roofline of the dominant kernel family (conv_umma2_kernel and its fused ResidualUnit
+               form conv_ru_kernel): algorithmic FLOPs of its
                launches / their CUDA-event time, against MEASURED_PEAKS.json (sustained figure: the kernel is
                timed inside a long step)
   cpu_baseline oracle port of the reference arithmetic on the host cores, bounded sample (rank 0, N=1 only)
@@ -276,7 +277,7 @@ def run_cuda(args):
             "decode_only": {"value": world * audio_s_per_step * args.steps / (dec_ms * 1e-3), "unit": UNIT,
                             "ms_per_step": dec_ms / args.steps,
                             "tflops": dec_r.flops(B, CLIP_FRAMES) / (dec_ms / args.steps * 1e-3) / 1e12},
-            "roofline": {"bound": "tensor", "kernel": "conv_umma_kernel", "achieved": achieved,
+            "roofline": {"bound": "tensor", "kernel": "conv_umma2_kernel + conv_ru_kernel (tcgen05 conv family)", "achieved": achieved,
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
                          "peak_source": peaks["source"] + " (sustained; burst %.1f)" % peaks["bf16_tflops"],

@@ -294,13 +294,12 @@ struct ConvTuning2 {
 };
 
 inline int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
-  }
-  return n;
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& v = n[dev & 63];
+  if (!v && (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0)) v = 148;
+  return v;
 }
 
 // ep.out_raw: fp32 channels-last via TMA unless ep.out_raw_cf (then channels-first direct, any dtype).
@@ -357,8 +356,14 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
     p.SA = 2;
     p.SB = static_cast<int>(std::min<size_t>(8, (budget - 2 * a_bytes) / b_bytes));
     while (p.SA < 4 && (p.SA + 1) * a_bytes + p.SB * b_bytes <= budget) ++p.SA;
-    if (const char* e = getenv("KVAE_SB")) p.SB = std::max(2, std::min(p.SB, atoi(e)));   // tuning experiments
-    if (const char* e = getenv("KVAE_SA")) p.SA = std::max(1, std::min(p.SA, atoi(e)));
+    if (const char* e = getenv("KVAE_SA")) {   // tuning experiments: deeper / shallower activation ring
+      const int sa = std::max(1, std::min(8, atoi(e)));
+      if (sa * a_bytes + 2 * b_bytes <= budget) {
+        p.SA = sa;
+        p.SB = static_cast<int>(std::min<size_t>(8, (budget - sa * a_bytes) / b_bytes));
+      }
+    }
+    if (const char* e = getenv("KVAE_SB")) p.SB = std::max(2, std::min(p.SB, atoi(e)));
     ok = true;
     break;
   }
@@ -399,11 +404,13 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
 }
 
 inline cudaError_t launch_conv_umma2(const ConvLaunch2& L, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};   // per device (the attribute is per device context)
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev & 63] = true;
   }
   conv_umma2_kernel<<<L.grid, 384, L.smem, stream>>>(L.tmA, L.tmW, L.tmR, L.tmO, L.tmX, L.p);
   return cudaGetLastError();
@@ -470,23 +477,27 @@ inline bool prepare_conv_ru(const RuArgs& a, int B, int T, int dilation, RuLaunc
 }
 
 inline cudaError_t launch_conv_ru(const RuLaunch& L, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
     cudaError_t e = cudaFuncSetAttribute(conv_ru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev & 63] = true;
   }
   conv_ru_kernel<<<L.grid, kRuThreads, L.smem, stream>>>(L.tmA, L.tmW7, L.tmW1, L.tmR, L.tmO, L.tmX, L.p);
   return cudaGetLastError();
 }
 
 inline cudaError_t launch_conv_umma(const ConvLaunch& L, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev & 63] = true;
   }
   conv_umma_kernel<<<L.grid, 256, L.smem, stream>>>(L.tmA, L.tmW, L.p);
   return cudaGetLastError();

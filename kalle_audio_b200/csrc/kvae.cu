@@ -540,13 +540,15 @@ bool prepare_run(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R, std
 
 cudaError_t launch_wave_out(WaveOutParams& w, int Cout, int B, cudaStream_t st) {
   const size_t smem = wave_out_smem(w.Cin);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
     cudaError_t e = cudaFuncSetAttribute(conv_wave_out_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(conv_wave_out_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_set[dev & 63] = true;
   }
   w.B = B;
   w.tiles_per_clip = (w.T + kWaveOutTile - 1) / kWaveOutTile;
