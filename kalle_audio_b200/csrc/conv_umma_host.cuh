@@ -335,6 +335,12 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
     cands.push_back({MT, NT, tune.acc_stages ? tune.acc_stages : (2 * MT * NT <= 512 ? 2 : 1)});
   } else {
     const int mt = p.Tq_out > 128 ? 2 : 1;
+    // tiles the big tiling would give; short sequences (first decoder / last encoder stages, small batches)
+    // would leave most of the 148 SMs idle, so they get smaller tiles (more CTAs) instead
+    const long long big_tiles = static_cast<long long>(B) * tp.P_out * ((p.Tq_out + 128 * mt - 1) / (128 * mt)) *
+                                (g.Cout % 256 == 0 && g.Cout >= 512 ? g.Cout / 256 : (g.Cout + 127) / 128);
+    const bool starved = big_tiles * 10 < static_cast<long long>(sm_count()) * 6;
+    if (starved && g.Cout % 128 == 0) cands.push_back({1, 128, 2});
     if (g.Cout % 256 == 0 && g.Cout >= 512) cands.push_back({mt, 256, mt * 256 * 2 <= 512 ? 2 : 1});
     if (g.Cout % 128 == 0) cands.push_back({mt, 128, 2});
     if (g.Cout % 128 == 0) cands.push_back({1, 128, 2});
