@@ -358,3 +358,20 @@ def test_fused_residual_unit_matches_two_kernel_path(dev):
     assert maxerr(y_fused, ref) <= bf16_tol(ref) and maxerr(y_split, ref) <= bf16_tol(ref)
     # same arithmetic in both forms (bf16 operands, fp32 accumulation, same rounding points)
     assert float((y_fused - y_split).abs().max()) <= 2e-5 * float(ref.abs().max())
+
+
+def test_config4_streaming_chunks_equal_unchunked_o12_latent1024(dev):
+    """BASELINE config 4: O12 latent-1024 decoder, decode_audio(chunked=True, chunk 128, overlap 32) over T=375
+    (4 windows) equals the unchunked decode: overlap/2 = 16 frames > receptive field 10 frames."""
+    torch.manual_seed(0)
+    dec = k.OobleckDecoder(out_channels=1, channels=128, latent_dim=1024, c_mults=[1, 2, 4, 8, 16],
+                           strides=[2, 4, 4, 5, 8], use_snake=True, final_tanh=False).eval().to(dev).set_precision("bf16")
+    ae = k.AudioAutoencoder(None, dec, latent_dim=1024, downsampling_ratio=1280, sample_rate=16000, io_channels=1)
+    z = torch.randn(1, 1024, 375, device=dev)
+    full = ae.decode_audio(z)
+    chunked = ae.decode_audio(z, chunked=True, overlap=32, chunk_size=128)
+    assert full.shape == chunked.shape == (1, 1, 480000)
+    # identical arithmetic per output row away from window edges -> differences only from fp32 summation order: none
+    assert float((full - chunked).abs().max()) <= 1e-6
+    dec.enable_cuda_graphs(True)
+    assert torch.equal(ae.decode_audio(z, chunked=True, overlap=32, chunk_size=128), chunked)
