@@ -112,6 +112,56 @@ int kvae_conv1d_fwd(const void* x, void* y, const float* w_folded, const float* 
                     void* scratch, size_t scratch_bytes, void* stream);
 size_t kvae_conv1d_scratch_bytes(int Cin, int Cout, int K);
 
+/* ---- training step (BASELINE config 5) --------------------------------------------------------------
+ * The reference trains the autoencoder with plain autograd through the module tree
+ * (AutoencoderTrainingWrapper.training_step, stable_audio_tools/training/autoencoders.py:221-352: encode ->
+ * bottleneck -> decode -> losses -> manual_backward -> optimizer step); these entry points are what the
+ * autograd nodes of OobleckEncoder / OobleckDecoder, VAEBottleneck and the loss bind to.
+ *
+ * Parameters and gradients cross the boundary as ONE flat fp32 buffer per plan whose segments follow
+ * module.parameters() order: per layer [alpha][beta] of its SnakeBeta (blocks.py:313-329), then the conv's
+ * [bias][weight_g][weight_v] (old-style torch weight_norm, dac.nn.layers.WNConv1d/WNConvTranspose1d). */
+long long kvae_plan_param_count(const kvae_plan* plan);
+/* segment sizes (floats) of the flat buffer, in order; returns the number of segments */
+int kvae_plan_param_sizes(const kvae_plan* plan, long long* sizes, int max_segments);
+/* Folds weight norm and packs every layer from the flat buffer (replaces kvae_plan_set_conv / _set_snake, one
+ * call per optimizer step).  train != 0 also packs the operands of the data-gradient kernels. */
+int kvae_plan_load_params(kvae_plan* plan, const float* params, int snake_logscale, int train, void* stream);
+/* workspace of a training pass: every layer's pre-activation stream and operand stay live for the backward
+ * pass, plus the backward scratch */
+size_t kvae_train_workspace_bytes(kvae_plan* plan, int B, long long T);
+/* OobleckEncoder.forward / OobleckDecoder.forward under autograd: same result as kvae_encode / kvae_decode,
+ * activations saved in `workspace` (must stay untouched until kvae_backward) */
+int kvae_forward_train(kvae_plan* plan, const void* x, int x_dtype, void* y, int y_dtype, int B, long long T,
+                       void* workspace, size_t workspace_bytes, void* stream);
+/* Backward of that pass: gy [B, C_out, T_out] -> grads (flat, overwritten; kvae_plan_param_count floats) and,
+ * when gx != NULL, gx [B, C_in, T].  x is the forward input.  params != NULL (the flat buffer the pass ran
+ * with) finishes with the weight-norm backward so the weight_g / weight_v segments hold d g / d v; with
+ * params == NULL the weight_v segments hold the gradient of the FOLDED weight and weight_g is zero. */
+int kvae_backward(kvae_plan* plan, const void* x, int x_dtype, const void* gy, int gy_dtype, void* gx, int gx_dtype,
+                  int B, long long T, void* workspace, size_t workspace_bytes, float* grads, const float* params,
+                  void* stream);
+/* torch.nn.utils.weight_norm backward, dim=0: (dw, v, g) -> (dv, dg); dv may alias dw. */
+int kvae_weight_norm_bwd(const float* v, const float* g, const float* dw, float* dv, float* dg, int dim0, int inner,
+                         void* stream);
+/* SnakeBeta backward on channels-last rows [rows, C] fp32 (blocks.py:301-302 differentiated): gx, d alpha,
+ * d beta (overwritten).  scratch: >= 2*C floats. */
+int kvae_snake_bwd(const float* x, const float* gy, float* gx, const float* alpha, const float* beta, int logscale,
+                   float* d_alpha, float* d_beta, long long rows, int C, void* scratch, void* stream);
+/* vae_sample backward (bottleneck.py:51-62): gz (may be NULL) and the scalar gkl (device fp32, may be NULL)
+ * -> gmean, gscale. */
+int kvae_vae_sample_bwd(const void* mean, const void* scale, const void* noise, const void* gz, const float* gkl,
+                        void* gmean, void* gscale, int B, int D, long long T, int dtype, void* stream);
+/* sigma-VAE reconstruction term: *loss = sum_i [0.5 ((x_i - xhat_i)/sigma)^2 + log sigma + 0.5 log 2 pi] / B and,
+ * when gxhat != NULL, its gradient w.r.t. xhat.  scratch: >= 8*1024 bytes.  (The reference's sigma-vae symlink
+ * dangles; SURVEY.md section 8c defines this form.) */
+int kvae_gaussian_nll(const void* x, const void* xhat, void* gxhat, float* loss, int B, size_t per_item,
+                      float log_sigma, int dtype, void* scratch, void* stream);
+/* torch.optim.AdamW step over a flat fp32 buffer; grads are multiplied by grad_scale first (1/world_size
+ * after a summing all-reduce).  step counts from 1. */
+int kvae_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+
 /* ---- latent sampling ---- */
 /* sample(mean,'fix') of model_sigmaVAE.py:153-178 / 187-213: out = mean + std*noise, rounded exactly as
  * torch does (mul, then add).  std_noise != NULL selects 'gaussian': per-item std_b = std_noise[b]*value. */

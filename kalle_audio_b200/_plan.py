@@ -139,6 +139,90 @@ class PlanRunner:
             launch(xin, out)
         return out if out.dtype == out_dtype else out.to(out_dtype)
 
+    # ------------------------------------------------------------------ training pass
+    def param_list(self) -> List[torch.nn.Parameter]:
+        """Parameters in the flat-buffer order of the plan (= module.parameters() order); checked against
+        the segment sizes libkvae reports."""
+        module = self.module_ref()
+        params = list(module.parameters())
+        L = _lib.lib()
+        n = 4 * (len(self.convs) + len(self.snakes)) + 8
+        sizes = (C.c_longlong * n)()
+        got = L.kvae_plan_param_sizes(self.handle, sizes, n)
+        if got < 0:
+            raise _lib.KvaeError(L.kvae_last_error().decode())
+        if [p.numel() for p in params] != [int(sizes[i]) for i in range(got)]:
+            raise _lib.KvaeError("training needs weight-normalised modules whose parameters() follow the reference's "
+                                 "order (alpha, beta, bias, weight_g, weight_v per layer); remove_weight_norm'ed or "
+                                 "re-ordered modules are inference-only")
+        return params
+
+    def flatten(self, params) -> torch.Tensor:
+        """One fp32 buffer holding every parameter in plan order.  Zero-copy when the parameters already are
+        views of such a buffer (``training.flatten_parameters``), else a ``torch.cat``."""
+        flat = getattr(self, "flat_master", None)
+        if flat is not None and flat.device == self.device:
+            off, ok = flat.data_ptr(), True
+            for p in params:
+                if p.data_ptr() != off or p.dtype != torch.float32:
+                    ok = False
+                    break
+                off += p.numel() * 4
+            if ok:
+                return flat
+        return torch.cat([p.detach().reshape(-1).float() for p in params])
+
+    def forward_train(self, x: torch.Tensor, flat: torch.Tensor, out_channels: int, ratio: int,
+                      out_dtype: torch.dtype):
+        """Forward pass that keeps every layer's activations in a fresh workspace; returns (y, xin, workspace)."""
+        _lib.require_cuda(x, "fused plan (training)")
+        if x.device != self.device:
+            raise _lib.KvaeError(f"input on {x.device}, plan on {self.device}")
+        if x.dim() != 3:
+            raise ValueError("expected [B, C, T]")
+        B, _, T = x.shape
+        if B == 0 or T == 0:
+            raise ValueError("empty input")
+        if self.direction == _lib.KVAE_ENCODER and T % ratio:
+            raise ValueError(f"audio length {T} is not a multiple of the downsampling ratio {ratio}")
+        L = _lib.lib()
+        st = _lib.stream_ptr(self.device)
+        logscale = {bool(m.alpha_logscale) for m in self.snakes}
+        if len(logscale) > 1:
+            raise _lib.KvaeError("mixed alpha_logscale settings are not supported in training")
+        _lib.check(L.kvae_plan_load_params(self.handle, flat.data_ptr(), int(logscale.pop() if logscale else True), 1, st))
+        self._fingerprint = None        # inference packs are refreshed lazily from the module parameters
+        xin = x.detach()
+        xin = xin if xin.dtype in (torch.float32, torch.bfloat16) else xin.float()
+        xin = xin.contiguous()
+        kdtype = out_dtype if out_dtype in (torch.float32, torch.bfloat16) else torch.float32
+        need = L.kvae_train_workspace_bytes(self.handle, B, T)
+        if need == 0:
+            raise _lib.KvaeError(L.kvae_last_error().decode())
+        ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+        out = torch.empty((B, out_channels, self.out_length(T, ratio)), dtype=kdtype, device=self.device)
+        _lib.check(L.kvae_forward_train(self.handle, xin.data_ptr(), _lib.dtype_code(xin.dtype), out.data_ptr(),
+                                        _lib.dtype_code(kdtype), B, T, ws.data_ptr(), ws.numel(), st))
+        return (out if out.dtype == out_dtype else out.to(out_dtype)), xin, ws
+
+    def backward(self, xin: torch.Tensor, gy: torch.Tensor, ws: torch.Tensor, flat: torch.Tensor, need_gx: bool):
+        """(gx or None, flat gradient buffer) for the pass whose activations live in ``ws``."""
+        L = _lib.lib()
+        B, _, T = xin.shape
+        g = gy.detach()
+        g = g if g.dtype in (torch.float32, torch.bfloat16) else g.float()
+        g = g.contiguous()
+        grads = torch.empty(L.kvae_plan_param_count(self.handle), dtype=torch.float32, device=self.device)
+        gx = torch.empty_like(xin, dtype=torch.float32) if need_gx else None
+        _lib.check(L.kvae_backward(self.handle, xin.data_ptr(), _lib.dtype_code(xin.dtype), g.data_ptr(),
+                                   _lib.dtype_code(g.dtype), _lib.ptr(gx), _lib.KVAE_F32, B, T, ws.data_ptr(),
+                                   ws.numel(), grads.data_ptr(), flat.data_ptr(), _lib.stream_ptr(self.device)))
+        self.last_grads = grads
+        hook = getattr(self, "grads_ready_hook", None)
+        if hook is not None:
+            hook(self, grads)
+        return gx, grads
+
     def set_profiling(self, enable: bool) -> None:
         _lib.check(_lib.lib().kvae_plan_profile(self.handle, int(enable)))
 
@@ -153,6 +237,35 @@ class PlanRunner:
 
     def flops(self, B: int, T: int) -> float:
         return float(_lib.lib().kvae_plan_flops(self.handle, B, T))
+
+
+class PlanFunction(torch.autograd.Function):
+    """autograd node of OobleckEncoder.forward / OobleckDecoder.forward: one kvae_forward_train call forward,
+    one kvae_backward call backward (the reference differentiates ~150 eager ops per direction instead)."""
+
+    @staticmethod
+    def forward(ctx, runner: "PlanRunner", x, out_channels, ratio, out_dtype, *params):
+        flat = runner.flatten(params)
+        y, xin, ws = runner.forward_train(x, flat, out_channels, ratio, out_dtype)
+        ctx.runner, ctx.xin, ctx.ws, ctx.flat = runner, xin, ws, flat
+        ctx.x_dtype = x.dtype
+        ctx.shapes = [p.shape for p in params]
+        ctx.dtypes = [p.dtype for p in params]
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        gx, grads = ctx.runner.backward(ctx.xin, gy, ctx.ws, ctx.flat, ctx.needs_input_grad[1])
+        ctx.ws = None
+        outs, off = [], 0
+        for shape, dt in zip(ctx.shapes, ctx.dtypes):
+            n = shape.numel()
+            g = grads[off:off + n].view(shape)
+            outs.append(g if dt == torch.float32 else g.to(dt))
+            off += n
+        if gx is not None and gx.dtype != ctx.x_dtype:
+            gx = gx.to(ctx.x_dtype)
+        return (None, gx, None, None, None, *outs)
 
 
 class PlanCache:

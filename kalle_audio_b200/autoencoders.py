@@ -20,7 +20,7 @@ import torch
 from torch import nn
 
 from . import _lib
-from ._plan import PlanCache
+from ._plan import PlanCache, PlanFunction
 from .bottleneck import Bottleneck, create_bottleneck_from_config
 from .layers import SnakeBeta, WNConv1d, WNConvTranspose1d, guard_grad
 
@@ -158,8 +158,11 @@ class _OobleckBase(nn.Module):
     def forward(self, x):
         _lib.require_cuda(x, type(self).__name__ + ".forward")
         r = self.runner(x.device)
-        y = r.run(x, self._out_channels_for_plan, self._ratio, self._out_dtype(x))
-        return guard_grad(y, list(self.parameters()))
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            # training: saved activations + hand-written backward (kvae_forward_train / kvae_backward)
+            return PlanFunction.apply(r, x, self._out_channels_for_plan, self._ratio, self._out_dtype(x),
+                                      *r.param_list())
+        return r.run(x, self._out_channels_for_plan, self._ratio, self._out_dtype(x))
 
     def _apply(self, fn, *args, **kwargs):
         out = super()._apply(fn, *args, **kwargs)

@@ -24,11 +24,25 @@ enum ConvKind { kConv = 0, kConvT = 1 };
 struct ConvGeom {
   int kind;      // kConv: nn.Conv1d ; kConvT: nn.ConvTranspose1d
   int Cin, Cout, K, stride, dilation, pad;
+  int out_pad = 0;   // ConvTranspose1d output_padding (only the data-gradient geometries use it)
   int out_len(int T_in) const {
     if (kind == kConv) return (T_in + 2 * pad - dilation * (K - 1) - 1) / stride + 1;
-    return (T_in - 1) * stride - 2 * pad + dilation * (K - 1) + 1;
+    return (T_in - 1) * stride - 2 * pad + dilation * (K - 1) + 1 + out_pad;
   }
 };
+
+// Geometry of the data gradient of `g` for an input of length T_in: the gradient of a Conv1d w.r.t. its
+// input is the ConvTranspose1d with the same weight tensor (and vice versa), so the backward pass reuses
+// the forward kernels with the weight re-packed under the opposite kind.
+inline ConvGeom dgrad_geom(const ConvGeom& g, int T_in) {
+  ConvGeom d = g;
+  d.kind = (g.kind == kConv) ? kConvT : kConv;
+  d.Cin = g.Cout;
+  d.Cout = g.Cin;
+  d.out_pad = 0;
+  if (d.kind == kConvT) d.out_pad = T_in - d.out_len(g.out_len(T_in));
+  return d;
+}
 
 inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 inline int posmod(int a, int b) { int r = a % b; return r < 0 ? r + b : r; }
@@ -57,14 +71,14 @@ inline bool build_taps(const ConvGeom& g, bool per_tap_slab, TapPlan& tp, std::s
     }
     by_out_phase.push_back(v);
   } else {
-    if (g.dilation != 1) { err = "dilated transposed conv unsupported"; return false; }
+    if (g.dilation != 1 && g.stride != 1) { err = "dilated strided transposed conv unsupported"; return false; }
     tp.P_in = 1;
     tp.P_out = g.stride;
     for (int phi = 0; phi < g.stride; ++phi) {
       std::vector<Raw> v;
       for (int k = 0; k < g.K; ++k)
-        if (posmod(phi + g.pad - k, g.stride) == 0)     // t_out = q*s+phi = t_in*s - pad + k
-          v.push_back({0, floordiv(phi + g.pad - k, g.stride), k});
+        if (posmod(phi + g.pad - k * g.dilation, g.stride) == 0)     // t_out = q*s+phi = t_in*s - pad + k*dil
+          v.push_back({0, floordiv(phi + g.pad - k * g.dilation, g.stride), k});
       by_out_phase.push_back(v);
     }
   }

@@ -107,6 +107,63 @@ __global__ void pack_weights_kernel(const float* w, int transposed, int Cout, in
   }
 }
 
+// ---------------------------------------------------------------- fold + pack from a flat parameter buffer
+// scale[i] = g[i] / ||v[i, :]||  (one block per dim-0 row); the tiled kernel below applies it while packing.
+__global__ void weight_norm_scale_kernel(const float* v, const float* g, float* scale, int inner) {
+  __shared__ float red[32];
+  const size_t base = static_cast<size_t>(blockIdx.x) * inner;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) { const float x = v[base + i]; s = fmaf(x, x, s); }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) scale[blockIdx.x] = g[blockIdx.x] / sqrtf(t);
+  }
+}
+
+// v [R][Cc][K] fp32 (torch layout: Conv1d R = Cout, Cc = Cin; ConvTranspose1d R = Cin, Cc = Cout), scaled per
+// row, written in both index orders and both precisions through a shared-memory tile so that reads and
+// writes are coalesced:  out1[(k*R + r)*Cc + c]   and   out2[(k*Cc + c)*R + r].
+// grid (ceil(R/16), ceil(Cc/32)), block 256, K <= 16.
+constexpr int kPackTR = 16, kPackTC = 32, kPackMaxK = 16;
+__global__ void __launch_bounds__(256)
+fold_pack_kernel(const float* v, const float* scale, int R, int Cc, int K, __nv_bfloat16* out1_bf16, float* out1_f32,
+                 __nv_bfloat16* out2_bf16, float* out2_f32) {
+  __shared__ float tile[kPackTR][kPackTC * kPackMaxK + 1];
+  const int r0 = blockIdx.x * kPackTR, c0 = blockIdx.y * kPackTC;
+  const int w = kPackTC * K;                 // contiguous floats per row of the tile
+  for (int idx = threadIdx.x; idx < kPackTR * w; idx += 256) {
+    const int r = idx / w, j = idx % w;      // j = c_local*K + k
+    float val = 0.f;
+    if (r0 + r < R && c0 + j / K < Cc) val = v[(static_cast<size_t>(r0 + r) * Cc + c0) * K + j] * scale[r0 + r];
+    tile[r][j] = val;
+  }
+  __syncthreads();
+  // out1: c fastest
+  for (int idx = threadIdx.x; idx < K * kPackTR * kPackTC; idx += 256) {
+    const int c = idx % kPackTC, r = (idx / kPackTC) % kPackTR, k = idx / (kPackTC * kPackTR);
+    if (r0 + r < R && c0 + c < Cc) {
+      const float val = tile[r][c * K + k];
+      const size_t o = (static_cast<size_t>(k) * R + r0 + r) * Cc + c0 + c;
+      if (out1_bf16) out1_bf16[o] = __float2bfloat16(val);
+      if (out1_f32) out1_f32[o] = val;
+    }
+  }
+  // out2: r fastest
+  for (int idx = threadIdx.x; idx < K * kPackTR * kPackTC; idx += 256) {
+    const int r = idx % kPackTR, c = (idx / kPackTR) % kPackTC, k = idx / (kPackTC * kPackTR);
+    if (r0 + r < R && c0 + c < Cc) {
+      const float val = tile[r][c * K + k];
+      const size_t o = (static_cast<size_t>(k) * Cc + c0 + c) * R + r0 + r;
+      if (out2_bf16) out2_bf16[o] = __float2bfloat16(val);
+      if (out2_f32) out2_f32[o] = val;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- latent sampling
 // sample(mean, 'fix') of model_sigmaVAE.py:153-178,187-213: mean + std * noise, evaluated as torch
 // does -- two separately rounded operations (mul then add), never an FMA -- so the result is

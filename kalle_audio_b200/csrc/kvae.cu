@@ -25,6 +25,7 @@
 #include "conv_edge.cuh"
 #include "conv_umma_host.cuh"
 #include "elementwise.cuh"
+#include "train.cuh"
 
 using namespace kvae;
 
@@ -64,17 +65,27 @@ struct ConvLayer {
   ConvGeom g;
   bool has_bias = true;
   bool umma = false;
-  __nv_bfloat16* w_umma = nullptr;
-  float* w_direct = nullptr;
+  __nv_bfloat16* w_umma = nullptr;    // [K][Cout][Cin] bf16: forward tensor-core operand
+  float* w_direct = nullptr;          // [K][Cin][Cout] fp32: forward CUDA-core operand
+  // training only (allocated by kvae_plan_load_params(train = 1)): the data-gradient kernels see the same
+  // weight tensor under the opposite kind (Cin <-> Cout), i.e. the other index order of each precision
+  __nv_bfloat16* w_umma_d = nullptr;  // [K][Cin][Cout] bf16
+  float* w_direct_d = nullptr;        // [K][Cout][Cin] fp32
   float* bias = nullptr;
   bool set = false;
+  // offsets (in floats) into the flat parameter / gradient buffer: [bias][weight_g][weight_v]
+  long long off_bias = -1, off_g = -1, off_v = -1;
+  int dim0() const { return g.kind == kConvT ? g.Cin : g.Cout; }
+  size_t numel() const { return static_cast<size_t>(g.Cin) * g.Cout * g.K; }
 };
 
 struct SnakeLayer {
   int C = 0;
   float* a = nullptr;
   float* inv_b = nullptr;
+  int logscale = 1;
   bool set = false;
+  long long off_alpha = -1, off_beta = -1;   // flat parameter / gradient offsets
 };
 
 // one convolution of the chain, with its fused prologue / epilogue
@@ -116,6 +127,26 @@ struct PreparedRun {
   std::vector<WaveInParams> wave_in;
   std::vector<WaveOutParams> wave_out;
   Layout layout;
+  // ---- training runs only: the backward pass over the saved activations
+  struct Bwd {
+    int dgrad_kind = 0;             // 0 none, 1 tensor-core (conv_umma2 under the dgrad geometry), 2 CUDA-core
+    ConvLaunch2 dg_umma;
+    DirectParams dg_direct;
+    dim3 dg_grid;
+    int dg_cfg = 0;
+    size_t dg_smem = 0;
+    WgradParams wg;
+    dim3 wg_grid;
+    bool wg_x_is_D = false, wg_x_is_S = false;   // step 0: the operand is the caller's input tensor
+    bool has_sb = false;
+    SnakeBwdParams sb;
+    dim3 sb_grid;
+  };
+  std::vector<Bwd> bwd;
+  SnakeBwdParams sb_last;           // bf16 copy + bias gradient of the incoming output gradient
+  dim3 sb_last_grid;
+  size_t off_G[3] = {0, 0, 0}, off_Gb[3] = {0, 0, 0}, off_dA = 0;   // byte offsets in the workspace
+  size_t total = 0;                 // forward + backward bytes
 };
 
 }  // namespace
@@ -127,9 +158,15 @@ struct kvae_plan {
   int device = 0;
   std::vector<ConvLayer> convs;
   std::vector<SnakeLayer> snakes;
-  std::vector<Step> steps;
+  std::vector<Step> steps;    // inference: fused ResidualUnits, only the tensors the next layer needs
+  std::vector<Step> tsteps;   // training: every layer's pre-activation stream is kept for the backward pass
   int ratio = 1;
+  long long n_params = 0;     // floats in the flat parameter / gradient buffer
+  std::vector<long long> param_sizes;   // segment sizes in module.parameters() order
+  bool train_packs = false;
+  float* scale_scratch = nullptr;   // g/||v|| per dim-0 row of the conv being packed
   std::map<std::tuple<int, long long, void*>, std::unique_ptr<PreparedRun>> runs;
+  std::map<std::tuple<int, long long, void*>, std::unique_ptr<PreparedRun>> truns;
   // optional per-step CUDA-event timing (bench.py's roofline leg)
   bool profile = false;
   std::vector<cudaEvent_t> events;
@@ -253,6 +290,25 @@ void finalize_steps(kvae_plan* p) {
     for (int j = k + 1; j < n; ++j)
       if (p->steps[j].residual_from == k) s.needs_raw = true;
   }
+  // training plan: same chain, every pre-activation stream kept, no ResidualUnit fusion
+  p->tsteps = p->steps;
+  for (Step& s : p->tsteps) s.needs_raw = true;
+  // flat parameter layout = module.parameters() order: per step [alpha, beta of its SnakeBeta] then the
+  // conv's [bias][weight_g][weight_v] (old-style weight_norm keeps bias first)
+  long long off = 0;
+  p->param_sizes.clear();
+  for (const Step& s : p->steps) {
+    if (s.pre_snake >= 0) {
+      SnakeLayer& sn = p->snakes[s.pre_snake];
+      sn.off_alpha = off; off += sn.C; p->param_sizes.push_back(sn.C);
+      sn.off_beta = off; off += sn.C; p->param_sizes.push_back(sn.C);
+    }
+    ConvLayer& c = p->convs[s.conv];
+    if (c.has_bias) { c.off_bias = off; off += c.g.Cout; p->param_sizes.push_back(c.g.Cout); }
+    c.off_g = off; off += c.dim0(); p->param_sizes.push_back(c.dim0());
+    c.off_v = off; off += static_cast<long long>(c.numel()); p->param_sizes.push_back(static_cast<long long>(c.numel()));
+  }
+  p->n_params = off;
   // ResidualUnits of 128-channel stages run as ONE kernel (conv_ru.cuh): k7 -> SnakeBeta -> k1 -> + skip
   const char* nf = getenv("KVAE_NO_RU_FUSION");
   const char* v1 = getenv("KVAE_CONV_V1");
@@ -282,24 +338,26 @@ long long step_len(const Step& s, long long T) { return T * s.len_num / s.len_de
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // Interval allocation of the intermediate tensors inside one workspace.
-bool make_layout(const kvae_plan* p, int B, long long T, Layout& L, std::string& err) {
-  const int n = static_cast<int>(p->steps.size());
+bool make_layout(const kvae_plan* p, const std::vector<Step>& steps, bool train, int B, long long T, Layout& L,
+                 std::string& err) {
+  const int n = static_cast<int>(steps.size());
   L.t.assign(1 + 2 * n, Tensor());
-  const ConvLayer& c0 = p->convs[p->steps[0].conv];
+  const ConvLayer& c0 = p->convs[steps[0].conv];
   if (c0.umma) {
     L.t[0].bytes = static_cast<size_t>(B) * T * c0.g.Cin * 2;
     L.t[0].first = 0;
     L.t[0].last = 0;
   }
   for (int k = 0; k < n; ++k) {
-    const Step& s = p->steps[k];
+    const Step& s = steps[k];
     const ConvLayer& c = p->convs[s.conv];
     const long long len = step_len(s, T);
     if (len <= 0) { err = "input too short for this architecture"; return false; }
     int last_use = k;
     if (k + 1 < n) last_use = k + 1;
     for (int j = k + 1; j < n; ++j)
-      if (p->steps[j].residual_from == k) last_use = std::max(last_use, j);
+      if (steps[j].residual_from == k) last_use = std::max(last_use, j);
+    if (train) last_use = 1 << 30;   // saved for the backward pass
     if (s.needs_raw && k != n - 1) {
       Tensor& t = L.t[1 + 2 * k];
       t.bytes = static_cast<size_t>(B) * len * c.g.Cout * 4;
@@ -310,9 +368,10 @@ bool make_layout(const kvae_plan* p, int B, long long T, Layout& L, std::string&
       Tensor& t = L.t[2 + 2 * k];
       t.bytes = static_cast<size_t>(B) * len * c.g.Cout * 2;
       t.first = k;
-      t.last = k + 1;
+      t.last = train ? (1 << 30) : k + 1;
     }
   }
+  if (train && L.t[0].bytes) L.t[0].last = 1 << 30;
   // first-fit over live intervals, in order of first use
   struct Live { size_t off, size; int last; };
   std::vector<Live> live;
@@ -336,10 +395,10 @@ bool make_layout(const kvae_plan* p, int B, long long T, Layout& L, std::string&
     for (const Live& l : live)
       if (l.last >= k) keep.push_back(l);
     live.swap(keep);
-    if (p->steps[k].fuse == 2) continue;          // placed together with the fused head (below)
+    if (steps[k].fuse == 2) continue;          // placed together with the fused head (below)
     place(L.t[1 + 2 * k]);
     place(L.t[2 + 2 * k]);
-    if (p->steps[k].fuse == 1) {
+    if (steps[k].fuse == 1) {
       // the fused ResidualUnit kernel runs at step k and writes step k+1's tensors: they must not share
       // memory with anything still live at step k (its own inputs included)
       place(L.t[1 + 2 * (k + 1)]);
@@ -350,9 +409,10 @@ bool make_layout(const kvae_plan* p, int B, long long T, Layout& L, std::string&
   return true;
 }
 
-bool prepare_run(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R, std::string& err) {
-  const int n = static_cast<int>(p->steps.size());
-  if (!make_layout(p, B, T, R.layout, err)) return false;
+bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B, long long T, void* ws,
+                 PreparedRun& R, std::string& err) {
+  const int n = static_cast<int>(steps.size());
+  if (!make_layout(p, steps, train, B, T, R.layout, err)) return false;
   R.umma.resize(n);
   R.umma2.resize(n);
   R.ru.resize(n);
@@ -370,9 +430,9 @@ bool prepare_run(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R, std
   uint8_t* base = static_cast<uint8_t*>(ws);
   auto tptr = [&](int id) -> void* { return R.layout.t[id].bytes ? base + R.layout.t[id].offset : nullptr; };
   for (int k = 0; k < n; ++k) {
-    const Step& s = p->steps[k];
+    const Step& s = steps[k];
     const ConvLayer& c = p->convs[s.conv];
-    const long long T_in = (k == 0) ? T : step_len(p->steps[k - 1], T);
+    const long long T_in = (k == 0) ? T : step_len(steps[k - 1], T);
     const long long T_out = step_len(s, T);
     if (c.g.out_len(static_cast<int>(T_in)) != T_out) {
       err = "length bookkeeping mismatch at step " + std::to_string(k) + " (input length must be a multiple of the stride product)";
@@ -385,7 +445,7 @@ bool prepare_run(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R, std
     if (s.residual_from >= 0 && !res) { err = "internal: residual tensor missing"; return false; }
     if (s.fuse == 2 && !R.use_v1) { R.kind[k] = 5; continue; }
     if (s.fuse == 1 && !R.use_v1) {
-      const Step& s1 = p->steps[k + 1];
+      const Step& s1 = steps[k + 1];
       const ConvLayer& c1 = p->convs[s1.conv];
       RuArgs ra;
       ra.a = static_cast<const __nv_bfloat16*>(tptr(2 + 2 * (k - 1)));
@@ -494,7 +554,7 @@ bool prepare_run(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R, std
         d.x_sT = 1;
         d.x_sC = T_in;
       } else {
-        const Step& prev = p->steps[k - 1];
+        const Step& prev = steps[k - 1];
         d.x = tptr(1 + 2 * (k - 1));
         if (!prev.needs_raw || !d.x) { err = "internal: raw input missing"; return false; }
         d.x_f32 = 1;
@@ -572,35 +632,47 @@ cudaError_t launch_direct(const DirectParams& d, dim3 grid, int cfg, size_t smem
   return cudaGetLastError();
 }
 
-int run_plan(kvae_plan* p, const void* in, int in_dtype, void* out, int out_dtype, int B, long long T, void* ws,
-             size_t ws_bytes, cudaStream_t st) {
+bool prepare_backward(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R, std::string& err);
+
+PreparedRun* get_run(kvae_plan* p, bool train, int B, long long T, void* ws, std::string& err) {
+  auto& cache = train ? p->truns : p->runs;
+  auto key = std::make_tuple(B, T, ws);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    auto R = std::make_unique<PreparedRun>();
+    if (!prepare_run(p, train ? p->tsteps : p->steps, train, B, T, ws, *R, err)) return nullptr;
+    R->total = R->layout.total;
+    if (train && !prepare_backward(p, B, T, ws, *R, err)) return nullptr;
+    if (cache.size() > 64) cache.clear();
+    it = cache.emplace(key, std::move(R)).first;
+  }
+  return it->second.get();
+}
+
+int run_plan(kvae_plan* p, bool train, const void* in, int in_dtype, void* out, int out_dtype, int B, long long T,
+             void* ws, size_t ws_bytes, cudaStream_t st) {
   if (!p) return fail("null plan");
   if (B <= 0 || T <= 0) return fail("empty batch or zero length input");
   if (T > (1ll << 30)) return fail("input too long");
   for (const ConvLayer& c : p->convs)
-    if (!c.set) return fail("plan weights not set (kvae_plan_set_conv)");
+    if (!c.set) return fail("plan weights not set (kvae_plan_set_conv / kvae_plan_load_params)");
   for (const SnakeLayer& s : p->snakes)
-    if (!s.set) return fail("plan SnakeBeta parameters not set (kvae_plan_set_snake)");
+    if (!s.set) return fail("plan SnakeBeta parameters not set (kvae_plan_set_snake / kvae_plan_load_params)");
+  if (train && !p->train_packs) return fail("training run needs kvae_plan_load_params(plan, params, train = 1)");
+  if (train && p->direction == KVAE_DECODER && p->arch.final_tanh) return fail("final_tanh is not supported in training");
   DeviceGuard guard(p->device);
   if (!guard.ok) return fail("cannot select device");
-  const int n = static_cast<int>(p->steps.size());
-  const Step& lastst = p->steps[n - 1];
+  const std::vector<Step>& steps = train ? p->tsteps : p->steps;
+  const int n = static_cast<int>(steps.size());
   if (p->direction == KVAE_ENCODER && T % p->ratio) return fail("audio length must be a multiple of the downsampling ratio");
-  auto key = std::make_tuple(B, T, ws);
-  auto it = p->runs.find(key);
-  if (it == p->runs.end()) {
-    auto R = std::make_unique<PreparedRun>();
-    std::string err;
-    if (!prepare_run(p, B, T, ws, *R, err)) return fail(err);
-    if (p->runs.size() > 64) p->runs.clear();
-    it = p->runs.emplace(key, std::move(R)).first;
-  }
-  PreparedRun& R = *it->second;
-  if (ws_bytes < R.layout.total) return fail("workspace too small");
-  if (R.layout.total > 1024 && !ws) return fail("null workspace");
-  (void)lastst;
+  std::string err;
+  PreparedRun* Rp = get_run(p, train, B, T, ws, err);
+  if (!Rp) return fail(err);
+  PreparedRun& R = *Rp;
+  if (ws_bytes < R.total) return fail("workspace too small");
+  if (R.total > 1024 && !ws) return fail("null workspace");
   // boundary layout change for a tensor-core first layer
-  const ConvLayer& c0 = p->convs[p->steps[0].conv];
+  const ConvLayer& c0 = p->convs[steps[0].conv];
   if (c0.umma) {
     dim3 grid(ceil_div(static_cast<int>(T), 32), ceil_div(c0.g.Cin, 32), B), block(32, 8);
     cf_to_cl_bf16_kernel<<<grid, block, 0, st>>>(in, in_dtype == KVAE_F32,
@@ -609,7 +681,8 @@ int run_plan(kvae_plan* p, const void* in, int in_dtype, void* out, int out_dtyp
     KV_CUDA(cudaGetLastError());
     ++g_launches;
   }
-  if (p->profile) {
+  const bool prof = p->profile && !train;
+  if (prof) {
     while (static_cast<int>(p->events.size()) < n + 1) {
       cudaEvent_t e;
       KV_CUDA(cudaEventCreate(&e));
@@ -621,7 +694,7 @@ int run_plan(kvae_plan* p, const void* in, int in_dtype, void* out, int out_dtyp
     p->prof_valid = true;
   }
   for (int k = 0; k < n; ++k) {
-    const ConvLayer& c = p->convs[p->steps[k].conv];
+    const ConvLayer& c = p->convs[steps[k].conv];
     if (R.kind[k] == 5) {
       // computed by the fused ResidualUnit launch of the previous step
     } else if (R.kind[k] == 4) {
@@ -658,7 +731,269 @@ int run_plan(kvae_plan* p, const void* in, int in_dtype, void* out, int out_dtyp
       KV_CUDA(launch_direct(d, R.direct_grid[k], R.direct_cfg[k], R.direct_smem[k], st));
     }
     if (R.kind[k] != 5) ++g_launches;
-    if (p->profile) KV_CUDA(cudaEventRecord(p->events[k + 1], st));
+    if (prof) KV_CUDA(cudaEventRecord(p->events[k + 1], st));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ backward pass (training plans)
+// Walks tsteps in reverse.  G_k = gradient w.r.t. the raw (pre-activation) output of step k, fp32
+// channels-last, plus a bf16 copy when a tensor-core kernel consumes it.  Per step k:
+//   wgrad:  dW_k   = G_k (x) a_{k-1}          a_{k-1} = SnakeBeta(raw_{k-1}) as saved by the forward pass
+//   dgrad:  dA     = conv^T(G_k, W_k)          the forward kernels under dgrad_geom() with re-packed weights
+//   snake:  G_{k-1} = dA * SnakeBeta'(raw_{k-1}) + [G_{k+1} if step k+1 adds raw_{k-1} as its skip connection]
+//           and, in the same pass, d alpha / d beta of that SnakeBeta and d bias of conv k-1 (= column sums of G_{k-1})
+void set_sb_grid(SnakeBwdParams& sb, dim3& grid) {
+  int CW = 1;
+  while (CW * 2 <= std::min(sb.C, 256)) CW *= 2;
+  sb.CW = CW;
+  const int cols = ceil_div(sb.C, CW);
+  const int nrl = 256 / CW;
+  // enough blocks to fill the machine, each with at least a few passes over its rows
+  long long blocks_x = std::max<long long>(1, std::min<long long>((sb.rows + 8 * nrl - 1) / (8 * nrl),
+                                                                     (4ll * sm_count() + cols - 1) / cols));
+  long long rpb = (sb.rows + blocks_x - 1) / blocks_x;
+  rpb = (rpb + nrl - 1) / nrl * nrl;
+  blocks_x = (sb.rows + rpb - 1) / rpb;
+  sb.rows_per_block = static_cast<int>(rpb);
+  grid = dim3(static_cast<unsigned>(blocks_x), cols, 1);
+}
+
+bool prepare_backward(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R, std::string& err) {
+  const std::vector<Step>& steps = p->tsteps;
+  const int n = static_cast<int>(steps.size());
+  // backward region: three rotating gradient slots (fp32 + bf16) and one dA buffer, each of the largest size
+  size_t max_elems = 0;
+  for (int k = 0; k < n; ++k) {
+    const ConvLayer& c = p->convs[steps[k].conv];
+    max_elems = std::max(max_elems, static_cast<size_t>(B) * static_cast<size_t>(step_len(steps[k], T)) * c.g.Cout);
+  }
+  size_t off = align_up(R.layout.total, 1024);
+  for (int i = 0; i < 3; ++i) { R.off_G[i] = off; off += align_up(max_elems * 4, 1024); }
+  for (int i = 0; i < 3; ++i) { R.off_Gb[i] = off; off += align_up(max_elems * 2, 1024); }
+  R.off_dA = off;
+  off += align_up(max_elems * 4, 1024);
+  R.total = off;
+  uint8_t* base = static_cast<uint8_t*>(ws);
+  auto tptr = [&](int id) -> void* { return R.layout.t[id].bytes ? base + R.layout.t[id].offset : nullptr; };
+  auto Gf = [&](int k) { return reinterpret_cast<float*>(base + R.off_G[k % 3]); };
+  auto Gb = [&](int k) { return reinterpret_cast<__nv_bfloat16*>(base + R.off_Gb[k % 3]); };
+  float* dA = reinterpret_cast<float*>(base + R.off_dA);
+  R.bwd.assign(n, PreparedRun::Bwd());
+  {
+    // incoming gradient (already transposed into Gf(n-1) at run time): bf16 copy + last conv's bias gradient
+    const ConvLayer& c = p->convs[steps[n - 1].conv];
+    SnakeBwdParams& sb = R.sb_last;
+    std::memset(&sb, 0, sizeof(sb));
+    sb.dA = Gf(n - 1);
+    sb.Gb = Gb(n - 1);
+    sb.rows = static_cast<long long>(B) * step_len(steps[n - 1], T);
+    sb.C = c.g.Cout;
+    set_sb_grid(sb, R.sb_last_grid);
+  }
+  for (int k = n - 1; k >= 0; --k) {
+    const Step& s = steps[k];
+    const ConvLayer& c = p->convs[s.conv];
+    PreparedRun::Bwd& bw = R.bwd[k];
+    const long long T_in = (k == 0) ? T : step_len(steps[k - 1], T);
+    const long long T_out = step_len(s, T);
+    // ---- weight gradient
+    WgradParams& w = bw.wg;
+    std::memset(&w, 0, sizeof(w));
+    const void* a_ptr = nullptr;
+    int a_f32 = 0;
+    long long a_sB = T_in * c.g.Cin, a_sT = c.g.Cin, a_sC = 1;
+    const float* a_sn = nullptr;
+    const float* a_ib = nullptr;
+    bool a_is_x = false;
+    if (k == 0) {
+      if (c.umma) {
+        a_ptr = tptr(0);
+      } else {   // the caller's input tensor, API layout [B, C, T]; pointer / dtype patched per call
+        a_is_x = true;
+        a_sB = static_cast<long long>(c.g.Cin) * T_in; a_sT = 1; a_sC = T_in;
+      }
+    } else if (steps[k - 1].needs_act) {
+      a_ptr = tptr(2 + 2 * (k - 1));
+    } else {
+      a_ptr = tptr(1 + 2 * (k - 1));
+      a_f32 = 1;
+      if (s.pre_snake >= 0) { a_sn = p->snakes[s.pre_snake].a; a_ib = p->snakes[s.pre_snake].inv_b; }
+    }
+    if (!a_ptr && !a_is_x) { err = "internal: saved operand missing at step " + std::to_string(k); return false; }
+    const float* g_ptr = Gf(k);
+    const long long g_sB = T_out * c.g.Cout, g_sT = c.g.Cout;
+    if (c.g.kind == kConv) {
+      w.D = g_ptr; w.D_f32 = 1; w.D_sB = g_sB; w.D_sT = g_sT; w.D_sC = 1;
+      w.S = a_ptr; w.S_f32 = a_f32; w.S_sB = a_sB; w.S_sT = a_sT; w.S_sC = a_sC; w.S_a = a_sn; w.S_inv_b = a_ib;
+      w.Td = static_cast<int>(T_out); w.Ts = static_cast<int>(T_in); w.Cd = c.g.Cout; w.Cs = c.g.Cin;
+      bw.wg_x_is_S = a_is_x;
+    } else {
+      w.D = a_ptr; w.D_f32 = a_f32; w.D_sB = a_sB; w.D_sT = a_sT; w.D_sC = a_sC; w.D_a = a_sn; w.D_inv_b = a_ib;
+      w.S = g_ptr; w.S_f32 = 1; w.S_sB = g_sB; w.S_sT = g_sT; w.S_sC = 1;
+      w.Td = static_cast<int>(T_in); w.Ts = static_cast<int>(T_out); w.Cd = c.g.Cin; w.Cs = c.g.Cout;
+      bw.wg_x_is_D = a_is_x;
+    }
+    w.B = B; w.K = c.g.K; w.stride = c.g.stride; w.dil = c.g.dilation; w.pad = c.g.pad;
+    {
+      const int tiles = ceil_div(w.Cd, 64) * ceil_div(w.Cs, 64);
+      const long long rows = static_cast<long long>(B) * w.Td;
+      long long nsplit = std::max<long long>(1, (4ll * sm_count()) / (static_cast<long long>(tiles) * w.K));
+      nsplit = std::min(nsplit, (rows + 4 * kWgRows - 1) / (4 * kWgRows));
+      nsplit = std::max<long long>(1, std::min<long long>(nsplit, 65535));
+      long long rps = (rows + nsplit - 1) / nsplit;
+      rps = (rps + kWgRows - 1) / kWgRows * kWgRows;
+      nsplit = (rows + rps - 1) / rps;
+      w.rows_per_split = rps;
+      bw.wg_grid = dim3(tiles, w.K, static_cast<unsigned>(nsplit));
+    }
+    // ---- data gradient (k == 0: only when the caller asks for the input gradient; patched per call)
+    const ConvGeom gd = dgrad_geom(c.g, static_cast<int>(T_in));
+    if (gd.out_len(static_cast<int>(T_out)) != T_in) { err = "internal: dgrad length bookkeeping"; return false; }
+    if (c.umma) {
+      bw.dgrad_kind = 1;
+      ConvEpilogue ep;
+      ep.out_raw = (k == 0) ? reinterpret_cast<void*>(0x1) : static_cast<void*>(dA);
+      ep.out_raw_f32 = 1;
+      ep.out_raw_cf = (k == 0) ? 1 : 0;
+      ConvTuning2 tune;
+      if (!prepare_conv_umma2(gd, Gb(k), B, static_cast<int>(T_out), c.w_umma_d, ep, tune, bw.dg_umma, err)) return false;
+    } else {
+      bw.dgrad_kind = 2;
+      DirectParams& d = bw.dg_direct;
+      std::memset(&d, 0, sizeof(d));
+      TapPlan tp;
+      if (!build_taps(gd, false, tp, err)) return false;
+      d.B = B; d.P_out = tp.P_out; d.P_in = tp.P_in;
+      d.Tq_out = static_cast<int>((T_in + tp.P_out - 1) / tp.P_out);
+      d.T_out = static_cast<int>(T_in); d.T_in = static_cast<int>(T_out);
+      d.Cin = gd.Cin; d.Cout = gd.Cout; d.span = tp.span;
+      for (int i = 0; i <= kMaxPhases; ++i) d.tap_begin[i] = tp.tap_begin[i];
+      for (size_t i = 0; i < tp.taps.size(); ++i) d.taps[i] = tp.taps[i];
+      d.x = Gf(k); d.x_f32 = 1;
+      d.x_sB = T_out * gd.Cin; d.x_sT = gd.Cin; d.x_sC = 1;
+      d.w = c.w_direct_d;
+      if (k == 0) {   // input gradient in the API layout
+        d.out_raw = nullptr;
+        d.o_sB = static_cast<long long>(gd.Cout) * T_in; d.o_sT = 1; d.o_sC = T_in;
+      } else {
+        d.out_raw = dA; d.out_raw_f32 = 1;
+        d.o_sB = T_in * gd.Cout; d.o_sT = gd.Cout; d.o_sC = 1;
+      }
+      const int cfg = (gd.Cout <= 4) ? 1 : 0;
+      const int BT = cfg ? 128 : 32, BN = cfg ? 4 : 64;
+      bw.dg_cfg = cfg;
+      bw.dg_grid = dim3(ceil_div(d.Tq_out, BT) * tp.P_out, ceil_div(gd.Cout, BN), B);
+      bw.dg_smem = (static_cast<size_t>(BT + tp.span) * (kDirectKC + 1) + kDirectKC * BN) * sizeof(float);
+    }
+    // ---- SnakeBeta backward producing G_{k-1}
+    if (k >= 1) {
+      const ConvLayer& cp = p->convs[steps[k - 1].conv];
+      SnakeBwdParams& sb = bw.sb;
+      std::memset(&sb, 0, sizeof(sb));
+      bw.has_sb = true;
+      sb.dA = dA;
+      if (s.pre_snake >= 0) {
+        const SnakeLayer& sn = p->snakes[s.pre_snake];
+        sb.x = static_cast<const float*>(tptr(1 + 2 * (k - 1)));
+        if (!sb.x) { err = "internal: saved stream missing at step " + std::to_string(k - 1); return false; }
+        sb.a = sn.a; sb.inv_b = sn.inv_b; sb.logscale = sn.logscale;
+      }
+      for (int j = k + 1; j < n; ++j)
+        if (steps[j].residual_from == k - 1) {
+          if (j != k + 1) { err = "internal: skip connection spans more than one ResidualUnit"; return false; }
+          sb.skip = Gf(j);
+        }
+      sb.G = Gf(k - 1);
+      sb.Gb = cp.umma ? Gb(k - 1) : nullptr;
+      sb.rows = static_cast<long long>(B) * T_in;
+      sb.C = c.g.Cin;
+      set_sb_grid(sb, bw.sb_grid);
+    }
+  }
+  return true;
+}
+
+int run_backward(kvae_plan* p, const void* x, int x_dtype, const void* gy, int gy_dtype, void* gx, int gx_dtype, int B,
+                 long long T, void* ws, size_t ws_bytes, float* grads, const float* params, cudaStream_t st) {
+  if (!p) return fail("null plan");
+  if (!gy || !grads || !x) return fail("null argument");
+  if (!p->train_packs) return fail("backward needs kvae_plan_load_params(plan, params, train = 1)");
+  DeviceGuard guard(p->device);
+  if (!guard.ok) return fail("cannot select device");
+  std::string err;
+  PreparedRun* Rp = get_run(p, true, B, T, ws, err);
+  if (!Rp) return fail(err);
+  PreparedRun& R = *Rp;
+  if (ws_bytes < R.total) return fail("workspace too small");
+  const std::vector<Step>& steps = p->tsteps;
+  const int n = static_cast<int>(steps.size());
+  uint8_t* base = static_cast<uint8_t*>(ws);
+  KV_CUDA(cudaMemsetAsync(grads, 0, static_cast<size_t>(p->n_params) * 4, st));
+  {
+    // grad_out [B, C, T_last] -> channels-last fp32, then bf16 copy + bias gradient of the last conv
+    const ConvLayer& c = p->convs[steps[n - 1].conv];
+    const long long T_last = step_len(steps[n - 1], T);
+    float* G = reinterpret_cast<float*>(base + R.off_G[(n - 1) % 3]);
+    dim3 grid(static_cast<unsigned>((T_last + 31) / 32), ceil_div(c.g.Cout, 32), B), block(32, 8);
+    cf_to_cl_f32_kernel<<<grid, block, 0, st>>>(gy, gy_dtype == KVAE_F32, G, c.g.Cout, T_last);
+    KV_CUDA(cudaGetLastError());
+    SnakeBwdParams sb = R.sb_last;
+    if (!c.umma) sb.Gb = nullptr;
+    sb.d_bias = c.has_bias ? grads + c.off_bias : nullptr;
+    if (sb.Gb || sb.d_bias) {
+      snake_bwd_kernel<<<R.sb_last_grid, 256, 0, st>>>(sb);
+      KV_CUDA(cudaGetLastError());
+      ++g_launches;
+    }
+    ++g_launches;
+  }
+  for (int k = n - 1; k >= 0; --k) {
+    const Step& s = steps[k];
+    const ConvLayer& c = p->convs[s.conv];
+    PreparedRun::Bwd& bw = R.bwd[k];
+    {
+      WgradParams w = bw.wg;
+      if (bw.wg_x_is_D) { w.D = x; w.D_f32 = (x_dtype == KVAE_F32); }
+      if (bw.wg_x_is_S) { w.S = x; w.S_f32 = (x_dtype == KVAE_F32); }
+      w.dW = grads + c.off_v;
+      wgrad_direct_kernel<<<bw.wg_grid, 256, 0, st>>>(w);
+      KV_CUDA(cudaGetLastError());
+      ++g_launches;
+    }
+    if (k == 0 && !gx) break;
+    if (bw.dgrad_kind == 1) {
+      ConvLaunch2& L = bw.dg_umma;
+      if (k == 0) { L.p.out_cf = gx; L.p.out_cf_f32 = (gx_dtype == KVAE_F32); }
+      KV_CUDA(launch_conv_umma2(L, st));
+    } else {
+      DirectParams& d = bw.dg_direct;
+      if (k == 0) { d.out_raw = gx; d.out_raw_f32 = (gx_dtype == KVAE_F32); }
+      KV_CUDA(launch_direct(d, bw.dg_grid, bw.dg_cfg, bw.dg_smem, st));
+    }
+    ++g_launches;
+    if (bw.has_sb) {
+      SnakeBwdParams sb = bw.sb;
+      const ConvLayer& cp = p->convs[steps[k - 1].conv];
+      if (s.pre_snake >= 0) {
+        sb.d_alpha = grads + p->snakes[s.pre_snake].off_alpha;
+        sb.d_beta = grads + p->snakes[s.pre_snake].off_beta;
+      }
+      sb.d_bias = cp.has_bias ? grads + cp.off_bias : nullptr;
+      snake_bwd_kernel<<<bw.sb_grid, 256, 0, st>>>(sb);
+      KV_CUDA(cudaGetLastError());
+      ++g_launches;
+    }
+  }
+  if (params) {
+    // weight-norm backward in place: the weight_v slot holds dW (folded-weight gradient) -> (dv, dg)
+    for (const ConvLayer& c : p->convs) {
+      const int inner = static_cast<int>(c.numel() / c.dim0());
+      weight_norm_bwd_kernel<<<c.dim0(), 256, 0, st>>>(params + c.off_v, params + c.off_g, grads + c.off_v,
+                                                       grads + c.off_v, grads + c.off_g, inner);
+      KV_CUDA(cudaGetLastError());
+      ++g_launches;
+    }
   }
   return 0;
 }
@@ -742,12 +1077,15 @@ void kvae_plan_destroy(kvae_plan* p) {
   for (ConvLayer& c : p->convs) {
     cudaFree(c.w_umma);
     cudaFree(c.w_direct);
+    cudaFree(c.w_umma_d);
+    cudaFree(c.w_direct_d);
     cudaFree(c.bias);
   }
   for (SnakeLayer& s : p->snakes) {
     cudaFree(s.a);
     cudaFree(s.inv_b);
   }
+  cudaFree(p->scale_scratch);
   delete p;
 }
 
@@ -793,6 +1131,7 @@ int kvae_plan_set_snake(kvae_plan* p, int idx, const float* alpha, const float* 
   snake_params_kernel<<<ceil_div(s.C, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(alpha, beta, logscale, s.C,
                                                                                         s.a, s.inv_b);
   KV_CUDA(cudaGetLastError());
+  s.logscale = logscale ? 1 : 0;
   s.set = true;
   return 0;
 }
@@ -801,7 +1140,7 @@ size_t kvae_workspace_bytes(kvae_plan* p, int B, long long T) {
   if (!p || B <= 0 || T <= 0) { fail("bad argument"); return 0; }
   Layout L;
   std::string err;
-  if (!make_layout(p, B, T, L, err)) { fail(err); return 0; }
+  if (!make_layout(p, p->steps, false, B, T, L, err)) { fail(err); return 0; }
   return L.total;
 }
 
@@ -811,7 +1150,7 @@ int kvae_decode(kvae_plan* p, const void* z, int z_dtype, void* wav, int wav_dty
   if (p->direction != KVAE_DECODER) return fail("plan is not a decoder");
   if (!z || !wav) return fail("null tensor");
   if (!check_dtype(z_dtype) || !check_dtype(wav_dtype)) return fail("bad dtype");
-  return run_plan(p, z, z_dtype, wav, wav_dtype, B, T, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+  return run_plan(p, false, z, z_dtype, wav, wav_dtype, B, T, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 int kvae_encode(kvae_plan* p, const void* wav, int wav_dtype, void* lat, int lat_dtype, int B, long long L, void* ws,
@@ -820,7 +1159,7 @@ int kvae_encode(kvae_plan* p, const void* wav, int wav_dtype, void* lat, int lat
   if (p->direction != KVAE_ENCODER) return fail("plan is not an encoder");
   if (!wav || !lat) return fail("null tensor");
   if (!check_dtype(wav_dtype) || !check_dtype(lat_dtype)) return fail("bad dtype");
-  return run_plan(p, wav, wav_dtype, lat, lat_dtype, B, L, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+  return run_plan(p, false, wav, wav_dtype, lat, lat_dtype, B, L, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
 double kvae_plan_flops(const kvae_plan* p, int B, long long T) {
@@ -934,6 +1273,173 @@ int kvae_conv1d_fwd(const void* x, void* y, const float* w, const float* bias, i
   const size_t smem = (static_cast<size_t>(BT + tp.span) * (kDirectKC + 1) + kDirectKC * BN) * sizeof(float);
   KV_CUDA(launch_direct(d, grid, cfg, smem, st));
   g_launches += 2;
+  return 0;
+}
+
+// ------------------------------------------------------------------ training step
+long long kvae_plan_param_count(const kvae_plan* p) { return p ? p->n_params : fail("null plan"); }
+
+int kvae_plan_param_sizes(const kvae_plan* p, long long* sizes, int max_segments) {
+  if (!p || !sizes) return fail("null argument");
+  const int n = static_cast<int>(p->param_sizes.size());
+  if (max_segments < n) return fail("output array too small");
+  for (int i = 0; i < n; ++i) sizes[i] = p->param_sizes[i];
+  return n;
+}
+
+int kvae_plan_load_params(kvae_plan* p, const float* params, int logscale, int train, void* stream) {
+  if (!p || !params) return fail("null argument");
+  DeviceGuard guard(p->device);
+  if (!guard.ok) return fail("cannot select device");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!p->scale_scratch) {
+    int m = 1;
+    for (const ConvLayer& c : p->convs) m = std::max(m, c.dim0());
+    KV_CUDA(cudaMalloc(&p->scale_scratch, static_cast<size_t>(m) * 4));
+  }
+  for (ConvLayer& c : p->convs) {
+    if (c.g.K > kPackMaxK) return fail("kernel size > 16 unsupported by kvae_plan_load_params");
+    const size_t n = c.numel();
+    if (train) {   // the backward pass needs the other index order of each precision
+      if (c.umma && !c.w_umma_d) KV_CUDA(cudaMalloc(&c.w_umma_d, n * 2));
+      if (!c.umma && !c.w_direct_d) KV_CUDA(cudaMalloc(&c.w_direct_d, n * 4));
+    }
+    const int R = c.dim0(), Cc = static_cast<int>(n / c.g.K / R);
+    weight_norm_scale_kernel<<<R, 256, 0, st>>>(params + c.off_v, params + c.off_g, p->scale_scratch, Cc * c.g.K);
+    KV_CUDA(cudaGetLastError());
+    dim3 grid(ceil_div(R, kPackTR), ceil_div(Cc, kPackTC));
+    // index order A = [K][Cout][Cin]: forward tensor-core operand / CUDA-core dgrad operand;
+    // index order B = [K][Cin][Cout]: forward CUDA-core operand / tensor-core dgrad operand
+    if (c.g.kind == kConv)   // R = Cout, Cc = Cin: out1 = A, out2 = B
+      fold_pack_kernel<<<grid, 256, 0, st>>>(params + c.off_v, p->scale_scratch, R, Cc, c.g.K, c.w_umma,
+                                             train ? c.w_direct_d : nullptr, train ? c.w_umma_d : nullptr, c.w_direct);
+    else                     // R = Cin, Cc = Cout: out1 = B, out2 = A
+      fold_pack_kernel<<<grid, 256, 0, st>>>(params + c.off_v, p->scale_scratch, R, Cc, c.g.K,
+                                             train ? c.w_umma_d : nullptr, c.w_direct, c.w_umma,
+                                             train ? c.w_direct_d : nullptr);
+    KV_CUDA(cudaGetLastError());
+    if (c.has_bias) KV_CUDA(cudaMemcpyAsync(c.bias, params + c.off_bias, c.g.Cout * 4, cudaMemcpyDeviceToDevice, st));
+    c.set = true;
+    g_launches += 2;
+  }
+  for (SnakeLayer& s : p->snakes) {
+    snake_params_kernel<<<ceil_div(s.C, 128), 128, 0, st>>>(params + s.off_alpha, params + s.off_beta, logscale, s.C,
+                                                           s.a, s.inv_b);
+    KV_CUDA(cudaGetLastError());
+    s.logscale = logscale ? 1 : 0;
+    s.set = true;
+    ++g_launches;
+  }
+  if (train) p->train_packs = true;
+  return 0;
+}
+
+size_t kvae_train_workspace_bytes(kvae_plan* p, int B, long long T) {
+  if (!p || B <= 0 || T <= 0) { fail("bad argument"); return 0; }
+  Layout L;
+  std::string err;
+  if (!make_layout(p, p->tsteps, true, B, T, L, err)) { fail(err); return 0; }
+  size_t max_elems = 0;
+  for (const Step& s : p->tsteps)
+    max_elems = std::max(max_elems, static_cast<size_t>(B) * static_cast<size_t>(step_len(s, T)) * p->convs[s.conv].g.Cout);
+  return align_up(L.total, 1024) + 4 * align_up(max_elems * 4, 1024) + 3 * align_up(max_elems * 2, 1024);
+}
+
+int kvae_forward_train(kvae_plan* p, const void* x, int x_dtype, void* y, int y_dtype, int B, long long T, void* ws,
+                       size_t ws_bytes, void* stream) {
+  if (!p) return fail("null plan");
+  if (!x || !y) return fail("null tensor");
+  if (!check_dtype(x_dtype) || !check_dtype(y_dtype)) return fail("bad dtype");
+  return run_plan(p, true, x, x_dtype, y, y_dtype, B, T, ws, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int kvae_backward(kvae_plan* p, const void* x, int x_dtype, const void* gy, int gy_dtype, void* gx, int gx_dtype,
+                  int B, long long T, void* ws, size_t ws_bytes, float* grads, const float* params, void* stream) {
+  if (!check_dtype(x_dtype) || !check_dtype(gy_dtype) || (gx && !check_dtype(gx_dtype))) return fail("bad dtype");
+  return run_backward(p, x, x_dtype, gy, gy_dtype, gx, gx_dtype, B, T, ws, ws_bytes, grads, params,
+                      static_cast<cudaStream_t>(stream));
+}
+
+int kvae_weight_norm_bwd(const float* v, const float* g, const float* dw, float* dv, float* dg, int dim0, int inner,
+                         void* stream) {
+  if (!v || !g || !dw || !dv || !dg) return fail("null argument");
+  if (dim0 <= 0 || inner <= 0) return 0;
+  weight_norm_bwd_kernel<<<dim0, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, g, dw, dv, dg, inner);
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int kvae_snake_bwd(const float* x, const float* gy, float* gx, const float* alpha, const float* beta, int logscale,
+                   float* d_alpha, float* d_beta, long long rows, int C, void* scratch, void* stream) {
+  if (!x || !gy || !gx || !alpha || !beta || !d_alpha || !d_beta || !scratch) return fail("null argument");
+  if (rows <= 0 || C <= 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* a = static_cast<float*>(scratch);
+  float* ib = a + C;
+  snake_params_kernel<<<ceil_div(C, 128), 128, 0, st>>>(alpha, beta, logscale, C, a, ib);
+  KV_CUDA(cudaGetLastError());
+  KV_CUDA(cudaMemsetAsync(d_alpha, 0, C * 4, st));
+  KV_CUDA(cudaMemsetAsync(d_beta, 0, C * 4, st));
+  SnakeBwdParams sb;
+  std::memset(&sb, 0, sizeof(sb));
+  sb.dA = gy; sb.x = x; sb.a = a; sb.inv_b = ib; sb.logscale = logscale ? 1 : 0;
+  sb.G = gx; sb.d_alpha = d_alpha; sb.d_beta = d_beta; sb.rows = rows; sb.C = C;
+  dim3 grid;
+  set_sb_grid(sb, grid);
+  snake_bwd_kernel<<<grid, 256, 0, st>>>(sb);
+  KV_CUDA(cudaGetLastError());
+  g_launches += 2;
+  return 0;
+}
+
+int kvae_vae_sample_bwd(const void* mean, const void* scale, const void* noise, const void* gz, const float* gkl,
+                        void* gmean, void* gscale, int B, int D, long long T, int dtype, void* stream) {
+  if (!mean || !scale || !noise || !gmean || !gscale) return fail("null argument");
+  if (!check_dtype(dtype)) return fail("bad dtype");
+  const size_t n = static_cast<size_t>(B) * D * T;
+  if (n == 0) return 0;
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
+  vae_sample_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      mean, scale, noise, gz, gkl, static_cast<float>(1.0 / (static_cast<double>(B) * static_cast<double>(T))), gmean,
+      gscale, n, dtype == KVAE_F32);
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int kvae_gaussian_nll(const void* x, const void* xhat, void* gxhat, float* loss, int B, size_t per_item, float log_sigma,
+                      int dtype, void* scratch, void* stream) {
+  if (!x || !xhat || !loss || !scratch) return fail("null argument");
+  if (!check_dtype(dtype)) return fail("bad dtype");
+  const size_t n = static_cast<size_t>(B) * per_item;
+  if (n == 0) return fail("empty input");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 1024));
+  const double inv_var = std::exp(-2.0 * static_cast<double>(log_sigma));
+  gaussian_nll_kernel<<<blocks, 256, 0, st>>>(x, xhat, n, dtype == KVAE_F32, static_cast<float>(inv_var),
+                                              1.0f / static_cast<float>(B), gxhat, static_cast<double*>(scratch));
+  KV_CUDA(cudaGetLastError());
+  gaussian_nll_finish_kernel<<<1, 256, 0, st>>>(static_cast<const double*>(scratch), blocks, static_cast<double>(n),
+                                                inv_var, static_cast<double>(log_sigma), 1.0 / B, loss);
+  KV_CUDA(cudaGetLastError());
+  g_launches += 2;
+  return 0;
+}
+
+int kvae_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq) return fail("null argument");
+  if (step < 1) return fail("step counts from 1");
+  if (n == 0) return 0;
+  const float bc1 = 1.f - std::pow(beta1, static_cast<float>(step));
+  const float bc2 = 1.f - std::pow(beta2, static_cast<float>(step));
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
+  adamw_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1,
+                                                                       beta2, eps, weight_decay, bc1, std::sqrt(bc2),
+                                                                       grad_scale);
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
   return 0;
 }
 

@@ -1,0 +1,322 @@
+// Kernels of the training step (BASELINE config 5; the reference gets these from autograd through
+// stable_audio_tools/models/autoencoders.py:39-191, blocks.py:301-339, bottleneck.py:51-62 and
+// torch.nn.utils.weight_norm -- there is no hand-written backward in the reference):
+//   snake_bwd_kernel      G_prev = dA * SnakeBeta'(x) (+ skip-connection gradient); per-channel sums for
+//                         d alpha, d beta and the producing conv's bias gradient, all in one HBM pass
+//   wgrad_direct_kernel   fp32 CUDA-core weight gradient of Conv1d / ConvTranspose1d (fp32 mode, edge convs)
+//   weight_norm_bwd       (dg, dv) from dw for torch.nn.utils.weight_norm(dim=0)
+//   vae_sample_bwd / gaussian_nll / adamw   latent sampling gradient, the sigma-VAE loss, the optimizer
+// All activations are channels-last [B, T, C]; gradients of the stream are fp32, with a bf16 copy as the
+// tensor-core operand of the data-/weight-gradient GEMMs.
+#pragma once
+#include <cuda_bf16.h>
+#include <cstdint>
+
+#include "conv_umma.cuh"    // snake_beta
+#include "elementwise.cuh"  // ld_elem / st_elem
+
+namespace kvae {
+
+// ---------------------------------------------------------------- [B, C, T] -> [B, T, C] fp32
+// grid (ceil(T/32), ceil(C/32), B), block (32, 8)
+__global__ void cf_to_cl_f32_kernel(const void* x, int f32, float* y, int C, long long T) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const long long t0 = static_cast<long long>(blockIdx.x) * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i;
+    const long long t = t0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t < T) ? ld_elem(x, (static_cast<size_t>(b) * C + c) * T + t, f32) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const long long t = t0 + i;
+    const int c = c0 + threadIdx.x;
+    if (c < C && t < T) y[(static_cast<size_t>(b) * T + t) * C + c] = tile[threadIdx.x][i];
+  }
+}
+
+// ---------------------------------------------------------------- SnakeBeta backward + reductions
+// y = x + inv_b * sin(a x)^2  (blocks.py:301-302), a = exp(alpha), inv_b = 1/(exp(beta) + 1e-9):
+//   dy/dx     = 1 + inv_b * a * sin(2 a x)
+//   dy/dalpha = inv_b * a * x * sin(2 a x)            (logscale; without it drop the factor a)
+//   dy/dbeta  = -inv_b^2 * exp(beta) * sin(a x)^2     (logscale; without it drop exp(beta))
+// The per-channel factors are applied once per block to the partial sums.
+struct SnakeBwdParams {
+  const float* dA;        // [rows, C] gradient w.r.t. the activated tensor (fp32)
+  const float* x;         // [rows, C] pre-activation stream saved by the forward pass (nullptr with a == nullptr)
+  const float* a;         // SnakeBeta exp(alpha) [C]; nullptr: identity (G = dA + skip)
+  const float* inv_b;
+  int logscale;
+  const float* skip;      // [rows, C] gradient arriving through the ResidualUnit skip connection or nullptr
+  float* G;               // [rows, C] fp32 out or nullptr
+  __nv_bfloat16* Gb;      // [rows, C] bf16 out or nullptr
+  float* d_alpha;         // [C] accumulated (atomicAdd) or nullptr
+  float* d_beta;
+  float* d_bias;          // [C] column sums of G (bias gradient of the conv that produced x) or nullptr
+  long long rows;
+  int C;
+  int CW;                 // channels per block column (power of two <= 256)
+  int rows_per_block;
+};
+
+__global__ void __launch_bounds__(256) snake_bwd_kernel(const SnakeBwdParams p) {
+  __shared__ float red[3][256];
+  const int CW = p.CW;
+  const int rl = threadIdx.x / CW;          // row lane
+  const int nrl = 256 / CW;
+  const int c = blockIdx.y * CW + (threadIdx.x % CW);
+  const long long r0 = static_cast<long long>(blockIdx.x) * p.rows_per_block;
+  const long long r1 = min(r0 + p.rows_per_block, p.rows);
+  float s1 = 0.f, s2 = 0.f, sb = 0.f;
+  if (c < p.C) {
+    float a = 0.f, ib = 0.f;
+    if (p.a) { a = p.a[c]; ib = p.inv_b[c]; }
+    for (long long r = r0 + rl; r < r1; r += nrl) {
+      const size_t i = static_cast<size_t>(r) * p.C + c;
+      float g = p.dA[i];
+      if (p.a) {
+        const float xv = p.x[i];
+        float sn, cs;
+        sincosf(a * xv, &sn, &cs);
+        const float s2x = 2.f * sn * cs;          // sin(2 a x)
+        s1 = fmaf(g * xv, s2x, s1);
+        s2 = fmaf(g, sn * sn, s2);
+        g = g * fmaf(ib * a, s2x, 1.f);
+      }
+      if (p.skip) g += p.skip[i];
+      sb += g;
+      if (p.G) p.G[i] = g;
+      if (p.Gb) p.Gb[i] = __float2bfloat16(g);
+    }
+  }
+  red[0][threadIdx.x] = s1;
+  red[1][threadIdx.x] = s2;
+  red[2][threadIdx.x] = sb;
+  __syncthreads();
+  if (threadIdx.x < CW && c < p.C) {
+    float t1 = 0.f, t2 = 0.f, tb = 0.f;
+    for (int j = 0; j < nrl; ++j) {
+      t1 += red[0][threadIdx.x + j * CW];
+      t2 += red[1][threadIdx.x + j * CW];
+      tb += red[2][threadIdx.x + j * CW];
+    }
+    if (p.a && p.d_alpha) {
+      const float a = p.a[c], ib = p.inv_b[c];
+      const float eb = 1.f / ib - 1e-9f;          // exp(beta)
+      atomicAdd(p.d_alpha + c, t1 * ib * (p.logscale ? a : 1.f));
+      atomicAdd(p.d_beta + c, -t2 * ib * ib * (p.logscale ? eb : 1.f));
+    }
+    if (p.d_bias) atomicAdd(p.d_bias + c, tb);
+  }
+}
+
+// ---------------------------------------------------------------- weight gradient, CUDA cores
+// dW[cd][cs][k] += sum_{b,t} D[b, t, cd] * S[b, t*stride + k*dil - pad, cs]
+//   Conv1d:          D = dY [B, T_out, Cout], S = a [B, T_in, Cin]   -> dW[Cout][Cin][K]  (torch layout)
+//   ConvTranspose1d: D = a  [B, T_in, Cin],   S = dY [B, T_out, Cout] -> dW[Cin][Cout][K] (torch layout)
+// where a = SnakeBeta(x) is either the bf16 operand the forward pass saved or recomputed from the fp32
+// stream on load.  grid (ceil(Cd/64) * ceil(Cs/64), K, nsplit), block 256; each block reduces a slice of
+// the B*Td rows into a 64x64 tile (4x4 per thread) and adds it with atomics.
+struct WgradParams {
+  const void* D;
+  int D_f32;
+  long long D_sB, D_sT, D_sC;   // element strides (so the API layout [B, C, T] can be read in place)
+  const float* D_a;             // SnakeBeta prologue on D (nullptr: none)
+  const float* D_inv_b;
+  const void* S;
+  int S_f32;
+  long long S_sB, S_sT, S_sC;
+  const float* S_a;
+  const float* S_inv_b;
+  float* dW;                    // [Cd][Cs][K]
+  int B, Td, Ts, Cd, Cs, K, stride, dil, pad;
+  long long rows_per_split;     // of the B*Td rows
+};
+
+constexpr int kWgRows = 16;
+
+__global__ void __launch_bounds__(256) wgrad_direct_kernel(const WgradParams p) {
+  __shared__ float sd[kWgRows][64 + 1];
+  __shared__ float ss[kWgRows][64 + 1];
+  const int n_cs = (p.Cs + 63) / 64;
+  const int cd0 = (blockIdx.x / n_cs) * 64, cs0 = (blockIdx.x % n_cs) * 64;
+  const int k = blockIdx.y;
+  const long long rows = static_cast<long long>(p.B) * p.Td;
+  const long long r_begin = static_cast<long long>(blockIdx.z) * p.rows_per_split;
+  const long long r_end = min(r_begin + p.rows_per_split, rows);
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;   // tx -> cs, ty -> cd
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long long r0 = r_begin; r0 < r_end; r0 += kWgRows) {
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < kWgRows * 64; idx += 256) {
+      // walk the contiguous dimension fastest: channels for channels-last tensors, time for the API layout
+      int rr, cc;
+      if (p.D_sC == 1) { rr = idx / 64; cc = idx % 64; } else { rr = idx % kWgRows; cc = idx / kWgRows; }
+      const long long r = r0 + rr;
+      float v = 0.f;
+      if (r < r_end && cd0 + cc < p.Cd) {
+        const long long b = r / p.Td, t = r % p.Td;
+        v = ld_elem(p.D, static_cast<size_t>(b * p.D_sB + t * p.D_sT + (cd0 + cc) * p.D_sC), p.D_f32);
+        if (p.D_a) v = snake_beta<false>(v, p.D_a[cd0 + cc], p.D_inv_b[cd0 + cc]);
+      }
+      sd[rr][cc] = v;
+      if (p.S_sC == 1) { rr = idx / 64; cc = idx % 64; } else { rr = idx % kWgRows; cc = idx / kWgRows; }
+      const long long r2 = r0 + rr;
+      v = 0.f;
+      if (r2 < r_end && cs0 + cc < p.Cs) {
+        const long long b = r2 / p.Td, t = r2 % p.Td;
+        const long long u = t * p.stride + static_cast<long long>(k) * p.dil - p.pad;
+        if (u >= 0 && u < p.Ts) {
+          v = ld_elem(p.S, static_cast<size_t>(b * p.S_sB + u * p.S_sT + (cs0 + cc) * p.S_sC), p.S_f32);
+          if (p.S_a) v = snake_beta<false>(v, p.S_a[cs0 + cc], p.S_inv_b[cs0 + cc]);
+        }
+      }
+      ss[rr][cc] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = 0; rr < kWgRows; ++rr) {
+      float dv[4], sv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dv[i] = sd[rr][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) sv[j] = ss[rr][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(dv[i], sv[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int cd = cd0 + ty * 4 + i;
+    if (cd >= p.Cd) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int cs = cs0 + tx * 4 + j;
+      if (cs < p.Cs) atomicAdd(p.dW + (static_cast<size_t>(cd) * p.Cs + cs) * p.K + k, acc[i][j]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- weight norm backward
+// w[i,:] = v[i,:] * g[i] / n_i,  n_i = ||v[i,:]||:
+//   dg[i] = <dw_i, v_i> / n_i ;  dv_i = (g_i / n_i) * (dw_i - v_i * <dw_i, v_i> / n_i^2)
+// One block per row i.  dw and dv may alias (in place).
+__global__ void weight_norm_bwd_kernel(const float* v, const float* g, const float* dw, float* dv, float* dg,
+                                       int inner) {
+  __shared__ float red[2][32];
+  const size_t base = static_cast<size_t>(blockIdx.x) * inner;
+  float nn = 0.f, dot = 0.f;
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) {
+    const float x = v[base + i];
+    nn = fmaf(x, x, nn);
+    dot = fmaf(dw[base + i], x, dot);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    nn += __shfl_xor_sync(0xffffffffu, nn, o);
+    dot += __shfl_xor_sync(0xffffffffu, dot, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = nn; red[1][threadIdx.x >> 5] = dot; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float a = (threadIdx.x < (blockDim.x >> 5)) ? red[0][threadIdx.x] : 0.f;
+    float b = (threadIdx.x < (blockDim.x >> 5)) ? red[1][threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (threadIdx.x == 0) { red[0][0] = a; red[1][0] = b; }
+  }
+  __syncthreads();
+  nn = red[0][0];
+  dot = red[1][0];
+  const float n = sqrtf(nn);
+  const float gi = g[blockIdx.x];
+  const float s = gi / n, q = dot / nn;
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) dv[base + i] = s * (dw[base + i] - v[base + i] * q);
+  if (threadIdx.x == 0) dg[blockIdx.x] = dot / n;
+}
+
+// ---------------------------------------------------------------- vae_sample backward (bottleneck.py:51-62)
+// latents = noise*scale + mean ; kl = (mean^2 + var - log var - 1).sum(1).mean(), stdev = softplus(scale)+1e-4.
+//   d mean  = gz + gkl * 2 mean / (B*T)
+//   d scale = gz * noise + gkl * (2 stdev - 2/stdev) * sigmoid(scale) / (B*T)
+__global__ void vae_sample_bwd_kernel(const void* mean, const void* scale, const void* noise, const void* gz,
+                                      const float* gkl, float inv_bt, void* gmean, void* gscale, size_t n, int f32) {
+  const float gk = gkl ? (*gkl) * inv_bt : 0.f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float m = ld_elem(mean, i, f32), sc = ld_elem(scale, i, f32);
+    const float g = gz ? ld_elem(gz, i, f32) : 0.f;
+    const float sp = (sc > 20.f) ? sc : log1pf(expf(sc));
+    const float stdev = sp + 1e-4f;
+    const float sig = 1.f / (1.f + expf(-sc));
+    st_elem(gmean, i, f32, g + gk * 2.f * m);
+    st_elem(gscale, i, f32, g * ld_elem(noise, i, f32) + gk * (2.f * stdev - 2.f / stdev) * sig);
+  }
+}
+
+// ---------------------------------------------------------------- sigma-VAE Gaussian NLL
+// nll = sum_i [ 0.5 ((x_i - xhat_i)/sigma)^2 + log sigma + 0.5 log(2 pi) ] / B ; d nll / d xhat = (xhat - x)/(sigma^2 B)
+// (no in-tree definition in the reference: SURVEY.md section 8c).  partial: per-block double sums.
+__global__ void gaussian_nll_kernel(const void* x, const void* xhat, size_t n, int f32, float inv_var, float inv_b,
+                                    void* gxhat, double* partial) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float d = ld_elem(xhat, i, f32) - ld_elem(x, i, f32);
+    acc += static_cast<double>(d * d);
+    if (gxhat) st_elem(gxhat, i, f32, d * inv_var * inv_b);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) partial[blockIdx.x] = t;
+  }
+}
+__global__ void gaussian_nll_finish_kernel(const double* partial, int nblocks, double n, double inv_var, double log_sigma,
+                                           double inv_b, float* loss) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < nblocks; i += blockDim.x) acc += partial[i];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += red[i];
+    *loss = static_cast<float>((0.5 * inv_var * t + n * (log_sigma + 0.9189385332046727)) * inv_b);
+  }
+}
+
+// ---------------------------------------------------------------- AdamW over a flat fp32 buffer
+// torch.optim.AdamW semantics (decoupled weight decay, bias-corrected moments); grad is scaled first
+// (1/world_size after a summing all-reduce).
+__global__ void adamw_kernel(float* p, const float* g, float* m, float* v, size_t n, float lr, float b1, float b2,
+                             float eps, float wd, float bc1, float bc2_sqrt, float grad_scale) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * grad_scale;
+    float pi = p[i];
+    pi -= lr * wd * pi;
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - (lr / bc1) * (mi / denom);
+  }
+}
+
+}  // namespace kvae

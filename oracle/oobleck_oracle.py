@@ -22,6 +22,13 @@ Reference lines each function follows (relative to /root/reference):
   decode_audio/encode_audio (chunked)   autoencoders.py:429-560
   vae_sample            stable_audio_tools/models/bottleneck.py:51-62
   sigma_sample          model_sigmaVAE.py:153-178, 187-213
+  training_loss         the generator branch of AutoencoderTrainingWrapper.training_step
+                        (stable_audio_tools/training/autoencoders.py:221-352: encode -> bottleneck -> decode ->
+                        losses), KL wired as in :446-456; gradients come from torch autograd through this
+                        restatement, exactly as the reference gets them from autograd through its modules
+  gaussian_nll          sigma-VAE reconstruction term of BASELINE config 5; NOT defined in the reference tree
+                        (dangling sigma-vae-pytorch symlink): standard form with a fixed
+                        scalar sigma, summed per clip, averaged over the batch
 """
 from __future__ import annotations
 
@@ -212,6 +219,25 @@ def sigma_sample(mean: Tensor, noise: Tensor, dist_type: str = "fix", std_noise:
             s = s.unsqueeze(-1)
         return mean + s * noise
     return mean
+
+
+# ----------------------------------------------------------------------------- training step
+def gaussian_nll(x: Tensor, xhat: Tensor, log_sigma: float = 0.0) -> Tensor:
+    """sum_{c,t} [0.5 ((x - xhat)/sigma)^2 + log sigma + 0.5 log 2 pi], mean over the batch."""
+    sigma = math.exp(log_sigma)
+    nll = 0.5 * ((x - xhat) / sigma) ** 2 + log_sigma + 0.5 * math.log(2.0 * math.pi)
+    return nll.flatten(1).sum(1).mean()
+
+
+def training_loss(sd: Dict[str, Tensor], x: Tensor, noise: Tensor, strides: Sequence[int], kl_weight: float = 1e-6,
+                  log_sigma: float = 0.0, enc_prefix: str = "encoder.", dec_prefix: str = "decoder."):
+    """encode -> (mean, scale) -> vae_sample -> decode -> nll + kl_weight * kl.  Returns (loss, nll, kl, decoded)."""
+    e = oobleck_encoder(sd, x, strides, prefix=enc_prefix)
+    mean, scale = e.chunk(2, dim=1)
+    z, kl = vae_sample(mean, scale, noise)
+    y = oobleck_decoder(sd, z, strides, prefix=dec_prefix)
+    nll = gaussian_nll(x, y, log_sigma)
+    return nll + kl_weight * kl, nll, kl, y
 
 
 # ----------------------------------------------------------------------------- bookkeeping

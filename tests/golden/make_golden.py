@@ -16,6 +16,10 @@ Fixtures (all float32, little-endian .npz):
   o12_d512.npz      12.5 Hz shape (strides 2,4,4,5,8), latent 512, [1,512,16] -> [1,1,20480]
   chunked.npz       decode_audio / encode_audio with chunked=True on the tiny model
   sampling.npz      vae_sample (bottleneck.py:51) and sample() (model_sigmaVAE.py:187) outputs
+  train_tiny.npz    one training step's loss and EVERY parameter gradient of the tiny model, from autograd through
+                    the reference modules + the reference's vae_sample (generator branch of
+                    training/autoencoders.py:221-352 with the Gaussian-NLL + KL objective of BASELINE config 5)
+  train_mid.npz     same on the C=64 model: loss terms, per-parameter gradient norms and a strided sample
 Weights of the larger models are NOT stored: they are re-created from the recorded seed by the
 same construction order (nn.Conv1d / nn.ConvTranspose1d default init), and the fixture carries a
 float64 checksum of every parameter so a mismatch is detected rather than silently compared.
@@ -109,8 +113,60 @@ def build(ae_mod, name, seed=0, snake_seed=None):
     return m
 
 
+KL_WEIGHT, LOG_SIGMA = 1e-2, -1.0   # large enough that both loss terms shape the gradients
+
+
+def ref_training_grads(ae_mod, bn_mod, name, x, snake_seed):
+    """Generator branch of the reference's training_step on reference modules, autograd gradients."""
+    import math
+    m = build(ae_mod, name, 0, snake_seed=snake_seed).train()
+    with torch.enable_grad():
+        enc = m.encoder(x)
+        mean, scale = enc.chunk(2, dim=1)
+        torch.manual_seed(3)
+        noise = torch.randn_like(mean)
+        torch.manual_seed(3)
+        with redirect_stdout(io.StringIO()):
+            lat, kl = bn_mod.vae_sample(mean, scale)       # draws the same noise
+        dec = m.decoder(lat)
+        nll = (0.5 * ((x - dec) / math.exp(LOG_SIGMA)) ** 2 + LOG_SIGMA + 0.5 * math.log(2 * math.pi)).flatten(1).sum(1).mean()
+        loss = nll + KL_WEIGHT * kl
+        loss.backward()
+    grads = {n: p.grad.detach().clone() for n, p in m.named_parameters()}
+    return m, noise, loss.detach(), nll.detach(), kl.detach(), dec.detach(), grads
+
+
+def train_fixtures(ae_mod, bn_mod):
+    x = 0.1 * torch.randn(2, 2, 40 * 9, generator=torch.Generator().manual_seed(2))
+    m, noise, loss, nll, kl, dec, grads = ref_training_grads(ae_mod, bn_mod, "tiny", x, 7)
+    out = {"x": x, "noise": noise, "loss": loss, "nll": nll, "kl": kl, "decoded": dec,
+           "kl_weight": torch.tensor(KL_WEIGHT), "log_sigma": torch.tensor(LOG_SIGMA)}
+    for k, v in m.state_dict().items():
+        out["sd." + k] = v
+    for k, v in grads.items():
+        out["g." + k] = v
+    np.savez_compressed(os.path.join(HERE, "train_tiny.npz"), **{k: v.numpy() for k, v in out.items()})
+
+    x = 0.1 * torch.randn(2, 2, 40 * 24, generator=torch.Generator().manual_seed(2))
+    m, noise, loss, nll, kl, dec, grads = ref_training_grads(ae_mod, bn_mod, "mid", x, 7)
+    cs = checksums(m.state_dict())
+    out = {"x": x.numpy(), "noise": noise.numpy(), "loss": float(loss), "nll": float(nll), "kl": float(kl),
+           "kl_weight": KL_WEIGHT, "log_sigma": LOG_SIGMA,
+           "cs_keys": np.array(list(cs.keys())), "cs_vals": np.array(list(cs.values()), dtype=np.float64),
+           "g_keys": np.array(list(grads.keys())),
+           "g_norm": np.array([float(g.double().norm()) for g in grads.values()], dtype=np.float64),
+           "g_sum": np.array([float(g.double().sum()) for g in grads.values()], dtype=np.float64)}
+    for i, g in enumerate(grads.values()):
+        out[f"g_sample{i}"] = g.reshape(-1)[::max(1, g.numel() // 256)][:256].numpy()
+    np.savez_compressed(os.path.join(HERE, "train_mid.npz"), **out)
+
+
 def main():
     ae_mod, bn_mod = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "train":      # only the training fixtures
+        train_fixtures(ae_mod, bn_mod)
+        return
+    train_fixtures(ae_mod, bn_mod)
     torch.set_grad_enabled(False)
 
     # ---- tiny: self-contained
