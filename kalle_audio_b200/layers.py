@@ -21,8 +21,8 @@ from . import _lib
 
 
 class _NoBackward(torch.autograd.Function):
-    """Marks outputs as non-differentiable through this library: backward is not built yet, so a
-    training step fails loudly instead of silently producing zero gradients."""
+    """Marks the output of a stand-alone leaf module as non-differentiable: only the fused encoder / decoder
+    plans have a backward pass, and a leaf fails loudly instead of silently producing zero gradients."""
 
     @staticmethod
     def forward(ctx, out, *params):
@@ -30,8 +30,9 @@ class _NoBackward(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad):
-        raise NotImplementedError("kalle_audio_b200: backward (training step, BASELINE config 5) is not implemented "
-                                  "in this round; forward/inference only")
+        raise NotImplementedError("kalle_audio_b200: the stand-alone leaf modules (SnakeBeta, WNConv1d, "
+                                  "WNConvTranspose1d) are forward-only; train through OobleckEncoder / "
+                                  "OobleckDecoder, whose fused plans carry the backward pass")
 
 
 def guard_grad(out: torch.Tensor, params) -> torch.Tensor:

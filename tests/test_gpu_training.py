@@ -51,11 +51,11 @@ def test_snake_bwd_kernel(dev):
     y = O.snake_beta(x.t().unsqueeze(0), al, be)      # [1, C, rows]
     y.backward(gy.t().unsqueeze(0))
     xd, gd = x.detach().to(dev), gy.to(dev)
+    ald, bed = al.detach().to(dev), be.detach().to(dev)
     gx = torch.empty_like(xd)
     da, db = torch.empty(Cc, device=dev), torch.empty(Cc, device=dev)
     scratch = torch.empty(2 * Cc, device=dev)
-    _lib.check(_lib.lib().kvae_snake_bwd(xd.data_ptr(), gd.data_ptr(), gx.data_ptr(), al.detach().to(dev).data_ptr(),
-                                         be.detach().to(dev).data_ptr(), 1, da.data_ptr(), db.data_ptr(), rows, Cc,
+    _lib.check(_lib.lib().kvae_snake_bwd(xd.data_ptr(), gd.data_ptr(), gx.data_ptr(), ald.data_ptr(), bed.data_ptr(), 1, da.data_ptr(), db.data_ptr(), rows, Cc,
                                          scratch.data_ptr(), _lib.stream_ptr(dev)))
     assert float((gx.cpu() - x.grad).abs().max()) <= 1e-5
     assert float((da.cpu() - al.grad).abs().max()) <= 1e-4 * float(al.grad.abs().max())
