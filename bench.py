@@ -412,6 +412,89 @@ def run_extra(args):
         dist.destroy_process_group()
 
 
+def run_train(args):
+    """BASELINE configs[4]: SAO encoder + decoder training step (encode -> vae_sample -> decode -> Gaussian NLL +
+    KL -> backward -> gradient all-reduce -> AdamW), 4 clips x 5.016 s per GPU (8 GPUs = the config's global batch
+    of 32), bf16 tensor-core mode with fp32 master weights.  Reports step time, trained audio-seconds per second,
+    algorithmic TFLOP/s (3 x forward FLOPs) and the exposed all-reduce time (step with the all-reduce minus the
+    same step without it)."""
+    import torch
+    import torch.distributed as dist
+    import kalle_audio_b200 as k
+    from kalle_audio_b200 import _lib, training as TR
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    ae = k.create_autoencoder_from_config(sao_config()).train().to(dev)
+    B, frames = args.micro_batch or 4, 108
+    L = frames * 2048
+    x = (0.1 * torch.randn(B, 2, L, generator=torch.Generator().manual_seed(2 + rank))).to(dev)
+    noise = torch.randn(B, 64, frames, generator=torch.Generator().manual_seed(3 + rank)).to(dev)
+    tr = TR.AutoencoderTrainer(ae, lr=1e-4, kl_weight=1e-4, log_sigma=-2.0, precision="bf16")
+
+    def sync():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(steps):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            info = tr.training_step(x, noise)
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps, info
+
+    losses = []
+    for _ in range(max(args.warmup, 3)):
+        losses.append(float(tr.training_step(x, noise)["loss"]))
+    _lib.lib().kvae_launch_count(1)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms, info = timed(args.steps)
+    clocks = sampler.stop()
+    launches = int(_lib.lib().kvae_launch_count(0))
+    losses.append(float(info["loss"]))
+    ms_nosync = ms
+    if world > 1:
+        tr.sync.enabled = False            # same step without the gradient all-reduce (ranks diverge; timing only)
+        ms_nosync, _ = timed(args.steps)
+        tr.sync.enabled = True
+    if rank == 0:
+        peaks = measured_peaks()
+        enc_r, dec_r = ae.encoder.runner(dev), ae.decoder.runner(dev)
+        fwd = enc_r.flops(B, L) + dec_r.flops(B, frames)
+        tfl = 3.0 * fwd / (ms * 1e-3) / 1e12
+        audio_s = world * B * L / SAO["sample_rate"]
+        print(json.dumps({
+            "metric": "vae_train_audio_sec_per_sec", "value": audio_s / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "BASELINE configs[4]: SAO sigmaVAE training step fwd+bwd (Gaussian NLL + KL), "
+                                   f"{B} clips x {L / SAO['sample_rate']:.3f} s per GPU (global batch {B * world}), bf16 "
+                                   "tensor-core operands, fp32 master weights / gradients / AdamW, NCCL all-reduce of "
+                                   "the flat gradients overlapped with the encoder backward"},
+            "clocks": clocks, "gpu_launches": launches,
+            "tflops_per_gpu": tfl, "frac_of_sustained_bf16": tfl / peaks["bf16_tflops_sustained"],
+            "allreduce_exposed_ms": ms - ms_nosync, "params": int(tr.flat_enc.numel() + tr.flat_dec.numel()),
+            "loss_first_to_last": [losses[0], losses[-1]]}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -419,12 +502,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["cuda", "reference"], default="cuda")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", choices=["roundtrip", "o12_decode", "stream"], default="roundtrip",
-                    help="roundtrip = BASELINE configs[1] (the driver's line); o12_decode = configs[2]; stream = configs[3]")
+    ap.add_argument("--workload", choices=["roundtrip", "o12_decode", "stream", "train"], default="roundtrip",
+                    help="roundtrip = BASELINE configs[1] (the driver's line); o12_decode = configs[2]; stream = configs[3]; "
+                         "train = configs[4]")
     ap.add_argument("--micro-batch", type=int, default=0)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "train":
+        run_train(args)
     elif args.workload != "roundtrip":
         run_extra(args)
     else:

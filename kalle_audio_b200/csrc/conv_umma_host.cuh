@@ -15,6 +15,7 @@
 #include "conv_umma.cuh"
 #include "conv_umma2.cuh"
 #include "conv_ru.cuh"
+#include "wgrad_umma.cuh"
 
 namespace kvae {
 
@@ -506,6 +507,114 @@ inline cudaError_t launch_conv_ru(const RuLaunch& L, cudaStream_t stream) {
     attr_set[dev & 63] = true;
   }
   conv_ru_kernel<<<L.grid, kRuThreads, L.smem, stream>>>(L.tmA, L.tmW7, L.tmW1, L.tmR, L.tmO, L.tmX, L.p);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ tensor-core weight gradient (wgrad_umma.cuh)
+struct WgradLaunch {
+  CUtensorMap tmD, tmS;
+  WgradUmmaParams p;
+  dim3 grid;
+  size_t smem = 0;
+};
+
+// dense [B, Td, Cd] and strided [B, Ts, Cs] are bf16 channels-last; dWp is the packed [K][Cd][Cs] fp32 accumulator.
+// (stride, dil, pad) are the FORWARD convolution's: the strided tensor is read at t*stride + k*dil - pad.
+inline bool prepare_wgrad_umma(const __nv_bfloat16* dense, int Td, int Cd, const __nv_bfloat16* strided, int Ts, int Cs,
+                               int B, int K, int stride, int dil, int pad, float* dWp, WgradLaunch& L, std::string& err) {
+  if (Cd % 64 || Cs % 64) { err = "wgrad: channel counts not multiples of 64"; return false; }
+  if (stride > 1 && dil != 1) { err = "wgrad: strided conv with dilation unsupported"; return false; }
+  if (Ts % stride) { err = "wgrad: strided length not divisible by stride"; return false; }
+  if (K > kWgMaxTaps * kWgMaxGroups) { err = "wgrad: too many taps"; return false; }
+  WgradUmmaParams& p = L.p;
+  std::memset(&p, 0, sizeof(p));
+  struct T3 { int phase, delta, k; };
+  std::vector<T3> taps;
+  for (int k = 0; k < K; ++k) {
+    const int off = k * dil - pad;
+    taps.push_back({posmod(off, stride), floordiv(off, stride), k});
+  }
+  std::stable_sort(taps.begin(), taps.end(), [](const T3& a, const T3& b) {
+    return a.phase != b.phase ? a.phase < b.phase : a.delta < b.delta;
+  });
+  p.n_groups = (K + kWgMaxTaps - 1) / kWgMaxTaps;
+  int span = 0, max_slabs = 1;
+  for (int g = 0; g < p.n_groups; ++g) {
+    const int lo = g * kWgMaxTaps, hi = std::min(K, lo + kWgMaxTaps);
+    p.g_ntaps[g] = hi - lo;
+    int nslabs = 0;
+    for (int t = lo; t < hi; ++t) {
+      int slab = -1;
+      for (int s2 = 0; s2 < nslabs; ++s2)
+        if (p.s_phase[g][s2] == taps[t].phase) slab = s2;
+      if (slab < 0) {          // taps are sorted by (phase, delta): the first tap of a phase has its smallest delta
+        slab = nslabs++;
+        p.s_phase[g][slab] = taps[t].phase;
+        p.s_row0[g][slab] = taps[t].delta;
+      }
+      p.g_k[g][t - lo] = taps[t].k;
+      p.g_slab[g][t - lo] = slab;
+      p.g_shift[g][t - lo] = taps[t].delta - p.s_row0[g][slab];
+      span = std::max(span, p.g_shift[g][t - lo]);
+    }
+    p.g_nslabs[g] = nslabs;
+    max_slabs = std::max(max_slabs, nslabs);
+  }
+  const size_t budget = 227 * 1024 - 2048;
+  bool ok = false;
+  for (int R : {128, 64, 32, 16}) {
+    const int RS = (R + span + 7) & ~7;
+    if (RS > 256) continue;
+    const size_t stage = wgrad_umma_stage_bytes(R, RS, max_slabs);
+    const int NS = static_cast<int>(std::min<size_t>(4, budget / stage));
+    if (NS < 2) continue;
+    if (NS < 3 && R > 32) continue;       // prefer a deeper pipeline over a taller stage
+    p.R = R; p.RS = RS; p.NS = NS;
+    ok = true;
+    break;
+  }
+  if (!ok) {
+    for (int R : {64, 32, 16}) {
+      const int RS = (R + span + 7) & ~7;
+      if (RS > 256) continue;
+      const size_t stage = wgrad_umma_stage_bytes(R, RS, max_slabs);
+      if (budget / stage < 2) continue;
+      p.R = R; p.RS = RS; p.NS = 2;
+      ok = true;
+      break;
+    }
+  }
+  if (!ok) { err = "wgrad: tile does not fit shared memory"; return false; }
+  p.B = B; p.Td = Td; p.Cd = Cd; p.Cs = Cs; p.K = K;
+  p.chunks_per_clip = (Td + p.R - 1) / p.R;
+  p.n_cd = (Cd + 127) / 128;
+  p.n_cs = (Cs + 127) / 128;
+  const long long combos = static_cast<long long>(p.n_groups) * p.n_cd * p.n_cs;
+  const long long items = static_cast<long long>(B) * p.chunks_per_clip;
+  long long nsplit = std::max<long long>(1, (3ll * sm_count() + combos - 1) / combos);
+  nsplit = std::min(nsplit, items);
+  long long ips = (items + nsplit - 1) / nsplit;
+  nsplit = (items + ips - 1) / ips;
+  if (nsplit > 65535) { err = "wgrad: too many splits"; return false; }
+  p.items_per_split = static_cast<int>(ips);
+  p.dWp = dWp;
+  if (!make_act_tmap(&L.tmD, dense, B, Td, Cd, 1, p.R, err)) return false;
+  if (!make_act_tmap(&L.tmS, strided, B, Ts, Cs, stride, p.RS, err)) return false;
+  L.grid = dim3(static_cast<unsigned>(combos), static_cast<unsigned>(nsplit));
+  L.smem = 1024 + 1024 + static_cast<size_t>(p.NS) * wgrad_umma_stage_bytes(p.R, p.RS, max_slabs);
+  return true;
+}
+
+inline cudaError_t launch_wgrad_umma(const WgradLaunch& L, cudaStream_t stream) {
+  static bool attr_set[64] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
+  wgrad_umma_kernel<<<L.grid, 256, L.smem, stream>>>(L.tmD, L.tmS, L.p);
   return cudaGetLastError();
 }
 

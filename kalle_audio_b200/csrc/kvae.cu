@@ -75,6 +75,7 @@ struct ConvLayer {
   bool set = false;
   // offsets (in floats) into the flat parameter / gradient buffer: [bias][weight_g][weight_v]
   long long off_bias = -1, off_g = -1, off_v = -1;
+  long long off_dwp = -1;             // tensor-core convs: offset of the packed [K][Cd][Cs] weight-gradient accumulator
   int dim0() const { return g.kind == kConvT ? g.Cin : g.Cout; }
   size_t numel() const { return static_cast<size_t>(g.Cin) * g.Cout * g.K; }
 };
@@ -135,6 +136,8 @@ struct PreparedRun {
     dim3 dg_grid;
     int dg_cfg = 0;
     size_t dg_smem = 0;
+    int wg_kind = 0;                // 0 CUDA-core (torch-layout atomics), 1 tensor-core (packed accumulator)
+    WgradLaunch wg_umma;
     WgradParams wg;
     dim3 wg_grid;
     bool wg_x_is_D = false, wg_x_is_S = false;   // step 0: the operand is the caller's input tensor
@@ -165,6 +168,8 @@ struct kvae_plan {
   std::vector<long long> param_sizes;   // segment sizes in module.parameters() order
   bool train_packs = false;
   float* scale_scratch = nullptr;   // g/||v|| per dim-0 row of the conv being packed
+  float* dwp = nullptr;             // packed weight-gradient accumulators of the tensor-core convs
+  size_t dwp_floats = 0;
   std::map<std::tuple<int, long long, void*>, std::unique_ptr<PreparedRun>> runs;
   std::map<std::tuple<int, long long, void*>, std::unique_ptr<PreparedRun>> truns;
   // optional per-step CUDA-event timing (bench.py's roofline leg)
@@ -835,7 +840,16 @@ bool prepare_backward(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R
       bw.wg_x_is_D = a_is_x;
     }
     w.B = B; w.K = c.g.K; w.stride = c.g.stride; w.dil = c.g.dilation; w.pad = c.g.pad;
-    {
+    if (c.off_dwp >= 0) {
+      // tensor-core weight gradient: bf16 operands (saved activation, bf16 copy of the gradient), MN-major
+      if (a_f32 || a_is_x) { err = "internal: bf16 operand missing for the tensor-core weight gradient"; return false; }
+      bw.wg_kind = 1;
+      const __nv_bfloat16* ab = static_cast<const __nv_bfloat16*>(a_ptr);
+      const bool conv = c.g.kind == kConv;
+      if (!prepare_wgrad_umma(conv ? Gb(k) : ab, w.Td, w.Cd, conv ? ab : Gb(k), w.Ts, w.Cs, B, c.g.K, c.g.stride,
+                              c.g.dilation, c.g.pad, p->dwp + c.off_dwp, bw.wg_umma, err))
+        return false;
+    } else {
       const int tiles = ceil_div(w.Cd, 64) * ceil_div(w.Cs, 64);
       const long long rows = static_cast<long long>(B) * w.Td;
       long long nsplit = std::max<long long>(1, (4ll * sm_count()) / (static_cast<long long>(tiles) * w.K));
@@ -930,6 +944,7 @@ int run_backward(kvae_plan* p, const void* x, int x_dtype, const void* gy, int g
   const int n = static_cast<int>(steps.size());
   uint8_t* base = static_cast<uint8_t*>(ws);
   KV_CUDA(cudaMemsetAsync(grads, 0, static_cast<size_t>(p->n_params) * 4, st));
+  if (p->dwp_floats) KV_CUDA(cudaMemsetAsync(p->dwp, 0, p->dwp_floats * 4, st));
   {
     // grad_out [B, C, T_last] -> channels-last fp32, then bf16 copy + bias gradient of the last conv
     const ConvLayer& c = p->convs[steps[n - 1].conv];
@@ -952,7 +967,10 @@ int run_backward(kvae_plan* p, const void* x, int x_dtype, const void* gy, int g
     const Step& s = steps[k];
     const ConvLayer& c = p->convs[s.conv];
     PreparedRun::Bwd& bw = R.bwd[k];
-    {
+    if (bw.wg_kind == 1) {
+      KV_CUDA(launch_wgrad_umma(bw.wg_umma, st));
+      ++g_launches;
+    } else {
       WgradParams w = bw.wg;
       if (bw.wg_x_is_D) { w.D = x; w.D_f32 = (x_dtype == KVAE_F32); }
       if (bw.wg_x_is_S) { w.S = x; w.S_f32 = (x_dtype == KVAE_F32); }
@@ -985,15 +1003,22 @@ int run_backward(kvae_plan* p, const void* x, int x_dtype, const void* gy, int g
       ++g_launches;
     }
   }
-  if (params) {
-    // weight-norm backward in place: the weight_v slot holds dW (folded-weight gradient) -> (dv, dg)
-    for (const ConvLayer& c : p->convs) {
-      const int inner = static_cast<int>(c.numel() / c.dim0());
-      weight_norm_bwd_kernel<<<c.dim0(), 256, 0, st>>>(params + c.off_v, params + c.off_g, grads + c.off_v,
-                                                       grads + c.off_v, grads + c.off_g, inner);
-      KV_CUDA(cudaGetLastError());
-      ++g_launches;
+  // weight-norm backward: dW (folded-weight gradient; in place in the weight_v slot, or packed by the
+  // tensor-core kernel) -> (dv, dg); without params the packed gradients are only re-ordered
+  for (const ConvLayer& c : p->convs) {
+    const int R = c.dim0(), inner = static_cast<int>(c.numel() / R);
+    if (c.off_dwp >= 0) {
+      weight_norm_bwd_packed_kernel<<<R, 256, 0, st>>>(params ? params + c.off_v : nullptr,
+                                                       params ? params + c.off_g : nullptr, p->dwp + c.off_dwp,
+                                                       grads + c.off_v, grads + c.off_g, R, inner / c.g.K, c.g.K);
+    } else if (params) {
+      weight_norm_bwd_kernel<<<R, 256, 0, st>>>(params + c.off_v, params + c.off_g, grads + c.off_v, grads + c.off_v,
+                                                grads + c.off_g, inner);
+    } else {
+      continue;
     }
+    KV_CUDA(cudaGetLastError());
+    ++g_launches;
   }
   return 0;
 }
@@ -1086,6 +1111,7 @@ void kvae_plan_destroy(kvae_plan* p) {
     cudaFree(s.inv_b);
   }
   cudaFree(p->scale_scratch);
+  cudaFree(p->dwp);
   delete p;
 }
 
@@ -1329,6 +1355,15 @@ int kvae_plan_load_params(kvae_plan* p, const float* params, int logscale, int t
     s.logscale = logscale ? 1 : 0;
     s.set = true;
     ++g_launches;
+  }
+  if (train && !p->dwp) {
+    const char* e = getenv("KVAE_WGRAD_DIRECT");     // development switch: CUDA-core weight gradients everywhere
+    const bool direct = e && e[0] == '1';
+    size_t off = 0;
+    for (ConvLayer& c : p->convs)
+      if (c.umma && !direct) { c.off_dwp = static_cast<long long>(off); off += c.numel(); }
+    p->dwp_floats = off;
+    if (off) KV_CUDA(cudaMalloc(&p->dwp, off * 4));
   }
   if (train) p->train_packs = true;
   return 0;

@@ -227,5 +227,15 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// Same with both operands MN-major (bits 15 / 16): the contraction dimension is the slow one in shared memory.
+__host__ __device__ constexpr uint32_t idesc_bf16_f32_mn(int M, int N) {
+  return idesc_bf16_f32(M, N) | (1u << 15) | (1u << 16);
+}
+
+// 16-byte vector reduction to global memory (fp32 x 4), address 16-byte aligned.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 }  // namespace ptx
 }  // namespace kvae

@@ -244,6 +244,52 @@ __global__ void weight_norm_bwd_kernel(const float* v, const float* g, const flo
   if (threadIdx.x == 0) dg[blockIdx.x] = dot / n;
 }
 
+// Same, with dw in the packed layout [K][R][Cc] the tensor-core weight-gradient kernel accumulates into
+// (v, dv in the torch layout [R][Cc][K]).  g == nullptr: no weight norm, dv = dw re-ordered.
+__global__ void weight_norm_bwd_packed_kernel(const float* v, const float* g, const float* dwp, float* dv, float* dg,
+                                              int R, int Cc, int K) {
+  __shared__ float red[2][32];
+  const int i = blockIdx.x;
+  const int inner = Cc * K;
+  const size_t base = static_cast<size_t>(i) * inner;
+  // walk the packed layout in its own order (c fastest) for coalesced reads of dw
+  float nn = 0.f, dot = 0.f;
+  if (g) {
+    for (int j = threadIdx.x; j < inner; j += blockDim.x) {
+      const int k = j / Cc, c = j % Cc;
+      const float x = v[base + static_cast<size_t>(c) * K + k];
+      nn = fmaf(x, x, nn);
+      dot = fmaf(dwp[(static_cast<size_t>(k) * R + i) * Cc + c], x, dot);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      nn += __shfl_xor_sync(0xffffffffu, nn, o);
+      dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = nn; red[1][threadIdx.x >> 5] = dot; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float a = (threadIdx.x < (blockDim.x >> 5)) ? red[0][threadIdx.x] : 0.f;
+      float b = (threadIdx.x < (blockDim.x >> 5)) ? red[1][threadIdx.x] : 0.f;
+      for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+      }
+      if (threadIdx.x == 0) { red[0][0] = a; red[1][0] = b; }
+    }
+    __syncthreads();
+    nn = red[0][0];
+    dot = red[1][0];
+  }
+  const float n = g ? sqrtf(nn) : 1.f;
+  const float s = g ? g[i] / n : 1.f, q = g ? dot / nn : 0.f;
+  for (int j = threadIdx.x; j < inner; j += blockDim.x) {     // torch order for coalesced writes of dv
+    const int c = j / K, k = j % K;
+    const float d = dwp[(static_cast<size_t>(k) * R + i) * Cc + c];
+    dv[base + j] = g ? s * (d - v[base + j] * q) : d;
+  }
+  if (g && threadIdx.x == 0) dg[i] = dot / n;
+}
+
 // ---------------------------------------------------------------- vae_sample backward (bottleneck.py:51-62)
 // latents = noise*scale + mean ; kl = (mean^2 + var - log var - 1).sum(1).mean(), stdev = softplus(scale)+1e-4.
 //   d mean  = gz + gkl * 2 mean / (B*T)
