@@ -136,7 +136,12 @@ struct PreparedRun {
     dim3 dg_grid;
     int dg_cfg = 0;
     size_t dg_smem = 0;
-    int wg_kind = 0;                // 0 CUDA-core (torch-layout atomics), 1 tensor-core (packed accumulator)
+    int wg_kind = 0;                // 0 CUDA-core (torch-layout atomics), 1 tensor-core (packed accumulator),
+                                    // 2 waveform-edge streaming kernel
+    EdgeWgradParams wg_edge;
+    int wg_edge_grid = 0;
+    size_t wg_edge_smem = 0;
+    bool wg_edge_x_is_thin = false;
     WgradLaunch wg_umma;
     WgradParams wg;
     dim3 wg_grid;
@@ -749,19 +754,48 @@ int run_plan(kvae_plan* p, bool train, const void* in, int in_dtype, void* out, 
 //   snake:  G_{k-1} = dA * SnakeBeta'(raw_{k-1}) + [G_{k+1} if step k+1 adds raw_{k-1} as its skip connection]
 //           and, in the same pass, d alpha / d beta of that SnakeBeta and d bias of conv k-1 (= column sums of G_{k-1})
 void set_sb_grid(SnakeBwdParams& sb, dim3& grid) {
+  const int width = (sb.C % 4 == 0) ? sb.C / 4 : sb.C;   // float4 columns (vectorised kernel) or scalar columns
   int CW = 1;
-  while (CW * 2 <= std::min(sb.C, 256)) CW *= 2;
+  while (CW * 2 <= std::min(width, 256)) CW *= 2;
   sb.CW = CW;
-  const int cols = ceil_div(sb.C, CW);
+  const int cols = ceil_div(width, CW);
   const int nrl = 256 / CW;
   // enough blocks to fill the machine, each with at least a few passes over its rows
   long long blocks_x = std::max<long long>(1, std::min<long long>((sb.rows + 8 * nrl - 1) / (8 * nrl),
-                                                                     (4ll * sm_count() + cols - 1) / cols));
+                                                                     (8ll * sm_count() + cols - 1) / cols));
   long long rpb = (sb.rows + blocks_x - 1) / blocks_x;
   rpb = (rpb + nrl - 1) / nrl * nrl;
   blocks_x = (sb.rows + rpb - 1) / rpb;
   sb.rows_per_block = static_cast<int>(rpb);
   grid = dim3(static_cast<unsigned>(blocks_x), cols, 1);
+}
+
+cudaError_t launch_snake_bwd(const SnakeBwdParams& sb, dim3 grid, cudaStream_t st) {
+  if (sb.C % 4 == 0) {
+    if (sb.fast) snake_bwd_vec4_kernel<true><<<grid, 256, 0, st>>>(sb);
+    else snake_bwd_vec4_kernel<false><<<grid, 256, 0, st>>>(sb);
+  } else {
+    snake_bwd_kernel<<<grid, 256, 0, st>>>(sb);
+  }
+  return cudaGetLastError();
+}
+
+// waveform-edge convs (C <-> io_channels, k7): HBM-streaming weight gradient (train.cuh::wgrad_edge_kernel)
+bool edge_wgrad_ok(const ConvGeom& g) {
+  const int thin = std::min(g.Cin, g.Cout), wide = std::max(g.Cin, g.Cout);
+  return g.kind == kConv && g.stride == 1 && g.K <= kEdgeMaxK && thin <= 2 && wide >= 32 && wide <= 256 &&
+         (wide & (wide - 1)) == 0;
+}
+
+void set_edge_grid(EdgeWgradParams& e, int& grid, size_t& smem) {
+  const int per_clip = std::max(1, (8 * sm_count() + e.B - 1) / e.B);
+  int rpb = std::max(256, (e.T + per_clip - 1) / per_clip);
+  rpb = std::min(rpb, 4096);
+  e.rows_per_block = rpb;
+  e.blocks_per_clip = (e.T + rpb - 1) / rpb;
+  grid = e.blocks_per_clip * e.B;
+  const int halo = std::max(e.pad, (e.K - 1) * e.dil - e.pad);
+  smem = static_cast<size_t>(rpb + 2 * halo) * 2 * sizeof(float);
 }
 
 bool prepare_backward(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R, std::string& err) {
@@ -849,6 +883,22 @@ bool prepare_backward(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R
       if (!prepare_wgrad_umma(conv ? Gb(k) : ab, w.Td, w.Cd, conv ? ab : Gb(k), w.Ts, w.Cs, B, c.g.K, c.g.stride,
                               c.g.dilation, c.g.pad, p->dwp + c.off_dwp, bw.wg_umma, err))
         return false;
+    } else if (edge_wgrad_ok(c.g) && ((c.g.Cout <= 2 && a_f32 && !a_is_x) || (c.g.Cin <= 2 && a_is_x))) {
+      bw.wg_kind = 2;
+      EdgeWgradParams& e = bw.wg_edge;
+      std::memset(&e, 0, sizeof(e));
+      e.B = B; e.T = static_cast<int>(T_out); e.K = c.g.K; e.dil = c.g.dilation; e.pad = c.g.pad;
+      if (c.g.Cout <= 2) {   // decoder tail: wide = SnakeBeta(stream), thin = output gradient (channels-last)
+        e.W = static_cast<const float*>(a_ptr); e.W_a = a_sn; e.W_inv_b = a_ib; e.C = c.g.Cin;
+        e.N = g_ptr; e.N_f32 = 1; e.N_sB = g_sB; e.N_sT = g_sT; e.N_sC = 1;
+        e.sigma = 1; e.out_wide_first = 0;
+      } else {               // encoder head: wide = gradient of the stream, thin = the caller's waveform (API layout)
+        e.W = g_ptr; e.C = c.g.Cout;
+        e.N = nullptr; e.N_sB = a_sB; e.N_sT = a_sT; e.N_sC = a_sC;
+        e.sigma = -1; e.out_wide_first = 1;
+        bw.wg_edge_x_is_thin = true;
+      }
+      set_edge_grid(e, bw.wg_edge_grid, bw.wg_edge_smem);
     } else {
       const int tiles = ceil_div(w.Cd, 64) * ceil_div(w.Cs, 64);
       const long long rows = static_cast<long long>(B) * w.Td;
@@ -922,6 +972,7 @@ bool prepare_backward(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R
       sb.Gb = cp.umma ? Gb(k - 1) : nullptr;
       sb.rows = static_cast<long long>(B) * T_in;
       sb.C = c.g.Cin;
+      sb.fast = (p->precision == KVAE_PREC_BF16) ? 1 : 0;
       set_sb_grid(sb, bw.sb_grid);
     }
   }
@@ -957,8 +1008,7 @@ int run_backward(kvae_plan* p, const void* x, int x_dtype, const void* gy, int g
     if (!c.umma) sb.Gb = nullptr;
     sb.d_bias = c.has_bias ? grads + c.off_bias : nullptr;
     if (sb.Gb || sb.d_bias) {
-      snake_bwd_kernel<<<R.sb_last_grid, 256, 0, st>>>(sb);
-      KV_CUDA(cudaGetLastError());
+      KV_CUDA(launch_snake_bwd(sb, R.sb_last_grid, st));
       ++g_launches;
     }
     ++g_launches;
@@ -969,6 +1019,14 @@ int run_backward(kvae_plan* p, const void* x, int x_dtype, const void* gy, int g
     PreparedRun::Bwd& bw = R.bwd[k];
     if (bw.wg_kind == 1) {
       KV_CUDA(launch_wgrad_umma(bw.wg_umma, st));
+      ++g_launches;
+    } else if (bw.wg_kind == 2) {
+      EdgeWgradParams e = bw.wg_edge;
+      if (bw.wg_edge_x_is_thin) { e.N = x; e.N_f32 = (x_dtype == KVAE_F32); }
+      e.dW = grads + c.off_v;
+      if (std::min(c.g.Cin, c.g.Cout) == 1) wgrad_edge_kernel<1><<<bw.wg_edge_grid, 256, bw.wg_edge_smem, st>>>(e);
+      else wgrad_edge_kernel<2><<<bw.wg_edge_grid, 256, bw.wg_edge_smem, st>>>(e);
+      KV_CUDA(cudaGetLastError());
       ++g_launches;
     } else {
       WgradParams w = bw.wg;
@@ -998,8 +1056,7 @@ int run_backward(kvae_plan* p, const void* x, int x_dtype, const void* gy, int g
         sb.d_beta = grads + p->snakes[s.pre_snake].off_beta;
       }
       sb.d_bias = cp.has_bias ? grads + cp.off_bias : nullptr;
-      snake_bwd_kernel<<<bw.sb_grid, 256, 0, st>>>(sb);
-      KV_CUDA(cudaGetLastError());
+      KV_CUDA(launch_snake_bwd(sb, bw.sb_grid, st));
       ++g_launches;
     }
   }
@@ -1422,8 +1479,7 @@ int kvae_snake_bwd(const float* x, const float* gy, float* gx, const float* alph
   sb.G = gx; sb.d_alpha = d_alpha; sb.d_beta = d_beta; sb.rows = rows; sb.C = C;
   dim3 grid;
   set_sb_grid(sb, grid);
-  snake_bwd_kernel<<<grid, 256, 0, st>>>(sb);
-  KV_CUDA(cudaGetLastError());
+  KV_CUDA(launch_snake_bwd(sb, grid, st));
   g_launches += 2;
   return 0;
 }

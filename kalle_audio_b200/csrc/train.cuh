@@ -59,6 +59,7 @@ struct SnakeBwdParams {
   int C;
   int CW;                 // channels per block column (power of two <= 256)
   int rows_per_block;
+  int fast;               // 1: MUFU sin/cos (bf16 mode); 0: sincosf (fp32 mode, <= 1e-5 budget)
 };
 
 __global__ void __launch_bounds__(256) snake_bwd_kernel(const SnakeBwdParams p) {
@@ -109,6 +110,176 @@ __global__ void __launch_bounds__(256) snake_bwd_kernel(const SnakeBwdParams p) 
       atomicAdd(p.d_beta + c, -t2 * ib * ib * (p.logscale ? eb : 1.f));
     }
     if (p.d_bias) atomicAdd(p.d_bias + c, tb);
+  }
+}
+
+// Vectorised form for C % 4 == 0: a thread owns 4 consecutive channels (float4 loads, 8-byte bf16 stores) and
+// walks rows; CW here counts float4 columns per block (power of two <= 256).  Same sums, same outputs.
+template <bool kFast>
+__device__ __forceinline__ void snake_bwd_elem(float& g, float xv, float a, float ib, float& s1, float& s2) {
+  float sn, cs;
+  if (kFast) { sn = __sinf(a * xv); cs = __cosf(a * xv); } else { sincosf(a * xv, &sn, &cs); }
+  const float s2x = 2.f * sn * cs;
+  s1 = fmaf(g * xv, s2x, s1);
+  s2 = fmaf(g, sn * sn, s2);
+  g = g * fmaf(ib * a, s2x, 1.f);
+}
+
+template <bool kFast>
+__global__ void __launch_bounds__(256) snake_bwd_vec4_kernel(const SnakeBwdParams p) {
+  __shared__ float4 red[3][256];
+  const int CW = p.CW;                      // float4 columns handled by this block
+  const int rl = threadIdx.x / CW;
+  const int nrl = 256 / CW;
+  const int c4 = blockIdx.y * CW + (threadIdx.x % CW);
+  const int C4 = p.C >> 2;
+  const long long r0 = static_cast<long long>(blockIdx.x) * p.rows_per_block;
+  const long long r1 = min(r0 + p.rows_per_block, p.rows);
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1, sb = s1;
+  float4 a = s1, ib = s1;
+  if (c4 < C4) {
+    if (p.a) {
+      a = __ldg(reinterpret_cast<const float4*>(p.a) + c4);
+      ib = __ldg(reinterpret_cast<const float4*>(p.inv_b) + c4);
+    }
+    const float4* dA = reinterpret_cast<const float4*>(p.dA);
+    const float4* X = reinterpret_cast<const float4*>(p.x);
+    const float4* SK = reinterpret_cast<const float4*>(p.skip);
+    float4* G = reinterpret_cast<float4*>(p.G);
+    uint2* Gb = reinterpret_cast<uint2*>(p.Gb);
+#pragma unroll 2
+    for (long long r = r0 + rl; r < r1; r += nrl) {
+      const size_t i = static_cast<size_t>(r) * C4 + c4;
+      float4 g = __ldcs(dA + i);
+      if (p.a) {
+        const float4 xv = __ldcs(X + i);
+        snake_bwd_elem<kFast>(g.x, xv.x, a.x, ib.x, s1.x, s2.x);
+        snake_bwd_elem<kFast>(g.y, xv.y, a.y, ib.y, s1.y, s2.y);
+        snake_bwd_elem<kFast>(g.z, xv.z, a.z, ib.z, s1.z, s2.z);
+        snake_bwd_elem<kFast>(g.w, xv.w, a.w, ib.w, s1.w, s2.w);
+      }
+      if (SK) {
+        const float4 k4 = __ldcs(SK + i);
+        g.x += k4.x; g.y += k4.y; g.z += k4.z; g.w += k4.w;
+      }
+      sb.x += g.x; sb.y += g.y; sb.z += g.z; sb.w += g.w;
+      if (G) G[i] = g;
+      if (Gb) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(g.x, g.y), h1 = __floats2bfloat162_rn(g.z, g.w);
+        Gb[i] = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      }
+    }
+  }
+  red[0][threadIdx.x] = s1;
+  red[1][threadIdx.x] = s2;
+  red[2][threadIdx.x] = sb;
+  __syncthreads();
+  if (threadIdx.x < CW && c4 < C4) {
+    float4 t1 = make_float4(0.f, 0.f, 0.f, 0.f), t2 = t1, tb = t1;
+    for (int j = 0; j < nrl; ++j) {
+      const float4 u1 = red[0][threadIdx.x + j * CW], u2 = red[1][threadIdx.x + j * CW], ub = red[2][threadIdx.x + j * CW];
+      t1.x += u1.x; t1.y += u1.y; t1.z += u1.z; t1.w += u1.w;
+      t2.x += u2.x; t2.y += u2.y; t2.z += u2.z; t2.w += u2.w;
+      tb.x += ub.x; tb.y += ub.y; tb.z += ub.z; tb.w += ub.w;
+    }
+    const int c = c4 * 4;
+    if (p.a && p.d_alpha) {
+      const float av[4] = {a.x, a.y, a.z, a.w}, iv[4] = {ib.x, ib.y, ib.z, ib.w};
+      const float v1[4] = {t1.x, t1.y, t1.z, t1.w}, v2[4] = {t2.x, t2.y, t2.z, t2.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float eb = 1.f / iv[e] - 1e-9f;
+        atomicAdd(p.d_alpha + c + e, v1[e] * iv[e] * (p.logscale ? av[e] : 1.f));
+        atomicAdd(p.d_beta + c + e, -v2[e] * iv[e] * iv[e] * (p.logscale ? eb : 1.f));
+      }
+    }
+    if (p.d_bias) {
+      atomicAdd(p.d_bias + c, tb.x); atomicAdd(p.d_bias + c + 1, tb.y);
+      atomicAdd(p.d_bias + c + 2, tb.z); atomicAdd(p.d_bias + c + 3, tb.w);
+    }
+  }
+}
+
+// ---------------------------------------------------------------- weight gradient of the waveform-edge convs
+// Conv1d(k, stride 1) between a wide tensor (C channels, channels-last fp32) and a thin one (NT <= 2 channels):
+//   out[c][j][k] = sum_{b,t} W[b, t + sigma*(k*dil - pad), c] * N[b, t, j]
+// sigma = +1: decoder tail (wide = SnakeBeta(stream) = conv input, thin = output gradient)  -> dW[j][c][k]
+// sigma = -1: encoder head (wide = output gradient, thin = the waveform = conv input)        -> dW[c][j][k]
+// HBM-bound (the wide tensor is read once); thread = channel, 7 x NT accumulators in registers, the thin rows a
+// block needs are staged in shared memory.  grid (nblocks), block 256 = (256 / C) row lanes x C channels.
+struct EdgeWgradParams {
+  const float* W;            // [B, T, C] fp32
+  const float* W_a;          // SnakeBeta prologue on W (nullptr: none)
+  const float* W_inv_b;
+  const void* N;             // thin tensor, element strides below
+  int N_f32;
+  long long N_sB, N_sT, N_sC;
+  float* dW;                 // torch layout; out_wide_first = 1: [C][NT][K], 0: [NT][C][K]
+  int out_wide_first;
+  int sigma;
+  int B, T, C, K, dil, pad;
+  int rows_per_block;        // rows of one clip per block (blocks never straddle clips)
+  int blocks_per_clip;
+};
+
+constexpr int kEdgeMaxK = 8;
+
+template <int NT>
+__global__ void __launch_bounds__(256) wgrad_edge_kernel(const EdgeWgradParams p) {
+  extern __shared__ float thin[];            // [rows_per_block + 2*halo][NT]
+  const int b = blockIdx.x / p.blocks_per_clip;
+  const int t0 = (blockIdx.x % p.blocks_per_clip) * p.rows_per_block;
+  const int t1 = min(t0 + p.rows_per_block, p.T);
+  const int halo = max(p.pad, (p.K - 1) * p.dil - p.pad);
+  const int nthin = (t1 - t0) + 2 * halo;
+  for (int i = threadIdx.x; i < nthin * NT; i += 256) {
+    const int r = i / NT, j = i % NT;
+    const int t = t0 - halo + r;
+    thin[i] = (t >= 0 && t < p.T) ? ld_elem(p.N, static_cast<size_t>(b * p.N_sB + t * p.N_sT + j * p.N_sC), p.N_f32) : 0.f;
+  }
+  __syncthreads();
+  const int lanes = 256 / p.C;               // row lanes (C <= 256, power of two)
+  const int c = threadIdx.x % p.C, rl = threadIdx.x / p.C;
+  float acc[kEdgeMaxK][NT];
+#pragma unroll
+  for (int k = 0; k < kEdgeMaxK; ++k)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) acc[k][j] = 0.f;
+  float a = 0.f, ib = 0.f;
+  if (p.W_a) { a = p.W_a[c]; ib = p.W_inv_b[c]; }
+  // wide row u pairs with thin row t = u - sigma*(k*dil - pad)
+  if (rl < lanes) {
+    const int u_lo = max(0, t0 - halo), u_hi = min(p.T, t1 + halo);
+    for (int u = u_lo + rl; u < u_hi; u += lanes) {
+      float w = __ldcs(p.W + (static_cast<size_t>(b) * p.T + u) * p.C + c);
+      if (p.W_a) w = snake_beta<false>(w, a, ib);
+#pragma unroll
+      for (int k = 0; k < kEdgeMaxK; ++k) {
+        if (k < p.K) {
+          const int t = u - p.sigma * (k * p.dil - p.pad);
+          if (t >= t0 && t < t1) {
+#pragma unroll
+            for (int j = 0; j < NT; ++j) acc[k][j] = fmaf(w, thin[(t - t0 + halo) * NT + j], acc[k][j]);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // reduce over row lanes through shared memory (re-using the thin buffer is not safe in size: use atomics per lane)
+#pragma unroll
+  for (int k = 0; k < kEdgeMaxK; ++k) {
+    if (k < p.K) {
+#pragma unroll
+      for (int j = 0; j < NT; ++j) {
+        float v = acc[k][j];
+        if (rl < lanes && v != 0.f) {
+          const size_t o = p.out_wide_first ? (static_cast<size_t>(c) * NT + j) * p.K + k
+                                            : (static_cast<size_t>(j) * p.C + c) * p.K + k;
+          atomicAdd(p.dW + o, v);
+        }
+      }
+    }
   }
 }
 
