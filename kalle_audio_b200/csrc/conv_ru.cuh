@@ -39,6 +39,7 @@ struct RuParams {
   int act_out;              // 1: bf16 operand out via tmO
   const float* sn_a;        // SnakeBeta folded into the operand output (nullptr: plain cast)
   const float* sn_inv_b;
+  int dbg;                  // ablation switches for tools/umma_probe (KVAE_RU_DBG); 0 in production
 };
 
 constexpr int kRuC = 128;
@@ -175,10 +176,12 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int cb = bs;
             if (++bs == p.SB) { bs = 0; bph ^= 1u; }
             ready = ptx::mbar_try_wait(&b_full[bs], bph);      // poll the NEXT stage while this tap's MMAs issue
+            if (!(p.dbg & 16) || t == 0) {
             ptx::umma_f16(d1, desc_hi | bl, desc_hi | al, idesc1, accum);
             ptx::umma_f16(d1, desc_hi | (bl + 2), desc_hi | (al + 2), idesc1, 1u);
             ptx::umma_f16(d1, desc_hi | (bl + 4), desc_hi | (al + 4), idesc1, 1u);
             ptx::umma_f16(d1, desc_hi | (bl + 6), desc_hi | (al + 6), idesc1, 1u);
+            }
             accum = 1u;
             ptx::umma_commit(&b_empty[cb]);
           }
@@ -244,7 +247,8 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::tmem_ld_wait();
           float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = snake_beta<true>(__uint_as_float(r[j]) + bias, sa, sib);
+          for (int j = 0; j < 16; ++j)
+            v[j] = (p.dbg & 4) ? __uint_as_float(r[j]) + bias : snake_beta<true>(__uint_as_float(r[j]) + bias, sa, sib);
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             *reinterpret_cast<__nv_bfloat16*>(hb[j & 7] + (tb * 16 + j) * 128) = __float2bfloat16(v[j]);
@@ -275,7 +279,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int jr = 0, ja = 0;
     uint32_t d2f_ph = 0, res_ph = 0;
     // items of this warp inside a tile: 16-row blocks sub, sub+2, ..., 14+sub
-    if (lane == 0 && static_cast<int>(blockIdx.x) < p.total_tiles) {
+    if (lane == 0 && static_cast<int>(blockIdx.x) < p.total_tiles && !(p.dbg & 1)) {
       const int b = blockIdx.x / p.q_tiles, q0 = (blockIdx.x % p.q_tiles) * 256;
       ptx::mbar_expect_tx(&my_res_full[0], kRuRawBlk);
       ptx::tma_load_4d(raw_ring, &tmX, &my_res_full[0], cbase, 0, q0 + sub * 16, b);
@@ -293,14 +297,14 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           ptx::bulk_wait_read<1>();
           int nt = tile, ni = item + 2;
           if (ni >= 16) { nt = tile + gridDim.x; ni = sub; }
-          if (nt < p.total_tiles) {
+          if (nt < p.total_tiles && !(p.dbg & 1)) {
             const int sn = (jr + 1) % 3;
             ptx::mbar_expect_tx(&my_res_full[sn], kRuRawBlk);
             ptx::tma_load_4d(raw_ring + sn * kRuRawBlk, &tmX, &my_res_full[sn], cbase, 0,
                              (nt % p.q_tiles) * 256 + ni * 16, nt / p.q_tiles);
           }
         }
-        ptx::mbar_wait(&my_res_full[jr], (res_ph >> jr) & 1u);
+        if (!(p.dbg & 1)) ptx::mbar_wait(&my_res_full[jr], (res_ph >> jr) & 1u);
         res_ph ^= (1u << jr);
         uint32_t r[16];
         __syncwarp();
@@ -320,7 +324,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 16; ++j) *reinterpret_cast<float*>(rbase[j & 7] + j * 128) = v[j];
         }
         if (p.act_out) {
-          if (p.sn_a) {
+          if (p.sn_a && !(p.dbg & 8)) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = snake_beta<true>(v[j], sa, sib);
           }
@@ -334,8 +338,8 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (p.raw_out) ptx::tma_store_4d(&tmR, rblk, cbase, 0, r0, b);
-          if (p.act_out) ptx::tma_store_4d(&tmO, ablk, cbase, 0, r0, b);
+          if (p.raw_out && !(p.dbg & 2)) ptx::tma_store_4d(&tmR, rblk, cbase, 0, r0, b);
+          if (p.act_out && !(p.dbg & 2)) ptx::tma_store_4d(&tmO, ablk, cbase, 0, r0, b);
           ptx::bulk_commit();
         }
         jr = (jr + 1 == 3) ? 0 : jr + 1;

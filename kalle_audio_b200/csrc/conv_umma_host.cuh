@@ -486,6 +486,7 @@ inline bool prepare_conv_ru(const RuArgs& a, int B, int T, int dilation, RuLaunc
   p.total_tiles = p.q_tiles * B;
   p.bias7 = a.bias7; p.s2_a = a.s2_a; p.s2_inv_b = a.s2_inv_b; p.bias1 = a.bias1;
   p.sn_a = a.sn_a; p.sn_inv_b = a.sn_inv_b;
+  if (const char* e = getenv("KVAE_RU_DBG")) p.dbg = atoi(e);
   if (!make_act_tmap(&L.tmA, a.a, B, T, kRuC, 1, p.RB, err)) return false;
   if (!make_w_tmap(&L.tmW7, a.w7, 7, kRuC, kRuC, kRuC, err)) return false;
   if (!make_w_tmap(&L.tmW1, a.w1, 1, kRuC, kRuC, kRuC, err)) return false;
