@@ -162,6 +162,19 @@ int kvae_gaussian_nll(const void* x, const void* xhat, void* gxhat, float* loss,
 int kvae_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, size_t n, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
 
+/* Backward of kvae_conv1d_fwd (autograd of F.conv1d / F.conv_transpose1d on the stand-alone WNConv1d /
+ * WNConvTranspose1d modules): dw = gradient of the folded weight (torch layout, overwritten), dbias [Cout] and gx
+ * (same shape as x) optional.  fp32 arithmetic; x, gy, gx of `dtype`.  scratch as for kvae_conv1d_fwd. */
+int kvae_conv1d_bwd(const void* x, const void* gy, const float* w_folded, void* gx, float* dw, float* dbias,
+                    int transposed, int B, int Cin, int Cout, long long T, int K, int stride, int dilation, int padding,
+                    int dtype, void* scratch, size_t scratch_bytes, void* stream);
+
+/* ---- post-decode tail ---- */
+/* audio.to(float32).div(max|audio|).clamp(-1,1).mul(32767).to(int16) -- the peak-normalised PCM conversion every
+ * caller of the decoder repeats (infer_0828_sigma.py:298, train_offline.py:302,319); bit-exact with torch's
+ * separately rounded ops.  scratch: >= 4 bytes. */
+int kvae_pcm16(const void* wav, int dtype, int16_t* out, size_t n, void* scratch, void* stream);
+
 /* ---- latent sampling ---- */
 /* sample(mean,'fix') of model_sigmaVAE.py:153-178 / 187-213: out = mean + std*noise, rounded exactly as
  * torch does (mul, then add).  std_noise != NULL selects 'gaussian': per-item std_b = std_noise[b]*value. */

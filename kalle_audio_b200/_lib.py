@@ -68,6 +68,9 @@ SIGNATURES = {
     "kvae_conv1d_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                   C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kvae_conv1d_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_size_t, C.c_void_p]),
     "kvae_conv1d_scratch_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "kvae_plan_param_count": (C.c_longlong, [C.c_void_p]),
     "kvae_plan_param_sizes": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.c_int]),
@@ -87,6 +90,7 @@ SIGNATURES = {
                                     C.c_int, C.c_void_p, C.c_void_p]),
     "kvae_adamw_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_float, C.c_float,
                                   C.c_float, C.c_float, C.c_float, C.c_int, C.c_float, C.c_void_p]),
+    "kvae_pcm16": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "kvae_sigma_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_float,
                                     C.c_void_p, C.c_float, C.c_size_t, C.c_void_p]),
     "kvae_vae_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,

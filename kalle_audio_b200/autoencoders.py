@@ -22,7 +22,7 @@ from torch import nn
 from . import _lib
 from ._plan import PlanCache, PlanFunction
 from .bottleneck import Bottleneck, create_bottleneck_from_config
-from .layers import SnakeBeta, WNConv1d, WNConvTranspose1d, guard_grad
+from .layers import SnakeBeta, WNConv1d, WNConvTranspose1d
 
 
 def get_activation(activation: Literal["elu", "snake", "none"], antialias=False, channels=None) -> nn.Module:
@@ -160,6 +160,9 @@ class _OobleckBase(nn.Module):
         r = self.runner(x.device)
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             # training: saved activations + hand-written backward (kvae_forward_train / kvae_backward)
+            if getattr(self._arch, "final_tanh", 0):
+                raise NotImplementedError("final_tanh=True is inference-only in kalle_audio_b200 (no reference config "
+                                          "trains with it)")
             return PlanFunction.apply(r, x, self._out_channels_for_plan, self._ratio, self._out_dtype(x),
                                       *r.param_list())
         return r.run(x, self._out_channels_for_plan, self._ratio, self._out_dtype(x))

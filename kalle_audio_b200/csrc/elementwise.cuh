@@ -164,6 +164,29 @@ fold_pack_kernel(const float* v, const float* scale, int R, int Cc, int K, __nv_
   }
 }
 
+// ---------------------------------------------------------------- waveform -> int16 PCM
+// The tail every caller of the decoder repeats (infer_0828_sigma.py:298, train_offline.py:302,319):
+//   audio.to(float32).div(max|audio|).clamp(-1, 1).mul(32767).to(int16)
+// two passes: peak (bit pattern of a non-negative float orders like an unsigned integer), then the same
+// separately rounded div / mul and the truncating conversion torch performs.
+__global__ void absmax_kernel(const void* x, size_t n, int f32, unsigned int* peak_bits) {
+  float m = 0.f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    m = fmaxf(m, fabsf(ld_elem(x, i, f32)));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(peak_bits, __float_as_uint(m));
+}
+__global__ void pcm16_kernel(const void* x, size_t n, int f32, const unsigned int* peak_bits, int16_t* out) {
+  const float peak = __uint_as_float(*peak_bits);
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    float v = __fdiv_rn(ld_elem(x, i, f32), peak);
+    v = fminf(fmaxf(v, -1.f), 1.f);
+    out[i] = static_cast<int16_t>(__float2int_rz(__fmul_rn(v, 32767.f)));
+  }
+}
+
 // ---------------------------------------------------------------- latent sampling
 // sample(mean, 'fix') of model_sigmaVAE.py:153-178,187-213: mean + std * noise, evaluated as torch
 // does -- two separately rounded operations (mul then add), never an FMA -- so the result is

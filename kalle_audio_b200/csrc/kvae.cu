@@ -1359,6 +1359,82 @@ int kvae_conv1d_fwd(const void* x, void* y, const float* w, const float* bias, i
   return 0;
 }
 
+int kvae_conv1d_bwd(const void* x, const void* gy, const float* w, void* gx, float* dw, float* dbias, int transposed,
+                    int B, int Cin, int Cout, long long T, int K, int stride, int dilation, int padding, int dtype,
+                    void* scratch, size_t scratch_bytes, void* stream) {
+  if (!x || !gy || !w || !dw || !scratch) return fail("null argument");
+  if (!check_dtype(dtype)) return fail("bad dtype");
+  if (B <= 0 || Cin <= 0 || Cout <= 0 || K <= 0 || T <= 0) return fail("empty input");
+  if (stride < 1 || stride > kMaxPhases) return fail("stride out of range (1..8)");
+  if (scratch_bytes < kvae_conv1d_scratch_bytes(Cin, Cout, K)) return fail("scratch too small");
+  ConvGeom g{transposed ? kConvT : kConv, Cin, Cout, K, stride, dilation, padding};
+  const long long T_out = g.out_len(static_cast<int>(T));
+  if (T_out <= 0) return fail("input shorter than the kernel");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int f32 = (dtype == KVAE_F32);
+  // ---- weight gradient (torch layout), straight from the API layout through element strides
+  const size_t n = static_cast<size_t>(Cin) * Cout * K;
+  KV_CUDA(cudaMemsetAsync(dw, 0, n * 4, st));
+  WgradParams wp;
+  std::memset(&wp, 0, sizeof(wp));
+  const long long xsB = static_cast<long long>(Cin) * T, gsB = static_cast<long long>(Cout) * T_out;
+  if (!transposed) {
+    wp.D = gy; wp.D_sB = gsB; wp.D_sT = 1; wp.D_sC = T_out; wp.Td = static_cast<int>(T_out); wp.Cd = Cout;
+    wp.S = x; wp.S_sB = xsB; wp.S_sT = 1; wp.S_sC = T; wp.Ts = static_cast<int>(T); wp.Cs = Cin;
+  } else {
+    wp.D = x; wp.D_sB = xsB; wp.D_sT = 1; wp.D_sC = T; wp.Td = static_cast<int>(T); wp.Cd = Cin;
+    wp.S = gy; wp.S_sB = gsB; wp.S_sT = 1; wp.S_sC = T_out; wp.Ts = static_cast<int>(T_out); wp.Cs = Cout;
+  }
+  wp.D_f32 = wp.S_f32 = f32;
+  wp.dW = dw; wp.B = B; wp.K = K; wp.stride = stride; wp.dil = dilation; wp.pad = padding;
+  {
+    const int tiles = ceil_div(wp.Cd, 64) * ceil_div(wp.Cs, 64);
+    const long long rows = static_cast<long long>(B) * wp.Td;
+    long long nsplit = std::max<long long>(1, (4ll * sm_count()) / (static_cast<long long>(tiles) * K));
+    nsplit = std::max<long long>(1, std::min<long long>(std::min(nsplit, (rows + 4 * kWgRows - 1) / (4 * kWgRows)), 65535));
+    long long rps = (rows + nsplit - 1) / nsplit;
+    rps = (rps + kWgRows - 1) / kWgRows * kWgRows;
+    nsplit = (rows + rps - 1) / rps;
+    wp.rows_per_split = rps;
+    wgrad_direct_kernel<<<dim3(tiles, K, static_cast<unsigned>(nsplit)), 256, 0, st>>>(wp);
+    KV_CUDA(cudaGetLastError());
+  }
+  if (dbias) {
+    bias_grad_cf_kernel<<<Cout, 256, 0, st>>>(gy, f32, dbias, B, Cout, T_out);
+    KV_CUDA(cudaGetLastError());
+  }
+  g_launches += 2;
+  if (!gx) return 0;
+  // ---- data gradient: the forward kernel under the opposite kind, same weight tensor
+  const ConvGeom gd = dgrad_geom(g, static_cast<int>(T));
+  TapPlan tp;
+  std::string err;
+  if (!build_taps(gd, false, tp, err)) return fail(err);
+  float* wd = static_cast<float*>(scratch);
+  pack_weights_kernel<<<static_cast<int>(std::min<size_t>((n + 255) / 256, 4096)), 256, 0, st>>>(
+      w, gd.kind == kConvT, gd.Cout, gd.Cin, K, nullptr, wd);
+  KV_CUDA(cudaGetLastError());
+  DirectParams d;
+  std::memset(&d, 0, sizeof(d));
+  d.B = B; d.P_out = tp.P_out; d.P_in = tp.P_in;
+  d.Tq_out = static_cast<int>((T + tp.P_out - 1) / tp.P_out); d.T_out = static_cast<int>(T);
+  d.T_in = static_cast<int>(T_out); d.Cin = gd.Cin; d.Cout = gd.Cout; d.span = tp.span;
+  for (int i = 0; i <= kMaxPhases; ++i) d.tap_begin[i] = tp.tap_begin[i];
+  for (size_t i = 0; i < tp.taps.size(); ++i) d.taps[i] = tp.taps[i];
+  d.x = gy; d.x_f32 = f32;
+  d.x_sB = gsB; d.x_sT = 1; d.x_sC = T_out;
+  d.w = wd;
+  d.out_raw = gx; d.out_raw_f32 = f32;
+  d.o_sB = xsB; d.o_sT = 1; d.o_sC = T;
+  const int cfg = (gd.Cout <= 4) ? 1 : 0;
+  const int BT = cfg ? 128 : 32, BN = cfg ? 4 : 64;
+  dim3 grid(ceil_div(d.Tq_out, BT) * tp.P_out, ceil_div(gd.Cout, BN), B);
+  const size_t smem = (static_cast<size_t>(BT + tp.span) * (kDirectKC + 1) + kDirectKC * BN) * sizeof(float);
+  KV_CUDA(launch_direct(d, grid, cfg, smem, st));
+  g_launches += 2;
+  return 0;
+}
+
 // ------------------------------------------------------------------ training step
 long long kvae_plan_param_count(const kvae_plan* p) { return p ? p->n_params : fail("null plan"); }
 
@@ -1531,6 +1607,22 @@ int kvae_adamw_step(float* params, const float* grads, float* exp_avg, float* ex
                                                                        grad_scale);
   KV_CUDA(cudaGetLastError());
   ++g_launches;
+  return 0;
+}
+
+// ------------------------------------------------------------------ PCM tail
+int kvae_pcm16(const void* wav, int dtype, int16_t* out, size_t n, void* scratch, void* stream) {
+  if (!wav || !out || !scratch) return fail("null argument");
+  if (!check_dtype(dtype)) return fail("bad dtype");
+  if (n == 0) return 0;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  KV_CUDA(cudaMemsetAsync(scratch, 0, 4, st));
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
+  absmax_kernel<<<blocks, 256, 0, st>>>(wav, n, dtype == KVAE_F32, static_cast<unsigned int*>(scratch));
+  KV_CUDA(cudaGetLastError());
+  pcm16_kernel<<<blocks, 256, 0, st>>>(wav, n, dtype == KVAE_F32, static_cast<const unsigned int*>(scratch), out);
+  KV_CUDA(cudaGetLastError());
+  g_launches += 2;
   return 0;
 }
 

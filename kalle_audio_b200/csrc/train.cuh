@@ -37,6 +37,26 @@ __global__ void cf_to_cl_f32_kernel(const void* x, int f32, float* y, int C, lon
   }
 }
 
+// ---------------------------------------------------------------- bias gradient, [B, C, T] layout
+// db[c] = sum_{b,t} gy[b, c, t].  One block per channel.
+__global__ void bias_grad_cf_kernel(const void* gy, int f32, float* db, int B, int C, long long T) {
+  __shared__ float red[32];
+  const int c = blockIdx.x;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const size_t base = (static_cast<size_t>(b) * C + c) * T;
+    for (long long t = threadIdx.x; t < T; t += blockDim.x) s += ld_elem(gy, base + t, f32);
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) db[c] = t;
+  }
+}
+
 // ---------------------------------------------------------------- SnakeBeta backward + reductions
 // y = x + inv_b * sin(a x)^2  (blocks.py:301-302), a = exp(alpha), inv_b = 1/(exp(beta) + 1e-9):
 //   dy/dx     = 1 + inv_b * a * sin(2 a x)

@@ -9,8 +9,9 @@ reference:
 Parameters are initialised through torch's own ``nn.Conv1d`` / ``nn.ConvTranspose1d`` constructors, so
 the same ``torch.manual_seed`` yields the same random-init ``state_dict`` as the reference.
 
-``forward`` of a leaf runs the layer-level C-ABI kernels (fp32 arithmetic).  The fast path is not here:
-``OobleckEncoder`` / ``OobleckDecoder`` hand the whole stack to a fused plan (see ``_plan.py``).
+``forward`` / ``backward`` of a leaf run the layer-level C-ABI kernels (fp32 arithmetic, autograd nodes
+``_SnakeFn`` / ``_ConvFn``).  The fast path is not here: ``OobleckEncoder`` / ``OobleckDecoder`` hand the whole
+stack to a fused plan (see ``_plan.py``).
 """
 from __future__ import annotations
 
@@ -20,27 +21,80 @@ from torch import nn
 from . import _lib
 
 
-class _NoBackward(torch.autograd.Function):
-    """Marks the output of a stand-alone leaf module as non-differentiable: only the fused encoder / decoder
-    plans have a backward pass, and a leaf fails loudly instead of silently producing zero gradients."""
+class _SnakeFn(torch.autograd.Function):
+    """SnakeBeta.forward / backward on [B, C, T] (blocks.py:331-339 and its autograd): kvae_snake_fwd / kvae_snake_bwd."""
 
     @staticmethod
-    def forward(ctx, out, *params):
-        return out.view_as(out)
+    def forward(ctx, x, alpha, beta, logscale):
+        a = alpha.detach().float().contiguous()
+        b = beta.detach().float().contiguous()
+        y = _snake_call(x.detach(), a, b, logscale)
+        ctx.save_for_backward(x.detach(), a, b)
+        ctx.logscale = bool(logscale)
+        ctx.param_dtypes = (alpha.dtype, beta.dtype)
+        return y
 
     @staticmethod
-    def backward(ctx, grad):
-        raise NotImplementedError("kalle_audio_b200: the stand-alone leaf modules (SnakeBeta, WNConv1d, "
-                                  "WNConvTranspose1d) are forward-only; train through OobleckEncoder / "
-                                  "OobleckDecoder, whose fused plans carry the backward pass")
+    def backward(ctx, gy):
+        x, a, b = ctx.saved_tensors
+        B, Cc, T = x.shape
+        # the kernel works on channels-last rows [B*T, C] (the layout of the fused plans)
+        xr = x.float().transpose(1, 2).contiguous()
+        gr = gy.detach().float().transpose(1, 2).contiguous()
+        gx = torch.empty_like(xr)
+        da = torch.empty(Cc, dtype=torch.float32, device=x.device)
+        db = torch.empty(Cc, dtype=torch.float32, device=x.device)
+        scratch = torch.empty(2 * Cc, dtype=torch.float32, device=x.device)
+        if xr.numel():
+            _lib.check(_lib.lib().kvae_snake_bwd(xr.data_ptr(), gr.data_ptr(), gx.data_ptr(), a.data_ptr(), b.data_ptr(),
+                                                 int(ctx.logscale), da.data_ptr(), db.data_ptr(), B * T, Cc,
+                                                 scratch.data_ptr(), _lib.stream_ptr(x.device)))
+        else:
+            da.zero_(); db.zero_()
+        return (gx.transpose(1, 2).contiguous().to(x.dtype), da.to(ctx.param_dtypes[0]), db.to(ctx.param_dtypes[1]),
+                None)
 
 
-def guard_grad(out: torch.Tensor, params) -> torch.Tensor:
-    if torch.is_grad_enabled():
-        ps = [p for p in params if p.requires_grad]
-        if ps:
-            return _NoBackward.apply(out, *ps)
-    return out
+class _ConvFn(torch.autograd.Function):
+    """WNConv1d / WNConvTranspose1d forward / backward on [B, C, T]: kvae_conv1d_fwd, kvae_conv1d_bwd and the
+    weight-norm backward (autograd of torch.nn.utils.weight_norm + F.conv1d / F.conv_transpose1d)."""
+
+    @staticmethod
+    def forward(ctx, mod, x, bias, *wparams):
+        y, xin, w = mod._forward_impl(x.detach())
+        ctx.mod = mod
+        ctx.save_for_backward(xin, w, *[p.detach() for p in wparams])
+        ctx.has_bias = bias is not None
+        ctx.x_dtype = x.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        mod = ctx.mod
+        xin, w, *wparams = ctx.saved_tensors
+        L = _lib.lib()
+        g = gy.detach().to(xin.dtype).contiguous()
+        B, _, T = xin.shape
+        K, s, d, p = mod.kernel_size[0], mod.stride[0], mod.dilation[0], mod.padding[0]
+        gx = torch.empty_like(xin) if ctx.needs_input_grad[1] else None
+        dw = torch.empty_like(w)
+        db = torch.empty(mod.out_channels, dtype=torch.float32, device=xin.device) if ctx.has_bias else None
+        nscratch = L.kvae_conv1d_scratch_bytes(mod.in_channels, mod.out_channels, K)
+        scratch = torch.empty(nscratch, dtype=torch.uint8, device=xin.device)
+        _lib.check(L.kvae_conv1d_bwd(xin.data_ptr(), g.data_ptr(), w.data_ptr(), _lib.ptr(gx), dw.data_ptr(), _lib.ptr(db),
+                                     int(mod.transposed), B, mod.in_channels, mod.out_channels, T, K, s, d, p,
+                                     _lib.dtype_code(xin.dtype), scratch.data_ptr(), nscratch, _lib.stream_ptr(xin.device)))
+        if len(wparams) == 2:     # (weight_g, weight_v): weight-norm backward
+            gparam, v = wparams
+            vf, gf = v.float().contiguous(), gparam.float().contiguous()
+            dv, dg = torch.empty_like(vf), torch.empty(vf.shape[0], dtype=torch.float32, device=vf.device)
+            _lib.check(L.kvae_weight_norm_bwd(vf.data_ptr(), gf.data_ptr(), dw.data_ptr(), dv.data_ptr(), dg.data_ptr(),
+                                              vf.shape[0], vf[0].numel(), _lib.stream_ptr(vf.device)))
+            wgrads = (dg.view_as(gparam).to(gparam.dtype), dv.to(v.dtype))
+        else:                     # plain weight (weight norm removed)
+            wgrads = (dw.to(wparams[0].dtype),)
+        gxo = None if gx is None else gx.to(ctx.x_dtype)
+        return (None, gxo, None if db is None else db, *wgrads)
 
 
 def snake_beta(x, alpha, beta):
@@ -84,9 +138,10 @@ class SnakeBeta(nn.Module):
 
     def forward(self, x):
         _lib.require_cuda(x, "SnakeBeta.forward")
-        y = _snake_call(x, self.alpha.detach().float().contiguous(), self.beta.detach().float().contiguous(),
-                        self.alpha_logscale)
-        return guard_grad(y, (self.alpha, self.beta))
+        if torch.is_grad_enabled() and (x.requires_grad or self.alpha.requires_grad or self.beta.requires_grad):
+            return _SnakeFn.apply(x, self.alpha, self.beta, self.alpha_logscale)
+        return _snake_call(x, self.alpha.detach().float().contiguous(), self.beta.detach().float().contiguous(),
+                           self.alpha_logscale)
 
 
 def _single(v):
@@ -154,6 +209,13 @@ class _WNConvBase(nn.Module):
             raise ValueError(f"expected [B, {self.in_channels}, T], got {tuple(x.shape)}")
         if x.shape[0] == 0 or x.shape[2] == 0:
             raise ValueError("empty input")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.conv_params())):
+            wparams = (self.weight_g, self.weight_v) if self.has_weight_norm else (self._parameters["weight"],)
+            return _ConvFn.apply(self, x, self.bias, *wparams)
+        return self._forward_impl(x)[0]
+
+    def _forward_impl(self, x):
+        """(y, the contiguous input actually used, the folded fp32 weight)"""
         xin = x if x.dtype in (torch.float32, torch.bfloat16) else x.float()
         xin = xin.contiguous()
         w = self.folded_weight()
@@ -175,7 +237,7 @@ class _WNConvBase(nn.Module):
                                      _lib.dtype_code(xin.dtype), scratch.data_ptr(), nscratch,
                                      _lib.stream_ptr(x.device)))
         y = y if y.dtype == x.dtype else y.to(x.dtype)
-        return guard_grad(y, self.conv_params())
+        return y, xin, w
 
     def extra_repr(self):
         return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, "

@@ -1,8 +1,25 @@
 """Checkpoint / weight-norm / audio-shape helpers (reference stable_audio_tools/models/utils.py:6-20,
-stable_audio_tools/inference/utils.py prepare_audio, stable_audio_tools/data/utils.py:8-20 PadCrop)."""
+stable_audio_tools/inference/utils.py prepare_audio, stable_audio_tools/data/utils.py:8-20 PadCrop) and the
+post-decode PCM tail the reference's callers repeat (infer_0828_sigma.py:298, train_offline.py:302,319)."""
 from __future__ import annotations
 
 import torch
+
+from . import _lib
+
+
+def to_pcm16(audio: torch.Tensor) -> torch.Tensor:
+    """``audio.to(float32).div(max|audio|).clamp(-1, 1).mul(32767).to(int16)`` in two kernels on the device
+    (global peak over the whole tensor, as in the reference); bit-identical to the torch expression."""
+    _lib.require_cuda(audio, "to_pcm16")
+    a = audio if audio.dtype in (torch.float32, torch.bfloat16) else audio.float()
+    a = a.contiguous()
+    out = torch.empty(a.shape, dtype=torch.int16, device=a.device)
+    if a.numel():
+        scratch = torch.empty(1, dtype=torch.int32, device=a.device)
+        _lib.check(_lib.lib().kvae_pcm16(a.data_ptr(), _lib.dtype_code(a.dtype), out.data_ptr(), a.numel(),
+                                         scratch.data_ptr(), _lib.stream_ptr(a.device)))
+    return out
 
 
 def load_ckpt_state_dict(ckpt_path):

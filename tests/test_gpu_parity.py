@@ -167,12 +167,11 @@ def test_errors(dev):
         m.decode(torch.randn(0, 4, 8, device=dev))
     with pytest.raises(k.KvaeError):
         m.decode(torch.randn(1, 4, 8))                        # CPU tensor
-    # leaf modules have no layer-level backward of their own (the stacks do: tests/test_gpu_training.py)
-    leaf = k.SnakeBeta(4).to(dev)
-    with torch.enable_grad():
-        y = leaf(torch.randn(1, 4, 8, device=dev))
-        with pytest.raises(NotImplementedError):
-            y.sum().backward()
+    with pytest.raises(NotImplementedError):                  # final_tanh has no backward
+        dt = k.OobleckDecoder(out_channels=2, channels=8, latent_dim=4, c_mults=[1, 2], strides=[2, 4], use_snake=True,
+                              final_tanh=True).to(dev)
+        with torch.enable_grad():
+            dt(torch.randn(1, 4, 8, device=dev))
 
 
 # --------------------------------------------------------------------------- full-size models
@@ -375,3 +374,12 @@ def test_config4_streaming_chunks_equal_unchunked_o12_latent1024(dev):
     assert float((full - chunked).abs().max()) <= 1e-6
     dec.enable_cuda_graphs(True)
     assert torch.equal(ae.decode_audio(z, chunked=True, overlap=32, chunk_size=128), chunked)
+
+
+def test_pcm16_tail_bit_exact(dev):
+    """infer_0828_sigma.py:298: output.to(float32).div(max|output|).clamp(-1, 1).mul(32767).to(int16)."""
+    torch.manual_seed(11)
+    for x in (0.3 * torch.randn(2, 2, 50001), torch.randn(1, 1, 7).bfloat16(), 1e-3 * torch.randn(3, 1, 4096)):
+        ref = x.to(torch.float32).div(torch.max(torch.abs(x.to(torch.float32)))).clamp(-1, 1).mul(32767).to(torch.int16)
+        got = k.to_pcm16(x.to(dev))
+        assert got.dtype == torch.int16 and torch.equal(got.cpu(), ref)

@@ -111,6 +111,69 @@ def test_flat_adamw_matches_torch(dev):
     assert float((flat.cpu() - ref.detach()).abs().max()) <= 2e-6
 
 
+# --------------------------------------------------------------------------- stand-alone leaf modules under autograd
+def test_snake_beta_module_backward(dev):
+    torch.manual_seed(4)
+    m = k.SnakeBeta(19).to(dev)
+    with torch.no_grad():
+        m.alpha.copy_(0.4 * torch.randn(19)); m.beta.copy_(0.4 * torch.randn(19))
+    x = torch.randn(2, 19, 333, requires_grad=True)
+    al, be = m.alpha.detach().cpu().requires_grad_(True), m.beta.detach().cpu().requires_grad_(True)
+    w = torch.randn(2, 19, 333)
+    (O.snake_beta(x, al, be) * w).sum().backward()
+    xd = x.detach().to(dev).requires_grad_(True)
+    (m(xd) * w.to(dev)).sum().backward()
+    assert float((xd.grad.cpu() - x.grad).abs().max()) <= 1e-5
+    assert float((m.alpha.grad.cpu() - al.grad).abs().max()) <= 1e-4 * float(al.grad.abs().max())
+    assert float((m.beta.grad.cpu() - be.grad).abs().max()) <= 1e-4 * float(be.grad.abs().max())
+
+
+@pytest.mark.parametrize("transposed,cin,cout,K,stride,dil,pad,T", [
+    (0, 5, 7, 7, 1, 1, 3, 50), (0, 16, 16, 7, 1, 9, 27, 300), (0, 8, 16, 8, 4, 1, 2, 64), (0, 8, 4, 10, 5, 1, 3, 45),
+    (0, 6, 6, 1, 1, 1, 0, 33), (0, 2, 32, 7, 1, 1, 3, 200), (1, 8, 4, 4, 2, 1, 1, 33), (1, 6, 3, 11, 5, 1, 3, 11),
+    (1, 16, 8, 8, 4, 1, 2, 20)])
+def test_wnconv_modules_backward(dev, transposed, cin, cout, K, stride, dil, pad, T):
+    torch.manual_seed(5)
+    if transposed:
+        m = k.WNConvTranspose1d(cin, cout, K, stride=stride, padding=pad)
+    else:
+        m = k.WNConv1d(cin, cout, K, stride=stride, dilation=dil, padding=pad)
+    with torch.no_grad():
+        m.weight_g.mul_(1.0 + 0.2 * torch.randn_like(m.weight_g))
+    sd = {"c." + n: p.detach().clone().requires_grad_(True) for n, p in m.state_dict().items()}
+    x = torch.randn(2, cin, T, requires_grad=True)
+    ref = (O._wn_conv_transpose1d(sd, "c", x, stride=stride, padding=pad) if transposed
+           else O._wn_conv1d(sd, "c", x, stride=stride, padding=pad, dilation=dil))
+    w = torch.randn_like(ref)
+    (ref * w).sum().backward()
+    m = m.to(dev)
+    xd = x.detach().to(dev).requires_grad_(True)
+    (m(xd) * w.to(dev)).sum().backward()
+    tol = lambda r: 2e-5 * max(1.0, float(r.abs().max()))
+    assert float((xd.grad.cpu() - x.grad).abs().max()) <= tol(x.grad)
+    for n, p in m.named_parameters():
+        r = sd["c." + n].grad
+        assert p.grad is not None and float((p.grad.cpu() - r).abs().max()) <= tol(r), n
+
+
+def test_residual_unit_standalone_backward(dev):
+    """A block of the module tree used on its own (leaf kernels chained by torch autograd)."""
+    torch.manual_seed(6)
+    ru = k.ResidualUnit(12, 12, dilation=3, use_snake=True)
+    H.randomize_snake(ru, 3)
+    sd = {"r." + n: p.detach().clone().requires_grad_(True) for n, p in ru.state_dict().items()}
+    x = torch.randn(2, 12, 90, requires_grad=True)
+    w = torch.randn(2, 12, 90)
+    (O.residual_unit(sd, "r", x, 3) * w).sum().backward()
+    ru = ru.to(dev)
+    xd = x.detach().to(dev).requires_grad_(True)
+    (ru(xd) * w.to(dev)).sum().backward()
+    assert float((xd.grad.cpu() - x.grad).abs().max()) <= 2e-5 * max(1.0, float(x.grad.abs().max()))
+    for n, p in ru.named_parameters():
+        r = sd["r." + n].grad
+        assert float((p.grad.cpu() - r).abs().max()) <= 1e-4 * max(1.0, float(r.abs().max())), n
+
+
 # --------------------------------------------------------------------------- whole training step
 def _loss_and_grads(m, x, noise, kl_weight, log_sigma, precision):
     m.encoder.set_precision(precision)
