@@ -394,6 +394,19 @@ def run_extra(args):
         y = dec(z[:, :, :chunk])
         y[0, 0, :8].cpu()
         first_wall = time.perf_counter() - t0
+        # exact-context streaming (kalle_audio_b200.StreamingDecoder): hop 96, window 96 + 10 + 10 frames
+        sdec = k.StreamingDecoder(dec, hop=chunk - overlap)
+        zz = torch.randn(1, latent, 96 * 12, generator=torch.Generator().manual_seed(5)).to(dev)
+        for i in range(4):
+            sdec.push(zz[:, :, i * 96:(i + 1) * 96])
+        sync()
+        es = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        es[0].record()
+        for i in range(4, 12):
+            sdec.push(zz[:, :, i * 96:(i + 1) * 96])
+        es[1].record()
+        sync()
+        stream_hop_ms = es[0].elapsed_time(es[1]) / 8
         if rank == 0:
             chunk_ms = ev[0].elapsed_time(ev[1]) / args.steps
             full_ms = ev[1].elapsed_time(ev[2]) / args.steps
@@ -404,6 +417,9 @@ def run_extra(args):
                               "data": "synthetic", "per_chunk_ms": chunk_ms,
                               "first_chunk_wall_ms_incl_d2h": first_wall * 1e3,
                               "real_time_factor_per_chunk": (chunk - overlap) * 1280 / 16000 / (chunk_ms * 1e-3),
+                              "exact_context_stream": {"hop_frames": chunk - overlap, "window_frames": chunk - overlap + sdec.left + sdec.right,
+                                                       "ms_per_hop": stream_hop_ms, "recompute_factor": sdec.recompute_factor,
+                                                       "real_time_factor": (chunk - overlap) * 1280 / 16000 / (stream_hop_ms * 1e-3)},
                               "config": {"workload": "BASELINE configs[3]: O12 latent-1024 (dim2048) decoder, batch 1, "
                                                      "chunked decode chunk 128 / overlap 32 over T=375 (4 windows), "
                                                      "CUDA-graph replay, bf16 mode"}}), flush=True)

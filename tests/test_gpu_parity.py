@@ -383,3 +383,26 @@ def test_pcm16_tail_bit_exact(dev):
         ref = x.to(torch.float32).div(torch.max(torch.abs(x.to(torch.float32)))).clamp(-1, 1).mul(32767).to(torch.int16)
         got = k.to_pcm16(x.to(dev))
         assert got.dtype == torch.int16 and torch.equal(got.cpu(), ref)
+
+
+@pytest.mark.parametrize("precision,hop", [("fp32", 7), ("bf16", 16), ("fp32", 96)])
+def test_streaming_decoder_equals_full_decode(dev, precision, hop):
+    """StreamingDecoder (exact receptive-field context) against one decode of the whole sequence, ragged pushes."""
+    m = H.build("tiny", 0, snake_seed=7).to(dev)
+    m.decoder.set_precision(precision)
+    z = torch.randn(2, 4, 211, generator=torch.Generator().manual_seed(4)).to(dev)
+    full = m.decoder(z)
+    sd = k.StreamingDecoder(m.decoder, hop=hop, use_cuda_graphs=(hop == 16))
+    assert (sd.left, sd.right) == (15, 15)
+    pieces, pos = [], 0
+    for n in [1, 0, 5, 40, 3, 97, 20, 45]:
+        pieces.append(sd.push(z[:, :, pos:pos + n]))
+        pos += n
+    assert pos == 211
+    emitted = sum(p.shape[2] for p in pieces)
+    assert emitted % (hop * 40) == 0 and emitted <= (211 - sd.right) * 40      # only final frames were emitted
+    pieces.append(sd.flush())
+    y = torch.cat(pieces, dim=2)
+    assert y.shape == full.shape
+    tol = 2e-6 if precision == "fp32" else 1e-6      # same inputs, same per-output summation order
+    assert float((y - full).abs().max()) <= tol * max(1.0, float(full.abs().max()))

@@ -116,3 +116,27 @@ def test_precision_selection():
     assert m.decoder._resolve_precision() == k._lib.KVAE_PREC_BF16
     with pytest.raises(ValueError):
         m.set_precision("fp8")
+
+
+def test_decoder_context_frames_is_the_exact_receptive_field():
+    """streaming.decoder_context_frames against a brute-force probe of the oracle decoder: perturb one latent
+    frame and see which output frames move."""
+    import torch
+    import helpers as H
+    from oracle import oobleck_oracle as O
+    from kalle_audio_b200.streaming import decoder_context_frames
+    assert decoder_context_frames([2, 4, 4, 8, 8]) == (10, 10)       # SAO; SURVEY.md Appendix C measured +-10
+    assert decoder_context_frames([2, 4, 4, 5, 8]) == (10, 10)       # 12.5 Hz models
+    g = H.golden("tiny_ae")
+    sd = {k[len("sd.decoder."):]: H.t(g[k]) for k in g.files if k.startswith("sd.decoder.")}
+    strides = H.strides_of("tiny")
+    left, right = decoder_context_frames(strides)
+    with torch.no_grad():
+        z = torch.randn(1, 4, 64, generator=torch.Generator().manual_seed(0))
+        y = O.oobleck_decoder(sd, z, strides)
+        z2 = z.clone()
+        z2[:, :, 32] += 1.0
+        moved = ((O.oobleck_decoder(sd, z2, strides) - y).abs().amax((0, 1)) > 0).nonzero().flatten()
+    ratio = 40
+    # frame 32 is right context of frames down to 32 - right and left context of frames up to 32 + left
+    assert int(moved.min()) // ratio == 32 - right and int(moved.max()) // ratio == 32 + left
