@@ -169,6 +169,199 @@ __global__ void __launch_bounds__(288, 1) conv_wave_out_kernel(const WaveOutPara
   }
 }
 
+// ---------------------------------------------------------------- decoder tail on the tensor cores (TF32)
+// Same layer as conv_wave_out_kernel.  On the CUDA cores it needs 1792 FMAs per output sample and ran at ~30 % of
+// HBM speed.  Here the channel contraction is ONE small tcgen05 kind::tf32 GEMM per tile and the 7 taps are summed
+// afterwards:   P[t, (k, co)] = sum_ci SnakeBeta(x)[t, ci] * w[k][ci][co]      (M = 128 rows, N = 16 >= 7*io, K = 128)
+//               y[t, co]      = sum_k P[t + k - 3, (k, co)]
+// so every staged element is read by the tensor core exactly once (a first version that used row-shifted
+// descriptors per tap re-read the tile 7 times and was bound by the shared-memory port).
+//   * warp 0 (TMA) streams the fp32 residual stream tile [128 rows x 128 ch] as four 32-channel boxes
+//     (SWIZZLE_128B: one 128-byte line = 32 floats = one K-major tf32 operand row) into a 3-slot ring;
+//   * warps 4-11 apply SnakeBeta IN PLACE on the staged tile (element-wise, so the swizzle is irrelevant; the
+//     channel of a 16-byte unit is recovered from its position), round to tf32 (cvt.rna) and hand the slot to the
+//     MMA warp through fence.proxy.async + mbarrier;
+//   * warp 1 issues 4 chunks x 4 K-steps MMAs of 128 x 16 x 8; the weights [4][16 x 32] stay in shared memory;
+//   * warps 12-15 move P (TMEM lane = row) to shared memory, sum the taps of the 122 outputs whose windows lie
+//     inside the tile and write [B, io, T] directly, coalesced.
+// The stream stays fp32 in HBM and the accumulation fp32; only the operands are rounded to tf32 (11 significant
+// bits), ~4x finer than the bf16 operands of every other conv in the stack.
+struct WaveOutTcParams {
+  const float* pro_a;       // SnakeBeta exp(alpha) [128]
+  const float* pro_inv_b;
+  const float* w;           // [7][128][COUT] fp32
+  void* y;                  // [B, COUT, T]
+  int y_f32;
+  int T, B, COUT, tanh_out;
+  int tiles_per_clip, total_tiles;
+};
+
+constexpr int kWoTcRows = 128;                       // staged rows per tile
+constexpr int kWoTcTile = kWoTcRows - 6;             // outputs per tile (k7: 3 halo rows each side)
+constexpr int kWoTcChunk = kWoTcRows * 128;          // bytes of one 32-channel chunk
+constexpr int kWoTcSlab = 4 * kWoTcChunk;            // 65536 B
+constexpr int kWoTcSlots = 3;
+constexpr int kWoTcWBytes = 4 * 16 * 128;            // 8192 B
+constexpr int kWoTcPStride = 17;                     // floats per P row in shared memory (conflict-free)
+constexpr int kWoTcThreads = 512;
+
+inline size_t wave_out_tc_smem() {
+  return 1024 + 1024 + kWoTcSlots * kWoTcSlab + kWoTcWBytes + 1024 + 2 * kWoTcRows * kWoTcPStride * 4;
+}
+
+__global__ void __launch_bounds__(kWoTcThreads, 1)
+conv_wave_out_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ WaveOutTcParams p) {
+  extern __shared__ uint8_t sm_wotc_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(sm_wotc_raw);
+  uint8_t* smem = sm_wotc_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);      // [3] TMA landed
+  uint64_t* ready = full + 4;                               // [3] SnakeBeta applied (8 warps)
+  uint64_t* empty = full + 8;                               // [3] MMAs done reading the slot
+  uint64_t* acc_full = full + 12;                           // [2]
+  uint64_t* acc_empty = full + 14;                          // [2] (4 epilogue warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full + 16);
+  uint8_t* ring = smem + 1024;
+  uint8_t* wsm = ring + kWoTcSlots * kWoTcSlab;
+  float* tab = reinterpret_cast<float*>(wsm + kWoTcWBytes);   // [128] a, [128] inv_b
+  float* pbuf = tab + 256;                                    // [2][128][17]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmX);
+    for (int i = 0; i < kWoTcSlots; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&ready[i], 8); ptx::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 4); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 2) {
+    ptx::tmem_alloc(tmem_slot, 32);
+    ptx::tmem_relinquish();
+  }
+  // weights -> K-major SWIZZLE_128B tiles [chunk][16 rows n = k*COUT + co (zero-padded)][32 floats]
+  for (int i = threadIdx.x; i < 4 * 16 * 32; i += kWoTcThreads) {
+    const int ci = i & 31, n = (i >> 5) & 15, c = i >> 9;
+    float v = 0.f;
+    if (n < 7 * p.COUT) {
+      const int k = n / p.COUT, co = n % p.COUT;
+      v = ptx::round_tf32(__ldg(p.w + (static_cast<size_t>(k) * 128 + c * 32 + ci) * p.COUT + co));
+    }
+    *reinterpret_cast<float*>(wsm + c * 2048 + n * 128 + (((ci >> 2) ^ (n & 7)) << 4) + (ci & 3) * 4) = v;
+  }
+  if (threadIdx.x < 128) {
+    tab[threadIdx.x] = __ldg(p.pro_a + threadIdx.x);
+    tab[128 + threadIdx.x] = __ldg(p.pro_inv_b + threadIdx.x);
+  }
+  ptx::fence_proxy_async();
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (ptx::elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int b = tile / p.tiles_per_clip;
+        const int t0 = (tile % p.tiles_per_clip) * kWoTcTile;
+        ptx::mbar_wait(&empty[s], ph ^ 1u);
+        ptx::mbar_expect_tx(&full[s], kWoTcSlab);
+        for (int c = 0; c < 4; ++c)
+          ptx::tma_load_4d(ring + s * kWoTcSlab + c * kWoTcChunk, &tmX, &full[s], c * 32, 0, t0 - 3, b);
+        if (++s == kWoTcSlots) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      const uint32_t idesc = ptx::idesc_tf32_f32(128, 16);
+      const uint64_t desc_hi = (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+      const uint32_t ring_lo = ((ptx::smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);
+      const uint32_t w_lo = ((ptx::smem_u32(wsm) & 0x3FFFFu) >> 4) | (1u << 16);
+      int s = 0, a = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&ready[s], ph);
+        ptx::mbar_wait(&acc_empty[a], aph ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d = tmem_base + a * 16;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint32_t al = ring_lo + ((s * kWoTcSlab + c * kWoTcChunk) >> 4);
+          const uint32_t bl = w_lo + ((c * 2048) >> 4);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)                         // 8 tf32 = 32 B per K-step
+            ptx::umma_tf32(d, desc_hi | (al + 2 * ks), desc_hi | (bl + 2 * ks), idesc, (c | ks) ? 1u : 0u);
+        }
+        ptx::umma_commit(&empty[s]);
+        ptx::umma_commit(&acc_full[a]);
+        if (++s == kWoTcSlots) { s = 0; ph ^= 1u; }
+        if (++a == 2) { a = 0; aph ^= 1u; }
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ------------------------------------------------------------ SnakeBeta in place on the staged tile
+    const int tid = threadIdx.x - 128;                    // 0..255
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      ptx::mbar_wait(&full[s], ph);
+      float4* slab = reinterpret_cast<float4*>(ring + s * kWoTcSlab);
+#pragma unroll 4
+      for (int u = tid; u < 4 * kWoTcRows * 8; u += 256) {
+        const int r = (u >> 3) & (kWoTcRows - 1), c = u >> 10;
+        const int ch = c * 32 + (((u & 7) ^ (r & 7)) << 2);
+        const float4 a4 = *reinterpret_cast<const float4*>(tab + ch);
+        const float4 b4 = *reinterpret_cast<const float4*>(tab + 128 + ch);
+        float4 v = slab[u];
+        v.x = ptx::round_tf32(snake_beta<true>(v.x, a4.x, b4.x));
+        v.y = ptx::round_tf32(snake_beta<true>(v.y, a4.y, b4.y));
+        v.z = ptx::round_tf32(snake_beta<true>(v.z, a4.z, b4.z));
+        v.w = ptx::round_tf32(snake_beta<true>(v.w, a4.w, b4.w));
+        slab[u] = v;
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&ready[s]);
+      if (++s == kWoTcSlots) { s = 0; ph ^= 1u; }
+    }
+  } else if (warp >= 12) {
+    // ------------------------------------------------------------ P -> shared memory -> tap sum -> [B, io, T]
+    const int quad = warp & 3;
+    const int i = quad * 32 + lane;                      // row of the tile / output index
+    int a = 0;
+    uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int b = tile / p.tiles_per_clip;
+      const int t = (tile % p.tiles_per_clip) * kWoTcTile + i;
+      ptx::mbar_wait(&acc_full[a], aph);
+      ptx::tc_fence_after();
+      uint32_t r[16];
+      ptx::tmem_ld_32x16(tmem_base + a * 16 + (static_cast<uint32_t>(quad * 32) << 16), r);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      float* pb = pbuf + a * kWoTcRows * kWoTcPStride;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pb[i * kWoTcPStride + j] = __uint_as_float(r[j]);
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[a]);
+      ptx::named_bar_sync(1, 128);                       // all 128 rows of P are in shared memory
+      if (i < kWoTcTile && t < p.T) {
+        for (int co = 0; co < p.COUT; ++co) {
+          float v = 0.f;
+#pragma unroll
+          for (int k = 0; k < 7; ++k) v += pb[(i + k) * kWoTcPStride + k * p.COUT + co];
+          if (p.tanh_out) v = tanhf(v);
+          st_elem(p.y, (static_cast<size_t>(b) * p.COUT + co) * p.T + t, p.y_f32, v);
+        }
+      }
+      if (++a == 2) { a = 0; aph ^= 1u; }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 2) ptx::tmem_dealloc(tmem_base, 32);
+}
+
 struct WaveInParams {
   const void* x;          // [B, CIN, T]
   int x_f32;

@@ -127,6 +127,8 @@ struct PreparedRun {
   std::vector<RuLaunch> ru;
   std::vector<WaveInParams> wave_in;
   std::vector<WaveOutParams> wave_out;
+  struct WaveOutTc { CUtensorMap tmX; WaveOutTcParams p; };
+  std::vector<WaveOutTc> wave_out_tc;   // kind 6: decoder tail on the tensor cores (TF32)
   Layout layout;
   // ---- training runs only: the backward pass over the saved activations
   struct Bwd {
@@ -437,6 +439,7 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
   R.kind.assign(n, 1);
   R.wave_in.resize(n);
   R.wave_out.resize(n);
+  R.wave_out_tc.resize(n);
   uint8_t* base = static_cast<uint8_t*>(ws);
   auto tptr = [&](int id) -> void* { return R.layout.t[id].bytes ? base + R.layout.t[id].offset : nullptr; };
   for (int k = 0; k < n; ++k) {
@@ -491,6 +494,17 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
       w.Cin = c.g.Cin;
       w.tanh_out = (p->direction == KVAE_DECODER && p->arch.final_tanh) ? 1 : 0;
       R.kind[k] = 3;
+      const char* cc = getenv("KVAE_WAVE_OUT_CC");     // development switch: the CUDA-core tail
+      if (!(cc && cc[0] == '1')) {
+        PreparedRun::WaveOutTc& t = R.wave_out_tc[k];
+        std::memset(&t.p, 0, sizeof(t.p));
+        t.p.pro_a = w.pro_a; t.p.pro_inv_b = w.pro_inv_b; t.p.w = w.w;
+        t.p.T = w.T; t.p.B = B; t.p.COUT = c.g.Cout; t.p.tanh_out = w.tanh_out;
+        t.p.tiles_per_clip = (w.T + kWoTcTile - 1) / kWoTcTile;
+        t.p.total_tiles = t.p.tiles_per_clip * B;
+        if (!make_out_tmap(&t.tmX, w.x, B, w.T, 128, 1, true, err, kWoTcRows)) return false;
+        R.kind[k] = 6;
+      }
       continue;
     }
     if (!c.umma && p->precision == KVAE_PREC_BF16 && k7same && k == 0 && !last && c.g.Cin <= 2 && c.has_bias &&
@@ -709,6 +723,19 @@ int run_plan(kvae_plan* p, bool train, const void* in, int in_dtype, void* out, 
       // computed by the fused ResidualUnit launch of the previous step
     } else if (R.kind[k] == 4) {
       KV_CUDA(launch_conv_ru(R.ru[k], st));
+    } else if (R.kind[k] == 6) {
+      PreparedRun::WaveOutTc& t = R.wave_out_tc[k];
+      t.p.y = out;
+      t.p.y_f32 = (out_dtype == KVAE_F32);
+      static bool attr_set[64] = {false};
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (!attr_set[dev & 63]) {
+        KV_CUDA(cudaFuncSetAttribute(conv_wave_out_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set[dev & 63] = true;
+      }
+      conv_wave_out_tc_kernel<<<std::min(t.p.total_tiles, sm_count()), kWoTcThreads, wave_out_tc_smem(), st>>>(t.tmX, t.p);
+      KV_CUDA(cudaGetLastError());
     } else if (R.kind[k] == 3) {
       WaveOutParams& w = R.wave_out[k];
       w.y = out;
@@ -968,7 +995,10 @@ bool prepare_backward(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R
           if (j != k + 1) { err = "internal: skip connection spans more than one ResidualUnit"; return false; }
           sb.skip = Gf(j);
         }
-      sb.G = Gf(k - 1);
+      // fp32 copy of G_{k-1}: only where something reads it -- the skip-connection add two steps later (k-1 is the
+      // k1 conv of a ResidualUnit), the CUDA-core kernels, or the input-gradient of step 0
+      const bool tc_only = cp.umma && cp.off_dwp >= 0 && steps[k - 1].residual_from < 0;
+      sb.G = tc_only ? nullptr : Gf(k - 1);
       sb.Gb = cp.umma ? Gb(k - 1) : nullptr;
       sb.rows = static_cast<long long>(B) * T_in;
       sb.C = c.g.Cin;

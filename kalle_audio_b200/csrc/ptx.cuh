@@ -175,6 +175,24 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same for fp32 operands read as TF32 (kind::tf32, K = 8 per instruction).
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// round-to-nearest fp32 -> tf32 (the tensor core itself truncates)
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 // Arrives (count 1) on `bar` once every tcgen05.mma issued so far by this thread has retired.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
@@ -234,6 +252,11 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// kind::tf32: tf32 x tf32 -> fp32, both operands K-major (rows of 32 floats = 128 B).
+__host__ __device__ constexpr uint32_t idesc_tf32_f32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
 // Same with both operands MN-major (bits 15 / 16): the contraction dimension is the slow one in shared memory.
 __host__ __device__ constexpr uint32_t idesc_bf16_f32_mn(int M, int N) {
   return idesc_bf16_f32(M, N) | (1u << 15) | (1u << 16);
