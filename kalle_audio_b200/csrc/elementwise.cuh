@@ -132,21 +132,23 @@ constexpr int kPackTR = 16, kPackTC = 32, kPackMaxK = 16;
 __global__ void __launch_bounds__(256)
 fold_pack_kernel(const float* v, const float* scale, int R, int Cc, int K, __nv_bfloat16* out1_bf16, float* out1_f32,
                  __nv_bfloat16* out2_bf16, float* out2_f32) {
-  __shared__ float tile[kPackTR][kPackTC * kPackMaxK + 1];
+  __shared__ float tile[kPackTR][kPackTC * (kPackMaxK + 1)];
   const int r0 = blockIdx.x * kPackTR, c0 = blockIdx.y * kPackTC;
   const int w = kPackTC * K;                 // contiguous floats per row of the tile
+  const int Kp = K | 1;                      // odd per-column stride in shared memory: the transposed reads below
+                                             // walk columns, which would be a K-way bank conflict for even K
   for (int idx = threadIdx.x; idx < kPackTR * w; idx += 256) {
     const int r = idx / w, j = idx % w;      // j = c_local*K + k
     float val = 0.f;
     if (r0 + r < R && c0 + j / K < Cc) val = v[(static_cast<size_t>(r0 + r) * Cc + c0) * K + j] * scale[r0 + r];
-    tile[r][j] = val;
+    tile[r][(j / K) * Kp + j % K] = val;
   }
   __syncthreads();
   // out1: c fastest
   for (int idx = threadIdx.x; idx < K * kPackTR * kPackTC; idx += 256) {
     const int c = idx % kPackTC, r = (idx / kPackTC) % kPackTR, k = idx / (kPackTC * kPackTR);
     if (r0 + r < R && c0 + c < Cc) {
-      const float val = tile[r][c * K + k];
+      const float val = tile[r][c * Kp + k];
       const size_t o = (static_cast<size_t>(k) * R + r0 + r) * Cc + c0 + c;
       if (out1_bf16) out1_bf16[o] = __float2bfloat16(val);
       if (out1_f32) out1_f32[o] = val;
@@ -156,7 +158,7 @@ fold_pack_kernel(const float* v, const float* scale, int R, int Cc, int K, __nv_
   for (int idx = threadIdx.x; idx < K * kPackTR * kPackTC; idx += 256) {
     const int r = idx % kPackTR, c = (idx / kPackTR) % kPackTC, k = idx / (kPackTC * kPackTR);
     if (r0 + r < R && c0 + c < Cc) {
-      const float val = tile[r][c * K + k];
+      const float val = tile[r][c * Kp + k];
       const size_t o = (static_cast<size_t>(k) * Cc + c0 + c) * R + r0 + r;
       if (out2_bf16) out2_bf16[o] = __float2bfloat16(val);
       if (out2_f32) out2_f32[o] = val;

@@ -141,6 +141,9 @@ struct PreparedRun {
     int wg_kind = 0;                // 0 CUDA-core (torch-layout atomics), 1 tensor-core (packed accumulator),
                                     // 2 waveform-edge streaming kernel
     EdgeWgradParams wg_edge;
+    EdgeDgradParams dg_edge;        // dgrad_kind 3: decoder tail (C -> io) data gradient
+    int dg_edge_grid = 0;
+    size_t dg_edge_smem = 0;
     int wg_edge_grid = 0;
     size_t wg_edge_smem = 0;
     bool wg_edge_x_is_thin = false;
@@ -949,6 +952,17 @@ bool prepare_backward(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R
       ep.out_raw_cf = (k == 0) ? 1 : 0;
       ConvTuning2 tune;
       if (!prepare_conv_umma2(gd, Gb(k), B, static_cast<int>(T_out), c.w_umma_d, ep, tune, bw.dg_umma, err)) return false;
+    } else if (k > 0 && edge_wgrad_ok(c.g) && c.g.Cout <= 2) {
+      bw.dgrad_kind = 3;
+      EdgeDgradParams& e = bw.dg_edge;
+      std::memset(&e, 0, sizeof(e));
+      e.gy = Gf(k); e.w = c.w_direct; e.dA = dA;
+      e.B = B; e.T = static_cast<int>(T_out); e.C = c.g.Cin; e.K = c.g.K; e.dil = c.g.dilation; e.pad = c.g.pad;
+      EdgeWgradParams tmp;
+      std::memset(&tmp, 0, sizeof(tmp));
+      tmp.B = B; tmp.T = e.T; tmp.K = e.K; tmp.dil = e.dil; tmp.pad = e.pad;
+      set_edge_grid(tmp, bw.dg_edge_grid, bw.dg_edge_smem);
+      e.rows_per_block = tmp.rows_per_block; e.blocks_per_clip = tmp.blocks_per_clip;
     } else {
       bw.dgrad_kind = 2;
       DirectParams& d = bw.dg_direct;
@@ -1068,7 +1082,11 @@ int run_backward(kvae_plan* p, const void* x, int x_dtype, const void* gy, int g
       ++g_launches;
     }
     if (k == 0 && !gx) break;
-    if (bw.dgrad_kind == 1) {
+    if (bw.dgrad_kind == 3) {
+      if (c.g.Cout == 1) dgrad_edge_kernel<1><<<bw.dg_edge_grid, 256, bw.dg_edge_smem, st>>>(bw.dg_edge);
+      else dgrad_edge_kernel<2><<<bw.dg_edge_grid, 256, bw.dg_edge_smem, st>>>(bw.dg_edge);
+      KV_CUDA(cudaGetLastError());
+    } else if (bw.dgrad_kind == 1) {
       ConvLaunch2& L = bw.dg_umma;
       if (k == 0) { L.p.out_cf = gx; L.p.out_cf_f32 = (gx_dtype == KVAE_F32); }
       KV_CUDA(launch_conv_umma2(L, st));

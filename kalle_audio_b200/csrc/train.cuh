@@ -267,19 +267,32 @@ __global__ void __launch_bounds__(256) wgrad_edge_kernel(const EdgeWgradParams p
     for (int j = 0; j < NT; ++j) acc[k][j] = 0.f;
   float a = 0.f, ib = 0.f;
   if (p.W_a) { a = p.W_a[c]; ib = p.W_inv_b[c]; }
-  // wide row u pairs with thin row t = u - sigma*(k*dil - pad)
+  // wide row u pairs with thin row t = u - sigma*(k*dil - pad); four rows per iteration so that four
+  // independent 512-byte row loads are in flight per warp (one load per iteration was latency-bound)
   if (rl < lanes) {
     const int u_lo = max(0, t0 - halo), u_hi = min(p.T, t1 + halo);
-    for (int u = u_lo + rl; u < u_hi; u += lanes) {
-      float w = __ldcs(p.W + (static_cast<size_t>(b) * p.T + u) * p.C + c);
-      if (p.W_a) w = snake_beta<false>(w, a, ib);
+    const float* Wc = p.W + static_cast<size_t>(b) * p.T * p.C + c;
+    for (int u0 = u_lo + rl; u0 < u_hi; u0 += 4 * lanes) {
+      float w[4];
 #pragma unroll
-      for (int k = 0; k < kEdgeMaxK; ++k) {
-        if (k < p.K) {
-          const int t = u - p.sigma * (k * p.dil - p.pad);
-          if (t >= t0 && t < t1) {
+      for (int q = 0; q < 4; ++q) {
+        const int u = u0 + q * lanes;
+        w[q] = (u < u_hi) ? __ldcs(Wc + static_cast<size_t>(u) * p.C) : 0.f;
+      }
 #pragma unroll
-            for (int j = 0; j < NT; ++j) acc[k][j] = fmaf(w, thin[(t - t0 + halo) * NT + j], acc[k][j]);
+      for (int q = 0; q < 4; ++q) {
+        const int u = u0 + q * lanes;
+        if (u >= u_hi) break;
+        float wv = w[q];
+        if (p.W_a) wv = snake_beta<false>(wv, a, ib);
+#pragma unroll
+        for (int k = 0; k < kEdgeMaxK; ++k) {
+          if (k < p.K) {
+            const int t = u - p.sigma * (k * p.dil - p.pad);
+            if (t >= t0 && t < t1) {
+#pragma unroll
+              for (int j = 0; j < NT; ++j) acc[k][j] = fmaf(wv, thin[(t - t0 + halo) * NT + j], acc[k][j]);
+            }
           }
         }
       }
@@ -300,6 +313,54 @@ __global__ void __launch_bounds__(256) wgrad_edge_kernel(const EdgeWgradParams p
         }
       }
     }
+  }
+}
+
+// ---------------------------------------------------------------- data gradient of the decoder tail
+// Conv1d(C -> NT <= 2, k, stride 1): dA[b, u, c] = sum_{k,j} w[k][c][j] * gy[b, u - (k*dil - pad), j].
+// The wide side is the output here (HBM-bound write of [B, T, C] fp32); thread = channel with its k x NT weights
+// in registers, the thin gradient rows of a block staged in shared memory.  Same grid as wgrad_edge_kernel.
+struct EdgeDgradParams {
+  const float* gy;           // [B, T, NT] fp32 channels-last
+  const float* w;            // [K][C][NT] fp32 (forward CUDA-core packing)
+  float* dA;                 // [B, T, C] fp32
+  int B, T, C, K, dil, pad;
+  int rows_per_block, blocks_per_clip;
+};
+
+template <int NT>
+__global__ void __launch_bounds__(256) dgrad_edge_kernel(const EdgeDgradParams p) {
+  extern __shared__ float thin[];            // [rows_per_block + 2*halo][NT]
+  const int b = blockIdx.x / p.blocks_per_clip;
+  const int t0 = (blockIdx.x % p.blocks_per_clip) * p.rows_per_block;
+  const int t1 = min(t0 + p.rows_per_block, p.T);
+  const int halo = max(p.pad, (p.K - 1) * p.dil - p.pad);
+  const int nthin = (t1 - t0) + 2 * halo;
+  for (int i = threadIdx.x; i < nthin * NT; i += 256) {
+    const int t = t0 - halo + i / NT;
+    thin[i] = (t >= 0 && t < p.T) ? p.gy[(static_cast<size_t>(b) * p.T + t) * NT + i % NT] : 0.f;
+  }
+  __syncthreads();
+  const int lanes = 256 / p.C;
+  const int c = threadIdx.x % p.C, rl = threadIdx.x / p.C;
+  if (rl >= lanes) return;
+  float w[kEdgeMaxK][NT];
+#pragma unroll
+  for (int k = 0; k < kEdgeMaxK; ++k)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) w[k][j] = (k < p.K) ? __ldg(p.w + (static_cast<size_t>(k) * p.C + c) * NT + j) : 0.f;
+  float* out = p.dA + static_cast<size_t>(b) * p.T * p.C + c;
+  for (int u = t0 + rl; u < t1; u += lanes) {
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < kEdgeMaxK; ++k) {
+      if (k < p.K) {
+        const int r = u - (k * p.dil - p.pad) - t0 + halo;     // staged thin row (zero outside the clip)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) v = fmaf(w[k][j], thin[r * NT + j], v);
+      }
+    }
+    __stcs(out + static_cast<size_t>(u) * p.C, v);
   }
 }
 
