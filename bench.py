@@ -264,6 +264,19 @@ def run_cuda(args):
         tc_ms, tc_fl = sum(m for m, _ in tc), sum(f for _, f in tc)
         other_ms = sum(ms for ms, _, on_tc in prof if not on_tc)
         achieved = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
+        # the single kernel that dominates the step: conv_ru_kernel (fused ResidualUnit of the 128-channel stages).
+        # It is HBM-bound by design (1536 B per output row against 2*128*128*8 FLOPs), so its roofline is HBM.
+        ru = [(prof[i][0], prof[i][1]) for i in range(len(prof) - 1)
+              if prof[i + 1][0] < 0.01 and abs(prof[i][1] / max(prof[i + 1][1], 1.0) - 7.0) < 1e-6]
+        ru_ms = sum(m for m, _ in ru)
+        ru_rows = sum(f / (2.0 * 128 * 128 * 7) for _, f in ru)
+        ru_bytes = ru_rows * 1536.0                       # bf16 operand in + fp32 skip in + fp32 stream out + bf16 operand out
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "conv_ru_traffic.json")
+        if os.path.exists(tpath) and ru:
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic = tj["dram_bytes"] / tj["rows"] * (ru_rows / len(ru))
         step_fl = enc_r.flops(B, L) + dec_r.flops(B, CLIP_FRAMES)
         ms_per_step = total_ms / args.steps
         value = world * audio_s_per_step * args.steps / (total_ms * 1e-3)
@@ -285,6 +298,14 @@ def run_cuda(args):
                          "other_kernels_ms_per_step": other_ms,
                          "whole_step_tflops": step_fl / (ms_per_step * 1e-3) / 1e12,
                          "whole_step_frac": step_fl / (ms_per_step * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]},
+            "roofline_dominant_kernel": {
+                "kernel": "conv_ru_kernel (one launch = one ResidualUnit of a 128-channel stage)", "bound": "hbm",
+                "achieved": ru_bytes / (ru_ms * 1e-3) / 1e9 if ru_ms > 0 else 0.0, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": (ru_bytes / (ru_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if ru_ms > 0 else 0.0,
+                "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, scaled by rows)",
+                "launches_per_step": len(ru), "kernel_ms_per_step": ru_ms,
+                "algorithmic_bytes_per_launch": ru_bytes / len(ru) if ru else 0.0,
+                "share_of_step": ru_ms / ms_per_step, "peak_source": peaks["source"] + " (copy bandwidth)"},
         }
         if world == 1 and not args.no_cpu_baseline:
             frames = 54
