@@ -11,6 +11,7 @@
 //                         bf16 operand of the first ResidualUnit, both channels-last.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 #include "conv_umma.cuh"    // snake_beta
@@ -196,21 +197,30 @@ struct WaveOutTcParams {
   int tiles_per_clip, total_tiles;
 };
 
+// kF16 = true: the residual stream is fp16 in HBM (inference plans).  The tile is then two 64-channel chunks of
+// 128-byte rows, SnakeBeta is applied in fp32 and written back as fp16, and the GEMM is kind::f16 (fp16 x fp16 ->
+// fp32; 11 significant bits like tf32) with K = 16 per instruction.
 constexpr int kWoTcRows = 128;                       // staged rows per tile
 constexpr int kWoTcTile = kWoTcRows - 6;             // outputs per tile (k7: 3 halo rows each side)
-constexpr int kWoTcChunk = kWoTcRows * 128;          // bytes of one 32-channel chunk
-constexpr int kWoTcSlab = 4 * kWoTcChunk;            // 65536 B
+constexpr int kWoTcChunk = kWoTcRows * 128;          // bytes of one chunk (32 fp32 or 64 fp16 channels)
 constexpr int kWoTcSlots = 3;
-constexpr int kWoTcWBytes = 4 * 16 * 128;            // 8192 B
 constexpr int kWoTcPStride = 17;                     // floats per P row in shared memory (conflict-free)
 constexpr int kWoTcThreads = 512;
+template <bool kF16> struct WoTc {
+  static constexpr int kChunks = kF16 ? 2 : 4;
+  static constexpr int kSlab = kChunks * kWoTcChunk;             // 32768 / 65536 B
+  static constexpr int kWBytes = kChunks * 16 * 128;             // weights [chunk][16 rows x 128 B]
+};
 
+template <bool kF16>
 inline size_t wave_out_tc_smem() {
-  return 1024 + 1024 + kWoTcSlots * kWoTcSlab + kWoTcWBytes + 1024 + 2 * kWoTcRows * kWoTcPStride * 4;
+  return 1024 + 1024 + kWoTcSlots * WoTc<kF16>::kSlab + WoTc<kF16>::kWBytes + 1024 + 2 * kWoTcRows * kWoTcPStride * 4;
 }
 
+template <bool kF16>
 __global__ void __launch_bounds__(kWoTcThreads, 1)
 conv_wave_out_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ WaveOutTcParams p) {
+  constexpr int kWoTcSlab = WoTc<kF16>::kSlab, kWoTcWBytes = WoTc<kF16>::kWBytes, kChunks = WoTc<kF16>::kChunks;
   extern __shared__ uint8_t sm_wotc_raw[];
   const uint32_t raw_addr = ptx::smem_u32(sm_wotc_raw);
   uint8_t* smem = sm_wotc_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -237,15 +247,21 @@ conv_wave_out_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     ptx::tmem_alloc(tmem_slot, 32);
     ptx::tmem_relinquish();
   }
-  // weights -> K-major SWIZZLE_128B tiles [chunk][16 rows n = k*COUT + co (zero-padded)][32 floats]
-  for (int i = threadIdx.x; i < 4 * 16 * 32; i += kWoTcThreads) {
-    const int ci = i & 31, n = (i >> 5) & 15, c = i >> 9;
+  // weights -> K-major SWIZZLE_128B tiles [chunk][16 rows n = k*COUT + co (zero-padded)][32 floats | 64 halves]
+  for (int i = threadIdx.x; i < 16 * 128; i += kWoTcThreads) {
+    const int ci = i & 127, n = i >> 7;               // input channel, GEMM column
     float v = 0.f;
     if (n < 7 * p.COUT) {
       const int k = n / p.COUT, co = n % p.COUT;
-      v = ptx::round_tf32(__ldg(p.w + (static_cast<size_t>(k) * 128 + c * 32 + ci) * p.COUT + co));
+      v = __ldg(p.w + (static_cast<size_t>(k) * 128 + ci) * p.COUT + co);
     }
-    *reinterpret_cast<float*>(wsm + c * 2048 + n * 128 + (((ci >> 2) ^ (n & 7)) << 4) + (ci & 3) * 4) = v;
+    if (kF16) {
+      const int c = ci >> 6, cc = ci & 63;
+      *reinterpret_cast<__half*>(wsm + c * 2048 + n * 128 + (((cc >> 3) ^ (n & 7)) << 4) + (cc & 7) * 2) = __float2half_rn(v);
+    } else {
+      const int c = ci >> 5, cc = ci & 31;
+      *reinterpret_cast<float*>(wsm + c * 2048 + n * 128 + (((cc >> 2) ^ (n & 7)) << 4) + (cc & 3) * 4) = ptx::round_tf32(v);
+    }
   }
   if (threadIdx.x < 128) {
     tab[threadIdx.x] = __ldg(p.pro_a + threadIdx.x);
@@ -266,14 +282,14 @@ conv_wave_out_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         const int t0 = (tile % p.tiles_per_clip) * kWoTcTile;
         ptx::mbar_wait(&empty[s], ph ^ 1u);
         ptx::mbar_expect_tx(&full[s], kWoTcSlab);
-        for (int c = 0; c < 4; ++c)
-          ptx::tma_load_4d(ring + s * kWoTcSlab + c * kWoTcChunk, &tmX, &full[s], c * 32, 0, t0 - 3, b);
+        for (int c = 0; c < kChunks; ++c)
+          ptx::tma_load_4d(ring + s * kWoTcSlab + c * kWoTcChunk, &tmX, &full[s], c * (kF16 ? 64 : 32), 0, t0 - 3, b);
         if (++s == kWoTcSlots) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     if (ptx::elect_one()) {
-      const uint32_t idesc = ptx::idesc_tf32_f32(128, 16);
+      const uint32_t idesc = kF16 ? ptx::idesc_f16_f32(128, 16) : ptx::idesc_tf32_f32(128, 16);
       const uint64_t desc_hi = (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
       const uint32_t ring_lo = ((ptx::smem_u32(ring) & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t w_lo = ((ptx::smem_u32(wsm) & 0x3FFFFu) >> 4) | (1u << 16);
@@ -285,12 +301,14 @@ conv_wave_out_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         ptx::tc_fence_after();
         const uint32_t d = tmem_base + a * 16;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < kChunks; ++c) {
           const uint32_t al = ring_lo + ((s * kWoTcSlab + c * kWoTcChunk) >> 4);
           const uint32_t bl = w_lo + ((c * 2048) >> 4);
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)                         // 8 tf32 = 32 B per K-step
-            ptx::umma_tf32(d, desc_hi | (al + 2 * ks), desc_hi | (bl + 2 * ks), idesc, (c | ks) ? 1u : 0u);
+          for (int ks = 0; ks < 4; ++ks) {                       // 8 tf32 / 16 fp16 = 32 B per K-step
+            if (kF16) ptx::umma_f16(d, desc_hi | (al + 2 * ks), desc_hi | (bl + 2 * ks), idesc, (c | ks) ? 1u : 0u);
+            else ptx::umma_tf32(d, desc_hi | (al + 2 * ks), desc_hi | (bl + 2 * ks), idesc, (c | ks) ? 1u : 0u);
+          }
         }
         ptx::umma_commit(&empty[s]);
         ptx::umma_commit(&acc_full[a]);
@@ -307,17 +325,31 @@ conv_wave_out_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       ptx::mbar_wait(&full[s], ph);
       float4* slab = reinterpret_cast<float4*>(ring + s * kWoTcSlab);
 #pragma unroll 4
-      for (int u = tid; u < 4 * kWoTcRows * 8; u += 256) {
+      for (int u = tid; u < kChunks * kWoTcRows * 8; u += 256) {     // 16-byte units
         const int r = (u >> 3) & (kWoTcRows - 1), c = u >> 10;
-        const int ch = c * 32 + (((u & 7) ^ (r & 7)) << 2);
-        const float4 a4 = *reinterpret_cast<const float4*>(tab + ch);
-        const float4 b4 = *reinterpret_cast<const float4*>(tab + 128 + ch);
-        float4 v = slab[u];
-        v.x = ptx::round_tf32(snake_beta<true>(v.x, a4.x, b4.x));
-        v.y = ptx::round_tf32(snake_beta<true>(v.y, a4.y, b4.y));
-        v.z = ptx::round_tf32(snake_beta<true>(v.z, a4.z, b4.z));
-        v.w = ptx::round_tf32(snake_beta<true>(v.w, a4.w, b4.w));
-        slab[u] = v;
+        if (kF16) {
+          const int ch = c * 64 + (((u & 7) ^ (r & 7)) << 3);          // 8 fp16 channels per unit
+          float4 q = slab[u];
+          __half2* h2 = reinterpret_cast<__half2*>(&q);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float2 f = __half22float2(h2[e]);
+            f.x = snake_beta<true>(f.x, tab[ch + 2 * e], tab[128 + ch + 2 * e]);
+            f.y = snake_beta<true>(f.y, tab[ch + 2 * e + 1], tab[128 + ch + 2 * e + 1]);
+            h2[e] = __floats2half2_rn(f.x, f.y);
+          }
+          slab[u] = q;
+        } else {
+          const int ch = c * 32 + (((u & 7) ^ (r & 7)) << 2);
+          const float4 a4 = *reinterpret_cast<const float4*>(tab + ch);
+          const float4 b4 = *reinterpret_cast<const float4*>(tab + 128 + ch);
+          float4 v = slab[u];
+          v.x = ptx::round_tf32(snake_beta<true>(v.x, a4.x, b4.x));
+          v.y = ptx::round_tf32(snake_beta<true>(v.y, a4.y, b4.y));
+          v.z = ptx::round_tf32(snake_beta<true>(v.z, a4.z, b4.z));
+          v.w = ptx::round_tf32(snake_beta<true>(v.w, a4.w, b4.w));
+          slab[u] = v;
+        }
       }
       ptx::fence_proxy_async();
       __syncwarp();
@@ -367,7 +399,8 @@ struct WaveInParams {
   int x_f32;
   const float* w;         // [7][CIN][Cout] fp32
   const float* bias;      // [Cout]
-  float* out_raw;         // [B, T, Cout] fp32 or nullptr
+  void* out_raw;          // [B, T, Cout] fp32 (or fp16 when raw_f16) or nullptr
+  int raw_f16;
   __nv_bfloat16* out_act; // [B, T, Cout] bf16 or nullptr
   const float* snake_a;   // epilogue SnakeBeta of the first ResidualUnit (or nullptr: plain cast)
   const float* snake_inv_b;
@@ -418,7 +451,15 @@ __global__ void __launch_bounds__(128) conv_wave_in_kernel(const WaveInParams p)
         v2 = fmaf(xv, w[k][c][2], v2); v3 = fmaf(xv, w[k][c][3], v3);
       }
     const size_t o = (static_cast<size_t>(b) * p.T + t) * p.Cout + co;
-    if (p.out_raw) *reinterpret_cast<float4*>(p.out_raw + o) = make_float4(v0, v1, v2, v3);
+    if (p.out_raw) {
+      if (p.raw_f16) {
+        __half2 h0 = __floats2half2_rn(v0, v1), h1 = __floats2half2_rn(v2, v3);
+        *reinterpret_cast<uint2*>(static_cast<__half*>(p.out_raw) + o) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      } else {
+        *reinterpret_cast<float4*>(static_cast<float*>(p.out_raw) + o) = make_float4(v0, v1, v2, v3);
+      }
+    }
     if (p.out_act) {
       if (p.snake_a) {
         v0 = snake_beta<true>(v0, sa.x, sib.x); v1 = snake_beta<true>(v1, sa.y, sib.y);

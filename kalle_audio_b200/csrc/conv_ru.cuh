@@ -18,6 +18,7 @@
 // chunks of the tile), h half 32 KB, EPI2 staging 8 x <=8 KB.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 #include "conv_umma2.cuh"
@@ -39,6 +40,7 @@ struct RuParams {
   int act_out;              // 1: bf16 operand out via tmO
   const float* sn_a;        // SnakeBeta folded into the operand output (nullptr: plain cast)
   const float* sn_inv_b;
+  int raw_f16;              // 1: residual stream (x in, x' out) is fp16 in HBM, 0: fp32
   int dbg;                  // ablation switches for tools/umma_probe (KVAE_RU_DBG); 0 in production
 };
 
@@ -49,10 +51,13 @@ constexpr int kRuRawBlk = 16 * 128;        // 16 rows x 32 fp32, SWIZZLE_128B
 constexpr int kRuActBlk = 16 * 64;         // 16 rows x 32 bf16, SWIZZLE_64B
 constexpr int kRuThreads = 640;
 
-__host__ __device__ inline int ru_stage_bytes_per_warp(int act_out) { return 3 * kRuRawBlk + (act_out ? 2 * kRuActBlk : 0); }
+__host__ __device__ inline int ru_raw_blk(int raw_f16) { return raw_f16 ? kRuActBlk : kRuRawBlk; }
+__host__ __device__ inline int ru_stage_bytes_per_warp(int act_out, int raw_f16) {
+  return 3 * ru_raw_blk(raw_f16) + (act_out ? 2 * kRuActBlk : 0);
+}
 __host__ __device__ inline size_t ru_smem_bytes(const RuParams& p) {
   return 1024 + 1024 + static_cast<size_t>(p.SA) * p.nbox * p.RB * 128 + static_cast<size_t>(p.SB) * kRuC * 128 +
-         kRuHBytes + 8 * ru_stage_bytes_per_warp(p.act_out);
+         kRuHBytes + 8 * ru_stage_bytes_per_warp(p.act_out, p.raw_f16);
 }
 
 __global__ void __launch_bounds__(kRuThreads, 1)
@@ -271,8 +276,9 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float bias = __ldg(p.bias1 + c);
     float sa = 1.f, sib = 0.f;
     if (p.sn_a) { sa = __ldg(p.sn_a + c); sib = __ldg(p.sn_inv_b + c); }
-    uint8_t* raw_ring = stage_base + e * ru_stage_bytes_per_warp(p.act_out);
-    uint8_t* act_ring = raw_ring + 3 * kRuRawBlk;
+    const int rawblk = ru_raw_blk(p.raw_f16);
+    uint8_t* raw_ring = stage_base + e * ru_stage_bytes_per_warp(p.act_out, p.raw_f16);
+    uint8_t* act_ring = raw_ring + 3 * rawblk;
     uint64_t* my_res_full = res_full + e * 3;
     const uint32_t rcol = (lane & 3) * 4, rchunk = lane >> 2;
     const uint32_t acol = (lane & 7) * 2, achunk = lane >> 3;
@@ -281,7 +287,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // items of this warp inside a tile: 16-row blocks sub, sub+2, ..., 14+sub
     if (lane == 0 && static_cast<int>(blockIdx.x) < p.total_tiles && !(p.dbg & 1)) {
       const int b = blockIdx.x / p.q_tiles, q0 = (blockIdx.x % p.q_tiles) * 256;
-      ptx::mbar_expect_tx(&my_res_full[0], kRuRawBlk);
+      ptx::mbar_expect_tx(&my_res_full[0], rawblk);
       ptx::tma_load_4d(raw_ring, &tmX, &my_res_full[0], cbase, 0, q0 + sub * 16, b);
     }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -299,8 +305,8 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (ni >= 16) { nt = tile + gridDim.x; ni = sub; }
           if (nt < p.total_tiles && !(p.dbg & 1)) {
             const int sn = (jr + 1) % 3;
-            ptx::mbar_expect_tx(&my_res_full[sn], kRuRawBlk);
-            ptx::tma_load_4d(raw_ring + sn * kRuRawBlk, &tmX, &my_res_full[sn], cbase, 0,
+            ptx::mbar_expect_tx(&my_res_full[sn], rawblk);
+            ptx::tma_load_4d(raw_ring + sn * rawblk, &tmX, &my_res_full[sn], cbase, 0,
                              (nt % p.q_tiles) * 256 + ni * 16, nt / p.q_tiles);
           }
         }
@@ -310,18 +316,31 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         ptx::tmem_ld_32x16(d2 + (static_cast<uint32_t>(quad * 32) << 16) + item * 16, r);
         ptx::tmem_ld_wait();
-        uint8_t* const rblk = raw_ring + jr * kRuRawBlk;
+        uint8_t* const rblk = raw_ring + jr * rawblk;
         uint8_t* const ablk = act_ring + ja * kRuActBlk;
-        uint8_t* rbase[8];
-#pragma unroll
-        for (int x = 0; x < 8; ++x) rbase[x] = rblk + ((rchunk ^ x) << 4) + rcol;
         float v[16];
+        if (p.raw_f16) {     // fp16 stream block: 16 rows x 64 B, SWIZZLE_64B (same shape as the operand block)
+          uint8_t* hbase[4];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          v[j] = __uint_as_float(r[j]) + bias + *reinterpret_cast<const float*>(rbase[j & 7] + j * 128);
-        if (p.raw_out) {
+          for (int x = 0; x < 4; ++x) hbase[x] = rblk + ((achunk ^ x) << 4) + acol;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) *reinterpret_cast<float*>(rbase[j & 7] + j * 128) = v[j];
+          for (int j = 0; j < 16; ++j)
+            v[j] = __uint_as_float(r[j]) + bias + __half2float(*reinterpret_cast<const __half*>(hbase[(j >> 1) & 3] + j * 64));
+          if (p.raw_out) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) *reinterpret_cast<__half*>(hbase[(j >> 1) & 3] + j * 64) = __float2half_rn(v[j]);
+          }
+        } else {
+          uint8_t* rbase[8];
+#pragma unroll
+          for (int x = 0; x < 8; ++x) rbase[x] = rblk + ((rchunk ^ x) << 4) + rcol;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            v[j] = __uint_as_float(r[j]) + bias + *reinterpret_cast<const float*>(rbase[j & 7] + j * 128);
+          if (p.raw_out) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) *reinterpret_cast<float*>(rbase[j & 7] + j * 128) = v[j];
+          }
         }
         if (p.act_out) {
           if (p.sn_a && !(p.dbg & 8)) {

@@ -18,6 +18,7 @@
 // warps 4-11 epilogue.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 #include "conv_umma.cuh"
@@ -44,7 +45,10 @@ struct ConvParams2 {
   // epilogue
   const float* bias;
   const float* residual;   // fp32 channels-last [B, T_out, Cout] or nullptr
-  int raw_mode;            // 0 none, 1 fp32 channels-last via TMA (tmR), 2 channels-first direct store
+  int raw_mode;            // 0 none, 1 channels-last stream via TMA (tmR), 2 channels-first direct store
+  int raw_f16;             // 1: the residual stream (raw_mode 1 output and the skip-connection input) is fp16 in HBM
+                           //    (fp32 in registers and TMEM); 0: fp32.  Inference plans use fp16: it halves the
+                           //    stream traffic of the HBM-bound 128-channel stages for +4e-5 of the 1e-3 budget
   void* out_cf;            // raw_mode 2: [B, Cout, T_out]
   int out_cf_f32;
   int act_mode;            // 0 none, 1 bf16 channels-last via TMA (tmO)
@@ -53,19 +57,20 @@ struct ConvParams2 {
 };
 
 constexpr int kRawBlkBytes = 32 * 128;   // 32 rows x 32 fp32, SWIZZLE_128B
-constexpr int kActBlkBytes = 32 * 64;    // 32 rows x 32 bf16, SWIZZLE_64B
+constexpr int kActBlkBytes = 32 * 64;    // 32 rows x 32 bf16 (or fp16 stream), SWIZZLE_64B
+__host__ __device__ inline int conv_umma2_raw_blk(int raw_f16) { return raw_f16 ? kActBlkBytes : kRawBlkBytes; }
 // per-epilogue-warp staging: a ring of fp32 blocks (3 deep when the skip connection is prefetched into
 // it, else 2) and two bf16 blocks; only what a layer needs is carved out
 __host__ __device__ inline int conv_umma2_raw_slots(int raw_mode, bool residual) {
   return (raw_mode == 1 || residual) ? (residual ? 3 : 2) : 0;
 }
-__host__ __device__ inline int conv_umma2_stage_bytes_per_warp(int raw_mode, int act_mode, bool residual) {
-  return conv_umma2_raw_slots(raw_mode, residual) * kRawBlkBytes + (act_mode == 1 ? 2 * kActBlkBytes : 0);
+__host__ __device__ inline int conv_umma2_stage_bytes_per_warp(int raw_mode, int act_mode, bool residual, int raw_f16) {
+  return conv_umma2_raw_slots(raw_mode, residual) * conv_umma2_raw_blk(raw_f16) + (act_mode == 1 ? 2 * kActBlkBytes : 0);
 }
 
 __host__ __device__ inline size_t conv_umma2_smem_bytes(const ConvParams2& p) {
   return 1024 + 1024 + static_cast<size_t>(p.SA) * p.nbox * p.RB * 128 + static_cast<size_t>(p.SB) * p.NT * 128 +
-         8 * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, p.residual != nullptr);
+         8 * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, p.residual != nullptr, p.raw_f16);
 }
 
 __global__ void __launch_bounds__(384, 1)
@@ -230,8 +235,9 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int T_out = p.Tq_out * p.P_out;
     const bool has_res = p.residual != nullptr;
     const int R = conv_umma2_raw_slots(p.raw_mode, has_res);
-    uint8_t* raw_ring = stage_base + e * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, has_res);
-    uint8_t* act_ring = raw_ring + R * kRawBlkBytes;
+    const int rawblk = conv_umma2_raw_blk(p.raw_f16);
+    uint8_t* raw_ring = stage_base + e * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, has_res, p.raw_f16);
+    uint8_t* act_ring = raw_ring + R * rawblk;
     uint64_t* my_res_full = res_full + e * 3;
     // An item is one 32-row x 32-channel output block.  swap = 0: TMEM lane = time row, so a thread owns one
     // row x 32 channels (vector shared-memory accesses).  swap = 1: TMEM lane = channel, so a thread owns one
@@ -254,7 +260,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (has_res && lane == 0 && static_cast<int>(blockIdx.x) < p.total_tiles && g < ipt) {
       int cb, ph, r0, bb;
       coords(blockIdx.x, g, cb, ph, r0, bb);
-      ptx::mbar_expect_tx(&my_res_full[0], kRawBlkBytes);
+      ptx::mbar_expect_tx(&my_res_full[0], rawblk);
       ptx::tma_load_4d(raw_ring, &tmX, &my_res_full[0], cb, ph, r0, bb);
     }
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -293,8 +299,8 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               int cb, ph, rr, bb;
               coords(nt, ni, cb, ph, rr, bb);
               const int sn = (jr + 1) % 3;
-              ptx::mbar_expect_tx(&my_res_full[sn], kRawBlkBytes);
-              ptx::tma_load_4d(raw_ring + sn * kRawBlkBytes, &tmX, &my_res_full[sn], cb, ph, rr, bb);
+              ptx::mbar_expect_tx(&my_res_full[sn], rawblk);
+              ptx::tma_load_4d(raw_ring + sn * rawblk, &tmX, &my_res_full[sn], cb, ph, rr, bb);
             }
           }
           ptx::mbar_wait(&my_res_full[jr], (res_ph >> jr) & 1u);
@@ -307,7 +313,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        uint8_t* const rblk = raw_ring + jr * kRawBlkBytes;
+        uint8_t* const rblk = raw_ring + jr * rawblk;
         uint8_t* const ablk = act_ring + ja * kActBlkBytes;
         if (p.swap) {
           // ---- thread = channel (cbase + lane), v[j] = row r0 + j
@@ -319,9 +325,17 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           uint8_t* rbase[8];     // the 8 distinct swizzle phases of a SWIZZLE_128B block
 #pragma unroll
           for (int c = 0; c < 8; ++c) rbase[c] = rblk + ((rchunk ^ c) << 4) + rcol;
-          if (has_res) {
+          uint8_t* hbase[4];     // fp16 stream block: same shape and swizzle as the bf16 operand block
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += *reinterpret_cast<const float*>(rbase[j & 7] + j * 128);
+          for (int c = 0; c < 4; ++c) hbase[c] = rblk + ((achunk ^ c) << 4) + acol;
+          if (has_res) {
+            if (p.raw_f16) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += __half2float(*reinterpret_cast<const __half*>(hbase[(j >> 1) & 3] + j * 64));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += *reinterpret_cast<const float*>(rbase[j & 7] + j * 128);
+            }
           }
           if (p.raw_mode == 2) {
             const int c = cbase + lane;
@@ -336,8 +350,13 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
           }
           if (p.raw_mode == 1) {
+            if (p.raw_f16) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) *reinterpret_cast<float*>(rbase[j & 7] + j * 128) = v[j];
+              for (int j = 0; j < 32; ++j) *reinterpret_cast<__half*>(hbase[(j >> 1) & 3] + j * 64) = __float2half_rn(v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) *reinterpret_cast<float*>(rbase[j & 7] + j * 128) = v[j];
+            }
           }
           if (p.act_mode == 1) {
             if (p.snake_a) {   // hoisted: a per-element test would put a branch between the 32 independent chains
@@ -361,11 +380,25 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         uint8_t* rt = rblk + lane * 128;
+        uint8_t* rt16 = rblk + lane * 64;                 // fp16 stream block row
         if (has_res) {
+          if (p.raw_f16) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 x = *reinterpret_cast<const float4*>(rt + ((j ^ (lane & 7)) << 4));
-            v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+            for (int j = 0; j < 4; ++j) {
+              const uint4 q = *reinterpret_cast<const uint4*>(rt16 + ((j ^ ((lane >> 1) & 3)) << 4));
+              const __half2* h2 = reinterpret_cast<const __half2*>(&q);
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                const float2 f = __half22float2(h2[q4]);
+                v[8 * j + 2 * q4] += f.x; v[8 * j + 2 * q4 + 1] += f.y;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 x = *reinterpret_cast<const float4*>(rt + ((j ^ (lane & 7)) << 4));
+              v[4 * j] += x.x; v[4 * j + 1] += x.y; v[4 * j + 2] += x.z; v[4 * j + 3] += x.w;
+            }
           }
         }
         if (p.raw_mode == 2) {
@@ -386,10 +419,23 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         if (p.raw_mode == 1) {
+          if (p.raw_f16) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(rt + ((j ^ (lane & 7)) << 4)) =
-                make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 4; ++j) {
+              uint32_t w[4];
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4) {
+                __half2 h = __floats2half2_rn(v[8 * j + 2 * q4], v[8 * j + 2 * q4 + 1]);
+                w[q4] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(rt16 + ((j ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(rt + ((j ^ (lane & 7)) << 4)) =
+                  make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
         }
         if (p.act_mode == 1) {
           if (p.snake_a) {
@@ -420,7 +466,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           ptx::fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            if (p.raw_mode == 1) ptx::tma_store_4d(&tmR, raw_ring + jr * kRawBlkBytes, cbase, phi, r0, b);
+            if (p.raw_mode == 1) ptx::tma_store_4d(&tmR, raw_ring + jr * rawblk, cbase, phi, r0, b);
             if (p.act_mode == 1) ptx::tma_store_4d(&tmO, act_ring + ja * kActBlkBytes, cbase, phi, r0, b);
             ptx::bulk_commit();   // (an empty group when only the skip block was consumed keeps the count uniform)
           }

@@ -179,8 +179,10 @@ inline bool make_w_tmap(CUtensorMap* m, const void* w, int nslab, int Cout, int 
 
 // Output tensor [B, T, C] viewed as [B, T/P, P, C] for TMA transfers of 32-row x 32-channel blocks:
 // fp32 blocks are 128 B wide (SWIZZLE_128B), bf16 blocks 64 B (SWIZZLE_64B).
-inline bool make_out_tmap(CUtensorMap* m, const void* y, int B, int T, int C, int P, bool f32, std::string& err,
+// dtype: 1 fp32, 0 bf16, 2 fp16 (2-byte types differ only in the tensor map's element type)
+inline bool make_out_tmap(CUtensorMap* m, const void* y, int B, int T, int C, int P, int dtype, std::string& err,
                           int box_rows = 32) {
+  const bool f32 = (dtype == 1);
   auto enc = tmap_encoder();
   if (!enc) { err = "cuTensorMapEncodeTiled unavailable"; return false; }
   if (T % P) { err = "output length not divisible by stride"; return false; }
@@ -189,7 +191,8 @@ inline bool make_out_tmap(CUtensorMap* m, const void* y, int B, int T, int C, in
   cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)P * C * es, (cuuint64_t)T * C * es};
   cuuint32_t box[4] = {32, 1, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+  CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                          : (dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16), 4,
                    const_cast<void*>(y), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    f32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -208,6 +211,7 @@ struct ConvEpilogue {
   __nv_bfloat16* out_act = nullptr;
   const float* snake_a = nullptr;
   const float* snake_inv_b = nullptr;
+  int stream_f16 = 0;     // persistent kernel only: residual and channels-last out_raw are fp16 instead of fp32
 };
 
 struct ConvTuning {
@@ -323,8 +327,8 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
                                const __nv_bfloat16* wpacked, const ConvEpilogue& ep, const ConvTuning2& tune,
                                ConvLaunch2& L, std::string& err) {
   if (!umma_supported(g)) { err = "channel counts not multiples of 64"; return false; }
-  if (ep.residual && !ep.residual_f32) { err = "residual must be fp32"; return false; }
-  if (ep.out_raw && !ep.out_raw_cf && !ep.out_raw_f32) { err = "channels-last raw output must be fp32"; return false; }
+  if (ep.residual && !ep.residual_f32 && !ep.stream_f16) { err = "residual must be fp32 (or the fp16 stream)"; return false; }
+  if (ep.out_raw && !ep.out_raw_cf && !ep.out_raw_f32 && !ep.stream_f16) { err = "channels-last raw output must be fp32 (or the fp16 stream)"; return false; }
   TapPlan tp;
   if (!build_taps(g, false, tp, err)) return false;
   const int T_out = g.out_len(T_in);
@@ -338,8 +342,10 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
   p.n_chunks = g.Cin / 64;
   p.raw_mode = ep.out_raw ? (ep.out_raw_cf ? 2 : 1) : 0;
   p.act_mode = ep.out_act ? 1 : 0;
-  const size_t stage =
-      8 * static_cast<size_t>(conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, ep.residual != nullptr));
+  p.raw_f16 = ep.stream_f16 ? 1 : 0;
+  const int sdt = ep.stream_f16 ? 2 : 1;     // element type of the stream tensor maps
+  const size_t stage = 8 * static_cast<size_t>(conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode,
+                                                                                ep.residual != nullptr, p.raw_f16));
   const size_t budget = 227 * 1024 - 2048 - stage;
   // candidate tilings, best first: double-buffered accumulators when they fit the 512 TMEM columns
   struct Cand { int MT, NT, acc; };
@@ -411,11 +417,11 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
   p.snake_inv_b = ep.snake_inv_b;
   if (!make_act_tmap(&L.tmA, x, B, T_in, g.Cin, tp.P_in, p.RB, err)) return false;
   if (!make_w_tmap(&L.tmW, wpacked, g.K, g.Cout, g.Cin, p.NT, err)) return false;
-  if (p.raw_mode == 1) { if (!make_out_tmap(&L.tmR, ep.out_raw, B, T_out, g.Cout, tp.P_out, true, err)) return false; }
+  if (p.raw_mode == 1) { if (!make_out_tmap(&L.tmR, ep.out_raw, B, T_out, g.Cout, tp.P_out, sdt, err)) return false; }
   else L.tmR = L.tmA;
   if (p.act_mode == 1) { if (!make_out_tmap(&L.tmO, ep.out_act, B, T_out, g.Cout, tp.P_out, false, err)) return false; }
   else L.tmO = L.tmA;
-  if (ep.residual) { if (!make_out_tmap(&L.tmX, ep.residual, B, T_out, g.Cout, tp.P_out, true, err)) return false; }
+  if (ep.residual) { if (!make_out_tmap(&L.tmX, ep.residual, B, T_out, g.Cout, tp.P_out, sdt, err)) return false; }
   else L.tmX = L.tmA;
   const int ctas = tune.max_ctas ? tune.max_ctas : sm_count();
   L.grid = std::min(p.total_tiles, ctas);
@@ -447,17 +453,18 @@ struct RuLaunch {
 
 struct RuArgs {
   const __nv_bfloat16* a = nullptr;       // SnakeBeta1(x), bf16 [B, T, 128]
-  const float* x = nullptr;               // residual stream, fp32 [B, T, 128]
+  const void* x = nullptr;                // residual stream, fp32 (or fp16: stream_f16) [B, T, 128]
   const __nv_bfloat16* w7 = nullptr;      // packed [7][128][128]
   const __nv_bfloat16* w1 = nullptr;      // packed [1][128][128]
   const float* bias7 = nullptr;
   const float* s2_a = nullptr;
   const float* s2_inv_b = nullptr;
   const float* bias1 = nullptr;
-  float* out_raw = nullptr;               // fp32 [B, T, 128] or nullptr
+  void* out_raw = nullptr;                // stream out, same type as x, [B, T, 128] or nullptr
   __nv_bfloat16* out_act = nullptr;       // bf16 [B, T, 128] or nullptr
   const float* sn_a = nullptr;
   const float* sn_inv_b = nullptr;
+  int stream_f16 = 0;                     // x and out_raw are fp16 instead of fp32
 };
 
 inline bool ru_supported(int C) { return C == kRuC; }
@@ -478,7 +485,9 @@ inline bool prepare_conv_ru(const RuArgs& a, int B, int T, int dilation, RuLaunc
   p.raw_out = a.out_raw ? 1 : 0;
   p.act_out = a.out_act ? 1 : 0;
   const size_t a_bytes = static_cast<size_t>(p.nbox) * p.RB * 128, b_bytes = kRuC * 128;
-  const size_t budget = 227 * 1024 - 2048 - kRuHBytes - 8 * static_cast<size_t>(ru_stage_bytes_per_warp(p.act_out));
+  p.raw_f16 = a.stream_f16 ? 1 : 0;
+  const int sdt = a.stream_f16 ? 2 : 1;
+  const size_t budget = 227 * 1024 - 2048 - kRuHBytes - 8 * static_cast<size_t>(ru_stage_bytes_per_warp(p.act_out, p.raw_f16));
   p.SA = 2;
   if (2 * a_bytes + 3 * b_bytes > budget) { err = "fused RU does not fit shared memory"; return false; }
   p.SB = static_cast<int>(std::min<size_t>(8, (budget - 2 * a_bytes) / b_bytes));
@@ -490,8 +499,8 @@ inline bool prepare_conv_ru(const RuArgs& a, int B, int T, int dilation, RuLaunc
   if (!make_act_tmap(&L.tmA, a.a, B, T, kRuC, 1, p.RB, err)) return false;
   if (!make_w_tmap(&L.tmW7, a.w7, 7, kRuC, kRuC, kRuC, err)) return false;
   if (!make_w_tmap(&L.tmW1, a.w1, 1, kRuC, kRuC, kRuC, err)) return false;
-  if (!make_out_tmap(&L.tmX, a.x, B, T, kRuC, 1, true, err, 16)) return false;
-  if (a.out_raw) { if (!make_out_tmap(&L.tmR, a.out_raw, B, T, kRuC, 1, true, err, 16)) return false; } else L.tmR = L.tmX;
+  if (!make_out_tmap(&L.tmX, a.x, B, T, kRuC, 1, sdt, err, 16)) return false;
+  if (a.out_raw) { if (!make_out_tmap(&L.tmR, a.out_raw, B, T, kRuC, 1, sdt, err, 16)) return false; } else L.tmR = L.tmX;
   if (a.out_act) { if (!make_out_tmap(&L.tmO, a.out_act, B, T, kRuC, 1, false, err, 16)) return false; } else L.tmO = L.tmX;
   L.grid = std::min(p.total_tiles, sm_count());
   L.smem = ru_smem_bytes(p);

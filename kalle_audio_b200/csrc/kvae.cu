@@ -128,7 +128,8 @@ struct PreparedRun {
   std::vector<WaveInParams> wave_in;
   std::vector<WaveOutParams> wave_out;
   struct WaveOutTc { CUtensorMap tmX; WaveOutTcParams p; };
-  std::vector<WaveOutTc> wave_out_tc;   // kind 6: decoder tail on the tensor cores (TF32)
+  std::vector<WaveOutTc> wave_out_tc;   // kind 6: decoder tail on the tensor cores (TF32, or fp16 with the fp16 stream)
+  bool stream_f16 = false;
   Layout layout;
   // ---- training runs only: the backward pass over the saved activations
   struct Bwd {
@@ -177,6 +178,7 @@ struct kvae_plan {
   long long n_params = 0;     // floats in the flat parameter / gradient buffer
   std::vector<long long> param_sizes;   // segment sizes in module.parameters() order
   bool train_packs = false;
+  bool stream_f16 = false;    // inference plans keep the residual stream in fp16 (bf16 mode, all-tensor-core chains)
   float* scale_scratch = nullptr;   // g/||v|| per dim-0 row of the conv being packed
   float* dwp = nullptr;             // packed weight-gradient accumulators of the tensor-core convs
   size_t dwp_floats = 0;
@@ -293,8 +295,38 @@ void build_encoder(kvae_plan* p) {
   p->ratio = den;
 }
 
+bool k7same_geom(const ConvGeom& g) {
+  return g.kind == kConv && g.K == 7 && g.stride == 1 && g.dilation == 1 && g.pad == 3;
+}
+// the two waveform-edge convs that have kernels of their own in bf16 mode (conv_edge.cuh)
+bool is_wave_out_step(const kvae_plan* p, const std::vector<Step>& steps, int k) {
+  const int n = static_cast<int>(steps.size());
+  const Step& s = steps[k];
+  const ConvLayer& c = p->convs[s.conv];
+  return !c.umma && p->precision == KVAE_PREC_BF16 && k7same_geom(c.g) && k == n - 1 && k > 0 && c.g.Cout <= 2 &&
+         !c.has_bias && c.g.Cin == 128 && s.pre_snake >= 0 && s.residual_from < 0;
+}
+bool is_wave_in_step(const kvae_plan* p, const std::vector<Step>& steps, int k) {
+  const int n = static_cast<int>(steps.size());
+  const Step& s = steps[k];
+  const ConvLayer& c = p->convs[s.conv];
+  return !c.umma && p->precision == KVAE_PREC_BF16 && k7same_geom(c.g) && k == 0 && n > 1 && c.g.Cin <= 2 && c.has_bias &&
+         c.g.Cout % 128 == 0 && s.pre_snake < 0 && s.residual_from < 0;
+}
+bool env_flag(const char* name) {
+  const char* e = getenv(name);
+  return e && e[0] == '1';
+}
+
 void finalize_steps(kvae_plan* p) {
   const int n = static_cast<int>(p->steps.size());
+  // fp16 residual stream: only when every step runs on a kernel that knows about it (tensor-core convs and the
+  // two waveform-edge kernels), i.e. the graded architectures in bf16 mode; anything else keeps fp32
+  p->stream_f16 = p->precision == KVAE_PREC_BF16 && !env_flag("KVAE_STREAM_F32") && !env_flag("KVAE_WAVE_OUT_CC") &&
+                  !env_flag("KVAE_CONV_V1");
+  for (int k = 0; k < n && p->stream_f16; ++k)
+    if (!p->convs[p->steps[k].conv].umma && !is_wave_in_step(p, p->steps, k) && !is_wave_out_step(p, p->steps, k))
+      p->stream_f16 = false;
   for (int k = 0; k < n; ++k) {
     Step& s = p->steps[k];
     const bool last = (k == n - 1);
@@ -375,7 +407,7 @@ bool make_layout(const kvae_plan* p, const std::vector<Step>& steps, bool train,
     if (train) last_use = 1 << 30;   // saved for the backward pass
     if (s.needs_raw && k != n - 1) {
       Tensor& t = L.t[1 + 2 * k];
-      t.bytes = static_cast<size_t>(B) * len * c.g.Cout * 4;
+      t.bytes = static_cast<size_t>(B) * len * c.g.Cout * ((p->stream_f16 && !train) ? 2 : 4);
       t.first = k;
       t.last = last_use;
     }
@@ -440,6 +472,8 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
   R.direct_cfg.assign(n, 0);
   R.direct_smem.assign(n, 0);
   R.kind.assign(n, 1);
+  R.stream_f16 = p->stream_f16 && !train;
+  const int sf16 = R.stream_f16 ? 1 : 0;
   R.wave_in.resize(n);
   R.wave_out.resize(n);
   R.wave_out_tc.resize(n);
@@ -465,14 +499,15 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
       const ConvLayer& c1 = p->convs[s1.conv];
       RuArgs ra;
       ra.a = static_cast<const __nv_bfloat16*>(tptr(2 + 2 * (k - 1)));
-      ra.x = static_cast<const float*>(tptr(1 + 2 * (k - 1)));
+      ra.x = tptr(1 + 2 * (k - 1));
+      ra.stream_f16 = sf16;
       ra.w7 = c.w_umma;
       ra.w1 = c1.w_umma;
       ra.bias7 = c.bias;
       ra.s2_a = p->snakes[s.epi_snake].a;
       ra.s2_inv_b = p->snakes[s.epi_snake].inv_b;
       ra.bias1 = c1.bias;
-      ra.out_raw = s1.needs_raw ? static_cast<float*>(tptr(1 + 2 * (k + 1))) : nullptr;
+      ra.out_raw = s1.needs_raw ? tptr(1 + 2 * (k + 1)) : nullptr;
       ra.out_act = s1.needs_act ? static_cast<__nv_bfloat16*>(tptr(2 + 2 * (k + 1))) : nullptr;
       if (s1.epi_snake >= 0) {
         ra.sn_a = p->snakes[s1.epi_snake].a;
@@ -482,9 +517,7 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
       R.kind[k] = 4;
       continue;
     }
-    const bool k7same = c.g.kind == kConv && c.g.K == 7 && c.g.stride == 1 && c.g.dilation == 1 && c.g.pad == 3;
-    if (!c.umma && p->precision == KVAE_PREC_BF16 && k7same && last && k > 0 && c.g.Cout <= 2 && !c.has_bias &&
-        c.g.Cin == 128 && s.pre_snake >= 0 && !res) {
+    if (is_wave_out_step(p, steps, k)) {
       // decoder tail (conv_edge.cuh)
       WaveOutParams& w = R.wave_out[k];
       w.x = static_cast<const float*>(tptr(1 + 2 * (k - 1)));
@@ -505,19 +538,23 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
         t.p.T = w.T; t.p.B = B; t.p.COUT = c.g.Cout; t.p.tanh_out = w.tanh_out;
         t.p.tiles_per_clip = (w.T + kWoTcTile - 1) / kWoTcTile;
         t.p.total_tiles = t.p.tiles_per_clip * B;
-        if (!make_out_tmap(&t.tmX, w.x, B, w.T, 128, 1, true, err, kWoTcRows)) return false;
+        if (sf16) { if (!make_act_tmap(&t.tmX, w.x, B, w.T, 128, 1, kWoTcRows, err)) return false; }
+        else if (!make_out_tmap(&t.tmX, w.x, B, w.T, 128, 1, 1, err, kWoTcRows)) return false;
         R.kind[k] = 6;
+      } else if (sf16) {
+        err = "internal: fp16 stream needs the tensor-core tail";
+        return false;
       }
       continue;
     }
-    if (!c.umma && p->precision == KVAE_PREC_BF16 && k7same && k == 0 && !last && c.g.Cin <= 2 && c.has_bias &&
-        c.g.Cout % 128 == 0 && s.pre_snake < 0 && !res) {
+    if (is_wave_in_step(p, steps, k)) {
       // encoder head (conv_edge.cuh)
       WaveInParams& w = R.wave_in[k];
       w.x = nullptr;  // patched per call
       w.w = c.w_direct;
       w.bias = c.bias;
-      w.out_raw = static_cast<float*>(raw);
+      w.out_raw = raw;
+      w.raw_f16 = sf16;
       w.out_act = static_cast<__nv_bfloat16*>(act);
       if (s.epi_snake >= 0) {
         w.snake_a = p->snakes[s.epi_snake].a;
@@ -538,9 +575,10 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
       ConvEpilogue ep;
       ep.bias = c.has_bias ? c.bias : nullptr;
       ep.residual = res;
-      ep.residual_f32 = 1;
+      ep.residual_f32 = sf16 ? 0 : 1;
+      ep.stream_f16 = sf16;
       ep.out_raw = raw;            // external output patched at call time when last
-      ep.out_raw_f32 = 1;
+      ep.out_raw_f32 = (sf16 && !last) ? 0 : 1;
       ep.out_raw_cf = last ? 1 : 0;
       if (last) ep.out_raw = reinterpret_cast<void*>(0x1);  // placeholder, patched per call
       ep.out_act = static_cast<__nv_bfloat16*>(act);
@@ -734,10 +772,13 @@ int run_plan(kvae_plan* p, bool train, const void* in, int in_dtype, void* out, 
       int dev = 0;
       cudaGetDevice(&dev);
       if (!attr_set[dev & 63]) {
-        KV_CUDA(cudaFuncSetAttribute(conv_wave_out_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        KV_CUDA(cudaFuncSetAttribute(conv_wave_out_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        KV_CUDA(cudaFuncSetAttribute(conv_wave_out_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         attr_set[dev & 63] = true;
       }
-      conv_wave_out_tc_kernel<<<std::min(t.p.total_tiles, sm_count()), kWoTcThreads, wave_out_tc_smem(), st>>>(t.tmX, t.p);
+      const int grid = std::min(t.p.total_tiles, sm_count());
+      if (R.stream_f16) conv_wave_out_tc_kernel<true><<<grid, kWoTcThreads, wave_out_tc_smem<true>(), st>>>(t.tmX, t.p);
+      else conv_wave_out_tc_kernel<false><<<grid, kWoTcThreads, wave_out_tc_smem<false>(), st>>>(t.tmX, t.p);
       KV_CUDA(cudaGetLastError());
     } else if (R.kind[k] == 3) {
       WaveOutParams& w = R.wave_out[k];

@@ -252,6 +252,10 @@ __host__ __device__ constexpr uint32_t idesc_bf16_f32(int M, int N) {
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
+// kind::f16 with fp16 (not bf16) operands, both K-major.
+__host__ __device__ constexpr uint32_t idesc_f16_f32(int M, int N) {
+  return (1u << 4) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
 // kind::tf32: tf32 x tf32 -> fp32, both operands K-major (rows of 32 floats = 128 B).
 __host__ __device__ constexpr uint32_t idesc_tf32_f32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
