@@ -11,11 +11,15 @@
 //   GEMM2  D2[co2, t] = sum_c W1[co2, c] * h[t, c]                                 (2 halves x 2 x 4 MMAs of 128x128x16)
 //   EPI2   x'[t, c]   = D2[c, t] + bias1[c] + x[t, c]  -> fp32 stream (TMA store); a' = bf16(SnakeBeta_next(x')) (TMA store)
 // TMEM: D1 = columns [0,256), D2 = [256,512).  Warp roles (640 threads): 0 TMA producer, 1 UMMA issuer,
-// 2 TMEM allocator, 4-11 EPI1, 12-19 EPI2.  Both epilogues are instruction-latency bound per warp, so each gets
-// 8 warps (2 per TMEM lane quadrant) working on 32-channel x 16-row blocks; every EPI2 warp runs its own
-// skip-connection prefetch ring + in-place TMA stores.
+// 2 TMEM allocator, 4-19 epilogue.  All 16 epilogue warps (4 per TMEM lane quadrant) do BOTH epilogues, one after
+// the other: their EPI1 share of a tile (2 of the 8 16-row blocks of each half), then their EPI2 share (4 of the
+// 16 16-row items).  With separate EPI1 / EPI2 warp groups the EPI1 warps idled 70 % of the time waiting for GEMM1
+// while the 8 EPI2 warps, one latency-bound item at a time, took ~14 K cycles per tile and held D2 back
+// (profiles/r01_conv_ru_bench_shape_B16.ncu-rep, warp-stall samples); now EPI2 of tile i runs on 16 warps
+// underneath GEMM1 of tile i+1.  Every warp prefetches its next skip-connection block by TMA and stores in place.
+// The residual stream is fp16 in HBM (inference plans only use this kernel).
 // Shared memory (227 KB): activation slab ring 2 x <=40 KB, weight ring 3-4 x 16 KB (W7 taps, then the two W1
-// chunks of the tile), h half 32 KB, EPI2 staging 8 x <=8 KB.
+// chunks of the tile), h half 32 KB, epilogue staging 16 x 3 KB.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -51,13 +55,12 @@ constexpr int kRuRawBlk = 16 * 128;        // 16 rows x 32 fp32, SWIZZLE_128B
 constexpr int kRuActBlk = 16 * 64;         // 16 rows x 32 bf16, SWIZZLE_64B
 constexpr int kRuThreads = 640;
 
-__host__ __device__ inline int ru_raw_blk(int raw_f16) { return raw_f16 ? kRuActBlk : kRuRawBlk; }
-__host__ __device__ inline int ru_stage_bytes_per_warp(int act_out, int raw_f16) {
-  return 3 * ru_raw_blk(raw_f16) + (act_out ? 2 * kRuActBlk : 0);
-}
+constexpr int kRuEpiWarps = 16;
+// per epilogue warp: 2 fp16 stream blocks (skip in / stream out, in place) + 1 bf16 operand block
+__host__ __device__ inline int ru_stage_bytes_per_warp(int act_out) { return 2 * kRuActBlk + (act_out ? kRuActBlk : 0); }
 __host__ __device__ inline size_t ru_smem_bytes(const RuParams& p) {
   return 1024 + 1024 + static_cast<size_t>(p.SA) * p.nbox * p.RB * 128 + static_cast<size_t>(p.SB) * kRuC * 128 +
-         kRuHBytes + 8 * ru_stage_bytes_per_warp(p.act_out, p.raw_f16);
+         kRuHBytes + kRuEpiWarps * ru_stage_bytes_per_warp(p.act_out);
 }
 
 __global__ void __launch_bounds__(kRuThreads, 1)
@@ -79,7 +82,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* d2_full = a_full + 52;
   uint64_t* d2_empty = a_full + 53;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 54);
-  uint64_t* res_full = a_full + 56;   // [8 EPI2 warps][3 slots]
+  uint64_t* res_full = a_full + 56;   // [16 epilogue warps][2 slots]
   uint8_t* a_ring = smem + 1024;
   const uint32_t a_bytes = static_cast<uint32_t>(p.nbox) * p.RB * 128;
   constexpr uint32_t b_bytes = kRuC * 128;
@@ -100,12 +103,12 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < p.SA; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.SB; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
     ptx::mbar_init(d1_full, 1);
-    ptx::mbar_init(d1_empty, 8);
-    ptx::mbar_init(h_full, 8);
+    ptx::mbar_init(d1_empty, kRuEpiWarps);
+    ptx::mbar_init(h_full, kRuEpiWarps);
     ptx::mbar_init(h_empty, 1);
     ptx::mbar_init(d2_full, 1);
-    ptx::mbar_init(d2_empty, 8);
-    for (int i = 0; i < 24; ++i) ptx::mbar_init(&res_full[i], 1);
+    ptx::mbar_init(d2_empty, kRuEpiWarps);
+    for (int i = 0; i < 2 * kRuEpiWarps; ++i) ptx::mbar_init(&res_full[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 2) {
@@ -224,28 +227,51 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::umma_commit(d2_full);
       }
     }
-  } else if (warp >= 4 && warp < 12) {
-    // ------------------------------------------------------------ EPI1: D1 -> bias, SnakeBeta -> h (shared memory)
-    const int quad = warp & 3;
-    const int sub = (warp - 4) >> 2;                   // which 16-column blocks of each 32 this warp takes
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue warps: EPI1 share, then EPI2 share, per tile
+    const int e = warp - 4;                            // 0..15
+    const int quad = warp & 3;                         // TMEM lane quadrant = channels quad*32 .. +31
+    const int sub = e >> 2;                            // 0..3: which blocks / items of the quadrant this warp takes
     const int c = quad * 32 + lane;                    // this thread's channel
-    const float bias = __ldg(p.bias7 + c);
-    const float sa = __ldg(p.s2_a + c), sib = __ldg(p.s2_inv_b + c);
-    // element (row r, channel c) of the K-major SWIZZLE_128B h tile: chunk tile c/64, 16-byte group (c%64)/8
+    const int cbase = quad * 32;
+    const float bias7 = __ldg(p.bias7 + c);
+    const float s2a = __ldg(p.s2_a + c), s2ib = __ldg(p.s2_inv_b + c);
+    const float bias1 = __ldg(p.bias1 + c);
+    float sa = 1.f, sib = 0.f;
+    if (p.sn_a) { sa = __ldg(p.sn_a + c); sib = __ldg(p.sn_inv_b + c); }
+    // EPI1: element (row r, channel c) of the K-major SWIZZLE_128B h tile: chunk tile c/64, 16-byte group (c%64)/8
     uint8_t* hb[8];
 #pragma unroll
     for (int x = 0; x < 8; ++x)
       hb[x] = h_buf + (c >> 6) * 16384 + (((((c & 63) >> 3)) ^ x) << 4) + (c & 7) * 2;
-    uint32_t d1f_ph = 0, he_ph = 0;
+    // EPI2 staging: fp16 stream blocks [16 rows x 64 B] and the bf16 operand block, SWIZZLE_64B
+    uint8_t* ring = stage_base + e * ru_stage_bytes_per_warp(p.act_out);
+    uint8_t* ablk = ring + 2 * kRuActBlk;
+    uint64_t* my_res_full = res_full + e * 2;
+    const uint32_t acol = (lane & 7) * 2, achunk = lane >> 3;
+    const bool use_skip = !(p.dbg & 1);
+    auto issue_skip = [&](int tile, int item, int slot) {   // lane 0 only
+      if (tile < p.total_tiles && use_skip) {
+        ptx::mbar_expect_tx(&my_res_full[slot], kRuActBlk);
+        ptx::tma_load_4d(ring + slot * kRuActBlk, &tmX, &my_res_full[slot], cbase, 0, (tile % p.q_tiles) * 256 + item * 16,
+                         tile / p.q_tiles);
+      }
+    };
+    if (lane == 0) issue_skip(blockIdx.x, sub, 0);
+    int slot = 0;
+    uint32_t d1f_ph = 0, he_ph = 0, d2f_ph = 0, res_ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int b = tile / p.q_tiles;
+      const int q0 = (tile % p.q_tiles) * 256;
+      // ---- EPI1 share: D1 -> bias, SnakeBeta -> h
       ptx::mbar_wait(d1_full, d1f_ph);
       d1f_ph ^= 1u;
       ptx::tc_fence_after();
       for (int half = 0; half < 2; ++half) {
-        ptx::mbar_wait(h_empty, he_ph ^ 1u);   // GEMM2 of the previous half has consumed h
+        ptx::mbar_wait(h_empty, he_ph ^ 1u);           // GEMM2 of the previous half has consumed h
         he_ph ^= 1u;
 #pragma unroll 1
-        for (int tb = sub; tb < 8; tb += 2) {          // 16-row blocks of this 128-row half
+        for (int tb = sub; tb < 8; tb += 4) {          // 16-row blocks of this 128-row half
           uint32_t r[16];
           __syncwarp();
           ptx::tmem_ld_32x16(d1 + (static_cast<uint32_t>(quad * 32) << 16) + half * 128 + tb * 16, r);
@@ -253,7 +279,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float v[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            v[j] = (p.dbg & 4) ? __uint_as_float(r[j]) + bias : snake_beta<true>(__uint_as_float(r[j]) + bias, sa, sib);
+            v[j] = (p.dbg & 4) ? __uint_as_float(r[j]) + bias7 : snake_beta<true>(__uint_as_float(r[j]) + bias7, s2a, s2ib);
 #pragma unroll
           for (int j = 0; j < 16; ++j)
             *reinterpret_cast<__nv_bfloat16*>(hb[j & 7] + (tb * 16 + j) * 128) = __float2bfloat16(v[j]);
@@ -264,83 +290,39 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(d1_empty);
-    }
-  } else if (warp >= 12) {
-    // ------------------------------------------------------------ EPI2: D2 -> bias, + skip -> stream / operand out
-    const int e = warp - 12;
-    const int quad = warp & 3;
-    const int sub = e >> 2;
-    const int c = quad * 32 + lane;
-    const int cbase = quad * 32;
-    const float bias = __ldg(p.bias1 + c);
-    float sa = 1.f, sib = 0.f;
-    if (p.sn_a) { sa = __ldg(p.sn_a + c); sib = __ldg(p.sn_inv_b + c); }
-    const int rawblk = ru_raw_blk(p.raw_f16);
-    uint8_t* raw_ring = stage_base + e * ru_stage_bytes_per_warp(p.act_out, p.raw_f16);
-    uint8_t* act_ring = raw_ring + 3 * rawblk;
-    uint64_t* my_res_full = res_full + e * 3;
-    const uint32_t rcol = (lane & 3) * 4, rchunk = lane >> 2;
-    const uint32_t acol = (lane & 7) * 2, achunk = lane >> 3;
-    int jr = 0, ja = 0;
-    uint32_t d2f_ph = 0, res_ph = 0;
-    // items of this warp inside a tile: 16-row blocks sub, sub+2, ..., 14+sub
-    if (lane == 0 && static_cast<int>(blockIdx.x) < p.total_tiles && !(p.dbg & 1)) {
-      const int b = blockIdx.x / p.q_tiles, q0 = (blockIdx.x % p.q_tiles) * 256;
-      ptx::mbar_expect_tx(&my_res_full[0], rawblk);
-      ptx::tma_load_4d(raw_ring, &tmX, &my_res_full[0], cbase, 0, q0 + sub * 16, b);
-    }
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int b = tile / p.q_tiles;
-      const int q0 = (tile % p.q_tiles) * 256;
+      if (lane == 0) ptx::mbar_arrive(d1_empty);       // GEMM1 of the next tile may start: it runs under EPI2 below
+      // ---- EPI2 share: D2 -> bias, + skip -> stream / operand out
       ptx::mbar_wait(d2_full, d2f_ph);
       d2f_ph ^= 1u;
       ptx::tc_fence_after();
 #pragma unroll 1
-      for (int item = sub; item < 16; item += 2) {
+      for (int item = sub; item < 16; item += 4) {
         const int r0 = q0 + item * 16;
         if (lane == 0) {
-          ptx::bulk_wait_read<1>();
-          int nt = tile, ni = item + 2;
+          // every store issued so far has read its shared-memory source: the other stream slot and the operand
+          // block are free again; fetch the NEXT item's skip block into the other slot
+          ptx::bulk_wait_read<0>();
+          int nt = tile, ni = item + 4;
           if (ni >= 16) { nt = tile + gridDim.x; ni = sub; }
-          if (nt < p.total_tiles && !(p.dbg & 1)) {
-            const int sn = (jr + 1) % 3;
-            ptx::mbar_expect_tx(&my_res_full[sn], rawblk);
-            ptx::tma_load_4d(raw_ring + sn * rawblk, &tmX, &my_res_full[sn], cbase, 0,
-                             (nt % p.q_tiles) * 256 + ni * 16, nt / p.q_tiles);
-          }
+          issue_skip(nt, ni, slot ^ 1);
         }
-        if (!(p.dbg & 1)) ptx::mbar_wait(&my_res_full[jr], (res_ph >> jr) & 1u);
-        res_ph ^= (1u << jr);
+        if (use_skip) ptx::mbar_wait(&my_res_full[slot], (res_ph >> slot) & 1u);
+        res_ph ^= (1u << slot);
         uint32_t r[16];
         __syncwarp();
         ptx::tmem_ld_32x16(d2 + (static_cast<uint32_t>(quad * 32) << 16) + item * 16, r);
         ptx::tmem_ld_wait();
-        uint8_t* const rblk = raw_ring + jr * rawblk;
-        uint8_t* const ablk = act_ring + ja * kRuActBlk;
+        uint8_t* const rblk = ring + slot * kRuActBlk;
+        uint8_t* hbase[4];                             // the 4 swizzle phases of a SWIZZLE_64B block
+#pragma unroll
+        for (int x = 0; x < 4; ++x) hbase[x] = rblk + ((achunk ^ x) << 4) + acol;
         float v[16];
-        if (p.raw_f16) {     // fp16 stream block: 16 rows x 64 B, SWIZZLE_64B (same shape as the operand block)
-          uint8_t* hbase[4];
 #pragma unroll
-          for (int x = 0; x < 4; ++x) hbase[x] = rblk + ((achunk ^ x) << 4) + acol;
+        for (int j = 0; j < 16; ++j)
+          v[j] = __uint_as_float(r[j]) + bias1 + __half2float(*reinterpret_cast<const __half*>(hbase[(j >> 1) & 3] + j * 64));
+        if (p.raw_out) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            v[j] = __uint_as_float(r[j]) + bias + __half2float(*reinterpret_cast<const __half*>(hbase[(j >> 1) & 3] + j * 64));
-          if (p.raw_out) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) *reinterpret_cast<__half*>(hbase[(j >> 1) & 3] + j * 64) = __float2half_rn(v[j]);
-          }
-        } else {
-          uint8_t* rbase[8];
-#pragma unroll
-          for (int x = 0; x < 8; ++x) rbase[x] = rblk + ((rchunk ^ x) << 4) + rcol;
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            v[j] = __uint_as_float(r[j]) + bias + *reinterpret_cast<const float*>(rbase[j & 7] + j * 128);
-          if (p.raw_out) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) *reinterpret_cast<float*>(rbase[j & 7] + j * 128) = v[j];
-          }
+          for (int j = 0; j < 16; ++j) *reinterpret_cast<__half*>(hbase[(j >> 1) & 3] + j * 64) = __float2half_rn(v[j]);
         }
         if (p.act_out) {
           if (p.sn_a && !(p.dbg & 8)) {
@@ -361,8 +343,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.act_out && !(p.dbg & 2)) ptx::tma_store_4d(&tmO, ablk, cbase, 0, r0, b);
           ptx::bulk_commit();
         }
-        jr = (jr + 1 == 3) ? 0 : jr + 1;
-        ja ^= 1;
+        slot ^= 1;
       }
       ptx::tc_fence_before();
       __syncwarp();

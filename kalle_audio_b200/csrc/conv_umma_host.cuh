@@ -485,9 +485,10 @@ inline bool prepare_conv_ru(const RuArgs& a, int B, int T, int dilation, RuLaunc
   p.raw_out = a.out_raw ? 1 : 0;
   p.act_out = a.out_act ? 1 : 0;
   const size_t a_bytes = static_cast<size_t>(p.nbox) * p.RB * 128, b_bytes = kRuC * 128;
-  p.raw_f16 = a.stream_f16 ? 1 : 0;
-  const int sdt = a.stream_f16 ? 2 : 1;
-  const size_t budget = 227 * 1024 - 2048 - kRuHBytes - 8 * static_cast<size_t>(ru_stage_bytes_per_warp(p.act_out, p.raw_f16));
+  if (!a.stream_f16) { err = "fused RU: needs the fp16 residual stream"; return false; }
+  p.raw_f16 = 1;
+  const int sdt = 2;
+  const size_t budget = 227 * 1024 - 2048 - kRuHBytes - kRuEpiWarps * static_cast<size_t>(ru_stage_bytes_per_warp(p.act_out));
   p.SA = 2;
   if (2 * a_bytes + 3 * b_bytes > budget) { err = "fused RU does not fit shared memory"; return false; }
   p.SB = static_cast<int>(std::min<size_t>(8, (budget - 2 * a_bytes) / b_bytes));

@@ -359,7 +359,7 @@ void finalize_steps(kvae_plan* p) {
   // ResidualUnits of 128-channel stages run as ONE kernel (conv_ru.cuh): k7 -> SnakeBeta -> k1 -> + skip
   const char* nf = getenv("KVAE_NO_RU_FUSION");
   const char* v1 = getenv("KVAE_CONV_V1");
-  if ((nf && nf[0] == '1') || (v1 && v1[0] == '1')) return;
+  if ((nf && nf[0] == '1') || (v1 && v1[0] == '1') || !p->stream_f16) return;   // the fused kernel reads / writes the fp16 stream
   for (int k = 1; k + 1 < n; ++k) {
     Step& a = p->steps[k];
     Step& b = p->steps[k + 1];

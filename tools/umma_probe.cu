@@ -344,22 +344,26 @@ static int run_ru(int dilation, int B, int T, int perf) {
   for (size_t i = 0; i < w7.size(); ++i) w7b[i] = __float2bfloat16(w7[i]);
   for (size_t i = 0; i < w1.size(); ++i) w1b[i] = __float2bfloat16(w1[i]);
   __nv_bfloat16 *da, *dw7, *dw1, *dact;
-  float *dx, *draw, *db7, *db1, *ds2a, *ds2ib, *dsna, *dsnib;
+  __half *dx, *draw;                       // the fused kernel reads / writes the fp16 residual stream
+  float *db7, *db1, *ds2a, *ds2ib, *dsna, *dsnib;
+  std::vector<__half> xh(n);
+  for (size_t i = 0; i < n; ++i) { xh[i] = __float2half(x[i]); x[i] = __half2float(xh[i]); }
   CK(cudaMalloc(&da, n * 2)); CK(cudaMalloc(&dw7, w7.size() * 2)); CK(cudaMalloc(&dw1, w1.size() * 2));
-  CK(cudaMalloc(&dact, n * 2)); CK(cudaMalloc(&dx, n * 4)); CK(cudaMalloc(&draw, n * 4));
+  CK(cudaMalloc(&dact, n * 2)); CK(cudaMalloc(&dx, n * 2)); CK(cudaMalloc(&draw, n * 2));
   CK(cudaMalloc(&db7, C * 4)); CK(cudaMalloc(&db1, C * 4)); CK(cudaMalloc(&ds2a, C * 4)); CK(cudaMalloc(&ds2ib, C * 4));
   CK(cudaMalloc(&dsna, C * 4)); CK(cudaMalloc(&dsnib, C * 4));
   CK(cudaMemcpy(da, ab.data(), n * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dw7, w7b.data(), w7.size() * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dw1, w1b.data(), w1.size() * 2, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(dx, x.data(), n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dx, xh.data(), n * 2, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(db7, b7.data(), C * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(db1, b1.data(), C * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(ds2a, s2a.data(), C * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(ds2ib, s2ib.data(), C * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dsna, sna.data(), C * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dsnib, snib.data(), C * 4, cudaMemcpyHostToDevice));
-  CK(cudaMemset(draw, 0xff, n * 4)); CK(cudaMemset(dact, 0xff, n * 2));
+  CK(cudaMemset(draw, 0xff, n * 2)); CK(cudaMemset(dact, 0xff, n * 2));
   RuArgs ra;
   ra.a = da; ra.x = dx; ra.w7 = dw7; ra.w1 = dw1; ra.bias7 = db7; ra.s2_a = ds2a; ra.s2_inv_b = ds2ib; ra.bias1 = db1;
   ra.out_raw = draw; ra.out_act = dact; ra.sn_a = dsna; ra.sn_inv_b = dsnib;
+  ra.stream_f16 = 1;
   RuLaunch L;
   std::string err;
   if (!prepare_conv_ru(ra, B, T, dilation, L, err)) { printf("RU d=%d: prepare failed: %s\n", dilation, err.c_str()); return 3; }
@@ -377,13 +381,15 @@ static int run_ru(int dilation, int B, int T, int perf) {
     CK(cudaEventRecord(e1));
     CK(cudaDeviceSynchronize());
     float ms; CK(cudaEventElapsedTime(&ms, e0, e1)); ms /= 10;
-    const double flops = 2.0 * B * T * C * C * 8.0, bytes = (double)n * (2 + 4 + 4 + 2);
+    const double flops = 2.0 * B * T * C * C * 8.0, bytes = (double)n * (2 + 2 + 2 + 2);
     printf("PERF fused RU d=%d B=%d T=%d: %.3f ms  %.1f TFLOP/s  %.1f GB/s\n", dilation, B, T, ms, flops / ms * 1e-9, bytes / ms * 1e-6);
     return 0;
   }
   std::vector<float> raw(n);
+  std::vector<__half> rawh(n);
   std::vector<__nv_bfloat16> act(n);
-  CK(cudaMemcpy(raw.data(), draw, n * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(rawh.data(), draw, n * 2, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i) raw[i] = __half2float(rawh[i]);
   CK(cudaMemcpy(act.data(), dact, n * 2, cudaMemcpyDeviceToHost));
   double max_err = 0, max_err_act = 0, max_ref = 0; size_t bad = 0, first_bad = (size_t)-1;
   std::vector<float> h((size_t)T * C);
