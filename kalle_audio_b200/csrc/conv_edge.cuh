@@ -179,11 +179,11 @@ __global__ void __launch_bounds__(288, 1) conv_wave_out_kernel(const WaveOutPara
 // descriptors per tap re-read the tile 7 times and was bound by the shared-memory port).
 //   * warp 0 (TMA) streams the fp32 residual stream tile [128 rows x 128 ch] as four 32-channel boxes
 //     (SWIZZLE_128B: one 128-byte line = 32 floats = one K-major tf32 operand row) into a 3-slot ring;
-//   * warps 4-11 apply SnakeBeta IN PLACE on the staged tile (element-wise, so the swizzle is irrelevant; the
+//   * warps 4-19 apply SnakeBeta IN PLACE on the staged tile (element-wise, so the swizzle is irrelevant; the
 //     channel of a 16-byte unit is recovered from its position), round to tf32 (cvt.rna) and hand the slot to the
 //     MMA warp through fence.proxy.async + mbarrier;
 //   * warp 1 issues 4 chunks x 4 K-steps MMAs of 128 x 16 x 8; the weights [4][16 x 32] stay in shared memory;
-//   * warps 12-15 move P (TMEM lane = row) to shared memory, sum the taps of the 122 outputs whose windows lie
+//   * warps 20-23 move P (TMEM lane = row) to shared memory, sum the taps of the 122 outputs whose windows lie
 //     inside the tile and write [B, io, T] directly, coalesced.
 // The stream stays fp32 in HBM and the accumulation fp32; only the operands are rounded to tf32 (11 significant
 // bits), ~4x finer than the bf16 operands of every other conv in the stack.
@@ -205,7 +205,7 @@ constexpr int kWoTcTile = kWoTcRows - 6;             // outputs per tile (k7: 3 
 constexpr int kWoTcChunk = kWoTcRows * 128;          // bytes of one chunk (32 fp32 or 64 fp16 channels)
 constexpr int kWoTcSlots = 3;
 constexpr int kWoTcPStride = 17;                     // floats per P row in shared memory (conflict-free)
-constexpr int kWoTcThreads = 512;
+constexpr int kWoTcThreads = 768;                   // warps 0-2 control, 4-19 SnakeBeta transform, 20-23 epilogue
 template <bool kF16> struct WoTc {
   static constexpr int kChunks = kF16 ? 2 : 4;
   static constexpr int kSlab = kChunks * kWoTcChunk;             // 32768 / 65536 B
@@ -239,7 +239,7 @@ conv_wave_out_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   const int lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmX);
-    for (int i = 0; i < kWoTcSlots; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&ready[i], 8); ptx::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kWoTcSlots; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&ready[i], 16); ptx::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 4); }
     ptx::fence_mbar_init();
   }
@@ -316,16 +316,16 @@ conv_wave_out_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         if (++a == 2) { a = 0; aph ^= 1u; }
       }
     }
-  } else if (warp >= 4 && warp < 12) {
+  } else if (warp >= 4 && warp < 20) {
     // ------------------------------------------------------------ SnakeBeta in place on the staged tile
-    const int tid = threadIdx.x - 128;                    // 0..255
+    const int tid = threadIdx.x - 128;                    // 0..511
     int s = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       ptx::mbar_wait(&full[s], ph);
       float4* slab = reinterpret_cast<float4*>(ring + s * kWoTcSlab);
 #pragma unroll 4
-      for (int u = tid; u < kChunks * kWoTcRows * 8; u += 256) {     // 16-byte units
+      for (int u = tid; u < kChunks * kWoTcRows * 8; u += 512) {     // 16-byte units
         const int r = (u >> 3) & (kWoTcRows - 1), c = u >> 10;
         if (kF16) {
           const int ch = c * 64 + (((u & 7) ^ (r & 7)) << 3);          // 8 fp16 channels per unit
@@ -356,7 +356,7 @@ conv_wave_out_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       if (lane == 0) ptx::mbar_arrive(&ready[s]);
       if (++s == kWoTcSlots) { s = 0; ph ^= 1u; }
     }
-  } else if (warp >= 12) {
+  } else if (warp >= 20) {
     // ------------------------------------------------------------ P -> shared memory -> tap sum -> [B, io, T]
     const int quad = warp & 3;
     const int i = quad * 32 + lane;                      // row of the tile / output index

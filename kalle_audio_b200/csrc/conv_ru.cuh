@@ -264,25 +264,30 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int b = tile / p.q_tiles;
       const int q0 = (tile % p.q_tiles) * 256;
       // ---- EPI1 share: D1 -> bias, SnakeBeta -> h
-      ptx::mbar_wait(d1_full, d1f_ph);
+      ptx::mbar_wait_parked(d1_full, d1f_ph);
       d1f_ph ^= 1u;
       ptx::tc_fence_after();
       for (int half = 0; half < 2; ++half) {
-        ptx::mbar_wait(h_empty, he_ph ^ 1u);           // GEMM2 of the previous half has consumed h
+        ptx::mbar_wait_parked(h_empty, he_ph ^ 1u);           // GEMM2 of the previous half has consumed h
         he_ph ^= 1u;
-#pragma unroll 1
-        for (int tb = sub; tb < 8; tb += 4) {          // 16-row blocks of this 128-row half
-          uint32_t r[16];
+        {
+          // this warp's two 16-row blocks of the half: both TMEM loads in flight before either is consumed
+          uint32_t r0[16], r1[16];
           __syncwarp();
-          ptx::tmem_ld_32x16(d1 + (static_cast<uint32_t>(quad * 32) << 16) + half * 128 + tb * 16, r);
+          const uint32_t t0 = d1 + (static_cast<uint32_t>(quad * 32) << 16) + half * 128 + sub * 16;
+          ptx::tmem_ld_32x16(t0, r0);
+          ptx::tmem_ld_32x16(t0 + 64, r1);
           ptx::tmem_ld_wait();
-          float v[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            v[j] = (p.dbg & 4) ? __uint_as_float(r[j]) + bias7 : snake_beta<true>(__uint_as_float(r[j]) + bias7, s2a, s2ib);
+          for (int j = 0; j < 16; ++j) {
+            const float v = (p.dbg & 4) ? __uint_as_float(r0[j]) + bias7 : snake_beta<true>(__uint_as_float(r0[j]) + bias7, s2a, s2ib);
+            *reinterpret_cast<__nv_bfloat16*>(hb[j & 7] + (sub * 16 + j) * 128) = __float2bfloat16(v);
+          }
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            *reinterpret_cast<__nv_bfloat16*>(hb[j & 7] + (tb * 16 + j) * 128) = __float2bfloat16(v[j]);
+          for (int j = 0; j < 16; ++j) {
+            const float v = (p.dbg & 4) ? __uint_as_float(r1[j]) + bias7 : snake_beta<true>(__uint_as_float(r1[j]) + bias7, s2a, s2ib);
+            *reinterpret_cast<__nv_bfloat16*>(hb[j & 7] + ((sub + 4) * 16 + j) * 128) = __float2bfloat16(v);
+          }
         }
         ptx::fence_proxy_async();
         __syncwarp();
@@ -292,7 +297,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(d1_empty);       // GEMM1 of the next tile may start: it runs under EPI2 below
       // ---- EPI2 share: D2 -> bias, + skip -> stream / operand out
-      ptx::mbar_wait(d2_full, d2f_ph);
+      ptx::mbar_wait_parked(d2_full, d2f_ph);
       d2f_ph ^= 1u;
       ptx::tc_fence_after();
 #pragma unroll 1
@@ -306,7 +311,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (ni >= 16) { nt = tile + gridDim.x; ni = sub; }
           issue_skip(nt, ni, slot ^ 1);
         }
-        if (use_skip) ptx::mbar_wait(&my_res_full[slot], (res_ph >> slot) & 1u);
+        if (use_skip) ptx::mbar_wait_parked(&my_res_full[slot], (res_ph >> slot) & 1u);
         res_ph ^= (1u << slot);
         uint32_t r[16];
         __syncwarp();

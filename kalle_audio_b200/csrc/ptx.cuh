@@ -72,6 +72,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Wait with a hardware suspend-time hint: the warp is parked by the barrier unit until the phase completes (or the
+// hint, in ns, expires) instead of re-issuing try_wait + loop overhead -- with 16 epilogue warps per CTA the plain
+// spin loops were a quarter of all issued instructions (profiles/r01_conv_ru_unified_epilogue_B16.ncu-rep).
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+        : "memory");
+    if (ok) return;
+    if (++spins > (KVAE_SPIN_LIMIT >> 6)) {
+      printf("kvae: mbarrier timeout (parked) block(%d,%d,%d) thread %d bar %p parity %u\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+
 // Same, for warps that are not on the critical path (epilogues): back off between polls so that a dozen
 // waiting warps do not eat the issue slots of the one thread that feeds the tensor core.
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
