@@ -336,7 +336,7 @@ conv_wave_out_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
             float2 f = __half22float2(h2[e]);
             f.x = snake_beta<true>(f.x, tab[ch + 2 * e], tab[128 + ch + 2 * e]);
             f.y = snake_beta<true>(f.y, tab[ch + 2 * e + 1], tab[128 + ch + 2 * e + 1]);
-            h2[e] = __floats2half2_rn(f.x, f.y);
+            reinterpret_cast<uint32_t*>(h2)[e] = ptx::f2h2_sat(f.x, f.y);
           }
           slab[u] = q;
         } else {
@@ -453,9 +453,8 @@ __global__ void __launch_bounds__(128) conv_wave_in_kernel(const WaveInParams p)
     const size_t o = (static_cast<size_t>(b) * p.T + t) * p.Cout + co;
     if (p.out_raw) {
       if (p.raw_f16) {
-        __half2 h0 = __floats2half2_rn(v0, v1), h1 = __floats2half2_rn(v2, v3);
         *reinterpret_cast<uint2*>(static_cast<__half*>(p.out_raw) + o) =
-            make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+            make_uint2(ptx::f2h2_sat(v0, v1), ptx::f2h2_sat(v2, v3));
       } else {
         *reinterpret_cast<float4*>(static_cast<float*>(p.out_raw) + o) = make_float4(v0, v1, v2, v3);
       }

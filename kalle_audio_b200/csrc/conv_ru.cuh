@@ -327,7 +327,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           v[j] = __uint_as_float(r[j]) + bias1 + __half2float(*reinterpret_cast<const __half*>(hbase[(j >> 1) & 3] + j * 64));
         if (p.raw_out) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) *reinterpret_cast<__half*>(hbase[(j >> 1) & 3] + j * 64) = __float2half_rn(v[j]);
+          for (int j = 0; j < 16; ++j) *reinterpret_cast<uint16_t*>(hbase[(j >> 1) & 3] + j * 64) = ptx::f2h_sat(v[j]);
         }
         if (p.act_out) {
           if (p.sn_a && !(p.dbg & 8)) {

@@ -352,7 +352,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           if (p.raw_mode == 1) {
             if (p.raw_f16) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) *reinterpret_cast<__half*>(hbase[(j >> 1) & 3] + j * 64) = __float2half_rn(v[j]);
+              for (int j = 0; j < 32; ++j) *reinterpret_cast<uint16_t*>(hbase[(j >> 1) & 3] + j * 64) = ptx::f2h_sat(v[j]);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) *reinterpret_cast<float*>(rbase[j & 7] + j * 128) = v[j];
@@ -425,8 +425,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               uint32_t w[4];
 #pragma unroll
               for (int q4 = 0; q4 < 4; ++q4) {
-                __half2 h = __floats2half2_rn(v[8 * j + 2 * q4], v[8 * j + 2 * q4 + 1]);
-                w[q4] = *reinterpret_cast<uint32_t*>(&h);
+                w[q4] = ptx::f2h2_sat(v[8 * j + 2 * q4], v[8 * j + 2 * q4 + 1]);
               }
               *reinterpret_cast<uint4*>(rt16 + ((j ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
             }

@@ -212,6 +212,18 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// fp32 -> fp16 for the residual stream: round to nearest, SATURATING at +-65504 instead of overflowing to inf
+// (a checkpoint with unusually large activations degrades gracefully instead of producing NaNs downstream)
+__device__ __forceinline__ uint16_t f2h_sat(float x) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ uint32_t f2h2_sat(float lo, float hi) {   // {hi, lo} packed, lo in bits 0-15
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
 // round-to-nearest fp32 -> tf32 (the tensor core itself truncates)
 __device__ __forceinline__ float round_tf32(float x) {
   uint32_t r;

@@ -406,3 +406,15 @@ def test_streaming_decoder_equals_full_decode(dev, precision, hop):
     assert y.shape == full.shape
     tol = 2e-6 if precision == "fp32" else 1e-6      # same inputs, same per-output summation order
     assert float((y - full).abs().max()) <= tol * max(1.0, float(full.abs().max()))
+
+
+def test_fp16_stream_saturates_instead_of_overflowing(dev):
+    """Inference plans keep the residual stream in fp16; activations beyond +-65504 must saturate, not become inf/NaN."""
+    m = H.build("sao", 0).to(dev).set_precision("bf16")
+    with torch.no_grad():
+        for name, p in m.decoder.named_parameters():
+            if name.endswith("layers.1.bias") and p.numel() == 128:      # biases of the 128-channel stages
+                p.fill_(3.0e5)
+    z = torch.randn(1, 64, 4, generator=torch.Generator().manual_seed(1)).to(dev)
+    y = m.decode(z)
+    assert bool(torch.isfinite(y).all())
