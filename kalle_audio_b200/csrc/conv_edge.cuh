@@ -319,37 +319,46 @@ conv_wave_out_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   } else if (warp >= 4 && warp < 20) {
     // ------------------------------------------------------------ SnakeBeta in place on the staged tile
     const int tid = threadIdx.x - 128;                    // 0..511
+    // A thread's 16-byte units are tid + 512*i: the same position inside a row and the same row phase (row & 7)
+    // for every i, so the channels it touches are fixed -- chunk i/2, group g -- and their SnakeBeta constants
+    // live in registers (a table lookup per element made this stage issue-bound).
+    constexpr int kPer = kF16 ? 8 : 4;                    // channels per 16-byte unit
+    constexpr int kChunkCh = kF16 ? 64 : 32;
+    const int g = (tid & 7) ^ ((tid >> 3) & 7);
+    float ca[kChunks][kPer], cb[kChunks][kPer];
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c)
+#pragma unroll
+      for (int e = 0; e < kPer; ++e) {
+        ca[c][e] = tab[c * kChunkCh + g * kPer + e];
+        cb[c][e] = tab[128 + c * kChunkCh + g * kPer + e];
+      }
     int s = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       ptx::mbar_wait(&full[s], ph);
       float4* slab = reinterpret_cast<float4*>(ring + s * kWoTcSlab);
-#pragma unroll 4
-      for (int u = tid; u < kChunks * kWoTcRows * 8; u += 512) {     // 16-byte units
-        const int r = (u >> 3) & (kWoTcRows - 1), c = u >> 10;
+#pragma unroll
+      for (int i = 0; i < 2 * kChunks; ++i) {              // kChunks * 128 rows * 8 units / 512 threads
+        const int u = tid + 512 * i;
+        const int c = i >> 1;
+        float4 q = slab[u];
         if (kF16) {
-          const int ch = c * 64 + (((u & 7) ^ (r & 7)) << 3);          // 8 fp16 channels per unit
-          float4 q = slab[u];
           __half2* h2 = reinterpret_cast<__half2*>(&q);
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float2 f = __half22float2(h2[e]);
-            f.x = snake_beta<true>(f.x, tab[ch + 2 * e], tab[128 + ch + 2 * e]);
-            f.y = snake_beta<true>(f.y, tab[ch + 2 * e + 1], tab[128 + ch + 2 * e + 1]);
+            f.x = snake_beta<true>(f.x, ca[c][2 * e], cb[c][2 * e]);
+            f.y = snake_beta<true>(f.y, ca[c][2 * e + 1], cb[c][2 * e + 1]);
             reinterpret_cast<uint32_t*>(h2)[e] = ptx::f2h2_sat(f.x, f.y);
           }
-          slab[u] = q;
         } else {
-          const int ch = c * 32 + (((u & 7) ^ (r & 7)) << 2);
-          const float4 a4 = *reinterpret_cast<const float4*>(tab + ch);
-          const float4 b4 = *reinterpret_cast<const float4*>(tab + 128 + ch);
-          float4 v = slab[u];
-          v.x = ptx::round_tf32(snake_beta<true>(v.x, a4.x, b4.x));
-          v.y = ptx::round_tf32(snake_beta<true>(v.y, a4.y, b4.y));
-          v.z = ptx::round_tf32(snake_beta<true>(v.z, a4.z, b4.z));
-          v.w = ptx::round_tf32(snake_beta<true>(v.w, a4.w, b4.w));
-          slab[u] = v;
+          q.x = ptx::round_tf32(snake_beta<true>(q.x, ca[c][0], cb[c][0]));
+          q.y = ptx::round_tf32(snake_beta<true>(q.y, ca[c][1], cb[c][1]));
+          q.z = ptx::round_tf32(snake_beta<true>(q.z, ca[c][2], cb[c][2]));
+          q.w = ptx::round_tf32(snake_beta<true>(q.w, ca[c][3], cb[c][3]));
         }
+        slab[u] = q;
       }
       ptx::fence_proxy_async();
       __syncwarp();
