@@ -451,6 +451,43 @@ def run_extra(args):
         dist.destroy_process_group()
 
 
+def run_eager_baseline(args):
+    """Context number, not a bench line the driver consumes: the oracle restatement (plain torch functional ops =
+    what the reference's nn.Modules execute, cuDNN convs + eager elementwise kernels) run on the same B200 in bf16
+    autocast, decode only, 16 clips x 10.03 s.  SURVEY.md section 8d names this 'the only existing Blackwell path'."""
+    import torch
+    import helpers as H
+    from oracle import oobleck_oracle as O
+    import kalle_audio_b200 as k
+    torch.set_grad_enabled(False)
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    m = k.create_autoencoder_from_config(sao_config()).eval()
+    dec_sd = {n: p.to(dev) for n, p in H.split_sd(m.state_dict(), "decoder.").items()}
+    B = args.micro_batch or 4
+    z = torch.randn(B, 64, CLIP_FRAMES, device=dev)
+
+    def step():
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            return O.oobleck_decoder(dec_sd, z, SAO["strides"])
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    audio_s = B * CLIP_FRAMES * 2048 / SAO["sample_rate"]
+    print(json.dumps({"impl": "torch-eager-bf16 (oracle restatement on cuda:0, cuDNN + eager elementwise)",
+                      "metric": METRIC, "value": audio_s / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+                      "ms_per_step": ms, "dtype": "bf16 autocast", "config": {"workload": f"SAO decode only, {B} clips x 10.03 s"}}),
+          flush=True)
+
+
 def run_train(args):
     """BASELINE configs[4]: SAO encoder + decoder training step (encode -> vae_sample -> decode -> Gaussian NLL +
     KL -> backward -> gradient all-reduce -> AdamW), 4 clips x 5.016 s per GPU (8 GPUs = the config's global batch
@@ -541,7 +578,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["cuda", "reference"], default="cuda")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", choices=["roundtrip", "o12_decode", "stream", "train"], default="roundtrip",
+    ap.add_argument("--workload", choices=["roundtrip", "o12_decode", "stream", "train", "eager_baseline"], default="roundtrip",
                     help="roundtrip = BASELINE configs[1] (the driver's line); o12_decode = configs[2]; stream = configs[3]; "
                          "train = configs[4]")
     ap.add_argument("--micro-batch", type=int, default=0)
@@ -550,6 +587,8 @@ def main():
         run_reference(args)
     elif args.workload == "train":
         run_train(args)
+    elif args.workload == "eager_baseline":
+        run_eager_baseline(args)
     elif args.workload != "roundtrip":
         run_extra(args)
     else:
