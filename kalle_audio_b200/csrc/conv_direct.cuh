@@ -32,6 +32,7 @@ struct DirectParams {
   int out_raw_f32;
   long long o_sB, o_sT, o_sC;     // element strides of out_raw
   __nv_bfloat16* out_act;         // channels-last bf16 (SnakeBeta applied if snake_a)
+  int act_split;                  // 1: out_act is [B, T, 2*Cout], bf16 (hi | lo) halves (fp32-mode tensor-core consumer)
   const float* snake_a;
   const float* snake_inv_b;
   int tanh_out;
@@ -135,7 +136,13 @@ conv_direct_kernel(const __grid_constant__ DirectParams p) {
       if (p.out_act) {
         float a = v;
         if (p.snake_a) a = snake_beta<false>(v, p.snake_a[co], p.snake_inv_b[co]);
-        p.out_act[cl_row + co] = __float2bfloat16(a);
+        if (p.act_split) {
+          const __nv_bfloat16 hi = __float2bfloat16(a);
+          p.out_act[2 * cl_row + co] = hi;
+          p.out_act[2 * cl_row + p.Cout + co] = __float2bfloat16(a - __bfloat162float(hi));
+        } else {
+          p.out_act[cl_row + co] = __float2bfloat16(a);
+        }
       }
     }
   }

@@ -52,6 +52,13 @@ struct ConvParams2 {
   void* out_cf;            // raw_mode 2: [B, Cout, T_out]
   int out_cf_f32;
   int act_mode;            // 0 none, 1 bf16 channels-last via TMA (tmO)
+  int split3;              // fp32-mode arithmetic on the tensor cores: both operands are stored as bf16 (hi | lo)
+                           // halves -- activations [.., 2*Cin], weights [tap][Cout][2*Cin] -- and every K chunk is
+                           // multiplied three times: hi*hi + lo*hi + hi*lo (the lo*lo term is below fp32 rounding).
+                           // The kernel just sees 3x the chunks, with different operand columns per chunk.
+  int Cin;                 // input channels (split3: column of the lo halves)
+  int act_split;           // 1: the bf16 operand output is written as (hi | lo) halves, lo at channel Cout + c
+  int precise;             // 1: SnakeBeta with sinf (fp32 mode), 0: MUFU sin
   const float* snake_a;    // SnakeBeta folded into the activated output (nullptr: plain cast)
   const float* snake_inv_b;
 };
@@ -64,13 +71,15 @@ __host__ __device__ inline int conv_umma2_raw_blk(int raw_f16) { return raw_f16 
 __host__ __device__ inline int conv_umma2_raw_slots(int raw_mode, bool residual) {
   return (raw_mode == 1 || residual) ? (residual ? 3 : 2) : 0;
 }
-__host__ __device__ inline int conv_umma2_stage_bytes_per_warp(int raw_mode, int act_mode, bool residual, int raw_f16) {
-  return conv_umma2_raw_slots(raw_mode, residual) * conv_umma2_raw_blk(raw_f16) + (act_mode == 1 ? 2 * kActBlkBytes : 0);
+__host__ __device__ inline int conv_umma2_stage_bytes_per_warp(int raw_mode, int act_mode, bool residual, int raw_f16,
+                                                               int act_split = 0) {
+  return conv_umma2_raw_slots(raw_mode, residual) * conv_umma2_raw_blk(raw_f16) +
+         (act_mode == 1 ? 2 * kActBlkBytes * (act_split ? 2 : 1) : 0);
 }
 
 __host__ __device__ inline size_t conv_umma2_smem_bytes(const ConvParams2& p) {
   return 1024 + 1024 + static_cast<size_t>(p.SA) * p.nbox * p.RB * 128 + static_cast<size_t>(p.SB) * p.NT * 128 +
-         8 * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, p.residual != nullptr, p.raw_f16);
+         8 * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, p.residual != nullptr, p.raw_f16, p.act_split);
 }
 
 __global__ void __launch_bounds__(384, 1)
@@ -143,7 +152,15 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         int b, q0, phi, n0;
         decode(tile, b, q0, phi, n0);
         const int t_lo = p.tap_begin[phi], t_hi = p.tap_begin[phi + 1];
-        for (int ch = 0; ch < p.n_chunks; ++ch) {
+        const int n_vc = p.split3 ? 3 * p.n_chunks : p.n_chunks;
+        for (int ch = 0; ch < n_vc; ++ch) {
+          // operand columns of this (virtual) chunk: plain, or hi*hi / lo*hi / hi*lo of the bf16x3 split
+          int a_col = ch * 64, w_col = ch * 64;
+          if (p.split3) {
+            const int c = ch % p.n_chunks, part = ch / p.n_chunks;
+            a_col = c * 64 + (part == 1 ? p.Cin : 0);
+            w_col = c * 64 + (part == 2 ? p.Cin : 0);
+          }
           for (int t = t_lo; t < t_hi; ++t) {
             const uint32_t tl = p.tap_ld[t];
             if (p.tap_mma[t] & 0x10000u) {
@@ -152,12 +169,12 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const int row = q0 + (static_cast<int32_t>(tl) >> 16);
               for (int bx = 0; bx < p.nbox; ++bx)
                 ptx::tma_load_4d(a_ring + static_cast<size_t>(as) * a_bytes + bx * p.RB * 128, &tmA, &a_full[as],
-                                 ch * 64, tl & 0xff, row + bx * p.RB, b);
+                                 a_col, tl & 0xff, row + bx * p.RB, b);
               if (++as == p.SA) { as = 0; aph ^= 1u; }
             }
             ptx::mbar_wait(&b_empty[bs], bph ^ 1u);
             ptx::mbar_expect_tx(&b_full[bs], b_bytes);
-            ptx::tma_load_3d(b_ring + static_cast<size_t>(bs) * b_bytes, &tmW, &b_full[bs], ch * 64, n0,
+            ptx::tma_load_3d(b_ring + static_cast<size_t>(bs) * b_bytes, &tmW, &b_full[bs], w_col, n0,
                              (tl >> 8) & 0xff);
             if (++bs == p.SB) { bs = 0; bph ^= 1u; }
           }
@@ -186,7 +203,8 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t d0 = tmem_base + acc * acc_cols;
         const uint32_t d1 = d0 + p.NT;
         uint32_t accum = 0;                          // first MMA of a tile overwrites the accumulator
-        for (int ch = 0; ch < p.n_chunks; ++ch) {
+        const int n_vc = p.split3 ? 3 * p.n_chunks : p.n_chunks;
+        for (int ch = 0; ch < n_vc; ++ch) {
           for (int t = t_lo; t < t_hi; ++t) {
             const uint32_t tw = p.tap_mma[t];
             if (tw & 0x10000u) {
@@ -236,7 +254,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const bool has_res = p.residual != nullptr;
     const int R = conv_umma2_raw_slots(p.raw_mode, has_res);
     const int rawblk = conv_umma2_raw_blk(p.raw_f16);
-    uint8_t* raw_ring = stage_base + e * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, has_res, p.raw_f16);
+    uint8_t* raw_ring = stage_base + e * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, has_res, p.raw_f16, p.act_split);
     uint8_t* act_ring = raw_ring + R * rawblk;
     uint64_t* my_res_full = res_full + e * 3;
     // An item is one 32-row x 32-channel output block.  swap = 0: TMEM lane = time row, so a thread owns one
@@ -314,7 +332,8 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
         uint8_t* const rblk = raw_ring + jr * rawblk;
-        uint8_t* const ablk = act_ring + ja * kActBlkBytes;
+        const int actblk = kActBlkBytes * (p.act_split ? 2 : 1);       // (hi | lo) blocks back to back
+        uint8_t* const ablk = act_ring + ja * actblk;
         if (p.swap) {
           // ---- thread = channel (cbase + lane), v[j] = row r0 + j
           // element (row j, channel lane) of a SWIZZLE_128B fp32 block / SWIZZLE_64B bf16 block
@@ -360,15 +379,30 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           if (p.act_mode == 1) {
             if (p.snake_a) {   // hoisted: a per-element test would put a branch between the 32 independent chains
+              if (p.precise) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = snake_beta<true>(v[j], sa_s, sib_s);
+                for (int j = 0; j < 32; ++j) v[j] = snake_beta<false>(v[j], sa_s, sib_s);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = snake_beta<true>(v[j], sa_s, sib_s);
+              }
             }
             uint8_t* abase[4];   // the 4 distinct swizzle phases of a SWIZZLE_64B block
 #pragma unroll
             for (int c = 0; c < 4; ++c) abase[c] = ablk + ((achunk ^ c) << 4) + acol;
+            if (p.act_split) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              *reinterpret_cast<__nv_bfloat16*>(abase[(j >> 1) & 3] + j * 64) = __float2bfloat16(v[j]);
+              for (int j = 0; j < 32; ++j) {
+                const __nv_bfloat16 hi = __float2bfloat16(v[j]);
+                *reinterpret_cast<__nv_bfloat16*>(abase[(j >> 1) & 3] + j * 64) = hi;
+                *reinterpret_cast<__nv_bfloat16*>(abase[(j >> 1) & 3] + kActBlkBytes + j * 64) =
+                    __float2bfloat16(v[j] - __bfloat162float(hi));
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                *reinterpret_cast<__nv_bfloat16*>(abase[(j >> 1) & 3] + j * 64) = __float2bfloat16(v[j]);
+            }
           }
         } else {
         // ---- thread = time row (r0 + lane), v[j] = channel cbase + j
@@ -442,22 +476,37 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             for (int j = 0; j < 32; j += 4) {
               const float4 a = __ldg(reinterpret_cast<const float4*>(p.snake_a + cbase + j));
               const float4 ib = __ldg(reinterpret_cast<const float4*>(p.snake_inv_b + cbase + j));
-              v[j] = snake_beta<true>(v[j], a.x, ib.x);
-              v[j + 1] = snake_beta<true>(v[j + 1], a.y, ib.y);
-              v[j + 2] = snake_beta<true>(v[j + 2], a.z, ib.z);
-              v[j + 3] = snake_beta<true>(v[j + 3], a.w, ib.w);
+              if (p.precise) {
+                v[j] = snake_beta<false>(v[j], a.x, ib.x);
+                v[j + 1] = snake_beta<false>(v[j + 1], a.y, ib.y);
+                v[j + 2] = snake_beta<false>(v[j + 2], a.z, ib.z);
+                v[j + 3] = snake_beta<false>(v[j + 3], a.w, ib.w);
+              } else {
+                v[j] = snake_beta<true>(v[j], a.x, ib.x);
+                v[j + 1] = snake_beta<true>(v[j + 1], a.y, ib.y);
+                v[j + 2] = snake_beta<true>(v[j + 2], a.z, ib.z);
+                v[j + 3] = snake_beta<true>(v[j + 3], a.w, ib.w);
+              }
             }
           }
           uint8_t* at = ablk + lane * 64;
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            uint32_t w[4];
+            uint32_t w[4], wl[4];
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
               __nv_bfloat162 h = __floats2bfloat162_rn(v[8 * j + 2 * q4], v[8 * j + 2 * q4 + 1]);
               w[q4] = *reinterpret_cast<uint32_t*>(&h);
+              if (p.act_split) {
+                const float2 hf = __bfloat1622float2(h);
+                __nv_bfloat162 l = __floats2bfloat162_rn(v[8 * j + 2 * q4] - hf.x, v[8 * j + 2 * q4 + 1] - hf.y);
+                wl[q4] = *reinterpret_cast<uint32_t*>(&l);
+              }
             }
             *reinterpret_cast<uint4*>(at + ((j ^ ((lane >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+            if (p.act_split)
+              *reinterpret_cast<uint4*>(at + kActBlkBytes + ((j ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(wl[0], wl[1], wl[2], wl[3]);
           }
         }
         }
@@ -466,7 +515,10 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           __syncwarp();
           if (lane == 0) {
             if (p.raw_mode == 1) ptx::tma_store_4d(&tmR, raw_ring + jr * rawblk, cbase, phi, r0, b);
-            if (p.act_mode == 1) ptx::tma_store_4d(&tmO, act_ring + ja * kActBlkBytes, cbase, phi, r0, b);
+            if (p.act_mode == 1) {
+              ptx::tma_store_4d(&tmO, ablk, cbase, phi, r0, b);
+              if (p.act_split) ptx::tma_store_4d(&tmO, ablk + kActBlkBytes, p.Cout + cbase, phi, r0, b);
+            }
             ptx::bulk_commit();   // (an empty group when only the skip block was consumed keeps the count uniform)
           }
           if (R > 0) jr = (jr + 1 == R) ? 0 : jr + 1;

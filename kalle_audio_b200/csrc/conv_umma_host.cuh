@@ -212,6 +212,10 @@ struct ConvEpilogue {
   const float* snake_a = nullptr;
   const float* snake_inv_b = nullptr;
   int stream_f16 = 0;     // persistent kernel only: residual and channels-last out_raw are fp16 instead of fp32
+  // fp32-mode arithmetic on the tensor cores (persistent kernel only, see ConvParams2::split3)
+  int split3 = 0;         // x is [B, T, 2*Cin] (hi | lo), wpacked is [K][Cout][2*Cin]
+  int act_split = 0;      // out_act is [B, T, 2*Cout] (hi | lo)
+  int precise = 0;        // sinf instead of MUFU sin in the fused SnakeBeta
 };
 
 struct ConvTuning {
@@ -343,9 +347,13 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
   p.raw_mode = ep.out_raw ? (ep.out_raw_cf ? 2 : 1) : 0;
   p.act_mode = ep.out_act ? 1 : 0;
   p.raw_f16 = ep.stream_f16 ? 1 : 0;
+  p.split3 = ep.split3 ? 1 : 0;
+  p.act_split = (ep.act_split && ep.out_act) ? 1 : 0;
+  p.precise = ep.precise ? 1 : 0;
+  p.Cin = g.Cin;
   const int sdt = ep.stream_f16 ? 2 : 1;     // element type of the stream tensor maps
-  const size_t stage = 8 * static_cast<size_t>(conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode,
-                                                                                ep.residual != nullptr, p.raw_f16));
+  const size_t stage = 8 * static_cast<size_t>(conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, ep.residual != nullptr,
+                                                                                p.raw_f16, p.act_split));
   const size_t budget = 227 * 1024 - 2048 - stage;
   // candidate tilings, best first: double-buffered accumulators when they fit the 512 TMEM columns
   struct Cand { int MT, NT, acc; };
@@ -415,11 +423,14 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
   p.out_cf_f32 = ep.out_raw_f32;
   p.snake_a = ep.snake_a;
   p.snake_inv_b = ep.snake_inv_b;
-  if (!make_act_tmap(&L.tmA, x, B, T_in, g.Cin, tp.P_in, p.RB, err)) return false;
-  if (!make_w_tmap(&L.tmW, wpacked, g.K, g.Cout, g.Cin, p.NT, err)) return false;
+  const int kmul = p.split3 ? 2 : 1;
+  if (!make_act_tmap(&L.tmA, x, B, T_in, g.Cin * kmul, tp.P_in, p.RB, err)) return false;
+  if (!make_w_tmap(&L.tmW, wpacked, g.K, g.Cout, g.Cin * kmul, p.NT, err)) return false;
   if (p.raw_mode == 1) { if (!make_out_tmap(&L.tmR, ep.out_raw, B, T_out, g.Cout, tp.P_out, sdt, err)) return false; }
   else L.tmR = L.tmA;
-  if (p.act_mode == 1) { if (!make_out_tmap(&L.tmO, ep.out_act, B, T_out, g.Cout, tp.P_out, false, err)) return false; }
+  if (p.act_mode == 1) {
+    if (!make_out_tmap(&L.tmO, ep.out_act, B, T_out, g.Cout * (p.act_split ? 2 : 1), tp.P_out, false, err)) return false;
+  }
   else L.tmO = L.tmA;
   if (ep.residual) { if (!make_out_tmap(&L.tmX, ep.residual, B, T_out, g.Cout, tp.P_out, sdt, err)) return false; }
   else L.tmX = L.tmA;

@@ -53,7 +53,8 @@ __global__ void snake_params_kernel(const float* alpha, const float* beta, int l
 
 // ---------------------------------------------------------------- [B, C, T] -> [B, T, C] bf16
 // 32x32 shared-memory tile transpose.  grid: (ceil(T/32), ceil(C/32), B), block (32, 8)
-__global__ void cf_to_cl_bf16_kernel(const void* x, int f32, __nv_bfloat16* y, int C, int T) {
+// split = 1: y is [B, T, 2C] with the bf16 (hi | lo) halves of the fp32 value (fp32-mode tensor-core operand)
+__global__ void cf_to_cl_bf16_kernel(const void* x, int f32, __nv_bfloat16* y, int C, int T, int split) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -64,7 +65,31 @@ __global__ void cf_to_cl_bf16_kernel(const void* x, int f32, __nv_bfloat16* y, i
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += 8) {
     const int t = t0 + i, c = c0 + threadIdx.x;
-    if (c < C && t < T) y[(static_cast<size_t>(b) * T + t) * C + c] = __float2bfloat16(tile[threadIdx.x][i]);
+    if (c < C && t < T) {
+      const float v = tile[threadIdx.x][i];
+      const __nv_bfloat16 hi = __float2bfloat16(v);
+      if (split) {
+        y[(static_cast<size_t>(b) * T + t) * 2 * C + c] = hi;
+        y[(static_cast<size_t>(b) * T + t) * 2 * C + C + c] = __float2bfloat16(v - __bfloat162float(hi));
+      } else {
+        y[(static_cast<size_t>(b) * T + t) * C + c] = hi;
+      }
+    }
+  }
+}
+
+// fp32-mode tensor-core weights: w_direct [K][Cin][Cout] fp32 -> [K][Cout][2*Cin] bf16, (hi | lo) halves per row
+__global__ void split_pack_kernel(const float* w_direct, int K, int Cin, int Cout, __nv_bfloat16* w_split) {
+  const size_t n = static_cast<size_t>(K) * Cin * Cout;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    const int ci = static_cast<int>(i % Cin);
+    const size_t r = i / Cin;                       // k*Cout + co
+    const int co = static_cast<int>(r % Cout), k = static_cast<int>(r / Cout);
+    const float v = w_direct[(static_cast<size_t>(k) * Cin + ci) * Cout + co];
+    const __nv_bfloat16 hi = __float2bfloat16(v);
+    w_split[r * 2 * Cin + ci] = hi;
+    w_split[r * 2 * Cin + Cin + ci] = __float2bfloat16(v - __bfloat162float(hi));
   }
 }
 

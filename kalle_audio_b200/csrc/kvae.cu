@@ -64,8 +64,9 @@ struct DeviceGuard {
 struct ConvLayer {
   ConvGeom g;
   bool has_bias = true;
-  bool umma = false;
-  __nv_bfloat16* w_umma = nullptr;    // [K][Cout][Cin] bf16: forward tensor-core operand
+  bool umma = false;                  // bf16 mode: tensor-core layer (forward, dgrad, wgrad)
+  bool umma32 = false;                // fp32 mode, inference only: tensor-core layer through the bf16x3 split
+  __nv_bfloat16* w_umma = nullptr;    // [K][Cout][Cin] bf16: forward tensor-core operand ([K][Cout][2*Cin] hi|lo with umma32)
   float* w_direct = nullptr;          // [K][Cin][Cout] fp32: forward CUDA-core operand
   // training only (allocated by kvae_plan_load_params(train = 1)): the data-gradient kernels see the same
   // weight tensor under the opposite kind (Cin <-> Cout), i.e. the other index order of each precision
@@ -196,11 +197,17 @@ namespace {
 
 int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+bool env_flag(const char* name) {
+  const char* e = getenv(name);
+  return e && e[0] == '1';
+}
+
 void add_conv(kvae_plan* p, int kind, int Cin, int Cout, int K, int stride, int dil, int pad, bool bias) {
   ConvLayer c;
   c.g = ConvGeom{kind, Cin, Cout, K, stride, dil, pad};
   c.has_bias = bias;
   c.umma = (p->precision == KVAE_PREC_BF16) && umma_supported(c.g);
+  c.umma32 = (p->precision == KVAE_PREC_F32) && umma_supported(c.g) && !env_flag("KVAE_F32_CUDA_CORES");
   p->convs.push_back(c);
 }
 int add_snake(kvae_plan* p, int C) {
@@ -295,6 +302,8 @@ void build_encoder(kvae_plan* p) {
   p->ratio = den;
 }
 
+bool conv_tc(const ConvLayer& c, bool train) { return c.umma || (!train && c.umma32); }
+
 bool k7same_geom(const ConvGeom& g) {
   return g.kind == kConv && g.K == 7 && g.stride == 1 && g.dilation == 1 && g.pad == 3;
 }
@@ -313,11 +322,6 @@ bool is_wave_in_step(const kvae_plan* p, const std::vector<Step>& steps, int k) 
   return !c.umma && p->precision == KVAE_PREC_BF16 && k7same_geom(c.g) && k == 0 && n > 1 && c.g.Cin <= 2 && c.has_bias &&
          c.g.Cout % 128 == 0 && s.pre_snake < 0 && s.residual_from < 0;
 }
-bool env_flag(const char* name) {
-  const char* e = getenv(name);
-  return e && e[0] == '1';
-}
-
 void finalize_steps(kvae_plan* p) {
   const int n = static_cast<int>(p->steps.size());
   // fp16 residual stream: only when every step runs on a kernel that knows about it (tensor-core convs and the
@@ -327,19 +331,23 @@ void finalize_steps(kvae_plan* p) {
   for (int k = 0; k < n && p->stream_f16; ++k)
     if (!p->convs[p->steps[k].conv].umma && !is_wave_in_step(p, p->steps, k) && !is_wave_out_step(p, p->steps, k))
       p->stream_f16 = false;
-  for (int k = 0; k < n; ++k) {
-    Step& s = p->steps[k];
-    const bool last = (k == n - 1);
-    const bool next_umma = !last && p->convs[p->steps[k + 1].conv].umma;
-    s.needs_act = next_umma;
-    s.epi_snake = next_umma ? p->steps[k + 1].pre_snake : -1;
-    s.needs_raw = last || (!last && !next_umma);
-    for (int j = k + 1; j < n; ++j)
-      if (p->steps[j].residual_from == k) s.needs_raw = true;
-  }
-  // training plan: same chain, every pre-activation stream kept, no ResidualUnit fusion
-  p->tsteps = p->steps;
-  for (Step& s : p->tsteps) s.needs_raw = true;
+  // a conv is a tensor-core step in bf16 mode (always) or in fp32 mode for inference (bf16x3 split); fp32-mode
+  // training stays on the CUDA cores, so the two step lists can differ in who needs which tensor
+  auto set_flags = [&](std::vector<Step>& steps, bool train) {
+    for (int k = 0; k < n; ++k) {
+      Step& s = steps[k];
+      const bool last = (k == n - 1);
+      const bool next_tc = !last && conv_tc(p->convs[steps[k + 1].conv], train);
+      s.needs_act = next_tc;
+      s.epi_snake = next_tc ? steps[k + 1].pre_snake : -1;
+      s.needs_raw = train || last || (!last && !next_tc);
+      for (int j = k + 1; j < n; ++j)
+        if (steps[j].residual_from == k) s.needs_raw = true;
+    }
+  };
+  p->tsteps = p->steps;       // training plan: same chain, every pre-activation stream kept, no ResidualUnit fusion
+  set_flags(p->steps, false);
+  set_flags(p->tsteps, true);
   // flat parameter layout = module.parameters() order: per step [alpha, beta of its SnakeBeta] then the
   // conv's [bias][weight_g][weight_v] (old-style weight_norm keeps bias first)
   long long off = 0;
@@ -390,8 +398,9 @@ bool make_layout(const kvae_plan* p, const std::vector<Step>& steps, bool train,
   const int n = static_cast<int>(steps.size());
   L.t.assign(1 + 2 * n, Tensor());
   const ConvLayer& c0 = p->convs[steps[0].conv];
-  if (c0.umma) {
-    L.t[0].bytes = static_cast<size_t>(B) * T * c0.g.Cin * 2;
+  const int split = (p->precision == KVAE_PREC_F32 && !train) ? 2 : 1;   // operand tensors hold (hi | lo) halves
+  if (conv_tc(c0, train)) {
+    L.t[0].bytes = static_cast<size_t>(B) * T * c0.g.Cin * 2 * split;
     L.t[0].first = 0;
     L.t[0].last = 0;
   }
@@ -413,7 +422,7 @@ bool make_layout(const kvae_plan* p, const std::vector<Step>& steps, bool train,
     }
     if (s.needs_act && s.fuse != 1) {   // the fused ResidualUnit keeps its intermediate in shared memory
       Tensor& t = L.t[2 + 2 * k];
-      t.bytes = static_cast<size_t>(B) * len * c.g.Cout * 2;
+      t.bytes = static_cast<size_t>(B) * len * c.g.Cout * 2 * split;
       t.first = k;
       t.last = train ? (1 << 30) : k + 1;
     }
@@ -568,7 +577,7 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
       R.kind[k] = 2;
       continue;
     }
-    if (c.umma) {
+    if (conv_tc(c, train)) {
       R.kind[k] = 0;
       const void* in = (k == 0) ? tptr(0) : tptr(2 + 2 * (k - 1));
       if (!in) { err = "internal: tensor-core operand missing"; return false; }
@@ -585,6 +594,12 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
       if (s.epi_snake >= 0) {
         ep.snake_a = p->snakes[s.epi_snake].a;
         ep.snake_inv_b = p->snakes[s.epi_snake].inv_b;
+      }
+      if (!c.umma) {               // fp32 mode on the tensor cores: bf16x3 split operands, sinf in the epilogue
+        if (R.use_v1) { err = "KVAE_CONV_V1 has no fp32-mode tensor-core path"; return false; }
+        ep.split3 = 1;
+        ep.act_split = 1;
+        ep.precise = 1;
       }
       if (R.use_v1) {
         ConvTuning tune;
@@ -649,6 +664,7 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
         d.o_sC = 1;
       }
       d.out_act = static_cast<__nv_bfloat16*>(act);
+      d.act_split = (act && p->precision == KVAE_PREC_F32 && !train) ? 1 : 0;
       if (s.epi_snake >= 0) {
         d.snake_a = p->snakes[s.epi_snake].a;
         d.snake_inv_b = p->snakes[s.epi_snake].inv_b;
@@ -738,11 +754,11 @@ int run_plan(kvae_plan* p, bool train, const void* in, int in_dtype, void* out, 
   if (R.total > 1024 && !ws) return fail("null workspace");
   // boundary layout change for a tensor-core first layer
   const ConvLayer& c0 = p->convs[steps[0].conv];
-  if (c0.umma) {
+  if (conv_tc(c0, train)) {
     dim3 grid(ceil_div(static_cast<int>(T), 32), ceil_div(c0.g.Cin, 32), B), block(32, 8);
     cf_to_cl_bf16_kernel<<<grid, block, 0, st>>>(in, in_dtype == KVAE_F32,
                                                  reinterpret_cast<__nv_bfloat16*>(static_cast<uint8_t*>(ws) + R.layout.t[0].offset),
-                                                 c0.g.Cin, static_cast<int>(T));
+                                                 c0.g.Cin, static_cast<int>(T), c0.umma ? 0 : 1);
     KV_CUDA(cudaGetLastError());
     ++g_launches;
   }
@@ -790,14 +806,14 @@ int run_plan(kvae_plan* p, bool train, const void* in, int in_dtype, void* out, 
       w.x = in;
       w.x_f32 = (in_dtype == KVAE_F32);
       KV_CUDA(launch_wave_in(w, c.g.Cin, B, st));
-    } else if (c.umma && !R.use_v1) {
+    } else if (R.kind[k] == 0 && !R.use_v1) {
       ConvLaunch2& L = R.umma2[k];
       if (k == n - 1) {
         L.p.out_cf = out;
         L.p.out_cf_f32 = (out_dtype == KVAE_F32);
       }
       KV_CUDA(launch_conv_umma2(L, st));
-    } else if (c.umma) {
+    } else if (R.kind[k] == 0) {
       ConvLaunch& L = R.umma[k];
       if (k == n - 1) {
         L.p.out_raw = out;
@@ -1223,7 +1239,7 @@ int kvae_plan_create(const kvae_arch* arch, int direction, int precision, int de
   if (direction == KVAE_DECODER) build_decoder(p.get());
   else build_encoder(p.get());
   finalize_steps(p.get());
-  if (direction == KVAE_DECODER && arch->final_tanh && p->convs.back().umma)
+  if (direction == KVAE_DECODER && arch->final_tanh && (p->convs.back().umma || p->convs.back().umma32))
     return fail("final_tanh with a tensor-core output conv is not supported");
   DeviceGuard guard(device);
   if (!guard.ok) return fail("cannot select device");
@@ -1231,6 +1247,7 @@ int kvae_plan_create(const kvae_arch* arch, int direction, int precision, int de
     const size_t n = static_cast<size_t>(c.g.Cin) * c.g.Cout * c.g.K;
     if (c.umma) KV_CUDA(cudaMalloc(&c.w_umma, n * 2));
     else KV_CUDA(cudaMalloc(&c.w_direct, n * 4));
+    if (c.umma32) KV_CUDA(cudaMalloc(&c.w_umma, n * 2 * 2));      // (hi | lo) halves
     if (c.has_bias) KV_CUDA(cudaMalloc(&c.bias, c.g.Cout * 4));
   }
   for (SnakeLayer& s : p->snakes) {
@@ -1288,8 +1305,13 @@ int kvae_plan_set_conv(kvae_plan* p, int idx, const float* w, const float* bias,
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t n = static_cast<size_t>(c.g.Cin) * c.g.Cout * c.g.K;
   const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 4096));
-  pack_weights_kernel<<<blocks, 256, 0, st>>>(w, c.g.kind == kConvT, c.g.Cout, c.g.Cin, c.g.K, c.w_umma, c.w_direct);
+  pack_weights_kernel<<<blocks, 256, 0, st>>>(w, c.g.kind == kConvT, c.g.Cout, c.g.Cin, c.g.K, c.umma ? c.w_umma : nullptr,
+                                              c.w_direct);
   KV_CUDA(cudaGetLastError());
+  if (c.umma32) {
+    split_pack_kernel<<<blocks, 256, 0, st>>>(c.w_direct, c.g.K, c.g.Cin, c.g.Cout, c.w_umma);
+    KV_CUDA(cudaGetLastError());
+  }
   if (bias) KV_CUDA(cudaMemcpyAsync(c.bias, bias, c.g.Cout * 4, cudaMemcpyDeviceToDevice, st));
   c.set = true;
   return 0;
@@ -1374,7 +1396,7 @@ int kvae_plan_step_profile(kvae_plan* p, float* ms, double* flops, int* tensor_c
   for (int k = 0; k < n; ++k) {
     KV_CUDA(cudaEventElapsedTime(&ms[k], p->events[k], p->events[k + 1]));
     flops[k] = step_flops(p, k, p->prof_B, p->prof_T);
-    tensor_core[k] = p->convs[p->steps[k].conv].umma ? 1 : 0;
+    tensor_core[k] = conv_tc(p->convs[p->steps[k].conv], false) ? 1 : 0;
   }
   return n;
 }
@@ -1559,13 +1581,18 @@ int kvae_plan_load_params(kvae_plan* p, const float* params, int logscale, int t
     // index order A = [K][Cout][Cin]: forward tensor-core operand / CUDA-core dgrad operand;
     // index order B = [K][Cin][Cout]: forward CUDA-core operand / tensor-core dgrad operand
     if (c.g.kind == kConv)   // R = Cout, Cc = Cin: out1 = A, out2 = B
-      fold_pack_kernel<<<grid, 256, 0, st>>>(params + c.off_v, p->scale_scratch, R, Cc, c.g.K, c.w_umma,
+      fold_pack_kernel<<<grid, 256, 0, st>>>(params + c.off_v, p->scale_scratch, R, Cc, c.g.K, c.umma ? c.w_umma : nullptr,
                                              train ? c.w_direct_d : nullptr, train ? c.w_umma_d : nullptr, c.w_direct);
     else                     // R = Cin, Cc = Cout: out1 = B, out2 = A
       fold_pack_kernel<<<grid, 256, 0, st>>>(params + c.off_v, p->scale_scratch, R, Cc, c.g.K,
-                                             train ? c.w_umma_d : nullptr, c.w_direct, c.w_umma,
+                                             train ? c.w_umma_d : nullptr, c.w_direct, c.umma ? c.w_umma : nullptr,
                                              train ? c.w_direct_d : nullptr);
     KV_CUDA(cudaGetLastError());
+    if (c.umma32) {          // fp32-mode inference operand: (hi | lo) halves from the fp32 packing just written
+      const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 4096));
+      split_pack_kernel<<<blocks, 256, 0, st>>>(c.w_direct, c.g.K, c.g.Cin, c.g.Cout, c.w_umma);
+      KV_CUDA(cudaGetLastError());
+    }
     if (c.has_bias) KV_CUDA(cudaMemcpyAsync(c.bias, params + c.off_bias, c.g.Cout * 4, cudaMemcpyDeviceToDevice, st));
     c.set = true;
     g_launches += 2;

@@ -57,6 +57,13 @@ try:
     P(f"SAO encode bf16: max err {float(de.abs().max()):.3e} rms err {float(de.pow(2).mean().sqrt()):.3e} "
       f"ref absmax {float(np.abs(g['enc_out']).max()):.3f}")
     profile(m.decoder.runner(dev), lambda: m.decode(z), "SAO decode B=1 T=216 bf16")
+    m32 = H.build("sao", 0).to(dev).set_precision("fp32")
+    z4 = torch.randn(4, 64, 216, device=dev)
+    profile(m32.decoder.runner(dev), lambda: m32.decode(z4), "SAO decode B=4 T=216 fp32 mode B=8-style (bf16x3 split on tensor cores)")
+    y32 = m32.decode(z)
+    d32 = (y32[:, :, idx].cpu() - H.t(g["dec_out_at_idx"]))
+    P(f"SAO decode fp32 mode, full clip: max err {float(d32.abs().max()):.3e}")
+    del m32
     profile(m.encoder.runner(dev), lambda: m.encode(x), "SAO encode B=1 L=442368 bf16")
     zb = torch.randn(8, 64, 216, device=dev)
     profile(m.decoder.runner(dev), lambda: m.decode(zb), "SAO decode B=8 T=216 bf16")
