@@ -80,6 +80,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* h_full = a_full + 50;
   uint64_t* h_empty = a_full + 51;
   uint64_t* d2_full = a_full + 52;
+  uint64_t* d2h_full = a_full + 46;   // GEMM2 of half 0 has retired: rows 0..127 of D2 are final (EPI2 starts on them)
   uint64_t* d2_empty = a_full + 53;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 54);
   uint64_t* res_full = a_full + 56;   // [16 epilogue warps][2 slots]
@@ -107,6 +108,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::mbar_init(h_full, kRuEpiWarps);
     ptx::mbar_init(h_empty, 1);
     ptx::mbar_init(d2_full, 1);
+    ptx::mbar_init(d2h_full, 1);
     ptx::mbar_init(d2_empty, kRuEpiWarps);
     for (int i = 0; i < 2 * kRuEpiWarps; ++i) ptx::mbar_init(&res_full[i], 1);
     ptx::fence_mbar_init();
@@ -221,6 +223,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               ptx::umma_f16(dd, desc_hi | (w_lo[kc] + 2 * k), desc_hi | (hl + 2 * k), idesc2, (kc | k) ? 1u : 0u);
           }
           ptx::umma_commit(h_empty);
+          if (half == 0) ptx::umma_commit(d2h_full);
         }
         ptx::umma_commit(&b_empty[s0]);
         ptx::umma_commit(&b_empty[s1]);
@@ -297,12 +300,15 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(d1_empty);       // GEMM1 of the next tile may start: it runs under EPI2 below
       // ---- EPI2 share: D2 -> bias, + skip -> stream / operand out
-      ptx::mbar_wait_parked(d2_full, d2f_ph);
-      d2f_ph ^= 1u;
+      ptx::mbar_wait_parked(d2h_full, d2f_ph);           // rows 0..127 first: GEMM2 of half 1 may still be running
       ptx::tc_fence_after();
 #pragma unroll 1
       for (int item = sub; item < 16; item += 4) {
         const int r0 = q0 + item * 16;
+        if (item == sub + 8) {                             // rows 128..255
+          ptx::mbar_wait_parked(d2_full, d2f_ph);
+          ptx::tc_fence_after();
+        }
         if (lane == 0) {
           // every store issued so far has read its shared-memory source: the other stream slot and the operand
           // block are free again; fetch the NEXT item's skip block into the other slot
@@ -350,6 +356,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         slot ^= 1;
       }
+      d2f_ph ^= 1u;
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(d2_empty);
