@@ -271,25 +271,29 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       d1f_ph ^= 1u;
       ptx::tc_fence_after();
       for (int half = 0; half < 2; ++half) {
-        ptx::mbar_wait_parked(h_empty, he_ph ^ 1u);           // GEMM2 of the previous half has consumed h
-        he_ph ^= 1u;
         {
-          // this warp's two 16-row blocks of the half: both TMEM loads in flight before either is consumed
+          // this warp's two 16-row blocks of the half: both TMEM loads in flight, the arithmetic done in registers
+          // BEFORE waiting for the h buffer (GEMM2 of the previous half may still be reading it), then the stores
           uint32_t r0[16], r1[16];
           __syncwarp();
           const uint32_t t0 = d1 + (static_cast<uint32_t>(quad * 32) << 16) + half * 128 + sub * 16;
           ptx::tmem_ld_32x16(t0, r0);
           ptx::tmem_ld_32x16(t0 + 64, r1);
           ptx::tmem_ld_wait();
+          __nv_bfloat16 v0[16], v1[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float v = (p.dbg & 4) ? __uint_as_float(r0[j]) + bias7 : snake_beta<true>(__uint_as_float(r0[j]) + bias7, s2a, s2ib);
-            *reinterpret_cast<__nv_bfloat16*>(hb[j & 7] + (sub * 16 + j) * 128) = __float2bfloat16(v);
+            const float a = (p.dbg & 4) ? __uint_as_float(r0[j]) + bias7 : snake_beta<true>(__uint_as_float(r0[j]) + bias7, s2a, s2ib);
+            const float b = (p.dbg & 4) ? __uint_as_float(r1[j]) + bias7 : snake_beta<true>(__uint_as_float(r1[j]) + bias7, s2a, s2ib);
+            v0[j] = __float2bfloat16(a);
+            v1[j] = __float2bfloat16(b);
           }
+          ptx::mbar_wait_parked(h_empty, he_ph ^ 1u);      // GEMM2 of the previous half has consumed h
+          he_ph ^= 1u;
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float v = (p.dbg & 4) ? __uint_as_float(r1[j]) + bias7 : snake_beta<true>(__uint_as_float(r1[j]) + bias7, s2a, s2ib);
-            *reinterpret_cast<__nv_bfloat16*>(hb[j & 7] + ((sub + 4) * 16 + j) * 128) = __float2bfloat16(v);
+            *reinterpret_cast<__nv_bfloat16*>(hb[j & 7] + (sub * 16 + j) * 128) = v0[j];
+            *reinterpret_cast<__nv_bfloat16*>(hb[j & 7] + ((sub + 4) * 16 + j) * 128) = v1[j];
           }
         }
         ptx::fence_proxy_async();
