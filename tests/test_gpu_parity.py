@@ -428,3 +428,31 @@ def test_fp16_stream_saturates_instead_of_overflowing(dev):
     z = torch.randn(1, 64, 4, generator=torch.Generator().manual_seed(1)).to(dev)
     y = m.decode(z)
     assert bool(torch.isfinite(y).all())
+
+
+def test_full_size_properties_sao_bench_shape(dev):
+    """BASELINE configs[1] at its full size (16 clips x 10.03 s, bf16 mode), checked through size-independent
+    properties: batch items are independent (what batch sharding relies on), the decoder is time-invariant away
+    from the clip edges (what chunked / streaming decode relies on), and the encode -> decode round trip of a
+    batch equals the round trip of one of its clips alone."""
+    m = H.build("sao", 0).to(dev).set_precision("bf16")
+    z = torch.randn(16, 64, 216, generator=torch.Generator().manual_seed(1)).to(dev)
+    y = m.decode(z)
+    assert y.shape == (16, 2, 442368) and bool(torch.isfinite(y).all())
+    y3 = m.decode(z[3:4])
+    assert float((y[3:4] - y3).abs().max()) == 0.0                     # same tiles, same summation order
+    # time invariance: drop 8 latent frames on the left; 10 frames = the receptive field (StreamingDecoder)
+    ys = m.decode(z[:2, :, 8:])
+    lo, hi = (8 + 10) * 2048, (216 - 10) * 2048
+    d = float((y[:2, :, lo:hi] - ys[:, :, lo - 8 * 2048:hi - 8 * 2048]).abs().max())
+    assert d <= 2e-6 * max(1.0, float(y.abs().max())), d
+    x = (0.1 * torch.randn(16, 2, 442368, generator=torch.Generator().manual_seed(2))).to(dev)
+    e = m.encode(x)
+    assert e.shape == (16, 128, 216)
+    assert float((e[5:6] - m.encode(x[5:6])).abs().max()) == 0.0
+    # golden anchor at this size: clip 0 of the batch is the fixture's input (same seed), sampled points
+    g = H.golden("sao_full")
+    z0 = torch.randn(1, 64, 216, generator=torch.Generator().manual_seed(1))
+    if torch.equal(z0, z[:1].cpu()):
+        idx = H.t(g["dec_idx"]).long().to(dev)
+        assert maxerr(y[:1][:, :, idx], g["dec_out_at_idx"]) <= TOL_BF16
