@@ -79,6 +79,18 @@ __device__ __forceinline__ float snake_beta(float v, float a, float inv_b) {
   return fmaf(inv_b * s, s, v);
 }
 
+// fp32-mode SnakeBeta inside the tensor-core epilogues: sinf costs ~40 instructions per element in epilogues that are
+// issue-bound, so reduce the argument to [-pi, pi] with a two-constant Cody-Waite step (exact to ~1e-7 for |x| < 1e4)
+// and use the MUFU sine there, where its absolute error is ~4e-7 -- an order of magnitude inside the 1e-5 budget.
+__device__ __forceinline__ float snake_beta_rr(float v, float a, float inv_b) {
+  const float t = v * a;
+  const float k = rintf(t * 0.15915494309189535f);
+  float r = fmaf(k, -6.2831854820251465f, t);          // 2*pi rounded to fp32
+  r = fmaf(k, 1.7484555314695172e-7f, r);              // 2*pi - fp32(2*pi) = -1.7484555e-7, sign folded in
+  const float s = __sinf(r);
+  return fmaf(inv_b * s, s, v);
+}
+
 __global__ void __launch_bounds__(256, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ ConvParams p) {

@@ -381,7 +381,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (p.snake_a) {   // hoisted: a per-element test would put a branch between the 32 independent chains
               if (p.precise) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = snake_beta<false>(v[j], sa_s, sib_s);
+                for (int j = 0; j < 32; ++j) v[j] = snake_beta_rr(v[j], sa_s, sib_s);
               } else {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = snake_beta<true>(v[j], sa_s, sib_s);
@@ -477,10 +477,10 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               const float4 a = __ldg(reinterpret_cast<const float4*>(p.snake_a + cbase + j));
               const float4 ib = __ldg(reinterpret_cast<const float4*>(p.snake_inv_b + cbase + j));
               if (p.precise) {
-                v[j] = snake_beta<false>(v[j], a.x, ib.x);
-                v[j + 1] = snake_beta<false>(v[j + 1], a.y, ib.y);
-                v[j + 2] = snake_beta<false>(v[j + 2], a.z, ib.z);
-                v[j + 3] = snake_beta<false>(v[j + 3], a.w, ib.w);
+                v[j] = snake_beta_rr(v[j], a.x, ib.x);
+                v[j + 1] = snake_beta_rr(v[j + 1], a.y, ib.y);
+                v[j + 2] = snake_beta_rr(v[j + 2], a.z, ib.z);
+                v[j + 3] = snake_beta_rr(v[j + 3], a.w, ib.w);
               } else {
                 v[j] = snake_beta<true>(v[j], a.x, ib.x);
                 v[j + 1] = snake_beta<true>(v[j + 1], a.y, ib.y);
