@@ -29,6 +29,7 @@ struct WaveOutParams {
   int y_f32;
   int T, Cin, tanh_out;
   int B, tiles_per_clip, total_tiles;
+  int precise;            // fp32 mode: range-reduced sine (<= 1e-5 budget) instead of the plain MUFU approximation
 };
 
 constexpr int kWaveOutTile = 128;              // outputs per tile
@@ -110,10 +111,13 @@ __global__ void __launch_bounds__(288, 1) conv_wave_out_kernel(const WaveOutPara
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (t >= 0 && t < p.T) {
         v = *reinterpret_cast<const float4*>(tile_s + r * CIN);
-        v.x = snake_beta<true>(v.x, sa.x, sib.x);
-        v.y = snake_beta<true>(v.y, sa.y, sib.y);
-        v.z = snake_beta<true>(v.z, sa.z, sib.z);
-        v.w = snake_beta<true>(v.w, sa.w, sib.w);
+        if (p.precise) {
+          v.x = snake_beta_rr(v.x, sa.x, sib.x); v.y = snake_beta_rr(v.y, sa.y, sib.y);
+          v.z = snake_beta_rr(v.z, sa.z, sib.z); v.w = snake_beta_rr(v.w, sa.w, sib.w);
+        } else {
+          v.x = snake_beta<true>(v.x, sa.x, sib.x); v.y = snake_beta<true>(v.y, sa.y, sib.y);
+          v.z = snake_beta<true>(v.z, sa.z, sib.z); v.w = snake_beta<true>(v.w, sa.w, sib.w);
+        }
       }
       return v;
     };
@@ -410,6 +414,8 @@ struct WaveInParams {
   const float* bias;      // [Cout]
   void* out_raw;          // [B, T, Cout] fp32 (or fp16 when raw_f16) or nullptr
   int raw_f16;
+  int precise;            // fp32 mode: range-reduced sine
+  int act_split;          // fp32 mode: out_act is [B, T, 2*Cout], bf16 (hi | lo) halves for the tensor-core consumer
   __nv_bfloat16* out_act; // [B, T, Cout] bf16 or nullptr
   const float* snake_a;   // epilogue SnakeBeta of the first ResidualUnit (or nullptr: plain cast)
   const float* snake_inv_b;
@@ -470,12 +476,27 @@ __global__ void __launch_bounds__(128) conv_wave_in_kernel(const WaveInParams p)
     }
     if (p.out_act) {
       if (p.snake_a) {
-        v0 = snake_beta<true>(v0, sa.x, sib.x); v1 = snake_beta<true>(v1, sa.y, sib.y);
-        v2 = snake_beta<true>(v2, sa.z, sib.z); v3 = snake_beta<true>(v3, sa.w, sib.w);
+        if (p.precise) {
+          v0 = snake_beta_rr(v0, sa.x, sib.x); v1 = snake_beta_rr(v1, sa.y, sib.y);
+          v2 = snake_beta_rr(v2, sa.z, sib.z); v3 = snake_beta_rr(v3, sa.w, sib.w);
+        } else {
+          v0 = snake_beta<true>(v0, sa.x, sib.x); v1 = snake_beta<true>(v1, sa.y, sib.y);
+          v2 = snake_beta<true>(v2, sa.z, sib.z); v3 = snake_beta<true>(v3, sa.w, sib.w);
+        }
       }
       __nv_bfloat162 h0 = __floats2bfloat162_rn(v0, v1), h1 = __floats2bfloat162_rn(v2, v3);
-      *reinterpret_cast<uint2*>(p.out_act + o) =
-          make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      if (p.act_split) {
+        const size_t o2 = (static_cast<size_t>(b) * p.T + t) * 2 * p.Cout + co;
+        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+        __nv_bfloat162 l0 = __floats2bfloat162_rn(v0 - f0.x, v1 - f0.y), l1 = __floats2bfloat162_rn(v2 - f1.x, v3 - f1.y);
+        *reinterpret_cast<uint2*>(p.out_act + o2) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+        *reinterpret_cast<uint2*>(p.out_act + o2 + p.Cout) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&l0), *reinterpret_cast<uint32_t*>(&l1));
+      } else {
+        *reinterpret_cast<uint2*>(p.out_act + o) =
+            make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+      }
     }
   }
 }

@@ -312,14 +312,14 @@ bool is_wave_out_step(const kvae_plan* p, const std::vector<Step>& steps, int k)
   const int n = static_cast<int>(steps.size());
   const Step& s = steps[k];
   const ConvLayer& c = p->convs[s.conv];
-  return !c.umma && p->precision == KVAE_PREC_BF16 && k7same_geom(c.g) && k == n - 1 && k > 0 && c.g.Cout <= 2 &&
+  return !c.umma && !c.umma32 && k7same_geom(c.g) && k == n - 1 && k > 0 && c.g.Cout <= 2 &&
          !c.has_bias && c.g.Cin == 128 && s.pre_snake >= 0 && s.residual_from < 0;
 }
 bool is_wave_in_step(const kvae_plan* p, const std::vector<Step>& steps, int k) {
   const int n = static_cast<int>(steps.size());
   const Step& s = steps[k];
   const ConvLayer& c = p->convs[s.conv];
-  return !c.umma && p->precision == KVAE_PREC_BF16 && k7same_geom(c.g) && k == 0 && n > 1 && c.g.Cin <= 2 && c.has_bias &&
+  return !c.umma && !c.umma32 && k7same_geom(c.g) && k == 0 && n > 1 && c.g.Cin <= 2 && c.has_bias &&
          c.g.Cout % 128 == 0 && s.pre_snake < 0 && s.residual_from < 0;
 }
 void finalize_steps(kvae_plan* p) {
@@ -538,9 +538,10 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
       w.T = static_cast<int>(T_out);
       w.Cin = c.g.Cin;
       w.tanh_out = (p->direction == KVAE_DECODER && p->arch.final_tanh) ? 1 : 0;
+      w.precise = (p->precision == KVAE_PREC_F32) ? 1 : 0;
       R.kind[k] = 3;
       const char* cc = getenv("KVAE_WAVE_OUT_CC");     // development switch: the CUDA-core tail
-      if (!(cc && cc[0] == '1')) {
+      if (!(cc && cc[0] == '1') && p->precision == KVAE_PREC_BF16) {   // fp32 mode keeps the exact fp32 FMAs
         PreparedRun::WaveOutTc& t = R.wave_out_tc[k];
         std::memset(&t.p, 0, sizeof(t.p));
         t.p.pro_a = w.pro_a; t.p.pro_inv_b = w.pro_inv_b; t.p.w = w.w;
@@ -564,6 +565,8 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
       w.bias = c.bias;
       w.out_raw = raw;
       w.raw_f16 = sf16;
+      w.precise = (p->precision == KVAE_PREC_F32) ? 1 : 0;
+      w.act_split = (act && p->precision == KVAE_PREC_F32 && !train) ? 1 : 0;
       w.out_act = static_cast<__nv_bfloat16*>(act);
       if (s.epi_snake >= 0) {
         w.snake_a = p->snakes[s.epi_snake].a;
