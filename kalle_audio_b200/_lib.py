@@ -13,7 +13,8 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkvae.so")
+# KVAE_LIB: development override (A/B builds of the same sources); there is still no non-CUDA fallback
+LIB_PATH = os.environ.get("KVAE_LIB") or os.path.join(_HERE, "libkvae.so")
 
 KVAE_F32, KVAE_BF16 = 0, 1
 KVAE_ENCODER, KVAE_DECODER = 0, 1

@@ -46,6 +46,10 @@ struct RuParams {
   const float* sn_inv_b;
   int raw_f16;              // 1: residual stream (x in, x' out) is fp16 in HBM, 0: fp32
   int dbg;                  // ablation switches for tools/umma_probe (KVAE_RU_DBG); 0 in production
+  const void* a_ptr;        // conv_ru2_kernel: base addresses of the operand / stream tensors for L2 prefetch
+  const void* x_ptr;
+  int pf;                   // bit 0: prefetch the operand rows of the tile after next into L2, bit 1: its skip rows
+  int k0, k1;               // conv_ru2_kernel: GEMM2 half 0 / 1 of tile i goes in before slab k0 / k1 of tile i+1's GEMM1
 };
 
 constexpr int kRuC = 128;
@@ -59,10 +63,16 @@ constexpr int kRuEpiWarps = 16;
 // per epilogue warp: 2 fp16 stream blocks (skip in / stream out, in place) + 1 bf16 operand block
 __host__ __device__ inline int ru_stage_bytes_per_warp(int act_out) { return 2 * kRuActBlk + (act_out ? kRuActBlk : 0); }
 __host__ __device__ inline size_t ru_smem_bytes(const RuParams& p) {
+  // (dbg 131 = barrier-protocol-only epilogue without skip loads: the staging area is never touched, so ring-depth
+  // experiments may spend it on weight stages)
+  const size_t staging = (p.dbg & 131) == 131 ? 0 : kRuEpiWarps * ru_stage_bytes_per_warp(p.act_out);
   return 1024 + 1024 + static_cast<size_t>(p.SA) * p.nbox * p.RB * 128 + static_cast<size_t>(p.SB) * kRuC * 128 +
-         kRuHBytes + kRuEpiWarps * ru_stage_bytes_per_warp(p.act_out);
+         kRuHBytes + staging;
 }
 
+// kEpi selects the epilogue register mapping: 0 = one channel per thread (tcgen05.ld.32x32b, 2-byte shared-memory
+// accesses), 1 = mma-style fragments (tcgen05.ld.16x256b + ldmatrix/stmatrix.trans + packed fp32 pairs).
+template <int kEpi>
 __global__ void __launch_bounds__(kRuThreads, 1)
 conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW7,
                const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmR,
@@ -91,7 +101,7 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint8_t* h_buf = b_ring + static_cast<size_t>(p.SB) * b_bytes;
   uint8_t* stage_base = h_buf + kRuHBytes;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = ptx::warp_idx();
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -133,22 +143,34 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int q0 = (tile % p.q_tiles) * 256;
         for (int ch = 0; ch < 2; ++ch) {
           ptx::mbar_wait(&a_empty[as], aph ^ 1u);
-          ptx::mbar_expect_tx(&a_full[as], a_bytes);
-          for (int bx = 0; bx < p.nbox; ++bx)
-            ptx::tma_load_4d(a_ring + static_cast<size_t>(as) * a_bytes + bx * p.RB * 128, &tmA, &a_full[as], ch * 64, 0,
-                             q0 + p.slab_row0 + bx * p.RB, b);
+          if (p.dbg & 64) {                                  // ablation: no activation loads
+            ptx::mbar_arrive(&a_full[as]);
+          } else {
+            ptx::mbar_expect_tx(&a_full[as], a_bytes);
+            for (int bx = 0; bx < p.nbox; ++bx)
+              ptx::tma_load_4d(a_ring + static_cast<size_t>(as) * a_bytes + bx * p.RB * 128, &tmA, &a_full[as], ch * 64, 0,
+                               q0 + p.slab_row0 + bx * p.RB, b);
+          }
           if (++as == p.SA) { as = 0; aph ^= 1u; }
           for (int t = 0; t < 7; ++t) {
             ptx::mbar_wait(&b_empty[bs], bph ^ 1u);
-            ptx::mbar_expect_tx(&b_full[bs], b_bytes);
-            ptx::tma_load_3d(b_ring + static_cast<size_t>(bs) * b_bytes, &tmW7, &b_full[bs], ch * 64, 0, t);
+            if (p.dbg & 32) {                                // ablation: no weight loads
+              ptx::mbar_arrive(&b_full[bs]);
+            } else {
+              ptx::mbar_expect_tx(&b_full[bs], b_bytes);
+              ptx::tma_load_3d(b_ring + static_cast<size_t>(bs) * b_bytes, &tmW7, &b_full[bs], ch * 64, 0, t);
+            }
             if (++bs == p.SB) { bs = 0; bph ^= 1u; }
           }
         }
         for (int kc = 0; kc < 2; ++kc) {   // the k=1 conv's weights ride the same ring
           ptx::mbar_wait(&b_empty[bs], bph ^ 1u);
-          ptx::mbar_expect_tx(&b_full[bs], b_bytes);
-          ptx::tma_load_3d(b_ring + static_cast<size_t>(bs) * b_bytes, &tmW1, &b_full[bs], kc * 64, 0, 0);
+          if (p.dbg & 32) {
+            ptx::mbar_arrive(&b_full[bs]);
+          } else {
+            ptx::mbar_expect_tx(&b_full[bs], b_bytes);
+            ptx::tma_load_3d(b_ring + static_cast<size_t>(bs) * b_bytes, &tmW1, &b_full[bs], kc * 64, 0, 0);
+          }
           if (++bs == p.SB) { bs = 0; bph ^= 1u; }
         }
       }
@@ -230,8 +252,187 @@ conv_ru_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::umma_commit(d2_full);
       }
     }
+  } else if (warp >= 4 && kEpi == 1) {
+    // ------------------------------------------------------------ epilogue warps, fragment mapping (see ptx.cuh,
+    // tmem_ld_16x256b_*): a thread holds (time, time+1) PAIRS of one channel, so bias / SnakeBeta run as packed
+    // fp32 pairs, a converted pair is one stmatrix.trans register, and the [time][channel] tiles in shared memory
+    // are read and written as 16-byte rows (ldmatrix / stmatrix) instead of one 2-byte access per element.
+    const int e = warp - 4;                            // 0..15
+    const int quad = warp & 3;                         // TMEM lane quadrant = channels quad*32 .. +31
+    const int sub = e >> 2;                            // 0..3
+    const int g = lane >> 2;                           // fragment row: channel within a group of 8
+    const int rr = lane & 7, mj = lane >> 3;           // ldmatrix/stmatrix: this lane addresses row rr of matrix mj
+    const int cbase = quad * 32;
+    auto dup = [](float f) { return ptx::f2_pack(f, f); };
+    // EPI1 share of a 128-column half: 16 channels (lane half hl) x 64 time columns (block cb)
+    const int hl = sub & 1, cb = sub >> 1;
+    const int c1 = cbase + hl * 16 + g;                // this thread's EPI1 channels: c1 and c1 + 8
+    const uint32_t d1_lane = d1 + (static_cast<uint32_t>(cbase + hl * 16) << 16) + cb * 64;
+    const int hch = cbase + hl * 16 + (mj & 1) * 8;    // first channel of the 8-channel group of matrix mj
+    const uint32_t h_lane = ptx::smem_u32(h_buf) + (hch >> 6) * 16384 + (cb * 64 + (mj >> 1) * 8 + rr) * 128 +
+                            ((((hch & 63) >> 3) ^ rr) << 4);
+    // EPI2 staging: fp16 stream blocks [16 rows x 64 B] and the bf16 operand block, SWIZZLE_64B; lane half 1 = ^ 32
+    uint8_t* ring = stage_base + e * ru_stage_bytes_per_warp(p.act_out);
+    const int brow = (mj >> 1) * 8 + rr;
+    const uint32_t blk_lane = brow * 64 + (((mj & 1) ^ ((brow >> 1) & 3)) << 4);
+    const uint32_t ring_lane = ptx::smem_u32(ring) + blk_lane;
+    const uint32_t ablk_lane = ring_lane + 2 * kRuActBlk;
+    uint8_t* ablk = ring + 2 * kRuActBlk;
+    uint64_t* my_res_full = res_full + e * 2;
+    const bool use_skip = !(p.dbg & 1);
+    const bool has_snake = p.sn_a != nullptr;
+    auto issue_skip = [&](int tb, int tq0, int item, int slot) {   // lane 0 only; (tb, tq0) = clip, first row of the tile
+      ptx::mbar_expect_tx(&my_res_full[slot], kRuActBlk);
+      ptx::tma_load_4d(ring + slot * kRuActBlk, &tmX, &my_res_full[slot], cbase, 0, tq0 + item * 16, tb);
+    };
+    if (lane == 0 && use_skip && static_cast<int>(blockIdx.x) < p.total_tiles)
+      issue_skip(blockIdx.x / p.q_tiles, (blockIdx.x % p.q_tiles) * 256, sub, 0);
+    int slot = 0;
+    uint32_t d1f_ph = 0, he_ph = 0, d2f_ph = 0, res_ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      const int b = tile / p.q_tiles;
+      const int q0 = (tile % p.q_tiles) * 256;
+      const int ntile = tile + gridDim.x;                // this CTA's next tile (its first skip block is prefetched below)
+      const int nb = ntile / p.q_tiles, nq0 = (ntile % p.q_tiles) * 256;
+      // ---- EPI1 share: D1 -> bias, SnakeBeta -> h
+      {
+        const uint64_t kb[2] = {dup(__ldg(p.bias7 + c1)), dup(__ldg(p.bias7 + c1 + 8))};
+        const uint64_t ka[2] = {dup(__ldg(p.s2_a + c1)), dup(__ldg(p.s2_a + c1 + 8))};
+        const uint64_t kib[2] = {dup(__ldg(p.s2_inv_b + c1)), dup(__ldg(p.s2_inv_b + c1 + 8))};
+        ptx::mbar_wait_parked(d1_full, d1f_ph);
+        d1f_ph ^= 1u;
+        ptx::tc_fence_after();
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r[32], pk[16];
+          __syncwarp();
+          if (!(p.dbg & 128)) {
+          ptx::tmem_ld_16x256b_x8(d1_lane + half * 128, r);
+          ptx::tmem_ld_wait();
+          }
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            if (p.dbg & 128) { pk[q] = 0u; continue; }       // ablation: barrier protocol only                 // q = 2n + hi: column group n, channel c1 + 8 hi
+            const uint64_t v = ptx::f2_add(ptx::f2_pack_u(r[2 * q], r[2 * q + 1]), kb[q & 1]);
+            float t0, t1, y0, y1;
+            ptx::f2_unpack(ptx::f2_mul(v, ka[q & 1]), t0, t1);
+            const uint64_t sn = ptx::f2_pack(sin_fast(t0), sin_fast(t1));
+            ptx::f2_unpack(ptx::f2_fma(ptx::f2_mul(kib[q & 1], sn), sn, v), y0, y1);
+            const __nv_bfloat162 hb2 = __floats2bfloat162_rn(y0, y1);
+            pk[q] = *reinterpret_cast<const uint32_t*>(&hb2);
+          }
+          ptx::mbar_wait_parked(h_empty, he_ph ^ 1u);      // GEMM2 of the previous half has consumed h
+          he_ph ^= 1u;
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+            if (!(p.dbg & 128)) ptx::stmatrix_x4_trans(h_lane + m * 2048, pk[4 * m], pk[4 * m + 1], pk[4 * m + 2], pk[4 * m + 3]);
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(h_full);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(d1_empty);       // GEMM1 of the next tile may start: it runs under EPI2 below
+      // ---- EPI2 share: D2 -> bias, + skip -> stream / operand out
+      uint64_t kb[4], ka[4], kib[4];                     // index 2 * lane half + hi: channel cbase + 16 L + 8 hi + g
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ch = cbase + (i >> 1) * 16 + (i & 1) * 8 + g;
+        kb[i] = dup(__ldg(p.bias1 + ch));
+        ka[i] = has_snake ? dup(__ldg(p.sn_a + ch)) : 0ull;
+        kib[i] = has_snake ? dup(__ldg(p.sn_inv_b + ch)) : 0ull;
+      }
+      ptx::mbar_wait_parked(d2h_full, d2f_ph);           // rows 0..127 first: GEMM2 of half 1 may still be running
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int item = sub; item < 16; item += 4) {
+        const int r0 = q0 + item * 16;
+        if (item == sub + 8) {                             // rows 128..255
+          ptx::mbar_wait_parked(d2_full, d2f_ph);
+          ptx::tc_fence_after();
+        }
+        if (lane == 0) {
+          // every store issued so far has read its shared-memory source: the other stream slot and the operand
+          // block are free again; fetch the NEXT item's skip block into the other slot
+          ptx::bulk_wait_read<0>();
+          if (use_skip) {
+            if (item + 4 < 16) issue_skip(b, q0, item + 4, slot ^ 1);
+            else if (ntile < p.total_tiles) issue_skip(nb, nq0, sub, slot ^ 1);
+          }
+        }
+        if (p.dbg & 128) { if (use_skip) ptx::mbar_wait_parked(&my_res_full[slot], (res_ph >> slot) & 1u); res_ph ^= (1u << slot); slot ^= 1; continue; }
+        uint32_t r[16], sk[8];
+        __syncwarp();
+        const uint32_t t2 = d2 + (static_cast<uint32_t>(cbase) << 16) + item * 16;
+        ptx::tmem_ld_16x256b_x2(t2, r);
+        ptx::tmem_ld_16x256b_x2(t2 + (16u << 16), r + 8);
+        const uint32_t rb = ring_lane + slot * kRuActBlk;
+        if (use_skip) {
+          ptx::mbar_wait_parked(&my_res_full[slot], (res_ph >> slot) & 1u);
+          ptx::ldmatrix_x4_trans(rb, sk[0], sk[1], sk[2], sk[3]);
+          ptx::ldmatrix_x4_trans(rb ^ 32u, sk[4], sk[5], sk[6], sk[7]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) sk[q] = 0u;
+        }
+        res_ph ^= (1u << slot);
+        ptx::tmem_ld_wait();
+        uint64_t v[8];                                     // q = 4 L + 2 n + hi
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float2 sf = __half22float2(*reinterpret_cast<const __half2*>(&sk[q]));
+          v[q] = ptx::f2_add(ptx::f2_add(ptx::f2_pack_u(r[2 * q], r[2 * q + 1]), kb[(q >> 2) * 2 + (q & 1)]),
+                             ptx::f2_pack(sf.x, sf.y));
+        }
+        if (p.raw_out) {
+          uint32_t w[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float y0, y1;
+            ptx::f2_unpack(v[q], y0, y1);
+            w[q] = ptx::f2h2_sat(y0, y1);
+          }
+          ptx::stmatrix_x4_trans(rb, w[0], w[1], w[2], w[3]);
+          ptx::stmatrix_x4_trans(rb ^ 32u, w[4], w[5], w[6], w[7]);
+        }
+        if (p.act_out) {
+          uint32_t w[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float y0, y1;
+            if (has_snake) {
+              const int ci = (q >> 2) * 2 + (q & 1);
+              float t0, t1;
+              ptx::f2_unpack(ptx::f2_mul(v[q], ka[ci]), t0, t1);
+              const uint64_t sn = ptx::f2_pack(sin_fast(t0), sin_fast(t1));
+              ptx::f2_unpack(ptx::f2_fma(ptx::f2_mul(kib[ci], sn), sn, v[q]), y0, y1);
+            } else {
+              ptx::f2_unpack(v[q], y0, y1);
+            }
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
+            w[q] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+          ptx::stmatrix_x4_trans(ablk_lane, w[0], w[1], w[2], w[3]);
+          ptx::stmatrix_x4_trans(ablk_lane ^ 32u, w[4], w[5], w[6], w[7]);
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          uint8_t* const rblk = ring + slot * kRuActBlk;
+          if (p.raw_out && !(p.dbg & 2)) ptx::tma_store_4d(&tmR, rblk, cbase, 0, r0, b);
+          if (p.act_out && !(p.dbg & 2)) ptx::tma_store_4d(&tmO, ablk, cbase, 0, r0, b);
+          ptx::bulk_commit();
+        }
+        slot ^= 1;
+      }
+      d2f_ph ^= 1u;
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(d2_empty);
+    }
+    if (lane == 0) ptx::bulk_wait<0>();
   } else if (warp >= 4) {
-    // ------------------------------------------------------------ epilogue warps: EPI1 share, then EPI2 share, per tile
+    // ------------------------------------------------------------ epilogue warps (kEpi == 0): EPI1 share, then EPI2 share, per tile
     const int e = warp - 4;                            // 0..15
     const int quad = warp & 3;                         // TMEM lane quadrant = channels quad*32 .. +31
     const int sub = e >> 2;                            // 0..3: which blocks / items of the quadrant this warp takes

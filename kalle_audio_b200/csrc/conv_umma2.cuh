@@ -52,6 +52,7 @@ struct ConvParams2 {
   void* out_cf;            // raw_mode 2: [B, Cout, T_out]
   int out_cf_f32;
   int act_mode;            // 0 none, 1 bf16 channels-last via TMA (tmO)
+  int one_producer;        // 1: activation and weight slabs requested by one thread in one FIFO (A/B switch)
   int split3;              // fp32-mode arithmetic on the tensor cores: both operands are stored as bf16 (hi | lo)
                            // halves -- activations [.., 2*Cin], weights [tap][Cout][2*Cin] -- and every K chunk is
                            // multiplied three times: hi*hi + lo*hi + hi*lo (the lo*lo term is below fp32 rounding).
@@ -103,7 +104,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint8_t* b_ring = a_ring + static_cast<size_t>(p.SA) * a_bytes;
   uint8_t* stage_base = b_ring + static_cast<size_t>(p.SB) * b_bytes;
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = ptx::warp_idx();
   const int lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
@@ -143,11 +144,17 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     b = r / p.q_tiles;
   };
 
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
+  // Two TMA producer threads.  In ONE FIFO with the weight slabs an activation slab was requested only SB weight
+  // stages (about a microsecond) before its first MMA -- less than an HBM round trip -- although its ring stage had
+  // been free for much longer; on its own thread a slab is requested the moment its stage is released.
+  // KVAE_SPLIT_PRODUCER=0 (ConvParams2::one_producer) restores the single FIFO for A/B measurements.
+  if (warp == 0 || warp == 3) {
     if (ptx::elect_one()) {
+      const bool do_a = p.one_producer ? warp == 0 : warp == 3;
+      const bool do_w = warp == 0;
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
+      if (do_a || do_w)
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int b, q0, phi, n0;
         decode(tile, b, q0, phi, n0);
@@ -163,7 +170,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           for (int t = t_lo; t < t_hi; ++t) {
             const uint32_t tl = p.tap_ld[t];
-            if (p.tap_mma[t] & 0x10000u) {
+            if (do_a && (p.tap_mma[t] & 0x10000u)) {
               ptx::mbar_wait(&a_empty[as], aph ^ 1u);
               ptx::mbar_expect_tx(&a_full[as], a_bytes);
               const int row = q0 + (static_cast<int32_t>(tl) >> 16);
@@ -172,11 +179,13 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                                  a_col, tl & 0xff, row + bx * p.RB, b);
               if (++as == p.SA) { as = 0; aph ^= 1u; }
             }
-            ptx::mbar_wait(&b_empty[bs], bph ^ 1u);
-            ptx::mbar_expect_tx(&b_full[bs], b_bytes);
-            ptx::tma_load_3d(b_ring + static_cast<size_t>(bs) * b_bytes, &tmW, &b_full[bs], w_col, n0,
-                             (tl >> 8) & 0xff);
-            if (++bs == p.SB) { bs = 0; bph ^= 1u; }
+            if (do_w) {
+              ptx::mbar_wait(&b_empty[bs], bph ^ 1u);
+              ptx::mbar_expect_tx(&b_full[bs], b_bytes);
+              ptx::tma_load_3d(b_ring + static_cast<size_t>(bs) * b_bytes, &tmW, &b_full[bs], w_col, n0,
+                               (tl >> 8) & 0xff);
+              if (++bs == p.SB) { bs = 0; bph ^= 1u; }
+            }
           }
         }
       }

@@ -15,6 +15,7 @@
 #include "conv_umma.cuh"
 #include "conv_umma2.cuh"
 #include "conv_ru.cuh"
+#include "conv_ru2.cuh"
 #include "wgrad_umma.cuh"
 
 namespace kvae {
@@ -348,6 +349,7 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
   p.act_mode = ep.out_act ? 1 : 0;
   p.raw_f16 = ep.stream_f16 ? 1 : 0;
   p.split3 = ep.split3 ? 1 : 0;
+  if (const char* e = getenv("KVAE_SPLIT_PRODUCER")) p.one_producer = atoi(e) ? 0 : 1;
   p.act_split = (ep.act_split && ep.out_act) ? 1 : 0;
   p.precise = ep.precise ? 1 : 0;
   p.Cin = g.Cin;
@@ -503,11 +505,23 @@ inline bool prepare_conv_ru(const RuArgs& a, int B, int T, int dilation, RuLaunc
   p.SA = 2;
   if (2 * a_bytes + 3 * b_bytes > budget) { err = "fused RU does not fit shared memory"; return false; }
   p.SB = static_cast<int>(std::min<size_t>(8, (budget - 2 * a_bytes) / b_bytes));
+  if (const char* e = getenv("KVAE_RU_DBG")) p.dbg = atoi(e);
+  if (const char* e = getenv("KVAE_RU_SB")) {   // ring-depth experiments
+    const size_t cap = (227 * 1024 - 2048 - kRuHBytes - 2 * a_bytes - ((p.dbg & 131) == 131 ? 0 : kRuEpiWarps * static_cast<size_t>(ru_stage_bytes_per_warp(p.act_out)))) / b_bytes;
+    p.SB = static_cast<int>(std::max<size_t>(2, std::min<size_t>({static_cast<size_t>(atoi(e)), cap, static_cast<size_t>(16)})));
+  }
   p.q_tiles = (T + 255) / 256;
   p.total_tiles = p.q_tiles * B;
   p.bias7 = a.bias7; p.s2_a = a.s2_a; p.s2_inv_b = a.s2_inv_b; p.bias1 = a.bias1;
   p.sn_a = a.sn_a; p.sn_inv_b = a.sn_inv_b;
   if (const char* e = getenv("KVAE_RU_DBG")) p.dbg = atoi(e);
+  p.a_ptr = a.a; p.x_ptr = a.x;
+  p.pf = 0;
+  if (const char* e = getenv("KVAE_RU_PF")) p.pf = atoi(e);
+  p.k0 = 3; p.k1 = 6;
+  if (const char* e = getenv("KVAE_RU_K0")) p.k0 = atoi(e);
+  if (const char* e = getenv("KVAE_RU_K1")) p.k1 = atoi(e);
+  if (p.k0 < 0 || p.k1 <= p.k0 || p.k1 > 13) { err = "fused RU: need 0 <= k0 < k1 <= 13"; return false; }
   if (!make_act_tmap(&L.tmA, a.a, B, T, kRuC, 1, p.RB, err)) return false;
   if (!make_w_tmap(&L.tmW7, a.w7, 7, kRuC, kRuC, kRuC, err)) return false;
   if (!make_w_tmap(&L.tmW1, a.w1, 1, kRuC, kRuC, kRuC, err)) return false;
@@ -515,20 +529,33 @@ inline bool prepare_conv_ru(const RuArgs& a, int B, int T, int dilation, RuLaunc
   if (a.out_raw) { if (!make_out_tmap(&L.tmR, a.out_raw, B, T, kRuC, 1, sdt, err, 16)) return false; } else L.tmR = L.tmX;
   if (a.out_act) { if (!make_out_tmap(&L.tmO, a.out_act, B, T, kRuC, 1, false, err, 16)) return false; } else L.tmO = L.tmX;
   L.grid = std::min(p.total_tiles, sm_count());
+  if (const char* e = getenv("KVAE_RU_GRID")) L.grid = std::max(1, std::min(L.grid, atoi(e)));   // tests: many tiles per CTA
   L.smem = ru_smem_bytes(p);
   return true;
 }
 
 inline cudaError_t launch_conv_ru(const RuLaunch& L, cudaStream_t stream) {
   static bool attr_set[64] = {false};
+  // KVAE_RU_EPI (A/B measurements): 0 = first-generation kernel, 1 = fragment-mapped epilogue on the serial
+  // GEMM1 -> EPI1 -> GEMM2 chain, 2 = conv_ru2_kernel (two accumulators, GEMM2 slotted into the next tile's GEMM1)
+  static const int epi = [] { const char* e = getenv("KVAE_RU_EPI"); return e ? atoi(e) : 2; }();
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_ru_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_ru_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(conv_ru_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(conv_ru2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
   }
-  conv_ru_kernel<<<L.grid, kRuThreads, L.smem, stream>>>(L.tmA, L.tmW7, L.tmW1, L.tmR, L.tmO, L.tmX, L.p);
+  if (epi == 2)
+    conv_ru2_kernel<<<L.grid, kRuThreads, L.smem, stream>>>(L.tmA, L.tmW7, L.tmW1, L.tmR, L.tmO, L.tmX, L.p);
+  else if (epi == 0)
+    conv_ru_kernel<0><<<L.grid, kRuThreads, L.smem, stream>>>(L.tmA, L.tmW7, L.tmW1, L.tmR, L.tmO, L.tmX, L.p);
+  else
+    conv_ru_kernel<1><<<L.grid, kRuThreads, L.smem, stream>>>(L.tmA, L.tmW7, L.tmW1, L.tmR, L.tmO, L.tmX, L.p);
   return cudaGetLastError();
 }
 
