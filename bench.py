@@ -16,7 +16,7 @@ The JSON line:
                decoded waveform inside the timed region
   decode_only  decode leg alone (the metric's name), same batch
   roofline     tensor-core roofline of the dominant kernel family (conv_umma2_kernel and its fused ResidualUnit
-               form conv_ru_kernel): algorithmic FLOPs of its
+               form conv_ru2_kernel): algorithmic FLOPs of its
                launches / their CUDA-event time, against MEASURED_PEAKS.json (sustained figure: the kernel is
                timed inside a long step)
   cpu_baseline oracle port of the reference arithmetic on the host cores, bounded sample (rank 0, N=1 only)
@@ -264,7 +264,7 @@ def run_cuda(args):
         tc_ms, tc_fl = sum(m for m, _ in tc), sum(f for _, f in tc)
         other_ms = sum(ms for ms, _, on_tc in prof if not on_tc)
         achieved = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-        # the single kernel that dominates the step: conv_ru_kernel (fused ResidualUnit of the 128-channel stages).
+        # the single kernel that dominates the step: conv_ru2_kernel (fused ResidualUnit of the 128-channel stages).
         # It moves 1024 B per output row against 2*128*128*8 FLOPs (256 FLOP/B, right at the machine balance), and its
         # epilogues are issue-bound; reported against the HBM roofline, with the tensor figure in `tflops`.
         ru = [(prof[i][0], prof[i][1]) for i in range(len(prof) - 1)
@@ -291,7 +291,7 @@ def run_cuda(args):
             "decode_only": {"value": world * audio_s_per_step * args.steps / (dec_ms * 1e-3), "unit": UNIT,
                             "ms_per_step": dec_ms / args.steps,
                             "tflops": dec_r.flops(B, CLIP_FRAMES) / (dec_ms / args.steps * 1e-3) / 1e12},
-            "roofline": {"bound": "tensor", "kernel": "conv_umma2_kernel + conv_ru_kernel (tcgen05 conv family)", "achieved": achieved,
+            "roofline": {"bound": "tensor", "kernel": "conv_umma2_kernel + conv_ru2_kernel (tcgen05 conv family)", "achieved": achieved,
                          "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": achieved / peaks["bf16_tflops_sustained"], "traffic": None,
                          "peak_source": peaks["source"] + " (sustained; burst %.1f)" % peaks["bf16_tflops"],
@@ -300,7 +300,7 @@ def run_cuda(args):
                          "whole_step_tflops": step_fl / (ms_per_step * 1e-3) / 1e12,
                          "whole_step_frac": step_fl / (ms_per_step * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"]},
             "roofline_dominant_kernel": {
-                "kernel": "conv_ru_kernel (one launch = one ResidualUnit of a 128-channel stage)", "bound": "hbm",
+                "kernel": "conv_ru2_kernel (one launch = one ResidualUnit of a 128-channel stage)", "bound": "hbm",
                 "achieved": ru_bytes / (ru_ms * 1e-3) / 1e9 if ru_ms > 0 else 0.0, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": (ru_bytes / (ru_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if ru_ms > 0 else 0.0,
                 "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write, scaled by rows)",
