@@ -462,6 +462,7 @@ struct RuLaunch {
   RuParams p;
   int grid = 0;
   size_t smem = 0;
+  int epi = 2;   // kernel: 2 = conv_ru2_kernel, 0 / 1 = conv_ru_kernel<0 / 1> (KVAE_RU_EPI, read when the launch is prepared)
 };
 
 struct RuArgs {
@@ -515,6 +516,10 @@ inline bool prepare_conv_ru(const RuArgs& a, int B, int T, int dilation, RuLaunc
   p.bias7 = a.bias7; p.s2_a = a.s2_a; p.s2_inv_b = a.s2_inv_b; p.bias1 = a.bias1;
   p.sn_a = a.sn_a; p.sn_inv_b = a.sn_inv_b;
   if (const char* e = getenv("KVAE_RU_DBG")) p.dbg = atoi(e);
+  // KVAE_RU_EPI (A/B measurements, parity test): 0 = first-generation kernel, 1 = fragment-mapped epilogue on the
+  // serial GEMM1 -> EPI1 -> GEMM2 chain, 2 (default) = conv_ru2_kernel
+  L.epi = 2;
+  if (const char* e = getenv("KVAE_RU_EPI")) L.epi = atoi(e);
   p.a_ptr = a.a; p.x_ptr = a.x;
   p.pf = 0;
   if (const char* e = getenv("KVAE_RU_PF")) p.pf = atoi(e);
@@ -536,9 +541,7 @@ inline bool prepare_conv_ru(const RuArgs& a, int B, int T, int dilation, RuLaunc
 
 inline cudaError_t launch_conv_ru(const RuLaunch& L, cudaStream_t stream) {
   static bool attr_set[64] = {false};
-  // KVAE_RU_EPI (A/B measurements): 0 = first-generation kernel, 1 = fragment-mapped epilogue on the serial
-  // GEMM1 -> EPI1 -> GEMM2 chain, 2 = conv_ru2_kernel (two accumulators, GEMM2 slotted into the next tile's GEMM1)
-  static const int epi = [] { const char* e = getenv("KVAE_RU_EPI"); return e ? atoi(e) : 2; }();
+  const int epi = L.epi;
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {

@@ -369,6 +369,29 @@ def test_fused_residual_unit_matches_two_kernel_path(dev):
     assert float((y_fused - y_split).abs().max()) <= 2e-5 * float(ref.abs().max())
 
 
+def test_pipelined_residual_unit_bit_identical_to_serial_kernels(dev):
+    """conv_ru2_kernel (two TMEM accumulators, GEMM2 of tile i inside GEMM1 of tile i+1, fragment-mapped epilogues)
+    against its predecessors conv_ru_kernel<0> (one channel per thread, scalar fp32) and <1> on the same plan: the
+    packed fp32 pairs round like the scalar instructions and the MMA order per tile is unchanged, so the waveform
+    must be bit-identical.  KVAE_RU_GRID=5 forces ~20 tiles per CTA through the cross-tile pipeline."""
+    import os
+    z = torch.randn(3, 64, 211, generator=torch.Generator().manual_seed(4)).to(dev)
+    outs = {}
+    for name, env in (("ru2", {}), ("ru2_few_ctas", {"KVAE_RU_GRID": "5"}), ("serial0", {"KVAE_RU_EPI": "0"}),
+                      ("serial1", {"KVAE_RU_EPI": "1", "KVAE_RU_GRID": "7"})):
+        os.environ.update(env)
+        try:
+            m = H.build("mid", 0, snake_seed=7).to(dev).set_precision("bf16")
+            outs[name] = m.decode(z)
+            torch.cuda.synchronize()
+        finally:
+            for key in env:
+                del os.environ[key]
+    assert bool(torch.isfinite(outs["ru2"]).all())
+    for name in ("ru2_few_ctas", "serial0", "serial1"):
+        assert torch.equal(outs["ru2"], outs[name]), name
+
+
 def test_config4_streaming_chunks_equal_unchunked_o12_latent1024(dev):
     """BASELINE config 4: O12 latent-1024 decoder, decode_audio(chunked=True, chunk 128, overlap 32) over T=375
     (4 windows) equals the unchunked decode: overlap/2 = 16 frames > receptive field 10 frames."""
