@@ -154,11 +154,10 @@ __global__ void weight_norm_scale_kernel(const float* v, const float* g, float* 
 // writes are coalesced:  out1[(k*R + r)*Cc + c]   and   out2[(k*Cc + c)*R + r].
 // grid (ceil(R/16), ceil(Cc/32)), block 256, K <= 16.
 constexpr int kPackTR = 16, kPackTC = 32, kPackMaxK = 16;
-__global__ void __launch_bounds__(256)
-fold_pack_kernel(const float* v, const float* scale, int R, int Cc, int K, __nv_bfloat16* out1_bf16, float* out1_f32,
-                 __nv_bfloat16* out2_bf16, float* out2_f32) {
-  __shared__ float tile[kPackTR][kPackTC * (kPackMaxK + 1)];
-  const int r0 = blockIdx.x * kPackTR, c0 = blockIdx.y * kPackTC;
+__device__ __forceinline__ void fold_pack_tile(float (*tile)[kPackTC * (kPackMaxK + 1)], const float* v, const float* scale,
+                                               int R, int Cc, int K, int bx, int by, __nv_bfloat16* out1_bf16,
+                                               float* out1_f32, __nv_bfloat16* out2_bf16, float* out2_f32) {
+  const int r0 = bx * kPackTR, c0 = by * kPackTC;
   const int w = kPackTC * K;                 // contiguous floats per row of the tile
   const int Kp = K | 1;                      // odd per-column stride in shared memory: the transposed reads below
                                              // walk columns, which would be a K-way bank conflict for even K
@@ -188,6 +187,81 @@ fold_pack_kernel(const float* v, const float* scale, int R, int Cc, int K, __nv_
       if (out2_bf16) out2_bf16[o] = __float2bfloat16(val);
       if (out2_f32) out2_f32[o] = val;
     }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+fold_pack_kernel(const float* v, const float* scale, int R, int Cc, int K, __nv_bfloat16* out1_bf16, float* out1_f32,
+                 __nv_bfloat16* out2_bf16, float* out2_f32) {
+  __shared__ float tile[kPackTR][kPackTC * (kPackMaxK + 1)];
+  fold_pack_tile(tile, v, scale, R, Cc, K, blockIdx.x, blockIdx.y, out1_bf16, out1_f32, out2_bf16, out2_f32);
+}
+
+// ---------------------------------------------------------------- the same for ALL layers of a plan in two launches
+// One optimizer step re-folds ~75 weight tensors; as one scale + one pack launch per layer (plus a bias copy and a
+// SnakeBeta-constant launch per activation) that is ~300 stream operations of a few microseconds of work each --
+// 2.9 ms of a 35 ms training step (profiles/r01_train_step_launches.txt).  Here a block finds its layer by binary
+// search in a prefix table.
+struct FoldDesc {
+  long long off_v, off_g, off_bias;   // floats into the flat parameter buffer; off_bias < 0: no bias
+  int R, Cc, K, Cout;
+  int row0;                           // first block of the layer in weight_norm_scale_all_kernel = offset into scale[]
+  int tile0, tiles_x;                 // first block in fold_pack_all_kernel, tiles along R
+  __nv_bfloat16* o1b; float* o1f; __nv_bfloat16* o2b; float* o2f;
+  float* bias;
+};
+struct SnakeDesc { long long off_alpha, off_beta; int C; float* a; float* inv_b; };
+
+__device__ __forceinline__ int find_layer_by_row(const FoldDesc* d, int n, int block) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (d[mid].row0 <= block) lo = mid; else hi = mid - 1; }
+  return lo;
+}
+__device__ __forceinline__ int find_layer_by_tile(const FoldDesc* d, int n, int block) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (d[mid].tile0 <= block) lo = mid; else hi = mid - 1; }
+  return lo;
+}
+
+// grid = sum of dim-0 rows over the layers; the block of a layer's first row also copies its bias
+__global__ void __launch_bounds__(256)
+weight_norm_scale_all_kernel(const float* params, const FoldDesc* d, int n_layers, float* scale) {
+  __shared__ float red[32];
+  const FoldDesc L = d[find_layer_by_row(d, n_layers, blockIdx.x)];
+  const int row = blockIdx.x - L.row0;
+  const int inner = L.Cc * L.K;
+  const float* v = params + L.off_v + static_cast<size_t>(row) * inner;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < inner; i += blockDim.x) { const float x = v[i]; s = fmaf(x, x, s); }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (threadIdx.x == 0) scale[blockIdx.x] = params[L.off_g + row] / sqrtf(t);
+  }
+  if (row == 0 && L.off_bias >= 0)
+    for (int i = threadIdx.x; i < L.Cout; i += blockDim.x) L.bias[i] = params[L.off_bias + i];
+}
+
+__global__ void __launch_bounds__(256)
+fold_pack_all_kernel(const float* params, const FoldDesc* d, int n_layers, const float* scale) {
+  __shared__ float tile[kPackTR][kPackTC * (kPackMaxK + 1)];
+  const FoldDesc L = d[find_layer_by_tile(d, n_layers, blockIdx.x)];
+  const int t = blockIdx.x - L.tile0;
+  fold_pack_tile(tile, params + L.off_v, scale + L.row0, L.R, L.Cc, L.K, t % L.tiles_x, t / L.tiles_x, L.o1b, L.o1f, L.o2b,
+                 L.o2f);
+}
+
+// one block per SnakeBeta layer
+__global__ void snake_params_all_kernel(const float* params, const SnakeDesc* d, int logscale) {
+  const SnakeDesc L = d[blockIdx.x];
+  for (int c = threadIdx.x; c < L.C; c += blockDim.x) {
+    float av = params[L.off_alpha + c], bv = params[L.off_beta + c];
+    if (logscale) { av = expf(av); bv = expf(bv); }
+    L.a[c] = av;
+    L.inv_b[c] = 1.0f / (bv + 1e-9f);
   }
 }
 

@@ -181,6 +181,14 @@ struct kvae_plan {
   bool train_packs = false;
   bool stream_f16 = false;    // inference plans keep the residual stream in fp16 (bf16 mode, all-tensor-core chains)
   float* scale_scratch = nullptr;   // g/||v|| per dim-0 row of the conv being packed
+  // batched kvae_plan_load_params (one scale + one pack + one SnakeBeta-constant launch for the whole plan)
+  FoldDesc* fold_desc = nullptr;    // device, one per conv
+  SnakeDesc* snake_desc = nullptr;  // device, one per SnakeBeta
+  float* scale_all = nullptr;       // device, sum of dim-0 rows
+  int fold_rows = 0, fold_tiles = 0;
+  int fold_train = -1;              // the `train` flag the descriptors were built for (-1: not built)
+  WnBwdDesc* wn_desc = nullptr;     // device, one per conv: batched weight-norm backward
+  int wn_rows = 0;
   float* dwp = nullptr;             // packed weight-gradient accumulators of the tensor-core convs
   size_t dwp_floats = 0;
   std::map<std::tuple<int, long long, void*>, std::unique_ptr<PreparedRun>> runs;
@@ -1170,6 +1178,29 @@ int run_backward(kvae_plan* p, const void* x, int x_dtype, const void* gy, int g
   }
   // weight-norm backward: dW (folded-weight gradient; in place in the weight_v slot, or packed by the
   // tensor-core kernel) -> (dv, dg); without params the packed gradients are only re-ordered
+  bool batched = true;               // KVAE_LOAD_PARAMS_PER_LAYER=1: per-layer launches (A/B, debugging)
+  if (const char* e = getenv("KVAE_LOAD_PARAMS_PER_LAYER")) batched = !(e[0] == '1');
+  if (batched) {
+    if (!p->wn_desc) {
+      std::vector<WnBwdDesc> wd(p->convs.size());
+      int rows = 0;
+      for (size_t i = 0; i < p->convs.size(); ++i) {
+        const ConvLayer& c = p->convs[i];
+        const int R = c.dim0();
+        wd[i].off_v = c.off_v; wd[i].off_g = c.off_g; wd[i].off_dwp = c.off_dwp;
+        wd[i].R = R; wd[i].Cc = static_cast<int>(c.numel() / c.g.K / R); wd[i].K = c.g.K; wd[i].row0 = rows;
+        rows += R;
+      }
+      KV_CUDA(cudaMalloc(&p->wn_desc, wd.size() * sizeof(WnBwdDesc)));
+      KV_CUDA(cudaMemcpy(p->wn_desc, wd.data(), wd.size() * sizeof(WnBwdDesc), cudaMemcpyHostToDevice));
+      p->wn_rows = rows;
+    }
+    weight_norm_bwd_all_kernel<<<p->wn_rows, 256, 0, st>>>(params, grads, p->dwp, p->wn_desc,
+                                                          static_cast<int>(p->convs.size()));
+    KV_CUDA(cudaGetLastError());
+    ++g_launches;
+    return 0;
+  }
   for (const ConvLayer& c : p->convs) {
     const int R = c.dim0(), inner = static_cast<int>(c.numel() / R);
     if (c.off_dwp >= 0) {
@@ -1277,6 +1308,10 @@ void kvae_plan_destroy(kvae_plan* p) {
     cudaFree(s.inv_b);
   }
   cudaFree(p->scale_scratch);
+  cudaFree(p->fold_desc);
+  cudaFree(p->snake_desc);
+  cudaFree(p->scale_all);
+  cudaFree(p->wn_desc);
   cudaFree(p->dwp);
   delete p;
 }
@@ -1570,6 +1605,70 @@ int kvae_plan_load_params(kvae_plan* p, const float* params, int logscale, int t
     for (const ConvLayer& c : p->convs) m = std::max(m, c.dim0());
     KV_CUDA(cudaMalloc(&p->scale_scratch, static_cast<size_t>(m) * 4));
   }
+  bool batched = true;               // KVAE_LOAD_PARAMS_PER_LAYER=1: the per-layer launches below (A/B, debugging)
+  if (const char* e = getenv("KVAE_LOAD_PARAMS_PER_LAYER")) batched = !(e[0] == '1');
+  for (const ConvLayer& c : p->convs) {
+    if (c.g.K > kPackMaxK) return fail("kernel size > 16 unsupported by kvae_plan_load_params");
+    if (c.umma32) batched = false;   // fp32-mode inference operands need the extra split pass per layer
+  }
+  if (batched) {
+    for (ConvLayer& c : p->convs)
+      if (train) {   // the backward pass needs the other index order of each precision
+        const size_t n = c.numel();
+        if (c.umma && !c.w_umma_d) KV_CUDA(cudaMalloc(&c.w_umma_d, n * 2));
+        if (!c.umma && !c.w_direct_d) KV_CUDA(cudaMalloc(&c.w_direct_d, n * 4));
+      }
+    if (p->fold_train != (train ? 1 : 0)) {
+      std::vector<FoldDesc> fd(p->convs.size());
+      int rows = 0, tiles = 0;
+      for (size_t i = 0; i < p->convs.size(); ++i) {
+        const ConvLayer& c = p->convs[i];
+        FoldDesc& d = fd[i];
+        const int R = c.dim0(), Cc = static_cast<int>(c.numel() / c.g.K / R);
+        d.off_v = c.off_v; d.off_g = c.off_g; d.off_bias = c.has_bias ? c.off_bias : -1;
+        d.R = R; d.Cc = Cc; d.K = c.g.K; d.Cout = c.g.Cout;
+        d.row0 = rows; d.tile0 = tiles; d.tiles_x = ceil_div(R, kPackTR);
+        rows += R;
+        tiles += d.tiles_x * ceil_div(Cc, kPackTC);
+        // index order A = [K][Cout][Cin]: forward tensor-core operand / CUDA-core dgrad operand;
+        // index order B = [K][Cin][Cout]: forward CUDA-core operand / tensor-core dgrad operand
+        if (c.g.kind == kConv) {   // R = Cout, Cc = Cin: out1 = A, out2 = B
+          d.o1b = c.umma ? c.w_umma : nullptr; d.o1f = train ? c.w_direct_d : nullptr;
+          d.o2b = train ? c.w_umma_d : nullptr; d.o2f = c.w_direct;
+        } else {                   // R = Cin, Cc = Cout: out1 = B, out2 = A
+          d.o1b = train ? c.w_umma_d : nullptr; d.o1f = c.w_direct;
+          d.o2b = c.umma ? c.w_umma : nullptr; d.o2f = train ? c.w_direct_d : nullptr;
+        }
+        d.bias = c.bias;
+      }
+      std::vector<SnakeDesc> sd(p->snakes.size());
+      for (size_t i = 0; i < p->snakes.size(); ++i) {
+        const SnakeLayer& sl = p->snakes[i];
+        sd[i].off_alpha = sl.off_alpha; sd[i].off_beta = sl.off_beta; sd[i].C = sl.C; sd[i].a = sl.a; sd[i].inv_b = sl.inv_b;
+      }
+      if (!p->fold_desc) KV_CUDA(cudaMalloc(&p->fold_desc, fd.size() * sizeof(FoldDesc)));
+      if (!p->snake_desc && !sd.empty()) KV_CUDA(cudaMalloc(&p->snake_desc, sd.size() * sizeof(SnakeDesc)));
+      if (!p->scale_all) KV_CUDA(cudaMalloc(&p->scale_all, static_cast<size_t>(rows) * 4));
+      // synchronous copies of pageable host vectors: once per plan and mode, not per step
+      KV_CUDA(cudaMemcpy(p->fold_desc, fd.data(), fd.size() * sizeof(FoldDesc), cudaMemcpyHostToDevice));
+      if (!sd.empty()) KV_CUDA(cudaMemcpy(p->snake_desc, sd.data(), sd.size() * sizeof(SnakeDesc), cudaMemcpyHostToDevice));
+      p->fold_rows = rows; p->fold_tiles = tiles;
+      p->fold_train = train ? 1 : 0;
+    }
+    const int nl = static_cast<int>(p->convs.size());
+    weight_norm_scale_all_kernel<<<p->fold_rows, 256, 0, st>>>(params, p->fold_desc, nl, p->scale_all);
+    KV_CUDA(cudaGetLastError());
+    fold_pack_all_kernel<<<p->fold_tiles, 256, 0, st>>>(params, p->fold_desc, nl, p->scale_all);
+    KV_CUDA(cudaGetLastError());
+    g_launches += 2;
+    if (!p->snakes.empty()) {
+      snake_params_all_kernel<<<static_cast<int>(p->snakes.size()), 256, 0, st>>>(params, p->snake_desc, logscale ? 1 : 0);
+      KV_CUDA(cudaGetLastError());
+      ++g_launches;
+    }
+    for (ConvLayer& c : p->convs) c.set = true;
+    for (SnakeLayer& sl : p->snakes) { sl.logscale = logscale ? 1 : 0; sl.set = true; }
+  } else {
   for (ConvLayer& c : p->convs) {
     if (c.g.K > kPackMaxK) return fail("kernel size > 16 unsupported by kvae_plan_load_params");
     const size_t n = c.numel();
@@ -1607,6 +1706,7 @@ int kvae_plan_load_params(kvae_plan* p, const float* params, int logscale, int t
     s.logscale = logscale ? 1 : 0;
     s.set = true;
     ++g_launches;
+  }
   }
   if (train && !p->dwp) {
     const char* e = getenv("KVAE_WGRAD_DIRECT");     // development switch: CUDA-core weight gradients everywhere

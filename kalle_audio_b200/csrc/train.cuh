@@ -461,10 +461,9 @@ __global__ void __launch_bounds__(256) wgrad_direct_kernel(const WgradParams p) 
 // w[i,:] = v[i,:] * g[i] / n_i,  n_i = ||v[i,:]||:
 //   dg[i] = <dw_i, v_i> / n_i ;  dv_i = (g_i / n_i) * (dw_i - v_i * <dw_i, v_i> / n_i^2)
 // One block per row i.  dw and dv may alias (in place).
-__global__ void weight_norm_bwd_kernel(const float* v, const float* g, const float* dw, float* dv, float* dg,
-                                       int inner) {
-  __shared__ float red[2][32];
-  const size_t base = static_cast<size_t>(blockIdx.x) * inner;
+__device__ __forceinline__ void weight_norm_bwd_row(float (*red)[32], const float* v, const float* g, const float* dw,
+                                                    float* dv, float* dg, int inner, int row) {
+  const size_t base = static_cast<size_t>(row) * inner;
   float nn = 0.f, dot = 0.f;
   for (int i = threadIdx.x; i < inner; i += blockDim.x) {
     const float x = v[base + i];
@@ -490,18 +489,22 @@ __global__ void weight_norm_bwd_kernel(const float* v, const float* g, const flo
   nn = red[0][0];
   dot = red[1][0];
   const float n = sqrtf(nn);
-  const float gi = g[blockIdx.x];
+  const float gi = g[row];
   const float s = gi / n, q = dot / nn;
   for (int i = threadIdx.x; i < inner; i += blockDim.x) dv[base + i] = s * (dw[base + i] - v[base + i] * q);
-  if (threadIdx.x == 0) dg[blockIdx.x] = dot / n;
+  if (threadIdx.x == 0) dg[row] = dot / n;
+}
+__global__ void weight_norm_bwd_kernel(const float* v, const float* g, const float* dw, float* dv, float* dg,
+                                       int inner) {
+  __shared__ float red[2][32];
+  weight_norm_bwd_row(red, v, g, dw, dv, dg, inner, blockIdx.x);
 }
 
 // Same, with dw in the packed layout [K][R][Cc] the tensor-core weight-gradient kernel accumulates into
 // (v, dv in the torch layout [R][Cc][K]).  g == nullptr: no weight norm, dv = dw re-ordered.
-__global__ void weight_norm_bwd_packed_kernel(const float* v, const float* g, const float* dwp, float* dv, float* dg,
-                                              int R, int Cc, int K) {
-  __shared__ float red[2][32];
-  const int i = blockIdx.x;
+__device__ __forceinline__ void weight_norm_bwd_packed_row(float (*red)[32], const float* v, const float* g,
+                                                           const float* dwp, float* dv, float* dg, int R, int Cc, int K,
+                                                           int i) {
   const int inner = Cc * K;
   const size_t base = static_cast<size_t>(i) * inner;
   // walk the packed layout in its own order (c fastest) for coalesced reads of dw
@@ -540,6 +543,32 @@ __global__ void weight_norm_bwd_packed_kernel(const float* v, const float* g, co
     dv[base + j] = g ? s * (d - v[base + j] * q) : d;
   }
   if (g && threadIdx.x == 0) dg[i] = dot / n;
+}
+__global__ void weight_norm_bwd_packed_kernel(const float* v, const float* g, const float* dwp, float* dv, float* dg,
+                                              int R, int Cc, int K) {
+  __shared__ float red[2][32];
+  weight_norm_bwd_packed_row(red, v, g, dwp, dv, dg, R, Cc, K, blockIdx.x);
+}
+
+// All layers of a plan in ONE launch (72 launches of ~16 us each before): grid = sum of dim-0 rows, a block finds its
+// layer by binary search in the prefix table.  params == nullptr: packed gradients are only re-ordered.
+struct WnBwdDesc {
+  long long off_v, off_g, off_dwp;    // floats; off_dwp < 0: dW sits in the weight_v slot of grads (in place)
+  int R, Cc, K, row0;
+};
+__global__ void __launch_bounds__(256)
+weight_norm_bwd_all_kernel(const float* params, float* grads, const float* dwp, const WnBwdDesc* d, int n_layers) {
+  __shared__ float red[2][32];
+  int lo = 0, hi = n_layers - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (d[mid].row0 <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid - 1; }
+  const WnBwdDesc L = d[lo];
+  const int row = blockIdx.x - L.row0;
+  if (L.off_dwp >= 0)
+    weight_norm_bwd_packed_row(red, params ? params + L.off_v : nullptr, params ? params + L.off_g : nullptr, dwp + L.off_dwp,
+                               grads + L.off_v, grads + L.off_g, L.R, L.Cc, L.K, row);
+  else if (params)
+    weight_norm_bwd_row(red, params + L.off_v, params + L.off_g, grads + L.off_v, grads + L.off_v, grads + L.off_g,
+                        L.Cc * L.K, row);
 }
 
 // ---------------------------------------------------------------- vae_sample backward (bottleneck.py:51-62)
