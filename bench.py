@@ -211,10 +211,13 @@ def run_cuda(args):
         y, _ = roundtrip(x_dev)
         return y
 
+    # end-to-end leg: the public host-buffer pipeline (kalle_audio_b200.HostPipeline) -- every step copies its input
+    # from pinned host memory and its waveform back inside the timed region; the copies of consecutive steps overlap
+    # the kernels (double-buffered device input, copy streams), as a serving loop over batches would run it
+    pipe = k.HostPipeline(lambda xd: roundtrip(xd)[0], dev)
+
     def step_e2e():
-        x = x_host.to(dev, non_blocking=True)
-        y, _ = roundtrip(x)
-        y_host.copy_(y, non_blocking=True)
+        pipe.submit(x_host, y_host)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -238,6 +241,20 @@ def run_cuda(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), clocks
 
+    def timed_e2e(steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step_e2e()
+        pipe.join()                      # the last step's device->host copy is inside the timed region
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), None
+
     for _ in range(max(args.warmup, 3)):
         step_resident()
     # roofline leg: per-step CUDA events inside the library, on the launching stream
@@ -256,7 +273,7 @@ def run_cuda(args):
     dec_ms, _ = timed(lambda: ae.decode(z_dev), args.steps)
     for _ in range(2):
         step_e2e()
-    e2e_ms, _ = timed(step_e2e, args.steps)
+    e2e_ms, _ = timed_e2e(args.steps)
 
     if rank == 0:
         peaks = measured_peaks()

@@ -392,6 +392,31 @@ def test_pipelined_residual_unit_bit_identical_to_serial_kernels(dev):
         assert torch.equal(outs["ru2"], outs[name]), name
 
 
+def test_host_pipeline_equals_direct_calls(dev):
+    """kalle_audio_b200.HostPipeline (pinned host buffers, copy streams, double-buffered device input): five
+    batches in flight give exactly the tensors of five synchronous host -> device -> decode -> host calls."""
+    m = H.build("mid", 0, snake_seed=7).to(dev).set_precision("bf16")
+    zs = [torch.randn(2, 64, 50 + 3 * i, generator=torch.Generator().manual_seed(20 + i)).pin_memory() for i in range(5)]
+    direct = [m.decode(z.to(dev)).cpu() for z in zs]
+    outs = [torch.empty_like(d).pin_memory() for d in direct]
+    pipe = k.HostPipeline(m.decode, dev)
+    for z, o in zip(zs, outs):
+        pipe.submit(z, o)
+    pipe.synchronize()
+    for d, o in zip(direct, outs):
+        assert torch.equal(d, o)
+    # one output buffer reused by consecutive submissions of one shape: the last submission wins
+    same = [zs[0], (zs[0] * 0.5).pin_memory(), (zs[0] * 0.25).pin_memory()]
+    y = torch.empty_like(direct[0]).pin_memory()
+    for z in same:
+        pipe.submit(z, y)
+    pipe.join()
+    torch.cuda.synchronize()
+    assert torch.equal(y, m.decode(same[-1].to(dev)).cpu())
+    with pytest.raises(ValueError):
+        pipe.submit(zs[0].to(dev), y)
+
+
 def test_config4_streaming_chunks_equal_unchunked_o12_latent1024(dev):
     """BASELINE config 4: O12 latent-1024 decoder, decode_audio(chunked=True, chunk 128, overlap 32) over T=375
     (4 windows) equals the unchunked decode: overlap/2 = 16 frames > receptive field 10 frames."""
