@@ -6,7 +6,7 @@ CSRC := kalle_audio_b200/csrc
 LIB := kalle_audio_b200/libkvae.so
 HDRS := $(wildcard $(CSRC)/*.cuh) include/kvae.h
 
-all: $(LIB) build/umma_probe oracle
+all: $(LIB) build/umma_probe build/tma_copy_probe oracle
 
 $(LIB): $(CSRC)/kvae.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $<
@@ -15,11 +15,15 @@ build/umma_probe: tools/umma_probe.cu $(HDRS)
 	@mkdir -p build
 	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -o $@ $<
 
+build/tma_copy_probe: tools/tma_copy_probe.cu $(CSRC)/ptx.cuh
+	@mkdir -p build
+	$(NVCC) $(ARCH) -O3 -std=c++17 -lineinfo -o $@ $< -lcuda
+
 oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -f $(LIB) build/umma_probe
+	rm -f $(LIB) build/umma_probe build/tma_copy_probe build/libkvae_nu.so
 	$(MAKE) -C oracle clean
 
 .PHONY: all clean oracle
