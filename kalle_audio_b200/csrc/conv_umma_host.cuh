@@ -372,6 +372,15 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
                                 (g.Cout % 256 == 0 && g.Cout >= 512 ? g.Cout / 256 : (g.Cout + 127) / 128);
     const bool starved = big_tiles * 10 < static_cast<long long>(sm_count()) * 6;
     if (starved && g.Cout % 128 == 0) cands.push_back({1, 128, 2});
+    // Cout >= 512: 128-channel swap tiles (N = 256 time rows) with double-buffered accumulators, like the narrower
+    // layers.  256 x 256 tiles (KVAE_WIDE_TILES=2, the first choice until the end of round 1) fill all 512 TMEM columns
+    // with ONE accumulator set, so their epilogue cannot overlap the next tile's MMAs: 63 % tensor-pipe activity at
+    // C = 512 (profiles/r01_ncu_summary.txt); the swap tiles read the activation slab twice as often from L2 but
+    // measured k7 C=512 0.295 -> 0.254 ms, k1 C=512 0.164 -> 0.121 ms, ConvTranspose 1024->512 0.249 -> 0.197 ms at
+    // B = 8 (profiles/r01_tile_shapes_B8.log).  KVAE_WIDE_TILES=1: 128 x 256 time-on-M tiles, double-buffered.
+    static const int wide = [] { const char* e = getenv("KVAE_WIDE_TILES"); return e ? atoi(e) : 0; }();
+    if (wide == 0 && g.Cout % 128 == 0) cands.push_back({mt, 128, 2});
+    if (wide == 1 && g.Cout % 256 == 0 && g.Cout >= 512) cands.push_back({1, 256, 2});
     if (g.Cout % 256 == 0 && g.Cout >= 512) cands.push_back({mt, 256, mt * 256 * 2 <= 512 ? 2 : 1});
     if (g.Cout % 128 == 0) cands.push_back({mt, 128, 2});
     if (g.Cout % 128 == 0) cands.push_back({1, 128, 2});
