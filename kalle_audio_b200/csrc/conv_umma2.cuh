@@ -53,6 +53,7 @@ struct ConvParams2 {
   int out_cf_f32;
   int act_mode;            // 0 none, 1 bf16 channels-last via TMA (tmO)
   int one_producer;        // 1: activation and weight slabs requested by one thread in one FIFO (A/B switch)
+  int no_frag;             // 1: scalar swap epilogue even where the fragment-mapped one applies (A/B switch, KVAE_FRAG_EPI=0)
   int split3;              // fp32-mode arithmetic on the tensor cores: both operands are stored as bf16 (hi | lo)
                            // halves -- activations [.., 2*Cin], weights [tap][Cout][2*Cin] -- and every K chunk is
                            // multiplied three times: hi*hi + lo*hi + hi*lo (the lo*lo term is below fp32 rounding).
@@ -270,6 +271,13 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // row x 32 channels (vector shared-memory accesses).  swap = 1: TMEM lane = channel, so a thread owns one
     // channel x 32 rows (scalar accesses into the same swizzled blocks; per-channel constants live in registers).
     const int ipt = p.swap ? 4 * p.MT : p.MT * (p.NT >> 5);
+    // fragment-mapped fast path of the swap orientation (inference plans in bf16 mode: fp16 stream, bf16 operand)
+    const bool frag = p.swap && !p.no_frag && !p.act_split && !p.precise && p.raw_mode != 2 &&
+                      (p.raw_f16 || (p.raw_mode == 0 && !has_res));
+    // ldmatrix / stmatrix: this lane addresses row (lane & 7) of matrix (lane >> 3) inside a 16-row half of a
+    // [32 rows x 64 B] SWIZZLE_64B block (lane half 1: address ^ 32, rows 16..31: + 1024)
+    const int frag_row = ((lane >> 4) << 3) + (lane & 7);
+    const uint32_t frag_lane = frag_row * 64 + ((((lane >> 3) & 1) ^ ((frag_row >> 1) & 3)) << 4);
     int acc = 0, jr = 0, ja = 0;
     uint32_t accph = 0, res_ph = 0;          // res_ph: one parity bit per ring slot
     // item -> block coordinates: (channel, phase, first row, batch)
@@ -294,8 +302,22 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       int b, q0, phi, n0;
       decode(tile, b, q0, phi, n0);
       // swap mode: this thread's channel and its constants
+      uint64_t fbias[4] = {0, 0, 0, 0}, fsa[4] = {0, 0, 0, 0}, fsib[4] = {0, 0, 0, 0};   // index 2 L + hi
+      if (frag) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = n0 + quad * 32 + (i >> 1) * 16 + (i & 1) * 8 + (lane >> 2);
+          const float bv = p.bias ? __ldg(p.bias + c) : 0.f;
+          fbias[i] = ptx::f2_pack(bv, bv);
+          if (p.snake_a) {
+            const float a = __ldg(p.snake_a + c), ib = __ldg(p.snake_inv_b + c);
+            fsa[i] = ptx::f2_pack(a, a);
+            fsib[i] = ptx::f2_pack(ib, ib);
+          }
+        }
+      }
       float bias_s = 0.f, sa_s = 1.f, sib_s = 0.f;
-      if (p.swap) {
+      if (p.swap && !frag) {
         const int c = n0 + quad * 32 + lane;
         if (p.bias) bias_s = __ldg(p.bias + c);
         if (p.snake_a) { sa_s = __ldg(p.snake_a + c); sib_s = __ldg(p.snake_inv_b + c); }
@@ -333,6 +355,81 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           ptx::mbar_wait(&my_res_full[jr], (res_ph >> jr) & 1u);
           res_ph ^= (1u << jr);
         }
+        uint8_t* const rblk = raw_ring + jr * rawblk;
+        const int actblk = kActBlkBytes * (p.act_split ? 2 : 1);       // (hi | lo) blocks back to back
+        uint8_t* const ablk = act_ring + ja * actblk;
+        if (frag) {
+          // ---- swap orientation, 2-byte stream / operand blocks: fragment mapping (see conv_ru2.cuh).  tcgen05.ld
+          // .16x256b hands a thread (time, time+1) PAIRS of one channel; bias, skip and SnakeBeta run on packed fp32
+          // pairs, a converted pair is one stmatrix.trans register and the skip block comes in through ldmatrix.trans,
+          // so the [32 rows x 64 B] SWIZZLE_64B blocks are touched in 16-byte rows instead of 2 bytes per element.
+          uint32_t r[32];                                    // r[16 L + 4 n + 2 hi + {0,1}]: lane half L, column group n
+          __syncwarp();
+          ptx::tmem_ld_16x256b_x4(acc_tmem + tcol, r);
+          ptx::tmem_ld_16x256b_x4(acc_tmem + tcol + (16u << 16), r + 16);
+          uint32_t sk[16];                                   // sk[8 L + 4 m + j]: rows 16 m + 8 (j >> 1) .., channel group 2 L + (j & 1)
+          const uint32_t rb = ptx::smem_u32(rblk) + frag_lane;
+          if (has_res) {
+#pragma unroll
+            for (int L = 0; L < 2; ++L)
+#pragma unroll
+              for (int m = 0; m < 2; ++m)
+                ptx::ldmatrix_x4_trans((rb + m * 1024) ^ (L * 32u), sk[8 * L + 4 * m], sk[8 * L + 4 * m + 1],
+                                       sk[8 * L + 4 * m + 2], sk[8 * L + 4 * m + 3]);
+          }
+          ptx::tmem_ld_wait();
+          uint64_t v[16];                                    // v[8 L + 4 m + j], j = 2 (n & 1) + hi, n = 2 m + (j >> 1)
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            const int L = q >> 3, ci = 2 * L + (q & 1);      // channel cbase + 16 L + 8 hi + (lane >> 2)
+            const int ri = 16 * L + 4 * (2 * ((q >> 2) & 1) + ((q >> 1) & 1)) + 2 * (q & 1);
+            v[q] = ptx::f2_add(ptx::f2_pack_u(r[ri], r[ri + 1]), fbias[ci]);
+            if (has_res) {
+              const float2 sf = __half22float2(*reinterpret_cast<const __half2*>(&sk[q]));
+              v[q] = ptx::f2_add(v[q], ptx::f2_pack(sf.x, sf.y));
+            }
+          }
+          if (p.raw_mode == 1) {
+            uint32_t w[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              float y0, y1;
+              ptx::f2_unpack(v[q], y0, y1);
+              w[q] = ptx::f2h2_sat(y0, y1);
+            }
+#pragma unroll
+            for (int L = 0; L < 2; ++L)
+#pragma unroll
+              for (int m = 0; m < 2; ++m)
+                ptx::stmatrix_x4_trans((rb + m * 1024) ^ (L * 32u), w[8 * L + 4 * m], w[8 * L + 4 * m + 1],
+                                       w[8 * L + 4 * m + 2], w[8 * L + 4 * m + 3]);
+          }
+          if (p.act_mode == 1) {
+            uint32_t w[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              float y0, y1;
+              if (p.snake_a) {
+                const int ci = 2 * (q >> 3) + (q & 1);
+                float t0, t1;
+                ptx::f2_unpack(ptx::f2_mul(v[q], fsa[ci]), t0, t1);
+                const uint64_t sn = ptx::f2_pack(sin_fast(t0), sin_fast(t1));
+                ptx::f2_unpack(ptx::f2_fma(ptx::f2_mul(fsib[ci], sn), sn, v[q]), y0, y1);
+              } else {
+                ptx::f2_unpack(v[q], y0, y1);
+              }
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
+              w[q] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            const uint32_t ab = ptx::smem_u32(ablk) + frag_lane;
+#pragma unroll
+            for (int L = 0; L < 2; ++L)
+#pragma unroll
+              for (int m = 0; m < 2; ++m)
+                ptx::stmatrix_x4_trans((ab + m * 1024) ^ (L * 32u), w[8 * L + 4 * m], w[8 * L + 4 * m + 1],
+                                       w[8 * L + 4 * m + 2], w[8 * L + 4 * m + 3]);
+          }
+        } else {
         uint32_t r[32];
         __syncwarp();
         ptx::tmem_ld_32x32(acc_tmem + tcol, r);
@@ -340,9 +437,6 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        uint8_t* const rblk = raw_ring + jr * rawblk;
-        const int actblk = kActBlkBytes * (p.act_split ? 2 : 1);       // (hi | lo) blocks back to back
-        uint8_t* const ablk = act_ring + ja * actblk;
         if (p.swap) {
           // ---- thread = channel (cbase + lane), v[j] = row r0 + j
           // element (row j, channel lane) of a SWIZZLE_128B fp32 block / SWIZZLE_64B bf16 block
@@ -519,6 +613,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
         }
         }
+        }   // !frag
         if (R > 0 || p.act_mode == 1) {
           ptx::fence_proxy_async();
           __syncwarp();
