@@ -73,7 +73,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE,
+                                          "-i", str(self.gpu), "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -85,17 +85,28 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def wait_first(self, timeout=8.0):
+        """nvidia-smi needs up to a few seconds before its first line on an 8-GPU box: wait for it (outside any timed
+        region) so that the timed region itself is covered."""
+        t0 = time.perf_counter()
+        while self.proc is not None and not self.rows and time.perf_counter() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self):
+        return len(self.rows)
+
+    def stats(self, i0=0, i1=None):
+        """Clocks / power / throttle reasons of the samples taken between two marks (widened by one sample on each
+        side when the region was shorter than the sampling period)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
+        i1 = len(self.rows) if i1 is None else i1
+        rows = self.rows[i0:i1]
+        if len(rows) < 2:
+            rows = self.rows[max(0, i0 - 1):i1 + 1]
         sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             if len(r) < 9:
                 continue
             try:
@@ -107,6 +118,15 @@ class ClockSampler:
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+    def stop(self):
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
 
 
 # ------------------------------------------------------------------------------------------ reference arm
@@ -227,15 +247,14 @@ def run_cuda(args):
 
     def timed(fn, steps, sampler=None):
         barrier()
-        if sampler:
-            sampler.start()
+        i0 = sampler.mark() if sampler else 0
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
         barrier()
-        clocks = sampler.stop() if sampler else None
+        clocks = sampler.stats(i0, sampler.mark()) if sampler else None
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -255,14 +274,17 @@ def run_cuda(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), None
 
+    sampler = ClockSampler(local)        # started before the warm-up: nvidia-smi is slow to produce its first line
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step_resident()
+    sampler.wait_first()
     # roofline leg: per-step CUDA events inside the library, on the launching stream
     enc_r, dec_r = ae.encoder.runner(dev), ae.decoder.runner(dev)
     enc_r.set_profiling(True); dec_r.set_profiling(True)
     _lib.lib().kvae_launch_count(1)
-    sampler = ClockSampler(local)
     total_ms, clocks = timed(step_resident, args.steps, sampler)
+    sampler.stop()
     launches = int(_lib.lib().kvae_launch_count(0))
     prof = enc_r.step_profile() + dec_r.step_profile()          # last step of the timed region
     enc_r.set_profiling(False); dec_r.set_profiling(False)
@@ -551,13 +573,16 @@ def run_train(args):
         return float(ms.item()) / steps, info
 
     losses = []
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         losses.append(float(tr.training_step(x, noise)["loss"]))
     _lib.lib().kvae_launch_count(1)
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler.wait_first()
+    i0 = sampler.mark()
     ms, info = timed(args.steps)
-    clocks = sampler.stop()
+    clocks = sampler.stats(i0, sampler.mark())
+    sampler.stop()
     launches = int(_lib.lib().kvae_launch_count(0))
     losses.append(float(info["loss"]))
     ms_nosync = ms
