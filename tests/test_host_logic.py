@@ -140,3 +140,36 @@ def test_decoder_context_frames_is_the_exact_receptive_field():
     ratio = 40
     # frame 32 is right context of frames down to 32 - right and left context of frames up to 32 + left
     assert int(moved.min()) // ratio == 32 - right and int(moved.max()) // ratio == 32 + left
+
+
+def test_host_pipeline_has_no_cpu_path():
+    with pytest.raises(ValueError, match="no CPU path"):
+        k.HostPipeline(lambda x: x, torch.device("cpu"))
+
+
+def test_bench_clock_sampler_windows():
+    """bench.py's ClockSampler: statistics of the samples between two marks; a region shorter than the sampling
+    period is widened by one sample on each side; throttle reasons are collected from the window only."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(H.__file__), "..", "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    s.proc = object()                       # pretend nvidia-smi is running
+
+    def row(mhz, watts, power_cap=False, thermal=False):
+        return ["0", str(mhz), "1965", str(watts), "0x0", "Not Active", "Active" if thermal else "Not Active",
+                "Not Active", "Active" if power_cap else "Not Active"]
+    s.rows = [row(1965, 200), row(1500, 990, power_cap=True), row(1600, 1000, power_cap=True), row(1965, 300),
+              row(900, 250, thermal=True)]
+    st = s.stats(1, 3)
+    assert st["samples"] == 2 and st["sm_mhz"] == 1550.0 and st["power_w_max"] == 1000.0
+    assert st["reasons"] == ["sw_power_cap"] and st["sm_max_mhz"] == 1965.0
+    st = s.stats(2, 2)                       # empty window -> neighbours on both sides
+    assert st["samples"] == 2 and st["sm_mhz"] == 1550.0
+    st = s.stats(4, 5)                       # a single sample -> widened to rows 3..4
+    assert st["samples"] == 2 and st["reasons"] == ["hw_thermal_slowdown"]
+    assert s.mark() == 5
+    s.proc = None
+    assert s.stats()["reasons"] == ["nvidia-smi unavailable"]
