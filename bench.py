@@ -304,8 +304,9 @@ def run_cuda(args):
         other_ms = sum(ms for ms, _, on_tc in prof if not on_tc)
         achieved = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
         # the single kernel that dominates the step: conv_ru2_kernel (fused ResidualUnit of the 128-channel stages).
-        # It moves 1024 B per output row against 2*128*128*8 FLOPs (256 FLOP/B, right at the machine balance), and its
-        # epilogues are issue-bound; reported against the HBM roofline, with the tensor figure in `tflops`.
+        # It moves 1024 B per output row against 2*128*128*8 FLOPs (256 FLOP/B, right at the machine balance), and
+        # no unit is above 60 % in ncu (profiles/r01_ncu_summary.txt); reported against the HBM roofline, with the
+        # tensor figure in `tflops`.
         ru = [(prof[i][0], prof[i][1]) for i in range(len(prof) - 1)
               if prof[i + 1][0] < 0.01 and abs(prof[i][1] / max(prof[i + 1][1], 1.0) - 7.0) < 1e-6]
         ru_ms = sum(m for m, _ in ru)
