@@ -173,3 +173,18 @@ def test_bench_clock_sampler_windows():
     assert s.mark() == 5
     s.proc = None
     assert s.stats()["reasons"] == ["nvidia-smi unavailable"]
+
+
+def test_layer_model_flops_match_survey():
+    """tools/layer_model.py (the work model behind DESIGN section 7) reproduces the algorithmic FLOP counts SURVEY.md
+    section 8(d) measured on the reference modules: SAO decode 1089.145 G per 216-frame clip, O12 latent-512 decode
+    1255.219 G per 375-frame clip."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("layer_model", os.path.join(os.path.dirname(H.__file__), "..", "tools",
+                                                                               "layer_model.py"))
+    lm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(lm)
+    for arch, want in (("sao", 1089.145), ("o12", 1255.219)):
+        total = sum(lm.model(l)["gflop"] for l in lm.decoder_layers(lm.ARCH[arch], 1))
+        assert abs(total - want) < 2e-3 * want, (arch, total)
