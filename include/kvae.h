@@ -34,8 +34,15 @@ extern "C" {
 #define KVAE_DECODER 1
 
 /* precision of the convolution arithmetic inside a plan */
-#define KVAE_PREC_BF16 0 /* bf16 tensor-core operands, fp32 accumulation, fp32 residual stream  (<= 1e-3) */
-#define KVAE_PREC_F32 1  /* fp32 CUDA-core arithmetic throughout                                 (<= 1e-5) */
+/* KVAE_PREC_BF16: bf16 tensor-core operands (tcgen05 kind::f16), fp32 accumulation in TMEM.  The residual stream is
+ *   fp32 in registers / TMEM and stored as fp16 in HBM by inference plans (fp32 in training plans); the decoder's
+ *   tail conv multiplies in fp16 with fp32 accumulation.  Waveform error <= 1e-3 against the reference's fp32 output.
+ * KVAE_PREC_F32: still on the tensor cores for every conv whose channel counts are multiples of 64 -- both operands
+ *   are stored as bf16 (hi | lo) halves and each K chunk is multiplied three times (hi*hi + lo*hi + hi*lo), fp32
+ *   accumulation, fp32 residual stream in HBM, fp32 SnakeBeta (range-reduced sine); the io-channel convs and
+ *   architectures with other channel counts use fp32 CUDA-core FMAs.  Waveform error <= 1e-5. */
+#define KVAE_PREC_BF16 0
+#define KVAE_PREC_F32 1
 
 #define KVAE_MAX_STAGES 8
 

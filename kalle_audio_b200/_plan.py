@@ -59,7 +59,8 @@ class PlanRunner:
     def sync_weights(self) -> None:
         """Re-folds weight norm (fp32) and re-packs when any parameter changed (in-place update, load_state_dict,
         .to()).  Load-time cost only; the steady state is a tuple comparison."""
-        fp = tuple((p.data_ptr(), p._version) for p in self._params())
+        module = self.module_ref()
+        fp = (getattr(module, "_weights_epoch", 0),) + tuple((p.data_ptr(), p._version) for p in self._params())
         if fp == self._fingerprint:
             return
         L = _lib.lib()
@@ -257,14 +258,17 @@ class PlanFunction(torch.autograd.Function):
     def backward(ctx, gy):
         gx, grads = ctx.runner.backward(ctx.xin, gy, ctx.ws, ctx.flat, ctx.needs_input_grad[1])
         ctx.ws = None
+        if gx is not None and gx.dtype != ctx.x_dtype:
+            gx = gx.to(ctx.x_dtype)
+        if not getattr(ctx.runner, "return_param_grads", True):
+            # trainer mode: the flat buffer (runner.last_grads) is the product; see AutoencoderTrainer
+            return (None, gx, None, None, None, *([None] * len(ctx.shapes)))
         outs, off = [], 0
         for shape, dt in zip(ctx.shapes, ctx.dtypes):
             n = shape.numel()
             g = grads[off:off + n].view(shape)
             outs.append(g if dt == torch.float32 else g.to(dt))
             off += n
-        if gx is not None and gx.dtype != ctx.x_dtype:
-            gx = gx.to(ctx.x_dtype)
         return (None, gx, None, None, None, *outs)
 
 
@@ -279,6 +283,9 @@ class PlanCache:
         r = self.runners.get(key)
         if r is None:
             r = PlanRunner(module, direction, arch, precision, device)
+            init = getattr(module, "_runner_init", None)      # e.g. AutoencoderTrainer's flat buffer + all-reduce hook
+            if init is not None:
+                init(r)
             self.runners[key] = r
         return r
 

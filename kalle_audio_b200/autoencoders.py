@@ -7,9 +7,11 @@ AudioAutoencoder :230-560, factories :611-731).  The compute is different: ``Oob
 SnakeBeta / residual / bias fused, see csrc/), instead of running ~75 eager kernels per direction.
 
 Precision (``set_precision`` or automatic):
-  * "fp32": fp32 arithmetic end to end -- default for fp32 modules outside autocast (<= 1e-5 vs reference fp32)
-  * "bf16": bf16 tensor-core operands, fp32 accumulation and fp32 residual stream -- default for bf16/fp16
-            modules and under ``torch.autocast`` (<= 1e-3 vs reference fp32)
+  * "fp32": fp32-accurate end to end (<= 1e-5 on the waveform vs reference fp32) -- default for fp32 modules outside
+            autocast.  Tensor-core convs run as a bf16x3 operand split (hi*hi + lo*hi + hi*lo) with fp32 accumulation,
+            fp32 residual stream and fp32 SnakeBeta; the io-channel convs use fp32 CUDA-core FMAs.
+  * "bf16": bf16 tensor-core operands, fp32 accumulation; the residual stream is fp32 in registers / TMEM and fp16
+            in HBM -- default for bf16/fp16 modules and under ``torch.autocast`` (<= 1e-3 vs reference fp32)
 """
 from __future__ import annotations
 
@@ -328,71 +330,60 @@ class AudioAutoencoder(nn.Module):
         return torch.stack(out)
 
     # -- chunked paths (autoencoders.py:429-560) --------------------------------------------------------
+    # Windows are independent clips for the convs, so a GROUP of windows goes through the plan as one batch.  The
+    # reference runs one window at a time precisely to bound memory; here the group size is bounded instead
+    # (``max_windows_per_call`` windows of the whole batch per plan call, 8 by default; 1 = the reference's loop) and
+    # every group is pasted straight into the output, so the peak stays at one group's workspace however long the
+    # clip is.  Like the reference (:475, :537) the per-window encode / decode takes no extra keyword arguments.
+    max_windows_per_call = 8
+
+    def _chunked(self, fn, x, size, hop, out_channels, out_len, to_out, ol):
+        """Shared window loop of encode_audio / decode_audio (autoencoders.py:456-497, 518-560): ``size`` / ``hop`` in
+        input units, ``to_out`` converts an input position to an output position, ``ol`` = trimmed overlap (output units)."""
+        total, bsz = x.shape[2], x.shape[0]
+        starts = _chunk_starts(total, size, hop)
+        n = len(starts)
+        y_final = torch.zeros((bsz, out_channels, out_len), device=x.device)
+        group = max(1, int(self.max_windows_per_call))
+        for g0 in range(0, n, group):
+            idx = range(g0, min(n, g0 + group))
+            y_all = fn(torch.cat([x[:, :, starts[i]:starts[i] + size] for i in idx], dim=0))
+            if y_all.shape[1] != out_channels:
+                raise RuntimeError(f"The expanded size of the tensor ({out_channels}) must match the existing size "
+                                   f"({y_all.shape[1]}) at non-singleton dimension 1 (reference behaviour: chunked encode "
+                                   "needs an encoder that emits latent_dim channels)")
+            for j, i in enumerate(idx):
+                y_chunk = y_all[j * bsz:(j + 1) * bsz]
+                if i == n - 1:
+                    t_end = out_len
+                    t_start = t_end - y_chunk.shape[2]
+                else:
+                    t_start = to_out(starts[i])
+                    t_end = t_start + to_out(size)
+                c0, c1 = 0, y_chunk.shape[2]
+                if i > 0:
+                    t_start += ol
+                    c0 += ol
+                if i < n - 1:
+                    t_end -= ol
+                    c1 -= ol
+                y_final[:, :, t_start:t_end] = y_chunk[:, :, c0:c1]
+        return y_final
+
     def encode_audio(self, audio, chunked=False, overlap=32, chunk_size=128, **kwargs):
         if not chunked:
             return self.encode(audio, **kwargs)
         spl = self.downsampling_ratio
-        total, bsz = audio.shape[2], audio.shape[0]
         cs, ov = chunk_size * spl, overlap * spl
-        starts = _chunk_starts(total, cs, cs - ov)
-        n = len(starts)
-        # all windows in one batched call: [n*B, C, cs] (windows are independent clips for the convs)
-        windows = torch.cat([audio[:, :, s:s + cs] for s in starts], dim=0)
-        y_all = self.encode(windows, **kwargs)
-        y_size = total // spl
-        if y_all.shape[1] != self.latent_dim:
-            raise RuntimeError(f"The expanded size of the tensor ({self.latent_dim}) must match the existing size "
-                               f"({y_all.shape[1]}) at non-singleton dimension 1 (reference behaviour: chunked encode "
-                               "needs an encoder that emits latent_dim channels)")
-        y_final = torch.zeros((bsz, self.latent_dim, y_size), device=audio.device)
-        ol = ov // spl // 2
-        for i, s in enumerate(starts):
-            y_chunk = y_all[i * bsz:(i + 1) * bsz]
-            if i == n - 1:
-                t_end = y_size
-                t_start = t_end - y_chunk.shape[2]
-            else:
-                t_start = s // spl
-                t_end = t_start + cs // spl
-            c0, c1 = 0, y_chunk.shape[2]
-            if i > 0:
-                t_start += ol
-                c0 += ol
-            if i < n - 1:
-                t_end -= ol
-                c1 -= ol
-            y_final[:, :, t_start:t_end] = y_chunk[:, :, c0:c1]
-        return y_final
+        return self._chunked(self.encode, audio, cs, cs - ov, self.latent_dim, audio.shape[2] // spl,
+                             lambda pos: pos // spl, ov // spl // 2)
 
     def decode_audio(self, latents, chunked=False, overlap=32, chunk_size=128, **kwargs):
         if not chunked:
             return self.decode(latents, **kwargs)
-        total, bsz = latents.shape[2], latents.shape[0]
-        starts = _chunk_starts(total, chunk_size, chunk_size - overlap)
-        n = len(starts)
-        windows = torch.cat([latents[:, :, s:s + chunk_size] for s in starts], dim=0)
-        y_all = self.decode(windows, **kwargs)
         spl = self.downsampling_ratio
-        y_size = total * spl
-        y_final = torch.zeros((bsz, self.out_channels, y_size), device=latents.device)
-        ol = (overlap // 2) * spl
-        for i, s in enumerate(starts):
-            y_chunk = y_all[i * bsz:(i + 1) * bsz]
-            if i == n - 1:
-                t_end = y_size
-                t_start = t_end - y_chunk.shape[2]
-            else:
-                t_start = s * spl
-                t_end = t_start + chunk_size * spl
-            c0, c1 = 0, y_chunk.shape[2]
-            if i > 0:
-                t_start += ol
-                c0 += ol
-            if i < n - 1:
-                t_end -= ol
-                c1 -= ol
-            y_final[:, :, t_start:t_end] = y_chunk[:, :, c0:c1]
-        return y_final
+        return self._chunked(self.decode, latents, chunk_size, chunk_size - overlap, self.out_channels,
+                             latents.shape[2] * spl, lambda pos: pos * spl, (overlap // 2) * spl)
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -61,6 +61,18 @@ struct DeviceGuard {
   }
 };
 
+// device that owns a tensor the caller passed in: the stand-alone entry points launch there, whatever the calling
+// thread's current device is (torch code routinely holds tensors on cuda:1 while the current device is 0)
+int device_of(const void* p) {
+  cudaPointerAttributes a;
+  if (p && cudaPointerGetAttributes(&a, p) == cudaSuccess && (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged))
+    return a.device;
+  cudaGetLastError();
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
+
 struct ConvLayer {
   ConvGeom g;
   bool has_bias = true;
@@ -1445,6 +1457,8 @@ int kvae_snake_fwd(const void* x, void* y, const float* alpha, const float* beta
   if (!x || !y || !alpha || !beta) return fail("null argument");
   if (!check_dtype(dtype)) return fail("bad dtype");
   if (B <= 0 || C <= 0 || T <= 0) return 0;  // empty tensor: nothing to do
+  DeviceGuard guard(device_of(x));
+  if (!guard.ok) return fail("cannot select the tensor's device");
   if (static_cast<long long>(B) * C > 65535) return fail("B*C too large");
   dim3 grid(static_cast<unsigned>((T + 1023) / 1024), B * C);
   snake_cf_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, alpha, beta, logscale, C, T,
@@ -1457,6 +1471,8 @@ int kvae_snake_fwd(const void* x, void* y, const float* alpha, const float* beta
 int kvae_weight_norm_fold(const float* v, const float* g, float* w, int dim0, int inner, void* stream) {
   if (!v || !g || !w) return fail("null argument");
   if (dim0 <= 0 || inner <= 0) return 0;
+  DeviceGuard guard(device_of(v));
+  if (!guard.ok) return fail("cannot select the tensor's device");
   weight_norm_fold_kernel<<<dim0, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, g, w, inner);
   KV_CUDA(cudaGetLastError());
   ++g_launches;
@@ -1478,6 +1494,8 @@ int kvae_conv1d_fwd(const void* x, void* y, const float* w, const float* bias, i
   ConvGeom g{transposed ? kConvT : kConv, Cin, Cout, K, stride, dilation, padding};
   const long long T_out = g.out_len(static_cast<int>(T));
   if (T_out <= 0) return fail("input shorter than the kernel");
+  DeviceGuard guard(device_of(x));
+  if (!guard.ok) return fail("cannot select the tensor's device");
   TapPlan tp;
   std::string err;
   if (!build_taps(g, false, tp, err)) return fail(err);
@@ -1519,6 +1537,8 @@ int kvae_conv1d_bwd(const void* x, const void* gy, const float* w, void* gx, flo
   ConvGeom g{transposed ? kConvT : kConv, Cin, Cout, K, stride, dilation, padding};
   const long long T_out = g.out_len(static_cast<int>(T));
   if (T_out <= 0) return fail("input shorter than the kernel");
+  DeviceGuard guard(device_of(x));
+  if (!guard.ok) return fail("cannot select the tensor's device");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int f32 = (dtype == KVAE_F32);
   // ---- weight gradient (torch layout), straight from the API layout through element strides
@@ -1649,7 +1669,9 @@ int kvae_plan_load_params(kvae_plan* p, const float* params, int logscale, int t
       if (!p->fold_desc) KV_CUDA(cudaMalloc(&p->fold_desc, fd.size() * sizeof(FoldDesc)));
       if (!p->snake_desc && !sd.empty()) KV_CUDA(cudaMalloc(&p->snake_desc, sd.size() * sizeof(SnakeDesc)));
       if (!p->scale_all) KV_CUDA(cudaMalloc(&p->scale_all, static_cast<size_t>(rows) * 4));
-      // synchronous copies of pageable host vectors: once per plan and mode, not per step
+      // synchronous copies of pageable host vectors: once per plan and mode, not per step.  A (non-blocking) caller
+      // stream may still be running kernels that read the previous descriptors: drain it before rewriting them
+      KV_CUDA(cudaStreamSynchronize(st));
       KV_CUDA(cudaMemcpy(p->fold_desc, fd.data(), fd.size() * sizeof(FoldDesc), cudaMemcpyHostToDevice));
       if (!sd.empty()) KV_CUDA(cudaMemcpy(p->snake_desc, sd.data(), sd.size() * sizeof(SnakeDesc), cudaMemcpyHostToDevice));
       p->fold_rows = rows; p->fold_tiles = tiles;
@@ -1751,6 +1773,8 @@ int kvae_weight_norm_bwd(const float* v, const float* g, const float* dw, float*
                          void* stream) {
   if (!v || !g || !dw || !dv || !dg) return fail("null argument");
   if (dim0 <= 0 || inner <= 0) return 0;
+  DeviceGuard guard(device_of(v));
+  if (!guard.ok) return fail("cannot select the tensor's device");
   weight_norm_bwd_kernel<<<dim0, 256, 0, static_cast<cudaStream_t>(stream)>>>(v, g, dw, dv, dg, inner);
   KV_CUDA(cudaGetLastError());
   ++g_launches;
@@ -1761,6 +1785,8 @@ int kvae_snake_bwd(const float* x, const float* gy, float* gx, const float* alph
                    float* d_alpha, float* d_beta, long long rows, int C, void* scratch, void* stream) {
   if (!x || !gy || !gx || !alpha || !beta || !d_alpha || !d_beta || !scratch) return fail("null argument");
   if (rows <= 0 || C <= 0) return 0;
+  DeviceGuard guard(device_of(x));
+  if (!guard.ok) return fail("cannot select the tensor's device");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* a = static_cast<float*>(scratch);
   float* ib = a + C;
@@ -1785,6 +1811,8 @@ int kvae_vae_sample_bwd(const void* mean, const void* scale, const void* noise, 
   if (!check_dtype(dtype)) return fail("bad dtype");
   const size_t n = static_cast<size_t>(B) * D * T;
   if (n == 0) return 0;
+  DeviceGuard guard(device_of(mean));
+  if (!guard.ok) return fail("cannot select the tensor's device");
   const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
   vae_sample_bwd_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       mean, scale, noise, gz, gkl, static_cast<float>(1.0 / (static_cast<double>(B) * static_cast<double>(T))), gmean,
@@ -1800,6 +1828,8 @@ int kvae_gaussian_nll(const void* x, const void* xhat, void* gxhat, float* loss,
   if (!check_dtype(dtype)) return fail("bad dtype");
   const size_t n = static_cast<size_t>(B) * per_item;
   if (n == 0) return fail("empty input");
+  DeviceGuard guard(device_of(x));
+  if (!guard.ok) return fail("cannot select the tensor's device");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 1024));
   const double inv_var = std::exp(-2.0 * static_cast<double>(log_sigma));
@@ -1818,6 +1848,8 @@ int kvae_adamw_step(float* params, const float* grads, float* exp_avg, float* ex
   if (!params || !grads || !exp_avg || !exp_avg_sq) return fail("null argument");
   if (step < 1) return fail("step counts from 1");
   if (n == 0) return 0;
+  DeviceGuard guard(device_of(params));
+  if (!guard.ok) return fail("cannot select the tensor's device");
   const float bc1 = 1.f - std::pow(beta1, static_cast<float>(step));
   const float bc2 = 1.f - std::pow(beta2, static_cast<float>(step));
   const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
@@ -1834,6 +1866,8 @@ int kvae_pcm16(const void* wav, int dtype, int16_t* out, size_t n, void* scratch
   if (!wav || !out || !scratch) return fail("null argument");
   if (!check_dtype(dtype)) return fail("bad dtype");
   if (n == 0) return 0;
+  DeviceGuard guard(device_of(wav));
+  if (!guard.ok) return fail("cannot select the tensor's device");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   KV_CUDA(cudaMemsetAsync(scratch, 0, 4, st));
   const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
@@ -1852,6 +1886,8 @@ int kvae_sigma_sample(const void* mean, const void* noise, void* out, size_t n, 
   if (!check_dtype(dtype)) return fail("bad dtype");
   if (n == 0) return 0;
   if (std_noise && per_batch == 0) return fail("per_batch must be > 0");
+  DeviceGuard guard(device_of(mean));
+  if (!guard.ok) return fail("cannot select the tensor's device");
   const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
   sigma_sample_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(mean, noise, out, n, dtype == KVAE_F32,
                                                                              std, std_noise, value, per_batch);
@@ -1866,6 +1902,8 @@ int kvae_vae_sample(const void* mean, const void* scale, const void* noise, void
   if (!check_dtype(dtype)) return fail("bad dtype");
   const size_t n = static_cast<size_t>(B) * D * T;
   if (n == 0) return fail("empty input");
+  DeviceGuard guard(device_of(mean));
+  if (!guard.ok) return fail("cannot select the tensor's device");
   const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 1024));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   vae_sample_kernel<<<blocks, 256, 0, st>>>(mean, scale, noise, out, n, dtype == KVAE_F32,

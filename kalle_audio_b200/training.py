@@ -132,6 +132,12 @@ class GradSync:
             w.wait()
         self._pending.clear()
 
+    def broadcast(self, tensors: List[torch.Tensor], src: int = 0) -> None:
+        """Every rank's ``tensors`` become rank ``src``'s (in place)."""
+        if self.enabled:
+            for t in tensors:
+                dist.broadcast(t, src, group=self.group)
+
     @property
     def grad_scale(self) -> float:
         return 1.0 / self.world
@@ -140,8 +146,14 @@ class GradSync:
 class FlatAdamW:
     """torch.optim.AdamW semantics over flat fp32 buffers, one kernel per buffer (kvae_adamw_step)."""
 
-    def __init__(self, flats: List[torch.Tensor], lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2):
+    def __init__(self, flats: List[torch.Tensor], lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
+                 modules: Optional[List[nn.Module]] = None):
         self.flats = flats
+        # modules whose parameters are views of ``flats``: every plan of theirs (any precision / device key) must
+        # re-pack after a step.  The kernel writes through the flat buffer, which does NOT bump the version counters
+        # of the parameter views, so the plans' (data_ptr, _version) fingerprint cannot see it: bump an explicit
+        # weights epoch that the fingerprint includes (PlanRunner.sync_weights).
+        self.modules = list(modules or [])
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.exp_avg = [torch.zeros_like(f) for f in flats]
         self.exp_avg_sq = [torch.zeros_like(f) for f in flats]
@@ -156,7 +168,11 @@ class FlatAdamW:
             _lib.check(L.kvae_adamw_step(f.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), f.numel(), self.lr,
                                          self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count,
                                          grad_scale, _lib.stream_ptr(f.device)))
-            f.add_(0)   # bump the version counter the parameter views share: the plans re-pack on next use
+        for m in self.modules:
+            m._weights_epoch = getattr(m, "_weights_epoch", 0) + 1
+
+    def state(self) -> List[torch.Tensor]:
+        return self.exp_avg + self.exp_avg_sq
 
 
 class AutoencoderTrainer:
@@ -169,7 +185,7 @@ class AutoencoderTrainer:
 
     def __init__(self, autoencoder: nn.Module, lr: float = 1e-4, betas=(0.8, 0.99), eps: float = 1e-8,
                  weight_decay: float = 1e-3, kl_weight: float = 1e-6, log_sigma: float = 0.0,
-                 precision: Optional[str] = "bf16", process_group=None):
+                 precision: Optional[str] = "bf16", process_group=None, data_parallel: bool = True):
         self.autoencoder = autoencoder
         self.encoder, self.decoder = autoencoder.encoder, autoencoder.decoder
         dev = next(self.encoder.parameters()).device
@@ -181,12 +197,49 @@ class AutoencoderTrainer:
         self.flat_dec = flatten_parameters(self.decoder)
         self.kl_weight, self.log_sigma = kl_weight, log_sigma
         self.sync = GradSync(process_group)
-        self.opt = FlatAdamW([self.flat_enc, self.flat_dec], lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        if not data_parallel:       # a single-process trainer inside an initialised process group
+            self.sync.enabled, self.sync.world = False, 1
+        self.opt = FlatAdamW([self.flat_enc, self.flat_dec], lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                             modules=[self.encoder, self.decoder])
         self._grads: Dict[str, torch.Tensor] = {}
         for name, mod, flat in (("enc", self.encoder, self.flat_enc), ("dec", self.decoder, self.flat_dec)):
-            r = mod.runner(dev)
-            r.flat_master = flat
-            r.grads_ready_hook = self._make_hook(name)
+            # applied to every runner the module creates from now on (another precision, a rebuilt cache after .to()):
+            # the flat master buffer, the all-reduce hook, and no per-parameter gradient views -- the trainer consumes
+            # the flat gradient buffer, and views handed to autograd would be cloned by AccumulateGrad while NCCL
+            # reduces the buffer in place
+            mod._runner_init = self._make_runner_init(name, flat)
+            mod._plans.clear()
+            mod.runner(dev)
+        self.broadcast_parameters()
+
+    def _make_runner_init(self, name, flat):
+        def init(runner):
+            runner.flat_master = flat
+            runner.grads_ready_hook = self._make_hook(name)
+            runner.return_param_grads = False
+        return init
+
+    def broadcast_parameters(self, src: int = 0) -> None:
+        """Every rank continues from rank ``src``'s parameters and optimizer moments (what DDP / Lightning do at
+        construction and on resume in the reference's trainer): replicas that were seeded or loaded differently would
+        otherwise diverge silently, since only gradients are exchanged afterwards."""
+        if not self.sync.enabled:
+            return
+        step = torch.tensor([self.opt.step_count], device=self.flat_enc.device, dtype=torch.int64)
+        self.sync.broadcast([self.flat_enc, self.flat_dec] + self.opt.state() + [step], src)
+        self.opt.step_count = int(step)
+        for m in (self.encoder, self.decoder):
+            m._weights_epoch = getattr(m, "_weights_epoch", 0) + 1
+
+    def replica_checksum_spread(self) -> float:
+        """max - min over ranks of the fp64 sum of all parameters: 0.0 when the replicas are in sync."""
+        cs = (self.flat_enc.double().sum() + self.flat_dec.double().sum()).reshape(1)
+        if not self.sync.enabled:
+            return 0.0
+        hi, lo = cs.clone(), cs.clone()
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.sync.group)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.sync.group)
+        return float(hi - lo)
 
     def _make_hook(self, name):
         def hook(runner, grads):

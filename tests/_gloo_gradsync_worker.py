@@ -19,5 +19,10 @@ b = torch.full((17,), float(rank + 1))                       # "encoder" gradien
 sync.launch(a)      # launched first, overlaps the work that produces b
 sync.launch(b)
 sync.wait()
-torch.save({"a": a, "b": b, "scale": sync.grad_scale, "world": sync.world}, sys.argv[4])
+# initial-state broadcast (AutoencoderTrainer.broadcast_parameters): ranks seeded differently continue from rank 0
+torch.manual_seed(100 + rank)
+w = torch.randn(333)
+m1 = torch.randn(333)
+sync.broadcast([w, m1], 0)
+torch.save({"a": a, "b": b, "scale": sync.grad_scale, "world": sync.world, "w": w, "m1": m1}, sys.argv[4])
 dist.destroy_process_group()

@@ -26,13 +26,14 @@ per = 4 // world
 
 
 def one_step(xb, nb, group_enabled):
-    m = H.build("mid", 0, snake_seed=7).to(dev).train()
-    tr = TR.AutoencoderTrainer(m, lr=1e-3, kl_weight=1e-2, log_sigma=-1.0, precision="fp32")
-    tr.sync.enabled = tr.sync.enabled and group_enabled
-    if not group_enabled:
-        tr.sync.world = 1
+    # data-parallel run: every rank initialises from its OWN seed; the trainer broadcasts rank 0's parameters
+    # (seed 0) at construction, so the ranks still end up with the single-process result
+    m = H.build("mid", rank if group_enabled else 0, snake_seed=7 + (rank if group_enabled else 0)).to(dev).train()
+    tr = TR.AutoencoderTrainer(m, lr=1e-3, kl_weight=1e-2, log_sigma=-1.0, precision="fp32", data_parallel=group_enabled)
+    assert tr.replica_checksum_spread() == 0.0
     tr.training_step(xb.to(dev), nb.to(dev))
     torch.cuda.synchronize(dev)
+    assert tr.replica_checksum_spread() == 0.0
     return tr.flat_enc.detach().cpu().clone(), tr.flat_dec.detach().cpu().clone()
 
 

@@ -20,3 +20,12 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_terminal_summary(terminalreporter, exitstatus, config):
+    """Parity numbers recorded by the tests (helpers.report) are printed after the run, so `pytest -q` shows them."""
+    import helpers
+    if helpers.REPORT:
+        terminalreporter.write_line("measured parity numbers (max-abs error vs the oracle / the reference's goldens):")
+        for name, value in helpers.REPORT:
+            terminalreporter.write_line(f"  {name}: {value}")

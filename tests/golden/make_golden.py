@@ -20,6 +20,11 @@ Fixtures (all float32, little-endian .npz):
                     the reference modules + the reference's vae_sample (generator branch of
                     training/autoencoders.py:221-352 with the Gaussian-NLL + KL objective of BASELINE config 5)
   train_mid.npz     same on the C=64 model: loss terms, per-parameter gradient norms and a strided sample
+  o12_d256.npz      12.5 Hz shape, latent 256 ("dim512"), [1,256,16] <-> [1,1,20480], full outputs
+  o12_d1024.npz     12.5 Hz shape, latent 1024 ("dim2048"), [1,1024,16] <-> [1,1,20480], full outputs
+  o12_full.npz      BASELINE configs 3 and 4 at their own length: latent 512, [1,512,375] -> [1,1,480000] (config 3's
+                    clip), and latent 1024, decode_audio(chunked=True, chunk_size=128, overlap=32) AND unchunked over
+                    T=375 (config 4); sampled points (clip edges, every window seam, every 97th sample) + sums
 Weights of the larger models are NOT stored: they are re-created from the recorded seed by the
 same construction order (nn.Conv1d / nn.ConvTranspose1d default init), and the fixture carries a
 float64 checksum of every parameter so a mismatch is detected rather than silently compared.
@@ -88,6 +93,8 @@ CONFIGS = {
     "mid": ae_config(64, [1, 2, 4], [2, 4, 5], 128, 64, 2, 16000),
     "sao": ae_config(128, [1, 2, 4, 8, 16], [2, 4, 4, 8, 8], 128, 64, 2, 44100),
     "o12_d512": ae_config(128, [1, 2, 4, 8, 16], [2, 4, 4, 5, 8], 1024, 512, 1, 16000),
+    "o12_d256": ae_config(128, [1, 2, 4, 8, 16], [2, 4, 4, 5, 8], 512, 256, 1, 16000),
+    "o12_d1024": ae_config(128, [1, 2, 4, 8, 16], [2, 4, 4, 5, 8], 2048, 1024, 1, 16000),
 }
 
 
@@ -161,11 +168,48 @@ def train_fixtures(ae_mod, bn_mod):
     np.savez_compressed(os.path.join(HERE, "train_mid.npz"), **out)
 
 
+def o12_fixtures(ae_mod):
+    """BASELINE configs 3 / 4 architectures (12.5 Hz, strides 2,4,4,5,8) at latent 256 / 1024 (short clip, full
+    outputs) and at the configs' own length T = 375 (sampled points)."""
+    torch.set_grad_enabled(False)
+    for name, D in (("o12_d256", 256), ("o12_d1024", 1024)):
+        m = build(ae_mod, name, 0)
+        z = torch.randn(1, D, 16, generator=torch.Generator().manual_seed(1))
+        x = 0.1 * torch.randn(1, 1, 1280 * 16, generator=torch.Generator().manual_seed(2))
+        cs = checksums(m.state_dict())
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), dec_out=m.decode(z).numpy(), enc_out=m.encode(x).numpy(),
+                            cs_keys=np.array(list(cs.keys())), cs_vals=np.array(list(cs.values()), dtype=np.float64))
+    L = 480000
+    seams = [s * 1280 for s in (16, 96, 112, 192, 208, 247, 263, 288, 359)]    # window starts / paste boundaries of 128/32 over 375
+    idx = torch.cat([torch.arange(0, 4096), torch.arange(L - 4096, L), torch.arange(0, L, 97)] +
+                    [torch.arange(s - 640, s + 640) for s in seams]).unique()
+    out = {"idx": idx.numpy()}
+    m = build(ae_mod, "o12_d512", 0)
+    z = torch.randn(1, 512, 375, generator=torch.Generator().manual_seed(1))
+    y = m.decode(z)
+    out.update(d512_at_idx=y[:, :, idx].numpy(), d512_abs_max=float(y.abs().max()), d512_sum=float(y.double().sum()),
+               d512_sq_sum=float((y.double() ** 2).sum()))
+    m = build(ae_mod, "o12_d1024", 0)
+    z = torch.randn(1, 1024, 375, generator=torch.Generator().manual_seed(1))
+    y = m.decode_audio(z, chunked=False)
+    yc = m.decode_audio(z, chunked=True, overlap=32, chunk_size=128)
+    out.update(d1024_at_idx=y[:, :, idx].numpy(), d1024_chunked_at_idx=yc[:, :, idx].numpy(),
+               d1024_abs_max=float(y.abs().max()), d1024_sq_sum=float((y.double() ** 2).sum()),
+               d1024_chunked_sq_sum=float((yc.double() ** 2).sum()),
+               d1024_chunked_vs_full_max=float((y - yc).abs().max()))
+    np.savez_compressed(os.path.join(HERE, "o12_full.npz"), **out)
+    torch.set_grad_enabled(True)
+
+
 def main():
     ae_mod, bn_mod = import_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "train":      # only the training fixtures
         train_fixtures(ae_mod, bn_mod)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "o12":        # only the 12.5 Hz fixtures at configs 3 / 4 sizes
+        o12_fixtures(ae_mod)
+        return
+    o12_fixtures(ae_mod)
     train_fixtures(ae_mod, bn_mod)
     torch.set_grad_enabled(False)
 

@@ -6,6 +6,11 @@ import numpy as np
 import torch
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+REPORT = []      # (name, value) pairs printed by conftest.pytest_terminal_summary
+
+
+def report(name, value):
+    REPORT.append((name, f"{value:.3e}" if isinstance(value, float) else str(value)))
 
 
 def ae_config(channels, c_mults, strides, enc_latent, dec_latent, io_channels, sample_rate):
@@ -35,6 +40,8 @@ CONFIGS = {
     "mid": ae_config(64, [1, 2, 4], [2, 4, 5], 128, 64, 2, 16000),
     "sao": ae_config(128, [1, 2, 4, 8, 16], [2, 4, 4, 8, 8], 128, 64, 2, 44100),
     "o12_d512": ae_config(128, [1, 2, 4, 8, 16], [2, 4, 4, 5, 8], 1024, 512, 1, 16000),
+    "o12_d256": ae_config(128, [1, 2, 4, 8, 16], [2, 4, 4, 5, 8], 512, 256, 1, 16000),
+    "o12_d1024": ae_config(128, [1, 2, 4, 8, 16], [2, 4, 4, 5, 8], 2048, 1024, 1, 16000),
 }
 
 

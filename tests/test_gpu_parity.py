@@ -176,25 +176,34 @@ def test_errors(dev):
 
 # --------------------------------------------------------------------------- full-size models
 def test_sao_full_size_decode_and_encode(dev):
-    """BASELINE configs 1/2 shapes: z [1,64,216] -> [1,2,442368] and back, against the reference's outputs."""
+    """BASELINE configs 1/2 shapes: z [1,64,216] -> [1,2,442368] and back.  EVERY one of the 884 736 output samples is
+    compared with the oracle run on this box (the oracle itself is pinned to the reference at the golden points,
+    tests/test_oracle_golden.py), plus the reference's recorded points directly."""
     g = H.golden("sao_full")
     m = H.build("sao", 0)
     H.check_checksums(m.state_dict(), g)
+    sd = {n: p.clone() for n, p in m.state_dict().items()}
+    zc = torch.randn(1, 64, 216, generator=torch.Generator().manual_seed(1))
+    xc = 0.1 * torch.randn(1, 2, 442368, generator=torch.Generator().manual_seed(2))
+    ref = O.oobleck_decoder(H.split_sd(sd, "decoder."), zc, H.strides_of("sao"))
     m.to(dev).set_precision("bf16")
-    z = torch.randn(1, 64, 216, generator=torch.Generator().manual_seed(1)).to(dev)
-    x = (0.1 * torch.randn(1, 2, 442368, generator=torch.Generator().manual_seed(2))).to(dev)
-    y = m.decode(z)
+    y = m.decode(zc.to(dev))
     assert y.shape == (1, 2, 442368)
     idx = H.t(g["dec_idx"]).long()
-    err = maxerr(y[:, :, idx.to(dev)], g["dec_out_at_idx"])
-    print(f"SAO bf16 decode max-abs err {err:.3e} (abs max {float(g['dec_abs_max']):.3f})")
+    assert maxerr(ref[:, :, idx], g["dec_out_at_idx"]) <= 5e-6          # the checker agrees with the reference here
+    err = maxerr(y, ref)
+    H.report("SAO decode bf16, all 884736 samples (budget 1e-3, abs max %.3f)" % float(g["dec_abs_max"]), err)
     assert err <= TOL_BF16
+    assert maxerr(y[:, :, idx.to(dev)], g["dec_out_at_idx"]) <= TOL_BF16
     assert abs(float((y.double() ** 2).sum()) - float(g["dec_sq_sum"])) <= 2e-2 * float(g["dec_sq_sum"])
-    e = m.encode(x)
-    scale = float(np.abs(g["enc_out"]).max())
+    e = m.encode(xc.to(dev))
     erre = maxerr(e, g["enc_out"])
-    print(f"SAO bf16 encode max-abs err {erre:.3e} (abs max {scale:.3f})")
+    H.report("SAO encode bf16, all latents (abs max %.3f)" % float(np.abs(g["enc_out"]).max()), erre)
     assert erre <= bf16_tol(g["enc_out"])
+    m.set_precision("fp32")
+    err32 = maxerr(m.decode(zc.to(dev)), ref)
+    H.report("SAO decode fp32 mode, all samples (budget 1e-5)", err32)
+    assert err32 <= TOL_F32
 
 
 @pytest.mark.parametrize("B,T", [(1, 6), (2, 24)])
@@ -216,18 +225,54 @@ def test_sao_fp32_mode_short_clip(dev, B, T):
     assert err_e <= 5e-5 * max(1.0, float(ref_e.abs().max()))
 
 
-def test_o12_latent512_decode_encode(dev):
-    g = H.golden("o12_d512")
-    m = H.build("o12_d512", 0)
+@pytest.mark.parametrize("name,D", [("o12_d256", 256), ("o12_d512", 512), ("o12_d1024", 1024)])
+def test_o12_short_clip_decode_encode(dev, name, D):
+    """The three 12.5 Hz widths ("dim512" / "dim1024" / "dim2048") against the reference's recorded outputs: absolute
+    1e-3 on the waveform in bf16 mode, 1e-5 in fp32 mode."""
+    g = H.golden(name)
+    m = H.build(name, 0)
     H.check_checksums(m.state_dict(), g)
     m.to(dev).set_precision("bf16")
-    z = torch.randn(1, 512, 16, generator=torch.Generator().manual_seed(1)).to(dev)
+    z = torch.randn(1, D, 16, generator=torch.Generator().manual_seed(1)).to(dev)
     x = (0.1 * torch.randn(1, 1, 1280 * 16, generator=torch.Generator().manual_seed(2))).to(dev)
     y = m.decode(z)
-    assert y.shape == (1, 1, 20480) and maxerr(y, g["dec_out"]) <= TOL_BF16
+    err = maxerr(y, g["dec_out"])
+    H.report(f"O12 latent {D} decode bf16 T=16", err)
+    assert y.shape == (1, 1, 20480) and err <= TOL_BF16
     e = m.encode(x)
-    assert e.shape == (1, 1024, 16)
-    assert maxerr(e, g["enc_out"]) <= bf16_tol(g["enc_out"])
+    assert e.shape == (1, 2 * D, 16)
+    erre = maxerr(e, g["enc_out"])
+    H.report(f"O12 latent {D} encode bf16 T=16 (abs max {float(np.abs(g['enc_out']).max()):.3f})", erre)
+    assert erre <= bf16_tol(g["enc_out"])
+    m.set_precision("fp32")
+    err32 = maxerr(m.decode(z), g["dec_out"])
+    H.report(f"O12 latent {D} decode fp32 mode T=16", err32)
+    assert err32 <= TOL_F32
+
+
+def test_config3_o12_latent512_full_length_vs_oracle(dev):
+    """BASELINE config 3 at its own clip length: [2,512,375] -> [2,1,480000]; every sample against the oracle run on
+    this box, clip 0 also against the reference's recorded points (tests/golden/o12_full.npz)."""
+    g = H.golden("o12_full")
+    m = H.build("o12_d512", 0)
+    sd = H.split_sd({n: p.clone() for n, p in m.state_dict().items()}, "decoder.")
+    z = torch.cat([torch.randn(1, 512, 375, generator=torch.Generator().manual_seed(1)),
+                   torch.randn(1, 512, 375, generator=torch.Generator().manual_seed(5))])
+    ref = O.oobleck_decoder(sd, z, H.strides_of("o12_d512"))
+    idx = H.t(g["idx"]).long()
+    assert maxerr(ref[:1, :, idx], g["d512_at_idx"]) <= 5e-6
+    m.to(dev).set_precision("bf16")
+    y = m.decode(z.to(dev))
+    assert y.shape == (2, 1, 480000)
+    err = maxerr(y, ref)
+    H.report("config 3 (O12 latent 512, T=375) decode bf16, all 2 x 480000 samples (budget 1e-3, abs max %.3f)"
+             % float(g["d512_abs_max"]), err)
+    assert err <= TOL_BF16
+    assert maxerr(y[:1, :, idx.to(dev)], g["d512_at_idx"]) <= TOL_BF16
+    m.set_precision("fp32")
+    err32 = maxerr(m.decode(z[:1].to(dev)), ref[:1])
+    H.report("config 3 decode fp32 mode, all samples (budget 1e-5)", err32)
+    assert err32 <= TOL_F32
 
 
 def test_batch_items_are_independent(dev):
@@ -417,21 +462,39 @@ def test_host_pipeline_equals_direct_calls(dev):
         pipe.submit(zs[0].to(dev), y)
 
 
-def test_config4_streaming_chunks_equal_unchunked_o12_latent1024(dev):
+def test_config4_chunked_decode_o12_latent1024_vs_oracle(dev):
     """BASELINE config 4: O12 latent-1024 decoder, decode_audio(chunked=True, chunk 128, overlap 32) over T=375
-    (4 windows) equals the unchunked decode: overlap/2 = 16 frames > receptive field 10 frames."""
-    torch.manual_seed(0)
-    dec = k.OobleckDecoder(out_channels=1, channels=128, latent_dim=1024, c_mults=[1, 2, 4, 8, 16],
-                           strides=[2, 4, 4, 5, 8], use_snake=True, final_tanh=False).eval().to(dev).set_precision("bf16")
-    ae = k.AudioAutoencoder(None, dec, latent_dim=1024, downsampling_ratio=1280, sample_rate=16000, io_channels=1)
-    z = torch.randn(1, 1024, 375, device=dev)
-    full = ae.decode_audio(z)
-    chunked = ae.decode_audio(z, chunked=True, overlap=32, chunk_size=128)
+    (4 windows) against the oracle's restatement of the reference's chunk/overlap stitching
+    (stable_audio_tools/models/autoencoders.py:514-560) run on this box, against the reference's recorded points,
+    and against the unchunked decode (overlap/2 = 16 frames > receptive field 10 frames)."""
+    g = H.golden("o12_full")
+    m = H.build("o12_d1024", 0)
+    sd = H.split_sd({n: p.clone() for n, p in m.state_dict().items()}, "decoder.")
+    st = H.strides_of("o12_d1024")
+    zc = torch.randn(1, 1024, 375, generator=torch.Generator().manual_seed(1))
+    ref = O.decode_audio_chunked(lambda zz: O.oobleck_decoder(sd, zz, st), zc, 1280, 1, overlap=32, chunk_size=128)
+    idx = H.t(g["idx"]).long()
+    assert maxerr(ref[:, :, idx], g["d1024_chunked_at_idx"]) <= 5e-6
+    m.to(dev).set_precision("bf16")
+    z = zc.to(dev)
+    full = m.decode_audio(z)
+    chunked = m.decode_audio(z, chunked=True, overlap=32, chunk_size=128)
     assert full.shape == chunked.shape == (1, 1, 480000)
+    err = maxerr(chunked, ref)
+    H.report("config 4 (O12 latent 1024, T=375, chunked 128/32) decode bf16, all 480000 samples (budget 1e-3, abs max %.3f)"
+             % float(g["d1024_abs_max"]), err)
+    assert err <= TOL_BF16
+    assert maxerr(chunked[:, :, idx.to(dev)], g["d1024_chunked_at_idx"]) <= TOL_BF16
+    assert maxerr(full[:, :, idx.to(dev)], g["d1024_at_idx"]) <= TOL_BF16
     # identical arithmetic per output row away from window edges -> differences only from fp32 summation order: none
     assert float((full - chunked).abs().max()) <= 1e-6
-    dec.enable_cuda_graphs(True)
-    assert torch.equal(ae.decode_audio(z, chunked=True, overlap=32, chunk_size=128), chunked)
+    m.decoder.enable_cuda_graphs(True)
+    assert torch.equal(m.decode_audio(z, chunked=True, overlap=32, chunk_size=128), chunked)
+    m.decoder.enable_cuda_graphs(False)
+    m.set_precision("fp32")
+    err32 = maxerr(m.decode_audio(z, chunked=True, overlap=32, chunk_size=128), ref)
+    H.report("config 4 chunked decode fp32 mode, all samples (budget 1e-5)", err32)
+    assert err32 <= TOL_F32
 
 
 def test_pcm16_tail_bit_exact(dev):
@@ -500,7 +563,8 @@ def test_full_size_properties_sao_bench_shape(dev):
     assert float((e[5:6] - m.encode(x[5:6])).abs().max()) == 0.0
     # golden anchor at this size: clip 0 of the batch is the fixture's input (same seed), sampled points
     g = H.golden("sao_full")
-    z0 = torch.randn(1, 64, 216, generator=torch.Generator().manual_seed(1))
-    if torch.equal(z0, z[:1].cpu()):
-        idx = H.t(g["dec_idx"]).long().to(dev)
-        assert maxerr(y[:1][:, :, idx], g["dec_out_at_idx"]) <= TOL_BF16
+    z[0] = torch.randn(1, 64, 216, generator=torch.Generator().manual_seed(1))[0].to(dev)
+    idx = H.t(g["dec_idx"]).long().to(dev)
+    err = maxerr(m.decode(z)[:1][:, :, idx], g["dec_out_at_idx"])
+    H.report("configs[1] shape (16 x 216 frames): clip 0 at the reference's recorded points", err)
+    assert err <= TOL_BF16

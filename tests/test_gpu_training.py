@@ -295,6 +295,38 @@ def test_trainer_step_updates_and_reduces_loss(dev):
     assert float((y1 - y2).abs().max()) <= 1e-6
 
 
+def test_other_precision_runner_sees_every_optimizer_step(dev):
+    """A second runner of the same module (fp32-mode validation between bf16 training steps) must re-pack after EVERY
+    optimizer step: kvae_adamw_step writes through the flat buffer, which does not bump the parameter views' version
+    counters, so the trainer bumps an explicit weights epoch that every runner's fingerprint includes."""
+    m = H.build("mid", 0, snake_seed=7).to(dev).train()
+    x = 0.1 * torch.randn(2, 2, 40 * 16, generator=torch.Generator().manual_seed(9)).to(dev)
+    noise = torch.randn(2, 64, 16, generator=torch.Generator().manual_seed(10)).to(dev)
+    tr = TR.AutoencoderTrainer(m, lr=5e-3, kl_weight=1e-4, log_sigma=-2.0, precision="bf16")
+
+    def fresh_eval():
+        m2 = H.build("mid", 0, snake_seed=7).to(dev)
+        m2.load_state_dict(m.state_dict())
+        with torch.no_grad():
+            return m2.set_precision("fp32").decode(noise)
+
+    outs = []
+    for _ in range(3):
+        m.set_precision("bf16")
+        tr.training_step(x, noise)
+        m.set_precision("fp32")
+        with torch.no_grad():
+            y = m.decode(noise)          # the fp32 runner: created at the first pass, must not serve stale weights later
+        assert float((y - fresh_eval()).abs().max()) <= 1e-6
+        outs.append(y)
+    assert float((outs[1] - outs[0]).abs().max()) > 1e-5 and float((outs[2] - outs[1]).abs().max()) > 1e-5
+    assert all(p.grad is None for p in m.parameters())      # trainer mode: the flat gradient buffer is the product
+    # .to() rebuilds the plan cache; the trainer's flat buffers and hook are re-attached to the new runners
+    m.set_precision("bf16")
+    m.encoder._plans.clear(); m.decoder._plans.clear()
+    assert np.isfinite(float(tr.training_step(x, noise)["loss"]))
+
+
 def test_training_step_config5_shape_properties(dev):
     """BASELINE configs[4] per-GPU shape (4 clips x 5.016 s, bf16 mode): finite loss and gradients, the backward is
     linear in the incoming gradient, and two runs agree (the only non-determinism is the order of fp32 atomics)."""

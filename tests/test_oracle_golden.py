@@ -106,6 +106,47 @@ def test_o12_latent512_matches_reference():
     assert np.abs(y.numpy() - g["dec_out"]).max() <= 5e-6
 
 
+@pytest.mark.parametrize("name,D", [("o12_d256", 256), ("o12_d1024", 1024)])
+def test_o12_latent256_and_1024_match_reference(name, D):
+    """The other two 12.5 Hz widths the reference ships ("dim512" / "dim2048"): decoder and encoder, full outputs."""
+    g = H.golden(name)
+    m = H.build(name, 0)
+    sd = m.state_dict()
+    H.check_checksums(sd, g)
+    st = H.strides_of(name)
+    z = torch.randn(1, D, 16, generator=torch.Generator().manual_seed(1))
+    x = 0.1 * torch.randn(1, 1, 1280 * 16, generator=torch.Generator().manual_seed(2))
+    y = O.oobleck_decoder(H.split_sd(sd, "decoder."), z, st)
+    e = O.oobleck_encoder(H.split_sd(sd, "encoder."), x, st)
+    assert y.shape == (1, 1, 1280 * 16) and e.shape == (1, 2 * D, 16)
+    assert np.abs(y.numpy() - g["dec_out"]).max() <= 5e-6
+    assert np.abs(e.numpy() - g["enc_out"]).max() <= 5e-6 * max(1.0, np.abs(g["enc_out"]).max())
+
+
+def test_o12_configs_3_and_4_at_full_length_match_reference():
+    """BASELINE config 3's clip (latent 512, T = 375 -> 480 000 samples) and config 4 (latent 1024, T = 375, unchunked
+    and decode_audio(chunked=True, chunk_size=128, overlap=32)) against the reference's outputs at the sampled points
+    (clip edges, every window seam, every 97th sample) and its energy."""
+    g = H.golden("o12_full")
+    idx = H.t(g["idx"]).long()
+    sd = H.split_sd(H.build("o12_d512", 0).state_dict(), "decoder.")
+    st = H.strides_of("o12_d512")
+    z = torch.randn(1, 512, 375, generator=torch.Generator().manual_seed(1))
+    y = O.oobleck_decoder(sd, z, st)
+    assert y.shape == (1, 1, 480000)
+    assert np.abs(y[:, :, idx].numpy() - g["d512_at_idx"]).max() <= 5e-6
+    assert abs(float((y.double() ** 2).sum()) - float(g["d512_sq_sum"])) <= 1e-4 * float(g["d512_sq_sum"])
+    sd = H.split_sd(H.build("o12_d1024", 0).state_dict(), "decoder.")
+    z = torch.randn(1, 1024, 375, generator=torch.Generator().manual_seed(1))
+    dec = lambda zz: O.oobleck_decoder(sd, zz, st)
+    yc = O.decode_audio_chunked(dec, z, 1280, 1, overlap=32, chunk_size=128)
+    assert np.abs(yc[:, :, idx].numpy() - g["d1024_chunked_at_idx"]).max() <= 5e-6
+    assert abs(float((yc.double() ** 2).sum()) - float(g["d1024_chunked_sq_sum"])) <= 1e-4 * float(g["d1024_chunked_sq_sum"])
+    # the reference's own chunked and unchunked outputs agree to fp32 noise (overlap / 2 = 16 > receptive field 10)
+    assert float(g["d1024_chunked_vs_full_max"]) <= 1e-6
+    assert np.abs(g["d1024_chunked_at_idx"] - g["d1024_at_idx"]).max() <= 1e-6
+
+
 def test_sao_full_size_decode_matches_reference():
     """BASELINE config 1: SAO-shape decoder, z [1,64,216] -> [1,2,442368], fp32 CPU."""
     g = H.golden("sao_full")

@@ -144,3 +144,8 @@ def test_grad_sync_gloo_world2(tmp_path):
         assert torch.equal(r["a"], want_a)
         assert torch.equal(r["b"], torch.full((17,), 3.0))
         assert r["scale"] == 0.5 and r["world"] == 2
+    # broadcast of the initial parameters / optimizer moments: both ranks hold rank 0's values (seed 100)
+    torch.manual_seed(100)
+    w0, m0 = torch.randn(333), torch.randn(333)
+    for r in res:
+        assert torch.equal(r["w"], w0) and torch.equal(r["m1"], m0)
