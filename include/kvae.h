@@ -48,8 +48,8 @@ extern "C" {
 
 /* Architecture of one OobleckEncoder / OobleckDecoder: the constructor arguments of
  * autoencoders.py:117-125 (encoder) and :151-160 (decoder).  use_snake must be true and
- * antialias_activation / use_nearest_upsample false (the only combination the reference's configs
- * use); the Python layer raises NotImplementedError for the others. */
+ * antialias_activation false (the only combination the reference's configs use); the Python layer
+ * raises NotImplementedError for the others. */
 typedef struct kvae_arch {
   int io_channels;                /* in_channels (encoder) / out_channels (decoder)            */
   int channels;                   /* base width, 128                                           */
@@ -58,6 +58,13 @@ typedef struct kvae_arch {
   int c_mults[KVAE_MAX_STAGES];   /* as passed to the constructor (without the implicit 1)     */
   int strides[KVAE_MAX_STAGES];
   int final_tanh;                 /* decoder only                                              */
+  int use_nearest_upsample;       /* decoder only: DecoderBlock's Upsample(nearest, x stride) + WNConv1d(k = 2*stride,
+                                     padding 'same', bias=False) branch (autoencoders.py:87-96).  Nearest upsampling
+                                     followed by a stride-1 conv IS a transposed conv: the plan runs it as
+                                     ConvTranspose1d(k = 3*stride - 1, stride, padding = stride, output_padding = 1)
+                                     whose taps are sums of the conv's taps (w'[k'] = sum of w[k] over
+                                     k = 2s-1-k' .. 3s-2-k' clipped to 0 .. 2s-1), which kvae_plan_conv_info reports
+                                     and kvae_plan_set_conv expects ([Cin, Cout, 3*stride - 1]).  Inference only. */
 } kvae_arch;
 
 typedef struct kvae_plan kvae_plan;
@@ -96,6 +103,27 @@ int kvae_decode(kvae_plan* plan, const void* z, int z_dtype, void* wav, int wav_
 /* OobleckEncoder.forward (:146): wav [B, io_channels, L] -> lat [B, latent_dim, L/prod(strides)]. */
 int kvae_encode(kvae_plan* plan, const void* wav, int wav_dtype, void* lat, int lat_dtype, int B, long long L,
                 void* workspace, size_t workspace_bytes, void* stream);
+/* Ragged batches -- what the reference gets by calling the module once per clip (pretransform iterate_batch,
+ * autoencoders.py:287-300; the per-item encode of twj_dataset.py:239): clip b holds valid_len[b] <= T valid input
+ * positions and is zero-padded to T by the caller; valid_len is a HOST array of B ints.  The library re-creates the
+ * reference's end-of-clip zero padding per clip inside every layer, so the first kvae_plan_out_length(valid_len[b])
+ * output positions of clip b equal the stand-alone call on that clip -- including audio lengths that are not
+ * multiples of the ratio, where the reference's strided convs floor; the rest of its output row is unspecified.
+ * For the encoder T must still be a multiple of prod(strides) (pad up); valid_len need not be. */
+int kvae_decode_ragged(kvae_plan* plan, const void* z, int z_dtype, void* wav, int wav_dtype, int B, long long T,
+                       const int* valid_len, void* workspace, size_t workspace_bytes, void* stream);
+int kvae_encode_ragged(kvae_plan* plan, const void* wav, int wav_dtype, void* lat, int lat_dtype, int B, long long L,
+                       const int* valid_len, void* workspace, size_t workspace_bytes, void* stream);
+/* Output length of a pass over an input of length T by the reference's own arithmetic (every conv floors,
+ * L_out = (L + 2p - d(K-1) - 1)/s + 1): T*prod(strides) for a decoder; for an encoder floor-ish, and not simply
+ * T / prod(strides) when a stride is odd (the stride-5 stage of the 12.5 Hz models maps 159 rows to 32). */
+long long kvae_plan_out_length(const kvae_plan* plan, long long T);
+/* Dataset-side preprocessing of twj_dataset.py:231-235 for a batch: B mono fp32 clips stored back to back in `wav`
+ * (clip b = wav[offsets[b] .. +lens[b]); offsets / lens are DEVICE arrays) -> out [B, channels, L_pad] fp32 =
+ * librosa.util.normalize(clip) * gain (peak normalisation; gain 0.95 there) copied to every channel (the stereo
+ * duplication of :235) and zero-padded.  scratch: >= 4*B bytes. */
+int kvae_prep_mono_clips(const float* wav, const long long* offsets, const int* lens, int B, long long L_pad,
+                         int channels, float gain, float* out, void* scratch, void* stream);
 /* algorithmic FLOPs of one pass (2*MACs of every conv, all taps counted) */
 double kvae_plan_flops(const kvae_plan* plan, int B, long long T);
 
@@ -187,6 +215,15 @@ int kvae_pcm16(const void* wav, int dtype, int16_t* out, size_t n, void* scratch
  * torch does (mul, then add).  std_noise != NULL selects 'gaussian': per-item std_b = std_noise[b]*value. */
 int kvae_sigma_sample(const void* mean, const void* noise, void* out, size_t n, int dtype, float std,
                       const void* std_noise, float value, size_t per_batch, void* stream);
+/* One autoregressive step of the LM <-> VAE glue (model_sigmaVAE.py:123-145, Llasa.infer), ONE launch:
+ *   mean = distribution_linear(hidden) = W2 gelu(W1 hidden + b1) + b2      (nn.Sequential(Linear, GELU, Linear), :42-50)
+ *   latent = mean + std*noise (sample 'fix', two roundings)   kl_end = KL(N(mean,std) || N(1,e)).sum(-1)/D (:134-139)
+ *   embed = audio_linear(latent) = Wa latent + ba                                                           (:143)
+ * hidden [B,H] (hidden_dtype), noise / mean / latent [B,D] and embed [B,H] in out_dtype, weights fp32 in torch's
+ * nn.Linear layout (W1 [D,H], W2 [D,D], Wa [H,D]), kl_end [B] fp32 or NULL.  H and D multiples of 8. */
+int kvae_lm_glue_step(const void* hidden, int hidden_dtype, const float* w1, const float* b1, const float* w2,
+                      const float* b2, const float* wa, const float* ba, const void* noise, void* mean, void* latent,
+                      void* embed, float* kl_end, int out_dtype, int B, int H, int D, float std, void* stream);
 /* vae_sample of bottleneck.py:51-62 (as edited in the reference): out = noise*scale + mean; *kl (device
  * fp32 scalar) = (mean^2 + var - log var - 1).sum(1).mean().  scratch: >= 8*1024 bytes. */
 int kvae_vae_sample(const void* mean, const void* scale, const void* noise, void* out, float* kl, int B, int D,

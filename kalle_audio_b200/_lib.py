@@ -31,6 +31,7 @@ class KvaeArch(C.Structure):
         ("c_mults", C.c_int * KVAE_MAX_STAGES),
         ("strides", C.c_int * KVAE_MAX_STAGES),
         ("final_tanh", C.c_int),
+        ("use_nearest_upsample", C.c_int),
     ]
 
 
@@ -59,6 +60,15 @@ SIGNATURES = {
                               C.c_void_p, C.c_size_t, C.c_void_p]),
     "kvae_encode": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
                               C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kvae_decode_ragged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
+                                     C.POINTER(C.c_int), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kvae_encode_ragged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
+                                     C.POINTER(C.c_int), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kvae_plan_out_length": (C.c_longlong, [C.c_void_p, C.c_longlong]),
+    "kvae_prep_mono_clips": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_float,
+                                       C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kvae_lm_glue_step": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_void_p] * 5 +
+                          [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "kvae_plan_flops": (C.c_double, [C.c_void_p, C.c_int, C.c_longlong]),
     "kvae_plan_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "kvae_plan_step_profile": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_double),

@@ -10,7 +10,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from . import _lib
-from .layers import SnakeBeta, _WNConvBase
+from .layers import SnakeBeta, _WNConvBase, nearest_upsample_conv_taps
 
 
 class PlanRunner:
@@ -37,6 +37,9 @@ class PlanRunner:
             _lib.check(L.kvae_plan_conv_info(handle, i, C.byref(info)))
             want = (int(m.transposed), m.in_channels, m.out_channels, m.kernel_size[0], m.stride[0], m.dilation[0],
                     m.padding[0], int(m.bias is not None))
+            us = getattr(m, "_upsample_stride", 0)
+            if us:     # Upsample(nearest) + 'same' conv runs as ConvTranspose1d(k = 3s - 1, stride s, padding s)
+                want = (1, m.in_channels, m.out_channels, 3 * us - 1, us, 1, us, 0)
             if tuple(info) != want:
                 raise _lib.KvaeError(f"conv {i}: module {want} does not match plan {tuple(info)}")
         for i, m in enumerate(self.snakes):
@@ -69,6 +72,8 @@ class PlanRunner:
             if next(m.parameters(recurse=False)).device != self.device:
                 raise _lib.KvaeError("module parameters moved to another device; plan is stale")
             w = m.folded_weight()
+            if getattr(m, "_upsample_stride", 0):
+                w = nearest_upsample_conv_taps(w, m._upsample_stride)
             b = None if m.bias is None else m.bias.detach().float().contiguous()
             _lib.check(L.kvae_plan_set_conv(self.handle, i, w.data_ptr(), _lib.ptr(b), st))
         for i, m in enumerate(self.snakes):
@@ -89,10 +94,17 @@ class PlanRunner:
             self._workspace = torch.empty(need, dtype=torch.uint8, device=self.device)
         return self._workspace
 
+    def valid_out_length(self, T: int) -> int:
+        """Output length for an input of length T by the reference's conv arithmetic (floors; odd strides)."""
+        return int(_lib.lib().kvae_plan_out_length(self.handle, int(T)))
+
     def out_length(self, T: int, ratio: int) -> int:
         return T * ratio if self.direction == _lib.KVAE_DECODER else T // ratio
 
-    def run(self, x: torch.Tensor, out_channels: int, ratio: int, out_dtype: torch.dtype) -> torch.Tensor:
+    def run(self, x: torch.Tensor, out_channels: int, ratio: int, out_dtype: torch.dtype,
+            valid_len=None) -> torch.Tensor:
+        """``valid_len`` (B ints, host): ragged batch -- clip b holds valid_len[b] valid input positions and is
+        zero-padded to the common length; its output beyond the matching length is zeroed (kvae_*_ragged)."""
         _lib.require_cuda(x, "fused plan")
         if x.device != self.device:
             raise _lib.KvaeError(f"input on {x.device}, plan on {self.device}")
@@ -112,6 +124,19 @@ class PlanRunner:
         L = _lib.lib()
         fn = L.kvae_decode if self.direction == _lib.KVAE_DECODER else L.kvae_encode
         out_shape = (B, out_channels, self.out_length(T, ratio))
+
+        if valid_len is not None:
+            lens = [int(v) for v in valid_len]
+            if len(lens) != B or any(v < 0 or v > T for v in lens):
+                raise ValueError("valid_len needs one length in 0..T per clip")
+            arr = (C.c_int * B)(*lens)
+            fn = L.kvae_decode_ragged if self.direction == _lib.KVAE_DECODER else L.kvae_encode_ragged
+            out = torch.empty(out_shape, dtype=kdtype, device=self.device)
+            _lib.check(fn(self.handle, xin.data_ptr(), _lib.dtype_code(xin.dtype), out.data_ptr(), _lib.dtype_code(kdtype),
+                          B, T, arr, ws.data_ptr(), ws.numel(), _lib.stream_ptr(self.device)))
+            out_valid = torch.tensor([self.valid_out_length(v) for v in lens], device=self.device)
+            out = out * (torch.arange(out_shape[2], device=self.device)[None, :] < out_valid[:, None])[:, None, :].to(out.dtype)
+            return out if out.dtype == out_dtype else out.to(out_dtype)
 
         def launch(src, dst):
             _lib.check(fn(self.handle, src.data_ptr(), _lib.dtype_code(src.dtype), dst.data_ptr(),

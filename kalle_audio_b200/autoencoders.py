@@ -24,7 +24,7 @@ from torch import nn
 from . import _lib
 from ._plan import PlanCache, PlanFunction
 from .bottleneck import Bottleneck, create_bottleneck_from_config
-from .layers import SnakeBeta, WNConv1d, WNConvTranspose1d
+from .layers import NearestUpsampleConv, SnakeBeta, WNConv1d, WNConvTranspose1d
 
 
 def get_activation(activation: Literal["elu", "snake", "none"], antialias=False, channels=None) -> nn.Module:
@@ -88,19 +88,21 @@ class DecoderBlock(_Sequential):
                  use_nearest_upsample=False):
         super().__init__()
         if use_nearest_upsample:
-            raise NotImplementedError("use_nearest_upsample=True (Upsample + 'same' conv, autoencoders.py:87-96) is "
-                                      "not built; the reference's configs use the transposed convolution")
+            upsample_layer = NearestUpsampleConv(in_channels, out_channels, stride)
+        else:
+            upsample_layer = WNConvTranspose1d(in_channels=in_channels, out_channels=out_channels,
+                                               kernel_size=2 * stride + stride % 2, stride=stride,
+                                               padding=math.ceil(stride / 2))
         self.layers = nn.Sequential(
             _act(use_snake, antialias_activation, in_channels),
-            WNConvTranspose1d(in_channels=in_channels, out_channels=out_channels,
-                              kernel_size=2 * stride + stride % 2, stride=stride, padding=math.ceil(stride / 2)),
+            upsample_layer,
             ResidualUnit(in_channels=out_channels, out_channels=out_channels, dilation=1, use_snake=use_snake),
             ResidualUnit(in_channels=out_channels, out_channels=out_channels, dilation=3, use_snake=use_snake),
             ResidualUnit(in_channels=out_channels, out_channels=out_channels, dilation=9, use_snake=use_snake),
         )
 
 
-def _make_arch(io_channels, channels, latent_dim, c_mults, strides, final_tanh) -> _lib.KvaeArch:
+def _make_arch(io_channels, channels, latent_dim, c_mults, strides, final_tanh, use_nearest_upsample=False) -> _lib.KvaeArch:
     if len(c_mults) != len(strides):
         raise ValueError("c_mults and strides must have the same length")
     if len(strides) > _lib.KVAE_MAX_STAGES:
@@ -110,6 +112,7 @@ def _make_arch(io_channels, channels, latent_dim, c_mults, strides, final_tanh) 
     for i, (c, s) in enumerate(zip(c_mults, strides)):
         a.c_mults[i], a.strides[i] = int(c), int(s)
     a.final_tanh = int(bool(final_tanh))
+    a.use_nearest_upsample = int(bool(use_nearest_upsample))
     return a
 
 
@@ -157,14 +160,24 @@ class _OobleckBase(nn.Module):
         r.use_graphs = getattr(self, "_use_graphs", False)
         return r
 
-    def forward(self, x):
+    def forward(self, x, valid_len=None):
+        """``valid_len`` (optional, B ints): ragged batch.  Clip b holds valid_len[b] valid input positions (latent
+        frames / audio samples) and is zero-padded to the common length (for an encoder: a multiple of the ratio);
+        its output up to the matching length equals the reference's stand-alone call on that clip -- including an
+        audio length that is not a multiple of the ratio, where the reference's strided convs floor -- and is zero
+        beyond.  Inference only."""
         _lib.require_cuda(x, type(self).__name__ + ".forward")
         r = self.runner(x.device)
+        if valid_len is not None:
+            return r.run(x, self._out_channels_for_plan, self._ratio, self._out_dtype(x), valid_len=valid_len)
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
             # training: saved activations + hand-written backward (kvae_forward_train / kvae_backward)
             if getattr(self._arch, "final_tanh", 0):
                 raise NotImplementedError("final_tanh=True is inference-only in kalle_audio_b200 (no reference config "
                                           "trains with it)")
+            if getattr(self._arch, "use_nearest_upsample", 0):
+                raise NotImplementedError("use_nearest_upsample=True is inference-only in kalle_audio_b200 (no reference "
+                                          "config uses it)")
             return PlanFunction.apply(r, x, self._out_channels_for_plan, self._ratio, self._out_dtype(x),
                                       *r.param_list())
         return r.run(x, self._out_channels_for_plan, self._ratio, self._out_dtype(x))
@@ -218,8 +231,8 @@ class OobleckDecoder(_OobleckBase):
                             bias=False),
                    nn.Tanh() if final_tanh else nn.Identity()]
         self.layers = nn.Sequential(*layers)
-        self._setup(_make_arch(out_channels, channels, latent_dim, user_c_mults, strides, final_tanh), out_channels,
-                    int(math.prod(strides)))
+        self._setup(_make_arch(out_channels, channels, latent_dim, user_c_mults, strides, final_tanh,
+                               use_nearest_upsample), out_channels, int(math.prod(strides)))
 
 
 # ---------------------------------------------------------------------------------------------------

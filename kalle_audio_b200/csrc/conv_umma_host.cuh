@@ -28,7 +28,10 @@ struct ConvGeom {
   int Cin, Cout, K, stride, dilation, pad;
   int out_pad = 0;   // ConvTranspose1d output_padding (only the data-gradient geometries use it)
   int out_len(int T_in) const {
-    if (kind == kConv) return (T_in + 2 * pad - dilation * (K - 1) - 1) / stride + 1;
+    if (kind == kConv) {   // floor division, as torch computes it (the numerator is negative for inputs shorter than the kernel)
+      const int num = T_in + 2 * pad - dilation * (K - 1) - 1;
+      return (num >= 0 ? num / stride : -((-num + stride - 1) / stride)) + 1;
+    }
     return (T_in - 1) * stride - 2 * pad + dilation * (K - 1) + 1 + out_pad;
   }
 };

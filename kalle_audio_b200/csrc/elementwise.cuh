@@ -288,6 +288,63 @@ __global__ void pcm16_kernel(const void* x, size_t n, int f32, const unsigned in
   }
 }
 
+// ---------------------------------------------------------------- ragged batches
+// A batch whose clips have different valid lengths is run at the padded length; after every layer the rows of each
+// clip beyond ITS valid length are set to zero in the layer's output tensors, so the next convolution sees exactly
+// the zero padding the reference's per-clip call would have applied at that clip's end (SnakeBeta(0) = 0, so a zero
+// stream row is a zero operand row).  v[b] = valid rows of clip b in this tensor.
+constexpr int kRaggedMaxClips = 64;
+struct RaggedLens { int v[kRaggedMaxClips]; };
+// grid: (blocks over the longest tail, clips of this group); base -> first clip of the group, channels-last rows
+__global__ void zero_tail_rows_kernel(uint8_t* base, long long clip_bytes, int row_bytes, long long rows, RaggedLens lens) {
+  const int b = blockIdx.y;
+  long long valid = lens.v[b];
+  if (valid >= rows) return;
+  if (valid < 0) valid = 0;
+  uint8_t* p0 = base + static_cast<size_t>(b) * clip_bytes + static_cast<size_t>(valid) * row_bytes;
+  const size_t nbytes = static_cast<size_t>(rows - valid) * row_bytes;
+  const size_t i0 = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x, step = static_cast<size_t>(gridDim.x) * blockDim.x;
+  if (((reinterpret_cast<uintptr_t>(p0) | nbytes) & 15) == 0) {
+    uint4* q = reinterpret_cast<uint4*>(p0);
+    for (size_t i = i0; i < nbytes / 16; i += step) q[i] = make_uint4(0, 0, 0, 0);
+  } else {   // row_bytes is always even (2- or 4-byte elements)
+    uint16_t* q = reinterpret_cast<uint16_t*>(p0);
+    for (size_t i = i0; i < nbytes / 2; i += step) q[i] = 0;
+  }
+}
+
+// twj_dataset.py:231-235 for a batch of mono clips: librosa.util.normalize(wav) * 0.95 (peak normalisation, clips
+// whose peak is below float32 tiny stay as they are), duplicated to two channels, zero-padded to the batch length.
+//   pass 1 (grid: (blocks, B)): per-clip absolute peak;  pass 2: out[b, 0 | 1, t] = wav_b[t] / peak_b * 0.95
+__global__ void clip_peak_kernel(const float* wav, const long long* offsets, const int* lens, unsigned int* peak_bits) {
+  const int b = blockIdx.y;
+  const float* x = wav + offsets[b];
+  const int n = lens[b];
+  float m = 0.f;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = fmaxf(m, fabsf(x[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(peak_bits + b, __float_as_uint(m));
+}
+__global__ void clip_normalize_dup_kernel(const float* wav, const long long* offsets, const int* lens,
+                                          const unsigned int* peak_bits, float gain, float* out, long long L_pad,
+                                          int channels) {
+  const int b = blockIdx.y;
+  const float* x = wav + offsets[b];
+  const int n = lens[b];
+  const float peak = __uint_as_float(peak_bits[b]);
+  const bool scale = peak > 1.17549435e-38f;            // librosa: norms below tiny are left alone (fill=None)
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < L_pad;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float v = 0.f;
+    if (i < n) {
+      v = x[i];
+      if (scale) v = __fdiv_rn(v, peak);
+      v = __fmul_rn(v, gain);
+    }
+    for (int c = 0; c < channels; ++c) out[(static_cast<size_t>(b) * channels + c) * L_pad + i] = v;
+  }
+}
+
 // ---------------------------------------------------------------- latent sampling
 // sample(mean, 'fix') of model_sigmaVAE.py:153-178,187-213: mean + std * noise, evaluated as torch
 // does -- two separately rounded operations (mul then add), never an FMA -- so the result is

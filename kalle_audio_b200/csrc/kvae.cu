@@ -25,6 +25,7 @@
 #include "conv_edge.cuh"
 #include "conv_umma_host.cuh"
 #include "elementwise.cuh"
+#include "glue.cuh"
 #include "train.cuh"
 
 using namespace kvae;
@@ -271,7 +272,14 @@ void build_decoder(kvae_plan* p) {
   for (int i = n; i >= 1; --i) {            // DecoderBlock (:83-114), strides walked in reverse (:171-180)
     const int cin = cm[i] * a.channels, cout = cm[i - 1] * a.channels, st = a.strides[i - 1];
     const int sn = add_snake(p, cin);
-    add_conv(p, kConvT, cin, cout, 2 * st + st % 2, st, 1, ceil_div(st, 2), true);
+    if (a.use_nearest_upsample) {
+      // Upsample(nearest, x st) + Conv1d(k = 2 st, 'same', no bias) (:87-96) == ConvTranspose1d(k = 3 st - 1, stride st,
+      // padding st, output_padding 1) with summed taps (include/kvae.h); the host folds the weight
+      add_conv(p, kConvT, cin, cout, 3 * st - 1, st, 1, st, false);
+      p->convs.back().g.out_pad = 1;
+    } else {
+      add_conv(p, kConvT, cin, cout, 2 * st + st % 2, st, 1, ceil_div(st, 2), true);
+    }
     num *= st;
     Step u;
     u.conv = static_cast<int>(p->convs.size()) - 1;
@@ -753,8 +761,55 @@ PreparedRun* get_run(kvae_plan* p, bool train, int B, long long T, void* ws, std
   return it->second.get();
 }
 
+// Ragged batches: valid rows of clip b after step k, by the reference's own length arithmetic (every conv floors:
+// L_out = (L + 2p - d(K-1) - 1) / s + 1, so e.g. the stride-5 stage of the 12.5 Hz models maps 159 rows to 32)
+std::vector<std::vector<int>> valid_rows_per_step(const kvae_plan* p, const std::vector<Step>& steps, const int* valid, int B) {
+  std::vector<std::vector<int>> v(steps.size(), std::vector<int>(B));
+  for (int b = 0; b < B; ++b) {
+    int len = valid[b];
+    for (size_t k = 0; k < steps.size(); ++k) {
+      len = len > 0 ? std::max(0, p->convs[steps[k].conv].g.out_len(len)) : 0;
+      v[k][b] = len;
+    }
+  }
+  return v;
+}
+
+// zero the rows beyond each clip's valid length in the tensors step k has just written
+cudaError_t zero_step_tails(const kvae_plan* p, const std::vector<Step>& steps, const PreparedRun& R, int k, int B,
+                            long long T, void* ws, const std::vector<int>& valid_k, bool train, cudaStream_t st) {
+  const Step& s = steps[k];
+  const ConvLayer& c = p->convs[s.conv];
+  const long long rows = step_len(s, T);
+  uint8_t* base = static_cast<uint8_t*>(ws);
+  const int split = (p->precision == KVAE_PREC_F32 && !train) ? 2 : 1;
+  for (int which = 0; which < 2; ++which) {
+    const Tensor& t = R.layout.t[1 + which + 2 * k];
+    if (!t.bytes) continue;
+    const int row_bytes = which == 0 ? c.g.Cout * (R.stream_f16 ? 2 : 4) : c.g.Cout * 2 * split;
+    for (int b0 = 0; b0 < B; b0 += kRaggedMaxClips) {
+      const int nb = std::min(kRaggedMaxClips, B - b0);
+      RaggedLens lens;
+      long long max_tail = 0;
+      for (int i = 0; i < nb; ++i) {
+        lens.v[i] = static_cast<int>(std::min<long long>(rows, valid_k[b0 + i]));
+        max_tail = std::max(max_tail, rows - lens.v[i]);
+      }
+      if (max_tail <= 0) continue;
+      const long long vecs = (max_tail * row_bytes + 15) / 16;
+      const int blocks = static_cast<int>(std::min<long long>((vecs + 255) / 256, 4 * 148));
+      zero_tail_rows_kernel<<<dim3(blocks, nb), 256, 0, st>>>(base + t.offset + static_cast<size_t>(b0) * rows * row_bytes,
+                                                             rows * row_bytes, row_bytes, rows, lens);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return e;
+      ++g_launches;
+    }
+  }
+  return cudaSuccess;
+}
+
 int run_plan(kvae_plan* p, bool train, const void* in, int in_dtype, void* out, int out_dtype, int B, long long T,
-             void* ws, size_t ws_bytes, cudaStream_t st) {
+             void* ws, size_t ws_bytes, cudaStream_t st, const int* valid = nullptr) {
   if (!p) return fail("null plan");
   if (B <= 0 || T <= 0) return fail("empty batch or zero length input");
   if (T > (1ll << 30)) return fail("input too long");
@@ -764,6 +819,8 @@ int run_plan(kvae_plan* p, bool train, const void* in, int in_dtype, void* out, 
     if (!s.set) return fail("plan SnakeBeta parameters not set (kvae_plan_set_snake / kvae_plan_load_params)");
   if (train && !p->train_packs) return fail("training run needs kvae_plan_load_params(plan, params, train = 1)");
   if (train && p->direction == KVAE_DECODER && p->arch.final_tanh) return fail("final_tanh is not supported in training");
+  if (train && p->direction == KVAE_DECODER && p->arch.use_nearest_upsample)
+    return fail("use_nearest_upsample is inference-only (its folded taps have no weight-norm parameter layout)");
   DeviceGuard guard(p->device);
   if (!guard.ok) return fail("cannot select device");
   const std::vector<Step>& steps = train ? p->tsteps : p->steps;
@@ -785,6 +842,8 @@ int run_plan(kvae_plan* p, bool train, const void* in, int in_dtype, void* out, 
     KV_CUDA(cudaGetLastError());
     ++g_launches;
   }
+  std::vector<std::vector<int>> valid_rows;
+  if (valid) valid_rows = valid_rows_per_step(p, steps, valid, B);
   const bool prof = p->profile && !train;
   if (prof) {
     while (static_cast<int>(p->events.size()) < n + 1) {
@@ -851,6 +910,7 @@ int run_plan(kvae_plan* p, bool train, const void* in, int in_dtype, void* out, 
       KV_CUDA(launch_direct(d, R.direct_grid[k], R.direct_cfg[k], R.direct_smem[k], st));
     }
     if (R.kind[k] != 5) ++g_launches;
+    if (valid && k != n - 1) KV_CUDA(zero_step_tails(p, steps, R, k, B, T, ws, valid_rows[k], train, st));
     if (prof) KV_CUDA(cudaEventRecord(p->events[k + 1], st));
   }
   return 0;
@@ -1406,6 +1466,61 @@ int kvae_encode(kvae_plan* p, const void* wav, int wav_dtype, void* lat, int lat
   return run_plan(p, false, wav, wav_dtype, lat, lat_dtype, B, L, ws, ws_bytes, static_cast<cudaStream_t>(stream));
 }
 
+static int check_valid(const int* valid, int B, long long T) {
+  if (!valid) return fail("null valid_len");
+  for (int b = 0; b < B; ++b)
+    if (valid[b] < 0 || valid[b] > T) return fail("valid_len out of range (0 .. padded length)");
+  return 0;
+}
+
+int kvae_decode_ragged(kvae_plan* p, const void* z, int z_dtype, void* wav, int wav_dtype, int B, long long T,
+                       const int* valid_len, void* ws, size_t ws_bytes, void* stream) {
+  if (!p) return fail("null plan");
+  if (p->direction != KVAE_DECODER) return fail("plan is not a decoder");
+  if (!z || !wav) return fail("null tensor");
+  if (!check_dtype(z_dtype) || !check_dtype(wav_dtype)) return fail("bad dtype");
+  if (B > 0 && T > 0 && check_valid(valid_len, B, T)) return -1;
+  return run_plan(p, false, z, z_dtype, wav, wav_dtype, B, T, ws, ws_bytes, static_cast<cudaStream_t>(stream), valid_len);
+}
+
+int kvae_encode_ragged(kvae_plan* p, const void* wav, int wav_dtype, void* lat, int lat_dtype, int B, long long L,
+                       const int* valid_len, void* ws, size_t ws_bytes, void* stream) {
+  if (!p) return fail("null plan");
+  if (p->direction != KVAE_ENCODER) return fail("plan is not an encoder");
+  if (!wav || !lat) return fail("null tensor");
+  if (!check_dtype(wav_dtype) || !check_dtype(lat_dtype)) return fail("bad dtype");
+  if (B > 0 && L > 0 && check_valid(valid_len, B, L)) return -1;
+  return run_plan(p, false, wav, wav_dtype, lat, lat_dtype, B, L, ws, ws_bytes, static_cast<cudaStream_t>(stream), valid_len);
+}
+
+long long kvae_plan_out_length(const kvae_plan* p, long long T) {
+  if (!p) return fail("null plan");
+  long long len = T;
+  for (const Step& st : p->steps) {
+    if (len <= 0 || len > (1ll << 30)) return 0;
+    len = p->convs[st.conv].g.out_len(static_cast<int>(len));
+  }
+  return len > 0 ? len : 0;
+}
+
+int kvae_prep_mono_clips(const float* wav, const long long* offsets, const int* lens, int B, long long L_pad, int channels,
+                         float gain, float* out, void* scratch, void* stream) {
+  if (!wav || !offsets || !lens || !out || !scratch) return fail("null argument");
+  if (B <= 0 || L_pad <= 0 || channels <= 0) return fail("empty input");
+  DeviceGuard guard(device_of(out));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  KV_CUDA(cudaMemsetAsync(scratch, 0, static_cast<size_t>(B) * 4, st));
+  const int blocks = static_cast<int>(std::min<long long>((L_pad + 255) / 256, 2 * 148));
+  clip_peak_kernel<<<dim3(blocks, B), 256, 0, st>>>(wav, offsets, lens, static_cast<unsigned int*>(scratch));
+  KV_CUDA(cudaGetLastError());
+  clip_normalize_dup_kernel<<<dim3(blocks, B), 256, 0, st>>>(wav, offsets, lens, static_cast<const unsigned int*>(scratch),
+                                                            gain, out, L_pad, channels);
+  KV_CUDA(cudaGetLastError());
+  g_launches += 2;
+  return 0;
+}
+
 double kvae_plan_flops(const kvae_plan* p, int B, long long T) {
   if (!p) return 0.0;
   double f = 0.0;
@@ -1892,6 +2007,27 @@ int kvae_sigma_sample(const void* mean, const void* noise, void* out, size_t n, 
   sigma_sample_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(mean, noise, out, n, dtype == KVAE_F32,
                                                                              std, std_noise, value, per_batch);
   KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int kvae_lm_glue_step(const void* hidden, int hidden_dtype, const float* w1, const float* b1, const float* w2,
+                      const float* b2, const float* wa, const float* ba, const void* noise, void* mean, void* latent,
+                      void* embed, float* kl_end, int out_dtype, int B, int H, int D, float std, void* stream) {
+  if (!hidden || !w1 || !b1 || !w2 || !b2 || !wa || !ba || !noise || !mean || !latent || !embed)
+    return fail("null argument");
+  if (!check_dtype(hidden_dtype) || !check_dtype(out_dtype)) return fail("bad dtype");
+  if (B <= 0) return 0;
+  if (H <= 0 || D <= 0 || H % kGlueCluster || D % kGlueCluster) return fail("H and D must be positive multiples of 8");
+  if (glue_smem_bytes(H, D) > 200 * 1024) return fail("H / D too large for the glue kernel's shared memory");
+  DeviceGuard guard(device_of(hidden));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  GlueParams p;
+  p.hidden = hidden; p.hidden_f32 = (hidden_dtype == KVAE_F32);
+  p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.wa = wa; p.ba = ba;
+  p.noise = noise; p.mean = mean; p.latent = latent; p.embed = embed; p.kl_end = kl_end;
+  p.out_f32 = (out_dtype == KVAE_F32); p.H = H; p.D = D; p.std = std;
+  KV_CUDA(launch_lm_glue_step(p, B, static_cast<cudaStream_t>(stream)));
   ++g_launches;
   return 0;
 }

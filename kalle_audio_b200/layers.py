@@ -217,6 +217,8 @@ class _WNConvBase(nn.Module):
     def _forward_impl(self, x):
         """(y, the contiguous input actually used, the folded fp32 weight)"""
         xin = x if x.dtype in (torch.float32, torch.bfloat16) else x.float()
+        if getattr(self, "_same_extra_right", 0):     # 'same' with an even kernel: one more zero on the right
+            xin = torch.nn.functional.pad(xin, (0, self._same_extra_right))
         xin = xin.contiguous()
         w = self.folded_weight()
         bias = None if self.bias is None else self.bias.detach().float().contiguous()
@@ -251,10 +253,21 @@ class WNConv1d(_WNConvBase):
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
                  bias=True, padding_mode="zeros", device=None, dtype=None):
         super().__init__()
-        if groups != 1 or padding_mode != "zeros" or isinstance(padding, str):
-            raise NotImplementedError("kalle_audio_b200.WNConv1d: groups=1, zero padding with an integer amount only "
-                                      "(the only form the Oobleck stack uses without use_nearest_upsample)")
-        conv = nn.Conv1d(in_channels, out_channels, kernel_size, stride=stride, padding=padding, dilation=dilation,
+        if groups != 1 or padding_mode != "zeros" or (isinstance(padding, str) and (padding != "same" or _single(stride) != 1)):
+            raise NotImplementedError("kalle_audio_b200.WNConv1d: groups=1, zero padding with an integer amount or "
+                                      "'same' at stride 1 only (the forms the Oobleck stack uses)")
+        # padding='same' (the conv of DecoderBlock's use_nearest_upsample branch, autoencoders.py:90-95): torch pads
+        # d(K-1) in total, the smaller half on the left
+        self.same_padding = isinstance(padding, str)
+        if self.same_padding:
+            total = _single(dilation) * (_single(kernel_size) - 1)
+            self._same_extra_right = total - 2 * (total // 2)
+            conv_padding = padding
+            padding = total // 2
+        else:
+            self._same_extra_right = 0
+            conv_padding = padding
+        conv = nn.Conv1d(in_channels, out_channels, kernel_size, stride=stride, padding=conv_padding, dilation=dilation,
                          bias=bias, device=device, dtype=dtype)
         self.in_channels, self.out_channels = in_channels, out_channels
         self.kernel_size = (_single(kernel_size),)
@@ -285,3 +298,33 @@ class WNConvTranspose1d(_WNConvBase):
         self.output_padding = (0,)
         self.groups = 1
         self._init_from(conv)
+
+
+def nearest_upsample_conv_taps(w: torch.Tensor, stride: int) -> torch.Tensor:
+    """Folded taps of ``Upsample(scale_factor=stride, mode='nearest')`` followed by ``Conv1d(k = 2*stride, padding='same')``
+    (DecoderBlock's use_nearest_upsample branch, autoencoders.py:87-96) as ONE transposed convolution: ``w`` [Cout, Cin,
+    2s] -> ConvTranspose1d weight [Cin, Cout, 3s - 1] for stride s, padding s, output_padding 1, with
+    ``w'[k'] = sum_{k = 2s-1-k'}^{3s-2-k'} w[k]`` (k clipped to 0 .. 2s-1): every group of s upsampled positions that
+    reads the same input sample contributes the sum of the taps that land on it."""
+    Cout, Cin, K = w.shape
+    s = int(stride)
+    if K != 2 * s:
+        raise ValueError("the nearest-upsample conv has kernel_size == 2 * stride")
+    wp = w.new_zeros(Cin, Cout, 3 * s - 1)
+    for kp in range(3 * s - 1):
+        lo, hi = max(0, 2 * s - 1 - kp), min(2 * s - 1, 3 * s - 2 - kp)
+        wp[:, :, kp] = w[:, :, lo:hi + 1].sum(-1).t()
+    return wp.contiguous()
+
+
+class NearestUpsampleConv(nn.Sequential):
+    """``nn.Sequential(nn.Upsample(scale_factor=stride, mode="nearest"), WNConv1d(k=2*stride, padding='same',
+    bias=False))`` exactly as the reference builds it (same state_dict keys ``0`` / ``1.weight_g`` / ``1.weight_v``).
+    Stand-alone it chains the two modules; inside an OobleckDecoder plan the pair runs as one tcgen05 transposed conv."""
+
+    def __init__(self, in_channels, out_channels, stride):
+        super().__init__(nn.Upsample(scale_factor=stride, mode="nearest"),
+                         WNConv1d(in_channels=in_channels, out_channels=out_channels, kernel_size=2 * stride, stride=1,
+                                  bias=False, padding="same"))
+        self.upsample_stride = int(stride)
+        self[1]._upsample_stride = int(stride)      # the plan folds this conv's weight into transposed-conv taps

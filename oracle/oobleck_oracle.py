@@ -89,9 +89,13 @@ def encoder_block(sd: Dict[str, Tensor], key: str, x: Tensor, stride: int) -> Te
     return _wn_conv1d(sd, f"{key}.layers.4", x, stride=stride, padding=math.ceil(stride / 2))
 
 
-def decoder_block(sd: Dict[str, Tensor], key: str, x: Tensor, stride: int) -> Tensor:
+def decoder_block(sd: Dict[str, Tensor], key: str, x: Tensor, stride: int, use_nearest_upsample: bool = False) -> Tensor:
     x = _snake(sd, f"{key}.layers.0", x)
-    x = _wn_conv_transpose1d(sd, f"{key}.layers.1", x, stride=stride, padding=math.ceil(stride / 2))
+    if use_nearest_upsample:     # autoencoders.py:87-96: Upsample(nearest) -> WNConv1d(k = 2 stride, 'same', no bias)
+        x = F.interpolate(x, scale_factor=stride, mode="nearest")
+        x = _wn_conv1d(sd, f"{key}.layers.1.1", x, padding="same")
+    else:
+        x = _wn_conv_transpose1d(sd, f"{key}.layers.1", x, stride=stride, padding=math.ceil(stride / 2))
     for j, d in enumerate((1, 3, 9)):
         x = residual_unit(sd, f"{key}.layers.{2 + j}", x, d)
     return x
@@ -109,14 +113,14 @@ def oobleck_encoder(sd: Dict[str, Tensor], x: Tensor, strides: Sequence[int], pr
 
 
 def oobleck_decoder(sd: Dict[str, Tensor], z: Tensor, strides: Sequence[int], prefix: str = "",
-                    final_tanh: bool = False) -> Tensor:
+                    final_tanh: bool = False, use_nearest_upsample: bool = False) -> Tensor:
     """z [B, latent_dim, T] -> [B, C_io, T * prod(strides)].  ``strides`` in *encoder* order
     (the decoder walks them reversed, autoencoders.py:171-180)."""
     p = prefix
     x = _wn_conv1d(sd, f"{p}layers.0", z, padding=3)
     n = len(strides)
     for i in range(n):
-        x = decoder_block(sd, f"{p}layers.{1 + i}", x, strides[n - 1 - i])
+        x = decoder_block(sd, f"{p}layers.{1 + i}", x, strides[n - 1 - i], use_nearest_upsample)
     x = _snake(sd, f"{p}layers.{1 + n}", x)
     x = _wn_conv1d(sd, f"{p}layers.{2 + n}", x, padding=3)   # bias=False in the reference: no bias key
     return torch.tanh(x) if final_tanh else x
@@ -270,3 +274,55 @@ def conv_flops_encoder(latent_dim: int, channels: int, c_mults: Sequence[int], s
         f += 2.0 * B * t * cin * cout * 2 * s
     f += 2.0 * B * t * cm[-1] * channels * latent_dim * 3
     return f
+
+
+# ------------------------------------------------------------------------------------------------ LM <-> VAE glue
+def lm_glue_step(sd: Dict[str, Tensor], last_hidden: Tensor, noise: Tensor, std: float = 0.5):
+    """One generated frame of ``Llasa.infer`` (model_sigmaVAE.py:123-145): distribution_linear (Linear, GELU, Linear;
+    :42-50) -> sample 'fix' (:153-157) -> KL against N(1, e), the stop criterion (:134-139) -> audio_linear (:143).
+    ``sd`` holds the reference's keys ``distribution_linear.{0,2}.{weight,bias}`` / ``audio_linear.{weight,bias}``."""
+    h = F.linear(last_hidden, sd["distribution_linear.0.weight"], sd["distribution_linear.0.bias"])
+    mean = F.linear(F.gelu(h), sd["distribution_linear.2.weight"], sd["distribution_linear.2.bias"])
+    latent = mean + torch.tensor(std) * noise
+    end = torch.distributions.Normal(torch.ones_like(mean), torch.exp(torch.ones_like(mean)))
+    cur = torch.distributions.Normal(mean, torch.tensor(std))
+    kl = torch.distributions.kl_divergence(cur, end).sum(2) / mean.shape[2]
+    embed = F.linear(latent, sd["audio_linear.weight"], sd["audio_linear.bias"])
+    return mean, latent, embed, kl
+
+
+def llasa_infer(sd: Dict[str, Tensor], backbone, text_embed: Tensor, audio_latents: Optional[Tensor], noises,
+                end_disp_kl_thres: float = 0.5, max_length: int = 200) -> Tensor:
+    """``Llasa.infer`` (model_sigmaVAE.py:105-148) around a caller-supplied backbone ``inputs_embeds -> hidden``;
+    ``noises[i]`` replaces the i-th ``torch.randn_like`` draw.  Returns [1, D, n] like the reference."""
+    audio_embed = None if audio_latents is None else F.linear(audio_latents, sd["audio_linear.weight"], sd["audio_linear.bias"])
+    input_embed = text_embed if audio_embed is None else torch.cat((text_embed, audio_embed), dim=1)
+    outs = []
+    for i in range(max_length):
+        last_hidden = backbone(input_embed)[:, -1:, :]
+        _, latent, embed, kl = lm_glue_step(sd, last_hidden, noises[i])
+        outs.append(latent)
+        if kl < end_disp_kl_thres and i > 3:
+            break
+        input_embed = torch.cat((input_embed, embed), dim=1)
+    return torch.stack(outs[:-1], dim=1).squeeze(1).squeeze(2).transpose(1, 2)
+
+
+# ------------------------------------------------------------------------------------------------ dataset side
+def peak_normalize(wav: Tensor, gain: float = 0.95) -> Tensor:
+    """``librosa.util.normalize(wav) * 0.95`` (twj_dataset.py:232; librosa is an un-vendored dependency without a pin
+    in the reference -- its default is the infinity norm, ``x / max|x|``, inputs whose norm is below float tiny are
+    left as they are)."""
+    peak = wav.abs().max()
+    return (wav / peak if float(peak) > 1.1754943508222875e-38 else wav) * gain
+
+
+def dataset_latents(enc_sd: Dict[str, Tensor], strides: Sequence[int], wav: Tensor, noise: Tensor, gain: float = 0.95,
+                    scale: float = 1.0):
+    """twj_dataset.py:231-256 for one mono clip: peak-normalise * 0.95 -> stereo duplicate -> pretransform.encode
+    (= the Oobleck encoder, / scale) -> chunk into mean | scale -> vae_sample -> [T, D].  Returns (latents, mean_scale)."""
+    dual = peak_normalize(wav.float(), gain).reshape(1, -1).repeat(2, 1).unsqueeze(0)
+    mean_scale = oobleck_encoder(enc_sd, dual, strides) / scale
+    mean, sc = mean_scale.chunk(2, dim=1)
+    latents, _ = vae_sample(mean, sc, noise)
+    return latents.squeeze(0).transpose(0, 1), mean_scale

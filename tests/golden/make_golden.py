@@ -20,6 +20,13 @@ Fixtures (all float32, little-endian .npz):
                     the reference modules + the reference's vae_sample (generator branch of
                     training/autoencoders.py:221-352 with the Gaussian-NLL + KL objective of BASELINE config 5)
   train_mid.npz     same on the C=64 model: loss terms, per-parameter gradient norms and a strided sample
+  glue.npz          the reference's own ``Llasa.infer`` loop (model_sigmaVAE.py:105-148) run with a small deterministic
+                    stand-in for the Llama backbone: generated latents with and without the KL stop, the parameters of
+                    audio_linear / distribution_linear, and the stand-in's matrix (so the test can re-create it)
+  dataset.npz       twj_dataset.py:231-256 on three clips of different, non-multiple-of-the-ratio lengths: the
+                    reference's pretransform.encode + vae_sample per clip (tiny model, self-contained)
+  nearest.npz       decoders built with use_nearest_upsample=True (autoencoders.py:87-96): a tiny one (self-contained) and
+                    a C=64 one (tensor-core path; checksums), outputs of the reference's OobleckDecoder
   o12_d256.npz      12.5 Hz shape, latent 256 ("dim512"), [1,256,16] <-> [1,1,20480], full outputs
   o12_d1024.npz     12.5 Hz shape, latent 1024 ("dim2048"), [1,1024,16] <-> [1,1,20480], full outputs
   o12_full.npz      BASELINE configs 3 and 4 at their own length: latent 512, [1,512,375] -> [1,1,480000] (config 3's
@@ -201,8 +208,129 @@ def o12_fixtures(ae_mod):
     torch.set_grad_enabled(True)
 
 
+class _FakeBackbone(nn.Module):
+    """Deterministic stand-in for ``AutoModelForCausalLM``: hidden_t = tanh(mean_{s<=t}(embed_s) @ M).  Only what
+    ``Llasa.__init__`` / ``Llasa.infer`` touch."""
+
+    class _Inner(nn.Module):
+        def __init__(self, hidden, vocab, M):
+            super().__init__()
+            self.embed_tokens = nn.Embedding(vocab, hidden)
+            self.register_buffer("M", M)
+
+        def forward(self, inputs_embeds=None, attention_mask=None):
+            c = inputs_embeds.cumsum(dim=1) / torch.arange(1, inputs_embeds.shape[1] + 1).view(1, -1, 1)
+            return (torch.tanh(c @ self.M),)
+
+    def __init__(self, hidden, vocab, M):
+        super().__init__()
+        self.model = self._Inner(hidden, vocab, M)
+        self.config = types.SimpleNamespace(vocab_size=vocab, hidden_size=hidden)
+
+    def resize_token_embeddings(self, n):
+        return None
+
+
+def glue_fixtures():
+    """Runs the reference's Llasa.infer (the per-frame distribution_linear -> sample -> KL stop -> audio_linear loop)
+    unmodified; only AutoModelForCausalLM.from_pretrained is replaced by the stand-in backbone above."""
+    import transformers
+    sys.path.insert(0, REF)
+    H, D, V = 256, 64, 50
+    torch.manual_seed(41)
+    M = torch.randn(H, H) / H ** 0.5
+    fake = _FakeBackbone(H, V, M)
+    orig = transformers.AutoModelForCausalLM.from_pretrained
+    transformers.AutoModelForCausalLM.from_pretrained = staticmethod(lambda *a, **k: fake)
+    try:
+        import importlib
+        msv = importlib.import_module("model_sigmaVAE")
+        torch.manual_seed(42)
+        llasa = msv.Llasa({"llm_model_name_or_path": "stand-in", "latent_dim": D, "audio_proj_dim": H},
+                          tokenizer=list(range(V)), use_flash_attention=False).eval()
+    finally:
+        transformers.AutoModelForCausalLM.from_pretrained = orig
+    ids = torch.arange(7) % V
+    prompt = torch.randn(1, 3, D, generator=torch.Generator().manual_seed(43))
+    out = {"M": M, "ids": ids, "prompt": prompt, "embed_tokens": fake.model.embed_tokens.weight.detach()}
+    for k, v in llasa.state_dict().items():
+        if k.startswith("audio_linear") or k.startswith("distribution_linear"):
+            out["sd." + k] = v
+    with torch.no_grad():
+        torch.manual_seed(44)
+        out["latents_no_stop"] = llasa.infer(ids, prompt, end_disp_kl_thres=0.0, max_length=7)      # [1, D, 6]
+        torch.manual_seed(44)
+        out["latents_kl_stop"] = llasa.infer(ids, prompt, end_disp_kl_thres=1e9, max_length=20)     # stops at i = 4
+        torch.manual_seed(44)
+        out["noise"] = torch.stack([torch.randn(1, 1, D) for _ in range(7)])
+    np.savez_compressed(os.path.join(HERE, "glue.npz"), **{k: v.numpy() for k, v in out.items()})
+
+
+def dataset_fixtures(ae_mod, bn_mod):
+    """twj_dataset.py:231-256 per clip on the reference's modules.  librosa is not installed here; its
+    ``util.normalize`` (norm=inf, the default) is the published ``x / max|x|`` (left alone below float tiny)."""
+    torch.set_grad_enabled(False)
+    from stable_audio_tools.models.factory import create_pretransform_from_config
+    torch.manual_seed(0)
+    pt = create_pretransform_from_config({"type": "autoencoder", "config": CONFIGS["tiny"]["model"], "scale": 1.0,
+                                          "iterate_batch": True}, 16000)
+    randomize_snake(pt.model, 7)
+    out = {}
+    for k, v in pt.model.state_dict().items():
+        out["sd." + k] = v
+    for i, L in enumerate((40 * 23 + 17, 40 * 9, 40 * 31 + 39)):
+        wav = (0.3 * torch.randn(L, generator=torch.Generator().manual_seed(60 + i))).numpy()
+        peak = np.abs(wav).max()
+        norm_wav = (wav / peak if peak > np.finfo(np.float32).tiny else wav) * 0.95
+        norm_wav = torch.from_numpy(norm_wav.astype(np.float32)).reshape(1, -1)
+        dual_norm_wav = norm_wav.repeat(2, 1).unsqueeze(0)
+        mean_scale_latent = pt.encode(dual_norm_wav).detach()
+        mean, scale = mean_scale_latent.chunk(2, dim=1)
+        torch.manual_seed(70 + i)
+        noise = torch.randn_like(mean)
+        torch.manual_seed(70 + i)
+        with redirect_stdout(io.StringIO()):
+            latents, kl = bn_mod.vae_sample(mean, scale)
+        latents = latents.squeeze(0).transpose(0, 1)
+        out.update({f"wav{i}": torch.from_numpy(wav), f"dual{i}": dual_norm_wav, f"mean_scale{i}": mean_scale_latent,
+                    f"noise{i}": noise, f"latents{i}": latents})
+    np.savez_compressed(os.path.join(HERE, "dataset.npz"), **{k: v.numpy() for k, v in out.items()})
+    torch.set_grad_enabled(True)
+
+
+def nearest_fixtures(ae_mod):
+    torch.set_grad_enabled(False)
+    out = {}
+    torch.manual_seed(0)
+    d = ae_mod.OobleckDecoder(out_channels=2, channels=8, latent_dim=4, c_mults=[1, 2, 4], strides=[2, 4, 5], use_snake=True,
+                              use_nearest_upsample=True, final_tanh=False).eval()
+    randomize_snake(d, 7)
+    z = torch.randn(2, 4, 13, generator=torch.Generator().manual_seed(1))
+    out.update(tiny_z=z, tiny_out=d(z))
+    for k, v in d.state_dict().items():
+        out["tiny_sd." + k] = v
+    torch.manual_seed(0)
+    d = ae_mod.OobleckDecoder(out_channels=2, channels=64, latent_dim=64, c_mults=[1, 2, 4], strides=[2, 4, 5], use_snake=True,
+                              use_nearest_upsample=True, final_tanh=True).eval()
+    randomize_snake(d, 7)
+    z = torch.randn(2, 64, 24, generator=torch.Generator().manual_seed(1))
+    cs = checksums(d.state_dict())
+    out.update(mid_z=z, mid_out=d(z))
+    out = {k: v.numpy() for k, v in out.items()}
+    out.update(cs_keys=np.array(list(cs.keys())), cs_vals=np.array(list(cs.values()), dtype=np.float64))
+    np.savez_compressed(os.path.join(HERE, "nearest.npz"), **out)
+    torch.set_grad_enabled(True)
+
+
 def main():
     ae_mod, bn_mod = import_reference()
+    if len(sys.argv) > 1 and sys.argv[1] == "nearest":
+        nearest_fixtures(ae_mod)
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "glue":       # only the LM-glue and dataset-side fixtures
+        glue_fixtures()
+        dataset_fixtures(ae_mod, bn_mod)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "train":      # only the training fixtures
         train_fixtures(ae_mod, bn_mod)
         return
@@ -210,6 +338,9 @@ def main():
         o12_fixtures(ae_mod)
         return
     o12_fixtures(ae_mod)
+    nearest_fixtures(ae_mod)
+    glue_fixtures()
+    dataset_fixtures(ae_mod, bn_mod)
     train_fixtures(ae_mod, bn_mod)
     torch.set_grad_enabled(False)
 

@@ -1,0 +1,197 @@
+"""GPU parity of the callers either side of the autoencoder: ragged batches, the dataset-side
+latent extraction (twj_dataset.py:231-256) and the LM <-> VAE glue of Llasa.infer (model_sigmaVAE.py:105-148),
+against the oracle and the fixtures recorded from the reference's own code."""
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+import kalle_audio_b200 as k
+from oracle import oobleck_oracle as O
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda:0")
+
+
+def _sd(g, prefix="sd."):
+    return {kk[len(prefix):]: H.t(g[kk]) for kk in g.files if kk.startswith(prefix)}
+
+
+def _fake_backbone(M):
+    def run(inputs_embeds):
+        c = inputs_embeds.cumsum(dim=1) / torch.arange(1, inputs_embeds.shape[1] + 1, device=inputs_embeds.device).view(1, -1, 1)
+        return torch.tanh(c @ M)
+    return run
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_ragged_decode_equals_per_clip_decode(dev, precision):
+    """kvae_decode_ragged: clips of 7 / 50 / 33 / 1 latent frames padded to 50 == each clip decoded alone."""
+    m = H.build("mid", 0, snake_seed=7).to(dev).set_precision(precision)
+    lens = [7, 50, 33, 1]
+    z = torch.zeros(4, 64, 50, device=dev)
+    clips = [torch.randn(1, 64, n, generator=torch.Generator().manual_seed(30 + n)).to(dev) for n in lens]
+    for i, c in enumerate(clips):
+        z[i, :, :lens[i]] = c[0]
+    y = m.decoder(z, valid_len=lens)
+    assert y.shape == (4, 2, 50 * 40)
+    for i, c in enumerate(clips):
+        alone = m.decoder(c)
+        d = float((y[i:i + 1, :, :lens[i] * 40] - alone).abs().max())
+        assert d <= 2e-6 * max(1.0, float(alone.abs().max())), (i, d)
+        assert float(y[i, :, lens[i] * 40:].abs().max()) == 0.0 if lens[i] < 50 else True
+    sd = H.split_sd({n: p.cpu() for n, p in m.state_dict().items()}, "decoder.")
+    ref = O.oobleck_decoder(sd, clips[2].cpu(), H.strides_of("mid"))
+    tol = 1e-5 if precision == "fp32" else 1e-3 * max(1.0, float(ref.abs().max()) / 0.125)
+    assert float((y[2:3, :, :33 * 40].cpu() - ref).abs().max()) <= tol
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_ragged_encode_handles_lengths_that_are_not_multiples_of_the_ratio(dev, precision):
+    """Audio of 937 / 360 / 1279 samples through the tensor-core encoder (ratio 40, odd stride 5): per clip the output
+    equals the oracle on that clip alone, with the reference's own floor arithmetic for the length (1279 -> 32)."""
+    m = H.build("mid", 0, snake_seed=7).to(dev).set_precision(precision)
+    lens = [937, 360, 1279, 40]
+    L_pad = 1280
+    x = torch.zeros(4, 2, L_pad)
+    for i, n in enumerate(lens):
+        x[i, :, :n] = 0.1 * torch.randn(2, n, generator=torch.Generator().manual_seed(50 + i))
+    e = m.encoder(x.to(dev), valid_len=lens)
+    assert e.shape == (4, 128, 32)
+    sd = H.split_sd({n: p.cpu() for n, p in m.state_dict().items()}, "encoder.")
+    for i, n in enumerate(lens):
+        ref = O.oobleck_encoder(sd, x[i:i + 1, :, :n], H.strides_of("mid"))
+        T = ref.shape[2]
+        assert T == [23, 9, 32, 1][i]
+        tol = 2e-5 * max(1.0, float(ref.abs().max())) if precision == "fp32" else 1e-3 * max(1.0, float(ref.abs().max()) / 0.125)
+        err = float((e[i:i + 1, :, :T].cpu() - ref).abs().max())
+        assert err <= tol, (i, err, tol)
+        if T < 32:
+            assert float(e[i, :, T:].abs().max()) == 0.0
+    with pytest.raises(ValueError):
+        m.encoder(x.to(dev), valid_len=[1, 2, 3])
+
+
+def test_dataset_latent_extractor_matches_reference_sequence(dev):
+    """LatentExtractor.extract on the three golden clips in ONE ragged batch == the reference's per-clip
+    normalise -> stereo dup -> pretransform.encode -> vae_sample -> [T, D] (twj_dataset.py:231-256), fp32 mode."""
+    g = H.golden("dataset")
+    pt = k.create_pretransform_from_config({"type": "autoencoder", "config": H.CONFIGS["tiny"]["model"], "scale": 1.0,
+                                            "iterate_batch": True}, 16000)
+    pt.model.load_state_dict(_sd(g))
+    pt.to(dev)
+    ex = k.LatentExtractor(pt)
+    wavs = [H.t(g[f"wav{i}"]).to(dev) for i in range(3)]
+    x, lens = ex.prepare(wavs)
+    assert x.shape == (3, 2, 1280) and lens == [937, 360, 1279]
+    for i in range(3):
+        assert torch.equal(x[i:i + 1, :, :lens[i]].cpu(), H.t(g[f"dual{i}"]))          # normalise * 0.95 and dup: bit-exact
+        assert float(x[i, :, lens[i]:].abs().max()) == 0.0 if lens[i] < 1280 else True
+    out = ex.extract(wavs, noise=[H.t(g[f"noise{i}"]).to(dev) for i in range(3)], return_mean_scale=True)
+    for i, (lat, mean, scale) in enumerate(out):
+        ms = torch.cat([mean, scale], dim=0).unsqueeze(0)
+        assert ms.shape == g[f"mean_scale{i}"].shape
+        assert float((ms.cpu() - H.t(g[f"mean_scale{i}"])).abs().max()) <= 1e-5
+        assert lat.shape == g[f"latents{i}"].shape
+        assert float((lat.cpu() - H.t(g[f"latents{i}"])).abs().max()) <= 1e-5
+        # the sampling step itself is bit-exact given the encoder output
+        assert torch.equal(lat.transpose(0, 1).unsqueeze(0).cpu(),
+                           O.vae_sample(mean.unsqueeze(0).cpu(), scale.unsqueeze(0).cpu(), H.t(g[f"noise{i}"]))[0])
+    # bounded groups: one clip per encoder call gives the same latents
+    ex1 = k.LatentExtractor(pt, max_batch_samples=1)
+    out1 = ex1.extract(wavs, noise=[H.t(g[f"noise{i}"]).to(dev) for i in range(3)])
+    for a, b in zip(out, out1):
+        assert float((a[0] - b).abs().max()) <= 1e-6
+
+
+def test_dataset_extractor_sao_shape_bf16_vs_oracle(dev):
+    """Same on the graded architecture (SAO, ratio 2048, bf16 tensor-core mode): two clips of ~0.4 s and ~0.7 s."""
+    m = H.build("sao", 0).to(dev).set_precision("bf16")
+    ex = k.LatentExtractor(m)
+    lens = [2048 * 8 + 1000, 2048 * 15 + 5]
+    wavs = [0.3 * torch.randn(n, generator=torch.Generator().manual_seed(80 + i)) for i, n in enumerate(lens)]
+    sd = H.split_sd({n: p.cpu() for n, p in m.state_dict().items()}, "encoder.")
+    noise = [torch.randn(1, 64, n // 2048, generator=torch.Generator().manual_seed(90 + i)) for i, n in enumerate(lens)]
+    out = ex.extract([w.to(dev) for w in wavs], noise=[n.to(dev) for n in noise])
+    for i in range(2):
+        ref, ms = O.dataset_latents(sd, H.strides_of("sao"), wavs[i], noise[i])
+        assert out[i].shape == ref.shape
+        err = float((out[i].cpu() - ref).abs().max())
+        H.report(f"dataset-side latents, SAO bf16, clip of {lens[i]} samples (abs max {float(ref.abs().max()):.2f})", err)
+        assert err <= 1e-3 * max(1.0, float(ms.abs().max()) / 0.125) * max(1.0, float(noise[i].abs().max()))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_lm_glue_step_vs_oracle(dev, dtype):
+    torch.manual_seed(5)
+    glue = k.LatentGlue(64, 2048).to(dev)
+    sd = {n: p.detach().cpu() for n, p in glue.state_dict().items()}
+    hidden = torch.randn(3, 1, 2048, generator=torch.Generator().manual_seed(6))
+    noise = torch.randn(3, 1, 64, generator=torch.Generator().manual_seed(7))
+    mean_r, lat_r, emb_r, kl_r = O.lm_glue_step(sd, hidden, noise)
+    if dtype == torch.bfloat16:
+        glue = glue.to(dtype)
+    mean, lat, emb, kl = glue.step(hidden.to(dev).to(dtype), noise.to(dev).to(dtype))
+    assert mean.shape == (3, 1, 64) and emb.shape == (3, 1, 2048) and kl.shape == (3, 1) and mean.dtype == dtype
+    tol = 2e-5 if dtype == torch.float32 else 3e-2
+    assert float((mean.float().cpu() - mean_r).abs().max()) <= tol
+    assert float((emb.float().cpu() - emb_r).abs().max()) <= tol
+    assert float((kl.cpu() - kl_r).abs().max()) <= (1e-5 if dtype == torch.float32 else 2e-2)
+    # the sampling step is bit-exact given the mean the kernel produced (two roundings, as torch)
+    want = mean + torch.tensor(0.5).to(dev) * noise.to(dev).to(dtype)
+    assert torch.equal(lat, want)
+    # RNG-stream parity: without an explicit noise tensor the draw is torch.randn_like(mean)
+    torch.manual_seed(9)
+    _, lat2, _, _ = glue.step(hidden.to(dev).to(dtype))
+    torch.manual_seed(9)
+    n2 = torch.randn_like(mean)
+    assert torch.equal(lat2, mean + torch.tensor(0.5).to(dev) * n2)
+    # a latent width of a 12.5 Hz model (D = 512), batch 1
+    g2 = k.LatentGlue(512, 1024).to(dev)
+    sd2 = {n: p.detach().cpu() for n, p in g2.state_dict().items()}
+    h2 = torch.randn(1, 1, 1024, generator=torch.Generator().manual_seed(8))
+    n2 = torch.randn(1, 1, 512, generator=torch.Generator().manual_seed(9))
+    r = O.lm_glue_step(sd2, h2, n2)
+    o = g2.step(h2.to(dev), n2.to(dev))
+    for a, b in zip(o, r):
+        assert float((a.float().cpu() - b).abs().max()) <= 5e-5
+
+
+def test_lm_glue_generation_loop_matches_reference_infer(dev):
+    """The reference's Llasa.infer (recorded around a stand-in backbone) re-run with LatentGlue.step as the per-frame
+    glue: same generated latents, with and without the KL stop."""
+    g = H.golden("glue")
+    glue = k.LatentGlue(64, 256)
+    glue.load_state_dict(_sd(g))
+    glue.to(dev)
+    M = H.t(g["M"]).to(dev)
+    backbone = _fake_backbone(M)
+    text = H.t(g["embed_tokens"])[H.t(g["ids"]).long()].unsqueeze(0).to(dev)
+    prompt = H.t(g["prompt"]).to(dev)
+    noises = [n.to(dev) for n in H.t(g["noise"])]
+
+    def infer(thres, max_length):
+        input_embed = torch.cat((text, glue.audio_linear(prompt)), dim=1)
+        outs = []
+        for i in range(max_length):
+            last_hidden = backbone(input_embed)[:, -1:, :]
+            _, latent, embed, kl = glue.step(last_hidden, noises[i])
+            outs.append(latent)
+            if float(kl) < thres and i > 3:
+                break
+            input_embed = torch.cat((input_embed, embed), dim=1)
+        return torch.stack(outs[:-1], dim=1).squeeze(1).squeeze(2).transpose(1, 2)
+
+    a = infer(0.0, 7)
+    assert a.shape == g["latents_no_stop"].shape
+    err = float((a.cpu() - H.t(g["latents_no_stop"])).abs().max())
+    H.report("LM glue loop (Llasa.infer, 6 frames) vs the reference's generated latents", err)
+    assert err <= 1e-5
+    b = infer(1e9, 20)
+    assert b.shape == g["latents_kl_stop"].shape and float((b.cpu() - H.t(g["latents_kl_stop"])).abs().max()) <= 1e-5

@@ -568,3 +568,40 @@ def test_full_size_properties_sao_bench_shape(dev):
     err = maxerr(m.decode(z)[:1][:, :, idx], g["dec_out_at_idx"])
     H.report("configs[1] shape (16 x 216 frames): clip 0 at the reference's recorded points", err)
     assert err <= TOL_BF16
+
+
+def test_nearest_upsample_decoder_vs_reference(dev):
+    """use_nearest_upsample=True (autoencoders.py:87-96; part of the preserved constructor signature): same state_dict
+    keys as the reference, outputs against its recorded decode -- tiny model (CUDA-core path, fp32), C=64 model
+    (tcgen05 path in bf16 and fp32 mode, with final_tanh) -- and the stand-alone block against the oracle."""
+    g = H.golden("nearest")
+    torch.manual_seed(0)
+    d = k.OobleckDecoder(out_channels=2, channels=8, latent_dim=4, c_mults=[1, 2, 4], strides=[2, 4, 5], use_snake=True,
+                         use_nearest_upsample=True, final_tanh=False).eval()
+    sd = {kk[len("tiny_sd."):]: H.t(g[kk]) for kk in g.files if kk.startswith("tiny_sd.")}
+    assert list(d.state_dict().keys()) == list(sd.keys())
+    d.load_state_dict(sd)
+    d.to(dev)
+    y = d(H.t(g["tiny_z"]).to(dev))
+    assert y.shape == g["tiny_out"].shape and maxerr(y, g["tiny_out"]) <= TOL_F32
+    blk = d.layers[1]                                    # stand-alone DecoderBlock: Upsample + 'same' conv leaf kernels
+    xb = torch.randn(2, 32, 9, generator=torch.Generator().manual_seed(3))
+    ref = O.decoder_block({"b." + n: p.cpu() for n, p in blk.state_dict().items()}, "b", xb, 5, use_nearest_upsample=True)
+    assert maxerr(blk(xb.to(dev)), ref) <= 5e-5
+    torch.manual_seed(0)
+    d = k.OobleckDecoder(out_channels=2, channels=64, latent_dim=64, c_mults=[1, 2, 4], strides=[2, 4, 5], use_snake=True,
+                         use_nearest_upsample=True, final_tanh=True).eval()
+    H.randomize_snake(d, 7)
+    H.check_checksums(d.state_dict(), g)
+    d.to(dev)
+    z = H.t(g["mid_z"]).to(dev)
+    e32 = maxerr(d.set_precision("fp32")(z), g["mid_out"])
+    e16 = maxerr(d.set_precision("bf16")(z), g["mid_out"])
+    H.report("nearest-upsample decoder (C=64, tcgen05): fp32 mode / bf16 mode", f"{e32:.3e} / {e16:.3e}")
+    # This random-init fixture keeps its activations at ~2.4 through all three stages (output abs-max 0.83 after tanh;
+    # the SAO waveform is 0.125): a CPU emulation of nothing but bf16 rounding of the conv operands gives 1.45e-2 on it
+    # (same emulation on the ConvTranspose fixture: 2.2e-3), so the budgets scale with the fixture as in bf16_tol
+    assert e32 <= TOL_F32 * max(1.0, float(np.abs(g["mid_out"]).max()) / 0.125) and e16 <= 2e-2
+    with pytest.raises(NotImplementedError):
+        with torch.enable_grad():
+            d(z.clone().requires_grad_(True))

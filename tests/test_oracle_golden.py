@@ -170,3 +170,53 @@ def test_flop_model_matches_survey():
     assert abs(f / 1e9 - 1089.089) < 0.01
     f = O.conv_flops_decoder(512, 128, [1, 2, 4, 8, 16], [2, 4, 4, 5, 8], 1, 1, 375)
     assert abs(f / 1e9 - 1255.219) < 0.01
+
+
+def _fake_backbone(M):
+    def run(inputs_embeds):
+        c = inputs_embeds.cumsum(dim=1) / torch.arange(1, inputs_embeds.shape[1] + 1, device=inputs_embeds.device).view(1, -1, 1)
+        return torch.tanh(c @ M)
+    return run
+
+
+def test_lm_glue_loop_matches_reference_infer():
+    """Llasa.infer of the reference (run unmodified around a stand-in backbone by make_golden.py) against the
+    oracle's restatement of its per-frame glue, with and without the KL stop."""
+    g = H.golden("glue")
+    sd = {k[3:]: H.t(g[k]) for k in g.files if k.startswith("sd.")}
+    text = H.t(g["embed_tokens"])[H.t(g["ids"]).long()].unsqueeze(0)
+    noises = list(H.t(g["noise"]))
+    a = O.llasa_infer(sd, _fake_backbone(H.t(g["M"])), text, H.t(g["prompt"]), noises, end_disp_kl_thres=0.0, max_length=7)
+    assert a.shape == g["latents_no_stop"].shape and np.abs(a.numpy() - g["latents_no_stop"]).max() <= 1e-6
+    b = O.llasa_infer(sd, _fake_backbone(H.t(g["M"])), text, H.t(g["prompt"]), noises, end_disp_kl_thres=1e9, max_length=20)
+    assert b.shape == g["latents_kl_stop"].shape == (1, 64, 4) and np.abs(b.numpy() - g["latents_kl_stop"]).max() <= 1e-6
+
+
+def test_dataset_side_latents_match_reference():
+    """twj_dataset.py:231-256 per clip (lengths that are not multiples of the ratio; the stride-5 stage floors
+    (T + 1) / 5, so 1279 samples give 32 frames, not 31)."""
+    g = H.golden("dataset")
+    enc = H.split_sd({k[3:]: H.t(g[k]) for k in g.files if k.startswith("sd.")}, "encoder.")
+    for i in range(3):
+        lat, ms = O.dataset_latents(enc, H.strides_of("tiny"), H.t(g[f"wav{i}"]), H.t(g[f"noise{i}"]))
+        assert ms.shape == g[f"mean_scale{i}"].shape and np.abs(ms.numpy() - g[f"mean_scale{i}"]).max() <= 2e-6
+        assert lat.shape == g[f"latents{i}"].shape and np.abs(lat.numpy() - g[f"latents{i}"]).max() <= 2e-6
+    assert g["latents2"].shape[0] == 32
+
+
+def test_nearest_upsample_decoder_matches_reference():
+    """DecoderBlock's use_nearest_upsample branch (autoencoders.py:87-96), and the fold the CUDA plan uses for it:
+    Upsample(nearest, x s) + Conv1d(k = 2s, 'same') == ConvTranspose1d(k = 3s - 1, stride s, padding s, output_padding 1)
+    with summed taps."""
+    g = H.golden("nearest")
+    sd = {k[len("tiny_sd."):]: H.t(g[k]) for k in g.files if k.startswith("tiny_sd.")}
+    y = O.oobleck_decoder(sd, H.t(g["tiny_z"]), [2, 4, 5], use_nearest_upsample=True)
+    assert y.shape == g["tiny_out"].shape and np.abs(y.numpy() - g["tiny_out"]).max() <= 2e-6
+    from kalle_audio_b200.layers import nearest_upsample_conv_taps
+    import torch.nn.functional as F
+    for s in (2, 4, 5, 8):
+        w = torch.randn(5, 6, 2 * s, dtype=torch.float64)
+        x = torch.randn(2, 6, 11, dtype=torch.float64)
+        ref = F.conv1d(F.interpolate(x, scale_factor=s, mode="nearest"), w, padding="same")
+        got = F.conv_transpose1d(x, nearest_upsample_conv_taps(w, s), stride=s, padding=s, output_padding=1)
+        assert got.shape == ref.shape and float((got - ref).abs().max()) <= 1e-12
