@@ -547,19 +547,27 @@ def measure_stream(args, dev):
     y = dec(z[:, :, :chunk])
     y[0, 0, :8].cpu()
     first_wall = time.perf_counter() - t0
-    # exact-context streaming (kalle_audio_b200.StreamingDecoder): hop 96, window 96 + 10 + 10 frames
-    sdec = k.StreamingDecoder(dec, hop=chunk - overlap)
+    # streaming decoders, hop 96 frames (= chunk - overlap, the reference's hop): the stateful engine of libkvae
+    # (persistent per-layer halo state, 0 % recompute, one CUDA graph per hop) and the exact-context window engine
     zz = torch.randn(1, latent, 96 * 12, generator=torch.Generator().manual_seed(5)).to(dev)
-    for i in range(4):
-        sdec.push(zz[:, :, i * 96:(i + 1) * 96])
-    torch.cuda.synchronize(dev)
-    es = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    es[0].record()
-    for i in range(4, 12):
-        sdec.push(zz[:, :, i * 96:(i + 1) * 96])
-    es[1].record()
-    torch.cuda.synchronize(dev)
-    stream_hop_ms = es[0].elapsed_time(es[1]) / 8
+    hop_ms = {}
+    for name, stateful in (("stateful", True), ("windows", False)):
+        sdec = k.StreamingDecoder(dec, hop=chunk - overlap, stateful=stateful)
+        for i in range(4):
+            sdec.push(zz[:, :, i * 96:(i + 1) * 96])
+        torch.cuda.synchronize(dev)
+        es = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        es[0].record()
+        for i in range(4, 12):
+            sdec.push(zz[:, :, i * 96:(i + 1) * 96])
+        es[1].record()
+        torch.cuda.synchronize(dev)
+        hop_ms[name] = es[0].elapsed_time(es[1]) / 8
+        if stateful:
+            lookahead = sdec.lookahead
+        sdec.flush()
+    stream_hop_ms = hop_ms["windows"]
+    sdec = k.StreamingDecoder(dec, hop=chunk - overlap, stateful=False)
     chunk_ms = ev[0].elapsed_time(ev[1]) / args.steps
     full_ms = ev[1].elapsed_time(ev[2]) / args.steps
     audio_s = T * 1280 / 16000
@@ -573,6 +581,11 @@ def measure_stream(args, dev):
             "per_chunk_frac_burst": flops_chunk / (chunk_ms * 1e-3) / 1e12 / peaks["bf16_tflops"],
             "first_chunk_wall_ms_incl_d2h": first_wall * 1e3,
             "real_time_factor_per_chunk": (chunk - overlap) * 1280 / 16000 / (chunk_ms * 1e-3),
+            "stateful_stream": {"hop_frames": chunk - overlap, "ms_per_hop": hop_ms["stateful"], "recompute_factor": 1.0,
+                                "lookahead_samples": lookahead,
+                                "tflops": dec.runner(dev).flops(1, chunk - overlap) / (hop_ms["stateful"] * 1e-3) / 1e12,
+                                "real_time_factor": (chunk - overlap) * 1280 / 16000 / (hop_ms["stateful"] * 1e-3),
+                                "engine": "kvae_decode_stream_push: persistent per-layer halo state, one CUDA graph per hop"},
             "exact_context_stream": {"hop_frames": chunk - overlap, "window_frames": chunk - overlap + sdec.left + sdec.right,
                                      "ms_per_hop": stream_hop_ms, "recompute_factor": sdec.recompute_factor,
                                      "real_time_factor": (chunk - overlap) * 1280 / 16000 / (stream_hop_ms * 1e-3)},

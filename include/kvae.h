@@ -124,6 +124,29 @@ long long kvae_plan_out_length(const kvae_plan* plan, long long T);
  * duplication of :235) and zero-padded.  scratch: >= 4*B bytes. */
 int kvae_prep_mono_clips(const float* wav, const long long* offsets, const int* lens, int B, long long L_pad,
                          int channels, float gain, float* out, void* scratch, void* stream);
+/* ---- stateful streaming decode: replaces decode_audio(chunked=True, chunk_size, overlap) (autoencoders.py:499-560)
+ * for callers that receive latents incrementally (infer_stream-style).  The reference re-decodes overlapping windows
+ * (1.33x the work at 128/32); a kvae_stream keeps every layer's input tail between calls instead (persistent
+ * per-layer halo state), so every row of every layer is computed once and the concatenated output equals
+ * kvae_decode of the whole sequence bit for bit.  One stream = B clips advancing in lockstep; not thread-safe.
+ *   begin   allocates the window buffers for pushes of up to max_frames latent frames; use_graphs != 0 replays
+ *           calls of a geometry seen before as one CUDA graph (constant-hop streams: one graph launch per hop)
+ *   samples how many samples per channel the next push of n_frames (or, end != 0, the end call) will emit
+ *   push    z [B, latent_dim, n_frames] -> wav [B, io_channels, *n_samples] (packed with that length); the output
+ *           trails the input by kvae_decode_stream_lookahead samples (the decoder's receptive field, 10 latent
+ *           frames for the SAO / 12.5 Hz strides), so early pushes may emit nothing
+ *   end     emits the remaining samples (right edge zero-padded like the unchunked decode) and resets the stream
+ * Decoder plans whose layers all run on the tensor-core kernels (latent_dim / channels multiples of 64, 128-channel
+ * tail), bf16 or fp32 mode; other architectures get an error (the Python layer then streams by exact-context windows). */
+typedef struct kvae_stream kvae_stream;
+int kvae_decode_stream_begin(kvae_plan* plan, int B, int max_frames, int use_graphs, kvae_stream** out);
+long long kvae_decode_stream_samples(kvae_stream* s, int n_frames, int end);
+long long kvae_decode_stream_lookahead(const kvae_stream* s);
+int kvae_decode_stream_push(kvae_stream* s, const void* z, int z_dtype, int n_frames, void* wav, int wav_dtype,
+                            long long wav_capacity, long long* n_samples, void* stream);
+int kvae_decode_stream_end(kvae_stream* s, void* wav, int wav_dtype, long long wav_capacity, long long* n_samples,
+                           void* stream);
+void kvae_decode_stream_destroy(kvae_stream* s);
 /* algorithmic FLOPs of one pass (2*MACs of every conv, all taps counted) */
 double kvae_plan_flops(const kvae_plan* plan, int B, long long T);
 

@@ -64,6 +64,14 @@ SIGNATURES = {
                                      C.POINTER(C.c_int), C.c_void_p, C.c_size_t, C.c_void_p]),
     "kvae_encode_ragged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_longlong,
                                      C.POINTER(C.c_int), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kvae_decode_stream_begin": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "kvae_decode_stream_samples": (C.c_longlong, [C.c_void_p, C.c_int, C.c_int]),
+    "kvae_decode_stream_lookahead": (C.c_longlong, [C.c_void_p]),
+    "kvae_decode_stream_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_longlong,
+                                          C.POINTER(C.c_longlong), C.c_void_p]),
+    "kvae_decode_stream_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.POINTER(C.c_longlong),
+                                         C.c_void_p]),
+    "kvae_decode_stream_destroy": (None, [C.c_void_p]),
     "kvae_plan_out_length": (C.c_longlong, [C.c_void_p, C.c_longlong]),
     "kvae_prep_mono_clips": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_float,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),

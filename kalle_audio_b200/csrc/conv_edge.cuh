@@ -30,6 +30,10 @@ struct WaveOutParams {
   int T, Cin, tanh_out;
   int B, tiles_per_clip, total_tiles;
   int precise;            // fp32 mode: range-reduced sine (<= 1e-5 budget) instead of the plain MUFU approximation
+  // input geometry (a whole clip: T_in = T, in_row0 = -3, x_pitch = T; the streaming decoder passes a window buffer):
+  // output t reads input rows t + in_row0 .. t + in_row0 + 6, rows outside [0, T_in) are the conv's zero padding
+  int T_in, in_row0;
+  long long x_pitch;      // rows between clips in x
 };
 
 constexpr int kWaveOutTile = 128;              // outputs per tile
@@ -71,11 +75,16 @@ __global__ void __launch_bounds__(288, 1) conv_wave_out_kernel(const WaveOutPara
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int b = tile / p.tiles_per_clip;
         const int t0 = (tile % p.tiles_per_clip) * TT;
-        const int r_lo = max(0, 3 - t0);                       // first staged row that exists
-        const int r_hi = min(RS, p.T - (t0 - 3));              // one past the last
+        const int r_lo = max(0, -(t0 + p.in_row0));             // first staged row that exists
+        const int r_hi = max(r_lo, min(RS, p.T_in - (t0 + p.in_row0)));   // one past the last
         ptx::mbar_wait(&empty[buf], ph ^ 1u);
+        if (r_hi == r_lo) {                                    // nothing to fetch (cannot happen for a tile with outputs)
+          ptx::mbar_arrive(&full[buf]);
+          if (++buf == NB) { buf = 0; ph ^= 1u; }
+          continue;
+        }
         ptx::mbar_expect_tx(&full[buf], static_cast<uint32_t>(r_hi - r_lo) * CIN * 4);
-        const float* src = p.x + (static_cast<size_t>(b) * p.T + (t0 - 3 + r_lo)) * CIN;
+        const float* src = p.x + (static_cast<size_t>(b) * p.x_pitch + (t0 + p.in_row0 + r_lo)) * CIN;
         float* dst = ring + static_cast<size_t>(buf) * RS * CIN + r_lo * CIN;
         for (int r = r_lo; r < r_hi; r += 32) {
           const int n = min(32, r_hi - r);
@@ -106,10 +115,10 @@ __global__ void __launch_bounds__(288, 1) conv_wave_out_kernel(const WaveOutPara
     const int t0 = (tile % p.tiles_per_clip) * TT;
     ptx::mbar_wait(&full[buf], ph);
     const float* tile_s = ring + static_cast<size_t>(buf) * RS * CIN + 4 * lane;
-    auto load_row = [&](int r) -> float4 {   // staged row r <-> time t0 - 3 + r; zero outside the clip (conv padding)
-      const int t = t0 - 3 + r;
+    auto load_row = [&](int r) -> float4 {   // staged row r <-> input row t0 + in_row0 + r; zero outside (conv padding)
+      const int t = t0 + p.in_row0 + r;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t >= 0 && t < p.T) {
+      if (t >= 0 && t < p.T_in) {
         v = *reinterpret_cast<const float4*>(tile_s + r * CIN);
         if (p.precise) {
           v.x = snake_beta_rr(v.x, sa.x, sib.x); v.y = snake_beta_rr(v.y, sa.y, sib.y);
@@ -199,6 +208,7 @@ struct WaveOutTcParams {
   int y_f32;
   int T, B, COUT, tanh_out;
   int tiles_per_clip, total_tiles;
+  int in_row0;              // output t reads input rows t + in_row0 .. +6 of tmX (-3 for a whole clip)
 };
 
 // kF16 = true: the residual stream is fp16 in HBM (inference plans).  The tile is then two 64-channel chunks of
@@ -287,7 +297,7 @@ conv_wave_out_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         ptx::mbar_wait(&empty[s], ph ^ 1u);
         ptx::mbar_expect_tx(&full[s], kWoTcSlab);
         for (int c = 0; c < kChunks; ++c)
-          ptx::tma_load_4d(ring + s * kWoTcSlab + c * kWoTcChunk, &tmX, &full[s], c * (kF16 ? 64 : 32), 0, t0 - 3, b);
+          ptx::tma_load_4d(ring + s * kWoTcSlab + c * kWoTcChunk, &tmX, &full[s], c * (kF16 ? 64 : 32), 0, t0 + p.in_row0, b);
         if (++s == kWoTcSlots) { s = 0; ph ^= 1u; }
       }
     }

@@ -149,13 +149,14 @@ inline PFN_tmapEncodeTiled tmap_encoder() {
 }
 
 // Activations x: [B, T, C] bf16 viewed as [B, T/P, P, C]; box = {64 ch, 1 phase, RB rows, 1}.
+// pitch_rows (0 = T): rows between consecutive clips in memory -- streaming buffers hold more rows than are valid
 inline bool make_act_tmap(CUtensorMap* m, const void* x, int B, int T, int C, int P, int RB,
-                          std::string& err) {
+                          std::string& err, long long pitch_rows = 0) {
   auto enc = tmap_encoder();
   if (!enc) { err = "cuTensorMapEncodeTiled unavailable"; return false; }
   if (T % P) { err = "input length not divisible by stride"; return false; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)P, (cuuint64_t)(T / P), (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)P * C * 2, (cuuint64_t)T * C * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)P * C * 2, (cuuint64_t)(pitch_rows ? pitch_rows : T) * C * 2};
   cuuint32_t box[4] = {64, 1, (cuuint32_t)RB, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box,
@@ -185,14 +186,14 @@ inline bool make_w_tmap(CUtensorMap* m, const void* w, int nslab, int Cout, int 
 // fp32 blocks are 128 B wide (SWIZZLE_128B), bf16 blocks 64 B (SWIZZLE_64B).
 // dtype: 1 fp32, 0 bf16, 2 fp16 (2-byte types differ only in the tensor map's element type)
 inline bool make_out_tmap(CUtensorMap* m, const void* y, int B, int T, int C, int P, int dtype, std::string& err,
-                          int box_rows = 32) {
+                          int box_rows = 32, long long pitch_rows = 0) {
   const bool f32 = (dtype == 1);
   auto enc = tmap_encoder();
   if (!enc) { err = "cuTensorMapEncodeTiled unavailable"; return false; }
   if (T % P) { err = "output length not divisible by stride"; return false; }
   const cuuint64_t es = f32 ? 4 : 2;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)P, (cuuint64_t)(T / P), (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)P * C * es, (cuuint64_t)T * C * es};
+  cuuint64_t strides[3] = {(cuuint64_t)C * es, (cuuint64_t)P * C * es, (cuuint64_t)(pitch_rows ? pitch_rows : T) * C * es};
   cuuint32_t box[4] = {32, 1, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
@@ -329,17 +330,33 @@ inline int sm_count() {
   return v;
 }
 
+// Incremental ("valid") form of a layer for the stateful streaming decoder: the input is a window buffer
+// [carry rows | new rows] of in_rows rows, every tap reads at a non-negative offset (row_bias = -min tap offset is
+// added to all of them), and exactly out_q output rows per phase are produced -- those whose receptive field lies
+// inside the window (or, at the end of the stream, beyond its last row, where TMA's out-of-bounds zero fill is the
+// conv's zero padding).  Output / skip pointers are passed already offset to their first row; *_pitch = rows between
+// clips in those buffers.
+struct StreamGeom {
+  int in_rows = 0, out_q = 0, row_bias = 0;
+  long long in_pitch = 0, raw_pitch = 0, act_pitch = 0, res_pitch = 0;
+};
+
 // ep.out_raw: fp32 channels-last via TMA unless ep.out_raw_cf (then channels-first direct, any dtype).
 // ep.residual must be fp32 channels-last.
 inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B, int T_in,
                                const __nv_bfloat16* wpacked, const ConvEpilogue& ep, const ConvTuning2& tune,
-                               ConvLaunch2& L, std::string& err) {
+                               ConvLaunch2& L, std::string& err, const StreamGeom* sg = nullptr) {
   if (!umma_supported(g)) { err = "channel counts not multiples of 64"; return false; }
   if (ep.residual && !ep.residual_f32 && !ep.stream_f16) { err = "residual must be fp32 (or the fp16 stream)"; return false; }
   if (ep.out_raw && !ep.out_raw_cf && !ep.out_raw_f32 && !ep.stream_f16) { err = "channels-last raw output must be fp32 (or the fp16 stream)"; return false; }
   TapPlan tp;
   if (!build_taps(g, false, tp, err)) return false;
-  const int T_out = g.out_len(T_in);
+  if (sg) {
+    if (tp.P_in != 1) { err = "streaming form needs a stride-1 or transposed conv"; return false; }
+    T_in = sg->in_rows;
+    for (Tap& t : tp.taps) t.a_row = static_cast<int16_t>(t.a_row + sg->row_bias);
+  }
+  const int T_out = sg ? sg->out_q * tp.P_out : g.out_len(T_in);
   if (T_out <= 0 || T_out % tp.P_out) { err = "bad output length"; return false; }
   ConvParams2& p = L.p;
   std::memset(&p, 0, sizeof(p));
@@ -439,15 +456,15 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
   p.snake_a = ep.snake_a;
   p.snake_inv_b = ep.snake_inv_b;
   const int kmul = p.split3 ? 2 : 1;
-  if (!make_act_tmap(&L.tmA, x, B, T_in, g.Cin * kmul, tp.P_in, p.RB, err)) return false;
+  if (!make_act_tmap(&L.tmA, x, B, T_in, g.Cin * kmul, tp.P_in, p.RB, err, sg ? sg->in_pitch : 0)) return false;
   if (!make_w_tmap(&L.tmW, wpacked, g.K, g.Cout, g.Cin * kmul, p.NT, err)) return false;
-  if (p.raw_mode == 1) { if (!make_out_tmap(&L.tmR, ep.out_raw, B, T_out, g.Cout, tp.P_out, sdt, err)) return false; }
+  if (p.raw_mode == 1) { if (!make_out_tmap(&L.tmR, ep.out_raw, B, T_out, g.Cout, tp.P_out, sdt, err, 32, sg ? sg->raw_pitch : 0)) return false; }
   else L.tmR = L.tmA;
   if (p.act_mode == 1) {
-    if (!make_out_tmap(&L.tmO, ep.out_act, B, T_out, g.Cout * (p.act_split ? 2 : 1), tp.P_out, false, err)) return false;
+    if (!make_out_tmap(&L.tmO, ep.out_act, B, T_out, g.Cout * (p.act_split ? 2 : 1), tp.P_out, false, err, 32, sg ? sg->act_pitch : 0)) return false;
   }
   else L.tmO = L.tmA;
-  if (ep.residual) { if (!make_out_tmap(&L.tmX, ep.residual, B, T_out, g.Cout, tp.P_out, sdt, err)) return false; }
+  if (ep.residual) { if (!make_out_tmap(&L.tmX, ep.residual, B, T_out, g.Cout, tp.P_out, sdt, err, 32, sg ? sg->res_pitch : 0)) return false; }
   else L.tmX = L.tmA;
   const int ctas = tune.max_ctas ? tune.max_ctas : sm_count();
   L.grid = std::min(p.total_tiles, ctas);
@@ -496,18 +513,22 @@ struct RuArgs {
 
 inline bool ru_supported(int C) { return C == kRuC; }
 
-inline bool prepare_conv_ru(const RuArgs& a, int B, int T, int dilation, RuLaunch& L, std::string& err) {
+// sg (streaming form): T = sg->out_q output rows from a window of sg->in_rows rows; a.x is the skip pointer already
+// offset by the unit's lag (3 * dilation rows into the window), out pointers offset to their first row
+inline bool prepare_conv_ru(const RuArgs& a, int B, int T, int dilation, RuLaunch& L, std::string& err,
+                            const StreamGeom* sg = nullptr) {
   if (!a.a || !a.x || !a.w7 || !a.w1 || !a.bias7 || !a.bias1 || !a.s2_a || !a.s2_inv_b) { err = "fused RU: null argument"; return false; }
   if (!a.out_raw && !a.out_act) { err = "fused RU: no output"; return false; }
   RuParams& p = L.p;
   std::memset(&p, 0, sizeof(p));
+  if (sg) T = sg->out_q;
   p.B = B;
   p.T = T;
   const int rows = 256 + 6 * dilation;
   p.nbox = (rows + 255) / 256;
   p.RB = (((rows + p.nbox - 1) / p.nbox) + 7) & ~7;
   if (p.RB > 256) { err = "fused RU: dilation too large"; return false; }
-  p.slab_row0 = -3 * dilation;
+  p.slab_row0 = sg ? -3 * dilation + sg->row_bias : -3 * dilation;
   for (int t = 0; t < 7; ++t) p.tap_shift16[t] = static_cast<uint32_t>(t * dilation * 8);
   p.raw_out = a.out_raw ? 1 : 0;
   p.act_out = a.out_act ? 1 : 0;
@@ -540,12 +561,12 @@ inline bool prepare_conv_ru(const RuArgs& a, int B, int T, int dilation, RuLaunc
   if (const char* e = getenv("KVAE_RU_K0")) p.k0 = atoi(e);
   if (const char* e = getenv("KVAE_RU_K1")) p.k1 = atoi(e);
   if (p.k0 < 0 || p.k1 <= p.k0 || p.k1 > 13) { err = "fused RU: need 0 <= k0 < k1 <= 13"; return false; }
-  if (!make_act_tmap(&L.tmA, a.a, B, T, kRuC, 1, p.RB, err)) return false;
+  if (!make_act_tmap(&L.tmA, a.a, B, sg ? sg->in_rows : T, kRuC, 1, p.RB, err, sg ? sg->in_pitch : 0)) return false;
   if (!make_w_tmap(&L.tmW7, a.w7, 7, kRuC, kRuC, kRuC, err)) return false;
   if (!make_w_tmap(&L.tmW1, a.w1, 1, kRuC, kRuC, kRuC, err)) return false;
-  if (!make_out_tmap(&L.tmX, a.x, B, T, kRuC, 1, sdt, err, 16)) return false;
-  if (a.out_raw) { if (!make_out_tmap(&L.tmR, a.out_raw, B, T, kRuC, 1, sdt, err, 16)) return false; } else L.tmR = L.tmX;
-  if (a.out_act) { if (!make_out_tmap(&L.tmO, a.out_act, B, T, kRuC, 1, false, err, 16)) return false; } else L.tmO = L.tmX;
+  if (!make_out_tmap(&L.tmX, a.x, B, T, kRuC, 1, sdt, err, 16, sg ? sg->res_pitch : 0)) return false;
+  if (a.out_raw) { if (!make_out_tmap(&L.tmR, a.out_raw, B, T, kRuC, 1, sdt, err, 16, sg ? sg->raw_pitch : 0)) return false; } else L.tmR = L.tmX;
+  if (a.out_act) { if (!make_out_tmap(&L.tmO, a.out_act, B, T, kRuC, 1, false, err, 16, sg ? sg->act_pitch : 0)) return false; } else L.tmO = L.tmX;
   L.grid = std::min(p.total_tiles, sm_count());
   if (const char* e = getenv("KVAE_RU_GRID")) L.grid = std::max(1, std::min(L.grid, atoi(e)));   // tests: many tiles per CTA
   L.smem = ru_smem_bytes(p);

@@ -54,7 +54,10 @@ __global__ void snake_params_kernel(const float* alpha, const float* beta, int l
 // ---------------------------------------------------------------- [B, C, T] -> [B, T, C] bf16
 // 32x32 shared-memory tile transpose.  grid: (ceil(T/32), ceil(C/32), B), block (32, 8)
 // split = 1: y is [B, T, 2C] with the bf16 (hi | lo) halves of the fp32 value (fp32-mode tensor-core operand)
-__global__ void cf_to_cl_bf16_kernel(const void* x, int f32, __nv_bfloat16* y, int C, int T, int split) {
+// y_pitch (0 = T): rows between clips in y (the streaming decoder writes into a window buffer)
+__global__ void cf_to_cl_bf16_kernel(const void* x, int f32, __nv_bfloat16* y, int C, int T, int split,
+                                     long long y_pitch = 0) {
+  const long long YP = y_pitch ? y_pitch : T;
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -69,10 +72,10 @@ __global__ void cf_to_cl_bf16_kernel(const void* x, int f32, __nv_bfloat16* y, i
       const float v = tile[threadIdx.x][i];
       const __nv_bfloat16 hi = __float2bfloat16(v);
       if (split) {
-        y[(static_cast<size_t>(b) * T + t) * 2 * C + c] = hi;
-        y[(static_cast<size_t>(b) * T + t) * 2 * C + C + c] = __float2bfloat16(v - __bfloat162float(hi));
+        y[(static_cast<size_t>(b) * YP + t) * 2 * C + c] = hi;
+        y[(static_cast<size_t>(b) * YP + t) * 2 * C + C + c] = __float2bfloat16(v - __bfloat162float(hi));
       } else {
-        y[(static_cast<size_t>(b) * T + t) * C + c] = hi;
+        y[(static_cast<size_t>(b) * YP + t) * C + c] = hi;
       }
     }
   }
@@ -286,6 +289,11 @@ __global__ void pcm16_kernel(const void* x, size_t n, int f32, const unsigned in
     v = fminf(fmaxf(v, -1.f), 1.f);
     out[i] = static_cast<int16_t>(__float2int_rz(__fmul_rn(v, 32767.f)));
   }
+}
+
+__global__ void f32_to_bf16_kernel(const float* x, __nv_bfloat16* y, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    y[i] = __float2bfloat16(x[i]);
 }
 
 // ---------------------------------------------------------------- ragged batches

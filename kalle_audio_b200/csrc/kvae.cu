@@ -564,6 +564,7 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
       w.w = c.w_direct;
       w.y = nullptr;  // patched per call
       w.T = static_cast<int>(T_out);
+      w.T_in = w.T; w.in_row0 = -3; w.x_pitch = w.T;
       w.Cin = c.g.Cin;
       w.tanh_out = (p->direction == KVAE_DECODER && p->arch.final_tanh) ? 1 : 0;
       w.precise = (p->precision == KVAE_PREC_F32) ? 1 : 0;
@@ -573,7 +574,7 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
         PreparedRun::WaveOutTc& t = R.wave_out_tc[k];
         std::memset(&t.p, 0, sizeof(t.p));
         t.p.pro_a = w.pro_a; t.p.pro_inv_b = w.pro_inv_b; t.p.w = w.w;
-        t.p.T = w.T; t.p.B = B; t.p.COUT = c.g.Cout; t.p.tanh_out = w.tanh_out;
+        t.p.T = w.T; t.p.B = B; t.p.COUT = c.g.Cout; t.p.tanh_out = w.tanh_out; t.p.in_row0 = -3;
         t.p.tiles_per_clip = (w.T + kWoTcTile - 1) / kWoTcTile;
         t.p.total_tiles = t.p.tiles_per_clip * B;
         if (sf16) { if (!make_act_tmap(&t.tmX, w.x, B, w.T, 128, 1, kWoTcRows, err)) return false; }
@@ -1293,6 +1294,8 @@ int run_backward(kvae_plan* p, const void* x, int x_dtype, const void* gy, int g
 
 bool check_dtype(int d) { return d == KVAE_F32 || d == KVAE_BF16; }
 
+#include "stream.inc.cuh"
+
 }  // namespace
 
 // =============================================================================== C ABI
@@ -2009,6 +2012,58 @@ int kvae_sigma_sample(const void* mean, const void* noise, void* out, size_t n, 
   KV_CUDA(cudaGetLastError());
   ++g_launches;
   return 0;
+}
+
+// ------------------------------------------------------------------ stateful streaming decode
+int kvae_decode_stream_begin(kvae_plan* plan, int B, int max_frames, int use_graphs, kvae_stream** out) {
+  return stream_create(plan, B, max_frames, use_graphs, out);
+}
+
+void kvae_decode_stream_destroy(kvae_stream* s) {
+  if (!s) return;
+  DeviceGuard guard(s->plan->device);
+  s->cache.clear();
+  if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
+  cudaFree(s->ws);
+  cudaFree(s->z_stage);
+  cudaFree(s->wav_stage);
+  cudaFree(s->scratch);
+  delete s;
+}
+
+long long kvae_decode_stream_samples(kvae_stream* s, int n_frames, int end) {
+  if (!s) return fail("null stream");
+  if (n_frames < 0 || n_frames > s->max_frames) return fail("streaming: n_frames out of range (0 .. max_frames)");
+  DeviceGuard guard(s->plan->device);
+  PreparedPush* P = stream_get(s, end ? 0 : n_frames, end != 0, KVAE_F32);
+  return P ? P->n_samples : -1;
+}
+
+long long kvae_decode_stream_lookahead(const kvae_stream* s) {
+  if (!s) return fail("null stream");
+  // samples by which the emitted waveform trails the pushed latents in steady state
+  long long lag = 0;                       // in rows of the current rate, accumulated front to back
+  for (size_t k = 0; k < s->ss.size(); ++k) {
+    if (s->ss[k].kind == 5) continue;
+    lag = (lag + s->ss[k].dmax) * s->ss[k].P_out;
+  }
+  return lag;
+}
+
+int kvae_decode_stream_push(kvae_stream* s, const void* z, int z_dtype, int n_frames, void* wav, int wav_dtype,
+                            long long wav_capacity, long long* n_samples, void* stream) {
+  if (!s) return fail("null stream");
+  if (n_frames > 0 && !z) return fail("null latents");
+  if (!check_dtype(z_dtype) || !check_dtype(wav_dtype)) return fail("bad dtype");
+  if (!wav && wav_capacity > 0) return fail("null wav");
+  return stream_run(s, z, z_dtype, n_frames, false, wav, wav_dtype, wav_capacity, n_samples, static_cast<cudaStream_t>(stream));
+}
+
+int kvae_decode_stream_end(kvae_stream* s, void* wav, int wav_dtype, long long wav_capacity, long long* n_samples,
+                           void* stream) {
+  if (!s) return fail("null stream");
+  if (!check_dtype(wav_dtype)) return fail("bad dtype");
+  return stream_run(s, nullptr, KVAE_F32, 0, true, wav, wav_dtype, wav_capacity, n_samples, static_cast<cudaStream_t>(stream));
 }
 
 int kvae_lm_glue_step(const void* hidden, int hidden_dtype, const float* w1, const float* b1, const float* w2,

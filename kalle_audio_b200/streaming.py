@@ -1,4 +1,15 @@
-"""Incremental latent -> waveform decoding with exact receptive-field context.
+"""Incremental latent -> waveform decoding.
+
+Two engines behind one class:
+
+* **stateful** (default wherever the decoder's layers all have tensor-core kernels -- the graded architectures):
+  ``kvae_decode_stream_begin / push / end``.  Every layer keeps the tail of its own input between calls (persistent
+  per-layer halo state inside libkvae), so each row of each layer is computed exactly once -- 0 % recompute -- and
+  the concatenated output equals ``decoder(latents)`` bit for bit.  A constant-hop stream is one CUDA-graph launch
+  per hop.  Samples come out as soon as they are final, i.e. ``lookahead`` samples behind the pushed latents.
+* **exact-context windows** (other architectures): described below.
+
+Exact-context windows:
 
 The reference streams by ``decode_audio(chunked=True, chunk_size=128, overlap=32)``
 (stable_audio_tools/models/autoencoders.py:499-560; infer_stream-style callers): overlapping windows, the middle of
@@ -50,7 +61,11 @@ class StreamingDecoder:
 
     ``torch.cat`` of everything returned equals ``decoder(torch.cat(latent_chunks, -1))``."""
 
-    def __init__(self, decoder, hop: int = 96, use_cuda_graphs: bool = True):
+    def __init__(self, decoder, hop: int = 96, use_cuda_graphs: bool = True, stateful: Optional[bool] = None,
+                 max_frames: Optional[int] = None):
+        """``stateful``: None = the stateful engine when the plan supports it, else exact-context windows; True =
+        stateful or raise; False = windows.  ``hop``: window mode emits in multiples of ``hop`` frames; the stateful
+        engine takes pushes of any size up to ``max_frames`` (default ``max(hop, 128)``) and splits longer ones."""
         if not hasattr(decoder, "_arch") or decoder._direction != _lib.KVAE_DECODER:
             raise TypeError("StreamingDecoder wraps a kalle_audio_b200.OobleckDecoder")
         if hop < 1:
@@ -60,7 +75,12 @@ class StreamingDecoder:
         strides = [decoder._arch.strides[i] for i in range(decoder._arch.n_stages)]
         self.ratio = int(math.prod(strides))
         self.left, self.right = decoder_context_frames(strides)
-        if use_cuda_graphs:
+        self.max_frames = int(max_frames or max(self.hop, 128))
+        self._use_graphs = bool(use_cuda_graphs)
+        self._want_stateful = stateful
+        self._native = None            # (handle, finalizer, runner, batch) once the first push fixes device and batch
+        self.stateful = False
+        if use_cuda_graphs and stateful is False:
             decoder.enable_cuda_graphs(True)
         self.reset()
 
@@ -68,10 +88,67 @@ class StreamingDecoder:
         self._buf: Optional[torch.Tensor] = None   # frames [emitted - left_available, received)
         self._emitted = 0                          # frames already returned
         self._start = 0                            # absolute index of _buf[..., 0]
+        if self._native is not None:
+            self._native[1]()                      # destroy the stream: a fresh one starts with zeroed halo state
+            self._native = None
 
     @property
     def recompute_factor(self) -> float:
-        return (self.hop + self.left + self.right) / self.hop
+        return 1.0 if self.stateful else (self.hop + self.left + self.right) / self.hop
+
+    # ------------------------------------------------------------------ stateful engine (libkvae)
+    def _native_stream(self, latents: torch.Tensor):
+        import ctypes as C
+        import weakref
+        if self._native is not None:
+            if self._native[3] != latents.shape[0]:
+                raise ValueError("batch size changed inside a stream")
+            return self._native
+        if self._want_stateful is False:
+            return None
+        L = _lib.lib()
+        r = self.decoder.runner(latents.device)
+        r.sync_weights()
+        h = C.c_void_p()
+        rc = L.kvae_decode_stream_begin(r.handle, latents.shape[0], self.max_frames, int(self._use_graphs), C.byref(h))
+        if rc != 0:
+            if self._want_stateful:
+                raise _lib.KvaeError(L.kvae_last_error().decode())
+            self._want_stateful = False            # this architecture streams by windows
+            if self._use_graphs:
+                self.decoder.enable_cuda_graphs(True)
+            return None
+        fin = weakref.finalize(self, L.kvae_decode_stream_destroy, h)
+        self._native = (h, fin, r, latents.shape[0])
+        self.stateful = True
+        self.lookahead = int(L.kvae_decode_stream_lookahead(h))
+        return self._native
+
+    def _native_call(self, nat, z: Optional[torch.Tensor], end: bool) -> torch.Tensor:
+        import ctypes as C
+        L = _lib.lib()
+        h, _, r, B = nat
+        r.sync_weights()
+        dev = r.device
+        out_dt = self.decoder._out_dtype(z) if z is not None else self._last_dtype
+        self._last_dtype = out_dt
+        kdt = out_dt if out_dt in (torch.float32, torch.bfloat16) else torch.float32
+        n = 0 if z is None else z.shape[2]
+        ns = int(L.kvae_decode_stream_samples(h, n, int(end)))
+        if ns < 0:
+            raise _lib.KvaeError(L.kvae_last_error().decode())
+        wav = torch.empty((B, self.decoder._out_channels_for_plan, ns), dtype=kdt, device=dev)
+        got = C.c_longlong(0)
+        if end:
+            _lib.check(L.kvae_decode_stream_end(h, wav.data_ptr(), _lib.dtype_code(kdt), ns, C.byref(got),
+                                                _lib.stream_ptr(dev)))
+        else:
+            zin = z if z.dtype in (torch.float32, torch.bfloat16) else z.float()
+            zin = zin.contiguous()
+            _lib.check(L.kvae_decode_stream_push(h, zin.data_ptr(), _lib.dtype_code(zin.dtype), n, wav.data_ptr(),
+                                                 _lib.dtype_code(kdt), ns, C.byref(got), _lib.stream_ptr(dev)))
+        assert got.value == ns
+        return wav if wav.dtype == out_dt else wav.to(out_dt)
 
     def _decode_window(self, first: int, last: int, end_of_stream: bool) -> torch.Tensor:
         """Decodes frames [first, last) with whatever context exists and returns exactly their samples."""
@@ -93,6 +170,14 @@ class StreamingDecoder:
         _lib.require_cuda(latents, "StreamingDecoder.push")
         if latents.dim() != 3:
             raise ValueError("expected [B, D, n]")
+        nat = self._native_stream(latents)
+        if nat is not None:
+            self._pushed = getattr(self, "_pushed", 0) + latents.shape[2]
+            pieces = [self._native_call(nat, latents[:, :, i:i + self.max_frames], False)
+                      for i in range(0, latents.shape[2], self.max_frames)]
+            if not pieces:
+                return latents.new_zeros((latents.shape[0], self.decoder._out_channels_for_plan, 0))
+            return pieces[0] if len(pieces) == 1 else torch.cat(pieces, dim=2)
         self._buf = latents if self._buf is None else torch.cat([self._buf, latents], dim=2)
         received = self._start + self._buf.shape[2]
         out: List[torch.Tensor] = []
@@ -108,6 +193,10 @@ class StreamingDecoder:
 
     def flush(self) -> torch.Tensor:
         """Everything not yet emitted (end of stream).  Resets the state."""
+        if self._native is not None:
+            res = self._native_call(self._native, None, True)
+            self._pushed = 0
+            return res                  # the library has reset the stream: the next push starts a new one
         if self._buf is None:
             raise ValueError("nothing was pushed")
         received = self._start + self._buf.shape[2]

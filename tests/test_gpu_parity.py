@@ -605,3 +605,65 @@ def test_nearest_upsample_decoder_vs_reference(dev):
     with pytest.raises(NotImplementedError):
         with torch.enable_grad():
             d(z.clone().requires_grad_(True))
+
+
+def _small_128_decoder(dev, latent=64):
+    torch.manual_seed(0)
+    d = k.OobleckDecoder(out_channels=2, channels=128, latent_dim=latent, c_mults=[1, 2], strides=[2, 4], use_snake=True,
+                         final_tanh=False).eval()
+    H.randomize_snake(d, 7)
+    return d.to(dev)
+
+
+@pytest.mark.parametrize("precision,graphs", [("bf16", False), ("bf16", True), ("fp32", False)])
+def test_stateful_streaming_equals_unchunked_bit_for_bit(dev, precision, graphs):
+    """kvae_decode_stream_*: persistent per-layer halo state, 0 % recompute.  Ragged pushes (incl. pushes shorter than a
+    layer's halo and an empty one) through a 128/256-channel decoder (fused ResidualUnits at C=128, separate k7/k1 at
+    C=256, transposed convs, tensor-core tail): the concatenation equals ONE decode of the whole sequence exactly, and
+    the decode equals the oracle."""
+    d = _small_128_decoder(dev).set_precision(precision)
+    z = torch.randn(2, 64, 211, generator=torch.Generator().manual_seed(4)).to(dev)
+    full = d(z)
+    sd = k.StreamingDecoder(d, hop=16, use_cuda_graphs=graphs, stateful=True, max_frames=64)
+    for rep in range(2):                                   # a second stream on the same object starts from clean state
+        pieces, pos = [], 0
+        for n in [1, 0, 5, 40, 3, 97, 20, 45]:
+            pieces.append(sd.push(z[:, :, pos:pos + n]))
+            pos += n
+        assert sd.stateful and sd.recompute_factor == 1.0 and pos == 211
+        emitted = sum(p.shape[2] for p in pieces)
+        assert emitted == 211 * 8 - sd.lookahead and sd.lookahead > 0
+        pieces.append(sd.flush())
+        y = torch.cat(pieces, dim=2)
+        assert y.shape == full.shape
+        assert torch.equal(y, full), float((y - full).abs().max())
+    ref = O.oobleck_decoder({n: p.cpu() for n, p in d.state_dict().items()}, z.cpu(), [2, 4])
+    # (a fixture with perturbed SnakeBeta parameters, not a BASELINE config: budgets scale with its magnitude, see bf16_tol)
+    assert maxerr(full, ref) <= (TOL_F32 * max(1.0, float(ref.abs().max()) / 0.125) if precision == "fp32" else bf16_tol(ref))
+    # constant-hop steady state (what a CUDA graph replays)
+    sd2 = k.StreamingDecoder(d, hop=32, use_cuda_graphs=graphs, stateful=True, max_frames=32)
+    out = [sd2.push(z[:, :, i:i + 32]) for i in range(0, 192, 32)] + [sd2.push(z[:, :, 192:])]
+    out.append(sd2.flush())
+    assert torch.equal(torch.cat(out, dim=2), full)
+
+
+def test_config4_stateful_stream_o12_latent1024(dev):
+    """BASELINE config 4's model (O12 latent 1024, batch 1) streamed in 96-frame hops with CUDA-graph replay: equals
+    the unchunked decode bit for bit (which test_config4_chunked_decode_... pins against the oracle and the reference)."""
+    m = H.build("o12_d1024", 0).to(dev).set_precision("bf16")
+    z = torch.randn(1, 1024, 375, generator=torch.Generator().manual_seed(1)).to(dev)
+    full = m.decoder(z)
+    sd = k.StreamingDecoder(m.decoder, hop=96, use_cuda_graphs=True, stateful=True)
+    out = [sd.push(z[:, :, i:i + 96]) for i in range(0, 375, 96)]
+    assert 0 < sd.lookahead <= 10 * 1280          # the decoder's receptive field: 10 latent frames (SURVEY section 5)
+    out.append(sd.flush())
+    y = torch.cat(out, dim=2)
+    assert y.shape == full.shape == (1, 1, 480000)
+    assert torch.equal(y, full), float((y - full).abs().max())
+    g = H.golden("o12_full")
+    idx = H.t(g["idx"]).long().to(dev)
+    err = maxerr(y[:, :, idx], g["d1024_at_idx"])
+    H.report("config 4 stateful stream (96-frame hops, 0 % recompute) at the reference's recorded points", err)
+    assert err <= TOL_BF16
+    with pytest.raises(k.KvaeError):
+        k.StreamingDecoder(H.build("tiny", 0).to(dev).decoder, stateful=True).push(torch.randn(1, 4, 8, device=dev))
