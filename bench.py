@@ -277,9 +277,9 @@ def run_cuda(args):
     audio_s_per_step = B * L / SAO["sample_rate"]
 
     def roundtrip(x):
-        e = ae.encode(x)
-        mean, _scale = e.chunk(2, dim=1)
-        z = k.sample(mean.contiguous(), "fix")
+        # encode -> split mean | scale -> sample('fix') in one plan call (the sampler runs in the epilogue of the
+        # encoder's last conv; torch only draws the noise), then decode
+        _ms, z = ae.encode_and_sample(x)
         return ae.decode(z), z
 
     def step_resident():

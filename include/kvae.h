@@ -147,6 +147,15 @@ int kvae_decode_stream_push(kvae_stream* s, const void* z, int z_dtype, int n_fr
 int kvae_decode_stream_end(kvae_stream* s, void* wav, int wav_dtype, long long wav_capacity, long long* n_samples,
                            void* stream);
 void kvae_decode_stream_destroy(kvae_stream* s);
+/* kvae_encode with the sigma-VAE sample fused into the last conv's epilogue: lat [B, latent_dim, T] as kvae_encode,
+ * and z [B, D, T] = lat[:, :D] + std * noise (sample(mean, 'fix') of model_sigmaVAE.py:187-213 applied to the mean
+ * half of the encoder output, D = latent_dim / 2 for the mean | scale layout of twj_dataset.py:251), evaluated on the
+ * STORED latents with torch's two roundings, so z is bit-identical to the two-step form.  noise, z and lat share
+ * lat_dtype.  Tensor-core encoder plans only (kvae_plan_fused_sample_supported). */
+int kvae_encode_sample(kvae_plan* plan, const void* wav, int wav_dtype, void* lat, void* z, const void* noise,
+                       int lat_dtype, int D, float std, int B, long long L, void* workspace, size_t workspace_bytes,
+                       void* stream);
+int kvae_plan_fused_sample_supported(const kvae_plan* plan);
 /* algorithmic FLOPs of one pass (2*MACs of every conv, all taps counted) */
 double kvae_plan_flops(const kvae_plan* plan, int B, long long T);
 
@@ -232,6 +241,14 @@ int kvae_conv1d_bwd(const void* x, const void* gy, const float* w_folded, void* 
  * caller of the decoder repeats (infer_0828_sigma.py:298, train_offline.py:302,319); bit-exact with torch's
  * separately rounded ops.  scratch: >= 4 bytes. */
 int kvae_pcm16(const void* wav, int dtype, int16_t* out, size_t n, void* scratch, void* stream);
+
+/* kvae_decode with phase 1 of that conversion (the global peak) fused into the tail conv's epilogue -- one atomicMax
+ * per warp and tile while the waveform is written -- followed by the conversion pass: wav [B, io, T*ratio] as
+ * kvae_decode, pcm = int16 of wav / max|wav| * 32767, bit-exact with kvae_decode + kvae_pcm16 (and so with torch)
+ * at one pass over the waveform less.  Tensor-core tail only (kvae_plan_fused_pcm_supported).  scratch: >= 4 bytes. */
+int kvae_decode_pcm16(kvae_plan* plan, const void* z, int z_dtype, void* wav, int wav_dtype, int16_t* pcm, int B,
+                      long long T, void* workspace, size_t workspace_bytes, void* scratch, void* stream);
+int kvae_plan_fused_pcm_supported(const kvae_plan* plan);
 
 /* ---- latent sampling ---- */
 /* sample(mean,'fix') of model_sigmaVAE.py:153-178 / 187-213: out = mean + std*noise, rounded exactly as

@@ -72,6 +72,12 @@ SIGNATURES = {
     "kvae_decode_stream_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.POINTER(C.c_longlong),
                                          C.c_void_p]),
     "kvae_decode_stream_destroy": (None, [C.c_void_p]),
+    "kvae_encode_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                     C.c_float, C.c_int, C.c_longlong, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kvae_plan_fused_sample_supported": (C.c_int, [C.c_void_p]),
+    "kvae_decode_pcm16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong,
+                                    C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "kvae_plan_fused_pcm_supported": (C.c_int, [C.c_void_p]),
     "kvae_plan_out_length": (C.c_longlong, [C.c_void_p, C.c_longlong]),
     "kvae_prep_mono_clips": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_float,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),

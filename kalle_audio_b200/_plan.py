@@ -165,6 +165,54 @@ class PlanRunner:
             launch(xin, out)
         return out if out.dtype == out_dtype else out.to(out_dtype)
 
+    def run_decode_pcm16(self, x: torch.Tensor, out_channels: int, ratio: int, out_dtype: torch.dtype):
+        """(wav, int16 pcm) with the peak search fused into the tail conv (kvae_decode_pcm16); None if unsupported."""
+        L = _lib.lib()
+        if self.direction != _lib.KVAE_DECODER or not L.kvae_plan_fused_pcm_supported(self.handle):
+            return None
+        _lib.require_cuda(x, "fused plan")
+        B, _, T = x.shape
+        if B == 0 or T == 0:
+            raise ValueError("empty input")
+        self.sync_weights()
+        xin = x if x.dtype in (torch.float32, torch.bfloat16) else x.float()
+        xin = xin.contiguous()
+        kdtype = out_dtype if out_dtype in (torch.float32, torch.bfloat16) else torch.float32
+        ws = self._get_workspace(B, T)
+        wav = torch.empty((B, out_channels, T * ratio), dtype=kdtype, device=self.device)
+        pcm = torch.empty((B, out_channels, T * ratio), dtype=torch.int16, device=self.device)
+        scratch = torch.empty(4, dtype=torch.uint8, device=self.device)
+        _lib.check(L.kvae_decode_pcm16(self.handle, xin.data_ptr(), _lib.dtype_code(xin.dtype), wav.data_ptr(),
+                                       _lib.dtype_code(kdtype), pcm.data_ptr(), B, T, ws.data_ptr(), ws.numel(),
+                                       scratch.data_ptr(), _lib.stream_ptr(self.device)))
+        return wav, pcm
+
+    def run_encode_sample(self, x: torch.Tensor, noise: torch.Tensor, out_channels: int, ratio: int,
+                          out_dtype: torch.dtype, D: int, std: float):
+        """(latents [B, out_channels, T], z [B, D, T]) with the sigma-VAE sample fused into the encoder's last conv
+        (kvae_encode_sample); None when this plan has no tensor-core output conv (the caller then samples separately)."""
+        L = _lib.lib()
+        if self.direction != _lib.KVAE_ENCODER or not L.kvae_plan_fused_sample_supported(self.handle):
+            return None
+        _lib.require_cuda(x, "fused plan")
+        B, _, T = x.shape
+        if T % ratio:
+            raise ValueError(f"audio length {T} is not a multiple of the downsampling ratio {ratio}")
+        self.sync_weights()
+        xin = x if x.dtype in (torch.float32, torch.bfloat16) else x.float()
+        xin = xin.contiguous()
+        kdtype = out_dtype if out_dtype in (torch.float32, torch.bfloat16) else torch.float32
+        ws = self._get_workspace(B, T)
+        lat = torch.empty((B, out_channels, T // ratio), dtype=kdtype, device=self.device)
+        z = torch.empty((B, D, T // ratio), dtype=kdtype, device=self.device)
+        nz = noise.to(kdtype).contiguous()
+        if nz.shape != z.shape:
+            raise ValueError(f"noise must be {tuple(z.shape)}")
+        _lib.check(L.kvae_encode_sample(self.handle, xin.data_ptr(), _lib.dtype_code(xin.dtype), lat.data_ptr(), z.data_ptr(),
+                                        nz.data_ptr(), _lib.dtype_code(kdtype), D, float(std), B, T, ws.data_ptr(),
+                                        ws.numel(), _lib.stream_ptr(self.device)))
+        return lat, z
+
     # ------------------------------------------------------------------ training pass
     def param_list(self) -> List[torch.nn.Parameter]:
         """Parameters in the flat-buffer order of the plan (= module.parameters() order); checked against

@@ -302,6 +302,29 @@ class AudioAutoencoder(nn.Module):
             return latents, info
         return latents
 
+    @torch.no_grad()
+    def encode_and_sample(self, audio, noise=None, dist_type="fix"):
+        """encode -> chunk(2, dim=1) -> sample(mean, 'fix') in ONE plan call: the sampler (model_sigmaVAE.py:187-213,
+        applied to the mean half of the encoder output as twj_dataset.py:251 splits it) runs in the epilogue of the
+        encoder's last conv.  Returns (mean_scale [B, 2D, T], z [B, D, T]); z is bit-identical to
+        ``sample(mean_scale.chunk(2, 1)[0], 'fix', noise)``.  ``noise`` defaults to ``torch.randn_like(mean)``."""
+        from .sampling import _STD, sample
+        if self.pretransform is not None or self.bottleneck is None or dist_type != "fix":
+            ms = self.encode(audio)
+            mean = ms.chunk(2, dim=1)[0].contiguous()
+            return ms, sample(mean, dist_type, noise=noise)
+        enc = self.encoder
+        D = enc._out_channels_for_plan // 2
+        if noise is None:
+            noise = torch.randn((audio.shape[0], D, audio.shape[2] // self.downsampling_ratio), device=audio.device,
+                                dtype=enc._out_dtype(audio))
+        got = enc.runner(audio.device).run_encode_sample(audio, noise, enc._out_channels_for_plan, enc._ratio,
+                                                         enc._out_dtype(audio), D, _STD)
+        if got is None:       # no tensor-core output conv in this architecture: two launches
+            ms = self.encode(audio)
+            return ms, sample(ms.chunk(2, dim=1)[0].contiguous(), "fix", noise=noise)
+        return got
+
     def decode(self, latents, iterate_batch=False, **kwargs):
         if self.bottleneck is not None:
             latents = self.bottleneck.decode(latents)
@@ -311,6 +334,22 @@ class AudioAutoencoder(nn.Module):
         if self.soft_clip:
             decoded = torch.tanh(decoded)
         return decoded
+
+    @torch.no_grad()
+    def decode_pcm16(self, latents):
+        """decode + the peak-normalised int16 conversion every caller of the reference repeats
+        (``output.to(float32).div(max|output|).clamp(-1, 1).mul(32767).to(int16)``, infer_0828_sigma.py:298): the peak is
+        found in the tail conv's epilogue while the waveform is written.  Returns (waveform, int16 pcm)."""
+        from .utils import to_pcm16
+        dec = self.decoder
+        plain = self.bottleneck is None or type(self.bottleneck).__name__ == "VAEBottleneck"
+        if plain and self.pretransform is None and not self.soft_clip and isinstance(dec, _OobleckBase):
+            got = dec.runner(latents.device).run_decode_pcm16(latents, dec._out_channels_for_plan, dec._ratio,
+                                                              dec._out_dtype(latents))
+            if got is not None:
+                return got
+        wav = self.decode(latents)
+        return wav, to_pcm16(wav)
 
     def decode_tokens(self, tokens, **kwargs):
         raise NotImplementedError("discrete bottlenecks are outside the sigmaVAE hot path")

@@ -209,6 +209,8 @@ struct WaveOutTcParams {
   int T, B, COUT, tanh_out;
   int tiles_per_clip, total_tiles;
   int in_row0;              // output t reads input rows t + in_row0 .. +6 of tmX (-3 for a whole clip)
+  unsigned int* peak_bits;  // nullptr, or: atomicMax of the bit pattern of |y| over everything written (phase 1 of the
+                            // peak-normalised int16 conversion, infer_0828_sigma.py:298) -- one atomic per warp and tile
 };
 
 // kF16 = true: the residual stream is fp16 in HBM (inference plans).  The tile is then two 64-channel chunks of
@@ -400,6 +402,7 @@ conv_wave_out_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&acc_empty[a]);
       ptx::named_bar_sync(1, 128);                       // all 128 rows of P are in shared memory
+      float peak = 0.f;
       if (i < kWoTcTile && t < p.T) {
         for (int co = 0; co < p.COUT; ++co) {
           float v = 0.f;
@@ -407,7 +410,14 @@ conv_wave_out_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
           for (int k = 0; k < 7; ++k) v += pb[(i + k) * kWoTcPStride + k * p.COUT + co];
           if (p.tanh_out) v = tanhf(v);
           st_elem(p.y, (static_cast<size_t>(b) * p.COUT + co) * p.T + t, p.y_f32, v);
+          // the peak of what a reader of y sees: the value rounded to the output dtype
+          peak = fmaxf(peak, fabsf(p.y_f32 ? v : __bfloat162float(__float2bfloat16(v))));
         }
+      }
+      if (p.peak_bits) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) peak = fmaxf(peak, __shfl_xor_sync(0xffffffffu, peak, o));
+        if (lane == 0 && peak > 0.f) atomicMax(p.peak_bits, __float_as_uint(peak));
       }
       if (++a == 2) { a = 0; aph ^= 1u; }
     }

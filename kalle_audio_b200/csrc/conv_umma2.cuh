@@ -63,7 +63,30 @@ struct ConvParams2 {
   int precise;             // 1: SnakeBeta with sinf (fp32 mode), 0: MUFU sin
   const float* snake_a;    // SnakeBeta folded into the activated output (nullptr: plain cast)
   const float* snake_inv_b;
+  // raw_mode 2 only: the sigma-VAE sample fused into the encoder's last conv (model_sigmaVAE.py:187-213 'fix' on the
+  // mean half of the latents, twj-style chunk(2, dim=1)): for channels c < samp_D,
+  //   samp_out[b, c, t] = mean + samp_std * samp_noise[b, c, t], two separately rounded operations on the value AS STORED
+  // (rounded to the output dtype first), i.e. bit-identical to torch on the stored latents.  Same dtype as out_cf.
+  const void* samp_noise;  // [B, samp_D, T_out] or nullptr
+  void* samp_out;          // [B, samp_D, T_out]
+  int samp_D;
+  float samp_std;
 };
+
+__device__ __forceinline__ void fused_sigma_sample(const ConvParams2& p, int b, int c, size_t t_out, int T_out, float v) {
+  if (p.samp_noise && c < p.samp_D) {
+    const size_t o = (static_cast<size_t>(b) * p.samp_D + c) * T_out + t_out;
+    if (p.out_cf_f32) {
+      const float n = static_cast<const float*>(p.samp_noise)[o];
+      static_cast<float*>(p.samp_out)[o] = __fadd_rn(v, __fmul_rn(p.samp_std, n));
+    } else {
+      const float m = __bfloat162float(__float2bfloat16(v));
+      const float n = __bfloat162float(static_cast<const __nv_bfloat16*>(p.samp_noise)[o]);
+      const float t = __bfloat162float(__float2bfloat16(__fmul_rn(p.samp_std, n)));
+      static_cast<__nv_bfloat16*>(p.samp_out)[o] = __float2bfloat16(__fadd_rn(m, t));
+    }
+  }
+}
 
 constexpr int kRawBlkBytes = 32 * 128;   // 32 rows x 32 fp32, SWIZZLE_128B
 constexpr int kActBlkBytes = 32 * 64;    // 32 rows x 32 bf16 (or fp16 stream), SWIZZLE_64B
@@ -468,6 +491,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const size_t o = (static_cast<size_t>(b) * p.Cout + c) * T_out + static_cast<size_t>(q) * p.P_out + phi;
                 if (p.out_cf_f32) static_cast<float*>(p.out_cf)[o] = v[j];
                 else static_cast<__nv_bfloat16*>(p.out_cf)[o] = __float2bfloat16(v[j]);
+                fused_sigma_sample(p, b, c, static_cast<size_t>(q) * p.P_out + phi, T_out, v[j]);
               }
             }
           }
@@ -552,6 +576,10 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               __nv_bfloat16* op = static_cast<__nv_bfloat16*>(p.out_cf) + o0;
 #pragma unroll
               for (int j = 0; j < 32; ++j) op[static_cast<size_t>(j) * T_out] = __float2bfloat16(v[j]);
+            }
+            if (p.samp_noise) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) fused_sigma_sample(p, b, cbase + j, t_out, T_out, v[j]);
             }
           }
         }

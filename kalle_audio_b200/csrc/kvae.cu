@@ -809,8 +809,10 @@ cudaError_t zero_step_tails(const kvae_plan* p, const std::vector<Step>& steps, 
   return cudaSuccess;
 }
 
+struct FusedSample { const void* noise = nullptr; void* out = nullptr; int D = 0; float std = 0.f; unsigned int* peak = nullptr; };
+
 int run_plan(kvae_plan* p, bool train, const void* in, int in_dtype, void* out, int out_dtype, int B, long long T,
-             void* ws, size_t ws_bytes, cudaStream_t st, const int* valid = nullptr) {
+             void* ws, size_t ws_bytes, cudaStream_t st, const int* valid = nullptr, const FusedSample* fs = nullptr) {
   if (!p) return fail("null plan");
   if (B <= 0 || T <= 0) return fail("empty batch or zero length input");
   if (T > (1ll << 30)) return fail("input too long");
@@ -867,6 +869,7 @@ int run_plan(kvae_plan* p, bool train, const void* in, int in_dtype, void* out, 
       PreparedRun::WaveOutTc& t = R.wave_out_tc[k];
       t.p.y = out;
       t.p.y_f32 = (out_dtype == KVAE_F32);
+      t.p.peak_bits = fs ? fs->peak : nullptr;
       static bool attr_set[64] = {false};
       int dev = 0;
       cudaGetDevice(&dev);
@@ -894,6 +897,10 @@ int run_plan(kvae_plan* p, bool train, const void* in, int in_dtype, void* out, 
       if (k == n - 1) {
         L.p.out_cf = out;
         L.p.out_cf_f32 = (out_dtype == KVAE_F32);
+        L.p.samp_noise = (fs && fs->out) ? fs->noise : nullptr;
+        L.p.samp_out = fs ? fs->out : nullptr;
+        L.p.samp_D = fs ? fs->D : 0;
+        L.p.samp_std = fs ? fs->std : 0.f;
       }
       KV_CUDA(launch_conv_umma2(L, st));
     } else if (R.kind[k] == 0) {
@@ -1524,6 +1531,26 @@ int kvae_prep_mono_clips(const float* wav, const long long* offsets, const int* 
   return 0;
 }
 
+int kvae_encode_sample(kvae_plan* p, const void* wav, int wav_dtype, void* lat, void* z, const void* noise, int lat_dtype,
+                       int D, float std, int B, long long L, void* ws, size_t ws_bytes, void* stream) {
+  if (!p) return fail("null plan");
+  if (p->direction != KVAE_ENCODER) return fail("plan is not an encoder");
+  if (!wav || !lat || !z || !noise) return fail("null tensor");
+  if (!check_dtype(wav_dtype) || !check_dtype(lat_dtype)) return fail("bad dtype");
+  if (D <= 0 || D > p->arch.latent_dim) return fail("D must be in 1 .. latent_dim");
+  const ConvLayer& cl = p->convs[p->steps.back().conv];
+  if (!conv_tc(cl, false) || env_flag("KVAE_CONV_V1"))
+    return fail("fused sampling needs a tensor-core output conv (use kvae_encode + kvae_sigma_sample)");
+  FusedSample fs;
+  fs.noise = noise; fs.out = z; fs.D = D; fs.std = std;
+  return run_plan(p, false, wav, wav_dtype, lat, lat_dtype, B, L, ws, ws_bytes, static_cast<cudaStream_t>(stream), nullptr, &fs);
+}
+
+int kvae_plan_fused_sample_supported(const kvae_plan* p) {
+  if (!p) return 0;
+  return p->direction == KVAE_ENCODER && conv_tc(p->convs[p->steps.back().conv], false) && !env_flag("KVAE_CONV_V1") ? 1 : 0;
+}
+
 double kvae_plan_flops(const kvae_plan* p, int B, long long T) {
   if (!p) return 0.0;
   double f = 0.0;
@@ -1980,6 +2007,37 @@ int kvae_adamw_step(float* params, const float* grads, float* exp_avg, float* ex
 }
 
 // ------------------------------------------------------------------ PCM tail
+int kvae_decode_pcm16(kvae_plan* p, const void* z, int z_dtype, void* wav, int wav_dtype, int16_t* pcm, int B, long long T,
+                      void* ws, size_t ws_bytes, void* scratch, void* stream) {
+  if (!p) return fail("null plan");
+  if (p->direction != KVAE_DECODER) return fail("plan is not a decoder");
+  if (!z || !wav || !pcm || !scratch) return fail("null tensor");
+  if (!check_dtype(z_dtype) || !check_dtype(wav_dtype)) return fail("bad dtype");
+  if (B <= 0 || T <= 0) return fail("empty batch or zero length input");
+  if (!(p->precision == KVAE_PREC_BF16 && p->stream_f16 && is_wave_out_step(p, p->steps, static_cast<int>(p->steps.size()) - 1)))
+    return fail("fused PCM tail needs the tensor-core tail conv (use kvae_decode + kvae_pcm16)");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DeviceGuard guard(p->device);
+  if (!guard.ok) return fail("cannot select device");
+  KV_CUDA(cudaMemsetAsync(scratch, 0, 4, st));
+  FusedSample fs;
+  fs.peak = static_cast<unsigned int*>(scratch);
+  const int rc = run_plan(p, false, z, z_dtype, wav, wav_dtype, B, T, ws, ws_bytes, st, nullptr, &fs);
+  if (rc) return rc;
+  const size_t n = static_cast<size_t>(B) * p->arch.io_channels * static_cast<size_t>(T) * p->ratio;
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
+  pcm16_kernel<<<blocks, 256, 0, st>>>(wav, n, wav_dtype == KVAE_F32, static_cast<const unsigned int*>(scratch), pcm);
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int kvae_plan_fused_pcm_supported(const kvae_plan* p) {
+  if (!p || p->direction != KVAE_DECODER) return 0;
+  return (p->precision == KVAE_PREC_BF16 && p->stream_f16 && !env_flag("KVAE_WAVE_OUT_CC") &&
+          is_wave_out_step(p, p->steps, static_cast<int>(p->steps.size()) - 1)) ? 1 : 0;
+}
+
 int kvae_pcm16(const void* wav, int dtype, int16_t* out, size_t n, void* scratch, void* stream) {
   if (!wav || !out || !scratch) return fail("null argument");
   if (!check_dtype(dtype)) return fail("bad dtype");
