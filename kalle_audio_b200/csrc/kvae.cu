@@ -949,6 +949,23 @@ void set_sb_grid(SnakeBwdParams& sb, dim3& grid) {
 }
 
 cudaError_t launch_snake_bwd(const SnakeBwdParams& sb, dim3 grid, cudaStream_t st) {
+  SnakeBwdStreamGeom gm;
+  static const bool no_stream = env_flag("KVAE_SNAKE_BWD_PLAIN");     // A/B switch: the latency-bound predecessor
+  if (!no_stream && snake_bwd_stream_geom(sb, gm)) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+      cudaError_t e = cudaFuncSetAttribute(snake_bwd_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(snake_bwd_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      if (e != cudaSuccess) return e;
+      attr_set[dev & 63] = true;
+    }
+    long long ctas = std::min<long long>(gm.row_tiles, std::max(1, sm_count() / gm.ncol)) * gm.ncol;
+    if (sb.fast) snake_bwd_stream_kernel<true><<<static_cast<unsigned>(ctas), kSbsThreads, snake_bwd_stream_smem(), st>>>(sb, gm);
+    else snake_bwd_stream_kernel<false><<<static_cast<unsigned>(ctas), kSbsThreads, snake_bwd_stream_smem(), st>>>(sb, gm);
+    return cudaGetLastError();
+  }
   if (sb.C % 4 == 0) {
     if (sb.fast) snake_bwd_vec4_kernel<true><<<grid, 256, 0, st>>>(sb);
     else snake_bwd_vec4_kernel<false><<<grid, 256, 0, st>>>(sb);
@@ -1092,12 +1109,19 @@ bool prepare_backward(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R
     // ---- data gradient (k == 0: only when the caller asks for the input gradient; patched per call)
     const ConvGeom gd = dgrad_geom(c.g, static_cast<int>(T_in));
     if (gd.out_len(static_cast<int>(T_out)) != T_in) { err = "internal: dgrad length bookkeeping"; return false; }
+    // bf16 mode: dA crosses HBM as bf16 (written by the data-gradient conv's fragment-mapped epilogue, read by the
+    // vectorised SnakeBeta backward); KVAE_BWD_DA_F32=1 keeps the fp32 hand-over (A/B, debugging)
+    const bool da_bf16 = c.umma && k >= 1 && p->precision == KVAE_PREC_BF16 && c.g.Cin % 4 == 0 && !env_flag("KVAE_BWD_DA_F32");
     if (c.umma) {
       bw.dgrad_kind = 1;
       ConvEpilogue ep;
-      ep.out_raw = (k == 0) ? reinterpret_cast<void*>(0x1) : static_cast<void*>(dA);
-      ep.out_raw_f32 = 1;
-      ep.out_raw_cf = (k == 0) ? 1 : 0;
+      if (da_bf16) {
+        ep.out_act = reinterpret_cast<__nv_bfloat16*>(dA);
+      } else {
+        ep.out_raw = (k == 0) ? reinterpret_cast<void*>(0x1) : static_cast<void*>(dA);
+        ep.out_raw_f32 = 1;
+        ep.out_raw_cf = (k == 0) ? 1 : 0;
+      }
       ConvTuning2 tune;
       if (!prepare_conv_umma2(gd, Gb(k), B, static_cast<int>(T_out), c.w_umma_d, ep, tune, bw.dg_umma, err)) return false;
     } else if (k > 0 && edge_wgrad_ok(c.g) && c.g.Cout <= 2) {
@@ -1146,6 +1170,7 @@ bool prepare_backward(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R
       std::memset(&sb, 0, sizeof(sb));
       bw.has_sb = true;
       sb.dA = dA;
+      sb.dA_bf16 = da_bf16 ? 1 : 0;
       if (s.pre_snake >= 0) {
         const SnakeLayer& sn = p->snakes[s.pre_snake];
         sb.x = static_cast<const float*>(tptr(1 + 2 * (k - 1)));
@@ -1156,10 +1181,21 @@ bool prepare_backward(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R
         if (steps[j].residual_from == k - 1) {
           if (j != k + 1) { err = "internal: skip connection spans more than one ResidualUnit"; return false; }
           sb.skip = Gf(j);
+          // bf16 mode: read the bf16 copy of that gradient (it exists whenever step j runs on the tensor cores)
+          if (p->convs[steps[j].conv].umma && p->precision == KVAE_PREC_BF16 && c.g.Cin % 4 == 0 && !env_flag("KVAE_BWD_DA_F32")) {
+            sb.skip = reinterpret_cast<const float*>(Gb(j));
+            sb.skip_bf16 = 1;
+          }
         }
       // fp32 copy of G_{k-1}: only where something reads it -- the skip-connection add two steps later (k-1 is the
       // k1 conv of a ResidualUnit), the CUDA-core kernels, or the input-gradient of step 0
-      const bool tc_only = cp.umma && cp.off_dwp >= 0 && steps[k - 1].residual_from < 0;
+      // (the skip-connection reader takes the bf16 copy in bf16 mode, see above)
+      bool skip_reader_bf16 = false;
+      if (steps[k - 1].residual_from >= 0 && p->precision == KVAE_PREC_BF16 && !env_flag("KVAE_BWD_DA_F32")) {
+        const int rf = steps[k - 1].residual_from;          // G_{k-1} is added into G_{rf} by the pass at step rf + 1
+        skip_reader_bf16 = cp.umma && rf + 1 < n && p->convs[steps[rf + 1].conv].g.Cin % 4 == 0;
+      }
+      const bool tc_only = cp.umma && cp.off_dwp >= 0 && (steps[k - 1].residual_from < 0 || skip_reader_bf16);
       sb.G = tc_only ? nullptr : Gf(k - 1);
       sb.Gb = cp.umma ? Gb(k - 1) : nullptr;
       sb.rows = static_cast<long long>(B) * T_in;

@@ -9,6 +9,7 @@
 // All activations are channels-last [B, T, C]; gradients of the stream are fp32, with a bf16 copy as the
 // tensor-core operand of the data-/weight-gradient GEMMs.
 #pragma once
+#include "ptx.cuh"
 #include <cuda_bf16.h>
 #include <cstdint>
 
@@ -80,6 +81,11 @@ struct SnakeBwdParams {
   int CW;                 // channels per block column (power of two <= 256)
   int rows_per_block;
   int fast;               // 1: MUFU sin/cos (bf16 mode); 0: sincosf (fp32 mode, <= 1e-5 budget)
+  // bf16 mode, vectorised kernels only: the data-gradient conv hands dA over as bf16 (its fragment-mapped epilogue,
+  // half the bytes), and the skip-connection gradient is read from the bf16 copy Gb of the later step -- the fp32
+  // copy of that gradient then has no reader and is not written at all.
+  int dA_bf16;            // dA points to bf16
+  int skip_bf16;          // skip points to bf16
 };
 
 __global__ void __launch_bounds__(256) snake_bwd_kernel(const SnakeBwdParams p) {
@@ -167,10 +173,16 @@ __global__ void __launch_bounds__(256) snake_bwd_vec4_kernel(const SnakeBwdParam
     const float4* SK = reinterpret_cast<const float4*>(p.skip);
     float4* G = reinterpret_cast<float4*>(p.G);
     uint2* Gb = reinterpret_cast<uint2*>(p.Gb);
+    auto ld_bf16x4 = [](const void* base, size_t i) {
+      const uint2 q = __ldcs(reinterpret_cast<const uint2*>(base) + i);
+      const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x));
+      const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
+      return make_float4(lo.x, lo.y, hi.x, hi.y);
+    };
 #pragma unroll 2
     for (long long r = r0 + rl; r < r1; r += nrl) {
       const size_t i = static_cast<size_t>(r) * C4 + c4;
-      float4 g = __ldcs(dA + i);
+      float4 g = p.dA_bf16 ? ld_bf16x4(p.dA, i) : __ldcs(dA + i);
       if (p.a) {
         const float4 xv = __ldcs(X + i);
         snake_bwd_elem<kFast>(g.x, xv.x, a.x, ib.x, s1.x, s2.x);
@@ -179,7 +191,7 @@ __global__ void __launch_bounds__(256) snake_bwd_vec4_kernel(const SnakeBwdParam
         snake_bwd_elem<kFast>(g.w, xv.w, a.w, ib.w, s1.w, s2.w);
       }
       if (SK) {
-        const float4 k4 = __ldcs(SK + i);
+        const float4 k4 = p.skip_bf16 ? ld_bf16x4(p.skip, i) : __ldcs(SK + i);
         g.x += k4.x; g.y += k4.y; g.z += k4.z; g.w += k4.w;
       }
       sb.x += g.x; sb.y += g.y; sb.z += g.z; sb.w += g.w;
@@ -218,6 +230,183 @@ __global__ void __launch_bounds__(256) snake_bwd_vec4_kernel(const SnakeBwdParam
       atomicAdd(p.d_bias + c + 2, tb.z); atomicAdd(p.d_bias + c + 3, tb.w);
     }
   }
+}
+
+// ---------------------------------------------------------------- SnakeBeta backward, HBM-streaming form
+// Same arithmetic and outputs as snake_bwd_vec4_kernel.  That kernel keeps one or two rows per thread in flight and is
+// bound by memory LATENCY, not bytes (ncu, profiles/r02_snake_bwd_vec4_before.txt: 23 % of DRAM peak, 22 stalled warps
+// per issue on long_scoreboard), so halving its bytes (bf16 dA / skip) did not shorten it.  Here a producer thread
+// streams [R rows x CW4 float4-columns] tiles of the 2-3 input tensors into a 4-stage shared-memory ring with bulk
+// async copies (mbarrier full / empty) -- ~100 KB per SM in flight whatever the compute warps are doing -- and 16
+// compute warps read the tiles from shared memory and write G / Gb straight to global memory (a warp's 32 threads
+// write one contiguous row segment).  Persistent CTAs; per-channel sums stay in registers across all tiles of a CTA.
+constexpr int kSbsStages = 4;
+constexpr int kSbsCompute = 512;                   // compute threads (warp 16 = producer)
+constexpr int kSbsThreads = kSbsCompute + 32;
+constexpr int kSbsTileVec = 1024;                  // float4 vectors per tile and tensor (16 KB fp32 / 8 KB bf16)
+
+struct SnakeBwdStreamGeom {
+  int CW4;              // float4 columns per tile (power of two, <= 512, divides 512)
+  int ncol;             // column blocks (C4 / CW4)
+  int R;                // rows per tile (kSbsTileVec / CW4)
+  long long row_tiles;  // ceil(rows / R)
+};
+
+inline size_t snake_bwd_stream_smem() { return 1024 + static_cast<size_t>(kSbsStages) * 3 * kSbsTileVec * 16 + 3 * kSbsCompute * 16; }
+
+template <bool kFast>
+__global__ void __launch_bounds__(kSbsThreads, 1) snake_bwd_stream_kernel(const SnakeBwdParams p, const SnakeBwdStreamGeom gm) {
+  extern __shared__ uint8_t sbs_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(sbs_raw);
+  uint8_t* smem = sbs_raw + (((raw_addr + 127u) & ~127u) - raw_addr);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + kSbsStages;
+  uint8_t* ring = smem + 128;
+  float4* red = reinterpret_cast<float4*>(ring + static_cast<size_t>(kSbsStages) * 3 * kSbsTileVec * 16);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C4 = p.C >> 2;
+  const long long total = gm.row_tiles * gm.ncol;
+  const int cb = blockIdx.x % gm.ncol;                   // this CTA's column block (fixed: grid is a multiple of ncol)
+  const long long t_first = blockIdx.x / gm.ncol, t_step = gridDim.x / gm.ncol;
+  const bool has_a = p.a != nullptr, has_sk = p.skip != nullptr;
+  const int esz_dA = p.dA_bf16 ? 8 : 16, esz_sk = p.skip_bf16 ? 8 : 16;   // bytes per 4 channels
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kSbsStages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], kSbsCompute / 32); }
+    ptx::fence_mbar_init();
+  }
+  __syncthreads();
+  (void)total;
+  if (warp == kSbsCompute / 32) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (long long rt = t_first; rt < gm.row_tiles; rt += t_step) {
+        const long long r0 = rt * gm.R;
+        const int nr = static_cast<int>(min(static_cast<long long>(gm.R), p.rows - r0));
+        ptx::mbar_wait(&empty[s], ph ^ 1u);
+        uint8_t* st = ring + static_cast<size_t>(s) * 3 * kSbsTileVec * 16;
+        const uint32_t bytes = static_cast<uint32_t>(nr) * gm.CW4 * (esz_dA + (has_a ? 16 : 0) + (has_sk ? esz_sk : 0));
+        ptx::mbar_expect_tx(&full[s], bytes);
+        const size_t e0 = static_cast<size_t>(r0) * C4 + static_cast<size_t>(cb) * gm.CW4;     // first float4 index
+        if (gm.ncol == 1) {                                // whole rows: one contiguous range per tensor
+          const uint32_t nv = static_cast<uint32_t>(nr) * gm.CW4;
+          ptx::bulk_load_1d(st, reinterpret_cast<const uint8_t*>(p.dA) + e0 * esz_dA, nv * esz_dA, &full[s]);
+          if (has_a) ptx::bulk_load_1d(st + kSbsTileVec * 16, reinterpret_cast<const uint8_t*>(p.x) + e0 * 16, nv * 16, &full[s]);
+          if (has_sk) ptx::bulk_load_1d(st + 2 * kSbsTileVec * 16, reinterpret_cast<const uint8_t*>(p.skip) + e0 * esz_sk, nv * esz_sk, &full[s]);
+        } else {
+          for (int r = 0; r < nr; ++r) {
+            const size_t e = e0 + static_cast<size_t>(r) * C4;
+            ptx::bulk_load_1d(st + static_cast<size_t>(r) * gm.CW4 * esz_dA, reinterpret_cast<const uint8_t*>(p.dA) + e * esz_dA,
+                              gm.CW4 * esz_dA, &full[s]);
+            if (has_a) ptx::bulk_load_1d(st + kSbsTileVec * 16 + static_cast<size_t>(r) * gm.CW4 * 16,
+                                         reinterpret_cast<const uint8_t*>(p.x) + e * 16, gm.CW4 * 16, &full[s]);
+            if (has_sk) ptx::bulk_load_1d(st + 2 * kSbsTileVec * 16 + static_cast<size_t>(r) * gm.CW4 * esz_sk,
+                                          reinterpret_cast<const uint8_t*>(p.skip) + e * esz_sk, gm.CW4 * esz_sk, &full[s]);
+          }
+        }
+        if (++s == kSbsStages) { s = 0; ph ^= 1u; }
+      }
+    }
+    return;
+  }
+  // ------------------------------------------------------------ compute warps
+  const int c4l = threadIdx.x % gm.CW4;                 // column inside the tile (CW4 <= 512 divides 512)
+  const int rl = threadIdx.x / gm.CW4, nrl = kSbsCompute / gm.CW4;
+  const int c4 = cb * gm.CW4 + c4l;
+  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1, sb = s1, a = s1, ib = s1;
+  if (has_a) {
+    a = __ldg(reinterpret_cast<const float4*>(p.a) + c4);
+    ib = __ldg(reinterpret_cast<const float4*>(p.inv_b) + c4);
+  }
+  float4* G = reinterpret_cast<float4*>(p.G);
+  uint2* Gb = reinterpret_cast<uint2*>(p.Gb);
+  auto bf4 = [](uint2 q) {
+    const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.x));
+    const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&q.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+  };
+  int s = 0;
+  uint32_t ph = 0;
+  for (long long rt = t_first; rt < gm.row_tiles; rt += t_step) {
+    const long long r0 = rt * gm.R;
+    const int nr = static_cast<int>(min(static_cast<long long>(gm.R), p.rows - r0));
+    ptx::mbar_wait(&full[s], ph);
+    const uint8_t* st = ring + static_cast<size_t>(s) * 3 * kSbsTileVec * 16;
+#pragma unroll 2
+    for (int r = rl; r < nr; r += nrl) {
+      const int v = r * gm.CW4 + c4l;
+      float4 g = p.dA_bf16 ? bf4(reinterpret_cast<const uint2*>(st)[v]) : reinterpret_cast<const float4*>(st)[v];
+      if (has_a) {
+        const float4 xv = reinterpret_cast<const float4*>(st + kSbsTileVec * 16)[v];
+        snake_bwd_elem<kFast>(g.x, xv.x, a.x, ib.x, s1.x, s2.x);
+        snake_bwd_elem<kFast>(g.y, xv.y, a.y, ib.y, s1.y, s2.y);
+        snake_bwd_elem<kFast>(g.z, xv.z, a.z, ib.z, s1.z, s2.z);
+        snake_bwd_elem<kFast>(g.w, xv.w, a.w, ib.w, s1.w, s2.w);
+      }
+      if (has_sk) {
+        const float4 k4 = p.skip_bf16 ? bf4(reinterpret_cast<const uint2*>(st + 2 * kSbsTileVec * 16)[v])
+                                      : reinterpret_cast<const float4*>(st + 2 * kSbsTileVec * 16)[v];
+        g.x += k4.x; g.y += k4.y; g.z += k4.z; g.w += k4.w;
+      }
+      sb.x += g.x; sb.y += g.y; sb.z += g.z; sb.w += g.w;
+      const size_t i = static_cast<size_t>(r0 + r) * C4 + c4;
+      if (G) __stcs(G + i, g);
+      if (Gb) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(g.x, g.y), h1 = __floats2bfloat162_rn(g.z, g.w);
+        __stcs(Gb + i, make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1)));
+      }
+    }
+    __syncwarp();
+    if (lane == 0) ptx::mbar_arrive(&empty[s]);
+    if (++s == kSbsStages) { s = 0; ph ^= 1u; }
+  }
+  // per-channel sums: reduce over the row lanes of this CTA, then one atomic per channel and CTA
+  red[threadIdx.x] = s1;
+  red[kSbsCompute + threadIdx.x] = s2;
+  red[2 * kSbsCompute + threadIdx.x] = sb;
+  ptx::named_bar_sync(1, kSbsCompute);
+  if (threadIdx.x < gm.CW4) {
+    float4 t1 = make_float4(0.f, 0.f, 0.f, 0.f), t2 = t1, tb = t1;
+    for (int j = 0; j < nrl; ++j) {
+      const float4 u1 = red[threadIdx.x + j * gm.CW4], u2 = red[kSbsCompute + threadIdx.x + j * gm.CW4],
+                   ub = red[2 * kSbsCompute + threadIdx.x + j * gm.CW4];
+      t1.x += u1.x; t1.y += u1.y; t1.z += u1.z; t1.w += u1.w;
+      t2.x += u2.x; t2.y += u2.y; t2.z += u2.z; t2.w += u2.w;
+      tb.x += ub.x; tb.y += ub.y; tb.z += ub.z; tb.w += ub.w;
+    }
+    const int c = c4 * 4;
+    if (has_a && p.d_alpha) {
+      const float av[4] = {a.x, a.y, a.z, a.w}, iv[4] = {ib.x, ib.y, ib.z, ib.w};
+      const float v1[4] = {t1.x, t1.y, t1.z, t1.w}, v2[4] = {t2.x, t2.y, t2.z, t2.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float eb = 1.f / iv[e] - 1e-9f;
+        atomicAdd(p.d_alpha + c + e, v1[e] * iv[e] * (p.logscale ? av[e] : 1.f));
+        atomicAdd(p.d_beta + c + e, -v2[e] * iv[e] * iv[e] * (p.logscale ? eb : 1.f));
+      }
+    }
+    if (p.d_bias) {
+      atomicAdd(p.d_bias + c, tb.x); atomicAdd(p.d_bias + c + 1, tb.y);
+      atomicAdd(p.d_bias + c + 2, tb.z); atomicAdd(p.d_bias + c + 3, tb.w);
+    }
+  }
+}
+
+// geometry of the streaming form, or false when the shape needs the plain kernels (C4 not a power of two / multiple of 512)
+inline bool snake_bwd_stream_geom(const SnakeBwdParams& p, SnakeBwdStreamGeom& g) {
+  if (p.C % 8) return false;
+  const int C4 = p.C / 4;
+  int cw = C4;
+  if (C4 > 512) { if (C4 % 512) return false; cw = 512; }
+  if (cw & (cw - 1)) return false;
+  if (cw < 8) return false;
+  if (p.rows < 4096) return false;                       // tiny tensors: the plain kernel's many small blocks do better
+  g.CW4 = cw;
+  g.ncol = C4 / cw;
+  g.R = kSbsTileVec / cw;
+  g.row_tiles = (p.rows + g.R - 1) / g.R;
+  // 16-byte alignment of every bulk copy: bf16 rows of CW4 * 8 bytes, pointers from the workspace (1 KB aligned)
+  return true;
 }
 
 // ---------------------------------------------------------------- weight gradient of the waveform-edge convs
