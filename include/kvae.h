@@ -236,6 +236,20 @@ int kvae_conv1d_bwd(const void* x, const void* gy, const float* w_folded, void* 
                     int transposed, int B, int Cin, int Cout, long long T, int K, int stride, int dilation, int padding,
                     int dtype, void* scratch, size_t scratch_bytes, void* stream);
 
+/* ---- BigVGANFlowVAE inference path (backup/flows.py:396-529: the reference's 12.5 Hz VAE) -- leaf kernels ----
+ * Activation1d of the AMP blocks (alias_free_torch, un-vendored; flows.py:266, 312, 443): x2 Kaiser-sinc upsampling
+ * (replicate padding) -> Snake (beta == NULL: x + sin^2(a x)/a) or SnakeBeta (x + sin^2(a x)/b) -> low-pass and x2
+ * decimation, in ONE pass over [B, C, T].  filt_up / filt_down: the module's 12-tap `upsample.filter` /
+ * `downsample.lowpass.filter` buffers (device fp32). */
+int kvae_aa_act_fwd(const void* x, void* y, const float* alpha, const float* beta, int logscale, const float* filt_up,
+                    const float* filt_down, int B, int C, long long T, int dtype, void* stream);
+/* op 0: nn.LeakyReLU(param) (flows.py:181-217), op 1: tanh (:527) */
+int kvae_unary_fwd(const void* x, void* y, size_t n, int op, float param, int dtype, void* stream);
+/* out = alpha*a + beta*b: the residual adds of the AMP blocks (:283) and their average (:519-520) */
+int kvae_axpby(const void* a, const void* b, void* out, size_t n, float alpha, float beta, int dtype, void* stream);
+/* z = mean + noise * exp(logs) (:500-501) */
+int kvae_gauss_sample(const void* mean, const void* logs, const void* noise, void* out, size_t n, int dtype, void* stream);
+
 /* ---- post-decode tail ---- */
 /* audio.to(float32).div(max|audio|).clamp(-1,1).mul(32767).to(int16) -- the peak-normalised PCM conversion every
  * caller of the decoder repeats (infer_0828_sigma.py:298, train_offline.py:302,319); bit-exact with torch's

@@ -21,6 +21,7 @@ from .streaming import StreamingDecoder, decoder_context_frames
 from .hostio import HostPipeline
 from .glue import LatentGlue
 from .dataset import LatentExtractor
+from .bigvgan import BigVGANFlowVAE
 from .utils import load_ckpt_state_dict, prepare_audio, remove_weight_norm_from_model, to_pcm16
 from .training import AutoencoderTrainer, FlatAdamW, GradSync, flatten_parameters, gaussian_nll, vae_sample_with_grad
 
@@ -32,5 +33,5 @@ __all__ = [
     "create_model_from_config", "create_model_from_config_path", "create_pretransform_from_config",
     "get_activation", "load_ckpt_state_dict", "prepare_audio", "remove_weight_norm_from_model", "sample",
     "snake_beta", "vae_sample", "to_pcm16", "AutoencoderTrainer", "FlatAdamW", "GradSync", "flatten_parameters",
-    "gaussian_nll", "vae_sample_with_grad", "StreamingDecoder", "decoder_context_frames", "HostPipeline", "LatentGlue", "LatentExtractor",
+    "gaussian_nll", "vae_sample_with_grad", "StreamingDecoder", "decoder_context_frames", "HostPipeline", "LatentGlue", "LatentExtractor", "BigVGANFlowVAE",
 ]

@@ -78,6 +78,11 @@ SIGNATURES = {
     "kvae_decode_pcm16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_longlong,
                                     C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "kvae_plan_fused_pcm_supported": (C.c_int, [C.c_void_p]),
+    "kvae_aa_act_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                  C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
+    "kvae_unary_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_float, C.c_int, C.c_void_p]),
+    "kvae_axpby": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_float, C.c_float, C.c_int, C.c_void_p]),
+    "kvae_gauss_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
     "kvae_plan_out_length": (C.c_longlong, [C.c_void_p, C.c_longlong]),
     "kvae_prep_mono_clips": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_float,
                                        C.c_void_p, C.c_void_p, C.c_void_p]),

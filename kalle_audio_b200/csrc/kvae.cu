@@ -26,6 +26,7 @@
 #include "conv_umma_host.cuh"
 #include "elementwise.cuh"
 #include "glue.cuh"
+#include "bigvgan.cuh"
 #include "train.cuh"
 
 using namespace kvae;
@@ -2103,6 +2104,63 @@ int kvae_sigma_sample(const void* mean, const void* noise, void* out, size_t n, 
   const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
   sigma_sample_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(mean, noise, out, n, dtype == KVAE_F32,
                                                                              std, std_noise, value, per_batch);
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+// ------------------------------------------------------------------ BigVGANFlowVAE leaf kernels (bigvgan.cuh)
+int kvae_aa_act_fwd(const void* x, void* y, const float* alpha, const float* beta, int logscale, const float* filt_up,
+                    const float* filt_down, int B, int C, long long T, int dtype, void* stream) {
+  if (!x || !y || !alpha || !filt_up || !filt_down) return fail("null argument");
+  if (!check_dtype(dtype)) return fail("bad dtype");
+  if (B <= 0 || C <= 0 || T <= 0) return 0;
+  if (static_cast<long long>(B) * C > 65535) return fail("B*C too large");
+  DeviceGuard guard(device_of(x));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  dim3 grid(static_cast<unsigned>((T + kAaTile - 1) / kAaTile), B * C);
+  aa_act_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, alpha, beta, logscale, filt_up, filt_down, C, T,
+                                                                     dtype == KVAE_F32);
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int kvae_unary_fwd(const void* x, void* y, size_t n, int op, float param, int dtype, void* stream) {
+  if (!x || !y) return fail("null argument");
+  if (!check_dtype(dtype)) return fail("bad dtype");
+  if (op != 0 && op != 1) return fail("unary op: 0 = leaky_relu, 1 = tanh");
+  if (n == 0) return 0;
+  DeviceGuard guard(device_of(x));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
+  unary_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, n, op, param, dtype == KVAE_F32);
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int kvae_axpby(const void* a, const void* b, void* out, size_t n, float alpha, float beta, int dtype, void* stream) {
+  if (!a || !b || !out) return fail("null argument");
+  if (!check_dtype(dtype)) return fail("bad dtype");
+  if (n == 0) return 0;
+  DeviceGuard guard(device_of(a));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
+  axpby_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(a, b, out, n, alpha, beta, dtype == KVAE_F32);
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int kvae_gauss_sample(const void* mean, const void* logs, const void* noise, void* out, size_t n, int dtype, void* stream) {
+  if (!mean || !logs || !noise || !out) return fail("null argument");
+  if (!check_dtype(dtype)) return fail("bad dtype");
+  if (n == 0) return 0;
+  DeviceGuard guard(device_of(mean));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 148 * 16));
+  gauss_sample_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(mean, logs, noise, out, n, dtype == KVAE_F32);
   KV_CUDA(cudaGetLastError());
   ++g_launches;
   return 0;

@@ -27,6 +27,10 @@ Fixtures (all float32, little-endian .npz):
                     reference's pretransform.encode + vae_sample per clip (tiny model, self-contained)
   nearest.npz       decoders built with use_nearest_upsample=True (autoencoders.py:87-96): a tiny one (self-contained) and
                     a C=64 one (tensor-core path; checksums), outputs of the reference's OobleckDecoder
+  bigvgan.npz       the reference's BigVGANFlowVAE (backup/flows.py, its 12.5 Hz VAE) at a small synthetic config, causal
+                    and non-causal, AMPBlock1: state_dict, extract_latents and inference_from_latents outputs (with and
+                    without sampling).  flows.py does ``from alias_free_torch import *`` (un-vendored): the published
+                    algorithm restated in oracle/alias_free_restated.py is installed under that name
   o12_d256.npz      12.5 Hz shape, latent 256 ("dim512"), [1,256,16] <-> [1,1,20480], full outputs
   o12_d1024.npz     12.5 Hz shape, latent 1024 ("dim2048"), [1,1024,16] <-> [1,1,20480], full outputs
   o12_full.npz      BASELINE configs 3 and 4 at their own length: latent 512, [1,512,375] -> [1,1,480000] (config 3's
@@ -322,7 +326,57 @@ def nearest_fixtures(ae_mod):
     torch.set_grad_enabled(True)
 
 
+BIGVGAN_H = dict(latent_dim=16, use_vae=True, downsample_channels=[12, 24, 48], downsample_rates=[2, 4],
+                 flow_hidden_channels=8, resblock_kernel_sizes=[3, 7], resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5]],
+                 upsample_rates=[4, 2], upsample_kernel_sizes=[8, 4], upsample_initial_channel=32, resblock="1",
+                 activation="snakebeta", snake_logscale=True)
+
+
+def bigvgan_fixtures():
+    import importlib
+    sys.path.insert(0, os.path.dirname(HERE))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle import alias_free_restated
+    sys.modules["alias_free_torch"] = alias_free_restated
+    sys.path.insert(0, os.path.join(REF, "backup"))
+    flows = importlib.import_module("flows")
+
+    class AttrDict(dict):
+        __getattr__ = dict.__getitem__
+
+    out = {}
+    torch.set_grad_enabled(False)
+    for tag, causal in (("causal", True), ("noncausal", False)):
+        h = AttrDict(BIGVGAN_H, causal=causal)
+        torch.manual_seed(0)
+        m = flows.BigVGANFlowVAE(h).eval()
+        g = torch.Generator().manual_seed(7)
+        for name, p in m.named_parameters():                 # alpha / beta start at zero: perturb them
+            if name.endswith(".alpha") or name.endswith(".beta"):
+                p.copy_(0.3 * torch.randn(p.shape, generator=g))
+        x = 0.3 * torch.randn(2, 1, 8 * 37, generator=torch.Generator().manual_seed(1))
+        lat = m.extract_latents(x)
+        torch.manual_seed(5)
+        noise = torch.randn(2, 16, 37)
+        torch.manual_seed(5)
+        y_s = m.inference_from_latents(lat)                  # do_sample: draws randn_like(m_q) -> the same noise
+        z = torch.randn(2, 16, 21, generator=torch.Generator().manual_seed(2))
+        y_z = m.inference_from_latents(z, do_sample=False)
+        out.update({f"{tag}.x": x, f"{tag}.latents": lat, f"{tag}.noise": noise, f"{tag}.wav_sampled": y_s, f"{tag}.z": z,
+                    f"{tag}.wav": y_z})
+        if causal:                                           # same seed, same shapes: both variants share the parameters
+            for k, v in m.state_dict().items():
+                out[f"sd.{k}"] = v
+        else:
+            assert all(torch.equal(v, out[f"sd.{k}"]) for k, v in m.state_dict().items())
+    np.savez_compressed(os.path.join(HERE, "bigvgan.npz"), **{k: v.numpy() for k, v in out.items()})
+    torch.set_grad_enabled(True)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "bigvgan":
+        bigvgan_fixtures()
+        return
     ae_mod, bn_mod = import_reference()
     if len(sys.argv) > 1 and sys.argv[1] == "nearest":
         nearest_fixtures(ae_mod)
@@ -337,6 +391,7 @@ def main():
     if len(sys.argv) > 1 and sys.argv[1] == "o12":        # only the 12.5 Hz fixtures at configs 3 / 4 sizes
         o12_fixtures(ae_mod)
         return
+    bigvgan_fixtures()
     o12_fixtures(ae_mod)
     nearest_fixtures(ae_mod)
     glue_fixtures()

@@ -220,3 +220,22 @@ def test_nearest_upsample_decoder_matches_reference():
         ref = F.conv1d(F.interpolate(x, scale_factor=s, mode="nearest"), w, padding="same")
         got = F.conv_transpose1d(x, nearest_upsample_conv_taps(w, s), stride=s, padding=s, output_padding=1)
         assert got.shape == ref.shape and float((got - ref).abs().max()) <= 1e-12
+
+
+def test_bigvgan_oracle_matches_reference():
+    """BigVGANFlowVAE.extract_latents / inference_from_latents of the reference (backup/flows.py:494-529), causal and
+    non-causal, against the functional restatement in oracle/bigvgan_oracle.py."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_golden import BIGVGAN_H
+    from oracle import bigvgan_oracle as BO
+    g = H.golden("bigvgan")
+    for tag, causal in (("causal", True), ("noncausal", False)):
+        h = dict(BIGVGAN_H, causal=causal)
+        sd = {k[3:]: H.t(g[k]) for k in g.files if k.startswith("sd.")}
+        lat = BO.extract_latents(sd, h, H.t(g[f"{tag}.x"]))
+        assert lat.shape == g[f"{tag}.latents"].shape and np.abs(lat.numpy() - g[f"{tag}.latents"]).max() <= 2e-6
+        y = BO.inference_from_latents(sd, h, H.t(g[f"{tag}.z"]))
+        assert y.shape == g[f"{tag}.wav"].shape and np.abs(y.numpy() - g[f"{tag}.wav"]).max() <= 2e-6
+        ys = BO.inference_from_latents(sd, h, H.t(g[f"{tag}.latents"]), noise=H.t(g[f"{tag}.noise"]))
+        assert np.abs(ys.numpy() - g[f"{tag}.wav_sampled"]).max() <= 2e-6
