@@ -438,6 +438,7 @@ def run_cuda(args):
                 ("config5_train", lambda: measure_train(args, dev, rank, world, ae))]
         if world == 1:
             legs += [("config4_stream", lambda: measure_stream(args, dev)),
+                     ("bigvgan_decode", lambda: measure_bigvgan(args, dev)),
                      ("gpu_eager_baseline", lambda: gpu_eager_baseline(dev))]
         for name, fn in legs:
             try:
@@ -594,6 +595,56 @@ def measure_stream(args, dev):
                                    "CUDA-graph replay, bf16 mode"}}
 
 
+def measure_bigvgan(args, dev):
+    """the reference's 12.5 Hz VAE, BigVGANFlowVAE.inference_from_latents
+    (backup/flows.py:498-529), at a production-like synthetic config (the reference ships no config json): 16 kHz mono,
+    ratio 1280 = 8*5*4*2*2*2, latent 512, channels 1024 -> 16, AMPBlock1 with kernels 3/7/11 and dilations 1/3/5,
+    causal, snakebeta.  2 clips x 30 s, decode only."""
+    import torch
+    from kalle_audio_b200 import bigvgan as BV
+
+    class AttrDict(dict):
+        __getattr__ = dict.__getitem__
+
+    h = AttrDict(causal=True, latent_dim=512, use_vae=True, downsample_channels=[12, 24, 48, 96, 192, 384, 768],
+                 downsample_rates=[2, 2, 4, 4, 4, 5], flow_hidden_channels=64, resblock_kernel_sizes=[3, 7, 11],
+                 resblock_dilation_sizes=[[1, 3, 5]] * 3, upsample_rates=[8, 5, 4, 2, 2, 2],
+                 upsample_kernel_sizes=[16, 10, 8, 4, 4, 4], upsample_initial_channel=1024, resblock="1",
+                 activation="snakebeta", snake_logscale=True)
+    torch.set_grad_enabled(False)
+    torch.manual_seed(0)
+    m = BV.BigVGANFlowVAE(h).eval().to(dev)
+    B, T = 2, 375
+    z = torch.randn(B, 512, T, device=dev)
+    # algorithmic FLOPs: 2 * Cin * Cout * K per output sample of every conv / transposed conv (per input sample)
+    fl, L, ch = 2.0 * 512 * 1024 * 7 * T, T, 1024
+    for u, k in zip(h.upsample_rates, h.upsample_kernel_sizes):
+        fl += 2.0 * ch * (ch // 2) * k * L
+        L, ch = L * u, ch // 2
+        fl += sum(2.0 * ch * ch * rk * L * 2 * 3 for rk in h.resblock_kernel_sizes)
+    fl += 2.0 * ch * 1 * 7 * L
+    out = {"config": {"workload": "BigVGANFlowVAE.inference_from_latents, synthetic 12.5 Hz config (latent 512, 1024 -> 16 "
+                                  f"channels, rates 8/5/4/2/2/2, AMPBlock1 k 3/7/11), {B} clips x 30 s, decode only"},
+           "gflop_per_clip": fl / 1e9}
+    audio_s = B * T * 1280 / 16000
+    for prec in ("bf16", "fp32"):
+        m.set_precision(prec)
+        for _ in range(2):
+            m.inference_from_latents(z, do_sample=False)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = max(2, args.steps // 2)
+        for _ in range(n):
+            m.inference_from_latents(z, do_sample=False)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / n
+        out[prec + "_mode"] = {"value": audio_s / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+                               "tflops": B * fl / (ms * 1e-3) / 1e12}
+    return out
+
+
 def run_extra(args):
     """--workload o12_decode / stream as stand-alone lines (the default line carries them as extra keys)."""
     import torch
@@ -605,7 +656,10 @@ def run_extra(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    out = measure_o12_decode(args, dev, rank, world) if args.workload == "o12_decode" else measure_stream(args, dev)
+    if args.workload == "bigvgan":
+        out = measure_bigvgan(args, dev)
+    else:
+        out = measure_o12_decode(args, dev, rank, world) if args.workload == "o12_decode" else measure_stream(args, dev)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
@@ -718,7 +772,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["cuda", "reference"], default="cuda")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", choices=["roundtrip", "o12_decode", "stream", "train", "eager_baseline"], default="roundtrip",
+    ap.add_argument("--workload", choices=["roundtrip", "o12_decode", "stream", "train", "eager_baseline", "bigvgan"], default="roundtrip",
                     help="roundtrip = BASELINE configs[1] (the driver's line); o12_decode = configs[2]; stream = configs[3]; "
                          "train = configs[4]")
     ap.add_argument("--micro-batch", type=int, default=0)

@@ -178,6 +178,16 @@ int kvae_conv1d_fwd(const void* x, void* y, const float* w_folded, const float* 
                     int Cin, int Cout, long long T, int K, int stride, int dilation, int padding, int dtype,
                     void* scratch, size_t scratch_bytes, void* stream);
 size_t kvae_conv1d_scratch_bytes(int Cin, int Cout, int K);
+/* Same layer on the tensor cores, for channel counts that are multiples of 64 (kvae_conv1d_tc_supported): one
+ * layout pass to a channels-last bf16 operand, then the tcgen05 implicit-GEMM conv writing [B, Cout, T_keep]
+ * directly.  precision: KVAE_PREC_BF16 (bf16 operands) or KVAE_PREC_F32 (bf16x3 operand split, <= 1e-5).
+ * T_keep (0 = all): keep only the first T_keep outputs -- the causal Conv1d / ConvTranspose1d of backup/flows.py
+ * (:607-608 left padding d (K - 1); :388-389 last `stride` samples dropped) are the symmetric layer truncated. */
+size_t kvae_conv1d_tc_scratch_bytes(int B, int Cin, int Cout, long long T, int K, int precision);
+int kvae_conv1d_tc_supported(int Cin, int Cout, int K, int stride, int dilation, int transposed);
+int kvae_conv1d_tc_fwd(const void* x, void* y, const float* w_folded, const float* bias, int transposed, int B, int Cin,
+                       int Cout, long long T, long long T_keep, int K, int stride, int dilation, int padding, int dtype,
+                       int precision, void* scratch, size_t scratch_bytes, void* stream);
 
 /* ---- training step (BASELINE config 5) --------------------------------------------------------------
  * The reference trains the autoencoder with plain autograd through the module tree

@@ -144,8 +144,12 @@ class Conv1d(WNConv1d):
         super().__init__(in_channels, out_channels, kernel_size, stride=stride, padding=pad, dilation=dilation, bias=bias)
 
     def forward(self, x):
-        y = super().forward(x)
-        return y[:, :, :x.shape[2]].contiguous() if self.causal and self.kernel_size[0] > 1 else y
+        if self.causal and self.kernel_size[0] > 1:
+            y = self._forward_tc(x, keep=x.shape[2])         # tensor-core layers truncate inside the kernel
+            if y is not None:
+                return y
+            return super().forward(x)[:, :, :x.shape[2]].contiguous()
+        return super().forward(x)
 
 
 class ConvTranspose1d(WNConvTranspose1d):
@@ -160,8 +164,12 @@ class ConvTranspose1d(WNConvTranspose1d):
         self._drop = stride if causal else 0
 
     def forward(self, x):
-        y = super().forward(x)
-        return y[:, :, :-self._drop].contiguous() if self._drop else y
+        if self._drop:
+            y = self._forward_tc(x, keep=x.shape[2] * self.stride[0])
+            if y is not None:
+                return y
+            return super().forward(x)[:, :, :-self._drop].contiguous()
+        return super().forward(x)
 
 
 class Conv1d_S(nn.Module):
@@ -303,6 +311,18 @@ class BigVGANFlowVAE(nn.Module):
                 self.resblocks.append(resblock(h, ch, k, d, activation=h.activation, causal=causal))
         self.activation_post = _make_act(h, ch)
         self.conv_post = Conv1d(ch, 1, 7, 1, causal=causal)
+        self.set_precision("fp32")
+
+    def set_precision(self, precision: Optional[str]):
+        """Arithmetic of the convolutions whose channel counts are multiples of 64 (the wide stages, > 90 % of the
+        FLOPs of a production-size model): "fp32" (default) = tensor cores through the bf16x3 operand split (<= 1e-5),
+        "bf16" = bf16 tensor-core operands (<= 1e-3 class), None = fp32 CUDA-core kernels everywhere."""
+        if precision not in (None, "fp32", "bf16"):
+            raise ValueError("precision must be None, 'fp32' or 'bf16'")
+        for m in self.modules():
+            if isinstance(m, (WNConv1d, WNConvTranspose1d)):
+                m.tc_precision = precision
+        return self
 
     def forward(self, x):
         raise NotImplementedError("BigVGANFlowVAE.forward (the training pass through the flow, flows.py:454-492) is "

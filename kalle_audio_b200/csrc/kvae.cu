@@ -1786,6 +1786,86 @@ int kvae_conv1d_bwd(const void* x, const void* gy, const float* w, void* gx, flo
   return 0;
 }
 
+// Tensor-core form of kvae_conv1d_fwd for stand-alone layers whose channel counts are multiples of 64 (the wide
+// layers of BigVGANFlowVAE): [B, Cin, T] -> channels-last bf16 operand (one layout pass) -> conv_umma2_kernel writing
+// [B, Cout, T_keep] directly.  precision KVAE_PREC_BF16: bf16 operands; KVAE_PREC_F32: bf16 x 3 split (<= 1e-5).
+// T_keep <= the conv's natural output length keeps only the first T_keep outputs (causal convs / transposed convs of
+// flows.py: symmetric padding d (K - 1), first T outputs; kernel 2 s, last s outputs dropped) without a slicing copy.
+size_t kvae_conv1d_tc_scratch_bytes(int B, int Cin, int Cout, long long T, int K, int precision) {
+  const size_t n = static_cast<size_t>(Cin) * Cout * K;
+  const int split = precision == KVAE_PREC_F32 ? 2 : 1;
+  return align_up(n * 2 * split, 1024) + (split == 2 ? align_up(n * 4, 1024) : 0) +
+         align_up(static_cast<size_t>(B) * T * Cin * 2 * split, 1024);
+}
+
+int kvae_conv1d_tc_supported(int Cin, int Cout, int K, int stride, int dilation, int transposed) {
+  ConvGeom g{transposed ? kConvT : kConv, Cin, Cout, K, stride, dilation, 0};
+  if (!umma_supported(g) || stride < 1 || stride > kMaxPhases || K > kMaxTaps) return 0;
+  if (stride > 1 && dilation != 1) return 0;
+  return 1;
+}
+
+int kvae_conv1d_tc_fwd(const void* x, void* y, const float* w, const float* bias, int transposed, int B, int Cin, int Cout,
+                       long long T, long long T_keep, int K, int stride, int dilation, int padding, int dtype,
+                       int precision, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!x || !y || !w || !scratch) return fail("null argument");
+  if (!check_dtype(dtype)) return fail("bad dtype");
+  if (precision != KVAE_PREC_BF16 && precision != KVAE_PREC_F32) return fail("bad precision");
+  if (B <= 0 || T <= 0) return fail("empty input");
+  if (!kvae_conv1d_tc_supported(Cin, Cout, K, stride, dilation, transposed))
+    return fail("kvae_conv1d_tc_fwd: channel counts must be multiples of 64 (use kvae_conv1d_fwd)");
+  if (scratch_bytes < kvae_conv1d_tc_scratch_bytes(B, Cin, Cout, T, K, precision)) return fail("scratch too small");
+  ConvGeom g{transposed ? kConvT : kConv, Cin, Cout, K, stride, dilation, padding};
+  const long long T_nat = g.out_len(static_cast<int>(T));
+  if (T_nat <= 0) return fail("input shorter than the kernel");
+  if (T_keep <= 0) T_keep = T_nat;
+  const int P_out = transposed ? stride : 1;
+  if (T_keep > T_nat || T_keep % P_out) return fail("T_keep must be <= the output length and a multiple of the stride (transposed)");
+  DeviceGuard guard(device_of(x));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int split = precision == KVAE_PREC_F32 ? 2 : 1;
+  const size_t n = static_cast<size_t>(Cin) * Cout * K;
+  uint8_t* sp = static_cast<uint8_t*>(scratch);
+  __nv_bfloat16* w_umma = reinterpret_cast<__nv_bfloat16*>(sp);
+  sp += align_up(n * 2 * split, 1024);
+  float* w_direct = nullptr;
+  if (split == 2) { w_direct = reinterpret_cast<float*>(sp); sp += align_up(n * 4, 1024); }
+  __nv_bfloat16* xcl = reinterpret_cast<__nv_bfloat16*>(sp);
+  const int blocks = static_cast<int>(std::min<size_t>((n + 255) / 256, 4096));
+  pack_weights_kernel<<<blocks, 256, 0, st>>>(w, transposed, Cout, Cin, K, split == 2 ? nullptr : w_umma, w_direct);
+  KV_CUDA(cudaGetLastError());
+  if (split == 2) {
+    split_pack_kernel<<<blocks, 256, 0, st>>>(w_direct, K, Cin, Cout, w_umma);
+    KV_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
+  {
+    dim3 grid(ceil_div(static_cast<int>(T), 32), ceil_div(Cin, 32), B), block(32, 8);
+    cf_to_cl_bf16_kernel<<<grid, block, 0, st>>>(x, dtype == KVAE_F32, xcl, Cin, static_cast<int>(T), split == 2 ? 1 : 0);
+    KV_CUDA(cudaGetLastError());
+  }
+  ConvEpilogue ep;
+  ep.bias = bias;
+  ep.out_raw = y;
+  ep.out_raw_cf = 1;
+  ep.out_raw_f32 = (dtype == KVAE_F32);
+  if (split == 2) { ep.split3 = 1; ep.precise = 1; }
+  ConvTuning2 tune;
+  ConvLaunch2 L;
+  std::string err;
+  StreamGeom sg;
+  sg.in_rows = static_cast<int>(T);
+  sg.out_q = static_cast<int>(T_keep / P_out);
+  sg.row_bias = 0;
+  const bool truncated = T_keep != T_nat;
+  if (truncated && !transposed && stride != 1) return fail("T_keep with a strided conv is unsupported");
+  if (!prepare_conv_umma2(g, xcl, B, static_cast<int>(T), w_umma, ep, tune, L, err, truncated ? &sg : nullptr)) return fail(err);
+  KV_CUDA(launch_conv_umma2(L, st));
+  g_launches += 3;
+  return 0;
+}
+
 // ------------------------------------------------------------------ training step
 long long kvae_plan_param_count(const kvae_plan* p) { return p ? p->n_params : fail("null plan"); }
 

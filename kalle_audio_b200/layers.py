@@ -212,7 +212,38 @@ class _WNConvBase(nn.Module):
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.conv_params())):
             wparams = (self.weight_g, self.weight_v) if self.has_weight_norm else (self._parameters["weight"],)
             return _ConvFn.apply(self, x, self.bias, *wparams)
-        return self._forward_impl(x)[0]
+        y = self._forward_tc(x)
+        return y if y is not None else self._forward_impl(x)[0]
+
+    # Stand-alone layers run fp32 CUDA-core arithmetic by default.  ``tc_precision`` ("bf16" | "fp32") sends layers
+    # whose channel counts are multiples of 64 through the tcgen05 conv instead (kvae_conv1d_tc_fwd; "fp32" = bf16x3
+    # operand split, <= 1e-5); ``keep`` truncates the output to its first ``keep`` samples inside the kernel.
+    tc_precision = None
+
+    def _forward_tc(self, x, keep=0):
+        L = _lib.lib()
+        K, s, d, p = self.kernel_size[0], self.stride[0], self.dilation[0], self.padding[0]
+        if self.tc_precision is None or getattr(self, "_same_extra_right", 0) or x.shape[2] < 64 or \
+                not L.kvae_conv1d_tc_supported(self.in_channels, self.out_channels, K, s, d, int(self.transposed)):
+            return None
+        xin = x if x.dtype in (torch.float32, torch.bfloat16) else x.float()
+        xin = xin.contiguous()
+        B, _, T = xin.shape
+        T_nat = (T - 1) * s - 2 * p + d * (K - 1) + 1 if self.transposed else (T + 2 * p - d * (K - 1) - 1) // s + 1
+        keep = int(keep) if keep else T_nat
+        if keep != T_nat and not self.transposed and s != 1:
+            return None
+        prec = _lib.KVAE_PREC_BF16 if self.tc_precision == "bf16" else _lib.KVAE_PREC_F32
+        w = self.folded_weight()
+        bias = None if self.bias is None else self.bias.detach().float().contiguous()
+        y = torch.empty((B, self.out_channels, keep), dtype=xin.dtype, device=x.device)
+        nscratch = L.kvae_conv1d_tc_scratch_bytes(B, self.in_channels, self.out_channels, T, K, prec)
+        scratch = torch.empty(nscratch, dtype=torch.uint8, device=x.device)
+        _lib.check(L.kvae_conv1d_tc_fwd(xin.data_ptr(), y.data_ptr(), w.data_ptr(), _lib.ptr(bias), int(self.transposed), B,
+                                        self.in_channels, self.out_channels, T, keep, K, s, d, p,
+                                        _lib.dtype_code(xin.dtype), prec, scratch.data_ptr(), nscratch,
+                                        _lib.stream_ptr(x.device)))
+        return y if y.dtype == x.dtype else y.to(x.dtype)
 
     def _forward_impl(self, x):
         """(y, the contiguous input actually used, the folded fp32 weight)"""

@@ -87,6 +87,22 @@ def test_bigvgan_wider_model_vs_oracle(dev):
     sd = {n: p.clone() for n, p in m.state_dict().items()}
     z = torch.randn(2, 16, 50, generator=torch.Generator().manual_seed(2))
     ref = BO.inference_from_latents(sd, dict(h), z)
-    y = m.to(dev).inference_from_latents(z.to(dev), do_sample=False)
-    assert y.shape == ref.shape == (2, 1, 400)
-    assert float((y.cpu() - ref).abs().max()) <= 2e-5
+    m.to(dev)
+    errs = {}
+    for prec in (None, "fp32", "bf16"):          # CUDA cores / tensor cores via the bf16x3 split / bf16 tensor-core operands
+        y = m.set_precision(prec).inference_from_latents(z.to(dev), do_sample=False)
+        assert y.shape == ref.shape == (2, 1, 400)
+        errs[prec] = float((y.cpu() - ref).abs().max())
+    H.report("BigVGANFlowVAE wide config: CUDA-core / tensor-core fp32 mode / bf16 mode", " / ".join(f"{v:.2e}" for v in errs.values()))
+    assert errs[None] <= 2e-5 and errs["fp32"] <= 2e-5 and errs["bf16"] <= 5e-3 * max(1.0, float(ref.abs().max()))
+    assert errs["bf16"] > errs["fp32"]           # the reduced-precision path really ran
+    # causal form on the tensor cores: truncation inside the kernel (no slicing copy)
+    hc = AttrDict(h, causal=True, resblock="1", activation="snakebeta", resblock_dilation_sizes=[[1, 3, 5], [1, 3, 5]],
+                  snake_logscale=True)
+    torch.manual_seed(2)
+    mc = BV.BigVGANFlowVAE(hc).eval()
+    sdc = {n: p.clone() for n, p in mc.state_dict().items()}
+    zc = torch.randn(1, 16, 90, generator=torch.Generator().manual_seed(3))
+    refc = BO.inference_from_latents(sdc, dict(hc), zc)
+    yc = mc.to(dev).inference_from_latents(zc.to(dev), do_sample=False)
+    assert float((yc.cpu() - refc).abs().max()) <= 2e-5
