@@ -259,6 +259,7 @@ conv_wave_out_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 4); }
     ptx::fence_mbar_init();
   }
+  ptx::pdl_launch_dependents();
   if (warp == 2) {
     ptx::tmem_alloc(tmem_slot, 32);
     ptx::tmem_relinquish();
@@ -287,6 +288,7 @@ conv_wave_out_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  ptx::pdl_wait();                 // the weight / table staging above reads constants only
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {

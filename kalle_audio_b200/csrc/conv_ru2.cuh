@@ -64,6 +64,7 @@ conv_ru2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int i = 0; i < 2 * kRuEpiWarps; ++i) ptx::mbar_init(&res_full[i], 1);
     ptx::fence_mbar_init();
   }
+  ptx::pdl_launch_dependents();
   if (warp == 2) {
     ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
@@ -71,6 +72,7 @@ conv_ru2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  ptx::pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
   const int k0 = p.k0, k1 = p.k1;       // GEMM2 half 0 / half 1 of tile i are issued before slab k0 / k1 of tile i+1
 

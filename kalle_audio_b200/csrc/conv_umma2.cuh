@@ -143,6 +143,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (p.residual) ptx::prefetch_tmap(&tmX);
     ptx::fence_mbar_init();
   }
+  ptx::pdl_launch_dependents();
   if (warp == 2) {
     ptx::tmem_alloc(tmem_slot, p.tmem_cols);
     ptx::tmem_relinquish();
@@ -150,6 +151,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  ptx::pdl_wait();                 // everything above overlapped the previous kernel's tail; its outputs are visible from here
   const uint32_t tmem_base = *tmem_slot;
   // Two operand assignments.  swap = 0: M = 128 time rows (x MT sub-tiles), N = NT out-channels.
   // swap = 1 (NT == 128): M = 128 out-channels, N = 128*MT time rows.  With N = 256 one instruction does the

@@ -2,6 +2,7 @@
 // ConvTranspose1d decompose into (input phase, row shift, weight slab) contributions),
 // TMA tensor maps over the channels-last activations and the packed weights, launch.
 #pragma once
+#include <utility>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -473,6 +474,27 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
   return true;
 }
 
+// Launch with programmatic stream serialization (ptx.cuh, pdl_*): the kernel may begin while its predecessor drains.
+// KVAE_PDL=0 restores plain stream-ordered launches (A/B measurements).
+inline bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("KVAE_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 inline cudaError_t launch_conv_umma2(const ConvLaunch2& L, cudaStream_t stream) {
   static bool attr_set[64] = {false};   // per device (the attribute is per device context)
   int dev = 0;
@@ -482,8 +504,7 @@ inline cudaError_t launch_conv_umma2(const ConvLaunch2& L, cudaStream_t stream) 
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
   }
-  conv_umma2_kernel<<<L.grid, 384, L.smem, stream>>>(L.tmA, L.tmW, L.tmR, L.tmO, L.tmX, L.p);
-  return cudaGetLastError();
+  return launch_pdl(conv_umma2_kernel, dim3(L.grid), dim3(384), L.smem, stream, L.tmA, L.tmW, L.tmR, L.tmO, L.tmX, L.p);
 }
 
 // ------------------------------------------------------------------ fused ResidualUnit (conv_ru.cuh)
@@ -588,7 +609,7 @@ inline cudaError_t launch_conv_ru(const RuLaunch& L, cudaStream_t stream) {
     attr_set[dev & 63] = true;
   }
   if (epi == 2)
-    conv_ru2_kernel<<<L.grid, kRuThreads, L.smem, stream>>>(L.tmA, L.tmW7, L.tmW1, L.tmR, L.tmO, L.tmX, L.p);
+    return launch_pdl(conv_ru2_kernel, dim3(L.grid), dim3(kRuThreads), L.smem, stream, L.tmA, L.tmW7, L.tmW1, L.tmR, L.tmO, L.tmX, L.p);
   else if (epi == 0)
     conv_ru_kernel<0><<<L.grid, kRuThreads, L.smem, stream>>>(L.tmA, L.tmW7, L.tmW1, L.tmR, L.tmO, L.tmX, L.p);
   else

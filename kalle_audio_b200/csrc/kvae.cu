@@ -880,9 +880,8 @@ int run_plan(kvae_plan* p, bool train, const void* in, int in_dtype, void* out, 
         attr_set[dev & 63] = true;
       }
       const int grid = std::min(t.p.total_tiles, sm_count());
-      if (R.stream_f16) conv_wave_out_tc_kernel<true><<<grid, kWoTcThreads, wave_out_tc_smem<true>(), st>>>(t.tmX, t.p);
-      else conv_wave_out_tc_kernel<false><<<grid, kWoTcThreads, wave_out_tc_smem<false>(), st>>>(t.tmX, t.p);
-      KV_CUDA(cudaGetLastError());
+      if (R.stream_f16) KV_CUDA(launch_pdl(conv_wave_out_tc_kernel<true>, dim3(grid), dim3(kWoTcThreads), wave_out_tc_smem<true>(), st, t.tmX, t.p));
+      else KV_CUDA(launch_pdl(conv_wave_out_tc_kernel<false>, dim3(grid), dim3(kWoTcThreads), wave_out_tc_smem<false>(), st, t.tmX, t.p));
     } else if (R.kind[k] == 3) {
       WaveOutParams& w = R.wave_out[k];
       w.y = out;

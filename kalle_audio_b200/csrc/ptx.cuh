@@ -40,6 +40,16 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in the
+// stream is still running: its CTAs are scheduled as soon as every CTA of the predecessor has executed
+// pdl_launch_dependents() (or exited) and SMs are free, run their prologue (barrier init, TMEM allocation,
+// tensor-map prefetch) and then block in pdl_wait() until the predecessor has completed and its writes are visible.
+// With small batches (streaming decode: ~30 launches of 5-30 us per hop) the prologues and the launch latency of
+// kernel N+1 disappear under the tail of kernel N.  Both are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

@@ -306,9 +306,8 @@ cudaError_t stream_launch_all(kvae_stream* s, PreparedPush& P, int n_frames, int
         attr_set[dev & 63] = true;
       }
       const int grid = std::min(P.wo_tc.p.total_tiles, sm_count());
-      if (s->stream_f16) conv_wave_out_tc_kernel<true><<<grid, kWoTcThreads, wave_out_tc_smem<true>(), st>>>(P.wo_tc.tmX, P.wo_tc.p);
-      else conv_wave_out_tc_kernel<false><<<grid, kWoTcThreads, wave_out_tc_smem<false>(), st>>>(P.wo_tc.tmX, P.wo_tc.p);
-      e = cudaGetLastError();
+      if (s->stream_f16) e = launch_pdl(conv_wave_out_tc_kernel<true>, dim3(grid), dim3(kWoTcThreads), wave_out_tc_smem<true>(), st, P.wo_tc.tmX, P.wo_tc.p);
+      else e = launch_pdl(conv_wave_out_tc_kernel<false>, dim3(grid), dim3(kWoTcThreads), wave_out_tc_smem<false>(), st, P.wo_tc.tmX, P.wo_tc.p);
     } else if (kind == 3) {
       e = launch_wave_out(P.wo_cc, P.wo_cout, s->B, st);
     }
