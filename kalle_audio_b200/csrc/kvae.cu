@@ -1252,7 +1252,14 @@ int run_backward(kvae_plan* p, const void* x, int x_dtype, const void* gy, int g
       EdgeWgradParams e = bw.wg_edge;
       if (bw.wg_edge_x_is_thin) { e.N = x; e.N_f32 = (x_dtype == KVAE_F32); }
       e.dW = grads + c.off_v;
-      if (std::min(c.g.Cin, c.g.Cout) == 1) wgrad_edge_kernel<1><<<bw.wg_edge_grid, 256, bw.wg_edge_smem, st>>>(e);
+      const int C4 = e.C / 4;
+      const bool vec = e.C % 4 == 0 && C4 >= 8 && C4 <= 256 && (C4 & (C4 - 1)) == 0 && !env_flag("KVAE_WGRAD_EDGE_SCALAR");
+      if (vec) {
+        // + the lane-reduction scratch: 256 threads x NT x 4 floats behind the thin rows
+        const size_t smem = bw.wg_edge_smem + 16 + 256 * 2 * 4 * sizeof(float);
+        if (std::min(c.g.Cin, c.g.Cout) == 1) wgrad_edge_vec4_kernel<1><<<bw.wg_edge_grid, 256, smem, st>>>(e);
+        else wgrad_edge_vec4_kernel<2><<<bw.wg_edge_grid, 256, smem, st>>>(e);
+      } else if (std::min(c.g.Cin, c.g.Cout) == 1) wgrad_edge_kernel<1><<<bw.wg_edge_grid, 256, bw.wg_edge_smem, st>>>(e);
       else wgrad_edge_kernel<2><<<bw.wg_edge_grid, 256, bw.wg_edge_smem, st>>>(e);
       KV_CUDA(cudaGetLastError());
       ++g_launches;
