@@ -194,6 +194,7 @@ struct kvae_plan {
   std::vector<long long> param_sizes;   // segment sizes in module.parameters() order
   bool train_packs = false;
   bool stream_f16 = false;    // inference plans keep the residual stream in fp16 (bf16 mode, all-tensor-core chains)
+  bool train_stream_f16 = false;   // ... and so do training plans whose every backward consumer of the stream knows fp16
   float* scale_scratch = nullptr;   // g/||v|| per dim-0 row of the conv being packed
   // batched kvae_plan_load_params (one scale + one pack + one SnakeBeta-constant launch for the whole plan)
   FoldDesc* fold_desc = nullptr;    // device, one per conv
@@ -360,6 +361,11 @@ void finalize_steps(kvae_plan* p) {
   for (int k = 0; k < n && p->stream_f16; ++k)
     if (!p->convs[p->steps[k].conv].umma && !is_wave_in_step(p, p->steps, k) && !is_wave_out_step(p, p->steps, k))
       p->stream_f16 = false;
+  // Training plans: the saved pre-activation stream is fp16 too when every step is a tensor-core conv or one of the
+  // two waveform-edge convs (the graded architectures): the forward k=1 convs then move 1024 instead of 1536 bytes per
+  // row and use the fragment-mapped epilogue, the SnakeBeta backward reads 2 instead of 4 bytes per element.  The
+  // 11 significant bits of fp16 are what the inference path already carries.  KVAE_TRAIN_STREAM_F32=1 keeps fp32.
+  p->train_stream_f16 = p->stream_f16 && !env_flag("KVAE_TRAIN_STREAM_F32") && n >= 3;
   // a conv is a tensor-core step in bf16 mode (always) or in fp32 mode for inference (bf16x3 split); fp32-mode
   // training stays on the CUDA cores, so the two step lists can differ in who needs which tensor
   auto set_flags = [&](std::vector<Step>& steps, bool train) {
@@ -445,7 +451,7 @@ bool make_layout(const kvae_plan* p, const std::vector<Step>& steps, bool train,
     if (train) last_use = 1 << 30;   // saved for the backward pass
     if (s.needs_raw && k != n - 1) {
       Tensor& t = L.t[1 + 2 * k];
-      t.bytes = static_cast<size_t>(B) * len * c.g.Cout * ((p->stream_f16 && !train) ? 2 : 4);
+      t.bytes = static_cast<size_t>(B) * len * c.g.Cout * ((train ? p->train_stream_f16 : p->stream_f16) ? 2 : 4);
       t.first = k;
       t.last = last_use;
     }
@@ -510,7 +516,7 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
   R.direct_cfg.assign(n, 0);
   R.direct_smem.assign(n, 0);
   R.kind.assign(n, 1);
-  R.stream_f16 = p->stream_f16 && !train;
+  R.stream_f16 = train ? p->train_stream_f16 : p->stream_f16;
   const int sf16 = R.stream_f16 ? 1 : 0;
   R.wave_in.resize(n);
   R.wave_out.resize(n);
@@ -1085,6 +1091,7 @@ bool prepare_backward(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R
       e.B = B; e.T = static_cast<int>(T_out); e.K = c.g.K; e.dil = c.g.dilation; e.pad = c.g.pad;
       if (c.g.Cout <= 2) {   // decoder tail: wide = SnakeBeta(stream), thin = output gradient (channels-last)
         e.W = static_cast<const float*>(a_ptr); e.W_a = a_sn; e.W_inv_b = a_ib; e.C = c.g.Cin;
+        e.W_f16 = R.stream_f16 ? 1 : 0;
         e.N = g_ptr; e.N_f32 = 1; e.N_sB = g_sB; e.N_sT = g_sT; e.N_sC = 1;
         e.sigma = 1; e.out_wide_first = 0;
       } else {               // encoder head: wide = gradient of the stream, thin = the caller's waveform (API layout)
@@ -1094,7 +1101,12 @@ bool prepare_backward(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R
         bw.wg_edge_x_is_thin = true;
       }
       set_edge_grid(e, bw.wg_edge_grid, bw.wg_edge_smem);
+      if (e.W_f16 && !(e.C % 4 == 0 && e.C / 4 >= 8 && e.C / 4 <= 256 && ((e.C / 4) & (e.C / 4 - 1)) == 0)) {
+        err = "internal: fp16 training stream with an edge conv the vectorised weight-gradient kernel does not cover";
+        return false;
+      }
     } else {
+      if (R.stream_f16 && a_f32) { err = "internal: fp16 training stream reaches a CUDA-core weight gradient"; return false; }
       const int tiles = ceil_div(w.Cd, 64) * ceil_div(w.Cs, 64);
       const long long rows = static_cast<long long>(B) * w.Td;
       long long nsplit = std::max<long long>(1, (4ll * sm_count()) / (static_cast<long long>(tiles) * w.K));
@@ -1174,6 +1186,8 @@ bool prepare_backward(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R
       if (s.pre_snake >= 0) {
         const SnakeLayer& sn = p->snakes[s.pre_snake];
         sb.x = static_cast<const float*>(tptr(1 + 2 * (k - 1)));
+        sb.x_f16 = R.stream_f16 ? 1 : 0;
+        if (sb.x_f16 && c.g.Cin % 8) { err = "internal: fp16 training stream needs channel counts that are multiples of 8"; return false; }
         if (!sb.x) { err = "internal: saved stream missing at step " + std::to_string(k - 1); return false; }
         sb.a = sn.a; sb.inv_b = sn.inv_b; sb.logscale = sn.logscale;
       }
@@ -1253,7 +1267,7 @@ int run_backward(kvae_plan* p, const void* x, int x_dtype, const void* gy, int g
       if (bw.wg_edge_x_is_thin) { e.N = x; e.N_f32 = (x_dtype == KVAE_F32); }
       e.dW = grads + c.off_v;
       const int C4 = e.C / 4;
-      const bool vec = e.C % 4 == 0 && C4 >= 8 && C4 <= 256 && (C4 & (C4 - 1)) == 0 && !env_flag("KVAE_WGRAD_EDGE_SCALAR");
+      const bool vec = e.C % 4 == 0 && C4 >= 8 && C4 <= 256 && (C4 & (C4 - 1)) == 0 && (e.W_f16 || !env_flag("KVAE_WGRAD_EDGE_SCALAR"));
       if (vec) {
         // + the lane-reduction scratch: 256 threads x NT x 4 floats behind the thin rows
         const size_t smem = bw.wg_edge_smem + 16 + 256 * 2 * 4 * sizeof(float);

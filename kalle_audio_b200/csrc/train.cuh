@@ -11,6 +11,7 @@
 #pragma once
 #include "ptx.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 
 #include "conv_umma.cuh"    // snake_beta
@@ -86,6 +87,7 @@ struct SnakeBwdParams {
   // copy of that gradient then has no reader and is not written at all.
   int dA_bf16;            // dA points to bf16
   int skip_bf16;          // skip points to bf16
+  int x_f16;              // x points to fp16 (training plans with the fp16 stream); vectorised kernels only
 };
 
 __global__ void __launch_bounds__(256) snake_bwd_kernel(const SnakeBwdParams p) {
@@ -184,7 +186,15 @@ __global__ void __launch_bounds__(256) snake_bwd_vec4_kernel(const SnakeBwdParam
       const size_t i = static_cast<size_t>(r) * C4 + c4;
       float4 g = p.dA_bf16 ? ld_bf16x4(p.dA, i) : __ldcs(dA + i);
       if (p.a) {
-        const float4 xv = __ldcs(X + i);
+        float4 xv;
+        if (p.x_f16) {
+          const uint2 q = __ldcs(reinterpret_cast<const uint2*>(p.x) + i);
+          const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
+          const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+          xv = make_float4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+          xv = __ldcs(X + i);
+        }
         snake_bwd_elem<kFast>(g.x, xv.x, a.x, ib.x, s1.x, s2.x);
         snake_bwd_elem<kFast>(g.y, xv.y, a.y, ib.y, s1.y, s2.y);
         snake_bwd_elem<kFast>(g.z, xv.z, a.z, ib.z, s1.z, s2.z);
@@ -269,7 +279,7 @@ __global__ void __launch_bounds__(kSbsThreads, 1) snake_bwd_stream_kernel(const 
   const int cb = blockIdx.x % gm.ncol;                   // this CTA's column block (fixed: grid is a multiple of ncol)
   const long long t_first = blockIdx.x / gm.ncol, t_step = gridDim.x / gm.ncol;
   const bool has_a = p.a != nullptr, has_sk = p.skip != nullptr;
-  const int esz_dA = p.dA_bf16 ? 8 : 16, esz_sk = p.skip_bf16 ? 8 : 16;   // bytes per 4 channels
+  const int esz_dA = p.dA_bf16 ? 8 : 16, esz_sk = p.skip_bf16 ? 8 : 16, esz_x = p.x_f16 ? 8 : 16;   // bytes per 4 channels
   if (threadIdx.x == 0) {
     for (int i = 0; i < kSbsStages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], kSbsCompute / 32); }
     ptx::fence_mbar_init();
@@ -285,21 +295,21 @@ __global__ void __launch_bounds__(kSbsThreads, 1) snake_bwd_stream_kernel(const 
         const int nr = static_cast<int>(min(static_cast<long long>(gm.R), p.rows - r0));
         ptx::mbar_wait(&empty[s], ph ^ 1u);
         uint8_t* st = ring + static_cast<size_t>(s) * 3 * kSbsTileVec * 16;
-        const uint32_t bytes = static_cast<uint32_t>(nr) * gm.CW4 * (esz_dA + (has_a ? 16 : 0) + (has_sk ? esz_sk : 0));
+        const uint32_t bytes = static_cast<uint32_t>(nr) * gm.CW4 * (esz_dA + (has_a ? esz_x : 0) + (has_sk ? esz_sk : 0));
         ptx::mbar_expect_tx(&full[s], bytes);
         const size_t e0 = static_cast<size_t>(r0) * C4 + static_cast<size_t>(cb) * gm.CW4;     // first float4 index
         if (gm.ncol == 1) {                                // whole rows: one contiguous range per tensor
           const uint32_t nv = static_cast<uint32_t>(nr) * gm.CW4;
           ptx::bulk_load_1d(st, reinterpret_cast<const uint8_t*>(p.dA) + e0 * esz_dA, nv * esz_dA, &full[s]);
-          if (has_a) ptx::bulk_load_1d(st + kSbsTileVec * 16, reinterpret_cast<const uint8_t*>(p.x) + e0 * 16, nv * 16, &full[s]);
+          if (has_a) ptx::bulk_load_1d(st + kSbsTileVec * 16, reinterpret_cast<const uint8_t*>(p.x) + e0 * esz_x, nv * esz_x, &full[s]);
           if (has_sk) ptx::bulk_load_1d(st + 2 * kSbsTileVec * 16, reinterpret_cast<const uint8_t*>(p.skip) + e0 * esz_sk, nv * esz_sk, &full[s]);
         } else {
           for (int r = 0; r < nr; ++r) {
             const size_t e = e0 + static_cast<size_t>(r) * C4;
             ptx::bulk_load_1d(st + static_cast<size_t>(r) * gm.CW4 * esz_dA, reinterpret_cast<const uint8_t*>(p.dA) + e * esz_dA,
                               gm.CW4 * esz_dA, &full[s]);
-            if (has_a) ptx::bulk_load_1d(st + kSbsTileVec * 16 + static_cast<size_t>(r) * gm.CW4 * 16,
-                                         reinterpret_cast<const uint8_t*>(p.x) + e * 16, gm.CW4 * 16, &full[s]);
+            if (has_a) ptx::bulk_load_1d(st + kSbsTileVec * 16 + static_cast<size_t>(r) * gm.CW4 * esz_x,
+                                         reinterpret_cast<const uint8_t*>(p.x) + e * esz_x, gm.CW4 * esz_x, &full[s]);
             if (has_sk) ptx::bulk_load_1d(st + 2 * kSbsTileVec * 16 + static_cast<size_t>(r) * gm.CW4 * esz_sk,
                                           reinterpret_cast<const uint8_t*>(p.skip) + e * esz_sk, gm.CW4 * esz_sk, &full[s]);
           }
@@ -337,7 +347,15 @@ __global__ void __launch_bounds__(kSbsThreads, 1) snake_bwd_stream_kernel(const 
       const int v = r * gm.CW4 + c4l;
       float4 g = p.dA_bf16 ? bf4(reinterpret_cast<const uint2*>(st)[v]) : reinterpret_cast<const float4*>(st)[v];
       if (has_a) {
-        const float4 xv = reinterpret_cast<const float4*>(st + kSbsTileVec * 16)[v];
+        float4 xv;
+        if (p.x_f16) {
+          const uint2 q = reinterpret_cast<const uint2*>(st + kSbsTileVec * 16)[v];
+          const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&q.x));
+          const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+          xv = make_float4(lo.x, lo.y, hi.x, hi.y);
+        } else {
+          xv = reinterpret_cast<const float4*>(st + kSbsTileVec * 16)[v];
+        }
         snake_bwd_elem<kFast>(g.x, xv.x, a.x, ib.x, s1.x, s2.x);
         snake_bwd_elem<kFast>(g.y, xv.y, a.y, ib.y, s1.y, s2.y);
         snake_bwd_elem<kFast>(g.z, xv.z, a.z, ib.z, s1.z, s2.z);
@@ -417,7 +435,8 @@ inline bool snake_bwd_stream_geom(const SnakeBwdParams& p, SnakeBwdStreamGeom& g
 // HBM-bound (the wide tensor is read once); thread = channel, 7 x NT accumulators in registers, the thin rows a
 // block needs are staged in shared memory.  grid (nblocks), block 256 = (256 / C) row lanes x C channels.
 struct EdgeWgradParams {
-  const float* W;            // [B, T, C] fp32
+  const float* W;            // [B, T, C] fp32 (fp16 with W_f16: the saved stream of a training plan)
+  int W_f16;
   const float* W_a;          // SnakeBeta prologue on W (nullptr: none)
   const float* W_inv_b;
   const void* N;             // thin tensor, element strides below
@@ -541,12 +560,21 @@ __global__ void __launch_bounds__(256, 2) wgrad_edge_vec4_kernel(const EdgeWgrad
   }
   const int u_lo = max(0, t0 - halo), u_hi = min(p.T, t1 + halo);
   const float4* Wc = reinterpret_cast<const float4*>(p.W + static_cast<size_t>(b) * p.T * p.C) + c4;
+  const uint2* Wh = reinterpret_cast<const uint2*>(reinterpret_cast<const __half*>(p.W) + static_cast<size_t>(b) * p.T * p.C) + c4;
   for (int u0 = u_lo + rl; u0 < u_hi; u0 += 4 * lanes) {
     float4 w[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int u = u0 + q * lanes;
-      w[q] = (u < u_hi) ? __ldcs(Wc + static_cast<size_t>(u) * C4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (u >= u_hi) { w[q] = make_float4(0.f, 0.f, 0.f, 0.f); continue; }
+      if (p.W_f16) {
+        const uint2 hq = __ldcs(Wh + static_cast<size_t>(u) * C4);
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&hq.x));
+        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&hq.y));
+        w[q] = make_float4(lo.x, lo.y, hi.x, hi.y);
+      } else {
+        w[q] = __ldcs(Wc + static_cast<size_t>(u) * C4);
+      }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
