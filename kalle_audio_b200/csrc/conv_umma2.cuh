@@ -67,6 +67,20 @@ struct ConvParams2 {
   // mean half of the latents, twj-style chunk(2, dim=1)): for channels c < samp_D,
   //   samp_out[b, c, t] = mean + samp_std * samp_noise[b, c, t], two separately rounded operations on the value AS STORED
   // (rounded to the output dtype first), i.e. bit-identical to torch on the stored latents.  Same dtype as out_cf.
+  // Training backward, data-gradient launches (fragment-mapped swap epilogue only): the SnakeBeta derivative and the
+  // skip-connection add of the layer BEFORE this conv are applied to the accumulator in the epilogue,
+  //   G = dA * (1 + a * inv_b * sin(2 a x)) + skip        (dA = this conv's output, x = that layer's saved fp16 stream)
+  // G leaves as bf16 through the operand path (act_mode 1), and the per-channel sums d alpha, d beta and the bias
+  // gradient of the producing conv (column sums of G) accumulate in registers and go out with one atomic per channel,
+  // warp and tile.  Replaces a separate HBM pass over dA, x, skip and G (snake_bwd_stream_kernel).
+  int bwd;                 // 1: this mode; tmX maps x (fp16), tmR maps skip (bf16) when bwd_skip
+  int bwd_skip;
+  int bwd_logscale;
+  const float* bwd_a;      // exp(alpha) / 1/(exp(beta)+1e-9) of that SnakeBeta
+  const float* bwd_inv_b;
+  float* d_alpha;          // [Cout] accumulated
+  float* d_beta;
+  float* d_bias;           // [Cout] accumulated or nullptr
   const void* samp_noise;  // [B, samp_D, T_out] or nullptr
   void* samp_out;          // [B, samp_D, T_out]
   int samp_D;
@@ -97,14 +111,15 @@ __host__ __device__ inline int conv_umma2_raw_slots(int raw_mode, bool residual)
   return (raw_mode == 1 || residual) ? (residual ? 3 : 2) : 0;
 }
 __host__ __device__ inline int conv_umma2_stage_bytes_per_warp(int raw_mode, int act_mode, bool residual, int raw_f16,
-                                                               int act_split = 0) {
+                                                               int act_split = 0, int bwd = 0) {
+  if (bwd) return 2 * (2 * kActBlkBytes) + 2 * kActBlkBytes;      // two slots of [x block | skip block], two bf16 output blocks
   return conv_umma2_raw_slots(raw_mode, residual) * conv_umma2_raw_blk(raw_f16) +
          (act_mode == 1 ? 2 * kActBlkBytes * (act_split ? 2 : 1) : 0);
 }
 
 __host__ __device__ inline size_t conv_umma2_smem_bytes(const ConvParams2& p) {
   return 1024 + 1024 + static_cast<size_t>(p.SA) * p.nbox * p.RB * 128 + static_cast<size_t>(p.SB) * p.NT * 128 +
-         8 * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, p.residual != nullptr, p.raw_f16, p.act_split);
+         8 * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, p.residual != nullptr, p.raw_f16, p.act_split, p.bwd);
 }
 
 __global__ void __launch_bounds__(384, 1)
@@ -134,13 +149,13 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmW);
-    if (p.raw_mode == 1) ptx::prefetch_tmap(&tmR);
+    if (p.raw_mode == 1 || p.bwd_skip) ptx::prefetch_tmap(&tmR);
     if (p.act_mode == 1) ptx::prefetch_tmap(&tmO);
     for (int i = 0; i < p.SA; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.SB; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 8); }
     for (int i = 0; i < 24; ++i) ptx::mbar_init(&res_full[i], 1);
-    if (p.residual) ptx::prefetch_tmap(&tmX);
+    if (p.residual || p.bwd) ptx::prefetch_tmap(&tmX);
     ptx::fence_mbar_init();
   }
   ptx::pdl_launch_dependents();
@@ -286,10 +301,11 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     const int g = e >> 2;              // item parity handled by this warp
     const int quad = warp & 3;         // TMEM lane quadrant = rows quad*32 .. +31 of a 128-row sub-tile
     const int T_out = p.Tq_out * p.P_out;
-    const bool has_res = p.residual != nullptr;
-    const int R = conv_umma2_raw_slots(p.raw_mode, has_res);
-    const int rawblk = conv_umma2_raw_blk(p.raw_f16);
-    uint8_t* raw_ring = stage_base + e * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, has_res, p.raw_f16, p.act_split);
+    const bool has_res = p.residual != nullptr || p.bwd;
+    const int R = p.bwd ? 2 : conv_umma2_raw_slots(p.raw_mode, has_res);
+    const int rawblk = p.bwd ? 2 * kActBlkBytes : conv_umma2_raw_blk(p.raw_f16);
+    const uint32_t res_tx = p.bwd ? (p.bwd_skip ? 2 * kActBlkBytes : kActBlkBytes) : rawblk;   // bytes one item's loads deliver
+    uint8_t* raw_ring = stage_base + e * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, has_res, p.raw_f16, p.act_split, p.bwd);
     uint8_t* act_ring = raw_ring + R * rawblk;
     uint64_t* my_res_full = res_full + e * 3;
     // An item is one 32-row x 32-channel output block.  swap = 0: TMEM lane = time row, so a thread owns one
@@ -297,8 +313,8 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // channel x 32 rows (scalar accesses into the same swizzled blocks; per-channel constants live in registers).
     const int ipt = p.swap ? 4 * p.MT : p.MT * (p.NT >> 5);
     // fragment-mapped fast path of the swap orientation (inference plans in bf16 mode: fp16 stream, bf16 operand)
-    const bool frag = p.swap && !p.no_frag && !p.act_split && !p.precise && p.raw_mode != 2 &&
-                      (p.raw_f16 || (p.raw_mode == 0 && !has_res));
+    const bool frag = p.swap && !p.act_split && !p.precise && p.raw_mode != 2 &&
+                      (p.bwd || (!p.no_frag && (p.raw_f16 || (p.raw_mode == 0 && !has_res))));
     // ldmatrix / stmatrix: this lane addresses row (lane & 7) of matrix (lane >> 3) inside a 16-row half of a
     // [32 rows x 64 B] SWIZZLE_64B block (lane half 1: address ^ 32, rows 16..31: + 1024)
     const int frag_row = ((lane >> 4) << 3) + (lane & 7);
@@ -320,9 +336,12 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (has_res && lane == 0 && static_cast<int>(blockIdx.x) < p.total_tiles && g < ipt) {
       int cb, ph, r0, bb;
       coords(blockIdx.x, g, cb, ph, r0, bb);
-      ptx::mbar_expect_tx(&my_res_full[0], rawblk);
+      ptx::mbar_expect_tx(&my_res_full[0], res_tx);
       ptx::tma_load_4d(raw_ring, &tmX, &my_res_full[0], cb, ph, r0, bb);
+      if (p.bwd_skip) ptx::tma_load_4d(raw_ring + kActBlkBytes, &tmR, &my_res_full[0], cb, ph, r0, bb);
     }
+    float bw_a[4] = {0.f, 0.f, 0.f, 0.f}, bw_ib[4] = {0.f, 0.f, 0.f, 0.f};          // bwd mode: this thread's 4 channels
+    float acc_da[4] = {0.f, 0.f, 0.f, 0.f}, acc_db[4] = {0.f, 0.f, 0.f, 0.f}, acc_bias[4] = {0.f, 0.f, 0.f, 0.f};
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int b, q0, phi, n0;
       decode(tile, b, q0, phi, n0);
@@ -339,6 +358,14 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             fsa[i] = ptx::f2_pack(a, a);
             fsib[i] = ptx::f2_pack(ib, ib);
           }
+        }
+      }
+      if (p.bwd) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = n0 + quad * 32 + (i >> 1) * 16 + (i & 1) * 8 + (lane >> 2);
+          bw_a[i] = __ldg(p.bwd_a + c);
+          bw_ib[i] = __ldg(p.bwd_inv_b + c);
         }
       }
       float bias_s = 0.f, sa_s = 1.f, sib_s = 0.f;
@@ -372,9 +399,10 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             if (nt < p.total_tiles && ni < ipt) {
               int cb, ph, rr, bb;
               coords(nt, ni, cb, ph, rr, bb);
-              const int sn = (jr + 1) % 3;
-              ptx::mbar_expect_tx(&my_res_full[sn], rawblk);
+              const int sn = (jr + 1) % R;
+              ptx::mbar_expect_tx(&my_res_full[sn], res_tx);
               ptx::tma_load_4d(raw_ring + sn * rawblk, &tmX, &my_res_full[sn], cb, ph, rr, bb);
+              if (p.bwd_skip) ptx::tma_load_4d(raw_ring + sn * rawblk + kActBlkBytes, &tmR, &my_res_full[sn], cb, ph, rr, bb);
             }
           }
           ptx::mbar_wait(&my_res_full[jr], (res_ph >> jr) & 1u);
@@ -394,6 +422,57 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           ptx::tmem_ld_16x256b_x4(acc_tmem + tcol + (16u << 16), r + 16);
           uint32_t sk[16];                                   // sk[8 L + 4 m + j]: rows 16 m + 8 (j >> 1) .., channel group 2 L + (j & 1)
           const uint32_t rb = ptx::smem_u32(rblk) + frag_lane;
+          if (p.bwd) {
+            // ---- fused SnakeBeta backward (see ConvParams2::bwd): x block at rb, skip-gradient block behind it
+            uint32_t gs[16];
+#pragma unroll
+            for (int L = 0; L < 2; ++L)
+#pragma unroll
+              for (int m = 0; m < 2; ++m) {
+                ptx::ldmatrix_x4_trans((rb + m * 1024) ^ (L * 32u), sk[8 * L + 4 * m], sk[8 * L + 4 * m + 1],
+                                       sk[8 * L + 4 * m + 2], sk[8 * L + 4 * m + 3]);
+                if (p.bwd_skip)
+                  ptx::ldmatrix_x4_trans((rb + kActBlkBytes + m * 1024) ^ (L * 32u), gs[8 * L + 4 * m], gs[8 * L + 4 * m + 1],
+                                         gs[8 * L + 4 * m + 2], gs[8 * L + 4 * m + 3]);
+              }
+            ptx::tmem_ld_wait();
+            uint32_t w[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const int L = q >> 3, ci = 2 * L + (q & 1);
+              const int ri = 16 * L + 4 * (2 * ((q >> 2) & 1) + ((q >> 1) & 1)) + 2 * (q & 1);
+              const float2 xf = __half22float2(*reinterpret_cast<const __half2*>(&sk[q]));
+              float d0 = __uint_as_float(r[ri]), d1 = __uint_as_float(r[ri + 1]);
+              // rows past the end of the clip hold whatever the taps that still reach valid input produced: the TMA store
+              // clips them, the column sums must not see them
+              const int trow = r0 + 8 * (2 * ((q >> 2) & 1) + ((q >> 1) & 1)) + 2 * (lane & 3);
+              if (trow >= p.Tq_out) d0 = 0.f;
+              if (trow + 1 >= p.Tq_out) d1 = 0.f;
+              const float t0 = bw_a[ci] * xf.x, t1 = bw_a[ci] * xf.y;
+              const float sn0 = __sinf(t0), cs0 = __cosf(t0), sn1 = __sinf(t1), cs1 = __cosf(t1);
+              const float s20 = 2.f * sn0 * cs0, s21 = 2.f * sn1 * cs1;
+              acc_da[ci] = fmaf(d0 * xf.x, s20, fmaf(d1 * xf.y, s21, acc_da[ci]));
+              acc_db[ci] = fmaf(d0, sn0 * sn0, fmaf(d1, sn1 * sn1, acc_db[ci]));
+              const float k = bw_ib[ci] * bw_a[ci];
+              d0 *= fmaf(k, s20, 1.f);
+              d1 *= fmaf(k, s21, 1.f);
+              if (p.bwd_skip) {
+                const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gs[q]));
+                d0 += gf.x;
+                d1 += gf.y;
+              }
+              acc_bias[ci] += d0 + d1;
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(d0, d1);
+              w[q] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
+            const uint32_t ab = ptx::smem_u32(ablk) + frag_lane;
+#pragma unroll
+            for (int L = 0; L < 2; ++L)
+#pragma unroll
+              for (int m = 0; m < 2; ++m)
+                ptx::stmatrix_x4_trans((ab + m * 1024) ^ (L * 32u), w[8 * L + 4 * m], w[8 * L + 4 * m + 1],
+                                       w[8 * L + 4 * m + 2], w[8 * L + 4 * m + 3]);
+          } else {
           if (has_res) {
 #pragma unroll
             for (int L = 0; L < 2; ++L)
@@ -454,6 +533,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 ptx::stmatrix_x4_trans((ab + m * 1024) ^ (L * 32u), w[8 * L + 4 * m], w[8 * L + 4 * m + 1],
                                        w[8 * L + 4 * m + 2], w[8 * L + 4 * m + 3]);
           }
+          }   // !bwd
         } else {
         uint32_t r[32];
         __syncwarp();
@@ -657,6 +737,26 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           }
           if (R > 0) jr = (jr + 1 == R) ? 0 : jr + 1;
           ja ^= 1;
+        }
+      }
+      if (p.bwd) {
+        // per-channel sums of this tile: the four lanes that share a channel (lane & 3 = time columns) combine, then
+        // one atomic per channel, warp and tile
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float va = acc_da[i], vb = acc_db[i], vc = acc_bias[i];
+          va += __shfl_xor_sync(0xffffffffu, va, 1); va += __shfl_xor_sync(0xffffffffu, va, 2);
+          vb += __shfl_xor_sync(0xffffffffu, vb, 1); vb += __shfl_xor_sync(0xffffffffu, vb, 2);
+          vc += __shfl_xor_sync(0xffffffffu, vc, 1); vc += __shfl_xor_sync(0xffffffffu, vc, 2);
+          if ((lane & 3) == 0) {
+            const int c = n0 + quad * 32 + (i >> 1) * 16 + (i & 1) * 8 + (lane >> 2);
+            const float ib = bw_ib[i], a = bw_a[i];
+            const float eb = 1.f / ib - 1e-9f;                      // exp(beta)
+            atomicAdd(p.d_alpha + c, va * ib * (p.bwd_logscale ? a : 1.f));
+            atomicAdd(p.d_beta + c, -vb * ib * ib * (p.bwd_logscale ? eb : 1.f));
+            if (p.d_bias) atomicAdd(p.d_bias + c, vc);
+          }
+          acc_da[i] = 0.f; acc_db[i] = 0.f; acc_bias[i] = 0.f;
         }
       }
       // accumulator buffer fully read: hand it back to the UMMA issuer

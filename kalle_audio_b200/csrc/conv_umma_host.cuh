@@ -222,6 +222,12 @@ struct ConvEpilogue {
   int split3 = 0;         // x is [B, T, 2*Cin] (hi | lo), wpacked is [K][Cout][2*Cin]
   int act_split = 0;      // out_act is [B, T, 2*Cout] (hi | lo)
   int precise = 0;        // sinf instead of MUFU sin in the fused SnakeBeta
+  // training backward (ConvParams2::bwd): SnakeBeta derivative of the previous layer + skip-gradient add in the epilogue
+  const void* bwd_x = nullptr;        // that layer's saved stream, fp16 channels-last, same shape as this conv's output
+  const void* bwd_skip = nullptr;     // bf16 gradient arriving through the skip connection, or nullptr
+  const float* bwd_a = nullptr;
+  const float* bwd_inv_b = nullptr;
+  int bwd_logscale = 1;
 };
 
 struct ConvTuning {
@@ -376,8 +382,19 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
   p.precise = ep.precise ? 1 : 0;
   p.Cin = g.Cin;
   const int sdt = ep.stream_f16 ? 2 : 1;     // element type of the stream tensor maps
+  if (ep.bwd_x) {
+    if (!ep.out_act || ep.out_raw || ep.residual || ep.split3 || !ep.bwd_a || !ep.bwd_inv_b || g.Cout % 128) {
+      err = "fused SnakeBeta backward needs a bf16-only output and 128-channel tiles";
+      return false;
+    }
+    p.bwd = 1;
+    p.bwd_skip = ep.bwd_skip ? 1 : 0;
+    p.bwd_logscale = ep.bwd_logscale;
+    p.bwd_a = ep.bwd_a;
+    p.bwd_inv_b = ep.bwd_inv_b;
+  }
   const size_t stage = 8 * static_cast<size_t>(conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, ep.residual != nullptr,
-                                                                                p.raw_f16, p.act_split));
+                                                                                p.raw_f16, p.act_split, p.bwd));
   const size_t budget = 227 * 1024 - 2048 - stage;
   // candidate tilings, best first: double-buffered accumulators when they fit the 512 TMEM columns
   struct Cand { int MT, NT, acc; };
@@ -467,6 +484,11 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
   else L.tmO = L.tmA;
   if (ep.residual) { if (!make_out_tmap(&L.tmX, ep.residual, B, T_out, g.Cout, tp.P_out, sdt, err, 32, sg ? sg->res_pitch : 0)) return false; }
   else L.tmX = L.tmA;
+  if (p.bwd) {
+    if (!p.swap) { err = "fused SnakeBeta backward needs the swap orientation"; return false; }
+    if (!make_out_tmap(&L.tmX, ep.bwd_x, B, T_out, g.Cout, tp.P_out, 2, err)) return false;
+    if (ep.bwd_skip && !make_out_tmap(&L.tmR, ep.bwd_skip, B, T_out, g.Cout, tp.P_out, 0, err)) return false;
+  }
   const int ctas = tune.max_ctas ? tune.max_ctas : sm_count();
   L.grid = std::min(p.total_tiles, ctas);
   L.smem = conv_umma2_smem_bytes(p);

@@ -170,6 +170,7 @@ struct PreparedRun {
     bool has_sb = false;
     SnakeBwdParams sb;
     dim3 sb_grid;
+    bool sb_fused = false;          // the SnakeBeta backward of this step runs in the epilogue of dg_umma (ConvParams2::bwd)
   };
   std::vector<Bwd> bwd;
   SnakeBwdParams sb_last;           // bf16 copy + bias gradient of the incoming output gradient
@@ -1216,6 +1217,27 @@ bool prepare_backward(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R
       sb.C = c.g.Cin;
       sb.fast = (p->precision == KVAE_PREC_BF16) ? 1 : 0;
       set_sb_grid(sb, bw.sb_grid);
+      // Fuse this pass into the data-gradient conv's epilogue when its only product is the bf16 gradient: tensor-core
+      // dgrad with 128-channel tiles, fp16 saved stream, bf16 skip gradient (or none), no fp32 copy of G wanted.
+      // KVAE_BWD_FUSE_SNAKE=0: separate pass (A/B).
+      static const bool no_fuse = [] { const char* e = getenv("KVAE_BWD_FUSE_SNAKE"); return e && e[0] == '0'; }();
+      if (!no_fuse && bw.dgrad_kind == 1 && da_bf16 && sb.a && sb.x_f16 && !sb.G && sb.Gb && (!sb.skip || sb.skip_bf16) &&
+          gd.Cout % 128 == 0) {
+        ConvEpilogue ep;
+        ep.out_act = sb.Gb;
+        ep.bwd_x = sb.x;
+        ep.bwd_skip = sb.skip;
+        ep.bwd_a = sb.a;
+        ep.bwd_inv_b = sb.inv_b;
+        ep.bwd_logscale = sb.logscale;
+        ConvTuning2 tune;
+        ConvLaunch2 fused;
+        std::string ferr;
+        if (prepare_conv_umma2(gd, Gb(k), B, static_cast<int>(T_out), c.w_umma_d, ep, tune, fused, ferr)) {
+          bw.dg_umma = fused;
+          bw.sb_fused = true;
+        }
+      }
     }
   }
   return true;
@@ -1294,6 +1316,12 @@ int run_backward(kvae_plan* p, const void* x, int x_dtype, const void* gy, int g
     } else if (bw.dgrad_kind == 1) {
       ConvLaunch2& L = bw.dg_umma;
       if (k == 0) { L.p.out_cf = gx; L.p.out_cf_f32 = (gx_dtype == KVAE_F32); }
+      if (bw.sb_fused) {
+        const ConvLayer& cp = p->convs[steps[k - 1].conv];
+        L.p.d_alpha = grads + p->snakes[s.pre_snake].off_alpha;
+        L.p.d_beta = grads + p->snakes[s.pre_snake].off_beta;
+        L.p.d_bias = cp.has_bias ? grads + cp.off_bias : nullptr;
+      }
       KV_CUDA(launch_conv_umma2(L, st));
     } else {
       DirectParams& d = bw.dg_direct;
@@ -1301,7 +1329,7 @@ int run_backward(kvae_plan* p, const void* x, int x_dtype, const void* gy, int g
       KV_CUDA(launch_direct(d, bw.dg_grid, bw.dg_cfg, bw.dg_smem, st));
     }
     ++g_launches;
-    if (bw.has_sb) {
+    if (bw.has_sb && !bw.sb_fused) {
       SnakeBwdParams sb = bw.sb;
       const ConvLayer& cp = p->convs[steps[k - 1].conv];
       if (s.pre_snake >= 0) {

@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu launch list of the training step (last of 3 steps), default and KVAE_BWD_DA_F32=1; prints per-kernel totals
 mkdir -p gpurun_out
-for mode in bf16 f32; do
+for mode in bf16; do
   if [ $mode = f32 ]; then export KVAE_BWD_DA_F32=1; else unset KVAE_BWD_DA_F32; fi
   ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/train_launches_$mode.csv python tools/prof_train.py 4 3 > gpurun_out/ncu_train_$mode.log 2>&1; echo "exit $?"
   python - $mode <<'PY'
