@@ -57,8 +57,11 @@ def test_cpu_tensors_fail_loudly():
 def test_unsupported_variants_raise():
     with pytest.raises(NotImplementedError):
         k.OobleckDecoder(use_snake=False)
-    with pytest.raises(NotImplementedError):
-        k.OobleckDecoder(use_snake=True, use_nearest_upsample=True)
+    # use_nearest_upsample=True is built (autoencoders.py:87-96): same module tree / keys as the reference
+    d = k.OobleckDecoder(out_channels=2, channels=8, latent_dim=4, c_mults=[1, 2], strides=[2, 5], use_snake=True,
+                         use_nearest_upsample=True)
+    assert "layers.1.layers.1.1.weight_v" in d.state_dict() and "layers.1.layers.1.1.bias" not in d.state_dict()
+    assert d.state_dict()["layers.1.layers.1.1.weight_v"].shape == (8, 16, 10)        # k = 2 * stride, 'same' padding
     with pytest.raises(NotImplementedError):
         k.OobleckEncoder(use_snake=True, antialias_activation=True)
     with pytest.raises(NotImplementedError):
