@@ -53,6 +53,7 @@ struct ConvParams2 {
   int out_cf_f32;
   int act_mode;            // 0 none, 1 bf16 channels-last via TMA (tmO)
   int one_producer;        // 1: activation and weight slabs requested by one thread in one FIFO (A/B switch)
+  int park;                // 1: epilogue warps wait with the barrier unit's suspend hint instead of a spin loop (KVAE_PARK)
   int no_frag;             // 1: scalar swap epilogue even where the fragment-mapped one applies (A/B switch, KVAE_FRAG_EPI=0)
   int split3;              // fp32-mode arithmetic on the tensor cores: both operands are stored as bf16 (hi | lo)
                            // halves -- activations [.., 2*Cin], weights [tap][Cout][2*Cin] -- and every K chunk is
@@ -374,7 +375,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (p.bias) bias_s = __ldg(p.bias + c);
         if (p.snake_a) { sa_s = __ldg(p.snake_a + c); sib_s = __ldg(p.snake_inv_b + c); }
       }
-      ptx::mbar_wait(&t_full[acc], accph);
+      if (p.park) ptx::mbar_wait_parked(&t_full[acc], accph); else ptx::mbar_wait(&t_full[acc], accph);
       ptx::tc_fence_after();
       const uint32_t acc_tmem = tmem_base + acc * acc_cols + (static_cast<uint32_t>(quad * 32) << 16);
       for (int item = g; item < ipt; item += 2) {
@@ -405,7 +406,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (p.bwd_skip) ptx::tma_load_4d(raw_ring + sn * rawblk + kActBlkBytes, &tmR, &my_res_full[sn], cb, ph, rr, bb);
             }
           }
-          ptx::mbar_wait(&my_res_full[jr], (res_ph >> jr) & 1u);
+          if (p.park) ptx::mbar_wait_parked(&my_res_full[jr], (res_ph >> jr) & 1u); else ptx::mbar_wait(&my_res_full[jr], (res_ph >> jr) & 1u);
           res_ph ^= (1u << jr);
         }
         uint8_t* const rblk = raw_ring + jr * rawblk;
