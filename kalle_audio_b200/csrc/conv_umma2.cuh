@@ -53,7 +53,8 @@ struct ConvParams2 {
   int out_cf_f32;
   int act_mode;            // 0 none, 1 bf16 channels-last via TMA (tmO)
   int one_producer;        // 1: activation and weight slabs requested by one thread in one FIFO (A/B switch)
-  int park;                // 1: epilogue warps wait with the barrier unit's suspend hint instead of a spin loop (KVAE_PARK)
+  int park;                // waits that use the barrier unit's suspend hint instead of a spin loop (KVAE_PARK): bit 0 epilogue
+                           // warps (t_full, skip blocks), bit 1 TMA producers (a_empty, b_empty), bit 2 the MMA thread's t_empty
   int no_frag;             // 1: scalar swap epilogue even where the fragment-mapped one applies (A/B switch, KVAE_FRAG_EPI=0)
   int split3;              // fp32-mode arithmetic on the tensor cores: both operands are stored as bf16 (hi | lo)
                            // halves -- activations [.., 2*Cin], weights [tap][Cout][2*Cin] -- and every K chunk is
@@ -213,7 +214,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           for (int t = t_lo; t < t_hi; ++t) {
             const uint32_t tl = p.tap_ld[t];
             if (do_a && (p.tap_mma[t] & 0x10000u)) {
-              ptx::mbar_wait(&a_empty[as], aph ^ 1u);
+              if (p.park & 2) ptx::mbar_wait_parked(&a_empty[as], aph ^ 1u); else ptx::mbar_wait(&a_empty[as], aph ^ 1u);
               ptx::mbar_expect_tx(&a_full[as], a_bytes);
               const int row = q0 + (static_cast<int32_t>(tl) >> 16);
               for (int bx = 0; bx < p.nbox; ++bx)
@@ -222,7 +223,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (++as == p.SA) { as = 0; aph ^= 1u; }
             }
             if (do_w) {
-              ptx::mbar_wait(&b_empty[bs], bph ^ 1u);
+              if (p.park & 2) ptx::mbar_wait_parked(&b_empty[bs], bph ^ 1u); else ptx::mbar_wait(&b_empty[bs], bph ^ 1u);
               ptx::mbar_expect_tx(&b_full[bs], b_bytes);
               ptx::tma_load_3d(b_ring + static_cast<size_t>(bs) * b_bytes, &tmW, &b_full[bs], w_col, n0,
                                (tl >> 8) & 0xff);
@@ -249,7 +250,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int phi = (tile / p.n_tiles) % p.P_out;
         const int t_lo = p.tap_begin[phi], t_hi = p.tap_begin[phi + 1];
-        ptx::mbar_wait(&t_empty[acc], accph ^ 1u);   // epilogue has drained this accumulator buffer
+        if (p.park & 4) ptx::mbar_wait_parked(&t_empty[acc], accph ^ 1u); else ptx::mbar_wait(&t_empty[acc], accph ^ 1u);   // epilogue has drained this accumulator buffer
         ptx::tc_fence_after();
         const uint32_t d0 = tmem_base + acc * acc_cols;
         const uint32_t d1 = d0 + p.NT;
@@ -375,7 +376,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (p.bias) bias_s = __ldg(p.bias + c);
         if (p.snake_a) { sa_s = __ldg(p.snake_a + c); sib_s = __ldg(p.snake_inv_b + c); }
       }
-      if (p.park) ptx::mbar_wait_parked(&t_full[acc], accph); else ptx::mbar_wait(&t_full[acc], accph);
+      if (p.park & 1) ptx::mbar_wait_parked(&t_full[acc], accph); else ptx::mbar_wait(&t_full[acc], accph);
       ptx::tc_fence_after();
       const uint32_t acc_tmem = tmem_base + acc * acc_cols + (static_cast<uint32_t>(quad * 32) << 16);
       for (int item = g; item < ipt; item += 2) {
@@ -406,7 +407,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
               if (p.bwd_skip) ptx::tma_load_4d(raw_ring + sn * rawblk + kActBlkBytes, &tmR, &my_res_full[sn], cb, ph, rr, bb);
             }
           }
-          if (p.park) ptx::mbar_wait_parked(&my_res_full[jr], (res_ph >> jr) & 1u); else ptx::mbar_wait(&my_res_full[jr], (res_ph >> jr) & 1u);
+          if (p.park & 1) ptx::mbar_wait_parked(&my_res_full[jr], (res_ph >> jr) & 1u); else ptx::mbar_wait(&my_res_full[jr], (res_ph >> jr) & 1u);
           res_ph ^= (1u << jr);
         }
         uint8_t* const rblk = raw_ring + jr * rawblk;

@@ -378,7 +378,7 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
   p.split3 = ep.split3 ? 1 : 0;
   if (const char* e = getenv("KVAE_SPLIT_PRODUCER")) p.one_producer = atoi(e) ? 0 : 1;
   if (const char* e = getenv("KVAE_FRAG_EPI")) p.no_frag = atoi(e) ? 0 : 1;
-  if (const char* e = getenv("KVAE_PARK")) p.park = atoi(e) ? 1 : 0;
+  if (const char* e = getenv("KVAE_PARK")) p.park = atoi(e);
   p.act_split = (ep.act_split && ep.out_act) ? 1 : 0;
   p.precise = ep.precise ? 1 : 0;
   p.Cin = g.Cin;
