@@ -55,6 +55,8 @@ struct ConvParams2 {
   int one_producer;        // 1: activation and weight slabs requested by one thread in one FIFO (A/B switch)
   int park;                // waits that use the barrier unit's suspend hint instead of a spin loop (KVAE_PARK): bit 0 epilogue
                            // warps (t_full, skip blocks), bit 1 TMA producers (a_empty, b_empty), bit 2 the MMA thread's t_empty
+  int fast;                // 1: conv_umma2_kernel<1> -- 16 epilogue warps on 16-row x 32-channel items (forward, swap orientation,
+                           //    2-byte stream / operand blocks only; see the kFast branch of the kernel)
   int no_frag;             // 1: scalar swap epilogue even where the fragment-mapped one applies (A/B switch, KVAE_FRAG_EPI=0)
   int split3;              // fp32-mode arithmetic on the tensor cores: both operands are stored as bf16 (hi | lo)
                            // halves -- activations [.., 2*Cin], weights [tap][Cout][2*Cin] -- and every K chunk is
@@ -106,6 +108,7 @@ __device__ __forceinline__ void fused_sigma_sample(const ConvParams2& p, int b, 
 
 constexpr int kRawBlkBytes = 32 * 128;   // 32 rows x 32 fp32, SWIZZLE_128B
 constexpr int kActBlkBytes = 32 * 64;    // 32 rows x 32 bf16 (or fp16 stream), SWIZZLE_64B
+constexpr int kFastBlk = 16 * 64;        // conv_umma2_kernel<1>: 16 rows x 32 bf16 / fp16, SWIZZLE_64B
 __host__ __device__ inline int conv_umma2_raw_blk(int raw_f16) { return raw_f16 ? kActBlkBytes : kRawBlkBytes; }
 // per-epilogue-warp staging: a ring of fp32 blocks (3 deep when the skip connection is prefetched into
 // it, else 2) and two bf16 blocks; only what a layer needs is carved out
@@ -113,7 +116,8 @@ __host__ __device__ inline int conv_umma2_raw_slots(int raw_mode, bool residual)
   return (raw_mode == 1 || residual) ? (residual ? 3 : 2) : 0;
 }
 __host__ __device__ inline int conv_umma2_stage_bytes_per_warp(int raw_mode, int act_mode, bool residual, int raw_f16,
-                                                               int act_split = 0, int bwd = 0) {
+                                                               int act_split = 0, int bwd = 0, int fast = 0) {
+  if (fast) return conv_umma2_raw_slots(raw_mode, residual) * kFastBlk + (act_mode == 1 ? 2 * kFastBlk : 0);
   if (bwd) return 2 * (2 * kActBlkBytes) + 2 * kActBlkBytes;      // two slots of [x block | skip block], two bf16 output blocks
   return conv_umma2_raw_slots(raw_mode, residual) * conv_umma2_raw_blk(raw_f16) +
          (act_mode == 1 ? 2 * kActBlkBytes * (act_split ? 2 : 1) : 0);
@@ -121,10 +125,12 @@ __host__ __device__ inline int conv_umma2_stage_bytes_per_warp(int raw_mode, int
 
 __host__ __device__ inline size_t conv_umma2_smem_bytes(const ConvParams2& p) {
   return 1024 + 1024 + static_cast<size_t>(p.SA) * p.nbox * p.RB * 128 + static_cast<size_t>(p.SB) * p.NT * 128 +
-         8 * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, p.residual != nullptr, p.raw_f16, p.act_split, p.bwd);
+         (p.fast ? 16 : 8) * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, p.residual != nullptr, p.raw_f16,
+                                                             p.act_split, p.bwd, p.fast);
 }
 
-__global__ void __launch_bounds__(384, 1)
+template <int kFast>
+__global__ void __launch_bounds__(kFast ? 640 : 384, 1)
 conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO,
                   const __grid_constant__ CUtensorMap tmX, const __grid_constant__ ConvParams2 p) {
@@ -138,7 +144,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   uint64_t* t_full = a_full + 48;    // [2] accumulator ready
   uint64_t* t_empty = a_full + 50;   // [2] accumulator drained (8 epilogue warps arrive)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_full + 52);
-  uint64_t* res_full = a_full + 56;  // [8 warps][3 slots] skip-connection block landed
+  uint64_t* res_full = a_full + 56;  // [8 or 16 warps][3 slots] skip-connection block landed
   uint8_t* a_ring = smem + 1024;
   const uint32_t a_bytes = static_cast<uint32_t>(p.nbox) * p.RB * 128;
   const uint32_t b_bytes = static_cast<uint32_t>(p.NT) * 128;
@@ -155,8 +161,8 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (p.act_mode == 1) ptx::prefetch_tmap(&tmO);
     for (int i = 0; i < p.SA; ++i) { ptx::mbar_init(&a_full[i], 1); ptx::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < p.SB; ++i) { ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], 8); }
-    for (int i = 0; i < 24; ++i) ptx::mbar_init(&res_full[i], 1);
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&t_full[i], 1); ptx::mbar_init(&t_empty[i], kFast ? 16 : 8); }
+    for (int i = 0; i < (kFast ? 48 : 24); ++i) ptx::mbar_init(&res_full[i], 1);
     if (p.residual || p.bwd) ptx::prefetch_tmap(&tmX);
     ptx::fence_mbar_init();
   }
@@ -297,6 +303,140 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (++acc == p.acc_stages) { acc = 0; accph ^= 1u; }
       }
     }
+  } else if (warp >= 4 && kFast) {
+    // ------------------------------------------------------------ epilogue, kFast: 16 warps (4 per TMEM lane quadrant) on
+    // 16-row x 32-channel items -- the EPI2 mapping of conv_ru2.cuh.  The generic epilogue below spends ~860 warp
+    // instructions per 32 x 32 item, most of them control (integer divisions for the prefetch coordinates, generic ->
+    // shared address conversions, ring geometry recomputed per item, run-time mode branches) executed as one dependent
+    // chain with two warps per scheduler (profiles/r02_k1_c256_B16.txt: the k = 1 / transposed / strided convs ran at the
+    // epilogue's item rate, 60 % of their HBM floor).  Here the tile decode happens once per tile, every address is a
+    // loop-invariant 32-bit shared-memory offset, and four warps per scheduler hide each other's latencies.
+    const int e = warp - 4, quad = warp & 3, sub = e >> 2;
+    const int g8 = lane >> 2, rr = lane & 7, mj = lane >> 3;
+    const bool has_res = p.residual != nullptr;
+    const bool raw_out = p.raw_mode == 1, act_out = p.act_mode == 1, has_snake = p.snake_a != nullptr;
+    const int R = conv_umma2_raw_slots(p.raw_mode, has_res);
+    uint8_t* ring = stage_base + e * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, has_res, 1, 0, 0, 1);
+    uint8_t* aring = ring + R * kFastBlk;
+    const int brow = (mj >> 1) * 8 + rr;     // ldmatrix / stmatrix: this lane addresses row brow of a [16 x 64 B] block
+    const uint32_t blk_lane = brow * 64 + (((mj & 1) ^ ((brow >> 1) & 3)) << 4);
+    const uint32_t ring_lane = ptx::smem_u32(ring) + blk_lane;
+    const uint32_t aring_lane = ring_lane + R * kFastBlk;
+    uint64_t* my_res_full = res_full + e * 3;
+    const int n_items = 8 * p.MT;            // 16-row items per quadrant and tile
+    const uint32_t acc_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
+    auto dup = [](float f) { return ptx::f2_pack(f, f); };
+    auto issue_skip = [&](int cb, int ph, int row, int bb, int slot) {   // lane 0 only
+      ptx::mbar_expect_tx(&my_res_full[slot], kFastBlk);
+      ptx::tma_load_4d(ring + slot * kFastBlk, &tmX, &my_res_full[slot], cb, ph, row, bb);
+    };
+    int tile = blockIdx.x;
+    int b = 0, q0 = 0, phi = 0, n0 = 0;
+    if (tile < p.total_tiles) decode(tile, b, q0, phi, n0);
+    if (has_res && lane == 0 && tile < p.total_tiles) issue_skip(n0 + quad * 32, phi, q0 + sub * 16, b, 0);
+    int acc = 0, jr = 0, ja = 0;
+    uint32_t accph = 0, res_ph = 0;
+    for (; tile < p.total_tiles; tile += gridDim.x) {
+      const int ntile = tile + gridDim.x;    // this CTA's next tile: its first skip block is prefetched during the last item
+      int nb = 0, nq0 = 0, nphi = 0, nn0 = 0;
+      if (ntile < p.total_tiles) decode(ntile, nb, nq0, nphi, nn0);
+      const int cbase = n0 + quad * 32;
+      uint64_t kb[4], ka[4], kib[4];         // index 2 * lane half + hi: channel cbase + 16 L + 8 hi + g8
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ch = cbase + (i >> 1) * 16 + (i & 1) * 8 + g8;
+        kb[i] = p.bias ? dup(__ldg(p.bias + ch)) : 0ull;
+        ka[i] = has_snake ? dup(__ldg(p.snake_a + ch)) : 0ull;
+        kib[i] = has_snake ? dup(__ldg(p.snake_inv_b + ch)) : 0ull;
+      }
+      ptx::mbar_wait_parked(&t_full[acc], accph);
+      ptx::tc_fence_after();
+      const uint32_t acc_tmem = acc_lane + acc * acc_cols;
+#pragma unroll 1
+      for (int item = sub; item < n_items; item += 4) {
+        const int r0 = q0 + item * 16;
+        const int sn = (jr + 1 == R) ? 0 : jr + 1;
+        if (lane == 0) {
+          // all but the newest store group have read their blocks: slot sn (last used two items ago) and the other
+          // operand block are free; fetch the NEXT item's skip block
+          ptx::bulk_wait_read<1>();
+          if (has_res) {
+            if (item + 4 < n_items) issue_skip(cbase, phi, r0 + 64, b, sn);
+            else if (ntile < p.total_tiles) issue_skip(nn0 + quad * 32, nphi, nq0 + sub * 16, nb, sn);
+          }
+        }
+        uint32_t r[16], sk[8];
+        __syncwarp();
+        const uint32_t t2 = acc_tmem + item * 16;
+        ptx::tmem_ld_16x256b_x2(t2, r);
+        ptx::tmem_ld_16x256b_x2(t2 + (16u << 16), r + 8);
+        const uint32_t rb = ring_lane + jr * kFastBlk;
+        if (has_res) {
+          ptx::mbar_wait_parked(&my_res_full[jr], (res_ph >> jr) & 1u);
+          res_ph ^= (1u << jr);
+          ptx::ldmatrix_x4_trans(rb, sk[0], sk[1], sk[2], sk[3]);
+          ptx::ldmatrix_x4_trans(rb ^ 32u, sk[4], sk[5], sk[6], sk[7]);
+        }
+        ptx::tmem_ld_wait();
+        uint64_t v[8];                       // q = 4 L + 2 n + hi
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          v[q] = ptx::f2_add(ptx::f2_pack_u(r[2 * q], r[2 * q + 1]), kb[(q >> 2) * 2 + (q & 1)]);
+          if (has_res) {
+            const float2 sf = __half22float2(*reinterpret_cast<const __half2*>(&sk[q]));
+            v[q] = ptx::f2_add(v[q], ptx::f2_pack(sf.x, sf.y));
+          }
+        }
+        if (raw_out) {
+          uint32_t w[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float y0, y1;
+            ptx::f2_unpack(v[q], y0, y1);
+            w[q] = ptx::f2h2_sat(y0, y1);
+          }
+          ptx::stmatrix_x4_trans(rb, w[0], w[1], w[2], w[3]);
+          ptx::stmatrix_x4_trans(rb ^ 32u, w[4], w[5], w[6], w[7]);
+        }
+        if (act_out) {
+          uint32_t w[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float y0, y1;
+            if (has_snake) {
+              const int ci = (q >> 2) * 2 + (q & 1);
+              float t0, t1;
+              ptx::f2_unpack(ptx::f2_mul(v[q], ka[ci]), t0, t1);
+              const uint64_t sn2 = ptx::f2_pack(sin_fast(t0), sin_fast(t1));
+              ptx::f2_unpack(ptx::f2_fma(ptx::f2_mul(kib[ci], sn2), sn2, v[q]), y0, y1);
+            } else {
+              ptx::f2_unpack(v[q], y0, y1);
+            }
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
+            w[q] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+          const uint32_t ab = aring_lane + ja * kFastBlk;
+          ptx::stmatrix_x4_trans(ab, w[0], w[1], w[2], w[3]);
+          ptx::stmatrix_x4_trans(ab ^ 32u, w[4], w[5], w[6], w[7]);
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (raw_out) ptx::tma_store_4d(&tmR, ring + jr * kFastBlk, cbase, phi, r0, b);
+          if (act_out) ptx::tma_store_4d(&tmO, aring + ja * kFastBlk, cbase, phi, r0, b);
+          ptx::bulk_commit();                // (an empty group when only the skip block was consumed keeps the count uniform)
+        }
+        if (R > 0) jr = sn;
+        ja ^= 1;
+      }
+      // accumulator buffer fully read: hand it back to the UMMA issuer
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&t_empty[acc]);
+      if (++acc == p.acc_stages) { acc = 0; accph ^= 1u; }
+      b = nb; q0 = nq0; phi = nphi; n0 = nn0;
+    }
+    if (lane == 0) ptx::bulk_wait<0>();
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue: 8 independent warp pipelines
     const int e = warp - 4;            // epilogue warp index

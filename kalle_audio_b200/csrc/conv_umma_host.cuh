@@ -394,6 +394,7 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
     p.bwd_a = ep.bwd_a;
     p.bwd_inv_b = ep.bwd_inv_b;
   }
+  // (the 8-warp and 16-warp epilogues stage the same number of bytes per CTA: 16-row instead of 32-row blocks)
   const size_t stage = 8 * static_cast<size_t>(conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, ep.residual != nullptr,
                                                                                 p.raw_f16, p.act_split, p.bwd));
   const size_t budget = 227 * 1024 - 2048 - stage;
@@ -454,6 +455,11 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
     break;
   }
   if (!ok) { err = "no tiling fits shared memory"; return false; }
+  // conv_umma2_kernel<1>: forward launches in the swap orientation whose stream / operand blocks are 2-byte
+  static const bool fast_on = [] { const char* e = getenv("KVAE_FAST_EPI"); return !(e && e[0] == '0'); }();
+  p.fast = (fast_on && p.swap && !p.bwd && !p.act_split && !p.precise && !p.no_frag && p.raw_mode != 2 &&
+            (p.raw_f16 || (p.raw_mode == 0 && !ep.residual))) ? 1 : 0;
+  const int box_rows = p.fast ? 16 : 32;
   int cols = 32;
   while (cols < p.acc_stages * p.MT * p.NT) cols <<= 1;
   p.tmem_cols = cols;
@@ -477,13 +483,13 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
   const int kmul = p.split3 ? 2 : 1;
   if (!make_act_tmap(&L.tmA, x, B, T_in, g.Cin * kmul, tp.P_in, p.RB, err, sg ? sg->in_pitch : 0)) return false;
   if (!make_w_tmap(&L.tmW, wpacked, g.K, g.Cout, g.Cin * kmul, p.NT, err)) return false;
-  if (p.raw_mode == 1) { if (!make_out_tmap(&L.tmR, ep.out_raw, B, T_out, g.Cout, tp.P_out, sdt, err, 32, sg ? sg->raw_pitch : 0)) return false; }
+  if (p.raw_mode == 1) { if (!make_out_tmap(&L.tmR, ep.out_raw, B, T_out, g.Cout, tp.P_out, sdt, err, box_rows, sg ? sg->raw_pitch : 0)) return false; }
   else L.tmR = L.tmA;
   if (p.act_mode == 1) {
-    if (!make_out_tmap(&L.tmO, ep.out_act, B, T_out, g.Cout * (p.act_split ? 2 : 1), tp.P_out, false, err, 32, sg ? sg->act_pitch : 0)) return false;
+    if (!make_out_tmap(&L.tmO, ep.out_act, B, T_out, g.Cout * (p.act_split ? 2 : 1), tp.P_out, false, err, box_rows, sg ? sg->act_pitch : 0)) return false;
   }
   else L.tmO = L.tmA;
-  if (ep.residual) { if (!make_out_tmap(&L.tmX, ep.residual, B, T_out, g.Cout, tp.P_out, sdt, err, 32, sg ? sg->res_pitch : 0)) return false; }
+  if (ep.residual) { if (!make_out_tmap(&L.tmX, ep.residual, B, T_out, g.Cout, tp.P_out, sdt, err, box_rows, sg ? sg->res_pitch : 0)) return false; }
   else L.tmX = L.tmA;
   if (p.bwd) {
     if (!p.swap) { err = "fused SnakeBeta backward needs the swap orientation"; return false; }
@@ -523,11 +529,14 @@ inline cudaError_t launch_conv_umma2(const ConvLaunch2& L, cudaStream_t stream) 
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
   }
-  return launch_pdl(conv_umma2_kernel, dim3(L.grid), dim3(384), L.smem, stream, L.tmA, L.tmW, L.tmR, L.tmO, L.tmX, L.p);
+  if (L.p.fast)
+    return launch_pdl(conv_umma2_kernel<1>, dim3(L.grid), dim3(640), L.smem, stream, L.tmA, L.tmW, L.tmR, L.tmO, L.tmX, L.p);
+  return launch_pdl(conv_umma2_kernel<0>, dim3(L.grid), dim3(384), L.smem, stream, L.tmA, L.tmW, L.tmR, L.tmO, L.tmX, L.p);
 }
 
 // ------------------------------------------------------------------ fused ResidualUnit (conv_ru.cuh)

@@ -36,6 +36,8 @@ for name, mod, inp in (("decoder", m.decoder, z), ("encoder", m.encoder, x)):
         ms = a / N
         L.kvae_plan_conv_info(r.handle, i, C.byref(info))
         kind, cin, cout, K, s = info[0], info[1], info[2], info[3], info[4]
+        if os.environ.get("PROF_STEPS"):
+            print(f"    step {i:2d} kind {kind} C{cin}->{cout} k{K} s{s}  {ms:7.3f} ms  {q[1] / (ms * 1e-3 + 1e-12) / 1e12:7.0f} TFLOP/s")
         if ms < 0.005:
             cls = None          # second half of a fused unit
         elif min(cin, cout) <= 2:
