@@ -523,4 +523,85 @@ __global__ void __launch_bounds__(128) conv_wave_in_kernel(const WaveInParams p)
   }
 }
 
+// ---- encoder head on the tensor cores (bf16 mode, inference).  conv_wave_in_kernel issues 14 * CIN FMAs + SnakeBeta
+// per output element on the CUDA cores and ran at 36 % of its HBM floor (1.55 ms per 16 x 442 368 rows).  The k = 7
+// conv over CIN <= 2 channels is a K = 7 CIN <= 14 dot product per output, i.e. ONE tcgen05 K-chunk: this kernel writes
+// the im2col rows as a channels-last bf16 operand [B, T, 64] and conv_umma2_kernel<1> runs the layer as a k = 1 conv
+// with its usual epilogue (bias, fp16 stream, SnakeBeta -> bf16 operand).  Four 16-column blocks, column
+// jj = tap * CIN + channel inside a block (jj >= 7 CIN: zero):
+//   block 0  hi(x) x hi(w)      block 1  lo(x) x hi(w)      block 2  hi(x) x lo(w)      block 3  zero
+// with hi = bf16 rounding and lo = bf16(v - hi): the product is exact to 2^-16 relative (the lo x lo term), far
+// inside the bf16 rounding of the operand the layer writes.  Blocks past the im2col rows pack the weights
+// [Cout][64] in the same column order, so the pair stays one launch ahead of the conv.
+struct WaveInColParams {
+  const void* x;          // [B, CIN, T]
+  int x_f32;
+  __nv_bfloat16* col;     // [B, T, 64]
+  const float* w;         // [7][CIN][Cout] fp32 (folded weight-norm weights)
+  __nv_bfloat16* wp;      // [Cout][64]
+  int T, B, Cout, CIN;
+  int row_blocks;         // blocks that write im2col rows (kColRows rows each); the rest pack weights
+};
+
+constexpr int kColRows = 512;   // im2col rows per block
+
+__global__ void __launch_bounds__(256) wave_in_im2col_kernel(const WaveInColParams p) {
+  const int n = 7 * p.CIN;
+  if (static_cast<int>(blockIdx.x) >= p.row_blocks) {
+    // weight pack: one thread per (out-channel, column)
+    const int i = (blockIdx.x - p.row_blocks) * 256 + threadIdx.x;
+    if (i < p.Cout * 64) {
+      const int co = i >> 6, blk = (i >> 4) & 3, jj = i & 15;
+      float v = 0.f;
+      if (blk < 3 && jj < n) {
+        const float wv = __ldg(p.w + static_cast<size_t>(jj) * p.Cout + co);
+        const float hi = __bfloat162float(__float2bfloat16(wv));
+        v = (blk < 2) ? hi : wv - hi;
+      }
+      p.wp[i] = __float2bfloat16(v);
+    }
+    return;
+  }
+  constexpr int RS = kColRows + 6;
+  __shared__ float xs[3 * RS];     // channels 0 .. CIN-1, then a row of zeros for the padding columns
+  const int tiles_per_clip = (p.T + kColRows - 1) / kColRows;
+  const int b = blockIdx.x / tiles_per_clip, t0 = (blockIdx.x % tiles_per_clip) * kColRows;
+  for (int i = threadIdx.x; i < (p.CIN + 1) * RS; i += 256) {
+    const int c = i / RS, r = i - c * RS;
+    const int t = t0 - 3 + r;
+    xs[i] = (c < p.CIN && t >= 0 && t < p.T) ? ld_elem(p.x, (static_cast<size_t>(b) * p.CIN + c) * p.T + t, p.x_f32) : 0.f;
+  }
+  // two threads per row: thread h owns columns 8h .. 8h+7 of every block, i.e. 16 bytes of the hi block (written
+  // twice), 16 bytes of the lo block and 16 bytes of zeros -- a lane pair writes 32 contiguous bytes per store
+  const int h = threadIdx.x & 1;
+  int off[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int jj = 8 * h + q, k = jj / p.CIN, c = jj - k * p.CIN;
+    off[q] = jj < n ? c * RS + k : p.CIN * RS;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = threadIdx.x >> 1; r < kColRows; r += 128) {
+    const int t = t0 + r;
+    if (t >= p.T) continue;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float x0 = xs[off[2 * q] + r], x1 = xs[off[2 * q + 1] + r];
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(x0, x1);
+      const float2 hf = __bfloat1622float2(h2);
+      const __nv_bfloat162 l2 = __floats2bfloat162_rn(x0 - hf.x, x1 - hf.y);
+      hi[q] = *reinterpret_cast<const uint32_t*>(&h2);
+      lo[q] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    uint4* row = reinterpret_cast<uint4*>(p.col + (static_cast<size_t>(b) * p.T + t) * 64) + h;
+    const uint4 hv = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    row[0] = hv;
+    row[2] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    row[4] = hv;
+    row[6] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 }  // namespace kvae

@@ -82,6 +82,7 @@ struct ConvLayer {
   bool umma32 = false;                // fp32 mode, inference only: tensor-core layer through the bf16x3 split
   __nv_bfloat16* w_umma = nullptr;    // [K][Cout][Cin] bf16: forward tensor-core operand ([K][Cout][2*Cin] hi|lo with umma32)
   float* w_direct = nullptr;          // [K][Cin][Cout] fp32: forward CUDA-core operand
+  __nv_bfloat16* w_head = nullptr;    // encoder head on the tensor cores: [Cout][64] bf16, written by wave_in_im2col_kernel
   // training only (allocated by kvae_plan_load_params(train = 1)): the data-gradient kernels see the same
   // weight tensor under the opposite kind (Cin <-> Cout), i.e. the other index order of each precision
   __nv_bfloat16* w_umma_d = nullptr;  // [K][Cin][Cout] bf16
@@ -138,9 +139,11 @@ struct PreparedRun {
   std::vector<int> direct_cfg;      // 0: 32x64 tile, 1: 128x4 tile
   std::vector<size_t> direct_smem;
   std::vector<int> kind;            // per step: 0 tensor-core, 1 generic, 2 waveform-in, 3 waveform-out,
-                                    //           4 fused ResidualUnit (this step + the next), 5 done by the previous step
+                                    //           4 fused ResidualUnit (this step + the next), 5 done by the previous step, 6 tensor-core tail,
+                                    //           7 encoder head as im2col + k = 1 tensor-core conv
   std::vector<RuLaunch> ru;
   std::vector<WaveInParams> wave_in;
+  WaveInColParams head_col;         // kind 7: im2col + weight pack in front of the head conv on the tensor cores
   std::vector<WaveOutParams> wave_out;
   struct WaveOutTc { CUtensorMap tmX; WaveOutTcParams p; };
   std::vector<WaveOutTc> wave_out_tc;   // kind 6: decoder tail on the tensor cores (TF32, or fp16 with the fp16 stream)
@@ -353,6 +356,12 @@ bool is_wave_in_step(const kvae_plan* p, const std::vector<Step>& steps, int k) 
   return !c.umma && !c.umma32 && k7same_geom(c.g) && k == 0 && n > 1 && c.g.Cin <= 2 && c.has_bias &&
          c.g.Cout % 128 == 0 && s.pre_snake < 0 && s.residual_from < 0;
 }
+// the encoder head runs as im2col + a k = 1 tensor-core conv (conv_edge.cuh, wave_in_im2col_kernel) in inference plans
+// with the fp16 stream; KVAE_WAVE_IN_CC=1 keeps the CUDA-core kernel
+bool head_on_tc(const kvae_plan* p, const std::vector<Step>& steps, bool train) {
+  return !train && p->precision == KVAE_PREC_BF16 && p->stream_f16 && is_wave_in_step(p, steps, 0) &&
+         p->convs[steps[0].conv].g.Cin <= 2 && !env_flag("KVAE_WAVE_IN_CC");
+}
 void finalize_steps(kvae_plan* p) {
   const int n = static_cast<int>(p->steps.size());
   // fp16 residual stream: only when every step runs on a kernel that knows about it (tensor-core convs and the
@@ -462,6 +471,11 @@ bool make_layout(const kvae_plan* p, const std::vector<Step>& steps, bool train,
       t.first = k;
       t.last = train ? (1 << 30) : k + 1;
     }
+  }
+  if (head_on_tc(p, steps, train)) {
+    L.t[0].bytes = static_cast<size_t>(B) * T * 64 * 2;     // im2col operand of the head conv
+    L.t[0].first = 0;
+    L.t[0].last = 0;
   }
   if (train && L.t[0].bytes) L.t[0].last = 1 << 30;
   // first-fit over live intervals, in order of first use
@@ -615,6 +629,28 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
       w.T = static_cast<int>(T_out);
       w.Cout = c.g.Cout;
       R.kind[k] = 2;
+      if (head_on_tc(p, steps, train)) {
+        WaveInColParams& h = R.head_col;
+        h.x = nullptr;  // patched per call
+        h.col = static_cast<__nv_bfloat16*>(tptr(0));
+        h.w = c.w_direct;
+        h.wp = c.w_head;
+        h.T = static_cast<int>(T_out); h.B = B; h.Cout = c.g.Cout; h.CIN = c.g.Cin;
+        h.row_blocks = B * static_cast<int>((T_out + kColRows - 1) / kColRows);
+        if (!h.col || !h.wp) { err = "internal: head operand missing"; return false; }
+        ConvGeom g1 = c.g;
+        g1.Cin = 64; g1.K = 1; g1.pad = 0; g1.dilation = 1; g1.stride = 1;
+        ConvEpilogue ep;
+        ep.bias = c.bias;
+        ep.stream_f16 = 1;
+        ep.out_raw = raw;
+        ep.out_act = static_cast<__nv_bfloat16*>(act);
+        ep.snake_a = w.snake_a;
+        ep.snake_inv_b = w.snake_inv_b;
+        ConvTuning2 tune;
+        if (!prepare_conv_umma2(g1, h.col, B, static_cast<int>(T_out), c.w_head, ep, tune, R.umma2[k], err)) return false;
+        R.kind[k] = 7;
+      }
       continue;
     }
     if (conv_tc(c, train)) {
@@ -894,6 +930,14 @@ int run_plan(kvae_plan* p, bool train, const void* in, int in_dtype, void* out, 
       w.y = out;
       w.y_f32 = (out_dtype == KVAE_F32);
       KV_CUDA(launch_wave_out(w, c.g.Cout, B, st));
+    } else if (R.kind[k] == 7) {
+      WaveInColParams& h = R.head_col;
+      h.x = in;
+      h.x_f32 = (in_dtype == KVAE_F32);
+      wave_in_im2col_kernel<<<h.row_blocks + (h.Cout * 64 + 255) / 256, 256, 0, st>>>(h);
+      KV_CUDA(cudaGetLastError());
+      ++g_launches;
+      KV_CUDA(launch_conv_umma2(R.umma2[k], st));
     } else if (R.kind[k] == 2) {
       WaveInParams& w = R.wave_in[k];
       w.x = in;
@@ -1449,6 +1493,7 @@ int kvae_plan_create(const kvae_arch* arch, int direction, int precision, int de
     if (c.umma) KV_CUDA(cudaMalloc(&c.w_umma, n * 2));
     else KV_CUDA(cudaMalloc(&c.w_direct, n * 4));
     if (c.umma32) KV_CUDA(cudaMalloc(&c.w_umma, n * 2 * 2));      // (hi | lo) halves
+    if (!c.umma && !c.umma32 && c.g.K == 7 && c.g.Cin <= 2) KV_CUDA(cudaMalloc(&c.w_head, static_cast<size_t>(c.g.Cout) * 64 * 2));
     if (c.has_bias) KV_CUDA(cudaMalloc(&c.bias, c.g.Cout * 4));
   }
   for (SnakeLayer& s : p->snakes) {
@@ -1466,6 +1511,7 @@ void kvae_plan_destroy(kvae_plan* p) {
   for (ConvLayer& c : p->convs) {
     cudaFree(c.w_umma);
     cudaFree(c.w_direct);
+    cudaFree(c.w_head);
     cudaFree(c.w_umma_d);
     cudaFree(c.w_direct_d);
     cudaFree(c.bias);
