@@ -117,6 +117,7 @@ __host__ __device__ inline int conv_umma2_raw_slots(int raw_mode, bool residual)
 }
 __host__ __device__ inline int conv_umma2_stage_bytes_per_warp(int raw_mode, int act_mode, bool residual, int raw_f16,
                                                                int act_split = 0, int bwd = 0, int fast = 0) {
+  if (fast && bwd) return 2 * (2 * kFastBlk) + 2 * kFastBlk;    // two slots of [x block | skip block], two bf16 output blocks
   if (fast) return conv_umma2_raw_slots(raw_mode, residual) * kFastBlk + (act_mode == 1 ? 2 * kFastBlk : 0);
   if (bwd) return 2 * (2 * kActBlkBytes) + 2 * kActBlkBytes;      // two slots of [x block | skip block], two bf16 output blocks
   return conv_umma2_raw_slots(raw_mode, residual) * conv_umma2_raw_blk(raw_f16) +
@@ -313,22 +314,26 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // loop-invariant 32-bit shared-memory offset, and four warps per scheduler hide each other's latencies.
     const int e = warp - 4, quad = warp & 3, sub = e >> 2;
     const int g8 = lane >> 2, rr = lane & 7, mj = lane >> 3;
-    const bool has_res = p.residual != nullptr;
-    const bool raw_out = p.raw_mode == 1, act_out = p.act_mode == 1, has_snake = p.snake_a != nullptr;
-    const int R = conv_umma2_raw_slots(p.raw_mode, has_res);
-    uint8_t* ring = stage_base + e * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, has_res, 1, 0, 0, 1);
-    uint8_t* aring = ring + R * kFastBlk;
+    constexpr bool kBwd = (kFast == 2);   // fused SnakeBeta backward of the data-gradient launches (ConvParams2::bwd)
+    const bool has_res = kBwd || p.residual != nullptr;
+    const bool raw_out = !kBwd && p.raw_mode == 1, act_out = kBwd || p.act_mode == 1, has_snake = p.snake_a != nullptr;
+    const int R = kBwd ? 2 : conv_umma2_raw_slots(p.raw_mode, has_res);
+    const uint32_t slot_bytes = kBwd ? 2 * kFastBlk : kFastBlk;
+    const uint32_t res_tx = (kBwd && p.bwd_skip) ? 2 * kFastBlk : kFastBlk;
+    uint8_t* ring = stage_base + e * conv_umma2_stage_bytes_per_warp(p.raw_mode, p.act_mode, has_res, 1, 0, kBwd ? 1 : 0, 1);
+    uint8_t* aring = ring + R * slot_bytes;
     const int brow = (mj >> 1) * 8 + rr;     // ldmatrix / stmatrix: this lane addresses row brow of a [16 x 64 B] block
     const uint32_t blk_lane = brow * 64 + (((mj & 1) ^ ((brow >> 1) & 3)) << 4);
     const uint32_t ring_lane = ptx::smem_u32(ring) + blk_lane;
-    const uint32_t aring_lane = ring_lane + R * kFastBlk;
+    const uint32_t aring_lane = ring_lane + R * slot_bytes;
     uint64_t* my_res_full = res_full + e * 3;
     const int n_items = 8 * p.MT;            // 16-row items per quadrant and tile
     const uint32_t acc_lane = tmem_base + (static_cast<uint32_t>(quad * 32) << 16);
     auto dup = [](float f) { return ptx::f2_pack(f, f); };
     auto issue_skip = [&](int cb, int ph, int row, int bb, int slot) {   // lane 0 only
-      ptx::mbar_expect_tx(&my_res_full[slot], kFastBlk);
-      ptx::tma_load_4d(ring + slot * kFastBlk, &tmX, &my_res_full[slot], cb, ph, row, bb);
+      ptx::mbar_expect_tx(&my_res_full[slot], res_tx);
+      ptx::tma_load_4d(ring + slot * slot_bytes, &tmX, &my_res_full[slot], cb, ph, row, bb);
+      if (kBwd && p.bwd_skip) ptx::tma_load_4d(ring + slot * slot_bytes + kFastBlk, &tmR, &my_res_full[slot], cb, ph, row, bb);
     };
     int tile = blockIdx.x;
     int b = 0, q0 = 0, phi = 0, n0 = 0;
@@ -336,18 +341,25 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (has_res && lane == 0 && tile < p.total_tiles) issue_skip(n0 + quad * 32, phi, q0 + sub * 16, b, 0);
     int acc = 0, jr = 0, ja = 0;
     uint32_t accph = 0, res_ph = 0;
+    float acc_da[4] = {0.f, 0.f, 0.f, 0.f}, acc_db[4] = {0.f, 0.f, 0.f, 0.f}, acc_bias[4] = {0.f, 0.f, 0.f, 0.f};
     for (; tile < p.total_tiles; tile += gridDim.x) {
       const int ntile = tile + gridDim.x;    // this CTA's next tile: its first skip block is prefetched during the last item
       int nb = 0, nq0 = 0, nphi = 0, nn0 = 0;
       if (ntile < p.total_tiles) decode(ntile, nb, nq0, nphi, nn0);
       const int cbase = n0 + quad * 32;
       uint64_t kb[4], ka[4], kib[4];         // index 2 * lane half + hi: channel cbase + 16 L + 8 hi + g8
+      float bw_a[4], bw_ib[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int ch = cbase + (i >> 1) * 16 + (i & 1) * 8 + g8;
-        kb[i] = p.bias ? dup(__ldg(p.bias + ch)) : 0ull;
-        ka[i] = has_snake ? dup(__ldg(p.snake_a + ch)) : 0ull;
-        kib[i] = has_snake ? dup(__ldg(p.snake_inv_b + ch)) : 0ull;
+        if constexpr (kBwd) {
+          bw_a[i] = __ldg(p.bwd_a + ch);
+          bw_ib[i] = __ldg(p.bwd_inv_b + ch);
+        } else {
+          kb[i] = p.bias ? dup(__ldg(p.bias + ch)) : 0ull;
+          ka[i] = has_snake ? dup(__ldg(p.snake_a + ch)) : 0ull;
+          kib[i] = has_snake ? dup(__ldg(p.snake_inv_b + ch)) : 0ull;
+        }
       }
       ptx::mbar_wait_parked(&t_full[acc], accph);
       ptx::tc_fence_after();
@@ -370,13 +382,52 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t t2 = acc_tmem + item * 16;
         ptx::tmem_ld_16x256b_x2(t2, r);
         ptx::tmem_ld_16x256b_x2(t2 + (16u << 16), r + 8);
-        const uint32_t rb = ring_lane + jr * kFastBlk;
+        const uint32_t rb = ring_lane + jr * slot_bytes;
         if (has_res) {
           ptx::mbar_wait_parked(&my_res_full[jr], (res_ph >> jr) & 1u);
           res_ph ^= (1u << jr);
           ptx::ldmatrix_x4_trans(rb, sk[0], sk[1], sk[2], sk[3]);
           ptx::ldmatrix_x4_trans(rb ^ 32u, sk[4], sk[5], sk[6], sk[7]);
         }
+        if constexpr (kBwd) {
+          uint32_t gs[8];
+          if (p.bwd_skip) {
+            ptx::ldmatrix_x4_trans(rb + kFastBlk, gs[0], gs[1], gs[2], gs[3]);
+            ptx::ldmatrix_x4_trans((rb + kFastBlk) ^ 32u, gs[4], gs[5], gs[6], gs[7]);
+          }
+          ptx::tmem_ld_wait();
+          uint32_t w[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {          // q = 4 L + 2 n + hi: time rows r0 + 8 n + 2 (lane & 3) + {0, 1}
+            const int ci = (q >> 2) * 2 + (q & 1);
+            const float2 xf = __half22float2(*reinterpret_cast<const __half2*>(&sk[q]));
+            float d0 = __uint_as_float(r[2 * q]), d1 = __uint_as_float(r[2 * q + 1]);
+            // rows past the end of the clip hold whatever the taps that still reach valid input produced: the TMA store
+            // clips them, the column sums must not see them
+            const int trow = r0 + 8 * ((q >> 1) & 1) + 2 * (lane & 3);
+            if (trow >= p.Tq_out) d0 = 0.f;
+            if (trow + 1 >= p.Tq_out) d1 = 0.f;
+            const float t0 = bw_a[ci] * xf.x, t1 = bw_a[ci] * xf.y;
+            const float sn0 = __sinf(t0), cs0 = __cosf(t0), sn1 = __sinf(t1), cs1 = __cosf(t1);
+            const float s20 = 2.f * sn0 * cs0, s21 = 2.f * sn1 * cs1;
+            acc_da[ci] = fmaf(d0 * xf.x, s20, fmaf(d1 * xf.y, s21, acc_da[ci]));
+            acc_db[ci] = fmaf(d0, sn0 * sn0, fmaf(d1, sn1 * sn1, acc_db[ci]));
+            const float k = bw_ib[ci] * bw_a[ci];
+            d0 *= fmaf(k, s20, 1.f);
+            d1 *= fmaf(k, s21, 1.f);
+            if (p.bwd_skip) {
+              const float2 gf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&gs[q]));
+              d0 += gf.x;
+              d1 += gf.y;
+            }
+            acc_bias[ci] += d0 + d1;
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(d0, d1);
+            w[q] = *reinterpret_cast<const uint32_t*>(&h2);
+          }
+          const uint32_t ab = aring_lane + ja * kFastBlk;
+          ptx::stmatrix_x4_trans(ab, w[0], w[1], w[2], w[3]);
+          ptx::stmatrix_x4_trans(ab ^ 32u, w[4], w[5], w[6], w[7]);
+        } else {
         ptx::tmem_ld_wait();
         uint64_t v[8];                       // q = 4 L + 2 n + hi
 #pragma unroll
@@ -419,15 +470,38 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           ptx::stmatrix_x4_trans(ab, w[0], w[1], w[2], w[3]);
           ptx::stmatrix_x4_trans(ab ^ 32u, w[4], w[5], w[6], w[7]);
         }
+        }   // !kBwd
         ptx::fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          if (raw_out) ptx::tma_store_4d(&tmR, ring + jr * kFastBlk, cbase, phi, r0, b);
+          if (raw_out) ptx::tma_store_4d(&tmR, ring + jr * slot_bytes, cbase, phi, r0, b);
           if (act_out) ptx::tma_store_4d(&tmO, aring + ja * kFastBlk, cbase, phi, r0, b);
           ptx::bulk_commit();                // (an empty group when only the skip block was consumed keeps the count uniform)
         }
         if (R > 0) jr = sn;
         ja ^= 1;
+      }
+      if constexpr (kBwd) {
+        // per-channel sums: kept in registers across this CTA's tiles while the channel block stays the same; the four
+        // lanes that share a channel (lane & 3 = time columns) combine, then one atomic per channel and warp
+        if (ntile >= p.total_tiles || nn0 != n0) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float va = acc_da[i], vb = acc_db[i], vc = acc_bias[i];
+            va += __shfl_xor_sync(0xffffffffu, va, 1); va += __shfl_xor_sync(0xffffffffu, va, 2);
+            vb += __shfl_xor_sync(0xffffffffu, vb, 1); vb += __shfl_xor_sync(0xffffffffu, vb, 2);
+            vc += __shfl_xor_sync(0xffffffffu, vc, 1); vc += __shfl_xor_sync(0xffffffffu, vc, 2);
+            if ((lane & 3) == 0) {
+              const int c = cbase + (i >> 1) * 16 + (i & 1) * 8 + g8;
+              const float ib = bw_ib[i], a = bw_a[i];
+              const float eb = 1.f / ib - 1e-9f;                      // exp(beta)
+              atomicAdd(p.d_alpha + c, va * ib * (p.bwd_logscale ? a : 1.f));
+              atomicAdd(p.d_beta + c, -vb * ib * ib * (p.bwd_logscale ? eb : 1.f));
+              if (p.d_bias) atomicAdd(p.d_bias + c, vc);
+            }
+            acc_da[i] = 0.f; acc_db[i] = 0.f; acc_bias[i] = 0.f;
+          }
+        }
       }
       // accumulator buffer fully read: hand it back to the UMMA issuer
       ptx::tc_fence_before();

@@ -459,6 +459,8 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
   static const bool fast_on = [] { const char* e = getenv("KVAE_FAST_EPI"); return !(e && e[0] == '0'); }();
   p.fast = (fast_on && p.swap && !p.bwd && !p.act_split && !p.precise && !p.no_frag && p.raw_mode != 2 &&
             (p.raw_f16 || (p.raw_mode == 0 && !ep.residual))) ? 1 : 0;
+  static const bool fast_bwd_on = [] { const char* e = getenv("KVAE_FAST_BWD"); return !(e && e[0] == '0'); }();
+  if (fast_on && fast_bwd_on && p.bwd && p.swap) p.fast = 2;
   const int box_rows = p.fast ? 16 : 32;
   int cols = 32;
   while (cols < p.acc_stages * p.MT * p.NT) cols <<= 1;
@@ -493,8 +495,8 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
   else L.tmX = L.tmA;
   if (p.bwd) {
     if (!p.swap) { err = "fused SnakeBeta backward needs the swap orientation"; return false; }
-    if (!make_out_tmap(&L.tmX, ep.bwd_x, B, T_out, g.Cout, tp.P_out, 2, err)) return false;
-    if (ep.bwd_skip && !make_out_tmap(&L.tmR, ep.bwd_skip, B, T_out, g.Cout, tp.P_out, 0, err)) return false;
+    if (!make_out_tmap(&L.tmX, ep.bwd_x, B, T_out, g.Cout, tp.P_out, 2, err, box_rows)) return false;
+    if (ep.bwd_skip && !make_out_tmap(&L.tmR, ep.bwd_skip, B, T_out, g.Cout, tp.P_out, 0, err, box_rows)) return false;
   }
   const int ctas = tune.max_ctas ? tune.max_ctas : sm_count();
   L.grid = std::min(p.total_tiles, ctas);
@@ -531,9 +533,12 @@ inline cudaError_t launch_conv_umma2(const ConvLaunch2& L, cudaStream_t stream) 
   if (!attr_set[dev & 63]) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_umma2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
   }
+  if (L.p.fast == 2)
+    return launch_pdl(conv_umma2_kernel<2>, dim3(L.grid), dim3(640), L.smem, stream, L.tmA, L.tmW, L.tmR, L.tmO, L.tmX, L.p);
   if (L.p.fast)
     return launch_pdl(conv_umma2_kernel<1>, dim3(L.grid), dim3(640), L.smem, stream, L.tmA, L.tmW, L.tmR, L.tmO, L.tmX, L.p);
   return launch_pdl(conv_umma2_kernel<0>, dim3(L.grid), dim3(384), L.smem, stream, L.tmA, L.tmW, L.tmR, L.tmO, L.tmX, L.p);
