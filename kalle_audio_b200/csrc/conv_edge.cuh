@@ -209,6 +209,8 @@ struct WaveOutTcParams {
   int T, B, COUT, tanh_out;
   int tiles_per_clip, total_tiles;
   int in_row0;              // output t reads input rows t + in_row0 .. +6 of tmX (-3 for a whole clip)
+  int preact;               // kF16 only: tmX maps SnakeBeta(x) already in fp16 (written by the last ResidualUnit's epilogue):
+                            // no transform stage, the MMAs read the tile as it lands
   unsigned int* peak_bits;  // nullptr, or: atomicMax of the bit pattern of |y| over everything written (phase 1 of the
                             // peak-normalised int16 conversion, infer_0828_sigma.py:298) -- one atomic per warp and tile
 };
@@ -314,7 +316,7 @@ conv_wave_out_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
       int s = 0, a = 0;
       uint32_t ph = 0, aph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(&ready[s], ph);
+        ptx::mbar_wait(p.preact ? &full[s] : &ready[s], ph);
         ptx::mbar_wait(&acc_empty[a], aph ^ 1u);
         ptx::tc_fence_after();
         const uint32_t d = tmem_base + a * 16;
@@ -334,7 +336,7 @@ conv_wave_out_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
         if (++a == 2) { a = 0; aph ^= 1u; }
       }
     }
-  } else if (warp >= 4 && warp < 20) {
+  } else if (warp >= 4 && warp < 20 && !p.preact) {
     // ------------------------------------------------------------ SnakeBeta in place on the staged tile
     const int tid = threadIdx.x - 128;                    // 0..511
     // A thread's 16-byte units are tid + 512*i: the same position inside a row and the same row phase (row & 7)

@@ -50,6 +50,8 @@ struct RuParams {
   const void* x_ptr;
   int pf;                   // bit 0: prefetch the operand rows of the tile after next into L2, bit 1: its skip rows
   int k0, k1;               // conv_ru2_kernel: GEMM2 half 0 / 1 of tile i goes in before slab k0 / k1 of tile i+1's GEMM1
+  int act_f16;              // conv_ru2_kernel: the operand output is fp16 instead of bf16 (the unit in front of the decoder tail,
+                            // whose GEMM is kind::f16 -- conv_edge.cuh, WaveOutTcParams::preact)
 };
 
 constexpr int kRuC = 128;

@@ -385,8 +385,12 @@ conv_ru2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             } else {
               ptx::f2_unpack(v[q], y0, y1);
             }
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
-            w[q] = *reinterpret_cast<const uint32_t*>(&h2);
+            if (p.act_f16) {
+              w[q] = ptx::f2h2_sat(y0, y1);
+            } else {
+              const __nv_bfloat162 h2 = __floats2bfloat162_rn(y0, y1);
+              w[q] = *reinterpret_cast<const uint32_t*>(&h2);
+            }
           }
           ptx::stmatrix_x4_trans(ablk_lane, w[0], w[1], w[2], w[3]);
           ptx::stmatrix_x4_trans(ablk_lane ^ 32u, w[4], w[5], w[6], w[7]);

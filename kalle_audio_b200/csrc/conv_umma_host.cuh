@@ -567,6 +567,7 @@ struct RuArgs {
   const float* sn_a = nullptr;
   const float* sn_inv_b = nullptr;
   int stream_f16 = 0;                     // x and out_raw are fp16 instead of fp32
+  int act_f16 = 0;                        // out_act is fp16 (SnakeBeta applied) for the decoder tail's kind::f16 GEMM
 };
 
 inline bool ru_supported(int C) { return C == kRuC; }
@@ -612,6 +613,8 @@ inline bool prepare_conv_ru(const RuArgs& a, int B, int T, int dilation, RuLaunc
   // serial GEMM1 -> EPI1 -> GEMM2 chain, 2 (default) = conv_ru2_kernel
   L.epi = 2;
   if (const char* e = getenv("KVAE_RU_EPI")) L.epi = atoi(e);
+  p.act_f16 = a.act_f16;
+  if (p.act_f16 && L.epi != 2) { err = "fused RU: the fp16 operand output needs conv_ru2_kernel"; return false; }
   p.a_ptr = a.a; p.x_ptr = a.x;
   p.pf = 0;
   if (const char* e = getenv("KVAE_RU_PF")) p.pf = atoi(e);

@@ -115,6 +115,7 @@ struct Step {
   bool needs_raw = false, needs_act = false;
   int epi_snake = -1;      // SnakeBeta folded into the epilogue for the next (tensor-core) conv
   int fuse = 0;            // 1: k7 conv of a ResidualUnit run by the fused kernel together with the next step (2)
+  bool act_f16 = false;    // the activated output is fp16 (the unit in front of the tensor-core decoder tail)
 };
 
 struct Tensor {
@@ -198,6 +199,7 @@ struct kvae_plan {
   std::vector<long long> param_sizes;   // segment sizes in module.parameters() order
   bool train_packs = false;
   bool stream_f16 = false;    // inference plans keep the residual stream in fp16 (bf16 mode, all-tensor-core chains)
+  bool tail_preact = false;   // the last ResidualUnit writes SnakeBeta(x) in fp16 and the decoder tail reads that (no transform stage)
   bool train_stream_f16 = false;   // ... and so do training plans whose every backward consumer of the stream knows fp16
   float* scale_scratch = nullptr;   // g/||v|| per dim-0 row of the conv being packed
   // batched kvae_plan_load_params (one scale + one pack + one SnakeBeta-constant launch for the whole plan)
@@ -431,6 +433,18 @@ void finalize_steps(kvae_plan* p) {
       ++k;
     }
   }
+  // Decoder tail (conv_edge.cuh): when the unit in front of it is a fused ResidualUnit, that unit applies the tail's
+  // SnakeBeta in its epilogue and writes the result in fp16; the tail's 16 transform warps (0.33 of its 0.49 ms at
+  // 16 x 442 368 rows) have nothing left to do.  One rounding fewer than snake(fp16(x)).  KVAE_TAIL_RAW=1: old flow.
+  if (n >= 3 && !env_flag("KVAE_TAIL_RAW") && !env_flag("KVAE_WAVE_OUT_CC") && is_wave_out_step(p, p->steps, n - 1) &&
+      p->steps[n - 2].fuse == 2 && p->steps[n - 1].pre_snake >= 0) {
+    Step& b = p->steps[n - 2];
+    b.needs_act = true;
+    b.needs_raw = false;
+    b.epi_snake = p->steps[n - 1].pre_snake;
+    b.act_f16 = true;
+    p->tail_preact = true;
+  }
 }
 
 long long step_len(const Step& s, long long T) { return T * s.len_num / s.len_den; }
@@ -568,6 +582,7 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
       ra.bias1 = c1.bias;
       ra.out_raw = s1.needs_raw ? tptr(1 + 2 * (k + 1)) : nullptr;
       ra.out_act = s1.needs_act ? static_cast<__nv_bfloat16*>(tptr(2 + 2 * (k + 1))) : nullptr;
+      ra.act_f16 = s1.act_f16 ? 1 : 0;
       if (s1.epi_snake >= 0) {
         ra.sn_a = p->snakes[s1.epi_snake].a;
         ra.sn_inv_b = p->snakes[s1.epi_snake].inv_b;
@@ -579,7 +594,8 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
     if (is_wave_out_step(p, steps, k)) {
       // decoder tail (conv_edge.cuh)
       WaveOutParams& w = R.wave_out[k];
-      w.x = static_cast<const float*>(tptr(1 + 2 * (k - 1)));
+      const bool preact = p->tail_preact && !train;
+      w.x = static_cast<const float*>(preact ? tptr(2 + 2 * (k - 1)) : tptr(1 + 2 * (k - 1)));
       if (!w.x) { err = "internal: raw input missing"; return false; }
       w.pro_a = p->snakes[s.pre_snake].a;
       w.pro_inv_b = p->snakes[s.pre_snake].inv_b;
@@ -597,6 +613,7 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
         std::memset(&t.p, 0, sizeof(t.p));
         t.p.pro_a = w.pro_a; t.p.pro_inv_b = w.pro_inv_b; t.p.w = w.w;
         t.p.T = w.T; t.p.B = B; t.p.COUT = c.g.Cout; t.p.tanh_out = w.tanh_out; t.p.in_row0 = -3;
+        t.p.preact = preact ? 1 : 0;
         t.p.tiles_per_clip = (w.T + kWoTcTile - 1) / kWoTcTile;
         t.p.total_tiles = t.p.tiles_per_clip * B;
         if (sf16) { if (!make_act_tmap(&t.tmX, w.x, B, w.T, 128, 1, kWoTcRows, err)) return false; }

@@ -188,11 +188,13 @@ bool stream_prepare(kvae_stream* s, int n_frames, bool flush, int z_dtype, Prepa
       ra.bias1 = c1.bias;
       ra.out_raw = out.raw_row_bytes ? raw_ptr(out, out.rows) : nullptr;
       ra.out_act = out.act_row_bytes ? reinterpret_cast<__nv_bfloat16*>(act_ptr(out, out.rows)) : nullptr;
+      ra.act_f16 = s1.act_f16 ? 1 : 0;
       if (s1.epi_snake >= 0) { ra.sn_a = p->snakes[s1.epi_snake].a; ra.sn_inv_b = p->snakes[s1.epi_snake].inv_b; }
       if (!prepare_conv_ru(ra, B, 0, c.g.dilation, P.ru[k], err, &sg)) return false;
     } else if (st.kind == 6 || st.kind == 3) {
       // decoder tail: reads the stream (raw) tensor of the previous step, writes the staging waveform [B, io, out_rows]
-      if (!in.raw_row_bytes) { err = "internal: streaming tail needs the stream tensor"; return false; }
+      const bool preact = p->tail_preact && st.kind == 6;    // the last unit wrote SnakeBeta(x) in fp16 (kvae.cu, finalize_steps)
+      if (preact ? !in.act_row_bytes : !in.raw_row_bytes) { err = "internal: streaming tail needs the stream tensor"; return false; }
       if (out_rows > s->max_samples) { err = "streaming: waveform staging overflow"; return false; }
       const int tanh_out = (p->arch.final_tanh) ? 1 : 0;
       P.wo_cout = c.g.Cout;
@@ -205,7 +207,8 @@ bool stream_prepare(kvae_stream* s, int n_frames, bool flush, int z_dtype, Prepa
         t.p.total_tiles = t.p.tiles_per_clip * B;
         t.p.in_row0 = 0;                                   // -3 + bias 3
         t.p.y = s->wav_stage; t.p.y_f32 = 1;
-        if (sf16) { if (!make_act_tmap(&t.tmX, raw_ptr(in, 0), B, static_cast<int>(in.rows), 128, 1, kWoTcRows, err, in.cap)) return false; }
+        t.p.preact = preact ? 1 : 0;
+        if (sf16) { if (!make_act_tmap(&t.tmX, preact ? act_ptr(in, 0) : raw_ptr(in, 0), B, static_cast<int>(in.rows), 128, 1, kWoTcRows, err, in.cap)) return false; }
         else if (!make_out_tmap(&t.tmX, raw_ptr(in, 0), B, static_cast<int>(in.rows), 128, 1, 1, err, kWoTcRows, in.cap)) return false;
       } else {
         WaveOutParams& w = P.wo_cc;
