@@ -17,8 +17,11 @@ namespace kvae {
 //   u[n]  = 2 * sum_i xp[i] * fu[n + 15 - 2 i]      xp[i] = x[clamp(i - 5, 0, T-1)], 0 <= n + 15 - 2 i < 12,  n in [0, 2T)
 //   v[n]  = u[n] + inv_b * sin(a * u[n])^2
 //   y[t]  = sum_m vp[2 t + m] * fd[m]               vp[j] = v[clamp(j - 5, 0, 2T-1)],  m in [0, 12)
-constexpr int kAaTile = 256;                         // outputs per block
+constexpr int kAaTile = 1024;                        // outputs per block
 constexpr int kAaK = 12;
+// Everything inside a tile is indexed relative to the tile start in 32 bits; 64-bit arithmetic only places the tile
+// and clamps at the two ends of the row (the first version did every tap's index in 64 bits and spent ~60 % of its
+// instructions there: 21 of the 60 ms of the bench decode).  Same operations in the same order per sample.
 __global__ void __launch_bounds__(256) aa_act_kernel(const void* x, void* y, const float* alpha, const float* beta, int logscale,
                                                      const float* fu, const float* fd, int C, long long T, int f32) {
   __shared__ float xs[kAaTile + 16];
@@ -31,39 +34,39 @@ __global__ void __launch_bounds__(256) aa_act_kernel(const void* x, void* y, con
   float a = alpha[c], bt = beta ? beta[c] : alpha[c];          // Snake: 1/alpha; SnakeBeta: 1/beta
   if (logscale) { a = expf(a); bt = expf(bt); }
   const float inv_b = 1.0f / (bt + 1e-9f);
+  // rows still inside the tensor, relative to the tile: x index i_rel = t - t0 in [lo_x, hi_x], v index n - 2 t0 in [lo_v, hi_v]
+  const int lo_x = static_cast<int>(-min(t0, 64ll)), hi_x = static_cast<int>(min(T - 1 - t0, static_cast<long long>(kAaTile + 64)));
+  const int lo_v = 2 * lo_x, hi_v = static_cast<int>(min(2 * T - 1 - 2 * t0, static_cast<long long>(2 * kAaTile + 64)));
   // x rows t0 - 8 .. t0 + TT + 7 (clamped = replicate padding)
   for (int i = threadIdx.x; i < kAaTile + 16; i += 256) {
-    long long t = t0 - 8 + i;
-    t = t < 0 ? 0 : (t > T - 1 ? T - 1 : t);
-    xs[i] = ld_elem(x, row + t, f32);
+    const int tr = max(lo_x, min(hi_x, i - 8));
+    xs[i] = ld_elem(x, row + t0 + tr, f32);
   }
   __syncthreads();
   // activated double-rate samples n = 2 t0 - 5 .. 2 t0 + 2 TT + 6, the index clamped to [0, 2T) (replicate padding of v)
   for (int j = threadIdx.x; j < 2 * kAaTile + kAaK; j += 256) {
-    long long n = 2 * t0 - 5 + j;
-    n = n < 0 ? 0 : (n > 2 * T - 1 ? 2 * T - 1 : n);
-    // taps i with 0 <= n + 15 - 2 i <= 11: i from ceil((n + 4) / 2) to floor((n + 15) / 2): six of them
-    const long long i_lo = (n + 5) >> 1;
+    const int n = max(lo_v, min(hi_v, j - 5));                  // relative to 2 t0
+    // taps i with 0 <= n + 15 - 2 i <= 11: six of them, from i_lo = floor((n + 5) / 2)
+    const int i_lo = (n + 5) >> 1;
+    const int k0 = n + 15 - 2 * i_lo;                           // 10 or 11
+    const float* xp = xs + i_lo + 3;                            // xs index of x[i - 5] = (i - 5) + 8
     float u = 0.f;
 #pragma unroll
-    for (int q = 0; q < 6; ++q) {
-      const long long i = i_lo + q;
-      const int k = static_cast<int>(n + 15 - 2 * i);
-      long long xt = i - 5;                                     // index into x before clamping
-      xt = xt < 0 ? 0 : (xt > T - 1 ? T - 1 : xt);
-      u = fmaf(xs[static_cast<int>(xt - (t0 - 8))], f_up[k], u);
-    }
+    for (int q = 0; q < 6; ++q) u = fmaf(xp[q], f_up[k0 - 2 * q], u);
     u *= 2.f;
     const float s = sinf(u * a);
     vs[j] = u + inv_b * (s * s);
   }
   __syncthreads();
-  const long long t = t0 + threadIdx.x;
-  if (t < T) {
-    float acc = 0.f;
 #pragma unroll
-    for (int m = 0; m < kAaK; ++m) acc = fmaf(vs[2 * threadIdx.x + m], f_dn[m], acc);
-    st_elem(y, row + t, f32, acc);
+  for (int r = 0; r < kAaTile / 256; ++r) {
+    const int tl = threadIdx.x + 256 * r;
+    if (t0 + tl < T) {
+      float acc = 0.f;
+#pragma unroll
+      for (int m = 0; m < kAaK; ++m) acc = fmaf(vs[2 * tl + m], f_dn[m], acc);
+      st_elem(y, row + t0 + tl, f32, acc);
+    }
   }
 }
 
