@@ -11,6 +11,9 @@ ncu --set full --clock-control none --import-source on -k regex:conv_ru2_kernel 
     -o gpurun_out/r02_conv_ru2_bench_shape_B16 python bench.py --steps 1 --warmup 1 --no-cpu-baseline --main-only > gpurun_out/r02_ncu_ru2.log 2>&1; echo "ncu ru2 rc=$?"
 ncu --set full --clock-control none -k regex:snake_bwd_stream --launch-skip 130 --launch-count 1 \
     -o gpurun_out/r02_snake_bwd_stream python tools/prof_train.py 4 2 > gpurun_out/r02_ncu_sbs.log 2>&1; echo "ncu sbs rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:conv_umma2_kernel --launch-skip 41 --launch-count 1 \
+    -o gpurun_out/r02_k1_c256_B16_fast python tools/prof_dec_once.py 16 > gpurun_out/r02_ncu_k1.log 2>&1; echo "ncu k1 rc=$?"
+PROF_STEPS=1 python tools/prof_sao_b16.py 16 > gpurun_out/r02_step_profile_sao_b16.txt 2>&1
 python tools/prof_o12_b1.py 128 1 > gpurun_out/r02_step_profile_o12_b1.txt 2>&1
 python tools/prof_o12_b1.py 96 1 >> gpurun_out/r02_step_profile_o12_b1.txt 2>&1
 bash tools/run_train_list2.sh > gpurun_out/r02_train_step_launches.txt 2>&1
