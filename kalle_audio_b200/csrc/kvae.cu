@@ -226,6 +226,8 @@ namespace {
 
 int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+int direct_cfg_for(int Cout);
+void direct_tile(int cfg, int& BT, int& BN);
 bool env_flag(const char* name) {
   const char* e = getenv(name);
   return e && e[0] == '1';
@@ -762,8 +764,9 @@ bool prepare_run(kvae_plan* p, const std::vector<Step>& steps, bool train, int B
         d.snake_a = p->snakes[s.epi_snake].a;
         d.snake_inv_b = p->snakes[s.epi_snake].inv_b;
       }
-      const int cfg = (c.g.Cout <= 4) ? 1 : 0;
-      const int BT = cfg ? 128 : 32, BN = cfg ? 4 : 64;
+      const int cfg = direct_cfg_for(c.g.Cout);
+      int BT, BN;
+      direct_tile(cfg, BT, BN);
       R.direct_cfg[k] = cfg;
       R.direct_grid[k] = dim3(ceil_div(d.Tq_out, BT) * tp.P_out, ceil_div(c.g.Cout, BN), B);
       R.direct_smem[k] = (static_cast<size_t>(BT + tp.span) * (kDirectKC + 1) + kDirectKC * BN) * sizeof(float);
@@ -800,8 +803,18 @@ cudaError_t launch_wave_in(const WaveInParams& w, int Cin, int B, cudaStream_t s
   return cudaGetLastError();
 }
 
+// CUDA-core conv tile (time rows x out-channels per 128-thread block) by output width: the 64-wide tile left 50-75 % of
+// the threads without a channel on the 32- and 16-channel stages of BigVGANFlowVAE.  The per-output summation order does
+// not depend on the tile, so every configuration gives the same bits.
+int direct_cfg_for(int Cout) { return Cout <= 4 ? 1 : Cout <= 16 ? 2 : Cout <= 32 ? 3 : 0; }
+void direct_tile(int cfg, int& BT, int& BN) {
+  BT = cfg == 1 ? 128 : cfg == 2 ? 128 : cfg == 3 ? 64 : 32;
+  BN = cfg == 1 ? 4 : cfg == 2 ? 16 : cfg == 3 ? 32 : 64;
+}
 cudaError_t launch_direct(const DirectParams& d, dim3 grid, int cfg, size_t smem, cudaStream_t st) {
   if (cfg == 1) conv_direct_kernel<128, 4, 1, 4><<<grid, 128, smem, st>>>(d);
+  else if (cfg == 2) conv_direct_kernel<128, 16, 4, 4><<<grid, 128, smem, st>>>(d);
+  else if (cfg == 3) conv_direct_kernel<64, 32, 4, 4><<<grid, 128, smem, st>>>(d);
   else conv_direct_kernel<32, 64, 4, 4><<<grid, 128, smem, st>>>(d);
   return cudaGetLastError();
 }
@@ -1231,8 +1244,9 @@ bool prepare_backward(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R
         d.out_raw = dA; d.out_raw_f32 = 1;
         d.o_sB = T_in * gd.Cout; d.o_sT = gd.Cout; d.o_sC = 1;
       }
-      const int cfg = (gd.Cout <= 4) ? 1 : 0;
-      const int BT = cfg ? 128 : 32, BN = cfg ? 4 : 64;
+      const int cfg = direct_cfg_for(gd.Cout);
+      int BT, BN;
+      direct_tile(cfg, BT, BN);
       bw.dg_cfg = cfg;
       bw.dg_grid = dim3(ceil_div(d.Tq_out, BT) * tp.P_out, ceil_div(gd.Cout, BN), B);
       bw.dg_smem = (static_cast<size_t>(BT + tp.span) * (kDirectKC + 1) + kDirectKC * BN) * sizeof(float);
@@ -1810,8 +1824,9 @@ int kvae_conv1d_fwd(const void* x, void* y, const float* w, const float* bias, i
   d.w = wd; d.bias = bias;
   d.out_raw = y; d.out_raw_f32 = (dtype == KVAE_F32);
   d.o_sB = static_cast<long long>(Cout) * T_out; d.o_sT = 1; d.o_sC = T_out;
-  const int cfg = (Cout <= 4) ? 1 : 0;
-  const int BT = cfg ? 128 : 32, BN = cfg ? 4 : 64;
+  const int cfg = direct_cfg_for(Cout);
+  int BT, BN;
+  direct_tile(cfg, BT, BN);
   dim3 grid(ceil_div(d.Tq_out, BT) * tp.P_out, ceil_div(Cout, BN), B);
   const size_t smem = (static_cast<size_t>(BT + tp.span) * (kDirectKC + 1) + kDirectKC * BN) * sizeof(float);
   KV_CUDA(launch_direct(d, grid, cfg, smem, st));
@@ -1888,8 +1903,9 @@ int kvae_conv1d_bwd(const void* x, const void* gy, const float* w, void* gx, flo
   d.w = wd;
   d.out_raw = gx; d.out_raw_f32 = f32;
   d.o_sB = xsB; d.o_sT = 1; d.o_sC = T;
-  const int cfg = (gd.Cout <= 4) ? 1 : 0;
-  const int BT = cfg ? 128 : 32, BN = cfg ? 4 : 64;
+  const int cfg = direct_cfg_for(gd.Cout);
+  int BT, BN;
+  direct_tile(cfg, BT, BN);
   dim3 grid(ceil_div(d.Tq_out, BT) * tp.P_out, ceil_div(gd.Cout, BN), B);
   const size_t smem = (static_cast<size_t>(BT + tp.span) * (kDirectKC + 1) + kDirectKC * BN) * sizeof(float);
   KV_CUDA(launch_direct(d, grid, cfg, smem, st));
