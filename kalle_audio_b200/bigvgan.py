@@ -312,6 +312,9 @@ class BigVGANFlowVAE(nn.Module):
         self.activation_post = _make_act(h, ch)
         self.conv_post = Conv1d(ch, 1, 7, 1, causal=causal)
         self.set_precision("fp32")
+        for m in self.modules():           # inference-only model: fold weight norm once per weight version (layers.py)
+            if isinstance(m, (WNConv1d, WNConvTranspose1d)):
+                m._cache_fold = True
 
     def set_precision(self, precision: Optional[str]):
         """Arithmetic of the convolutions whose channel counts are multiples of 64 (the wide stages, > 90 % of the

@@ -174,12 +174,23 @@ class _WNConvBase(nn.Module):
         """fp32 folded weight w = v * g/||v|| computed on the device by libkvae (fold in fp32, round once)."""
         if not self.has_weight_norm:
             return self._parameters["weight"].detach().float().contiguous()
+        # Inference-only models built from stand-alone layers (BigVGANFlowVAE) set ``_cache_fold``: the folded weight is
+        # reused until weight_v / weight_g change (storage or torch version counter, i.e. .to(), load_state_dict and
+        # in-place optimizer steps all invalidate it).  Read-only for the callers.
+        key = None
+        if getattr(self, "_cache_fold", False) and not torch.is_grad_enabled():
+            key = (self.weight_v.data_ptr(), self.weight_v._version, self.weight_g.data_ptr(), self.weight_g._version)
+            hit = self.__dict__.get("_fold_cache")
+            if hit is not None and hit[0] == key:
+                return hit[1]
         v = self.weight_v.detach().float().contiguous()
         g = self.weight_g.detach().float().contiguous()
         _lib.require_cuda(v, "weight-norm fold")
         w = torch.empty_like(v)
         _lib.check(_lib.lib().kvae_weight_norm_fold(v.data_ptr(), g.data_ptr(), w.data_ptr(), v.shape[0],
                                                     v[0].numel(), _lib.stream_ptr(v.device)))
+        if key is not None:
+            self.__dict__["_fold_cache"] = (key, w)
         return w
 
     @property

@@ -106,3 +106,28 @@ def test_bigvgan_wider_model_vs_oracle(dev):
     refc = BO.inference_from_latents(sdc, dict(hc), zc)
     yc = mc.to(dev).inference_from_latents(zc.to(dev), do_sample=False)
     assert float((yc.cpu() - refc).abs().max()) <= 2e-5
+
+
+def test_folded_weight_cache_follows_the_weights(dev):
+    """The inference-only model folds weight norm once per weight version (layers.py, ``_cache_fold``): in-place updates
+    and load_state_dict must invalidate the cached fold."""
+    g = H.golden("bigvgan")
+    sd = {kk[3:]: H.t(g[kk]) for kk in g.files if kk.startswith("sd.")}
+    m = BV.BigVGANFlowVAE(AttrDict(BIGVGAN_H, causal=True)).eval()
+    m.load_state_dict(sd, strict=True)
+    m.to(dev)
+    z = H.t(g["causal.z"]).to(dev)
+    y0 = m.inference_from_latents(z, do_sample=False)
+    assert m.conv_pre.__dict__.get("_fold_cache") is not None            # the cache is in use
+    assert torch.equal(y0, m.inference_from_latents(z, do_sample=False))
+    with torch.no_grad():
+        m.conv_pre.weight_g.mul_(1.25)                                   # bumps the version counter
+    y1 = m.inference_from_latents(z, do_sample=False)
+    assert not torch.equal(y0, y1)
+    fresh = BV.BigVGANFlowVAE(AttrDict(BIGVGAN_H, causal=True)).eval()
+    sd2 = dict(sd)
+    sd2["conv_pre.weight_g"] = sd["conv_pre.weight_g"] * 1.25
+    fresh.load_state_dict(sd2, strict=True)
+    assert torch.equal(y1, fresh.to(dev).inference_from_latents(z, do_sample=False))
+    m.load_state_dict(sd, strict=True)                                   # copy_ into the parameters: version bump again
+    assert torch.equal(y0, m.inference_from_latents(z, do_sample=False))
