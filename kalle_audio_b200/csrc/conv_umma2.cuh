@@ -242,9 +242,13 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ UMMA issuer
-    // One thread feeds the tensor core; at N = 128 an MMA retires every 64 cycles, so this loop must stay
-    // a few dozen instructions per tap: descriptors are a constant high word plus a running low word.
-    if (ptx::elect_one()) {
+    // The WHOLE warp walks the (tile, chunk, tap) loop and the barriers; one elected lane issues the MMAs and commits.
+    // With the loop inside `if (elect_one())` (the first form) every loop variable lived in a vector register of a
+    // divergent thread: 79 instructions per weight stage with an indexed constant load, six R2UR transfers and the
+    // parameter block re-read each iteration -- ~540 cycles per stage of four MMAs, which 256-row tiles hide (512 tensor
+    // cycles) but 128-row tiles do not: the batch-1 streaming layers ran their tensor pipe at 16 %
+    // (profiles/r02_o12_b1_k7_c1024.txt).  Warp-uniform, the loop state sits in uniform registers next to the descriptors.
+    {
       const uint32_t idesc = ptx::idesc_bf16_f32(128, p.NT);
       const uint32_t idesc_swap = ptx::idesc_bf16_f32(128, 128 * p.MT);
       const uint64_t desc_hi = (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -252,6 +256,10 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const uint32_t b_lo0 = ((ptx::smem_u32(b_ring) & 0x3FFFFu) >> 4) | (1u << 16);
       const uint32_t a_stage16 = a_bytes >> 4, b_stage16 = b_bytes >> 4;
       const bool two = (p.MT == 2);
+      const bool swap = p.swap != 0;
+      const int SA = p.SA, SB = p.SB, acc_stages = p.acc_stages;
+      const int n_vc = p.split3 ? 3 * p.n_chunks : p.n_chunks;
+      const uint32_t NT16 = p.NT;
       int as = 0, bs = 0, cur = 0, acc = 0;
       uint32_t aph = 0, bph = 0, accph = 0, cur_lo = a_lo0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -260,48 +268,53 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (p.park & 4) ptx::mbar_wait_parked(&t_empty[acc], accph ^ 1u); else ptx::mbar_wait(&t_empty[acc], accph ^ 1u);   // epilogue has drained this accumulator buffer
         ptx::tc_fence_after();
         const uint32_t d0 = tmem_base + acc * acc_cols;
-        const uint32_t d1 = d0 + p.NT;
+        const uint32_t d1 = d0 + NT16;
         uint32_t accum = 0;                          // first MMA of a tile overwrites the accumulator
-        const int n_vc = p.split3 ? 3 * p.n_chunks : p.n_chunks;
         for (int ch = 0; ch < n_vc; ++ch) {
+          uint32_t tw = p.tap_mma[t_lo];
           for (int t = t_lo; t < t_hi; ++t) {
-            const uint32_t tw = p.tap_mma[t];
+            const uint32_t tw_next = p.tap_mma[t + 1 < t_hi ? t + 1 : t_lo];   // fetched under this stage's MMAs
             if (tw & 0x10000u) {
               ptx::mbar_wait(&a_full[as], aph);
               cur = as;
               cur_lo = a_lo0 + as * a_stage16;
-              if (++as == p.SA) { as = 0; aph ^= 1u; }
+              if (++as == SA) { as = 0; aph ^= 1u; }
             }
             ptx::mbar_wait(&b_full[bs], bph);
             ptx::tc_fence_after();
             const uint32_t al = cur_lo + (tw & 0xffffu);
             const uint32_t bl = b_lo0 + bs * b_stage16;
-            if (p.swap) {
-              ptx::umma_f16(d0, desc_hi | bl, desc_hi | al, idesc_swap, accum);
-              ptx::umma_f16(d0, desc_hi | (bl + 2), desc_hi | (al + 2), idesc_swap, 1u);
-              ptx::umma_f16(d0, desc_hi | (bl + 4), desc_hi | (al + 4), idesc_swap, 1u);
-              ptx::umma_f16(d0, desc_hi | (bl + 6), desc_hi | (al + 6), idesc_swap, 1u);
-            } else {
-            ptx::umma_f16(d0, desc_hi | al, desc_hi | bl, idesc, accum);
-            ptx::umma_f16(d0, desc_hi | (al + 2), desc_hi | (bl + 2), idesc, 1u);
-            ptx::umma_f16(d0, desc_hi | (al + 4), desc_hi | (bl + 4), idesc, 1u);
-            ptx::umma_f16(d0, desc_hi | (al + 6), desc_hi | (bl + 6), idesc, 1u);
-            if (two) {
-              const uint32_t al1 = al + 1024;        // second 128-row sub-tile: +128 rows * 128 B >> 4
-              ptx::umma_f16(d1, desc_hi | al1, desc_hi | bl, idesc, accum);
-              ptx::umma_f16(d1, desc_hi | (al1 + 2), desc_hi | (bl + 2), idesc, 1u);
-              ptx::umma_f16(d1, desc_hi | (al1 + 4), desc_hi | (bl + 4), idesc, 1u);
-              ptx::umma_f16(d1, desc_hi | (al1 + 6), desc_hi | (bl + 6), idesc, 1u);
+            if (ptx::elect_one()) {
+              if (swap) {
+                ptx::umma_f16(d0, desc_hi | bl, desc_hi | al, idesc_swap, accum);
+                ptx::umma_f16(d0, desc_hi | (bl + 2), desc_hi | (al + 2), idesc_swap, 1u);
+                ptx::umma_f16(d0, desc_hi | (bl + 4), desc_hi | (al + 4), idesc_swap, 1u);
+                ptx::umma_f16(d0, desc_hi | (bl + 6), desc_hi | (al + 6), idesc_swap, 1u);
+              } else {
+                ptx::umma_f16(d0, desc_hi | al, desc_hi | bl, idesc, accum);
+                ptx::umma_f16(d0, desc_hi | (al + 2), desc_hi | (bl + 2), idesc, 1u);
+                ptx::umma_f16(d0, desc_hi | (al + 4), desc_hi | (bl + 4), idesc, 1u);
+                ptx::umma_f16(d0, desc_hi | (al + 6), desc_hi | (bl + 6), idesc, 1u);
+                if (two) {
+                  const uint32_t al1 = al + 1024;        // second 128-row sub-tile: +128 rows * 128 B >> 4
+                  ptx::umma_f16(d1, desc_hi | al1, desc_hi | bl, idesc, accum);
+                  ptx::umma_f16(d1, desc_hi | (al1 + 2), desc_hi | (bl + 2), idesc, 1u);
+                  ptx::umma_f16(d1, desc_hi | (al1 + 4), desc_hi | (bl + 4), idesc, 1u);
+                  ptx::umma_f16(d1, desc_hi | (al1 + 6), desc_hi | (bl + 6), idesc, 1u);
+                }
+              }
+              ptx::umma_commit(&b_empty[bs]);
+              if (tw & 0x20000u) ptx::umma_commit(&a_empty[cur]);
             }
-            }
+            __syncwarp();
             accum = 1u;
-            ptx::umma_commit(&b_empty[bs]);
-            if (tw & 0x20000u) ptx::umma_commit(&a_empty[cur]);
-            if (++bs == p.SB) { bs = 0; bph ^= 1u; }
+            if (++bs == SB) { bs = 0; bph ^= 1u; }
+            tw = tw_next;
           }
         }
-        ptx::umma_commit(&t_full[acc]);
-        if (++acc == p.acc_stages) { acc = 0; accph ^= 1u; }
+        if (ptx::elect_one()) ptx::umma_commit(&t_full[acc]);
+        __syncwarp();
+        if (++acc == acc_stages) { acc = 0; accph ^= 1u; }
       }
     }
   } else if (warp >= 4 && kFast) {
