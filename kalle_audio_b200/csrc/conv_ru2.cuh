@@ -147,7 +147,7 @@ conv_ru2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ UMMA issuer
-    if (ptx::elect_one()) {
+    {   // the whole warp walks the schedule and the barriers, one elected lane issues (see conv_umma2.cuh)
       const uint32_t idesc1 = ptx::idesc_bf16_f32(128, 256);
       const uint32_t idesc2 = ptx::idesc_bf16_f32(128, 128);
       const uint64_t desc_hi = (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -181,17 +181,20 @@ conv_ru2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             ptx::tc_fence_after();
             const uint32_t dd = dcur + half * 128;
             const uint32_t w_lo[2] = {b_lo0 + s0 * b_stage16, b_lo0 + s1 * b_stage16};
+            if (ptx::elect_one()) {
 #pragma unroll
-            for (int kc = 0; kc < 2; ++kc) {
-              const uint32_t hl = h_lo0 + kc * (16384 >> 4);
+              for (int kc = 0; kc < 2; ++kc) {
+                const uint32_t hl = h_lo0 + kc * (16384 >> 4);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                ptx::umma_f16(dd, desc_hi | (w_lo[kc] + 2 * k), desc_hi | (hl + 2 * k), idesc2, (kc | k) ? 1u : 0u);
+                for (int k = 0; k < 4; ++k)
+                  ptx::umma_f16(dd, desc_hi | (w_lo[kc] + 2 * k), desc_hi | (hl + 2 * k), idesc2, (kc | k) ? 1u : 0u);
+              }
+              ptx::umma_commit(h_empty);
+              ptx::umma_commit(&b_empty[s0]);
+              ptx::umma_commit(&b_empty[s1]);
+              ptx::umma_commit(half == 0 ? d2h_full : d2_full);
             }
-            ptx::umma_commit(h_empty);
-            ptx::umma_commit(&b_empty[s0]);
-            ptx::umma_commit(&b_empty[s1]);
-            ptx::umma_commit(half == 0 ? d2h_full : d2_full);
+            __syncwarp();
           }
           if (has_next) {
             // ---- slab s of GEMM1 of tile i + 1: chunk s / 7, tap s % 7
@@ -213,15 +216,18 @@ conv_ru2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             const uint32_t bl = b_lo0 + bs * b_stage16;
             const int cbs = bs;
             if (++bs == p.SB) { bs = 0; bph ^= 1u; }
-            if (!(p.dbg & 16) || t == 0) {
-              ptx::umma_f16(dnext, desc_hi | bl, desc_hi | al, idesc1, s ? 1u : 0u);
-              ptx::umma_f16(dnext, desc_hi | (bl + 2), desc_hi | (al + 2), idesc1, 1u);
-              ptx::umma_f16(dnext, desc_hi | (bl + 4), desc_hi | (al + 4), idesc1, 1u);
-              ptx::umma_f16(dnext, desc_hi | (bl + 6), desc_hi | (al + 6), idesc1, 1u);
+            if (ptx::elect_one()) {
+              if (!(p.dbg & 16) || t == 0) {
+                ptx::umma_f16(dnext, desc_hi | bl, desc_hi | al, idesc1, s ? 1u : 0u);
+                ptx::umma_f16(dnext, desc_hi | (bl + 2), desc_hi | (al + 2), idesc1, 1u);
+                ptx::umma_f16(dnext, desc_hi | (bl + 4), desc_hi | (al + 4), idesc1, 1u);
+                ptx::umma_f16(dnext, desc_hi | (bl + 6), desc_hi | (al + 6), idesc1, 1u);
+              }
+              ptx::umma_commit(&b_empty[cbs]);
+              if (s == 6 || s == 13) ptx::umma_commit(&a_empty[cur_a]);
+              if (s == 13) ptx::umma_commit(&d1_full[(i + 1) & 1]);
             }
-            ptx::umma_commit(&b_empty[cbs]);
-            if (s == 6 || s == 13) ptx::umma_commit(&a_empty[cur_a]);
-            if (s == 13) ptx::umma_commit(&d1_full[(i + 1) & 1]);
+            __syncwarp();
           }
         }
         if (!has_next) break;
