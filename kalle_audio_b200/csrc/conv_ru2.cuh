@@ -78,17 +78,20 @@ conv_ru2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer: ring entries in MMA issue order
-    if (ptx::elect_one()) {
+    {   // warp-uniform loop, one elected lane issues
       int bs = 0;
       uint32_t bph = 0;
       auto load_w = [&](const CUtensorMap* tm, int c0, int c2) {
         ptx::mbar_wait(&b_empty[bs], bph ^ 1u);
-        if (p.dbg & 32) {                                  // ablation: no weight loads
-          ptx::mbar_arrive(&b_full[bs]);
-        } else {
-          ptx::mbar_expect_tx(&b_full[bs], b_bytes);
-          ptx::tma_load_3d(b_ring + static_cast<size_t>(bs) * b_bytes, tm, &b_full[bs], c0, 0, c2);
+        if (ptx::elect_one()) {
+          if (p.dbg & 32) {                                // ablation: no weight loads
+            ptx::mbar_arrive(&b_full[bs]);
+          } else {
+            ptx::mbar_expect_tx(&b_full[bs], b_bytes);
+            ptx::tma_load_3d(b_ring + static_cast<size_t>(bs) * b_bytes, tm, &b_full[bs], c0, 0, c2);
+          }
         }
+        __syncwarp();
         if (++bs == p.SB) { bs = 0; bph ^= 1u; }
       };
       for (int i = -1, nxt = blockIdx.x;; ++i, nxt += gridDim.x) {
@@ -108,13 +111,13 @@ conv_ru2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // thread: in one FIFO with the weights a slab was requested only SB weight stages (~1 us) before its first MMA,
     // less than an HBM round trip, although its ring stage had been free for half a tile (profiles/r02_ru_ablation.txt:
     // removing these 67 KB per tile saved 23 % of the launch).  Here a slab is requested the moment its stage is free.
-    if (ptx::elect_one()) {
+    {   // warp-uniform loop, one elected lane issues
       int as = 0;
       uint32_t aph = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int b = tile / p.q_tiles;
         const int q0 = (tile % p.q_tiles) * 256;
-        if (p.pf) {
+        if (p.pf && ptx::elect_one()) {
           // HBM -> L2 one tile period ahead: the rows of this CTA's next tile are contiguous in both tensors
           const int t2 = tile + gridDim.x;
           if (t2 < p.total_tiles) {
@@ -133,14 +136,17 @@ conv_ru2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         for (int ch = 0; ch < 2; ++ch) {
           ptx::mbar_wait(&a_empty[as], aph ^ 1u);
-          if (p.dbg & 64) {                              // ablation: no activation loads
-            ptx::mbar_arrive(&a_full[as]);
-          } else {
-            ptx::mbar_expect_tx(&a_full[as], a_bytes);
-            for (int bx = 0; bx < p.nbox; ++bx)
-              ptx::tma_load_4d(a_ring + static_cast<size_t>(as) * a_bytes + bx * p.RB * 128, &tmA, &a_full[as], ch * 64, 0,
-                               q0 + p.slab_row0 + bx * p.RB, b);
+          if (ptx::elect_one()) {
+            if (p.dbg & 64) {                            // ablation: no activation loads
+              ptx::mbar_arrive(&a_full[as]);
+            } else {
+              ptx::mbar_expect_tx(&a_full[as], a_bytes);
+              for (int bx = 0; bx < p.nbox; ++bx)
+                ptx::tma_load_4d(a_ring + static_cast<size_t>(as) * a_bytes + bx * p.RB * 128, &tmA, &a_full[as], ch * 64, 0,
+                                 q0 + p.slab_row0 + bx * p.RB, b);
+            }
           }
+          __syncwarp();
           if (++as == p.SA) { as = 0; aph ^= 1u; }
         }
       }

@@ -199,9 +199,11 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   // been free for much longer; on its own thread a slab is requested the moment its stage is released.
   // KVAE_SPLIT_PRODUCER=0 (ConvParams2::one_producer) restores the single FIFO for A/B measurements.
   if (warp == 0 || warp == 3) {
-    if (ptx::elect_one()) {
+    // (warp-uniform loops, one elected lane issues -- see the UMMA issuer below)
+    {
       const bool do_a = p.one_producer ? warp == 0 : warp == 3;
       const bool do_w = warp == 0;
+      const int SA = p.SA, SB = p.SB, nbox = p.nbox, RB = p.RB;
       int as = 0, bs = 0;
       uint32_t aph = 0, bph = 0;
       if (do_a || do_w)
@@ -222,19 +224,25 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint32_t tl = p.tap_ld[t];
             if (do_a && (p.tap_mma[t] & 0x10000u)) {
               if (p.park & 2) ptx::mbar_wait_parked(&a_empty[as], aph ^ 1u); else ptx::mbar_wait(&a_empty[as], aph ^ 1u);
-              ptx::mbar_expect_tx(&a_full[as], a_bytes);
-              const int row = q0 + (static_cast<int32_t>(tl) >> 16);
-              for (int bx = 0; bx < p.nbox; ++bx)
-                ptx::tma_load_4d(a_ring + static_cast<size_t>(as) * a_bytes + bx * p.RB * 128, &tmA, &a_full[as],
-                                 a_col, tl & 0xff, row + bx * p.RB, b);
-              if (++as == p.SA) { as = 0; aph ^= 1u; }
+              if (ptx::elect_one()) {
+                ptx::mbar_expect_tx(&a_full[as], a_bytes);
+                const int row = q0 + (static_cast<int32_t>(tl) >> 16);
+                for (int bx = 0; bx < nbox; ++bx)
+                  ptx::tma_load_4d(a_ring + static_cast<size_t>(as) * a_bytes + bx * RB * 128, &tmA, &a_full[as],
+                                   a_col, tl & 0xff, row + bx * RB, b);
+              }
+              __syncwarp();
+              if (++as == SA) { as = 0; aph ^= 1u; }
             }
             if (do_w) {
               if (p.park & 2) ptx::mbar_wait_parked(&b_empty[bs], bph ^ 1u); else ptx::mbar_wait(&b_empty[bs], bph ^ 1u);
-              ptx::mbar_expect_tx(&b_full[bs], b_bytes);
-              ptx::tma_load_3d(b_ring + static_cast<size_t>(bs) * b_bytes, &tmW, &b_full[bs], w_col, n0,
-                               (tl >> 8) & 0xff);
-              if (++bs == p.SB) { bs = 0; bph ^= 1u; }
+              if (ptx::elect_one()) {
+                ptx::mbar_expect_tx(&b_full[bs], b_bytes);
+                ptx::tma_load_3d(b_ring + static_cast<size_t>(bs) * b_bytes, &tmW, &b_full[bs], w_col, n0,
+                                 (tl >> 8) & 0xff);
+              }
+              __syncwarp();
+              if (++bs == SB) { bs = 0; bph ^= 1u; }
             }
           }
         }
