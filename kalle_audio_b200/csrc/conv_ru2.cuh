@@ -269,16 +269,18 @@ conv_ru2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       ptx::mbar_expect_tx(&my_res_full[slot], kRuActBlk);
       ptx::tma_load_4d(ring + slot * kRuActBlk, &tmX, &my_res_full[slot], cbase, 0, tq0 + item * 16, tb);
     };
-    if (lane == 0 && use_skip && static_cast<int>(blockIdx.x) < p.total_tiles)
+    if (use_skip && static_cast<int>(blockIdx.x) < p.total_tiles && ptx::elect_one())
       issue_skip(blockIdx.x / p.q_tiles, (blockIdx.x % p.q_tiles) * 256, sub, 0);
     int slot = 0;
     uint32_t he_ph = 0, d2f_ph = 0, res_ph = 0;
     int it = 0;                                          // this CTA's it-th tile: accumulator buffer it & 1
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int b = tile / p.q_tiles;
-      const int q0 = (tile % p.q_tiles) * 256;
+      // (quotients come out of the vector ALU; the lane-0 broadcast tells ptxas they are warp-uniform, so the TMA
+      // coordinates built from them sit in uniform registers instead of going through an R2UR waterfall loop per issue)
+      const int b = __shfl_sync(0xffffffffu, tile / p.q_tiles, 0);
+      const int q0 = __shfl_sync(0xffffffffu, (tile % p.q_tiles) * 256, 0);
       const int ntile = tile + gridDim.x;                // this CTA's next tile (its first skip block is prefetched below)
-      const int nb = ntile / p.q_tiles, nq0 = (ntile % p.q_tiles) * 256;
+      const int nb = __shfl_sync(0xffffffffu, ntile / p.q_tiles, 0), nq0 = __shfl_sync(0xffffffffu, (ntile % p.q_tiles) * 256, 0);
       const uint32_t boff = static_cast<uint32_t>(it & 1) * 256;
       // ---- EPI1 share: D1 -> bias, SnakeBeta -> h
       {
@@ -334,7 +336,7 @@ conv_ru2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           ptx::mbar_wait_parked(d2_full, d2f_ph);
           ptx::tc_fence_after();
         }
-        if (lane == 0) {
+        if (ptx::elect_one()) {
           // every store issued so far has read its shared-memory source: the other stream slot and the operand
           // block are free again; fetch the NEXT item's skip block into the other slot
           ptx::bulk_wait_read<0>();
@@ -409,7 +411,7 @@ conv_ru2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         ptx::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
+        if (ptx::elect_one()) {
           uint8_t* const rblk = ring + slot * kRuActBlk;
           if (p.raw_out && !(p.dbg & 2)) ptx::tma_store_4d(&tmR, rblk, cbase, 0, r0, b);
           if (p.act_out && !(p.dbg & 2)) ptx::tma_store_4d(&tmO, ablk, cbase, 0, r0, b);

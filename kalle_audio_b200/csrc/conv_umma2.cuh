@@ -356,17 +356,26 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       ptx::tma_load_4d(ring + slot * slot_bytes, &tmX, &my_res_full[slot], cb, ph, row, bb);
       if (kBwd && p.bwd_skip) ptx::tma_load_4d(ring + slot * slot_bytes + kFastBlk, &tmR, &my_res_full[slot], cb, ph, row, bb);
     };
+    // decode() divides in the vector ALU; the lane-0 broadcast tells ptxas the results are warp-uniform, so the TMA
+    // coordinates built from them sit in uniform registers instead of going through an R2UR waterfall loop per issue
+    auto decode_u = [&](int t, int& ob, int& oq0, int& ophi, int& on0) {
+      decode(t, ob, oq0, ophi, on0);
+      ob = __shfl_sync(0xffffffffu, ob, 0);
+      oq0 = __shfl_sync(0xffffffffu, oq0, 0);
+      ophi = __shfl_sync(0xffffffffu, ophi, 0);
+      on0 = __shfl_sync(0xffffffffu, on0, 0);
+    };
     int tile = blockIdx.x;
     int b = 0, q0 = 0, phi = 0, n0 = 0;
-    if (tile < p.total_tiles) decode(tile, b, q0, phi, n0);
-    if (has_res && lane == 0 && tile < p.total_tiles) issue_skip(n0 + quad * 32, phi, q0 + sub * 16, b, 0);
+    if (tile < p.total_tiles) decode_u(tile, b, q0, phi, n0);
+    if (has_res && tile < p.total_tiles && ptx::elect_one()) issue_skip(n0 + quad * 32, phi, q0 + sub * 16, b, 0);
     int acc = 0, jr = 0, ja = 0;
     uint32_t accph = 0, res_ph = 0;
     float acc_da[4] = {0.f, 0.f, 0.f, 0.f}, acc_db[4] = {0.f, 0.f, 0.f, 0.f}, acc_bias[4] = {0.f, 0.f, 0.f, 0.f};
     for (; tile < p.total_tiles; tile += gridDim.x) {
       const int ntile = tile + gridDim.x;    // this CTA's next tile: its first skip block is prefetched during the last item
       int nb = 0, nq0 = 0, nphi = 0, nn0 = 0;
-      if (ntile < p.total_tiles) decode(ntile, nb, nq0, nphi, nn0);
+      if (ntile < p.total_tiles) decode_u(ntile, nb, nq0, nphi, nn0);
       const int cbase = n0 + quad * 32;
       uint64_t kb[4], ka[4], kib[4];         // index 2 * lane half + hi: channel cbase + 16 L + 8 hi + g8
       float bw_a[4], bw_ib[4];
@@ -389,7 +398,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int item = sub; item < n_items; item += 4) {
         const int r0 = q0 + item * 16;
         const int sn = (jr + 1 == R) ? 0 : jr + 1;
-        if (lane == 0) {
+        if (ptx::elect_one()) {
           // all but the newest store group have read their blocks: slot sn (last used two items ago) and the other
           // operand block are free; fetch the NEXT item's skip block
           ptx::bulk_wait_read<1>();
@@ -494,7 +503,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }   // !kBwd
         ptx::fence_proxy_async();
         __syncwarp();
-        if (lane == 0) {
+        if (ptx::elect_one()) {
           if (raw_out) ptx::tma_store_4d(&tmR, ring + jr * slot_bytes, cbase, phi, r0, b);
           if (act_out) ptx::tma_store_4d(&tmO, aring + ja * kFastBlk, cbase, phi, r0, b);
           ptx::bulk_commit();                // (an empty group when only the skip block was consumed keeps the count uniform)
