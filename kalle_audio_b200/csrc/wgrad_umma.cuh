@@ -100,30 +100,34 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (ptx::elect_one()) {
+    // (warp-uniform loop, one elected lane issues: the loop state stays in uniform registers -- conv_umma2.cuh)
+    {
       int st = 0;
       uint32_t ph = 0;
       for (long long it = it0; it < it1; ++it) {
-        const int b = static_cast<int>(it / p.chunks_per_clip);
-        const int r0 = static_cast<int>(it % p.chunks_per_clip) * p.R;
+        const int b = __shfl_sync(0xffffffffu, static_cast<int>(it / p.chunks_per_clip), 0);
+        const int r0 = __shfl_sync(0xffffffffu, static_cast<int>(it % p.chunks_per_clip) * p.R, 0);
         ptx::mbar_wait(&empty[st], ph ^ 1u);
-        ptx::mbar_expect_tx(&full[st], stage_bytes);
-        uint8_t* dst = ring + static_cast<size_t>(st) * stage_bytes;
-        ptx::tma_load_4d(dst, &tmD, &full[st], cd0, 0, r0, b);
-        ptx::tma_load_4d(dst + d_half, &tmD, &full[st], cd0 + 64, 0, r0, b);
-        dst += 2 * d_half;
-        for (int s = 0; s < nslabs; ++s) {
-          const int row = r0 + p.s_row0[grp][s];
-          ptx::tma_load_4d(dst, &tmS, &full[st], cs0, p.s_phase[grp][s], row, b);
-          ptx::tma_load_4d(dst + s_half, &tmS, &full[st], cs0 + 64, p.s_phase[grp][s], row, b);
-          dst += 2 * s_half;
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(&full[st], stage_bytes);
+          uint8_t* dst = ring + static_cast<size_t>(st) * stage_bytes;
+          ptx::tma_load_4d(dst, &tmD, &full[st], cd0, 0, r0, b);
+          ptx::tma_load_4d(dst + d_half, &tmD, &full[st], cd0 + 64, 0, r0, b);
+          dst += 2 * d_half;
+          for (int s = 0; s < nslabs; ++s) {
+            const int row = r0 + p.s_row0[grp][s];
+            ptx::tma_load_4d(dst, &tmS, &full[st], cs0, p.s_phase[grp][s], row, b);
+            ptx::tma_load_4d(dst + s_half, &tmS, &full[st], cs0 + 64, p.s_phase[grp][s], row, b);
+            dst += 2 * s_half;
+          }
         }
+        __syncwarp();
         if (++st == p.NS) { st = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ UMMA issuer
-    if (ptx::elect_one()) {
+    {   // warp-uniform loop, one elected lane issues
       const uint32_t idesc = ptx::idesc_bf16_f32_mn(128, 128);
       // MN-major SW128 descriptors: LBO = distance between 64-channel halves, SBO = 1024 B (8 time rows)
       const uint64_t hi_common = (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -131,9 +135,12 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant
       const uint64_t s_hi = hi_common | (static_cast<uint64_t>(s_half >> 4) << 16);
       const uint32_t ring_lo = (ptx::smem_u32(ring) & 0x3FFFFu) >> 4;
       const int ksteps = p.R / 16;
-      uint32_t tap_off[kWgMaxTaps];          // (slab offset + shift rows) >> 4, relative to the stage's S area
-      for (int t = 0; t < ntaps; ++t)
-        tap_off[t] = (static_cast<uint32_t>(p.g_slab[grp][t]) * 2 * s_half + static_cast<uint32_t>(p.g_shift[grp][t]) * 128) >> 4;
+      // lane t holds tap t's (slab offset + shift rows) >> 4, relative to the stage's S area; read back by shuffle
+      const int tl = lane < ntaps ? lane : 0;
+      const uint32_t my_tap_off = (static_cast<uint32_t>(p.g_slab[grp][tl]) * 2 * s_half + static_cast<uint32_t>(p.g_shift[grp][tl]) * 128) >> 4;
+      uint32_t toff[kWgMaxTaps];
+#pragma unroll
+      for (int t = 0; t < kWgMaxTaps; ++t) toff[t] = __shfl_sync(0xffffffffu, my_tap_off, t);
       int st = 0;
       uint32_t ph = 0, accum = 0;
       for (long long it = it0; it < it1; ++it) {
@@ -141,17 +148,23 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmD, const __grid_constant
         ptx::tc_fence_after();
         const uint32_t d_lo = ring_lo + ((static_cast<uint32_t>(st) * stage_bytes) >> 4);
         const uint32_t s_lo = d_lo + ((2 * d_half) >> 4);
-        for (int j = 0; j < ksteps; ++j) {
-          const uint32_t koff = static_cast<uint32_t>(j) * (2048 >> 4);       // 16 time rows
-          for (int t = 0; t < ntaps; ++t)
-            ptx::umma_f16(tmem_base + t * 128, d_hi | ((d_lo + koff) & 0x3FFFu), s_hi | ((s_lo + tap_off[t] + koff) & 0x3FFFu),
-                          idesc, accum);
-          accum = 1u;
+        if (ptx::elect_one()) {
+          for (int j = 0; j < ksteps; ++j) {
+            const uint32_t koff = static_cast<uint32_t>(j) * (2048 >> 4);       // 16 time rows
+#pragma unroll
+            for (int t = 0; t < kWgMaxTaps; ++t)
+              if (t < ntaps)
+                ptx::umma_f16(tmem_base + t * 128, d_hi | ((d_lo + koff) & 0x3FFFu), s_hi | ((s_lo + toff[t] + koff) & 0x3FFFu),
+                              idesc, (j | static_cast<int>(accum)) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty[st]);
         }
-        ptx::umma_commit(&empty[st]);
+        __syncwarp();
+        accum = 1u;
         if (++st == p.NS) { st = 0; ph ^= 1u; }
       }
-      ptx::umma_commit(acc_full);
+      if (ptx::elect_one()) ptx::umma_commit(acc_full);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue: accumulators -> packed dW (reductions)
