@@ -443,6 +443,21 @@ inline bool prepare_conv_umma2(const ConvGeom& g, const __nv_bfloat16* x, int B,
     p.SA = 2;
     p.SB = static_cast<int>(std::min<size_t>(8, (budget - 2 * a_bytes) / b_bytes));
     while (p.SA < 4 && (p.SA + 1) * a_bytes + p.SB * b_bytes <= budget) ++p.SA;
+    {
+      // Light-GEMM layers (k = 1, strided and transposed convs: at most two weight stages per activation slab) consume
+      // an activation stage every 4-8 MMAs, so with two stages the slab ring covers less than one L2 round trip while
+      // the weight ring sits on 4-5 stages it cannot use: give the third slab stage priority over weight stages
+      // (k1 C512 0.233 -> 0.190 ms, strided 256 -> 512 0.469 -> 0.394 ms, ConvTranspose 512 -> 256 0.502 -> 0.446 ms
+      // at 16 clips; the k = 7 layers keep two slab stages, each serves seven weight stages).
+      int n_slabs = 0;
+      for (int t = tp.tap_begin[0]; t < tp.tap_begin[1]; ++t) n_slabs += tp.taps[t].first ? 1 : 0;
+      const int n_taps = tp.tap_begin[1] - tp.tap_begin[0];
+      static const bool deep_a = [] { const char* e = getenv("KVAE_DEEP_A"); return !(e && e[0] == '0'); }();
+      if (deep_a && p.SA < 3 && n_taps <= 2 * std::max(1, n_slabs) && 3 * a_bytes + 2 * b_bytes <= budget) {
+        p.SA = 3;
+        p.SB = static_cast<int>(std::min<size_t>(8, (budget - 3 * a_bytes) / b_bytes));
+      }
+    }
     if (const char* e = getenv("KVAE_SA")) {   // tuning experiments: deeper / shallower activation ring
       const int sa = std::max(1, std::min(8, atoi(e)));
       if (sa * a_bytes + 2 * b_bytes <= budget) {
