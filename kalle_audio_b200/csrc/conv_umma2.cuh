@@ -5,17 +5,20 @@
 //     in flight while tile i is still being multiplied / written out;
 //   * the accumulator lives in TMEM twice (2 x MT*NT columns) when that fits in 512 columns: the UMMA
 //     issuer starts tile i+1 as soon as its operands land while the epilogue drains tile i;
-//   * 8 epilogue warps (two warpgroups, each covering the 128 TMEM lanes) split a tile's 32-column
-//     blocks between them;
-//   * every epilogue warp runs its own little pipeline over 32-row x 32-channel blocks, with no
-//     block-level barrier: lane 0 prefetches the block's ResidualUnit skip (fp32 stream) with a TMA
-//     load one block ahead, every lane adds its row, writes the result IN PLACE into the same swizzled
-//     shared-memory block (conflict-free) plus the SnakeBeta-activated bf16 block, and lane 0 hands both
-//     to TMA stores; the bulk-group mechanism recycles the blocks.  Every HBM access is a full line
-//     and no thread waits on a store.
+//   * three instantiations.  <0>: 8 epilogue warps (two warpgroups, each covering the 128 TMEM lanes), every warp its own
+//     little pipeline over 32-row x 32-channel blocks with no block-level barrier -- the generic epilogue (fp32
+//     streams, bf16x3 split, channels-first output, time-on-M tiles).  <1> / <2>: 16 epilogue warps (four per TMEM lane
+//     quadrant) on 16-row x 32-channel items with a specialised fragment-mapped epilogue -- <1> the forward launches
+//     in the swap orientation with 2-byte stream / operand blocks (every tensor-core conv of an inference plan and of
+//     the training forward), <2> the data-gradient launches with the fused SnakeBeta backward;
+//   * in every epilogue one elected lane prefetches the item's ResidualUnit skip block with a TMA load one item
+//     ahead, every lane adds its part, writes the result IN PLACE into the same swizzled shared-memory block
+//     (conflict-free) plus the SnakeBeta-activated bf16 block, and the elected lane hands both to TMA stores; the
+//     bulk-group mechanism recycles the blocks.  Every HBM access is a full line and no thread waits on a store.
 //
-// Warp roles (384 threads): warp 0 TMA producer, warp 1 UMMA issuer, warp 2 TMEM allocator, warp 3 idle,
-// warps 4-11 epilogue.
+// Warp roles (384 threads in <0>, 640 in <1> / <2>): warp 0 weight TMA producer, warp 1 UMMA issuer, warp 2 TMEM
+// allocator, warp 3 activation-slab TMA producer, warps 4.. epilogue.  Producers and issuer run WARP-UNIFORM loops with
+// an elected lane doing the issue (loop state in uniform registers).
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
