@@ -246,6 +246,24 @@ int kvae_conv1d_bwd(const void* x, const void* gy, const float* w_folded, void* 
                     int transposed, int B, int Cin, int Cout, long long T, int K, int stride, int dilation, int padding,
                     int dtype, void* scratch, size_t scratch_bytes, void* stream);
 
+/* ---- Multi-resolution STFT loss of the autoencoder training wrapper (loss half) ----
+ * training/losses/auraloss.py: MultiResolutionSTFTLoss (443-531) / SumAndDifferenceSTFTLoss (534-606) over STFTLoss
+ * (220-441: torch.stft with reflect padding and a periodic Hann window, magnitude sqrt(clamp(re^2 + im^2, 1e-8)),
+ * w_sc * spectral convergence + w_log_mag * L1 of the log magnitudes) with the optional A-weighting pre-filter
+ * (FIRFilter "aw", 70-162), as instantiated at training/autoencoders.py:123-129 and called at :163 as
+ * module(input = reals, target = decoded).  input / target [B, C, T] of `dtype`; loss: one device float;
+ * grad_input / grad_target: optional device fp32 [B, C, T] (d loss / d argument, overwritten).
+ *   fft_sizes / hop_sizes: n_res host ints (fft sizes powers of two in [8, 2048]); windows: device fp32, the n_res
+ *   analysis windows back to back, each ALREADY zero-padded to its fft size (torch.stft centres a shorter window);
+ *   fir_taps: device fp32 [n_taps] (odd, <= 129) or NULL for no pre-filter; sum_diff = 1: stereo sum / difference
+ *   signals weighted w_sum / w_diff and averaged (C must be 2), 0: every channel is a signal (view(-1, T)).
+ * Nothing of spectrogram size is stored: the backward pass transforms the frames again. */
+size_t kvae_mrstft_scratch_bytes(int B, int C, long long T, int n_res, int sum_diff, int want_grad);
+int kvae_mrstft_loss(const void* input, const void* target, int B, int C, long long T, int dtype, int n_res,
+                     const int* fft_sizes, const int* hop_sizes, const float* windows, const float* fir_taps, int n_taps,
+                     int sum_diff, float w_sum, float w_diff, float w_sc, float w_log_mag, float* loss, float* grad_input,
+                     float* grad_target, void* scratch, size_t scratch_bytes, void* stream);
+
 /* ---- BigVGANFlowVAE inference path (backup/flows.py:396-529: the reference's 12.5 Hz VAE) -- leaf kernels ----
  * Activation1d of the AMP blocks (alias_free_torch, un-vendored; flows.py:266, 312, 443): x2 Kaiser-sinc upsampling
  * (replicate padding) -> Snake (beta == NULL: x + sin^2(a x)/a) or SnakeBeta (x + sin^2(a x)/b) -> low-pass and x2

@@ -27,6 +27,7 @@
 #include "elementwise.cuh"
 #include "glue.cuh"
 #include "bigvgan.cuh"
+#include "mrstft.cuh"
 #include "train.cuh"
 
 using namespace kvae;
@@ -1990,6 +1991,91 @@ int kvae_conv1d_tc_fwd(const void* x, void* y, const float* w, const float* bias
   if (!prepare_conv_umma2(g, xcl, B, static_cast<int>(T), w_umma, ep, tune, L, err, truncated ? &sg : nullptr)) return fail(err);
   KV_CUDA(launch_conv_umma2(L, st));
   g_launches += 3;
+  return 0;
+}
+
+// ------------------------------------------------------------------ multi-resolution STFT loss (mrstft.cuh)
+namespace {
+int mrstft_signals(int B, int C, int sum_diff) { return sum_diff ? 2 * B : B * C; }
+}
+size_t kvae_mrstft_scratch_bytes(int B, int C, long long T, int n_res, int sum_diff, int want_grad) {
+  if (B <= 0 || C <= 0 || T <= 0 || n_res <= 0) return 0;
+  const size_t M = static_cast<size_t>(mrstft_signals(B, C, sum_diff));
+  const size_t sig = align_up(M * static_cast<size_t>(T) * 4, 1024);
+  return (want_grad ? 4 : 2) * sig + align_up(static_cast<size_t>(n_res) * M * 3 * 8, 1024);
+}
+
+int kvae_mrstft_loss(const void* input, const void* target, int B, int C, long long T, int dtype, int n_res,
+                     const int* fft_sizes, const int* hop_sizes, const float* windows, const float* fir_taps, int n_taps,
+                     int sum_diff, float w_sum, float w_diff, float w_sc, float w_log_mag, float* loss, float* grad_input,
+                     float* grad_target, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!input || !target || !fft_sizes || !hop_sizes || !windows || !loss || !scratch) return fail("null argument");
+  if (!check_dtype(dtype)) return fail("bad dtype");
+  if (B <= 0 || C <= 0 || T <= 0) return fail("empty input");
+  if (n_res <= 0 || n_res > kStftMaxRes) return fail("mrstft: 1..16 resolutions");
+  if (sum_diff && C != 2) return fail("mrstft: the sum-and-difference form needs stereo input");
+  if (n_taps < 0 || n_taps > kFirMaxTaps || (n_taps && !(n_taps & 1)) || (n_taps && !fir_taps)) return fail("mrstft: the pre-filter needs an odd number of taps <= 129");
+  const bool want_grad = grad_input || grad_target;
+  if (scratch_bytes < kvae_mrstft_scratch_bytes(B, C, T, n_res, sum_diff, want_grad)) return fail("scratch too small");
+  const int M = mrstft_signals(B, C, sum_diff);
+  if (M > 65535) return fail("mrstft: too many signals");
+  StftRes res[kStftMaxRes];
+  for (int r = 0; r < n_res; ++r) {
+    const int n = fft_sizes[r];
+    int l2 = 0;
+    while ((1 << l2) < n) ++l2;
+    if (n < 8 || n > kStftMaxN || (1 << l2) != n) return fail("mrstft: fft sizes must be powers of two in [8, 2048]");
+    if (hop_sizes[r] <= 0) return fail("mrstft: bad hop size");
+    if (T <= n / 2) return fail("mrstft: signal shorter than half an fft frame (reflect padding)");
+    res[r] = StftRes{n, l2, hop_sizes[r], static_cast<int>(1 + T / hop_sizes[r])};
+  }
+  DeviceGuard guard(device_of(input));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t sig = align_up(static_cast<size_t>(M) * T * 4, 1024);
+  uint8_t* sp = static_cast<uint8_t*>(scratch);
+  float* Xf = reinterpret_cast<float*>(sp);
+  float* Yf = reinterpret_cast<float*>(sp + sig);
+  float* gX = want_grad ? reinterpret_cast<float*>(sp + 2 * sig) : nullptr;
+  float* gY = want_grad ? reinterpret_cast<float*>(sp + 3 * sig) : nullptr;
+  double* sums = reinterpret_cast<double*>(sp + (want_grad ? 4 : 2) * sig);
+  KV_CUDA(cudaMemsetAsync(sums, 0, static_cast<size_t>(n_res) * M * 3 * 8, st));
+  KV_CUDA(cudaMemsetAsync(loss, 0, 4, st));
+  if (want_grad) KV_CUDA(cudaMemsetAsync(gX, 0, 2 * sig, st));
+  const dim3 pgrid(static_cast<unsigned>((T + kFirTile - 1) / kFirTile), M);
+  const int f32 = dtype == KVAE_F32;
+  mrstft_prep_kernel<<<pgrid, 256, 0, st>>>(input, f32, sum_diff, B, T, fir_taps, n_taps, Xf);
+  mrstft_prep_kernel<<<pgrid, 256, 0, st>>>(target, f32, sum_diff, B, T, fir_taps, n_taps, Yf);
+  KV_CUDA(cudaGetLastError());
+  g_launches += 2;
+  const int Mg = sum_diff ? B : M, n_groups = sum_diff ? 2 : 1;
+  const float wg0 = sum_diff ? 0.5f * w_sum : 1.f, wg1 = sum_diff ? 0.5f * w_diff : 1.f;
+  const float* win = windows;
+  for (int r = 0; r < n_res; ++r) {
+    const int fpb = kStftMaxN / res[r].n;
+    const dim3 grid((res[r].frames + fpb - 1) / fpb, M);
+    mrstft_fwd_kernel<<<grid, 256, 0, st>>>(Xf, Yf, win, res[r], T, sums + static_cast<size_t>(r) * M * 3);
+    mrstft_finish_kernel<<<1, 256, 0, st>>>(sums + static_cast<size_t>(r) * M * 3, M, Mg, w_sc, w_log_mag, wg0, wg1, n_groups,
+                                            1.0 / n_res, static_cast<double>(res[r].n / 2 + 1) * res[r].frames, loss);
+    win += res[r].n;
+    g_launches += 2;
+  }
+  KV_CUDA(cudaGetLastError());
+  if (!want_grad) return 0;
+  win = windows;
+  for (int r = 0; r < n_res; ++r) {
+    const int fpb = kStftMaxN / res[r].n;
+    const dim3 grid((res[r].frames + fpb - 1) / fpb, M);
+    mrstft_bwd_kernel<<<grid, 256, 0, st>>>(Xf, Yf, win, res[r], T, sums + static_cast<size_t>(r) * M * 3, Mg, w_sc, w_log_mag,
+                                            wg0, wg1, n_groups, 1.f / n_res, grad_input ? gX : nullptr, grad_target ? gY : nullptr);
+    win += res[r].n;
+    ++g_launches;
+  }
+  KV_CUDA(cudaGetLastError());
+  const dim3 tgrid(static_cast<unsigned>((T + kFirTile - 1) / kFirTile), sum_diff ? B : M);
+  if (grad_input) { mrstft_prep_T_kernel<<<tgrid, 256, 0, st>>>(gX, sum_diff, B, C, T, fir_taps, n_taps, 1.f, grad_input); ++g_launches; }
+  if (grad_target) { mrstft_prep_T_kernel<<<tgrid, 256, 0, st>>>(gY, sum_diff, B, C, T, fir_taps, n_taps, 1.f, grad_target); ++g_launches; }
+  KV_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -373,7 +373,63 @@ def bigvgan_fixtures():
     torch.set_grad_enabled(True)
 
 
+
+MRSTFT_ARGS = dict(fft_sizes=[2048, 1024, 512, 256, 128, 64, 32], hop_sizes=[512, 256, 128, 64, 32, 16, 8],
+                   win_lengths=[2048, 1024, 512, 256, 128, 64, 32], perceptual_weighting=True)
+
+
+def mrstft_fixtures():
+    """SURVEY section 8(f) item 4 (loss half): the reference's own auraloss copy (training/losses/auraloss.py:443-606)
+    with the stft_loss_args of the Stable Audio autoencoder configs, called the way the training wrapper calls it
+    (training/autoencoders.py:163: AuralossLoss(self.sdstft, 'reals', 'decoded') -> module(input = reals, target =
+    decoded), so the gradient that matters is the one w.r.t. the TARGET argument).  Values + autograd gradients w.r.t.
+    both arguments, for the stereo sum-and-difference form, the plain multi-resolution form on stereo and on mono
+    input, and a short-window variant (win_length < fft_size, no pre-filter)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_auraloss", os.path.join(REF, "stable_audio_tools", "training", "losses",
+                                                                               "auraloss.py"))
+    al = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(al)
+    torch.manual_seed(11)
+    T = 4500
+    out = {}
+
+    def signals(B, C):
+        t = torch.arange(T, dtype=torch.float32) / 44100.0
+        base = 0.3 * torch.sin(2 * np.pi * 440.0 * t) + 0.1 * torch.sin(2 * np.pi * 3100.0 * t + 0.5)
+        x = (base + 0.05 * torch.randn(B, C, T)).contiguous()
+        y = (0.9 * base + 0.07 * torch.randn(B, C, T)).contiguous()
+        return x, y
+
+    def run(tag, mod, x, y):
+        x = x.clone().requires_grad_(True)
+        y = y.clone().requires_grad_(True)
+        loss = mod(x, y)
+        gx, gy = torch.autograd.grad(loss, (x, y))
+        out[f"{tag}.loss"] = np.float64(loss.item())
+        out[f"{tag}.gx"] = gx.numpy()
+        out[f"{tag}.gy"] = gy.numpy()
+        print(tag, "loss", loss.item(), "|gx|", float(gx.abs().max()), "|gy|", float(gy.abs().max()))
+
+    x2, y2 = signals(2, 2)
+    out["x2"], out["y2"] = x2.numpy(), y2.numpy()
+    run("sd", al.SumAndDifferenceSTFTLoss(sample_rate=44100, **MRSTFT_ARGS), x2, y2)
+    run("mr_stereo", al.MultiResolutionSTFTLoss(sample_rate=44100, **MRSTFT_ARGS), x2, y2)
+    x1, y1 = signals(2, 1)
+    out["x1"], out["y1"] = x1.numpy(), y1.numpy()
+    run("mr_mono", al.MultiResolutionSTFTLoss(sample_rate=44100, **MRSTFT_ARGS), x1, y1)
+    run("short_win", al.MultiResolutionSTFTLoss(fft_sizes=[1024, 2048, 512], hop_sizes=[120, 240, 50],
+                                                win_lengths=[600, 1200, 240]), x1, y1)
+    # the A-weighting FIR taps the reference designs with scipy (101 taps at 44.1 kHz)
+    out["aw_taps_44100"] = al.FIRFilter(filter_type="aw", fs=44100).fir.weight.data.view(-1).numpy()
+    np.savez_compressed(os.path.join(HERE, "mrstft.npz"), **out)
+    print("wrote mrstft.npz", os.path.getsize(os.path.join(HERE, "mrstft.npz")) // 1024, "KiB")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "mrstft":
+        mrstft_fixtures()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "bigvgan":
         bigvgan_fixtures()
         return
