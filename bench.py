@@ -439,6 +439,7 @@ def run_cuda(args):
         if world == 1:
             legs += [("config4_stream", lambda: measure_stream(args, dev)),
                      ("bigvgan_decode", lambda: measure_bigvgan(args, dev)),
+                     ("mrstft_loss", lambda: measure_mrstft(args, dev)),
                      ("gpu_eager_baseline", lambda: gpu_eager_baseline(dev))]
         for name, fn in legs:
             try:
@@ -642,6 +643,67 @@ def measure_bigvgan(args, dev):
         ms = e0.elapsed_time(e1) / n
         out[prec + "_mode"] = {"value": audio_s / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
                                "tflops": B * fl / (ms * 1e-3) / 1e12}
+    return out
+
+
+def measure_mrstft(args, dev):
+    """SURVEY section 8(f) item 4 (loss half): the spectral loss of the reference's autoencoder training wrapper
+    (SumAndDifferenceSTFTLoss with the 7 resolutions 2048 .. 32 and A-weighting, training/autoencoders.py:123-129) at the
+    training batch of BASELINE configs[4] (4 clips x 5.016 s stereo): value + gradient w.r.t. the decoded signal through
+    kvae_mrstft_loss, next to the same loss written with torch.stft (cuFFT) + autograd on the same GPU."""
+    import torch
+    import kalle_audio_b200 as k
+    A = dict(fft_sizes=[2048, 1024, 512, 256, 128, 64, 32], hop_sizes=[512, 256, 128, 64, 32, 16, 8],
+             win_lengths=[2048, 1024, 512, 256, 128, 64, 32], perceptual_weighting=True, sample_rate=44100)
+    mod = k.SumAndDifferenceSTFTLoss(**A)
+    torch.manual_seed(0)
+    B, T = 4, 221184
+    x = 0.1 * torch.randn(B, 2, T, device=dev)
+    y = (0.9 * x + 0.02 * torch.randn_like(x)).requires_grad_(True)
+    taps = mod.fir_taps.to(dev).view(1, 1, -1)
+
+    def ours():
+        l = mod(x, y)
+        l.backward()
+        y.grad = None
+        return l
+
+    def eager():
+        tot = 0.0
+        for sx_, sy_ in ((x[:, 0] + x[:, 1], y[:, 0] + y[:, 1]), (x[:, 0] - x[:, 1], y[:, 0] - y[:, 1])):
+            fx = torch.nn.functional.conv1d(sx_.unsqueeze(1), taps, padding=50).squeeze(1)
+            fy = torch.nn.functional.conv1d(sy_.unsqueeze(1), taps, padding=50).squeeze(1)
+            acc = 0.0
+            for n, h in zip(A["fft_sizes"], A["hop_sizes"]):
+                w = torch.hann_window(n, device=dev)
+                a = torch.stft(fx, n, h, n, w, return_complex=True)
+                b = torch.stft(fy, n, h, n, w, return_complex=True)
+                am = torch.sqrt(torch.clamp(a.real ** 2 + a.imag ** 2, min=1e-8))
+                bm = torch.sqrt(torch.clamp(b.real ** 2 + b.imag ** 2, min=1e-8))
+                sc = (torch.norm(bm - am, p="fro", dim=[-1, -2]) / torch.norm(bm, p="fro", dim=[-1, -2])).mean()
+                acc = acc + sc + torch.nn.functional.l1_loss(torch.log(am), torch.log(bm))
+            tot = tot + acc / len(A["fft_sizes"])
+        l = tot / 2
+        l.backward()
+        y.grad = None
+        return l
+
+    out = {"config": {"workload": f"SumAndDifferenceSTFTLoss (7 resolutions, A-weighting), {B} x 2 x {T} samples, value + "
+                                  "gradient w.r.t. the decoded signal"}}
+    for name, fn in (("kvae", ours), ("torch_eager_cufft", eager)):
+        for _ in range(3):
+            l = fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n = max(3, args.steps // 2)
+        for _ in range(n):
+            l = fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        out[name] = {"ms_fwd_bwd": e0.elapsed_time(e1) / n, "loss": float(l.detach())}
+    # signal bytes one call has to touch at least: read input + target, write one gradient (fp32)
+    out["hbm_floor_bytes"] = 3 * B * 2 * T * 4
     return out
 
 
