@@ -178,15 +178,22 @@ class FlatAdamW:
 class AutoencoderTrainer:
     """Data-parallel training step for an ``AudioAutoencoder`` with Oobleck encoder/decoder.
 
-    ``training_step(reals)`` = encode -> split mean/scale -> vae_sample -> decode -> Gaussian NLL + kl_weight * KL ->
-    backward -> gradient all-reduce -> AdamW, the generator branch of the reference's ``training_step``.
+    ``training_step(reals)`` = encode -> split mean/scale -> vae_sample -> decode -> Gaussian NLL + kl_weight * KL
+    (+ spectral_weight * multi-resolution STFT loss when ``spectral_loss`` is given) -> backward -> gradient
+    all-reduce -> AdamW, the generator branch of the reference's ``training_step`` without its GAN terms.
     One process per GPU; pass the process group (NCCL over NVLink) or leave ``None`` for the default group /
     single-GPU operation."""
 
     def __init__(self, autoencoder: nn.Module, lr: float = 1e-4, betas=(0.8, 0.99), eps: float = 1e-8,
                  weight_decay: float = 1e-3, kl_weight: float = 1e-6, log_sigma: float = 0.0,
-                 precision: Optional[str] = "bf16", process_group=None, data_parallel: bool = True):
+                 precision: Optional[str] = "bf16", process_group=None, data_parallel: bool = True,
+                 spectral_loss: Optional[nn.Module] = None, spectral_weight: float = 1.0, nll_weight: float = 1.0):
         self.autoencoder = autoencoder
+        # the reference's generator loss is MR-STFT + adversarial + feature matching + KL (training/autoencoders.py:
+        # 150-200); ``spectral_loss`` (kalle_audio_b200.SumAndDifferenceSTFTLoss / MultiResolutionSTFTLoss, called as
+        # module(reals, decoded) like the reference's AuralossLoss) adds its spectral term, ``nll_weight=0`` drops the
+        # Gaussian NLL of BASELINE config 5
+        self.spectral_loss, self.spectral_weight, self.nll_weight = spectral_loss, spectral_weight, nll_weight
         self.encoder, self.decoder = autoencoder.encoder, autoencoder.decoder
         dev = next(self.encoder.parameters()).device
         if dev.type != "cuda":
@@ -253,8 +260,13 @@ class AutoencoderTrainer:
         latents, kl = vae_sample_with_grad(mean, scale, noise)
         decoded = self.decoder(latents)
         nll = gaussian_nll(reals, decoded, self.log_sigma)
-        loss = nll + self.kl_weight * kl
-        return loss, {"nll": nll.detach(), "kl": kl.detach(), "latents": latents.detach(), "decoded": decoded.detach()}
+        loss = self.nll_weight * nll + self.kl_weight * kl
+        info = {"nll": nll.detach(), "kl": kl.detach(), "latents": latents.detach(), "decoded": decoded.detach()}
+        if self.spectral_loss is not None:
+            st = self.spectral_loss(reals, decoded)
+            loss = loss + self.spectral_weight * st
+            info["mrstft"] = st.detach()
+        return loss, info
 
     def training_step(self, reals: torch.Tensor, noise: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         for p in self.autoencoder.parameters():

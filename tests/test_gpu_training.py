@@ -353,3 +353,22 @@ def test_training_step_config5_shape_properties(dev):
     n = float(g1.norm())
     assert float((g1 - g2).norm()) <= 1e-4 * n                      # atomics order only
     assert float((g3 - 2.0 * g1).norm()) <= 2e-4 * 2.0 * n          # linear in the incoming gradient
+
+
+def test_trainer_with_the_spectral_loss(dev):
+    """AutoencoderTrainer with the reference's spectral term (SumAndDifferenceSTFTLoss(reals, decoded), the way
+    training/autoencoders.py:163 wires it) instead of the Gaussian NLL: the loss the decoder is trained on in the
+    reference minus its GAN terms.  A fixed batch must be fitted better step by step."""
+    torch.manual_seed(0)
+    ae = H.build("mid", 0).to(dev)
+    sd = k.SumAndDifferenceSTFTLoss(fft_sizes=[512, 256, 128, 64, 32], hop_sizes=[128, 64, 32, 16, 8],
+                                    win_lengths=[512, 256, 128, 64, 32], perceptual_weighting=True, sample_rate=16000)
+    tr = k.AutoencoderTrainer(ae, lr=2e-4, precision="bf16", data_parallel=False, spectral_loss=sd, nll_weight=0.0)
+    x = 0.1 * torch.randn(2, 2, 40 * 64, device=dev)
+    noise = torch.randn(2, 64, 64, device=dev)
+    losses = []
+    for _ in range(6):
+        info = tr.training_step(x, noise)
+        assert "mrstft" in info and torch.isfinite(info["loss"])
+        losses.append(float(info["mrstft"]))
+    assert losses[-1] < losses[0], losses
