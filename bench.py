@@ -663,12 +663,17 @@ def measure_mrstft(args, dev):
     taps = mod.fir_taps.to(dev).view(1, 1, -1)
 
     def ours():
-        l = mod(x, y)
-        l.backward()
+        with torch.enable_grad():
+            l = mod(x, y)
+            l.backward()
         y.grad = None
         return l
 
     def eager():
+        with torch.enable_grad():
+            return eager_()
+
+    def eager_():
         tot = 0.0
         for sx_, sy_ in ((x[:, 0] + x[:, 1], y[:, 0] + y[:, 1]), (x[:, 0] - x[:, 1], y[:, 0] - y[:, 1])):
             fx = torch.nn.functional.conv1d(sx_.unsqueeze(1), taps, padding=50).squeeze(1)

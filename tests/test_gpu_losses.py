@@ -20,11 +20,12 @@ def dev():
 
 
 def _run(mod, x, y, dev):
-    x = H.t(x).to(dev).requires_grad_(True)
-    y = H.t(y).to(dev).requires_grad_(True)
-    loss = mod(x, y)
-    gx, gy = torch.autograd.grad(loss, (x, y))
-    return float(loss), gx.cpu().numpy(), gy.cpu().numpy()
+    with torch.enable_grad():          # other test modules of the suite switch autograd off globally
+        x = H.t(x).to(dev).requires_grad_(True)
+        y = H.t(y).to(dev).requires_grad_(True)
+        loss = mod(x, y)
+        gx, gy = torch.autograd.grad(loss, (x, y))
+    return float(loss.detach()), gx.cpu().numpy(), gy.cpu().numpy()
 
 
 @pytest.mark.parametrize("tag,cls,kw,xk,yk", [
@@ -52,8 +53,9 @@ def test_mrstft_matches_reference(dev, tag, cls, kw, xk, yk):
     # value only (no gradient buffers), and a scaled upstream gradient
     with torch.no_grad():
         assert abs(float(mod(H.t(g[xk]).to(dev), H.t(g[yk]).to(dev))) - loss) <= 1e-6 * abs(loss)
-    y = H.t(g[yk]).to(dev).requires_grad_(True)
-    (3.0 * mod(H.t(g[xk]).to(dev), y)).backward()
+    with torch.enable_grad():
+        y = H.t(g[yk]).to(dev).requires_grad_(True)
+        (3.0 * mod(H.t(g[xk]).to(dev), y)).backward()
     assert np.abs(y.grad.cpu().numpy() - 3.0 * gy).max() <= 1e-5 * np.abs(gy).max() * 3.0 + 1e-9
 
 

@@ -368,7 +368,7 @@ def test_trainer_with_the_spectral_loss(dev):
     noise = torch.randn(2, 64, 64, device=dev)
     losses = []
     for _ in range(6):
-        info = tr.training_step(x, noise)
+        info = tr.training_step(x, noise)          # (enables autograd itself)
         assert "mrstft" in info and torch.isfinite(info["loss"])
         losses.append(float(info["mrstft"]))
     assert losses[-1] < losses[0], losses
