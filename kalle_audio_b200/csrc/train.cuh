@@ -820,11 +820,15 @@ __device__ __forceinline__ void weight_norm_bwd_packed_row(float (*red)[32], con
   // walk the packed layout in its own order (c fastest) for coalesced reads of dw
   float nn = 0.f, dot = 0.f;
   if (g) {
+    // (k, c) of j = k Cc + c advance by the block size without a division per element
+    const int dk1 = blockDim.x / Cc, dc1 = blockDim.x % Cc;
+    int k = threadIdx.x / Cc, c = threadIdx.x % Cc;
     for (int j = threadIdx.x; j < inner; j += blockDim.x) {
-      const int k = j / Cc, c = j % Cc;
       const float x = v[base + static_cast<size_t>(c) * K + k];
       nn = fmaf(x, x, nn);
       dot = fmaf(dwp[(static_cast<size_t>(k) * R + i) * Cc + c], x, dot);
+      k += dk1; c += dc1;
+      if (c >= Cc) { c -= Cc; ++k; }
     }
     for (int o = 16; o > 0; o >>= 1) {
       nn += __shfl_xor_sync(0xffffffffu, nn, o);
@@ -847,10 +851,13 @@ __device__ __forceinline__ void weight_norm_bwd_packed_row(float (*red)[32], con
   }
   const float n = g ? sqrtf(nn) : 1.f;
   const float s = g ? g[i] / n : 1.f, q = g ? dot / nn : 0.f;
-  for (int j = threadIdx.x; j < inner; j += blockDim.x) {     // torch order for coalesced writes of dv
-    const int c = j / K, k = j % K;
-    const float d = dwp[(static_cast<size_t>(k) * R + i) * Cc + c];
+  const int dc2 = blockDim.x / K, dk2 = blockDim.x % K;
+  int c2 = threadIdx.x / K, k2 = threadIdx.x % K;
+  for (int j = threadIdx.x; j < inner; j += blockDim.x) {     // torch order (j = c K + k) for coalesced writes of dv
+    const float d = dwp[(static_cast<size_t>(k2) * R + i) * Cc + c2];
     dv[base + j] = g ? s * (d - v[base + j] * q) : d;
+    c2 += dc2; k2 += dk2;
+    if (k2 >= K) { k2 -= K; ++c2; }
   }
   if (g && threadIdx.x == 0) dg[i] = dot / n;
 }
