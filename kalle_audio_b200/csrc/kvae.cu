@@ -1168,6 +1168,7 @@ bool prepare_backward(kvae_plan* p, int B, long long T, void* ws, PreparedRun& R
       if (c.g.Cout <= 2) {   // decoder tail: wide = SnakeBeta(stream), thin = output gradient (channels-last)
         e.W = static_cast<const float*>(a_ptr); e.W_a = a_sn; e.W_inv_b = a_ib; e.C = c.g.Cin;
         e.W_f16 = R.stream_f16 ? 1 : 0;
+        e.fast_sin = (p->precision == KVAE_PREC_BF16) ? 1 : 0;
         e.N = g_ptr; e.N_f32 = 1; e.N_sB = g_sB; e.N_sT = g_sT; e.N_sC = 1;
         e.sigma = 1; e.out_wide_first = 0;
       } else {               // encoder head: wide = gradient of the stream, thin = the caller's waveform (API layout)

@@ -448,6 +448,7 @@ struct EdgeWgradParams {
   int B, T, C, K, dil, pad;
   int rows_per_block;        // rows of one clip per block (blocks never straddle clips)
   int blocks_per_clip;
+  int fast_sin;              // bf16-mode plans: MUFU sine in the SnakeBeta prologue, as the forward pass computed it
 };
 
 constexpr int kEdgeMaxK = 8;
@@ -582,8 +583,13 @@ __global__ void __launch_bounds__(256, 2) wgrad_edge_vec4_kernel(const EdgeWgrad
       if (u >= u_hi) break;
       float wv[4] = {w[q].x, w[q].y, w[q].z, w[q].w};
       if (p.W_a) {
-        wv[0] = snake_beta<false>(wv[0], a.x, ib.x); wv[1] = snake_beta<false>(wv[1], a.y, ib.y);
-        wv[2] = snake_beta<false>(wv[2], a.z, ib.z); wv[3] = snake_beta<false>(wv[3], a.w, ib.w);
+        if (p.fast_sin) {
+          wv[0] = snake_beta<true>(wv[0], a.x, ib.x); wv[1] = snake_beta<true>(wv[1], a.y, ib.y);
+          wv[2] = snake_beta<true>(wv[2], a.z, ib.z); wv[3] = snake_beta<true>(wv[3], a.w, ib.w);
+        } else {
+          wv[0] = snake_beta<false>(wv[0], a.x, ib.x); wv[1] = snake_beta<false>(wv[1], a.y, ib.y);
+          wv[2] = snake_beta<false>(wv[2], a.z, ib.z); wv[3] = snake_beta<false>(wv[3], a.w, ib.w);
+        }
       }
 #pragma unroll
       for (int k = 0; k < kEdgeMaxK; ++k) {
