@@ -794,6 +794,22 @@ def measure_train(args, dev, rank, world, ae=None):
             tr.sync.enabled = False            # same step without the gradient all-reduce (ranks diverge; timing only)
             ms_nosync, _ = timed(args.steps)
             tr.sync.enabled = True
+        # the same step on the reference's spectral term instead of the Gaussian NLL (SumAndDifferenceSTFTLoss(reals,
+        # decoded), training/autoencoders.py:163): its generator loss minus the GAN terms.  Timing only, after the
+        # configs[4] measurement (the parameters keep moving, the workload does not).
+        ms_spectral = None
+        if world == 1:
+            try:
+                tr.spectral_loss = k.SumAndDifferenceSTFTLoss(
+                    fft_sizes=[2048, 1024, 512, 256, 128, 64, 32], hop_sizes=[512, 256, 128, 64, 32, 16, 8],
+                    win_lengths=[2048, 1024, 512, 256, 128, 64, 32], perceptual_weighting=True, sample_rate=SAO["sample_rate"])
+                tr.nll_weight = 0.0
+                for _ in range(2):
+                    tr.training_step(x, noise)
+                ms_spectral, _ = timed(max(3, args.steps // 2))
+            except Exception as exc:
+                ms_spectral = f"{type(exc).__name__}: {exc}"
+            tr.spectral_loss, tr.nll_weight = None, 1.0
     peaks = measured_peaks()
     enc_r, dec_r = ae.encoder.runner(dev), ae.decoder.runner(dev)
     fwd = enc_r.flops(B, L) + dec_r.flops(B, frames)
@@ -811,7 +827,7 @@ def measure_train(args, dev, rank, world, ae=None):
         "tflops_per_gpu": tfl, "frac_of_sustained_bf16": tfl / peaks["bf16_tflops_sustained"],
         "frac_of_burst_bf16": tfl / peaks["bf16_tflops"],
         "allreduce_exposed_ms": ms - ms_nosync, "params": int(tr.flat_enc.numel() + tr.flat_dec.numel()),
-        "loss_first_to_last": [losses[0], losses[-1]]}
+        "loss_first_to_last": [losses[0], losses[-1]], "ms_per_step_mrstft_plus_kl": ms_spectral}
 
 
 def run_train(args):
