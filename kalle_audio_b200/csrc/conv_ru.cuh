@@ -15,7 +15,7 @@
 // the other: their EPI1 share of a tile (2 of the 8 16-row blocks of each half), then their EPI2 share (4 of the
 // 16 16-row items).  With separate EPI1 / EPI2 warp groups the EPI1 warps idled 70 % of the time waiting for GEMM1
 // while the 8 EPI2 warps, one latency-bound item at a time, took ~14 K cycles per tile and held D2 back
-// (profiles/r01_conv_ru_bench_shape_B16.ncu-rep, warp-stall samples); now EPI2 of tile i runs on 16 warps
+// (profiles/r01_conv_ru_unified_epilogue_B16.ncu-rep, warp-stall samples); now EPI2 of tile i runs on 16 warps
 // underneath GEMM1 of tile i+1.  Every warp prefetches its next skip-connection block by TMA and stores in place.
 // The residual stream is fp16 in HBM (inference plans only use this kernel).
 // Shared memory (227 KB): activation slab ring 2 x <=40 KB, weight ring 3-4 x 16 KB (W7 taps, then the two W1

@@ -1,6 +1,6 @@
 // conv_ru2: the fused ResidualUnit of conv_ru.cuh (reference autoencoders.py:39-62) with the tensor pipe kept busy
 // across tiles.  conv_ru_kernel runs GEMM1 -> EPI1 -> GEMM2 of a tile as a serial chain on one accumulator; the
-// ablation in profiles/r02_ru_ablation.txt shows that chain alone (no HBM traffic at all) costs 0.35 of the 0.47 ms
+// ablation in profiles/r01_ru_ablation.txt shows that chain alone (no HBM traffic at all) costs 0.35 of the 0.47 ms
 // per launch, against 0.19 ms of tensor work.  Here:
 //   * TMEM holds TWO 256-column accumulators; tile i uses buffer i & 1.  GEMM2 of a half writes D2 IN PLACE over the
 //     128 columns of D1 that EPI1 has just consumed, so two tiles are in flight in 512 columns.
@@ -109,7 +109,7 @@ conv_ru2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp == 3) {
     // ------------------------------------------------------------ TMA producer for the activation slabs, on its own
     // thread: in one FIFO with the weights a slab was requested only SB weight stages (~1 us) before its first MMA,
-    // less than an HBM round trip, although its ring stage had been free for half a tile (profiles/r02_ru_ablation.txt:
+    // less than an HBM round trip, although its ring stage had been free for half a tile (profiles/r01_ru_ablation.txt:
     // removing these 67 KB per tile saved 23 % of the launch).  Here a slab is requested the moment its stage is free.
     {   // warp-uniform loop, one elected lane issues
       int as = 0;

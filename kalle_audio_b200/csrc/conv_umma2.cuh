@@ -258,7 +258,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // divergent thread: 79 instructions per weight stage with an indexed constant load, six R2UR transfers and the
     // parameter block re-read each iteration -- ~540 cycles per stage of four MMAs, which 256-row tiles hide (512 tensor
     // cycles) but 128-row tiles do not: the batch-1 streaming layers ran their tensor pipe at 16 %
-    // (profiles/r02_o12_b1_k7_c1024.txt).  Warp-uniform, the loop state sits in uniform registers next to the descriptors.
+    // (profiles/r02_o12_b1_k7_c1024.ncu-rep).  Warp-uniform, the loop state sits in uniform registers next to the descriptors.
     {
       const uint32_t idesc = ptx::idesc_bf16_f32(128, p.NT);
       const uint32_t idesc_swap = ptx::idesc_bf16_f32(128, 128 * p.MT);
@@ -333,7 +333,7 @@ conv_umma2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // 16-row x 32-channel items -- the EPI2 mapping of conv_ru2.cuh.  The generic epilogue below spends ~860 warp
     // instructions per 32 x 32 item, most of them control (integer divisions for the prefetch coordinates, generic ->
     // shared address conversions, ring geometry recomputed per item, run-time mode branches) executed as one dependent
-    // chain with two warps per scheduler (profiles/r02_k1_c256_B16.txt: the k = 1 / transposed / strided convs ran at the
+    // chain with two warps per scheduler (profiles/r02_k1_c256_before_after.txt: the k = 1 / transposed / strided convs ran at the
     // epilogue's item rate, 60 % of their HBM floor).  Here the tile decode happens once per tile, every address is a
     // loop-invariant 32-bit shared-memory offset, and four warps per scheduler hide each other's latencies.
     const int e = warp - 4, quad = warp & 3, sub = e >> 2;
