@@ -241,7 +241,7 @@ int kvae_adamw_step(float* params, const float* grads, float* exp_avg, float* ex
 
 /* Backward of kvae_conv1d_fwd (autograd of F.conv1d / F.conv_transpose1d on the stand-alone WNConv1d /
  * WNConvTranspose1d modules): dw = gradient of the folded weight (torch layout, overwritten), dbias [Cout] and gx
- * (same shape as x) optional.  fp32 arithmetic; x, gy, gx of `dtype`.  scratch as for kvae_conv1d_fwd. */
+ * (same shape as x); each of the three is optional (NULL = not computed).  fp32 arithmetic; x, gy, gx of `dtype`.  scratch as for kvae_conv1d_fwd. */
 int kvae_conv1d_bwd(const void* x, const void* gy, const float* w_folded, void* gx, float* dw, float* dbias,
                     int transposed, int B, int Cin, int Cout, long long T, int K, int stride, int dilation, int padding,
                     int dtype, void* scratch, size_t scratch_bytes, void* stream);
@@ -310,6 +310,42 @@ int kvae_lm_glue_step(const void* hidden, int hidden_dtype, const float* w1, con
  * fp32 scalar) = (mean^2 + var - log var - 1).sum(1).mean().  scratch: >= 8*1024 bytes. */
 int kvae_vae_sample(const void* mean, const void* scale, const void* noise, void* out, float* kl, int B, int D,
                     long long T, int dtype, void* scratch, void* stream);
+
+/* ---- Oobleck discriminator of the autoencoder's GAN training (discriminator half) ----
+ * stable_audio_tools/models/discriminators.py: SharedDiscriminatorConvNet (62-116), MultiScaleDiscriminator (119-138),
+ * MultiPeriodDiscriminator (140-168), MultiDiscriminator (171-238), OobleckDiscriminator.loss (240-297),
+ * get_hinge_losses (11-14); wired at training/autoencoders.py:133-134, 288.  Every net is a stack of strided
+ * convolutions + SiLU; they run on kvae_conv1d_fwd / kvae_conv1d_bwd (dw may be NULL there when only the data gradient
+ * is wanted).  The multi-period nets' 15 x 15 Conv2d over [N, C, ceil(T / n), n] becomes a Conv1d over the folded
+ * channels (c, w): same products, minus those with padding zeros.  All tensors fp32, contiguous; `backward` = 1 runs the
+ * adjoint with the roles of the two tensor arguments exchanged (first = incoming gradient, second = outgoing). */
+/* MultiPeriodDiscriminator.fold (:164-168): y[b, c n + w, h] = x[b, c, h n + w] (0 past T); x [N, C, T], y [N, C n, ceil(T / n)] */
+int kvae_disc_period_fold(const float* x, float* y, int N, int C, long long T, int n, int backward, void* stream);
+/* nn.functional.avg_pool1d(x, 2) between the scales (:137): x [rows, T] -> y [rows, T / 2] */
+int kvae_disc_avg_pool2(const float* x, float* y, long long rows, long long T, int backward, void* stream);
+/* width of the folded axis after a conv: (W + 2 pad - K) / stride + 1 (0 if the arguments are invalid) */
+int kvae_disc_folded_width(int W, int K, int stride, int pad);
+/* Conv2d weight w [Cout, Cin, K, K] (weight-norm already folded) + bias [Cout] -> Conv1d weight over the folded channels
+ * wf [Cout Wo, Cin W, K], wf[(co, wo), (ci, wi), kh] = w[co, ci, kh, wi - stride wo + pad], bias_f[(co, wo)] = bias[co].
+ * backward = 1: wf / bias_f hold gradients, w / bias receive them (overwritten).  bias / bias_f may be NULL together. */
+int kvae_disc_fold_weight2d(const float* w, const float* bias, float* wf, float* bias_f, int Cout, int Cin, int K, int stride,
+                            int pad, int W, int backward, void* stream);
+/* nn.SiLU (:76): a = f sigmoid(f);  backward: gf = ga * silu'(f) + gfeat (gfeat, the gradient arriving at the feature
+ * tensor itself, may be NULL; gf may alias ga) */
+int kvae_disc_silu_fwd(const float* f, float* a, size_t n, void* stream);
+int kvae_disc_silu_bwd(const float* f, const float* ga, const float* gfeat, float* gf, size_t n, void* stream);
+/* score[b] (+)= mean(y[b, :]) (:115);  backward: gy[b, i] = gscore[b] / inner + gfeat[b, i] (either may be NULL) */
+int kvae_disc_score(const float* y, float* score, int N, long long inner, int accumulate, void* stream);
+int kvae_disc_score_bwd(const float* gscore, const float* gfeat, float* gy, int N, long long inner, void* stream);
+/* get_hinge_losses (:11-14) on score [2B] = (reals | fakes): losses[0] = relu(1 - s_real).mean() + relu(1 + s_fake).mean(),
+ * losses[1] = -s_fake.mean().  With g_losses [2] (device) it writes d / d score into g_score [2B] instead. */
+int kvae_disc_hinge(const float* score, int B, float* losses, const float* g_losses, float* g_score, void* stream);
+/* feature-matching distance (:285-295) over n_feats tensors in one launch: loss[0] = sum_k mean |real_k - fake_k|, the
+ * real half of tensor k being its first half[k] floats and the fake half the next half[k] (feats / half / grads: HOST
+ * arrays).  With g_loss (one device float) it writes the gradients into grads[k] (2 half[k] floats each) instead. */
+size_t kvae_disc_feature_match_scratch_bytes(const long long* half, int n_feats);
+int kvae_disc_feature_match(const float* const* feats, const long long* half, int n_feats, float* loss,
+                            const float* g_loss, float* const* grads, void* scratch, size_t scratch_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -134,6 +134,19 @@ SIGNATURES = {
                                     C.c_void_p, C.c_float, C.c_size_t, C.c_void_p]),
     "kvae_vae_sample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                   C.c_longlong, C.c_int, C.c_void_p, C.c_void_p]),
+    "kvae_disc_period_fold": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_int, C.c_int, C.c_void_p]),
+    "kvae_disc_avg_pool2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p]),
+    "kvae_disc_folded_width": (C.c_int, [C.c_int] * 4),
+    "kvae_disc_fold_weight2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "kvae_disc_silu_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kvae_disc_silu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kvae_disc_score": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_int, C.c_void_p]),
+    "kvae_disc_score_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_longlong, C.c_void_p]),
+    "kvae_disc_hinge": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "kvae_disc_feature_match_scratch_bytes": (C.c_size_t, [C.POINTER(C.c_longlong), C.c_int]),
+    "kvae_disc_feature_match": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.c_int, C.c_void_p, C.c_void_p,
+                                          C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 
 

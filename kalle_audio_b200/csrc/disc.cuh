@@ -1,0 +1,282 @@
+// Oobleck discriminator (stable_audio_tools/models/discriminators.py:62-297) -- the kernels around its convolutions.
+//
+// Every sub-discriminator is a stack of strided Conv1d(k = 15, s = 4, p = 7) + SiLU.  That is literally so for the
+// multi-scale nets; the multi-period nets are Conv2d(15 x 15, stride 4, padding 7) over the waveform folded to
+// [N, C, H = ceil(T / n), W = n] with n <= 11 < 15, so most of the 225 taps only ever meet zero padding.  Here the
+// W axis moves into the channels: x' [N, C * W, H], w' [(co, wo), (ci, wi), kh] = w[co, ci, kh, wi - 4 wo + 7] (0 where
+// that column index falls outside the kernel) -- the SAME arithmetic as the Conv2d minus the products with padding
+// zeros (15 x fewer multiply-adds once W has shrunk to 1, which is the case from the second or third layer on).  The
+// convolutions themselves run on the layer-level conv kernels (conv_direct_kernel / wgrad_direct_kernel, fp32); this
+// file holds the fold / unfold of inputs and weights, SiLU, avg_pool1d(2), the score mean, the hinge losses and the
+// feature-matching distance over all feature tensors in one launch, each with its backward.
+#pragma once
+#include <cstdint>
+
+namespace kvae {
+
+constexpr int kDiscThreads = 256;
+
+__device__ __forceinline__ float block_sum_256(float v, float* red /*[8]*/) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kDiscThreads / 32; ++i) s += red[i];
+  return s;
+}
+
+// ---- MultiPeriodDiscriminator.fold (:164-168) with the period axis moved into the channels
+// forward:  y[b, c * n + w, h] = x[b, c, h * n + w]  (0 for h * n + w >= T);  y: [N, C * n, H]
+__global__ void __launch_bounds__(kDiscThreads)
+disc_period_fold_kernel(const float* __restrict__ x, float* __restrict__ y, int C, long long T, int n, long long H,
+                        size_t total) {
+  for (size_t idx = blockIdx.x * static_cast<size_t>(kDiscThreads) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * kDiscThreads) {
+    const long long h = static_cast<long long>(idx % H);
+    const size_t cw = idx / H;                 // b * C * n + c * n + w
+    const int w = static_cast<int>(cw % n);
+    const size_t bc = cw / n;                  // b * C + c
+    const long long t = h * n + w;
+    y[idx] = t < T ? x[bc * T + t] : 0.f;
+  }
+}
+// backward: gx[b, c, t] = gy[b, c * n + t % n, t / n];  gx: [N, C, T]
+__global__ void __launch_bounds__(kDiscThreads)
+disc_period_unfold_kernel(const float* __restrict__ gy, float* __restrict__ gx, long long T, int n, long long H,
+                          size_t total) {
+  for (size_t idx = blockIdx.x * static_cast<size_t>(kDiscThreads) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * kDiscThreads) {
+    const long long t = static_cast<long long>(idx % T);
+    const size_t bc = idx / T;
+    gx[idx] = gy[(bc * n + static_cast<size_t>(t % n)) * H + t / n];
+  }
+}
+
+// ---- nn.functional.avg_pool1d(x, 2) between the scales (:137): y[r, t] = (x[r, 2t] + x[r, 2t + 1]) / 2, To = T / 2
+__global__ void __launch_bounds__(kDiscThreads)
+disc_avg_pool2_kernel(const float* __restrict__ x, float* __restrict__ y, long long T, long long To, size_t total) {
+  for (size_t idx = blockIdx.x * static_cast<size_t>(kDiscThreads) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * kDiscThreads) {
+    const long long t = static_cast<long long>(idx % To);
+    const size_t r = idx / To;
+    const float2 v = *reinterpret_cast<const float2*>(x + r * T + 2 * t);   // r * T + 2t is even when T is even ...
+    y[idx] = (v.x + v.y) * 0.5f;
+  }
+}
+__global__ void __launch_bounds__(kDiscThreads)
+disc_avg_pool2_odd_kernel(const float* __restrict__ x, float* __restrict__ y, long long T, long long To, size_t total) {
+  for (size_t idx = blockIdx.x * static_cast<size_t>(kDiscThreads) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * kDiscThreads) {
+    const long long t = static_cast<long long>(idx % To);
+    const size_t r = idx / To;
+    y[idx] = (x[r * T + 2 * t] + x[r * T + 2 * t + 1]) * 0.5f;             // ... odd T: rows are not 8-byte aligned
+  }
+}
+// backward: gx[r, t] = gy[r, t / 2] / 2 for t < 2 To, 0 for the dropped last sample of an odd-length row
+__global__ void __launch_bounds__(kDiscThreads)
+disc_avg_pool2_bwd_kernel(const float* __restrict__ gy, float* __restrict__ gx, long long T, long long To, size_t total) {
+  for (size_t idx = blockIdx.x * static_cast<size_t>(kDiscThreads) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * kDiscThreads) {
+    const long long t = static_cast<long long>(idx % T);
+    const size_t r = idx / T;
+    gx[idx] = t < 2 * To ? 0.5f * gy[r * To + t / 2] : 0.f;
+  }
+}
+
+// ---- Conv2d weight [Cout, Cin, K, K] (torch layout, already weight-norm folded) -> Conv1d weight over the folded
+// channels: wf[(co, wo), (ci, wi), kh] = w[co, ci, kh, wi - stride * wo + pad]; bias_f[(co, wo)] = bias[co]
+__global__ void __launch_bounds__(kDiscThreads)
+disc_fold_weight2d_kernel(const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ wf,
+                          float* __restrict__ bias_f, int Cout, int Cin, int K, int stride, int pad, int W, int Wo) {
+  const size_t total = static_cast<size_t>(Cout) * Wo * Cin * W * K;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(kDiscThreads) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * kDiscThreads) {
+    const int kh = static_cast<int>(idx % K);
+    size_t r = idx / K;
+    const int wi = static_cast<int>(r % W); r /= W;
+    const int ci = static_cast<int>(r % Cin); r /= Cin;
+    const int wo = static_cast<int>(r % Wo);
+    const int co = static_cast<int>(r / Wo);
+    const int kw = wi - stride * wo + pad;
+    wf[idx] = (kw >= 0 && kw < K) ? w[((static_cast<size_t>(co) * Cin + ci) * K + kh) * K + kw] : 0.f;
+  }
+  if (bias && bias_f)
+    for (int i = blockIdx.x * kDiscThreads + threadIdx.x; i < Cout * Wo; i += gridDim.x * kDiscThreads)
+      bias_f[i] = bias[i / Wo];
+}
+// adjoint: dw[co, ci, kh, kw] = sum_wo dwf[(co, wo), (ci, kw + stride * wo - pad), kh]; dbias[co] = sum_wo dbias_f[(co, wo)]
+__global__ void __launch_bounds__(kDiscThreads)
+disc_unfold_weight2d_kernel(const float* __restrict__ dwf, const float* __restrict__ dbias_f, float* __restrict__ dw,
+                            float* __restrict__ dbias, int Cout, int Cin, int K, int stride, int pad, int W, int Wo) {
+  const size_t total = static_cast<size_t>(Cout) * Cin * K * K;
+  for (size_t idx = blockIdx.x * static_cast<size_t>(kDiscThreads) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * kDiscThreads) {
+    const int kw = static_cast<int>(idx % K);
+    size_t r = idx / K;
+    const int kh = static_cast<int>(r % K); r /= K;
+    const int ci = static_cast<int>(r % Cin);
+    const int co = static_cast<int>(r / Cin);
+    float s = 0.f;
+    for (int wo = 0; wo < Wo; ++wo) {
+      const int wi = kw + stride * wo - pad;
+      if (wi >= 0 && wi < W) s += dwf[(((static_cast<size_t>(co) * Wo + wo) * Cin + ci) * W + wi) * K + kh];
+    }
+    dw[idx] = s;
+  }
+  if (dbias && dbias_f)
+    for (int co = blockIdx.x * kDiscThreads + threadIdx.x; co < Cout; co += gridDim.x * kDiscThreads) {
+      float s = 0.f;
+      for (int wo = 0; wo < Wo; ++wo) s += dbias_f[co * Wo + wo];
+      dbias[co] = s;
+    }
+}
+
+// ---- nn.SiLU between the convs (:76): a = f * sigmoid(f)
+__device__ __forceinline__ float silu_f(float f) { return f / (1.f + expf(-f)); }
+__global__ void __launch_bounds__(kDiscThreads)
+disc_silu_kernel(const float* __restrict__ f, float* __restrict__ a, size_t n) {
+  const size_t n4 = n / 4;
+  const size_t stride = static_cast<size_t>(gridDim.x) * kDiscThreads;
+  const size_t i0 = blockIdx.x * static_cast<size_t>(kDiscThreads) + threadIdx.x;
+  for (size_t i = i0; i < n4; i += stride) {
+    float4 v = reinterpret_cast<const float4*>(f)[i];
+    v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
+    reinterpret_cast<float4*>(a)[i] = v;
+  }
+  for (size_t i = n4 * 4 + i0; i < n; i += stride) a[i] = silu_f(f[i]);
+}
+// gf = ga * d silu(f) / df + gfeat, d silu / df = s (1 + f (1 - s)), s = sigmoid(f).  gfeat (the gradient arriving at the
+// feature tensor itself, from the feature-matching distance) may be null; gf may alias ga.
+__device__ __forceinline__ float silu_grad_f(float f) {
+  const float s = 1.f / (1.f + expf(-f));
+  return s * (1.f + f * (1.f - s));
+}
+__global__ void __launch_bounds__(kDiscThreads)
+disc_silu_bwd_kernel(const float* __restrict__ f, const float* ga, const float* __restrict__ gfeat, float* gf, size_t n) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(kDiscThreads) + threadIdx.x; i < n;
+       i += static_cast<size_t>(gridDim.x) * kDiscThreads) {
+    float g = ga[i] * silu_grad_f(f[i]);
+    if (gfeat) g += gfeat[i];
+    gf[i] = g;
+  }
+}
+
+// ---- score = x.reshape(N, -1).mean(-1) of the last conv's output (:115); one block per batch item
+__global__ void __launch_bounds__(kDiscThreads)
+disc_score_kernel(const float* __restrict__ y, float* __restrict__ score, long long inner, int accumulate) {
+  __shared__ float red[8];
+  const float* row = y + static_cast<size_t>(blockIdx.x) * inner;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < inner; i += kDiscThreads) s += row[i];
+  s = block_sum_256(s, red);
+  if (threadIdx.x == 0) {
+    const float m = s / static_cast<float>(inner);
+    score[blockIdx.x] = accumulate ? score[blockIdx.x] + m : m;
+  }
+}
+// gy[b, i] = gscore[b] / inner + gfeat[b, i]   (either source may be null)
+__global__ void __launch_bounds__(kDiscThreads)
+disc_score_bwd_kernel(const float* __restrict__ gscore, const float* __restrict__ gfeat, float* __restrict__ gy,
+                      long long inner, size_t total) {
+  for (size_t i = blockIdx.x * static_cast<size_t>(kDiscThreads) + threadIdx.x; i < total;
+       i += static_cast<size_t>(gridDim.x) * kDiscThreads) {
+    float g = gscore ? gscore[i / inner] / static_cast<float>(inner) : 0.f;
+    if (gfeat) g += gfeat[i];
+    gy[i] = g;
+  }
+}
+
+// ---- get_hinge_losses (:11-14) on score [2B] = (reals | fakes): losses[0] = dis, losses[1] = gen.
+// With g_losses (d L / d dis, d L / d gen) it writes g_score [2B] instead.  One block.
+__global__ void __launch_bounds__(kDiscThreads)
+disc_hinge_kernel(const float* __restrict__ score, int B, float* __restrict__ losses, const float* __restrict__ g_losses,
+                  float* __restrict__ g_score) {
+  __shared__ float red[8];
+  if (g_losses) {
+    const float gd = g_losses[0] / static_cast<float>(B), gg = g_losses[1] / static_cast<float>(B);
+    for (int i = threadIdx.x; i < 2 * B; i += kDiscThreads) {
+      const float s = score[i];
+      g_score[i] = i < B ? ((1.f - s) > 0.f ? -gd : 0.f) : (((1.f + s) > 0.f ? gd : 0.f) - gg);
+    }
+    return;
+  }
+  float r = 0.f, f = 0.f, m = 0.f;
+  for (int i = threadIdx.x; i < B; i += kDiscThreads) {
+    r += fmaxf(1.f - score[i], 0.f);
+    f += fmaxf(1.f + score[B + i], 0.f);
+    m += score[B + i];
+  }
+  r = block_sum_256(r, red);
+  f = block_sum_256(f, red);
+  m = block_sum_256(m, red);
+  if (threadIdx.x == 0) {
+    losses[0] = r / static_cast<float>(B) + f / static_cast<float>(B);
+    losses[1] = -(m / static_cast<float>(B));
+  }
+}
+
+// ---- feature-matching distance (:285-295): sum over the feature tensors of mean |real - fake|, the real half being the
+// first `half` floats of a tensor and the fake half the next `half` (batch-concatenated input).  All tensors in ONE
+// launch: the table rides in the kernel parameters; block -> tensor by its first block index.
+constexpr int kFmMax = 56;
+constexpr int kFmChunk = kDiscThreads * 16;
+struct FmTable {
+  const float* feat[kFmMax];
+  float* grad[kFmMax];          // backward only: [2 * half] each
+  long long half[kFmMax];
+  int blk_begin[kFmMax + 1];
+  int n;
+};
+
+__device__ __forceinline__ int fm_find(const FmTable& t, int blk) {
+  int k = 0;
+  while (k + 1 < t.n && t.blk_begin[k + 1] <= blk) ++k;
+  return k;
+}
+
+// partial[block] = sum |r - f| / half over this block's chunk
+__global__ void __launch_bounds__(kDiscThreads)
+disc_fm_partial_kernel(const __grid_constant__ FmTable t, float* __restrict__ partial) {
+  __shared__ float red[8];
+  const int k = fm_find(t, blockIdx.x);
+  const long long half = t.half[k];
+  const long long i0 = static_cast<long long>(blockIdx.x - t.blk_begin[k]) * kFmChunk;
+  const long long i1 = min(i0 + kFmChunk, half);
+  const float* r = t.feat[k];
+  const float* f = r + half;
+  float s = 0.f;
+  for (long long i = i0 + threadIdx.x; i < i1; i += kDiscThreads) s += fabsf(r[i] - f[i]);
+  s = block_sum_256(s, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s / static_cast<float>(half);
+}
+// loss (+)= sum of the partials in a fixed order (one block)
+__global__ void __launch_bounds__(kDiscThreads)
+disc_fm_finish_kernel(const float* __restrict__ partial, int n, float* __restrict__ loss, int accumulate) {
+  __shared__ float red[8];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += kDiscThreads) s += partial[i];
+  s = block_sum_256(s, red);
+  if (threadIdx.x == 0) loss[0] = accumulate ? loss[0] + s : s;
+}
+// grad[k][i] = g * sign(r - f) / half, grad[k][half + i] = -that   (g = d L / d distance, one device float)
+__global__ void __launch_bounds__(kDiscThreads)
+disc_fm_bwd_kernel(const __grid_constant__ FmTable t, const float* __restrict__ g_loss) {
+  const int k = fm_find(t, blockIdx.x);
+  const long long half = t.half[k];
+  const long long i0 = static_cast<long long>(blockIdx.x - t.blk_begin[k]) * kFmChunk;
+  const long long i1 = min(i0 + kFmChunk, half);
+  const float* r = t.feat[k];
+  const float* f = r + half;
+  float* gr = t.grad[k];
+  const float g = g_loss[0] / static_cast<float>(half);
+  for (long long i = i0 + threadIdx.x; i < i1; i += kDiscThreads) {
+    const float d = r[i] - f[i];
+    const float v = d > 0.f ? g : (d < 0.f ? -g : 0.f);
+    gr[i] = v;
+    gr[half + i] = -v;
+  }
+}
+
+}  // namespace kvae

@@ -28,6 +28,7 @@
 #include "glue.cuh"
 #include "bigvgan.cuh"
 #include "mrstft.cuh"
+#include "disc.cuh"
 #include "train.cuh"
 
 using namespace kvae;
@@ -1839,7 +1840,8 @@ int kvae_conv1d_fwd(const void* x, void* y, const float* w, const float* bias, i
 int kvae_conv1d_bwd(const void* x, const void* gy, const float* w, void* gx, float* dw, float* dbias, int transposed,
                     int B, int Cin, int Cout, long long T, int K, int stride, int dilation, int padding, int dtype,
                     void* scratch, size_t scratch_bytes, void* stream) {
-  if (!x || !gy || !w || !dw || !scratch) return fail("null argument");
+  if (!x || !gy || !w || !scratch) return fail("null argument");
+  if (!dw && !gx && !dbias) return fail("nothing to compute (dw, dbias and gx are all null)");
   if (!check_dtype(dtype)) return fail("bad dtype");
   if (B <= 0 || Cin <= 0 || Cout <= 0 || K <= 0 || T <= 0) return fail("empty input");
   if (stride < 1 || stride > kMaxPhases) return fail("stride out of range (1..8)");
@@ -1853,10 +1855,11 @@ int kvae_conv1d_bwd(const void* x, const void* gy, const float* w, void* gx, flo
   const int f32 = (dtype == KVAE_F32);
   // ---- weight gradient (torch layout), straight from the API layout through element strides
   const size_t n = static_cast<size_t>(Cin) * Cout * K;
+  const long long xsB = static_cast<long long>(Cin) * T, gsB = static_cast<long long>(Cout) * T_out;
+  if (dw) {
   KV_CUDA(cudaMemsetAsync(dw, 0, n * 4, st));
   WgradParams wp;
   std::memset(&wp, 0, sizeof(wp));
-  const long long xsB = static_cast<long long>(Cin) * T, gsB = static_cast<long long>(Cout) * T_out;
   if (!transposed) {
     wp.D = gy; wp.D_sB = gsB; wp.D_sT = 1; wp.D_sC = T_out; wp.Td = static_cast<int>(T_out); wp.Cd = Cout;
     wp.S = x; wp.S_sB = xsB; wp.S_sT = 1; wp.S_sC = T; wp.Ts = static_cast<int>(T); wp.Cs = Cin;
@@ -1877,12 +1880,14 @@ int kvae_conv1d_bwd(const void* x, const void* gy, const float* w, void* gx, flo
     wp.rows_per_split = rps;
     wgrad_direct_kernel<<<dim3(tiles, K, static_cast<unsigned>(nsplit)), 256, 0, st>>>(wp);
     KV_CUDA(cudaGetLastError());
+    ++g_launches;
   }
+  }  // dw
   if (dbias) {
     bias_grad_cf_kernel<<<Cout, 256, 0, st>>>(gy, f32, dbias, B, Cout, T_out);
     KV_CUDA(cudaGetLastError());
+    ++g_launches;
   }
-  g_launches += 2;
   if (!gx) return 0;
   // ---- data gradient: the forward kernel under the opposite kind, same weight tensor
   const ConvGeom gd = dgrad_geom(g, static_cast<int>(T));
@@ -2550,6 +2555,194 @@ int kvae_vae_sample(const void* mean, const void* scale, const void* noise, void
                                       static_cast<double>(B) * static_cast<double>(T), kl);
   KV_CUDA(cudaGetLastError());
   g_launches += 2;
+  return 0;
+}
+
+// ------------------------------------------------------------------ Oobleck discriminator (disc.cuh)
+namespace {
+inline int disc_grid(size_t total) {
+  return static_cast<int>(std::max<size_t>(1, std::min<size_t>((total + kDiscThreads - 1) / kDiscThreads,
+                                                               static_cast<size_t>(sm_count()) * 16)));
+}
+}  // namespace
+
+int kvae_disc_period_fold(const float* x, float* y, int N, int C, long long T, int n, int backward, void* stream) {
+  if (!x || !y) return fail("null argument");
+  if (N <= 0 || C <= 0 || T <= 0) return fail("empty input");
+  if (n < 1) return fail("disc: the period must be >= 1");
+  DeviceGuard guard(device_of(x));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long H = (T + n - 1) / n;
+  if (!backward) {
+    const size_t total = static_cast<size_t>(N) * C * n * H;
+    disc_period_fold_kernel<<<disc_grid(total), kDiscThreads, 0, st>>>(x, y, C, T, n, H, total);
+  } else {   // x: gradient of the folded tensor [N, C n, H] -> y: gradient of the waveform [N, C, T]
+    const size_t total = static_cast<size_t>(N) * C * T;
+    disc_period_unfold_kernel<<<disc_grid(total), kDiscThreads, 0, st>>>(x, y, T, n, H, total);
+  }
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int kvae_disc_avg_pool2(const float* x, float* y, long long rows, long long T, int backward, void* stream) {
+  if (!x || !y) return fail("null argument");
+  if (rows <= 0 || T < 2) return fail("disc: avg_pool1d(2) needs at least two samples");
+  DeviceGuard guard(device_of(x));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long To = T / 2;
+  if (!backward) {
+    const size_t total = static_cast<size_t>(rows) * To;
+    if (T % 2 == 0 && (reinterpret_cast<uintptr_t>(x) & 7) == 0)
+      disc_avg_pool2_kernel<<<disc_grid(total), kDiscThreads, 0, st>>>(x, y, T, To, total);
+    else
+      disc_avg_pool2_odd_kernel<<<disc_grid(total), kDiscThreads, 0, st>>>(x, y, T, To, total);
+  } else {   // x: gradient of the pooled tensor [rows, T / 2] -> y: gradient of the input [rows, T]
+    const size_t total = static_cast<size_t>(rows) * T;
+    disc_avg_pool2_bwd_kernel<<<disc_grid(total), kDiscThreads, 0, st>>>(x, y, T, To, total);
+  }
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int kvae_disc_folded_width(int W, int K, int stride, int pad) {
+  if (W <= 0 || K <= 0 || stride <= 0 || pad < 0 || W + 2 * pad < K) return 0;
+  return (W + 2 * pad - K) / stride + 1;
+}
+
+int kvae_disc_fold_weight2d(const float* w, const float* bias, float* wf, float* bias_f, int Cout, int Cin, int K, int stride,
+                            int pad, int W, int backward, void* stream) {
+  if (!w || !wf) return fail("null argument");
+  if (Cout <= 0 || Cin <= 0 || K <= 0) return fail("empty weight");
+  const int Wo = kvae_disc_folded_width(W, K, stride, pad);
+  if (Wo <= 0) return fail("disc: folded width smaller than the kernel");
+  DeviceGuard guard(device_of(w));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!backward) {
+    const size_t total = static_cast<size_t>(Cout) * Wo * Cin * W * K;
+    disc_fold_weight2d_kernel<<<disc_grid(total), kDiscThreads, 0, st>>>(w, bias, wf, bias_f, Cout, Cin, K, stride, pad, W, Wo);
+  } else {   // wf / bias_f: gradients of the folded tensors (in) -> w / bias: gradients in torch layout (out; const cast)
+    const size_t total = static_cast<size_t>(Cout) * Cin * K * K;
+    disc_unfold_weight2d_kernel<<<disc_grid(total), kDiscThreads, 0, st>>>(wf, bias_f, const_cast<float*>(w),
+                                                                         const_cast<float*>(bias), Cout, Cin, K, stride,
+                                                                         pad, W, Wo);
+  }
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int kvae_disc_silu_fwd(const float* f, float* a, size_t n, void* stream) {
+  if (!f || !a) return fail("null argument");
+  if (n == 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(f) | reinterpret_cast<uintptr_t>(a)) & 15) return fail("disc: 16-byte aligned buffers");
+  DeviceGuard guard(device_of(f));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  disc_silu_kernel<<<disc_grid((n + 3) / 4), kDiscThreads, 0, static_cast<cudaStream_t>(stream)>>>(f, a, n);
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int kvae_disc_silu_bwd(const float* f, const float* ga, const float* gfeat, float* gf, size_t n, void* stream) {
+  if (!f || !ga || !gf) return fail("null argument");
+  if (n == 0) return 0;
+  DeviceGuard guard(device_of(f));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  disc_silu_bwd_kernel<<<disc_grid(n), kDiscThreads, 0, static_cast<cudaStream_t>(stream)>>>(f, ga, gfeat, gf, n);
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int kvae_disc_score(const float* y, float* score, int N, long long inner, int accumulate, void* stream) {
+  if (!y || !score) return fail("null argument");
+  if (N <= 0 || inner <= 0) return fail("empty input");
+  DeviceGuard guard(device_of(y));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  disc_score_kernel<<<N, kDiscThreads, 0, static_cast<cudaStream_t>(stream)>>>(y, score, inner, accumulate);
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int kvae_disc_score_bwd(const float* gscore, const float* gfeat, float* gy, int N, long long inner, void* stream) {
+  if (!gy) return fail("null argument");
+  if (N <= 0 || inner <= 0) return fail("empty input");
+  DeviceGuard guard(device_of(gy));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  const size_t total = static_cast<size_t>(N) * inner;
+  disc_score_bwd_kernel<<<disc_grid(total), kDiscThreads, 0, static_cast<cudaStream_t>(stream)>>>(gscore, gfeat, gy, inner, total);
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int kvae_disc_hinge(const float* score, int B, float* losses, const float* g_losses, float* g_score, void* stream) {
+  if (!score) return fail("null argument");
+  if (B <= 0) return fail("empty input");
+  if (g_losses ? !g_score : !losses) return fail("null argument");
+  DeviceGuard guard(device_of(score));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  disc_hinge_kernel<<<1, kDiscThreads, 0, static_cast<cudaStream_t>(stream)>>>(score, B, losses, g_losses, g_score);
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+size_t kvae_disc_feature_match_scratch_bytes(const long long* half, int n_feats) {
+  size_t blocks = 0;
+  for (int i = 0; half && i < n_feats; ++i)
+    if (half[i] > 0) blocks += static_cast<size_t>((half[i] + kFmChunk - 1) / kFmChunk);
+  return align_up(std::max<size_t>(blocks, 1) * 4, 1024);
+}
+
+int kvae_disc_feature_match(const float* const* feats, const long long* half, int n_feats, float* loss,
+                            const float* g_loss, float* const* grads, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!feats || !half || !loss) return fail("null argument");
+  if (n_feats <= 0) return fail("disc: no feature tensors");
+  const bool backward = g_loss != nullptr;
+  if (backward && !grads) return fail("null argument");
+  if (!backward && (!scratch || scratch_bytes < kvae_disc_feature_match_scratch_bytes(half, n_feats)))
+    return fail("scratch too small");
+  for (int i = 0; i < n_feats; ++i) {
+    if (!feats[i] || half[i] <= 0) return fail("disc: empty feature tensor");
+    if (backward && !grads[i]) return fail("null argument");
+  }
+  DeviceGuard guard(device_of(feats[0]));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(scratch);
+  for (int first = 0; first < n_feats; first += kFmMax) {
+    FmTable t;
+    std::memset(&t, 0, sizeof(t));
+    t.n = std::min(kFmMax, n_feats - first);
+    long long blocks = 0;
+    for (int k = 0; k < t.n; ++k) {
+      t.feat[k] = feats[first + k];
+      t.grad[k] = backward ? grads[first + k] : nullptr;
+      t.half[k] = half[first + k];
+      t.blk_begin[k] = static_cast<int>(blocks);
+      blocks += (half[first + k] + kFmChunk - 1) / kFmChunk;
+      if (blocks > 0x7fffffffll) return fail("disc: feature tensors too large");
+    }
+    t.blk_begin[t.n] = static_cast<int>(blocks);
+    if (backward) {
+      disc_fm_bwd_kernel<<<static_cast<unsigned>(blocks), kDiscThreads, 0, st>>>(t, g_loss);
+      KV_CUDA(cudaGetLastError());
+      ++g_launches;
+    } else {
+      disc_fm_partial_kernel<<<static_cast<unsigned>(blocks), kDiscThreads, 0, st>>>(t, partial);
+      KV_CUDA(cudaGetLastError());
+      disc_fm_finish_kernel<<<1, kDiscThreads, 0, st>>>(partial, static_cast<int>(blocks), loss, first > 0);
+      KV_CUDA(cudaGetLastError());
+      g_launches += 2;
+    }
+  }
   return 0;
 }
 

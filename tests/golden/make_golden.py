@@ -36,6 +36,12 @@ Fixtures (all float32, little-endian .npz):
   o12_full.npz      BASELINE configs 3 and 4 at their own length: latent 512, [1,512,375] -> [1,1,480000] (config 3's
                     clip), and latent 1024, decode_audio(chunked=True, chunk_size=128, overlap=32) AND unchunked over
                     T=375 (config 4); sampled points (clip edges, every window seam, every 97th sample) + sums
+  disc.npz          the reference's OobleckDiscriminator (models/discriminators.py:240-297; multi-scale Conv1d nets +
+                    multi-period 15 x 15 Conv2d nets) at random init, stereo and mono (a length that is no multiple of
+                    any period): loss(reals, fakes) = hinge discriminator / generator losses and the feature-matching
+                    distance, the summed scores, a checksum of each of the 40 feature tensors, autograd gradients of
+                    each loss w.r.t. the fakes and of the discriminator loss w.r.t. every parameter (norm + a strided
+                    sample); weights re-created from the seed, per-parameter checksums recorded
 Weights of the larger models are NOT stored: they are re-created from the recorded seed by the
 same construction order (nn.Conv1d / nn.ConvTranspose1d default init), and the fixture carries a
 float64 checksum of every parameter so a mismatch is detected rather than silently compared.
@@ -426,7 +432,62 @@ def mrstft_fixtures():
     print("wrote mrstft.npz", os.path.getsize(os.path.join(HERE, "mrstft.npz")) // 1024, "KiB")
 
 
+def disc_fixtures():
+    """SURVEY section 8(f) item 4 (discriminator half): the reference's OobleckDiscriminator, imported unmodified
+    (audiotools / dac.model.discriminator / encodec, which this class never touches, are stubbed)."""
+    import importlib.util
+    for m in ["audiotools", "dac", "dac.model", "dac.model.discriminator", "encodec", "encodec.msstftd"]:
+        sys.modules.setdefault(m, MagicMock())
+    spec = importlib.util.spec_from_file_location("ref_discriminators",
+                                                  os.path.join(REF, "stable_audio_tools", "models", "discriminators.py"))
+    dm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(dm)
+    out = {}
+    for tag, C, B, T, seed in (("stereo", 2, 2, 3000, 21), ("mono", 1, 3, 2999, 22)):
+        torch.manual_seed(seed)
+        m = dm.OobleckDiscriminator(in_channels=C)
+        g = torch.Generator().manual_seed(seed + 100)
+        t = torch.arange(T, dtype=torch.float32) / 44100.0
+        base = 0.3 * torch.sin(2 * np.pi * 440.0 * t) + 0.1 * torch.sin(2 * np.pi * 3100.0 * t + 0.5)
+        reals = (base + 0.05 * torch.randn(B, C, T, generator=g)).contiguous()
+        fakes = (0.9 * base + 0.07 * torch.randn(B, C, T, generator=g)).contiguous().requires_grad_(True)
+        out[f"{tag}.seed"] = np.int64(seed)
+        out[f"{tag}.reals"], out[f"{tag}.fakes"] = reals.numpy(), fakes.detach().numpy()
+        for k, v in checksums(m.state_dict()).items():
+            out[f"{tag}.cs.{k}"] = v
+        dis, gen, fm = m.loss(reals, fakes)
+        out[f"{tag}.dis"], out[f"{tag}.gen"], out[f"{tag}.fm"] = (np.float64(dis.item()), np.float64(gen.item()),
+                                                                  np.float64(fm.item()))
+        inputs = m.multi_discriminator({"reals": reals, "fakes": fakes})
+        out[f"{tag}.score_reals"] = inputs["score_reals"].detach().numpy()
+        out[f"{tag}.score_fakes"] = inputs["score_fakes"].detach().numpy()
+        fr, ff = inputs["features_reals"], inputs["features_fakes"]
+        out[f"{tag}.n_features"] = np.int64(len(fr))
+        for i, (a, b) in enumerate(zip(fr, ff)):
+            out[f"{tag}.feat{i}.shape"] = np.array(a.shape, dtype=np.int64)
+            out[f"{tag}.feat{i}.sums"] = np.array([a.double().sum().item(), a.double().abs().sum().item(),
+                                                   b.double().sum().item(), b.double().abs().sum().item()])
+        params = [p for p in m.parameters()]
+        names = [k for k, _ in m.named_parameters()]
+        for lname, loss in (("dis", dis), ("gen", gen), ("fm", fm)):
+            gr = torch.autograd.grad(loss, [fakes] + params, retain_graph=True, allow_unused=True)
+            out[f"{tag}.g_fakes.{lname}"] = gr[0].numpy()
+            if lname == "gen":
+                continue
+            for k, gp in zip(names, gr[1:]):
+                gp = torch.zeros(1) if gp is None else gp
+                out[f"{tag}.gp.{lname}.{k}.norm"] = np.float64(gp.double().norm().item())
+                flat = gp.reshape(-1)
+                out[f"{tag}.gp.{lname}.{k}.sample"] = flat[:: max(1, flat.numel() // 61)][:64].numpy()
+        print(tag, "dis", dis.item(), "gen", gen.item(), "fm", fm.item(), "features", len(fr))
+    np.savez_compressed(os.path.join(HERE, "disc.npz"), **out)
+    print("wrote disc.npz", os.path.getsize(os.path.join(HERE, "disc.npz")) // 1024, "KiB")
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "disc":
+        disc_fixtures()
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "mrstft":
         mrstft_fixtures()
         return
@@ -448,6 +509,8 @@ def main():
         o12_fixtures(ae_mod)
         return
     bigvgan_fixtures()
+    disc_fixtures()
+    mrstft_fixtures()
     o12_fixtures(ae_mod)
     nearest_fixtures(ae_mod)
     glue_fixtures()
