@@ -440,6 +440,7 @@ def run_cuda(args):
             legs += [("config4_stream", lambda: measure_stream(args, dev)),
                      ("bigvgan_decode", lambda: measure_bigvgan(args, dev)),
                      ("mrstft_loss", lambda: measure_mrstft(args, dev)),
+                     ("oobleck_discriminator", lambda: measure_discriminator(args, dev)),
                      ("gpu_eager_baseline", lambda: gpu_eager_baseline(dev))]
         for name, fn in legs:
             try:
@@ -712,6 +713,92 @@ def measure_mrstft(args, dev):
     return out
 
 
+def measure_discriminator(args, dev):
+    """SURVEY section 8(f) item 4 (discriminator half): OobleckDiscriminator.loss of the reference's autoencoder training
+    wrapper (models/discriminators.py:240-297, called at training/autoencoders.py:288) at the per-GPU training batch of
+    BASELINE configs[4] (4 clips x 5.016 s stereo): the generator step (losses + gradient w.r.t. the decoded signal) and
+    the discriminator step (losses + gradients of all 50.4 M parameters), next to the reference's own module in torch
+    eager on the same GPU (cuDNN, torch's default conv settings) when a copy of the reference is reachable."""
+    import torch
+    import kalle_audio_b200.discriminators as D
+    torch.manual_seed(0)
+    ours = D.OobleckDiscriminator(in_channels=2)
+    sd = {k: v.detach().clone() for k, v in ours.state_dict().items()}
+    ours = ours.to(dev)
+    B, T = 4, 221184
+    reals = 0.1 * torch.randn(B, 2, T, device=dev)
+    fakes = (0.9 * reals + 0.02 * torch.randn_like(reals)).requires_grad_(True)
+    # multiply-adds the folded form executes (2 FLOP each), forward, both halves of the batch
+    flops = 0.0
+    for net, W0, T0 in [(n, 1, T >> i) for i, n in enumerate(ours.multi_discriminator.discriminators[0].layers)] + \
+                       [(n, p, -(-T // p)) for n, p in zip(ours.multi_discriminator.discriminators[1].layers,
+                                                           ours.multi_discriminator.discriminators[1].periods)]:
+        W, t = W0, T0
+        for cv in net.convs():
+            Wo = (W + 2 * cv.padding - cv.kernel_size) // cv.stride + 1 if cv.two_d else 1
+            t = (t + 2 * cv.padding - cv.kernel_size) // cv.stride + 1
+            flops += 2.0 * 2 * B * t * (cv.out_channels * Wo) * (cv.in_channels * W) * cv.kernel_size
+            W = Wo
+    out = {"config": {"workload": f"OobleckDiscriminator.loss, {B} x 2 x {T} samples (reals + fakes = {2 * B} signals), fp32"},
+           "fwd_flops_folded": flops}
+
+    def steps(mod):
+        params = [p for p in mod.parameters()]
+
+        def gen_step():
+            for p in params:
+                p.requires_grad_(False)
+            with torch.enable_grad():
+                dis, gen, fm = mod.loss(reals, fakes)
+                (gen + fm).backward()
+            fakes.grad = None
+            return gen
+
+        def dis_step():
+            for p in params:
+                p.requires_grad_(True)
+            with torch.enable_grad():
+                dis, gen, fm = mod.loss(reals, fakes.detach())
+                dis.backward()
+            for p in params:
+                p.grad = None
+            return dis
+        return (("generator_step", gen_step), ("discriminator_step", dis_step))
+
+    mods = [("kvae", ours)]
+    try:
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        from oracle.reference_loader import load_reference_discriminators
+        rd = load_reference_discriminators()
+        if rd is not None:
+            ref = rd.OobleckDiscriminator(in_channels=2)
+            ref.load_state_dict(sd)
+            mods.append(("reference_torch_eager", ref.to(dev)))
+    except Exception as exc:
+        out["reference_torch_eager"] = {"error": f"{type(exc).__name__}: {exc}"}
+    for name, mod in mods:
+        res = {}
+        for sname, fn in steps(mod):
+            for _ in range(2):
+                l = fn()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            n = max(2, args.steps // 4)
+            for _ in range(n):
+                l = fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            res[sname] = {"ms": e0.elapsed_time(e1) / n, "loss": float(l.detach())}
+        out[name] = res
+        del mod
+        torch.cuda.empty_cache()
+    k = out["kvae"]
+    out["kvae"]["generator_step"]["tflops_folded"] = 2 * flops / (k["generator_step"]["ms"] * 1e9)      # fwd + dgrad
+    out["kvae"]["discriminator_step"]["tflops_folded"] = 3 * flops / (k["discriminator_step"]["ms"] * 1e9)  # + wgrad
+    return out
+
+
 def run_extra(args):
     """--workload o12_decode / stream as stand-alone lines (the default line carries them as extra keys)."""
     import torch
@@ -725,6 +812,8 @@ def run_extra(args):
         dist.init_process_group("nccl", device_id=dev)
     if args.workload == "bigvgan":
         out = measure_bigvgan(args, dev)
+    elif args.workload == "discriminator":
+        out = measure_discriminator(args, dev)
     else:
         out = measure_o12_decode(args, dev, rank, world) if args.workload == "o12_decode" else measure_stream(args, dev)
     if rank == 0:
@@ -855,7 +944,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["cuda", "reference"], default="cuda")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", choices=["roundtrip", "o12_decode", "stream", "train", "eager_baseline", "bigvgan"], default="roundtrip",
+    ap.add_argument("--workload", choices=["roundtrip", "o12_decode", "stream", "train", "eager_baseline", "bigvgan", "discriminator"], default="roundtrip",
                     help="roundtrip = BASELINE configs[1] (the driver's line); o12_decode = configs[2]; stream = configs[3]; "
                          "train = configs[4]")
     ap.add_argument("--micro-batch", type=int, default=0)

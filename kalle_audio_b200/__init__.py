@@ -23,11 +23,12 @@ from .glue import LatentGlue
 from .dataset import LatentExtractor
 from .bigvgan import BigVGANFlowVAE
 from .losses import MultiResolutionSTFTLoss, SumAndDifferenceSTFTLoss, aw_fir_taps
+from .discriminators import OobleckDiscriminator, get_hinge_losses
 from .utils import load_ckpt_state_dict, prepare_audio, remove_weight_norm_from_model, to_pcm16
 from .training import AutoencoderTrainer, FlatAdamW, GradSync, flatten_parameters, gaussian_nll, vae_sample_with_grad
 
 __all__ = [
-    "MultiResolutionSTFTLoss", "SumAndDifferenceSTFTLoss", "aw_fir_taps",
+    "MultiResolutionSTFTLoss", "SumAndDifferenceSTFTLoss", "aw_fir_taps", "OobleckDiscriminator", "get_hinge_losses",
     "AudioAutoencoder", "AutoencoderPretransform", "Bottleneck", "DecoderBlock", "EncoderBlock", "KvaeError",
     "OobleckDecoder", "OobleckEncoder", "Pretransform", "ResidualUnit", "SigmaVAESampler", "SnakeBeta",
     "VAEBottleneck", "WNConv1d", "WNConvTranspose1d", "create_autoencoder_from_config",

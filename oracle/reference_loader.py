@@ -56,3 +56,22 @@ def load_reference():
     from stable_audio_tools.models import autoencoders, bottleneck
     _cached = (autoencoders, bottleneck, root)
     return _cached
+
+
+def load_reference_discriminators():
+    """The reference's stable_audio_tools/models/discriminators.py, imported unmodified from the same copy (audiotools /
+    dac.model.discriminator / encodec -- which OobleckDiscriminator never touches -- stubbed), or None."""
+    root = reference_root()
+    if root is None:
+        return None
+    path = os.path.join(root, "stable_audio_tools", "models", "discriminators.py")
+    if not os.path.isfile(path):
+        return None
+    import importlib.util
+    warnings.filterwarnings("ignore")
+    for m in ["audiotools", "dac", "dac.model", "dac.model.discriminator", "encodec", "encodec.msstftd"]:
+        sys.modules.setdefault(m, MagicMock())
+    spec = importlib.util.spec_from_file_location("ref_discriminators", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod

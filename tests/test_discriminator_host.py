@@ -15,6 +15,13 @@ import helpers                # noqa: E402
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+@pytest.fixture(autouse=True)
+def _grad_enabled():
+    """other test modules switch autograd off globally at import"""
+    with torch.enable_grad():
+        yield
+
+
 def _oracle():
     sys.path.insert(0, ROOT)
     from oracle import discriminator_oracle as O
