@@ -180,15 +180,22 @@ class AutoencoderTrainer:
 
     ``training_step(reals)`` = encode -> split mean/scale -> vae_sample -> decode -> Gaussian NLL + kl_weight * KL
     (+ spectral_weight * multi-resolution STFT loss when ``spectral_loss`` is given) -> backward -> gradient
-    all-reduce -> AdamW, the generator branch of the reference's ``training_step`` without its GAN terms.
+    all-reduce -> AdamW, the generator branch of the reference's ``training_step``.  With ``discriminator`` (an
+    ``OobleckDiscriminator``) the step alternates the way training/autoencoders.py:288-337 does once warmed up: odd steps
+    train the discriminator on ``loss_dis``, even steps train the autoencoder with ``adversarial_weight * loss_adv +
+    feature_matching_weight * feature_matching_distance`` added to its loss.
     One process per GPU; pass the process group (NCCL over NVLink) or leave ``None`` for the default group /
     single-GPU operation."""
 
     def __init__(self, autoencoder: nn.Module, lr: float = 1e-4, betas=(0.8, 0.99), eps: float = 1e-8,
                  weight_decay: float = 1e-3, kl_weight: float = 1e-6, log_sigma: float = 0.0,
                  precision: Optional[str] = "bf16", process_group=None, data_parallel: bool = True,
-                 spectral_loss: Optional[nn.Module] = None, spectral_weight: float = 1.0, nll_weight: float = 1.0):
+                 spectral_loss: Optional[nn.Module] = None, spectral_weight: float = 1.0, nll_weight: float = 1.0,
+                 discriminator: Optional[nn.Module] = None, adversarial_weight: float = 0.1,
+                 feature_matching_weight: float = 5.0, disc_lr: Optional[float] = None, warmup_steps: int = 0):
         self.autoencoder = autoencoder
+        self.discriminator, self.adversarial_weight = discriminator, adversarial_weight
+        self.feature_matching_weight, self.warmup_steps, self.global_step = feature_matching_weight, warmup_steps, 0
         # the reference's generator loss is MR-STFT + adversarial + feature matching + KL (training/autoencoders.py:
         # 150-200); ``spectral_loss`` (kalle_audio_b200.SumAndDifferenceSTFTLoss / MultiResolutionSTFTLoss, called as
         # module(reals, decoded) like the reference's AuralossLoss) adds its spectral term, ``nll_weight=0`` drops the
@@ -208,6 +215,11 @@ class AutoencoderTrainer:
             self.sync.enabled, self.sync.world = False, 1
         self.opt = FlatAdamW([self.flat_enc, self.flat_dec], lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
                              modules=[self.encoder, self.decoder])
+        if discriminator is not None:
+            # the discriminator has its own optimizer in the reference (optimizer_configs['discriminator'])
+            self.flat_disc = flatten_parameters(discriminator)
+            self.opt_disc = FlatAdamW([self.flat_disc], lr=lr if disc_lr is None else disc_lr, betas=betas, eps=eps,
+                                      weight_decay=weight_decay)
         self._grads: Dict[str, torch.Tensor] = {}
         for name, mod, flat in (("enc", self.encoder, self.flat_enc), ("dec", self.decoder, self.flat_dec)):
             # applied to every runner the module creates from now on (another precision, a rebuilt cache after .to()):
@@ -235,6 +247,10 @@ class AutoencoderTrainer:
         step = torch.tensor([self.opt.step_count], device=self.flat_enc.device, dtype=torch.int64)
         self.sync.broadcast([self.flat_enc, self.flat_dec] + self.opt.state() + [step], src)
         self.opt.step_count = int(step)
+        if self.discriminator is not None:
+            dstep = torch.tensor([self.opt_disc.step_count, self.global_step], device=self.flat_enc.device, dtype=torch.int64)
+            self.sync.broadcast([self.flat_disc] + self.opt_disc.state() + [dstep], src)
+            self.opt_disc.step_count, self.global_step = int(dstep[0]), int(dstep[1])
         for m in (self.encoder, self.decoder):
             m._weights_epoch = getattr(m, "_weights_epoch", 0) + 1
 
@@ -266,9 +282,53 @@ class AutoencoderTrainer:
             st = self.spectral_loss(reals, decoded)
             loss = loss + self.spectral_weight * st
             info["mrstft"] = st.detach()
+        if self._warmed_up():       # training/autoencoders.py:287-296, 144-145: the GAN terms of the generator loss
+            for p in self.discriminator.parameters():
+                p.requires_grad_(False)       # only the gradient w.r.t. the decoded signal is wanted here
+            loss_dis, loss_adv, fm = self.discriminator.loss(reals, decoded)
+            loss = loss + self.adversarial_weight * loss_adv + self.feature_matching_weight * fm
+            info.update(loss_dis=loss_dis.detach(), loss_adv=loss_adv.detach(), feature_matching_distance=fm.detach())
         return loss, info
 
+    def _warmed_up(self) -> bool:
+        return self.discriminator is not None and self.global_step >= self.warmup_steps
+
+    def discriminator_step(self, reals: torch.Tensor, noise: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        """training/autoencoders.py:308-321: loss_dis -> backward -> discriminator optimizer.  The reference leaves
+        ``decoded`` attached, so its backward also runs through the autoencoder and throws those gradients away at the
+        next ``opt_gen.zero_grad()``; here the autoencoder runs without autograd."""
+        disc = self.discriminator
+        with torch.no_grad():
+            mean, scale = self.encoder(reals).chunk(2, dim=1)
+            latents, _ = vae_sample_with_grad(mean, scale, noise)
+            decoded = self.decoder(latents)
+        params = list(disc.parameters())
+        for p in params:
+            p.requires_grad_(True)
+            p.grad = None
+        with torch.enable_grad():
+            loss_dis, loss_adv, fm = disc.loss(reals, decoded)
+            loss_dis.backward()
+        grads = torch.cat([(torch.zeros_like(p) if p.grad is None else p.grad).reshape(-1).float() for p in params])
+        for p in params:
+            p.grad = None
+        self.sync.launch(grads)
+        self.sync.wait()
+        self.opt_disc.step([grads], grad_scale=self.sync.grad_scale)
+        return {"loss": loss_dis.detach(), "loss_dis": loss_dis.detach(), "loss_adv": loss_adv.detach(),
+                "feature_matching_distance": fm.detach(), "decoded": decoded}
+
     def training_step(self, reals: torch.Tensor, noise: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+        step = self.global_step
+        if self._warmed_up() and step % 2:      # training/autoencoders.py:309: odd steps train the discriminator
+            info = self.discriminator_step(reals, noise)
+            self.global_step = step + 1
+            return info
+        info = self.generator_step(reals, noise)
+        self.global_step = step + 1
+        return info
+
+    def generator_step(self, reals: torch.Tensor, noise: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
         for p in self.autoencoder.parameters():
             p.grad = None
         self._grads.clear()

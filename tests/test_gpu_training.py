@@ -372,3 +372,42 @@ def test_trainer_with_the_spectral_loss(dev):
         assert "mrstft" in info and torch.isfinite(info["loss"])
         losses.append(float(info["mrstft"]))
     assert losses[-1] < losses[0], losses
+
+
+def test_trainer_with_the_discriminator(dev):
+    """AutoencoderTrainer with the reference's GAN terms (training/autoencoders.py:287-337): even steps train the
+    autoencoder on spectral + adversarial + feature-matching + KL, odd steps train the OobleckDiscriminator on the hinge
+    loss; each step moves only its own parameters, and the logged GAN terms are the discriminator's own loss() on the
+    step's decoded signal."""
+    from kalle_audio_b200.discriminators import OobleckDiscriminator
+    torch.manual_seed(0)
+    ae = H.build("mid", 0).to(dev)
+    disc = OobleckDiscriminator(in_channels=2).to(dev)
+    sd = k.SumAndDifferenceSTFTLoss(fft_sizes=[512, 256, 128, 64, 32], hop_sizes=[128, 64, 32, 16, 8],
+                                    win_lengths=[512, 256, 128, 64, 32], perceptual_weighting=True, sample_rate=16000)
+    tr = k.AutoencoderTrainer(ae, lr=2e-4, precision="bf16", data_parallel=False, spectral_loss=sd, nll_weight=0.0,
+                              discriminator=disc, adversarial_weight=0.1, feature_matching_weight=5.0)
+    x = 0.1 * torch.randn(2, 2, 40 * 64, device=dev)
+    noise = torch.randn(2, 64, 64, device=dev)
+    ae0 = torch.cat([tr.flat_enc, tr.flat_dec]).clone()
+    d0 = tr.flat_disc.clone()
+    info = tr.training_step(x, noise)                      # step 0: generator
+    assert {"mrstft", "loss_adv", "feature_matching_distance", "kl"} <= set(info)
+    assert torch.isfinite(info["loss"])
+    assert not torch.equal(torch.cat([tr.flat_enc, tr.flat_dec]), ae0) and torch.equal(tr.flat_disc, d0)
+    with torch.no_grad():
+        dis, adv, fm = disc.loss(x, info["decoded"].float())
+    assert abs(float(adv) - float(info["loss_adv"])) <= 1e-5 + 1e-4 * abs(float(adv))
+    assert abs(float(fm) - float(info["feature_matching_distance"])) <= 1e-4 * float(fm)
+    want = float(info["mrstft"]) + 0.1 * float(adv) + 5.0 * float(fm) + tr.kl_weight * float(info["kl"])
+    assert abs(float(info["loss"]) - want) <= 1e-4 * abs(want)
+    ae1 = torch.cat([tr.flat_enc, tr.flat_dec]).clone()
+    info = tr.training_step(x, noise)                      # step 1: discriminator
+    assert "mrstft" not in info and torch.isfinite(info["loss_dis"])
+    assert torch.equal(torch.cat([tr.flat_enc, tr.flat_dec]), ae1) and not torch.equal(tr.flat_disc, d0)
+    first = float(info["loss_dis"])
+    for _ in range(3):                                     # discriminator steps on a fixed batch lower its hinge loss
+        info = tr.discriminator_step(x, noise)
+    assert float(info["loss_dis"]) < first, (first, float(info["loss_dis"]))
+    info = tr.training_step(x, noise)                      # step 2: generator again, with the updated discriminator
+    assert "mrstft" in info and torch.isfinite(info["loss"])
