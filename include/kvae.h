@@ -347,6 +347,14 @@ size_t kvae_disc_feature_match_scratch_bytes(const long long* half, int n_feats)
 int kvae_disc_feature_match(const float* const* feats, const long long* half, int n_feats, float* loss,
                             const float* g_loss, float* const* grads, void* scratch, size_t scratch_bytes, void* stream);
 
+/* The nets' own conv geometry -- Conv1d(k = 15, stride 4, padding 7) on [N, Cin, T] fp32 with a folded weight in torch
+ * layout (discriminators.py:70-71, 85-100) -- on register-tiled kernels written for it; same contract as kvae_conv1d_fwd /
+ * kvae_conv1d_bwd (scratch: kvae_conv1d_scratch_bytes(Cin, Cout, 15); dw, dbias, gx each optional). */
+int kvae_disc_conv15_supported(int K, int stride, int pad);
+int kvae_disc_conv15_fwd(const float* x, float* y, const float* w, const float* bias, int N, int Cin, int Cout, long long T,
+                         void* scratch, size_t scratch_bytes, void* stream);
+int kvae_disc_conv15_bwd(const float* x, const float* gy, const float* w, float* gx, float* dw, float* dbias, int N, int Cin,
+                         int Cout, long long T, void* scratch, size_t scratch_bytes, void* stream);
 #ifdef __cplusplus
 }
 #endif

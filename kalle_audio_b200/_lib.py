@@ -147,6 +147,11 @@ SIGNATURES = {
     "kvae_disc_feature_match_scratch_bytes": (C.c_size_t, [C.POINTER(C.c_longlong), C.c_int]),
     "kvae_disc_feature_match": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_longlong), C.c_int, C.c_void_p, C.c_void_p,
                                           C.POINTER(C.c_void_p), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kvae_disc_conv15_supported": (C.c_int, [C.c_int] * 3),
+    "kvae_disc_conv15_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong,
+                                       C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kvae_disc_conv15_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                       C.c_int, C.c_longlong, C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 
 

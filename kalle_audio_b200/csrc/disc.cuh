@@ -279,4 +279,244 @@ disc_fm_bwd_kernel(const __grid_constant__ FmTable t, const float* __restrict__ 
   }
 }
 
+// =====================================================================================================================
+// The discriminator's strided convolution -- k = 15, stride 4, padding 7 on [N, C, T] fp32 (discriminators.py:70-71, 85-
+// 100: every conv of every net but the last 1 x 1) -- as three register-tiled fp32 kernels.  The generic layer kernels
+// (conv_direct_kernel / wgrad_direct_kernel) reach ~9 / ~4 TFLOP/s on this geometry in the API layout (one tap and 16
+// channels per barrier pair, 16-row stages in the weight gradient); here each thread keeps a register window of the
+// input that serves all 15 taps of several outputs, shared memory is read with 16-byte loads at >= 13 FMAs per load, and
+// the layouts are chosen so that those loads are bank-conflict free (see each kernel).
+// =====================================================================================================================
+constexpr int kDK = 15, kDS = 4, kDP = 7;
+
+// ---- forward: y[n, co, t] = bias[co] + sum_{ci, k} wp[k][ci][co] * x[n, ci, 4 t + k - 7]      (wp = pack_weights layout)
+// Block: 64 co x 128 t; 256 threads = 16 t-groups (8 consecutive t) x 16 co-groups (4 co); lane % 16 = t-group.
+// A thread's 8 outputs x 15 taps read the 43 consecutive inputs 32 tg + 4 j + k: one register window per input channel.
+// The slab row is stored in 32-float segments 36 floats apart, so the 8 lanes of a quarter warp (8 t-groups) hit 32
+// different banks with their 16-byte loads; lanes of different co-groups read the same slab address (broadcast).
+constexpr int kCfTt = 128, kCfCo = 64, kCfKc = 4;
+constexpr int kCfSeg = 36;
+constexpr int kCfSlab = 16 * 32 + 12;           // slab entries per channel: j = 0 .. 523
+constexpr int kCfRow = kCfSeg * 16 + 12;        // 588 floats
+
+__global__ void __launch_bounds__(256, 2)
+disc_conv15_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wp, const float* __restrict__ bias,
+                       float* __restrict__ y, int Cin, int Cout, int T, int To) {
+  __shared__ __align__(16) float xs[kCfKc][kCfRow];
+  __shared__ __align__(16) float ws[kCfKc][kDK][kCfCo];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tg = lane & 15, cg = warp * 2 + (lane >> 4);
+  const int tb0 = blockIdx.x * kCfTt, co0 = blockIdx.y * kCfCo, n = blockIdx.z;
+  const long long u0 = static_cast<long long>(kDS) * tb0 - kDP;      // input index of slab entry 0
+  const float* xn = x + static_cast<size_t>(n) * Cin * T;
+  float acc[4][8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+  for (int c0 = 0; c0 < Cin; c0 += kCfKc) {
+    const int nci = min(kCfKc, Cin - c0);
+    __syncthreads();
+    for (int idx = tid; idx < nci * kCfSlab; idx += 256) {
+      const int ci = idx / kCfSlab, j = idx - ci * kCfSlab;
+      const long long u = u0 + j;
+      float v = 0.f;
+      if (u >= 0 && u < T) v = xn[static_cast<size_t>(c0 + ci) * T + u];
+      xs[ci][kCfSeg * (j >> 5) + (j & 31)] = v;
+    }
+    for (int idx = tid; idx < nci * kDK * kCfCo; idx += 256) {
+      const int co = idx & (kCfCo - 1), r = idx >> 6;
+      const int k = r % kDK, ci = r / kDK;
+      ws[ci][k][co] = (co0 + co < Cout) ? wp[(static_cast<size_t>(k) * Cin + c0 + ci) * Cout + co0 + co] : 0.f;
+    }
+    __syncthreads();
+    for (int ci = 0; ci < nci; ++ci) {
+      float xw[44];
+      const float4* seg = reinterpret_cast<const float4*>(&xs[ci][kCfSeg * tg]);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 v = seg[q];
+        xw[4 * q] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w;
+      }
+      const float4* nxt = reinterpret_cast<const float4*>(&xs[ci][kCfSeg * (tg + 1)]);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4 v = nxt[q];
+        xw[32 + 4 * q] = v.x; xw[33 + 4 * q] = v.y; xw[34 + 4 * q] = v.z; xw[35 + 4 * q] = v.w;
+      }
+#pragma unroll
+      for (int k = 0; k < kDK; ++k) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&ws[ci][k][4 * cg]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xv = xw[4 * j + k];
+          acc[0][j] = fmaf(w4.x, xv, acc[0][j]);
+          acc[1][j] = fmaf(w4.y, xv, acc[1][j]);
+          acc[2][j] = fmaf(w4.z, xv, acc[2][j]);
+          acc[3][j] = fmaf(w4.w, xv, acc[3][j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int co = co0 + 4 * cg + i;
+    if (co >= Cout) continue;
+    const float b = bias ? bias[co] : 0.f;
+    float* yr = y + (static_cast<size_t>(n) * Cout + co) * To;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int t = tb0 + 8 * tg + j;
+      if (t < To) yr[t] = acc[i][j] + b;
+    }
+  }
+}
+
+// ---- data gradient: with v = u + 7, phi = v % 4, q = v / 4:  gx[n, ci, u] = sum_{co, m} wT[phi + 4 m][co][ci] * gy[n, co, q - m]
+// (wT = pack_weights layout of the weight read as a ConvTranspose1d weight).  Block: 64 ci x 256 v; 256 threads = 16
+// v-groups (16 consecutive v = 4 q x 4 phases) x 16 ci-groups (4 ci).  Per output channel a thread loads the 8 gradients
+// gy[q0 - 4 .. q0 + 3] (two 16-byte loads, consecutive lanes consecutive addresses) and, per tap, 4 weights.
+constexpr int kDgV = 256, kDgCi = 64, kDgKc = 4;
+constexpr int kDgRow = 72;
+
+__global__ void __launch_bounds__(256, 2)
+disc_conv15_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__ wT, float* __restrict__ gx, int Cin,
+                         int Cout, int T, int To) {
+  __shared__ __align__(16) float gs[kDgKc][kDgRow];
+  __shared__ __align__(16) float ws[kDgKc][kDK][kDgCi];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int vg = lane & 15, cig = warp * 2 + (lane >> 4);
+  const int vb0 = blockIdx.x * kDgV, ci0 = blockIdx.y * kDgCi, n = blockIdx.z;
+  const int qb0 = vb0 / kDS;
+  const float* gn = gy + static_cast<size_t>(n) * Cout * To;
+  float acc[4][16];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+  for (int c0 = 0; c0 < Cout; c0 += kDgKc) {
+    const int nco = min(kDgKc, Cout - c0);
+    __syncthreads();
+    for (int idx = tid; idx < nco * 68; idx += 256) {
+      const int co = idx / 68, i = idx - co * 68;
+      const int t = qb0 - 4 + i;
+      gs[co][i] = (t >= 0 && t < To) ? gn[static_cast<size_t>(c0 + co) * To + t] : 0.f;
+    }
+    for (int idx = tid; idx < nco * kDK * kDgCi; idx += 256) {
+      const int ci = idx & (kDgCi - 1), r = idx >> 6;
+      const int k = r % kDK, co = r / kDK;
+      ws[co][k][ci] = (ci0 + ci < Cin) ? wT[(static_cast<size_t>(k) * Cout + c0 + co) * Cin + ci0 + ci] : 0.f;
+    }
+    __syncthreads();
+    for (int co = 0; co < nco; ++co) {
+      float gw[8];
+      {
+        const float4 a = *reinterpret_cast<const float4*>(&gs[co][4 * vg]);
+        const float4 b = *reinterpret_cast<const float4*>(&gs[co][4 * vg + 4]);
+        gw[0] = a.x; gw[1] = a.y; gw[2] = a.z; gw[3] = a.w; gw[4] = b.x; gw[5] = b.y; gw[6] = b.z; gw[7] = b.w;
+      }
+#pragma unroll
+      for (int k = 0; k < kDK; ++k) {
+        const float4 w4 = *reinterpret_cast<const float4*>(&ws[co][k][4 * cig]);
+        const int phi = k & 3, m = k >> 2;
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const float g = gw[4 + qq - m];
+          acc[0][4 * qq + phi] = fmaf(w4.x, g, acc[0][4 * qq + phi]);
+          acc[1][4 * qq + phi] = fmaf(w4.y, g, acc[1][4 * qq + phi]);
+          acc[2][4 * qq + phi] = fmaf(w4.z, g, acc[2][4 * qq + phi]);
+          acc[3][4 * qq + phi] = fmaf(w4.w, g, acc[3][4 * qq + phi]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ci = ci0 + 4 * cig + i;
+    if (ci >= Cin) continue;
+    float* gr = gx + (static_cast<size_t>(n) * Cin + ci) * T;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int u = vb0 + 16 * vg + j - kDP;
+      if (u >= 0 && u < T) gr[u] = acc[i][j];
+    }
+  }
+}
+
+// ---- weight gradient: dw[co][ci][k] += sum_{n, t} gy[n, co, t] * x[n, ci, 4 t + k - 7]      (torch layout, atomics)
+// Block: 64 co x 16 ci x 15 taps over a slice of the (n, 64-sample t block) items; 256 threads = 16 ci (lane % 16) x 16
+// co-groups (4 co): 60 accumulators per thread.  Per 4 outputs t a thread loads 4 x 4 gradients and a 28-float input
+// window (11 16-byte loads for 240 FMAs).  The input slab rows are 276 floats apart (= 20 mod 32), so the 8 channels of
+// a quarter warp hit 32 different banks; gradient rows are read by all 16 lanes of a co-group at once (broadcast).
+constexpr int kWgTc = 64, kWgCo = 64, kWgCi = 16;
+constexpr int kWgXRow = 276, kWgXUsed = kDS * kWgTc + 12;   // 268 slab entries per channel
+constexpr int kWgGRow = 68;
+
+__global__ void __launch_bounds__(256)
+disc_conv15_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ dw, int Cin,
+                         int Cout, int T, int To, int n_items) {
+  __shared__ __align__(16) float gs[kWgCo][kWgGRow];
+  __shared__ __align__(16) float xs[kWgCi][kWgXRow];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int cil = lane & 15, cg = warp * 2 + (lane >> 4);
+  const int n_ci_tiles = (Cin + kWgCi - 1) / kWgCi;
+  const int co0 = (blockIdx.x / n_ci_tiles) * kWgCo, ci0 = (blockIdx.x % n_ci_tiles) * kWgCi;
+  const int tiles_t = (To + kWgTc - 1) / kWgTc;
+  float acc[4][kDK];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int k = 0; k < kDK; ++k) acc[i][k] = 0.f;
+  for (int item = blockIdx.y; item < n_items; item += gridDim.y) {
+    const int n = item / tiles_t, t0 = (item - n * tiles_t) * kWgTc;
+    __syncthreads();
+    for (int idx = tid; idx < kWgCo * kWgTc; idx += 256) {
+      const int row = idx >> 6, col = idx & 63;
+      const int co = co0 + row, t = t0 + col;
+      gs[row][col] = (co < Cout && t < To) ? gy[(static_cast<size_t>(n) * Cout + co) * To + t] : 0.f;
+    }
+    const long long u0 = static_cast<long long>(kDS) * t0 - kDP;
+    for (int idx = tid; idx < kWgCi * kWgXUsed; idx += 256) {
+      const int ci = idx / kWgXUsed, j = idx - ci * kWgXUsed;
+      const long long u = u0 + j;
+      const int c = ci0 + ci;
+      xs[ci][j] = (c < Cin && u >= 0 && u < T) ? x[(static_cast<size_t>(n) * Cin + c) * T + u] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int tau0 = 0; tau0 < kWgTc; tau0 += 4) {
+      float g[4][4], xw[28];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float4 v = *reinterpret_cast<const float4*>(&gs[4 * cg + i][tau0]);
+        g[i][0] = v.x; g[i][1] = v.y; g[i][2] = v.z; g[i][3] = v.w;
+      }
+#pragma unroll
+      for (int q = 0; q < 7; ++q) {
+        const float4 v = *reinterpret_cast<const float4*>(&xs[cil][kDS * tau0 + 4 * q]);
+        xw[4 * q] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w;
+      }
+#pragma unroll
+      for (int tt = 0; tt < 4; ++tt)
+#pragma unroll
+        for (int k = 0; k < kDK; ++k) {
+          const float xv = xw[4 * tt + k];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) acc[i][k] = fmaf(g[i][tt], xv, acc[i][k]);
+        }
+    }
+  }
+  const int c = ci0 + cil;
+  if (c < Cin) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int co = co0 + 4 * cg + i;
+      if (co >= Cout) continue;
+      float* d = dw + (static_cast<size_t>(co) * Cin + c) * kDK;
+#pragma unroll
+      for (int k = 0; k < kDK; ++k) atomicAdd(d + k, acc[i][k]);
+    }
+  }
+}
+
 }  // namespace kvae

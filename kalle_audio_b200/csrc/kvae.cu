@@ -2746,4 +2746,70 @@ int kvae_disc_feature_match(const float* const* feats, const long long* half, in
   return 0;
 }
 
+// ---- the discriminator's own conv geometry (k = 15, stride 4, padding 7) on the register-tiled kernels of disc.cuh
+int kvae_disc_conv15_supported(int K, int stride, int pad) { return K == kDK && stride == kDS && pad == kDP; }
+
+int kvae_disc_conv15_fwd(const float* x, float* y, const float* w, const float* bias, int N, int Cin, int Cout, long long T,
+                         void* scratch, size_t scratch_bytes, void* stream) {
+  if (!x || !y || !w || !scratch) return fail("null argument");
+  if (N <= 0 || Cin <= 0 || Cout <= 0 || T <= 0) return fail("empty input");
+  if (N > 65535 || T > 0x7fffffffll - 64) return fail("disc conv: batch or length too large");
+  if (scratch_bytes < kvae_conv1d_scratch_bytes(Cin, Cout, kDK)) return fail("scratch too small");
+  DeviceGuard guard(device_of(x));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int To = static_cast<int>((T - 1) / kDS + 1);
+  float* wp = static_cast<float*>(scratch);
+  const size_t n = static_cast<size_t>(Cin) * Cout * kDK;
+  pack_weights_kernel<<<static_cast<int>(std::min<size_t>((n + 255) / 256, 4096)), 256, 0, st>>>(w, 0, Cout, Cin, kDK, nullptr, wp);
+  KV_CUDA(cudaGetLastError());
+  dim3 grid(ceil_div(To, kCfTt), ceil_div(Cout, kCfCo), N);
+  disc_conv15_fwd_kernel<<<grid, 256, 0, st>>>(x, wp, bias, y, Cin, Cout, static_cast<int>(T), To);
+  KV_CUDA(cudaGetLastError());
+  g_launches += 2;
+  return 0;
+}
+
+int kvae_disc_conv15_bwd(const float* x, const float* gy, const float* w, float* gx, float* dw, float* dbias, int N, int Cin,
+                         int Cout, long long T, void* scratch, size_t scratch_bytes, void* stream) {
+  if (!x || !gy || !w || !scratch) return fail("null argument");
+  if (!dw && !gx && !dbias) return fail("nothing to compute (dw, dbias and gx are all null)");
+  if (N <= 0 || Cin <= 0 || Cout <= 0 || T <= 0) return fail("empty input");
+  if (N > 65535 || T > 0x7fffffffll - 64) return fail("disc conv: batch or length too large");
+  if (scratch_bytes < kvae_conv1d_scratch_bytes(Cin, Cout, kDK)) return fail("scratch too small");
+  DeviceGuard guard(device_of(x));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int To = static_cast<int>((T - 1) / kDS + 1);
+  const size_t n = static_cast<size_t>(Cin) * Cout * kDK;
+  if (dw) {
+    KV_CUDA(cudaMemsetAsync(dw, 0, n * 4, st));
+    const int tiles = ceil_div(Cout, kWgCo) * ceil_div(Cin, kWgCi);
+    const long long items = static_cast<long long>(N) * ceil_div(To, kWgTc);
+    const int nsplit = static_cast<int>(std::max<long long>(1, std::min<long long>(std::min<long long>(items, 65535),
+                                                                                   (6ll * sm_count() + tiles - 1) / tiles)));
+    disc_conv15_wgrad_kernel<<<dim3(tiles, nsplit), 256, 0, st>>>(x, gy, dw, Cin, Cout, static_cast<int>(T), To,
+                                                                  static_cast<int>(items));
+    KV_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
+  if (dbias) {
+    bias_grad_cf_kernel<<<Cout, 256, 0, st>>>(gy, 1, dbias, N, Cout, To);
+    KV_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
+  if (!gx) return 0;
+  if (Cin < 32)      // the io-side layer (2 .. 22 folded channels): a 64-channel tile would idle; generic data gradient
+    return kvae_conv1d_bwd(x, gy, w, gx, nullptr, nullptr, 0, N, Cin, Cout, T, kDK, kDS, 1, kDP, KVAE_F32, scratch,
+                           scratch_bytes, stream);
+  float* wT = static_cast<float*>(scratch);
+  pack_weights_kernel<<<static_cast<int>(std::min<size_t>((n + 255) / 256, 4096)), 256, 0, st>>>(w, 1, Cin, Cout, kDK, nullptr, wT);
+  KV_CUDA(cudaGetLastError());
+  dim3 grid(ceil_div(static_cast<int>(T) + kDP, kDgV), ceil_div(Cin, kDgCi), N);
+  disc_conv15_dgrad_kernel<<<grid, 256, 0, st>>>(gy, wT, gx, Cin, Cout, static_cast<int>(T), To);
+  KV_CUDA(cudaGetLastError());
+  g_launches += 2;
+  return 0;
+}
+
 }  // extern "C"

@@ -11,8 +11,9 @@ Parameters are initialised through torch's own ``nn.Conv1d`` / ``nn.Conv2d`` con
 the same ``torch.manual_seed`` gives the reference's random-init ``state_dict``.
 
 Compute: every net is ONE autograd node (``_SharedNetFn``) whose forward and backward chain libkvae kernels -- the
-strided convolutions on ``kvae_conv1d_fwd`` / ``kvae_conv1d_bwd`` (fp32), everything between them on the
-``kvae_disc_*`` entry points (csrc/disc.cuh).  The multi-period nets' 15 x 15 ``Conv2d`` over ``[N, C, ceil(T / n), n]``
+strided convolutions on ``kvae_disc_conv15_fwd`` / ``kvae_disc_conv15_bwd`` (fp32 kernels written for the nets' k = 15 /
+stride 4 geometry; any other geometry on ``kvae_conv1d_fwd`` / ``kvae_conv1d_bwd``), everything between them on the
+other ``kvae_disc_*`` entry points (csrc/disc.cuh).  The multi-period nets' 15 x 15 ``Conv2d`` over ``[N, C, ceil(T / n), n]``
 runs as a ``Conv1d`` over the folded channels ``(c, w)``: identical products, without the ones that only ever meet the
 zero padding of the width axis (n <= 11 < 15).  ``EncodecDiscriminator`` and ``DACGANLoss`` wrap un-vendored packages
 (``encodec.msstftd``, ``dac.model.discriminator`` / ``audiotools``) whose arithmetic is not in the reference tree; they
@@ -21,6 +22,7 @@ raise ``NotImplementedError``.  There is no CPU path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import typing as tp
 from functools import reduce
 
@@ -36,6 +38,11 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
     return t.contiguous() if t.dtype == torch.float32 else t.float().contiguous()
 
 
+# KVAE_DISC_GENERIC=1: development switch -- every conv on the generic layer kernels (kvae_conv1d_fwd / kvae_conv1d_bwd)
+# instead of the kernels written for the nets' own k = 15 / stride 4 / padding 7 geometry (same results to fp32 rounding)
+_GENERIC = os.environ.get("KVAE_DISC_GENERIC", "0") == "1"
+
+
 def _conv_fwd(x, w, bias, Cin, Cout, K, stride, pad):
     """Conv1d on [N, Cin, T] fp32 with a folded weight [Cout, Cin, K]."""
     L = _lib.lib()
@@ -46,6 +53,10 @@ def _conv_fwd(x, w, bias, Cin, Cout, K, stride, pad):
     y = torch.empty((N, Cout, T_out), dtype=torch.float32, device=x.device)
     ns = L.kvae_conv1d_scratch_bytes(Cin, Cout, K)
     scratch = torch.empty(ns, dtype=torch.uint8, device=x.device)
+    if not _GENERIC and L.kvae_disc_conv15_supported(K, stride, pad):
+        _lib.check(L.kvae_disc_conv15_fwd(x.data_ptr(), y.data_ptr(), w.data_ptr(), _lib.ptr(bias), N, Cin, Cout, T,
+                                          scratch.data_ptr(), ns, _lib.stream_ptr(x.device)))
+        return y
     _lib.check(L.kvae_conv1d_fwd(x.data_ptr(), y.data_ptr(), w.data_ptr(), _lib.ptr(bias), 0, N, Cin, Cout, T, K, stride, 1,
                                  pad, _lib.KVAE_F32, scratch.data_ptr(), ns, _lib.stream_ptr(x.device)))
     return y
@@ -61,6 +72,10 @@ def _conv_bwd(x, gy, w, Cin, Cout, K, stride, pad, want_gx, want_dw, want_db):
         return None, None, None
     ns = L.kvae_conv1d_scratch_bytes(Cin, Cout, K)
     scratch = torch.empty(ns, dtype=torch.uint8, device=x.device)
+    if not _GENERIC and L.kvae_disc_conv15_supported(K, stride, pad):
+        _lib.check(L.kvae_disc_conv15_bwd(x.data_ptr(), gy.data_ptr(), w.data_ptr(), _lib.ptr(gx), _lib.ptr(dw), _lib.ptr(db),
+                                          N, Cin, Cout, T, scratch.data_ptr(), ns, _lib.stream_ptr(x.device)))
+        return gx, dw, db
     _lib.check(L.kvae_conv1d_bwd(x.data_ptr(), gy.data_ptr(), w.data_ptr(), _lib.ptr(gx), _lib.ptr(dw), _lib.ptr(db), 0, N,
                                  Cin, Cout, T, K, stride, 1, pad, _lib.KVAE_F32, scratch.data_ptr(), ns,
                                  _lib.stream_ptr(x.device)))

@@ -67,6 +67,15 @@ class FakeLib:
         self.calls.append(("conv_bwd", gx is not None, dw is not None))
         return 0
 
+    def kvae_disc_conv15_supported(self, K, stride, pad):
+        return int(K == 15 and stride == 4 and pad == 7)
+
+    def kvae_disc_conv15_fwd(self, x, y, w, bias, N, Cin, Cout, Tn, scratch, ns, st):
+        return self.kvae_conv1d_fwd(x, y, w, bias, 0, N, Cin, Cout, Tn, 15, 4, 1, 7, 0, scratch, ns, st)
+
+    def kvae_disc_conv15_bwd(self, x, gy, w, gx, dw, dbias, N, Cin, Cout, Tn, scratch, ns, st):
+        return self.kvae_conv1d_bwd(x, gy, w, gx, dw, dbias, 0, N, Cin, Cout, Tn, 15, 4, 1, 7, 0, scratch, ns, st)
+
     # ---- csrc/disc.cuh
     def kvae_disc_period_fold(self, x, y, N, Cc, Tn, n, backward, st):
         H = (Tn + n - 1) // n

@@ -140,11 +140,15 @@ def test_silu_score_hinge_feature_match():
         assert float((a - b).abs().max()) <= 1e-7 + 1e-5 * float(b.abs().max())
 
 
-@pytest.mark.parametrize("Cin,Cout,T", [(2, 32, 2999), (32, 64, 751), (96, 64, 70), (128, 256, 47), (256, 1, 12)])
-def test_strided_k15_conv_fwd_bwd(Cin, Cout, T):
-    """the discriminator's conv geometry (k = 15, stride 4, padding 7; k = 1 for the last layer) on the layer-level conv
-    kernels, forward and all three gradients, against torch"""
+@pytest.mark.parametrize("generic", [False, True])
+@pytest.mark.parametrize("Cin,Cout,T", [(2, 32, 2999), (32, 64, 751), (96, 64, 70), (128, 256, 47), (256, 1, 12),
+                                        (64, 128, 3001), (22, 96, 1030), (33, 65, 517), (128, 256, 1)])
+def test_strided_k15_conv_fwd_bwd(Cin, Cout, T, generic, monkeypatch):
+    """the discriminator's conv geometry (k = 15, stride 4, padding 7; k = 1 for the last layer) forward and all three
+    gradients against torch, on the kernels written for it (kvae_disc_conv15_*: full and ragged tiles in every dimension)
+    and on the generic layer-level conv kernels"""
     import kalle_audio_b200.discriminators as D
+    monkeypatch.setattr(D, "_GENERIC", generic)
     torch.manual_seed(Cin + T)
     K, s, p = (15, 4, 7) if Cout > 1 else (1, 1, 0)
     N = 3
@@ -163,6 +167,8 @@ def test_strided_k15_conv_fwd_bwd(Cin, Cout, T):
     assert float((db - dbw).abs().max()) <= 1e-4 * float(dbw.abs().max())
     gx2, dw2, db2 = D._conv_bwd(x.detach(), gy, w.detach(), Cin, Cout, K, s, p, True, False, False)
     assert dw2 is None and db2 is None and torch.equal(gx2, gx)
+    _, dw3, _ = D._conv_bwd(x.detach(), gy, w.detach(), Cin, Cout, K, s, p, False, True, False)
+    assert float((dw3 - dww).abs().max()) <= 1e-4 * float(dww.abs().max())
 
 
 @pytest.mark.parametrize("tag", ["stereo", "mono"])
