@@ -770,7 +770,7 @@ def measure_discriminator(args, dev):
         sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
         from oracle.reference_loader import load_reference_discriminators
         rd = load_reference_discriminators()
-        if rd is not None:
+        if rd is not None and os.environ.get("KVAE_DISC_NO_REF", "0") != "1":
             ref = rd.OobleckDiscriminator(in_channels=2)
             ref.load_state_dict(sd)
             mods.append(("reference_torch_eager", ref.to(dev)))
@@ -779,17 +779,19 @@ def measure_discriminator(args, dev):
     for name, mod in mods:
         res = {}
         for sname, fn in steps(mod):
-            for _ in range(2):
+            for _ in range(1 if args.steps < 4 else 2):
                 l = fn()
             torch.cuda.synchronize(dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.perf_counter()
             e0.record()
-            n = max(2, args.steps // 4)
+            n = max(1 if args.steps < 4 else 2, args.steps // 4)
             for _ in range(n):
                 l = fn()
             e1.record()
+            t1 = time.perf_counter()           # host time to ISSUE the steps (no synchronisation inside the loop)
             torch.cuda.synchronize(dev)
-            res[sname] = {"ms": e0.elapsed_time(e1) / n, "loss": float(l.detach())}
+            res[sname] = {"ms": e0.elapsed_time(e1) / n, "host_issue_ms": (t1 - t0) * 1e3 / n, "loss": float(l.detach())}
         out[name] = res
         del mod
         torch.cuda.empty_cache()

@@ -355,6 +355,12 @@ int kvae_disc_conv15_fwd(const float* x, float* y, const float* w, const float* 
                          void* scratch, size_t scratch_bytes, void* stream);
 int kvae_disc_conv15_bwd(const float* x, const float* gy, const float* w, float* gx, float* dw, float* dbias, int N, int Cin,
                          int Cout, long long T, void* scratch, size_t scratch_bytes, void* stream);
+/* The nets' last layer: Conv1d(k = 1) onto 1..8 channels (discriminators.py:104), x [N, Cin, T] fp32, w [Cout, Cin] */
+int kvae_disc_conv1x1_supported(int K, int stride, int pad, int Cout);
+int kvae_disc_conv1x1_fwd(const float* x, float* y, const float* w, const float* bias, int N, int Cin, int Cout, long long T,
+                          void* stream);
+int kvae_disc_conv1x1_bwd(const float* x, const float* gy, const float* w, float* gx, float* dw, float* dbias, int N, int Cin,
+                          int Cout, long long T, void* stream);
 #ifdef __cplusplus
 }
 #endif

@@ -152,6 +152,11 @@ SIGNATURES = {
                                        C.c_void_p, C.c_size_t, C.c_void_p]),
     "kvae_disc_conv15_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                        C.c_int, C.c_longlong, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "kvae_disc_conv1x1_supported": (C.c_int, [C.c_int] * 4),
+    "kvae_disc_conv1x1_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong,
+                                        C.c_void_p]),
+    "kvae_disc_conv1x1_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                        C.c_int, C.c_longlong, C.c_void_p]),
 }
 
 

@@ -284,61 +284,104 @@ disc_fm_bwd_kernel(const __grid_constant__ FmTable t, const float* __restrict__ 
 // 100: every conv of every net but the last 1 x 1) -- as three register-tiled fp32 kernels.  The generic layer kernels
 // (conv_direct_kernel / wgrad_direct_kernel) reach ~9 / ~4 TFLOP/s on this geometry in the API layout (one tap and 16
 // channels per barrier pair, 16-row stages in the weight gradient); here each thread keeps a register window of the
-// input that serves all 15 taps of several outputs, shared memory is read with 16-byte loads at >= 13 FMAs per load, and
-// the layouts are chosen so that those loads are bank-conflict free (see each kernel).
+// input that serves all 15 taps of several outputs, shared memory is read with 16-byte loads at >= 13 FMAs per load, the
+// layouts are chosen so that those loads are bank-conflict free (see each kernel), and the operand tiles of the next
+// channel chunk arrive through cp.async while the current one is multiplied (two stages; the first version filled one
+// stage between two barriers and was latency-bound: 320 us for a 256-channel layer whatever the grid size,
+// profiles/r02_disc_launches_conv15_v1_ncu.csv).
 // =====================================================================================================================
 constexpr int kDK = 15, kDS = 4, kDP = 7;
+
+__device__ __forceinline__ void cp_async4(float* dst, const float* src, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+  const int sz = valid ? 4 : 0;      // 0 source bytes: the destination is zero-filled, nothing is read
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
+  const uint32_t d = static_cast<uint32_t>(__cvta_generic_to_shared(dst));
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- forward: y[n, co, t] = bias[co] + sum_{ci, k} wp[k][ci][co] * x[n, ci, 4 t + k - 7]      (wp = pack_weights layout)
 // Block: 64 co x 128 t; 256 threads = 16 t-groups (8 consecutive t) x 16 co-groups (4 co); lane % 16 = t-group.
 // A thread's 8 outputs x 15 taps read the 43 consecutive inputs 32 tg + 4 j + k: one register window per input channel.
 // The slab row is stored in 32-float segments 36 floats apart, so the 8 lanes of a quarter warp (8 t-groups) hit 32
 // different banks with their 16-byte loads; lanes of different co-groups read the same slab address (broadcast).
-constexpr int kCfTt = 128, kCfCo = 64, kCfKc = 4;
+constexpr int kCfTt = 128, kCfCo = 64, kCfKc = 8;
 constexpr int kCfSeg = 36;
 constexpr int kCfSlab = 16 * 32 + 12;           // slab entries per channel: j = 0 .. 523
 constexpr int kCfRow = kCfSeg * 16 + 12;        // 588 floats
+constexpr int kCfXs = kCfKc * kCfRow, kCfWs = kCfKc * kDK * kCfCo;
+constexpr int kCfStage = kCfXs + kCfWs;         // floats per pipeline stage
+constexpr size_t kCfSmem = 2 * static_cast<size_t>(kCfStage) * sizeof(float);
 
 __global__ void __launch_bounds__(256, 2)
 disc_conv15_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wp, const float* __restrict__ bias,
                        float* __restrict__ y, int Cin, int Cout, int T, int To) {
-  __shared__ __align__(16) float xs[kCfKc][kCfRow];
-  __shared__ __align__(16) float ws[kCfKc][kDK][kCfCo];
+  extern __shared__ __align__(16) float disc_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tg = lane & 15, cg = warp * 2 + (lane >> 4);
   const int tb0 = blockIdx.x * kCfTt, co0 = blockIdx.y * kCfCo, n = blockIdx.z;
   const long long u0 = static_cast<long long>(kDS) * tb0 - kDP;      // input index of slab entry 0
   const float* xn = x + static_cast<size_t>(n) * Cin * T;
+  const bool w16 = (Cout & 3) == 0;
   float acc[4][8];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-  for (int c0 = 0; c0 < Cin; c0 += kCfKc) {
+
+  auto load = [&](int c0, int stage) {
+    float* xs = disc_smem + stage * kCfStage;
+    float* ws = xs + kCfXs;
     const int nci = min(kCfKc, Cin - c0);
-    __syncthreads();
     for (int idx = tid; idx < nci * kCfSlab; idx += 256) {
       const int ci = idx / kCfSlab, j = idx - ci * kCfSlab;
       const long long u = u0 + j;
-      float v = 0.f;
-      if (u >= 0 && u < T) v = xn[static_cast<size_t>(c0 + ci) * T + u];
-      xs[ci][kCfSeg * (j >> 5) + (j & 31)] = v;
+      const bool ok = u >= 0 && u < T;
+      cp_async4(xs + ci * kCfRow + kCfSeg * (j >> 5) + (j & 31), ok ? xn + static_cast<size_t>(c0 + ci) * T + u : xn, ok);
     }
-    for (int idx = tid; idx < nci * kDK * kCfCo; idx += 256) {
-      const int co = idx & (kCfCo - 1), r = idx >> 6;
-      const int k = r % kDK, ci = r / kDK;
-      ws[ci][k][co] = (co0 + co < Cout) ? wp[(static_cast<size_t>(k) * Cin + c0 + ci) * Cout + co0 + co] : 0.f;
+    if (w16) {
+      for (int idx = tid; idx < nci * kDK * (kCfCo / 4); idx += 256) {
+        const int co = (idx & 15) * 4, r = idx >> 4;        // r = ci * 15 + k
+        const int k = r % kDK, ci = r / kDK;
+        const bool ok = co0 + co < Cout;
+        cp_async16(ws + r * kCfCo + co, ok ? wp + (static_cast<size_t>(k) * Cin + c0 + ci) * Cout + co0 + co : wp, ok);
+      }
+    } else {
+      for (int idx = tid; idx < nci * kDK * kCfCo; idx += 256) {
+        const int co = idx & (kCfCo - 1), r = idx >> 6;
+        const int k = r % kDK, ci = r / kDK;
+        const bool ok = co0 + co < Cout;
+        cp_async4(ws + r * kCfCo + co, ok ? wp + (static_cast<size_t>(k) * Cin + c0 + ci) * Cout + co0 + co : wp, ok);
+      }
     }
+  };
+
+  const int n_chunks = (Cin + kCfKc - 1) / kCfKc;
+  load(0, 0);
+  cp_async_commit();
+  for (int c = 0; c < n_chunks; ++c) {
+    if (c + 1 < n_chunks) load((c + 1) * kCfKc, (c + 1) & 1);
+    cp_async_commit();
+    cp_async_wait<1>();          // everything but the newest group has landed: chunk c
     __syncthreads();
+    const float* xs = disc_smem + (c & 1) * kCfStage;
+    const float* ws = xs + kCfXs;
+    const int nci = min(kCfKc, Cin - c * kCfKc);
     for (int ci = 0; ci < nci; ++ci) {
       float xw[44];
-      const float4* seg = reinterpret_cast<const float4*>(&xs[ci][kCfSeg * tg]);
+      const float4* seg = reinterpret_cast<const float4*>(xs + ci * kCfRow + kCfSeg * tg);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const float4 v = seg[q];
         xw[4 * q] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w;
       }
-      const float4* nxt = reinterpret_cast<const float4*>(&xs[ci][kCfSeg * (tg + 1)]);
+      const float4* nxt = reinterpret_cast<const float4*>(xs + ci * kCfRow + kCfSeg * (tg + 1));
 #pragma unroll
       for (int q = 0; q < 3; ++q) {
         const float4 v = nxt[q];
@@ -346,7 +389,7 @@ disc_conv15_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wp
       }
 #pragma unroll
       for (int k = 0; k < kDK; ++k) {
-        const float4 w4 = *reinterpret_cast<const float4*>(&ws[ci][k][4 * cg]);
+        const float4 w4 = *reinterpret_cast<const float4*>(ws + (ci * kDK + k) * kCfCo + 4 * cg);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float xv = xw[4 * j + k];
@@ -357,6 +400,7 @@ disc_conv15_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wp
         }
       }
     }
+    __syncthreads();             // this stage is overwritten by the load issued in the next iteration
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -376,48 +420,76 @@ disc_conv15_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wp
 // (wT = pack_weights layout of the weight read as a ConvTranspose1d weight).  Block: 64 ci x 256 v; 256 threads = 16
 // v-groups (16 consecutive v = 4 q x 4 phases) x 16 ci-groups (4 ci).  Per output channel a thread loads the 8 gradients
 // gy[q0 - 4 .. q0 + 3] (two 16-byte loads, consecutive lanes consecutive addresses) and, per tap, 4 weights.
-constexpr int kDgV = 256, kDgCi = 64, kDgKc = 4;
+constexpr int kDgV = 256, kDgCi = 64, kDgKc = 8;
 constexpr int kDgRow = 72;
+constexpr int kDgGs = kDgKc * kDgRow, kDgWs = kDgKc * kDK * kDgCi;
+constexpr int kDgStage = kDgGs + kDgWs;
+constexpr size_t kDgSmem = 2 * static_cast<size_t>(kDgStage) * sizeof(float);
 
 __global__ void __launch_bounds__(256, 2)
 disc_conv15_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__ wT, float* __restrict__ gx, int Cin,
                          int Cout, int T, int To) {
-  __shared__ __align__(16) float gs[kDgKc][kDgRow];
-  __shared__ __align__(16) float ws[kDgKc][kDK][kDgCi];
+  extern __shared__ __align__(16) float disc_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int vg = lane & 15, cig = warp * 2 + (lane >> 4);
   const int vb0 = blockIdx.x * kDgV, ci0 = blockIdx.y * kDgCi, n = blockIdx.z;
   const int qb0 = vb0 / kDS;
   const float* gn = gy + static_cast<size_t>(n) * Cout * To;
+  const bool w16 = (Cin & 3) == 0;
   float acc[4][16];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
-  for (int c0 = 0; c0 < Cout; c0 += kDgKc) {
+
+  auto load = [&](int c0, int stage) {
+    float* gs = disc_smem + stage * kDgStage;
+    float* ws = gs + kDgGs;
     const int nco = min(kDgKc, Cout - c0);
-    __syncthreads();
     for (int idx = tid; idx < nco * 68; idx += 256) {
       const int co = idx / 68, i = idx - co * 68;
       const int t = qb0 - 4 + i;
-      gs[co][i] = (t >= 0 && t < To) ? gn[static_cast<size_t>(c0 + co) * To + t] : 0.f;
+      const bool ok = t >= 0 && t < To;
+      cp_async4(gs + co * kDgRow + i, ok ? gn + static_cast<size_t>(c0 + co) * To + t : gn, ok);
     }
-    for (int idx = tid; idx < nco * kDK * kDgCi; idx += 256) {
-      const int ci = idx & (kDgCi - 1), r = idx >> 6;
-      const int k = r % kDK, co = r / kDK;
-      ws[co][k][ci] = (ci0 + ci < Cin) ? wT[(static_cast<size_t>(k) * Cout + c0 + co) * Cin + ci0 + ci] : 0.f;
+    if (w16) {
+      for (int idx = tid; idx < nco * kDK * (kDgCi / 4); idx += 256) {
+        const int ci = (idx & 15) * 4, r = idx >> 4;        // r = co * 15 + k
+        const int k = r % kDK, co = r / kDK;
+        const bool ok = ci0 + ci < Cin;
+        cp_async16(ws + r * kDgCi + ci, ok ? wT + (static_cast<size_t>(k) * Cout + c0 + co) * Cin + ci0 + ci : wT, ok);
+      }
+    } else {
+      for (int idx = tid; idx < nco * kDK * kDgCi; idx += 256) {
+        const int ci = idx & (kDgCi - 1), r = idx >> 6;
+        const int k = r % kDK, co = r / kDK;
+        const bool ok = ci0 + ci < Cin;
+        cp_async4(ws + r * kDgCi + ci, ok ? wT + (static_cast<size_t>(k) * Cout + c0 + co) * Cin + ci0 + ci : wT, ok);
+      }
     }
+  };
+
+  const int n_chunks = (Cout + kDgKc - 1) / kDgKc;
+  load(0, 0);
+  cp_async_commit();
+  for (int c = 0; c < n_chunks; ++c) {
+    if (c + 1 < n_chunks) load((c + 1) * kDgKc, (c + 1) & 1);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
+    const float* gs = disc_smem + (c & 1) * kDgStage;
+    const float* ws = gs + kDgGs;
+    const int nco = min(kDgKc, Cout - c * kDgKc);
     for (int co = 0; co < nco; ++co) {
       float gw[8];
       {
-        const float4 a = *reinterpret_cast<const float4*>(&gs[co][4 * vg]);
-        const float4 b = *reinterpret_cast<const float4*>(&gs[co][4 * vg + 4]);
+        const float4 a = *reinterpret_cast<const float4*>(gs + co * kDgRow + 4 * vg);
+        const float4 b = *reinterpret_cast<const float4*>(gs + co * kDgRow + 4 * vg + 4);
         gw[0] = a.x; gw[1] = a.y; gw[2] = a.z; gw[3] = a.w; gw[4] = b.x; gw[5] = b.y; gw[6] = b.z; gw[7] = b.w;
       }
 #pragma unroll
       for (int k = 0; k < kDK; ++k) {
-        const float4 w4 = *reinterpret_cast<const float4*>(&ws[co][k][4 * cig]);
+        const float4 w4 = *reinterpret_cast<const float4*>(ws + (co * kDK + k) * kDgCi + 4 * cig);
         const int phi = k & 3, m = k >> 2;
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {
@@ -429,6 +501,7 @@ disc_conv15_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__
         }
       }
     }
+    __syncthreads();
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -451,12 +524,14 @@ disc_conv15_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__
 constexpr int kWgTc = 64, kWgCo = 64, kWgCi = 16;
 constexpr int kWgXRow = 276, kWgXUsed = kDS * kWgTc + 12;   // 268 slab entries per channel
 constexpr int kWgGRow = 68;
+constexpr int kWgGs = kWgCo * kWgGRow, kWgXs = kWgCi * kWgXRow;
+constexpr int kWgStage = kWgGs + kWgXs;
+constexpr size_t kWgSmem = 2 * static_cast<size_t>(kWgStage) * sizeof(float);
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 disc_conv15_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ gy, float* __restrict__ dw, int Cin,
                          int Cout, int T, int To, int n_items) {
-  __shared__ __align__(16) float gs[kWgCo][kWgGRow];
-  __shared__ __align__(16) float xs[kWgCi][kWgXRow];
+  extern __shared__ __align__(16) float disc_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int cil = lane & 15, cg = warp * 2 + (lane >> 4);
   const int n_ci_tiles = (Cin + kWgCi - 1) / kWgCi;
@@ -467,33 +542,48 @@ disc_conv15_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ 
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int k = 0; k < kDK; ++k) acc[i][k] = 0.f;
-  for (int item = blockIdx.y; item < n_items; item += gridDim.y) {
+
+  auto load = [&](int item, int stage) {
+    float* gs = disc_smem + stage * kWgStage;
+    float* xs = gs + kWgGs;
     const int n = item / tiles_t, t0 = (item - n * tiles_t) * kWgTc;
-    __syncthreads();
     for (int idx = tid; idx < kWgCo * kWgTc; idx += 256) {
       const int row = idx >> 6, col = idx & 63;
       const int co = co0 + row, t = t0 + col;
-      gs[row][col] = (co < Cout && t < To) ? gy[(static_cast<size_t>(n) * Cout + co) * To + t] : 0.f;
+      const bool ok = co < Cout && t < To;
+      cp_async4(gs + row * kWgGRow + col, ok ? gy + (static_cast<size_t>(n) * Cout + co) * To + t : gy, ok);
     }
     const long long u0 = static_cast<long long>(kDS) * t0 - kDP;
     for (int idx = tid; idx < kWgCi * kWgXUsed; idx += 256) {
       const int ci = idx / kWgXUsed, j = idx - ci * kWgXUsed;
       const long long u = u0 + j;
       const int c = ci0 + ci;
-      xs[ci][j] = (c < Cin && u >= 0 && u < T) ? x[(static_cast<size_t>(n) * Cin + c) * T + u] : 0.f;
+      const bool ok = c < Cin && u >= 0 && u < T;
+      cp_async4(xs + ci * kWgXRow + j, ok ? x + (static_cast<size_t>(n) * Cin + c) * T + u : x, ok);
     }
+  };
+
+  int item = blockIdx.y, stage = 0;
+  if (item < n_items) load(item, 0);
+  cp_async_commit();
+  for (; item < n_items; item += gridDim.y, stage ^= 1) {
+    if (item + static_cast<int>(gridDim.y) < n_items) load(item + gridDim.y, stage ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
     __syncthreads();
+    const float* gs = disc_smem + stage * kWgStage;
+    const float* xs = gs + kWgGs;
 #pragma unroll 1
     for (int tau0 = 0; tau0 < kWgTc; tau0 += 4) {
       float g[4][4], xw[28];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float4 v = *reinterpret_cast<const float4*>(&gs[4 * cg + i][tau0]);
+        const float4 v = *reinterpret_cast<const float4*>(gs + (4 * cg + i) * kWgGRow + tau0);
         g[i][0] = v.x; g[i][1] = v.y; g[i][2] = v.z; g[i][3] = v.w;
       }
 #pragma unroll
       for (int q = 0; q < 7; ++q) {
-        const float4 v = *reinterpret_cast<const float4*>(&xs[cil][kDS * tau0 + 4 * q]);
+        const float4 v = *reinterpret_cast<const float4*>(xs + cil * kWgXRow + kDS * tau0 + 4 * q);
         xw[4 * q] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w;
       }
 #pragma unroll
@@ -505,6 +595,7 @@ disc_conv15_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ 
           for (int i = 0; i < 4; ++i) acc[i][k] = fmaf(g[i][tt], xv, acc[i][k]);
         }
     }
+    __syncthreads();
   }
   const int c = ci0 + cil;
   if (c < Cin) {
@@ -517,6 +608,67 @@ disc_conv15_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ 
       for (int k = 0; k < kDK; ++k) atomicAdd(d + k, acc[i][k]);
     }
   }
+}
+
+// ---- the nets' last layer: a 1 x 1 convolution onto a few channels (256 -> 1 per folded column).  Pure streaming:
+// forward  y[n, co, t] = b[co] + sum_ci w[co][ci] a[n, ci, t]  (one thread per (n, t), channels walked with coalesced loads),
+// data gradient  ga[n, ci, t] = sum_co w[co][ci] gy[n, co, t],  weight gradient  dw[co][ci] = sum_{n, t} gy[n, co, t] a[n, ci, t].
+constexpr int kC1MaxCo = 8;
+
+__global__ void __launch_bounds__(kDiscThreads)
+disc_conv1x1_fwd_kernel(const float* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
+                        float* __restrict__ y, int Cin, int Cout, long long T) {
+  const long long t = blockIdx.x * static_cast<long long>(kDiscThreads) + threadIdx.x;
+  const int n = blockIdx.y;
+  if (t >= T) return;
+  float acc[kC1MaxCo];
+#pragma unroll
+  for (int co = 0; co < kC1MaxCo; ++co) acc[co] = (bias && co < Cout) ? bias[co] : 0.f;
+  const float* an = a + static_cast<size_t>(n) * Cin * T + t;
+  for (int ci = 0; ci < Cin; ++ci) {
+    const float v = an[static_cast<size_t>(ci) * T];
+#pragma unroll
+    for (int co = 0; co < kC1MaxCo; ++co)
+      if (co < Cout) acc[co] = fmaf(w[co * Cin + ci], v, acc[co]);
+  }
+#pragma unroll
+  for (int co = 0; co < kC1MaxCo; ++co)
+    if (co < Cout) y[(static_cast<size_t>(n) * Cout + co) * T + t] = acc[co];
+}
+
+__global__ void __launch_bounds__(kDiscThreads)
+disc_conv1x1_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__ w, float* __restrict__ ga, int Cin,
+                          int Cout, long long T) {
+  const long long t = blockIdx.x * static_cast<long long>(kDiscThreads) + threadIdx.x;
+  const int n = blockIdx.y;
+  if (t >= T) return;
+  float g[kC1MaxCo];
+#pragma unroll
+  for (int co = 0; co < kC1MaxCo; ++co) g[co] = co < Cout ? gy[(static_cast<size_t>(n) * Cout + co) * T + t] : 0.f;
+  float* gn = ga + static_cast<size_t>(n) * Cin * T + t;
+  for (int ci = 0; ci < Cin; ++ci) {
+    float v = 0.f;
+#pragma unroll
+    for (int co = 0; co < kC1MaxCo; ++co)
+      if (co < Cout) v = fmaf(w[co * Cin + ci], g[co], v);
+    gn[static_cast<size_t>(ci) * T] = v;
+  }
+}
+
+// one block per (ci, co): dw[co][ci] = sum over (n, t)
+__global__ void __launch_bounds__(kDiscThreads)
+disc_conv1x1_wgrad_kernel(const float* __restrict__ a, const float* __restrict__ gy, float* __restrict__ dw, int N, int Cin,
+                          int Cout, long long T) {
+  __shared__ float red[8];
+  const int ci = blockIdx.x, co = blockIdx.y;
+  float s = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float* ar = a + (static_cast<size_t>(n) * Cin + ci) * T;
+    const float* gr = gy + (static_cast<size_t>(n) * Cout + co) * T;
+    for (long long t = threadIdx.x; t < T; t += kDiscThreads) s = fmaf(ar[t], gr[t], s);
+  }
+  s = block_sum_256(s, red);
+  if (threadIdx.x == 0) dw[co * Cin + ci] = s;
 }
 
 }  // namespace kvae

@@ -2764,7 +2764,8 @@ int kvae_disc_conv15_fwd(const float* x, float* y, const float* w, const float* 
   pack_weights_kernel<<<static_cast<int>(std::min<size_t>((n + 255) / 256, 4096)), 256, 0, st>>>(w, 0, Cout, Cin, kDK, nullptr, wp);
   KV_CUDA(cudaGetLastError());
   dim3 grid(ceil_div(To, kCfTt), ceil_div(Cout, kCfCo), N);
-  disc_conv15_fwd_kernel<<<grid, 256, 0, st>>>(x, wp, bias, y, Cin, Cout, static_cast<int>(T), To);
+  KV_CUDA(cudaFuncSetAttribute(disc_conv15_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCfSmem)));
+  disc_conv15_fwd_kernel<<<grid, 256, kCfSmem, st>>>(x, wp, bias, y, Cin, Cout, static_cast<int>(T), To);
   KV_CUDA(cudaGetLastError());
   g_launches += 2;
   return 0;
@@ -2788,8 +2789,9 @@ int kvae_disc_conv15_bwd(const float* x, const float* gy, const float* w, float*
     const long long items = static_cast<long long>(N) * ceil_div(To, kWgTc);
     const int nsplit = static_cast<int>(std::max<long long>(1, std::min<long long>(std::min<long long>(items, 65535),
                                                                                    (6ll * sm_count() + tiles - 1) / tiles)));
-    disc_conv15_wgrad_kernel<<<dim3(tiles, nsplit), 256, 0, st>>>(x, gy, dw, Cin, Cout, static_cast<int>(T), To,
-                                                                  static_cast<int>(items));
+    KV_CUDA(cudaFuncSetAttribute(disc_conv15_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWgSmem)));
+    disc_conv15_wgrad_kernel<<<dim3(tiles, nsplit), 256, kWgSmem, st>>>(x, gy, dw, Cin, Cout, static_cast<int>(T), To,
+                                                                        static_cast<int>(items));
     KV_CUDA(cudaGetLastError());
     ++g_launches;
   }
@@ -2806,9 +2808,57 @@ int kvae_disc_conv15_bwd(const float* x, const float* gy, const float* w, float*
   pack_weights_kernel<<<static_cast<int>(std::min<size_t>((n + 255) / 256, 4096)), 256, 0, st>>>(w, 1, Cin, Cout, kDK, nullptr, wT);
   KV_CUDA(cudaGetLastError());
   dim3 grid(ceil_div(static_cast<int>(T) + kDP, kDgV), ceil_div(Cin, kDgCi), N);
-  disc_conv15_dgrad_kernel<<<grid, 256, 0, st>>>(gy, wT, gx, Cin, Cout, static_cast<int>(T), To);
+  KV_CUDA(cudaFuncSetAttribute(disc_conv15_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kDgSmem)));
+  disc_conv15_dgrad_kernel<<<grid, 256, kDgSmem, st>>>(gy, wT, gx, Cin, Cout, static_cast<int>(T), To);
   KV_CUDA(cudaGetLastError());
   g_launches += 2;
+  return 0;
+}
+
+// ---- the nets' last layer (1 x 1 conv onto <= 8 channels): streaming kernels of disc.cuh
+int kvae_disc_conv1x1_supported(int K, int stride, int pad, int Cout) {
+  return K == 1 && stride == 1 && pad == 0 && Cout >= 1 && Cout <= kC1MaxCo;
+}
+
+int kvae_disc_conv1x1_fwd(const float* x, float* y, const float* w, const float* bias, int N, int Cin, int Cout, long long T,
+                          void* stream) {
+  if (!x || !y || !w) return fail("null argument");
+  if (N <= 0 || Cin <= 0 || T <= 0) return fail("empty input");
+  if (Cout < 1 || Cout > kC1MaxCo || N > 65535) return fail("disc 1x1 conv: 1..8 output channels, batch <= 65535");
+  DeviceGuard guard(device_of(x));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  dim3 grid(static_cast<unsigned>((T + kDiscThreads - 1) / kDiscThreads), N);
+  disc_conv1x1_fwd_kernel<<<grid, kDiscThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, Cin, Cout, T);
+  KV_CUDA(cudaGetLastError());
+  ++g_launches;
+  return 0;
+}
+
+int kvae_disc_conv1x1_bwd(const float* x, const float* gy, const float* w, float* gx, float* dw, float* dbias, int N, int Cin,
+                          int Cout, long long T, void* stream) {
+  if (!x || !gy || !w) return fail("null argument");
+  if (!dw && !gx && !dbias) return fail("nothing to compute (dw, dbias and gx are all null)");
+  if (N <= 0 || Cin <= 0 || T <= 0) return fail("empty input");
+  if (Cout < 1 || Cout > kC1MaxCo || N > 65535 || Cin > 65535) return fail("disc 1x1 conv: 1..8 output channels, batch and channels <= 65535");
+  DeviceGuard guard(device_of(x));
+  if (!guard.ok) return fail("cannot select the tensor's device");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dw) {
+    disc_conv1x1_wgrad_kernel<<<dim3(Cin, Cout), kDiscThreads, 0, st>>>(x, gy, dw, N, Cin, Cout, T);
+    KV_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
+  if (dbias) {
+    bias_grad_cf_kernel<<<Cout, 256, 0, st>>>(gy, 1, dbias, N, Cout, T);
+    KV_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
+  if (gx) {
+    dim3 grid(static_cast<unsigned>((T + kDiscThreads - 1) / kDiscThreads), N);
+    disc_conv1x1_dgrad_kernel<<<grid, kDiscThreads, 0, st>>>(gy, w, gx, Cin, Cout, T);
+    KV_CUDA(cudaGetLastError());
+    ++g_launches;
+  }
   return 0;
 }
 

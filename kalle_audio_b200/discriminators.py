@@ -51,6 +51,10 @@ def _conv_fwd(x, w, bias, Cin, Cout, K, stride, pad):
     if T_out <= 0:
         raise RuntimeError("Kernel size can't be greater than actual input size")
     y = torch.empty((N, Cout, T_out), dtype=torch.float32, device=x.device)
+    if not _GENERIC and L.kvae_disc_conv1x1_supported(K, stride, pad, Cout):
+        _lib.check(L.kvae_disc_conv1x1_fwd(x.data_ptr(), y.data_ptr(), w.data_ptr(), _lib.ptr(bias), N, Cin, Cout, T,
+                                           _lib.stream_ptr(x.device)))
+        return y
     ns = L.kvae_conv1d_scratch_bytes(Cin, Cout, K)
     scratch = torch.empty(ns, dtype=torch.uint8, device=x.device)
     if not _GENERIC and L.kvae_disc_conv15_supported(K, stride, pad):
@@ -70,6 +74,10 @@ def _conv_bwd(x, gy, w, Cin, Cout, K, stride, pad, want_gx, want_dw, want_db):
     db = torch.empty(Cout, dtype=torch.float32, device=x.device) if want_db else None
     if gx is None and dw is None and db is None:
         return None, None, None
+    if not _GENERIC and L.kvae_disc_conv1x1_supported(K, stride, pad, Cout):
+        _lib.check(L.kvae_disc_conv1x1_bwd(x.data_ptr(), gy.data_ptr(), w.data_ptr(), _lib.ptr(gx), _lib.ptr(dw), _lib.ptr(db),
+                                           N, Cin, Cout, T, _lib.stream_ptr(x.device)))
+        return gx, dw, db
     ns = L.kvae_conv1d_scratch_bytes(Cin, Cout, K)
     scratch = torch.empty(ns, dtype=torch.uint8, device=x.device)
     if not _GENERIC and L.kvae_disc_conv15_supported(K, stride, pad):

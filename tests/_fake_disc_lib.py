@@ -76,6 +76,15 @@ class FakeLib:
     def kvae_disc_conv15_bwd(self, x, gy, w, gx, dw, dbias, N, Cin, Cout, Tn, scratch, ns, st):
         return self.kvae_conv1d_bwd(x, gy, w, gx, dw, dbias, 0, N, Cin, Cout, Tn, 15, 4, 1, 7, 0, scratch, ns, st)
 
+    def kvae_disc_conv1x1_supported(self, K, stride, pad, Cout):
+        return int(K == 1 and stride == 1 and pad == 0 and 1 <= Cout <= 8)
+
+    def kvae_disc_conv1x1_fwd(self, x, y, w, bias, N, Cin, Cout, Tn, st):
+        return self.kvae_conv1d_fwd(x, y, w, bias, 0, N, Cin, Cout, Tn, 1, 1, 1, 0, 0, None, 0, st)
+
+    def kvae_disc_conv1x1_bwd(self, x, gy, w, gx, dw, dbias, N, Cin, Cout, Tn, st):
+        return self.kvae_conv1d_bwd(x, gy, w, gx, dw, dbias, 0, N, Cin, Cout, Tn, 1, 1, 1, 0, 0, None, 0, st)
+
     # ---- csrc/disc.cuh
     def kvae_disc_period_fold(self, x, y, N, Cc, Tn, n, backward, st):
         H = (Tn + n - 1) // n

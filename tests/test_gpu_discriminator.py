@@ -171,6 +171,25 @@ def test_strided_k15_conv_fwd_bwd(Cin, Cout, T, generic, monkeypatch):
     assert float((dw3 - dww).abs().max()) <= 1e-4 * float(dww.abs().max())
 
 
+def test_conv1x1_small_cout():
+    """the nets' last layer on its streaming kernels with more than one output channel (a folded width > 1)"""
+    import kalle_audio_b200.discriminators as D
+    torch.manual_seed(9)
+    N, Cin, Cout, T = 3, 70, 3, 517
+    x = torch.randn(N, Cin, T, device=DEV, requires_grad=True)
+    w = (torch.randn(Cout, Cin, 1, device=DEV) / Cin ** 0.5).requires_grad_(True)
+    b = torch.randn(Cout, device=DEV, requires_grad=True)
+    y = D._conv_fwd(x.detach(), w.detach(), b.detach(), Cin, Cout, 1, 1, 0)
+    want = F.conv1d(x, w, b)
+    assert float((y - want.detach()).abs().max()) <= 1e-5 * float(want.abs().max())
+    gy = torch.randn_like(y)
+    gx, dw, db = D._conv_bwd(x.detach(), gy, w.detach(), Cin, Cout, 1, 1, 0, True, True, True)
+    gxw, dww, dbw = torch.autograd.grad(want, (x, w, b), gy)
+    assert float((gx - gxw).abs().max()) <= 2e-5 * float(gxw.abs().max())
+    assert float((dw - dww).abs().max()) <= 1e-4 * float(dww.abs().max())
+    assert float((db - dbw).abs().max()) <= 1e-4 * float(dbw.abs().max())
+
+
 @pytest.mark.parametrize("tag", ["stereo", "mono"])
 def test_discriminator_vs_reference(tag):
     """OobleckDiscriminator at the reference's random init: loss values, summed scores, every feature tensor's shape and
