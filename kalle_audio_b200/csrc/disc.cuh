@@ -311,39 +311,45 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // A thread's 8 outputs x 15 taps read the 43 consecutive inputs 32 tg + 4 j + k: one register window per input channel.
 // The slab row is stored in 32-float segments 36 floats apart, so the 8 lanes of a quarter warp (8 t-groups) hit 32
 // different banks with their 16-byte loads; lanes of different co-groups read the same slab address (broadcast).
-constexpr int kCfTt = 128, kCfCo = 64, kCfKc = 8;
-constexpr int kCfSeg = 36;
-constexpr int kCfSlab = 16 * 32 + 12;           // slab entries per channel: j = 0 .. 523
-constexpr int kCfRow = kCfSeg * 16 + 12;        // 588 floats
-constexpr int kCfXs = kCfKc * kCfRow, kCfWs = kCfKc * kDK * kCfCo;
-constexpr int kCfStage = kCfXs + kCfWs;         // floats per pipeline stage
-constexpr size_t kCfSmem = 2 * static_cast<size_t>(kCfStage) * sizeof(float);
+constexpr int kCfCo = 64, kCfKc = 8;
+template <int TT>
+struct CfGeom {
+  static constexpr int BT = 16 * TT;                                   // outputs t per block
+  static constexpr int SLAB = 4 * BT + 12;                             // slab entries per channel
+  static constexpr int ROW = ((SLAB - 1) + 4 * ((SLAB - 1) >> 5) + 4) & ~3;   // 4 floats of padding after every 32
+  static constexpr int XS = kCfKc * ROW, WS = kCfKc * kDK * kCfCo;
+  static constexpr int STAGE = XS + WS;                                // floats per pipeline stage
+  static constexpr size_t SMEM = 2 * static_cast<size_t>(STAGE) * sizeof(float);
+};
 
+// TT = outputs per thread: 8 (128 per block) for long layers; 2 (32 per block) when the long tiles would leave SMs idle
+template <int TT>
 __global__ void __launch_bounds__(256, 2)
 disc_conv15_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wp, const float* __restrict__ bias,
                        float* __restrict__ y, int Cin, int Cout, int T, int To) {
+  using G = CfGeom<TT>;
   extern __shared__ __align__(16) float disc_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tg = lane & 15, cg = warp * 2 + (lane >> 4);
-  const int tb0 = blockIdx.x * kCfTt, co0 = blockIdx.y * kCfCo, n = blockIdx.z;
+  const int tb0 = blockIdx.x * G::BT, co0 = blockIdx.y * kCfCo, n = blockIdx.z;
   const long long u0 = static_cast<long long>(kDS) * tb0 - kDP;      // input index of slab entry 0
   const float* xn = x + static_cast<size_t>(n) * Cin * T;
   const bool w16 = (Cout & 3) == 0;
-  float acc[4][8];
+  float acc[4][TT];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < TT; ++j) acc[i][j] = 0.f;
 
   auto load = [&](int c0, int stage) {
-    float* xs = disc_smem + stage * kCfStage;
-    float* ws = xs + kCfXs;
+    float* xs = disc_smem + stage * G::STAGE;
+    float* ws = xs + G::XS;
     const int nci = min(kCfKc, Cin - c0);
-    for (int idx = tid; idx < nci * kCfSlab; idx += 256) {
-      const int ci = idx / kCfSlab, j = idx - ci * kCfSlab;
+    for (int idx = tid; idx < nci * G::SLAB; idx += 256) {
+      const int ci = idx / G::SLAB, j = idx - ci * G::SLAB;
       const long long u = u0 + j;
       const bool ok = u >= 0 && u < T;
-      cp_async4(xs + ci * kCfRow + kCfSeg * (j >> 5) + (j & 31), ok ? xn + static_cast<size_t>(c0 + ci) * T + u : xn, ok);
+      cp_async4(xs + ci * G::ROW + j + 4 * (j >> 5), ok ? xn + static_cast<size_t>(c0 + ci) * T + u : xn, ok);
     }
     if (w16) {
       for (int idx = tid; idx < nci * kDK * (kCfCo / 4); idx += 256) {
@@ -370,28 +376,22 @@ disc_conv15_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wp
     cp_async_commit();
     cp_async_wait<1>();          // everything but the newest group has landed: chunk c
     __syncthreads();
-    const float* xs = disc_smem + (c & 1) * kCfStage;
-    const float* ws = xs + kCfXs;
+    const float* xs = disc_smem + (c & 1) * G::STAGE;
+    const float* ws = xs + G::XS;
     const int nci = min(kCfKc, Cin - c * kCfKc);
     for (int ci = 0; ci < nci; ++ci) {
-      float xw[44];
-      const float4* seg = reinterpret_cast<const float4*>(xs + ci * kCfRow + kCfSeg * tg);
+      float xw[4 * TT + 12];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        const float4 v = seg[q];
+      for (int q = 0; q < TT + 3; ++q) {
+        const int jj = 4 * TT * tg + 4 * q;
+        const float4 v = *reinterpret_cast<const float4*>(xs + ci * G::ROW + jj + 4 * (jj >> 5));
         xw[4 * q] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w;
-      }
-      const float4* nxt = reinterpret_cast<const float4*>(xs + ci * kCfRow + kCfSeg * (tg + 1));
-#pragma unroll
-      for (int q = 0; q < 3; ++q) {
-        const float4 v = nxt[q];
-        xw[32 + 4 * q] = v.x; xw[33 + 4 * q] = v.y; xw[34 + 4 * q] = v.z; xw[35 + 4 * q] = v.w;
       }
 #pragma unroll
       for (int k = 0; k < kDK; ++k) {
         const float4 w4 = *reinterpret_cast<const float4*>(ws + (ci * kDK + k) * kCfCo + 4 * cg);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < TT; ++j) {
           const float xv = xw[4 * j + k];
           acc[0][j] = fmaf(w4.x, xv, acc[0][j]);
           acc[1][j] = fmaf(w4.y, xv, acc[1][j]);
@@ -409,8 +409,8 @@ disc_conv15_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wp
     const float b = bias ? bias[co] : 0.f;
     float* yr = y + (static_cast<size_t>(n) * Cout + co) * To;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int t = tb0 + 8 * tg + j;
+    for (int j = 0; j < TT; ++j) {
+      const int t = tb0 + TT * tg + j;
       if (t < To) yr[t] = acc[i][j] + b;
     }
   }
@@ -420,51 +420,59 @@ disc_conv15_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wp
 // (wT = pack_weights layout of the weight read as a ConvTranspose1d weight).  Block: 64 ci x 256 v; 256 threads = 16
 // v-groups (16 consecutive v = 4 q x 4 phases) x 16 ci-groups (4 ci).  Per output channel a thread loads the 8 gradients
 // gy[q0 - 4 .. q0 + 3] (two 16-byte loads, consecutive lanes consecutive addresses) and, per tap, 4 weights.
-constexpr int kDgV = 256, kDgCi = 64, kDgKc = 8;
-constexpr int kDgRow = 72;
-constexpr int kDgGs = kDgKc * kDgRow, kDgWs = kDgKc * kDK * kDgCi;
-constexpr int kDgStage = kDgGs + kDgWs;
-constexpr size_t kDgSmem = 2 * static_cast<size_t>(kDgStage) * sizeof(float);
+constexpr int kDgKc = 8;
+template <int VQ, int CPT>
+struct DgGeom {
+  static constexpr int V = 4 * VQ, BV = 16 * V, CI = 16 * CPT;
+  static constexpr int GUSED = 16 * VQ + 4, GROW = 16 * VQ + 8;
+  static constexpr int GS = kDgKc * GROW, WS = kDgKc * kDK * CI;
+  static constexpr int STAGE = GS + WS;
+  static constexpr size_t SMEM = 2 * static_cast<size_t>(STAGE) * sizeof(float);
+};
 
+// VQ = q positions (x 4 phases) per thread: 4 (256 outputs per block) or 1 (64 per block, when the long tiles would leave
+// SMs idle); CPT = input channels per thread: 4 (64-channel tile) or 2 (32-channel tile, for the 32- and 96-channel layers)
+template <int VQ, int CPT>
 __global__ void __launch_bounds__(256, 2)
 disc_conv15_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__ wT, float* __restrict__ gx, int Cin,
                          int Cout, int T, int To) {
+  using G = DgGeom<VQ, CPT>;
   extern __shared__ __align__(16) float disc_smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int vg = lane & 15, cig = warp * 2 + (lane >> 4);
-  const int vb0 = blockIdx.x * kDgV, ci0 = blockIdx.y * kDgCi, n = blockIdx.z;
+  const int vb0 = blockIdx.x * G::BV, ci0 = blockIdx.y * G::CI, n = blockIdx.z;
   const int qb0 = vb0 / kDS;
   const float* gn = gy + static_cast<size_t>(n) * Cout * To;
   const bool w16 = (Cin & 3) == 0;
-  float acc[4][16];
+  float acc[CPT][G::V];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < CPT; ++i)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < G::V; ++j) acc[i][j] = 0.f;
 
   auto load = [&](int c0, int stage) {
-    float* gs = disc_smem + stage * kDgStage;
-    float* ws = gs + kDgGs;
+    float* gs = disc_smem + stage * G::STAGE;
+    float* ws = gs + G::GS;
     const int nco = min(kDgKc, Cout - c0);
-    for (int idx = tid; idx < nco * 68; idx += 256) {
-      const int co = idx / 68, i = idx - co * 68;
+    for (int idx = tid; idx < nco * G::GUSED; idx += 256) {
+      const int co = idx / G::GUSED, i = idx - co * G::GUSED;
       const int t = qb0 - 4 + i;
       const bool ok = t >= 0 && t < To;
-      cp_async4(gs + co * kDgRow + i, ok ? gn + static_cast<size_t>(c0 + co) * To + t : gn, ok);
+      cp_async4(gs + co * G::GROW + i, ok ? gn + static_cast<size_t>(c0 + co) * To + t : gn, ok);
     }
     if (w16) {
-      for (int idx = tid; idx < nco * kDK * (kDgCi / 4); idx += 256) {
-        const int ci = (idx & 15) * 4, r = idx >> 4;        // r = co * 15 + k
+      for (int idx = tid; idx < nco * kDK * (G::CI / 4); idx += 256) {
+        const int ci = (idx % (G::CI / 4)) * 4, r = idx / (G::CI / 4);        // r = co * 15 + k
         const int k = r % kDK, co = r / kDK;
         const bool ok = ci0 + ci < Cin;
-        cp_async16(ws + r * kDgCi + ci, ok ? wT + (static_cast<size_t>(k) * Cout + c0 + co) * Cin + ci0 + ci : wT, ok);
+        cp_async16(ws + r * G::CI + ci, ok ? wT + (static_cast<size_t>(k) * Cout + c0 + co) * Cin + ci0 + ci : wT, ok);
       }
     } else {
-      for (int idx = tid; idx < nco * kDK * kDgCi; idx += 256) {
-        const int ci = idx & (kDgCi - 1), r = idx >> 6;
+      for (int idx = tid; idx < nco * kDK * G::CI; idx += 256) {
+        const int ci = idx % G::CI, r = idx / G::CI;
         const int k = r % kDK, co = r / kDK;
         const bool ok = ci0 + ci < Cin;
-        cp_async4(ws + r * kDgCi + ci, ok ? wT + (static_cast<size_t>(k) * Cout + c0 + co) * Cin + ci0 + ci : wT, ok);
+        cp_async4(ws + r * G::CI + ci, ok ? wT + (static_cast<size_t>(k) * Cout + c0 + co) * Cin + ci0 + ci : wT, ok);
       }
     }
   };
@@ -477,40 +485,48 @@ disc_conv15_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__
     cp_async_commit();
     cp_async_wait<1>();
     __syncthreads();
-    const float* gs = disc_smem + (c & 1) * kDgStage;
-    const float* ws = gs + kDgGs;
+    const float* gs = disc_smem + (c & 1) * G::STAGE;
+    const float* ws = gs + G::GS;
     const int nco = min(kDgKc, Cout - c * kDgKc);
     for (int co = 0; co < nco; ++co) {
-      float gw[8];
-      {
-        const float4 a = *reinterpret_cast<const float4*>(gs + co * kDgRow + 4 * vg);
-        const float4 b = *reinterpret_cast<const float4*>(gs + co * kDgRow + 4 * vg + 4);
+      float gw[VQ + 4];
+      if constexpr (VQ == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(gs + co * G::GROW + 4 * vg);
+        const float4 b = *reinterpret_cast<const float4*>(gs + co * G::GROW + 4 * vg + 4);
         gw[0] = a.x; gw[1] = a.y; gw[2] = a.z; gw[3] = a.w; gw[4] = b.x; gw[5] = b.y; gw[6] = b.z; gw[7] = b.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < VQ + 4; ++e) gw[e] = gs[co * G::GROW + VQ * vg + e];
       }
 #pragma unroll
       for (int k = 0; k < kDK; ++k) {
-        const float4 w4 = *reinterpret_cast<const float4*>(ws + (co * kDK + k) * kDgCi + 4 * cig);
+        float w[CPT];
+        if constexpr (CPT == 4) {
+          const float4 w4 = *reinterpret_cast<const float4*>(ws + (co * kDK + k) * G::CI + 4 * cig);
+          w[0] = w4.x; w[1] = w4.y; w[2] = w4.z; w[3] = w4.w;
+        } else {
+          const float2 w2 = *reinterpret_cast<const float2*>(ws + (co * kDK + k) * G::CI + 2 * cig);
+          w[0] = w2.x; w[1] = w2.y;
+        }
         const int phi = k & 3, m = k >> 2;
 #pragma unroll
-        for (int qq = 0; qq < 4; ++qq) {
+        for (int qq = 0; qq < VQ; ++qq) {
           const float g = gw[4 + qq - m];
-          acc[0][4 * qq + phi] = fmaf(w4.x, g, acc[0][4 * qq + phi]);
-          acc[1][4 * qq + phi] = fmaf(w4.y, g, acc[1][4 * qq + phi]);
-          acc[2][4 * qq + phi] = fmaf(w4.z, g, acc[2][4 * qq + phi]);
-          acc[3][4 * qq + phi] = fmaf(w4.w, g, acc[3][4 * qq + phi]);
+#pragma unroll
+          for (int i = 0; i < CPT; ++i) acc[i][4 * qq + phi] = fmaf(w[i], g, acc[i][4 * qq + phi]);
         }
       }
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int ci = ci0 + 4 * cig + i;
+  for (int i = 0; i < CPT; ++i) {
+    const int ci = ci0 + CPT * cig + i;
     if (ci >= Cin) continue;
     float* gr = gx + (static_cast<size_t>(n) * Cin + ci) * T;
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int u = vb0 + 16 * vg + j - kDP;
+    for (int j = 0; j < G::V; ++j) {
+      const int u = vb0 + G::V * vg + j - kDP;
       if (u >= 0 && u < T) gr[u] = acc[i][j];
     }
   }
@@ -615,44 +631,72 @@ disc_conv15_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ 
 // data gradient  ga[n, ci, t] = sum_co w[co][ci] gy[n, co, t],  weight gradient  dw[co][ci] = sum_{n, t} gy[n, co, t] a[n, ci, t].
 constexpr int kC1MaxCo = 8;
 
+// block: 32 consecutive t x 8 channel slices (ci = slice, slice + 8, ...), reduced through shared memory
 __global__ void __launch_bounds__(kDiscThreads)
 disc_conv1x1_fwd_kernel(const float* __restrict__ a, const float* __restrict__ w, const float* __restrict__ bias,
                         float* __restrict__ y, int Cin, int Cout, long long T) {
-  const long long t = blockIdx.x * static_cast<long long>(kDiscThreads) + threadIdx.x;
+  __shared__ float red[8][kC1MaxCo][33];
+  const int tl = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const long long t = blockIdx.x * 32ll + tl;
   const int n = blockIdx.y;
-  if (t >= T) return;
   float acc[kC1MaxCo];
 #pragma unroll
-  for (int co = 0; co < kC1MaxCo; ++co) acc[co] = (bias && co < Cout) ? bias[co] : 0.f;
-  const float* an = a + static_cast<size_t>(n) * Cin * T + t;
-  for (int ci = 0; ci < Cin; ++ci) {
-    const float v = an[static_cast<size_t>(ci) * T];
+  for (int co = 0; co < kC1MaxCo; ++co) acc[co] = 0.f;
+  if (t < T) {
+    const float* an = a + static_cast<size_t>(n) * Cin * T + t;
+#pragma unroll 4
+    for (int ci = sl; ci < Cin; ci += 8) {
+      const float v = an[static_cast<size_t>(ci) * T];
 #pragma unroll
-    for (int co = 0; co < kC1MaxCo; ++co)
-      if (co < Cout) acc[co] = fmaf(w[co * Cin + ci], v, acc[co]);
+      for (int co = 0; co < kC1MaxCo; ++co)
+        if (co < Cout) acc[co] = fmaf(w[co * Cin + ci], v, acc[co]);
+    }
   }
 #pragma unroll
-  for (int co = 0; co < kC1MaxCo; ++co)
-    if (co < Cout) y[(static_cast<size_t>(n) * Cout + co) * T + t] = acc[co];
+  for (int co = 0; co < kC1MaxCo; ++co) red[sl][co][tl] = acc[co];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < Cout * 32; idx += kDiscThreads) {
+    const int co = idx >> 5, tt = idx & 31;
+    const long long to = blockIdx.x * 32ll + tt;
+    if (to >= T) continue;
+    float v = bias ? bias[co] : 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v += red[q][co][tt];
+    y[(static_cast<size_t>(n) * Cout + co) * T + to] = v;
+  }
 }
 
+// one thread per element of ga [N, Cin, T]
 __global__ void __launch_bounds__(kDiscThreads)
 disc_conv1x1_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__ w, float* __restrict__ ga, int Cin,
-                          int Cout, long long T) {
-  const long long t = blockIdx.x * static_cast<long long>(kDiscThreads) + threadIdx.x;
-  const int n = blockIdx.y;
-  if (t >= T) return;
-  float g[kC1MaxCo];
-#pragma unroll
-  for (int co = 0; co < kC1MaxCo; ++co) g[co] = co < Cout ? gy[(static_cast<size_t>(n) * Cout + co) * T + t] : 0.f;
-  float* gn = ga + static_cast<size_t>(n) * Cin * T + t;
-  for (int ci = 0; ci < Cin; ++ci) {
+                          int Cout, long long T, size_t total) {
+  for (size_t idx = blockIdx.x * static_cast<size_t>(kDiscThreads) + threadIdx.x; idx < total;
+       idx += static_cast<size_t>(gridDim.x) * kDiscThreads) {
+    const long long t = static_cast<long long>(idx % T);
+    const size_t r = idx / T;
+    const int ci = static_cast<int>(r % Cin);
+    const size_t n = r / Cin;
     float v = 0.f;
-#pragma unroll
-    for (int co = 0; co < kC1MaxCo; ++co)
-      if (co < Cout) v = fmaf(w[co * Cin + ci], g[co], v);
-    gn[static_cast<size_t>(ci) * T] = v;
+    for (int co = 0; co < Cout; ++co) v = fmaf(w[co * Cin + ci], gy[(n * Cout + co) * T + t], v);
+    ga[idx] = v;
   }
+}
+
+// dbias[c] += sum over this block's slice of the (n, t) positions of gy[n, c, t]; grid (C, splits), dbias zeroed before
+__global__ void __launch_bounds__(kDiscThreads)
+disc_bias_grad_kernel(const float* __restrict__ gy, float* __restrict__ db, int N, int C, long long T) {
+  __shared__ float red[8];
+  const int c = blockIdx.x;
+  const long long total = static_cast<long long>(N) * T;
+  const long long per = (total + gridDim.y - 1) / gridDim.y;
+  const long long r0 = blockIdx.y * per, r1 = min(r0 + per, total);
+  float s = 0.f;
+  for (long long r = r0 + threadIdx.x; r < r1; r += kDiscThreads) {
+    const long long n = r / T, t = r - n * T;
+    s += gy[(static_cast<size_t>(n) * C + c) * T + t];
+  }
+  s = block_sum_256(s, red);
+  if (threadIdx.x == 0) atomicAdd(db + c, s);
 }
 
 // one block per (ci, co): dw[co][ci] = sum over (n, t)

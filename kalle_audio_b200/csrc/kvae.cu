@@ -2763,9 +2763,16 @@ int kvae_disc_conv15_fwd(const float* x, float* y, const float* w, const float* 
   const size_t n = static_cast<size_t>(Cin) * Cout * kDK;
   pack_weights_kernel<<<static_cast<int>(std::min<size_t>((n + 255) / 256, 4096)), 256, 0, st>>>(w, 0, Cout, Cin, kDK, nullptr, wp);
   KV_CUDA(cudaGetLastError());
-  dim3 grid(ceil_div(To, kCfTt), ceil_div(Cout, kCfCo), N);
-  KV_CUDA(cudaFuncSetAttribute(disc_conv15_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kCfSmem)));
-  disc_conv15_fwd_kernel<<<grid, 256, kCfSmem, st>>>(x, wp, bias, y, Cin, Cout, static_cast<int>(T), To);
+  const long long long_blocks = static_cast<long long>(ceil_div(To, CfGeom<8>::BT)) * ceil_div(Cout, kCfCo) * N;
+  if (long_blocks >= 2ll * sm_count()) {
+    dim3 grid(ceil_div(To, CfGeom<8>::BT), ceil_div(Cout, kCfCo), N);
+    KV_CUDA(cudaFuncSetAttribute(disc_conv15_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(CfGeom<8>::SMEM)));
+    disc_conv15_fwd_kernel<8><<<grid, 256, CfGeom<8>::SMEM, st>>>(x, wp, bias, y, Cin, Cout, static_cast<int>(T), To);
+  } else {      // short layer: 32 outputs per block instead of 128, four times the blocks
+    dim3 grid(ceil_div(To, CfGeom<2>::BT), ceil_div(Cout, kCfCo), N);
+    KV_CUDA(cudaFuncSetAttribute(disc_conv15_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(CfGeom<2>::SMEM)));
+    disc_conv15_fwd_kernel<2><<<grid, 256, CfGeom<2>::SMEM, st>>>(x, wp, bias, y, Cin, Cout, static_cast<int>(T), To);
+  }
   KV_CUDA(cudaGetLastError());
   g_launches += 2;
   return 0;
@@ -2796,7 +2803,10 @@ int kvae_disc_conv15_bwd(const float* x, const float* gy, const float* w, float*
     ++g_launches;
   }
   if (dbias) {
-    bias_grad_cf_kernel<<<Cout, 256, 0, st>>>(gy, 1, dbias, N, Cout, To);
+    KV_CUDA(cudaMemsetAsync(dbias, 0, static_cast<size_t>(Cout) * 4, st));
+    const int splits = static_cast<int>(std::max<long long>(1, std::min<long long>((2ll * sm_count() + Cout - 1) / Cout,
+                                                                                 (static_cast<long long>(N) * To + 4095) / 4096)));
+    disc_bias_grad_kernel<<<dim3(Cout, splits), kDiscThreads, 0, st>>>(gy, dbias, N, Cout, To);
     KV_CUDA(cudaGetLastError());
     ++g_launches;
   }
@@ -2807,9 +2817,25 @@ int kvae_disc_conv15_bwd(const float* x, const float* gy, const float* w, float*
   float* wT = static_cast<float*>(scratch);
   pack_weights_kernel<<<static_cast<int>(std::min<size_t>((n + 255) / 256, 4096)), 256, 0, st>>>(w, 1, Cin, Cout, kDK, nullptr, wT);
   KV_CUDA(cudaGetLastError());
-  dim3 grid(ceil_div(static_cast<int>(T) + kDP, kDgV), ceil_div(Cin, kDgCi), N);
-  KV_CUDA(cudaFuncSetAttribute(disc_conv15_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kDgSmem)));
-  disc_conv15_dgrad_kernel<<<grid, 256, kDgSmem, st>>>(gy, wT, gx, Cin, Cout, static_cast<int>(T), To);
+  {
+    const int Ti = static_cast<int>(T);
+    const bool narrow = ceil_div(Cin, 32) * 32 < ceil_div(Cin, 64) * 64;      // a 32-channel tile wastes less (32, 96, ...)
+    const int ci_tiles = narrow ? ceil_div(Cin, 32) : ceil_div(Cin, 64);
+    const bool shortl = static_cast<long long>(ceil_div(Ti + kDP, 256)) * ci_tiles * N < 2ll * sm_count();
+#define KVAE_DG_LAUNCH(VQ, CPT)                                                                                           \
+    do {                                                                                                                  \
+      using G = DgGeom<VQ, CPT>;                                                                                          \
+      dim3 grid(ceil_div(Ti + kDP, G::BV), ceil_div(Cin, G::CI), N);                                                      \
+      KV_CUDA(cudaFuncSetAttribute(disc_conv15_dgrad_kernel<VQ, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                   static_cast<int>(G::SMEM)));                                                           \
+      disc_conv15_dgrad_kernel<VQ, CPT><<<grid, 256, G::SMEM, st>>>(gy, wT, gx, Cin, Cout, Ti, To);                        \
+    } while (0)
+    if (!shortl && !narrow) KVAE_DG_LAUNCH(4, 4);
+    else if (!shortl) KVAE_DG_LAUNCH(4, 2);
+    else if (!narrow) KVAE_DG_LAUNCH(1, 4);
+    else KVAE_DG_LAUNCH(1, 2);
+#undef KVAE_DG_LAUNCH
+  }
   KV_CUDA(cudaGetLastError());
   g_launches += 2;
   return 0;
@@ -2827,7 +2853,7 @@ int kvae_disc_conv1x1_fwd(const float* x, float* y, const float* w, const float*
   if (Cout < 1 || Cout > kC1MaxCo || N > 65535) return fail("disc 1x1 conv: 1..8 output channels, batch <= 65535");
   DeviceGuard guard(device_of(x));
   if (!guard.ok) return fail("cannot select the tensor's device");
-  dim3 grid(static_cast<unsigned>((T + kDiscThreads - 1) / kDiscThreads), N);
+  dim3 grid(static_cast<unsigned>((T + 31) / 32), N);
   disc_conv1x1_fwd_kernel<<<grid, kDiscThreads, 0, static_cast<cudaStream_t>(stream)>>>(x, w, bias, y, Cin, Cout, T);
   KV_CUDA(cudaGetLastError());
   ++g_launches;
@@ -2854,8 +2880,8 @@ int kvae_disc_conv1x1_bwd(const float* x, const float* gy, const float* w, float
     ++g_launches;
   }
   if (gx) {
-    dim3 grid(static_cast<unsigned>((T + kDiscThreads - 1) / kDiscThreads), N);
-    disc_conv1x1_dgrad_kernel<<<grid, kDiscThreads, 0, st>>>(gy, w, gx, Cin, Cout, T);
+    const size_t total = static_cast<size_t>(N) * Cin * T;
+    disc_conv1x1_dgrad_kernel<<<disc_grid(total), kDiscThreads, 0, st>>>(gy, w, gx, Cin, Cout, T, total);
     KV_CUDA(cudaGetLastError());
     ++g_launches;
   }
