@@ -532,6 +532,46 @@ disc_conv15_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__
   }
 }
 
+// ---- data gradient of the io-side layer (2 .. 24 folded input channels, <= 128 output channels): too few channels for a
+// channel tile.  One thread per output sample and group of 4 input channels; the group's weights [co][k][4 ci] sit in
+// shared memory; per output channel a thread reads the <= 4 gradients q - m that reach its sample.
+constexpr int kDsMaxCo = 128;
+
+__global__ void __launch_bounds__(kDiscThreads)
+disc_conv15_dgrad_small_kernel(const float* __restrict__ gy, const float* __restrict__ w, float* __restrict__ gx, int Cin,
+                               int Cout, int T, int To) {
+  __shared__ __align__(16) float ws[kDsMaxCo * kDK * 4];
+  const int ci0 = 4 * blockIdx.y, n = blockIdx.z;
+  for (int idx = threadIdx.x; idx < Cout * kDK * 4; idx += kDiscThreads) {
+    const int i = idx & 3, r = idx >> 2;
+    const int k = r % kDK, co = r / kDK;
+    ws[idx] = (ci0 + i < Cin) ? w[(static_cast<size_t>(co) * Cin + ci0 + i) * kDK + k] : 0.f;
+  }
+  __syncthreads();
+  const int u = blockIdx.x * kDiscThreads + threadIdx.x;
+  if (u >= T) return;
+  const int v = u + kDP, phi = v & 3, q = v >> 2;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  const float* gn = gy + static_cast<size_t>(n) * Cout * To;
+  for (int co = 0; co < Cout; ++co) {
+    const float* gr = gn + static_cast<size_t>(co) * To;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int k = phi + 4 * m, t = q - m;
+      if (k < kDK && t >= 0 && t < To) {
+        const float g = gr[t];
+        const float4 w4 = *reinterpret_cast<const float4*>(&ws[(co * kDK + k) * 4]);
+        a0 = fmaf(w4.x, g, a0); a1 = fmaf(w4.y, g, a1); a2 = fmaf(w4.z, g, a2); a3 = fmaf(w4.w, g, a3);
+      }
+    }
+  }
+  float* gr = gx + (static_cast<size_t>(n) * Cin + ci0) * T + u;
+  if (ci0 < Cin) gr[0] = a0;
+  if (ci0 + 1 < Cin) gr[static_cast<size_t>(T)] = a1;
+  if (ci0 + 2 < Cin) gr[2 * static_cast<size_t>(T)] = a2;
+  if (ci0 + 3 < Cin) gr[3 * static_cast<size_t>(T)] = a3;
+}
+
 // ---- weight gradient: dw[co][ci][k] += sum_{n, t} gy[n, co, t] * x[n, ci, 4 t + k - 7]      (torch layout, atomics)
 // Block: 64 co x 16 ci x 15 taps over a slice of the (n, 64-sample t block) items; 256 threads = 16 ci (lane % 16) x 16
 // co-groups (4 co): 60 accumulators per thread.  Per 4 outputs t a thread loads 4 x 4 gradients and a 28-float input

@@ -2811,7 +2811,14 @@ int kvae_disc_conv15_bwd(const float* x, const float* gy, const float* w, float*
     ++g_launches;
   }
   if (!gx) return 0;
-  if (Cin < 32)      // the io-side layer (2 .. 22 folded channels): a 64-channel tile would idle; generic data gradient
+  if (Cin < 32 && Cout <= kDsMaxCo) {      // the io-side layer (2 .. 22 folded channels): no channel tile to fill
+    dim3 grid(ceil_div(static_cast<int>(T), kDiscThreads), ceil_div(Cin, 4), N);
+    disc_conv15_dgrad_small_kernel<<<grid, kDiscThreads, 0, st>>>(gy, w, gx, Cin, Cout, static_cast<int>(T), To);
+    KV_CUDA(cudaGetLastError());
+    ++g_launches;
+    return 0;
+  }
+  if (Cin < 32)
     return kvae_conv1d_bwd(x, gy, w, gx, nullptr, nullptr, 0, N, Cin, Cout, T, kDK, kDS, 1, kDP, KVAE_F32, scratch,
                            scratch_bytes, stream);
   float* wT = static_cast<float*>(scratch);
