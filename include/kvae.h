@@ -315,8 +315,8 @@ int kvae_vae_sample(const void* mean, const void* scale, const void* noise, void
  * stable_audio_tools/models/discriminators.py: SharedDiscriminatorConvNet (62-116), MultiScaleDiscriminator (119-138),
  * MultiPeriodDiscriminator (140-168), MultiDiscriminator (171-238), OobleckDiscriminator.loss (240-297),
  * get_hinge_losses (11-14); wired at training/autoencoders.py:133-134, 288.  Every net is a stack of strided
- * convolutions + SiLU; they run on kvae_conv1d_fwd / kvae_conv1d_bwd (dw may be NULL there when only the data gradient
- * is wanted).  The multi-period nets' 15 x 15 Conv2d over [N, C, ceil(T / n), n] becomes a Conv1d over the folded
+ * convolutions + SiLU; they run on kvae_disc_conv15_* / kvae_disc_conv1x1_* below (kvae_conv1d_fwd / kvae_conv1d_bwd for
+ * any other kernel size / stride; dw may be NULL when only the data gradient is wanted).  The multi-period nets' 15 x 15 Conv2d over [N, C, ceil(T / n), n] becomes a Conv1d over the folded
  * channels (c, w): same products, minus those with padding zeros.  All tensors fp32, contiguous; `backward` = 1 runs the
  * adjoint with the roles of the two tensor arguments exchanged (first = incoming gradient, second = outgoing). */
 /* MultiPeriodDiscriminator.fold (:164-168): y[b, c n + w, h] = x[b, c, h n + w] (0 past T); x [N, C, T], y [N, C n, ceil(T / n)] */

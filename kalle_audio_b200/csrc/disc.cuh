@@ -5,10 +5,11 @@
 // [N, C, H = ceil(T / n), W = n] with n <= 11 < 15, so most of the 225 taps only ever meet zero padding.  Here the
 // W axis moves into the channels: x' [N, C * W, H], w' [(co, wo), (ci, wi), kh] = w[co, ci, kh, wi - 4 wo + 7] (0 where
 // that column index falls outside the kernel) -- the SAME arithmetic as the Conv2d minus the products with padding
-// zeros (15 x fewer multiply-adds once W has shrunk to 1, which is the case from the second or third layer on).  The
-// convolutions themselves run on the layer-level conv kernels (conv_direct_kernel / wgrad_direct_kernel, fp32); this
+// zeros (15 x fewer multiply-adds once W has shrunk to 1, which is the case from the second or third layer on).  This
 // file holds the fold / unfold of inputs and weights, SiLU, avg_pool1d(2), the score mean, the hinge losses and the
-// feature-matching distance over all feature tensors in one launch, each with its backward.
+// feature-matching distance over all feature tensors in one launch, each with its backward (first half), and the fp32
+// kernels of the convolutions themselves: k = 15 / stride 4 forward, data gradient, weight gradient, and the final 1 x 1
+// conv (second half).  Convs of any other geometry run on the generic layer kernels (conv_direct_kernel / wgrad_direct_kernel).
 #pragma once
 #include <cstdint>
 

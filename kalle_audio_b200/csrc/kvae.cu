@@ -2764,7 +2764,7 @@ int kvae_disc_conv15_fwd(const float* x, float* y, const float* w, const float* 
   pack_weights_kernel<<<static_cast<int>(std::min<size_t>((n + 255) / 256, 4096)), 256, 0, st>>>(w, 0, Cout, Cin, kDK, nullptr, wp);
   KV_CUDA(cudaGetLastError());
   const long long long_blocks = static_cast<long long>(ceil_div(To, CfGeom<8>::BT)) * ceil_div(Cout, kCfCo) * N;
-  if (long_blocks >= 2ll * sm_count()) {
+  if (2 * long_blocks >= sm_count()) {      // (measured: the short tiles only pay when the long ones fill < half the SMs)
     dim3 grid(ceil_div(To, CfGeom<8>::BT), ceil_div(Cout, kCfCo), N);
     KV_CUDA(cudaFuncSetAttribute(disc_conv15_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(CfGeom<8>::SMEM)));
     disc_conv15_fwd_kernel<8><<<grid, 256, CfGeom<8>::SMEM, st>>>(x, wp, bias, y, Cin, Cout, static_cast<int>(T), To);
@@ -2828,7 +2828,7 @@ int kvae_disc_conv15_bwd(const float* x, const float* gy, const float* w, float*
     const int Ti = static_cast<int>(T);
     const bool narrow = ceil_div(Cin, 32) * 32 < ceil_div(Cin, 64) * 64;      // a 32-channel tile wastes less (32, 96, ...)
     const int ci_tiles = narrow ? ceil_div(Cin, 32) : ceil_div(Cin, 64);
-    const bool shortl = static_cast<long long>(ceil_div(Ti + kDP, 256)) * ci_tiles * N < 2ll * sm_count();
+    const bool shortl = 2ll * ceil_div(Ti + kDP, 256) * ci_tiles * N < sm_count();
 #define KVAE_DG_LAUNCH(VQ, CPT)                                                                                           \
     do {                                                                                                                  \
       using G = DgGeom<VQ, CPT>;                                                                                          \
