@@ -317,22 +317,15 @@ template <int TT>
 struct CfGeom {
   static constexpr int BT = 16 * TT;                                   // outputs t per block
   static constexpr int SLAB = 4 * BT + 12;                             // slab entries per channel
-  // 4 floats of padding after every 32 slab entries (every 64 for TT = 16): the window starts of 8 consecutive t-groups,
-  // 4 TT floats apart, then fall into 8 different groups of 4 banks
-  static constexpr int SH = TT == 16 ? 6 : 5;
-  static constexpr int ROW = ((SLAB - 1) + 4 * ((SLAB - 1) >> SH) + 4) & ~3;
+  static constexpr int ROW = ((SLAB - 1) + 4 * ((SLAB - 1) >> 5) + 4) & ~3;   // 4 floats of padding after every 32
   static constexpr int XS = kCfKc * ROW, WS = kCfKc * kDK * kCfCo;
   static constexpr int STAGE = XS + WS;                                // floats per pipeline stage
   static constexpr size_t SMEM = 2 * static_cast<size_t>(STAGE) * sizeof(float);
 };
 
-// TT = outputs per thread: 16 (256 per block, one block per SM) for the long layers -- every 16-byte shared-memory load
-// costs four transactions whether its lanes share addresses or not, so at TT = 8 the 26 loads per input channel (104
-// transactions for 480 FMA instructions, four of which issue per clock) keep the load pipe 87 % busy and the FMA pipe
-// reaches ~46 %; at TT = 16 it is 34 loads for 960; 8 (128 per block) for the medium ones; 2 (32 per block) when even those
-// would leave more than half the SMs idle
+// TT = outputs per thread: 8 (128 per block) for long layers; 2 (32 per block) when the long tiles would leave SMs idle
 template <int TT>
-__global__ void __launch_bounds__(256, TT == 16 ? 1 : 2)
+__global__ void __launch_bounds__(256, 2)
 disc_conv15_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wp, const float* __restrict__ bias,
                        float* __restrict__ y, int Cin, int Cout, int T, int To) {
   using G = CfGeom<TT>;
@@ -357,7 +350,7 @@ disc_conv15_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wp
       const int ci = idx / G::SLAB, j = idx - ci * G::SLAB;
       const long long u = u0 + j;
       const bool ok = u >= 0 && u < T;
-      cp_async4(xs + ci * G::ROW + j + 4 * (j >> G::SH), ok ? xn + static_cast<size_t>(c0 + ci) * T + u : xn, ok);
+      cp_async4(xs + ci * G::ROW + j + 4 * (j >> 5), ok ? xn + static_cast<size_t>(c0 + ci) * T + u : xn, ok);
     }
     if (w16) {
       for (int idx = tid; idx < nci * kDK * (kCfCo / 4); idx += 256) {
@@ -392,7 +385,7 @@ disc_conv15_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wp
 #pragma unroll
       for (int q = 0; q < TT + 3; ++q) {
         const int jj = 4 * TT * tg + 4 * q;
-        const float4 v = *reinterpret_cast<const float4*>(xs + ci * G::ROW + jj + 4 * (jj >> G::SH));
+        const float4 v = *reinterpret_cast<const float4*>(xs + ci * G::ROW + jj + 4 * (jj >> 5));
         xw[4 * q] = v.x; xw[4 * q + 1] = v.y; xw[4 * q + 2] = v.z; xw[4 * q + 3] = v.w;
       }
 #pragma unroll
@@ -438,10 +431,8 @@ struct DgGeom {
   static constexpr size_t SMEM = 2 * static_cast<size_t>(STAGE) * sizeof(float);
 };
 
-// VQ = q positions (x 4 phases) per thread: 8 / 4 (512 / 256 outputs per block) or 1 (64 per block, when the long tiles
-// would leave SMs idle); CPT = input channels per thread: 4 (64-channel tile) or 2 (32-channel tile).  <8, 2> is the form
-// for the long layers: a weight read from shared memory feeds 8 FMAs instead of 4 (42 load transactions per 240 FMA
-// instructions instead of 68 at <4, 4>, which is load-pipe bound)
+// VQ = q positions (x 4 phases) per thread: 4 (256 outputs per block) or 1 (64 per block, when the long tiles would leave
+// SMs idle); CPT = input channels per thread: 4 (64-channel tile) or 2 (32-channel tile, for the 32- and 96-channel layers)
 template <int VQ, int CPT>
 __global__ void __launch_bounds__(256, 2)
 disc_conv15_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__ wT, float* __restrict__ gx, int Cin,
@@ -500,12 +491,10 @@ disc_conv15_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__
     const int nco = min(kDgKc, Cout - c * kDgKc);
     for (int co = 0; co < nco; ++co) {
       float gw[VQ + 4];
-      if constexpr (VQ % 4 == 0) {
-#pragma unroll
-        for (int e = 0; e < (VQ + 4) / 4; ++e) {
-          const float4 a = *reinterpret_cast<const float4*>(gs + co * G::GROW + VQ * vg + 4 * e);
-          gw[4 * e] = a.x; gw[4 * e + 1] = a.y; gw[4 * e + 2] = a.z; gw[4 * e + 3] = a.w;
-        }
+      if constexpr (VQ == 4) {
+        const float4 a = *reinterpret_cast<const float4*>(gs + co * G::GROW + 4 * vg);
+        const float4 b = *reinterpret_cast<const float4*>(gs + co * G::GROW + 4 * vg + 4);
+        gw[0] = a.x; gw[1] = a.y; gw[2] = a.z; gw[3] = a.w; gw[4] = b.x; gw[5] = b.y; gw[6] = b.z; gw[7] = b.w;
       } else {
 #pragma unroll
         for (int e = 0; e < VQ + 4; ++e) gw[e] = gs[co * G::GROW + VQ * vg + e];

@@ -2763,20 +2763,16 @@ int kvae_disc_conv15_fwd(const float* x, float* y, const float* w, const float* 
   const size_t n = static_cast<size_t>(Cin) * Cout * kDK;
   pack_weights_kernel<<<static_cast<int>(std::min<size_t>((n + 255) / 256, 4096)), 256, 0, st>>>(w, 0, Cout, Cin, kDK, nullptr, wp);
   KV_CUDA(cudaGetLastError());
-  const long long co_tiles = ceil_div(Cout, kCfCo);
-#define KVAE_CF_LAUNCH(TT)                                                                                                \
-  do {                                                                                                                    \
-    dim3 grid(ceil_div(To, CfGeom<TT>::BT), static_cast<unsigned>(co_tiles), N);                                          \
-    KV_CUDA(cudaFuncSetAttribute(disc_conv15_fwd_kernel<TT>, cudaFuncAttributeMaxDynamicSharedMemorySize,                 \
-                                 static_cast<int>(CfGeom<TT>::SMEM)));                                                    \
-    disc_conv15_fwd_kernel<TT><<<grid, 256, CfGeom<TT>::SMEM, st>>>(x, wp, bias, y, Cin, Cout, static_cast<int>(T), To);   \
-  } while (0)
-  // 256-output tiles (one block per SM) when they give every SM a block, 128-output tiles while those fill half the SMs
-  // (measured: with more blocks than that the 32-output tiles are slower), 32-output tiles for the short layers
-  if (ceil_div(To, CfGeom<16>::BT) * co_tiles * N >= sm_count()) KVAE_CF_LAUNCH(16);
-  else if (2 * ceil_div(To, CfGeom<8>::BT) * co_tiles * N >= sm_count()) KVAE_CF_LAUNCH(8);
-  else KVAE_CF_LAUNCH(2);
-#undef KVAE_CF_LAUNCH
+  const long long long_blocks = static_cast<long long>(ceil_div(To, CfGeom<8>::BT)) * ceil_div(Cout, kCfCo) * N;
+  if (2 * long_blocks >= sm_count()) {      // (measured: the short tiles only pay when the long ones fill < half the SMs)
+    dim3 grid(ceil_div(To, CfGeom<8>::BT), ceil_div(Cout, kCfCo), N);
+    KV_CUDA(cudaFuncSetAttribute(disc_conv15_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(CfGeom<8>::SMEM)));
+    disc_conv15_fwd_kernel<8><<<grid, 256, CfGeom<8>::SMEM, st>>>(x, wp, bias, y, Cin, Cout, static_cast<int>(T), To);
+  } else {      // short layer: 32 outputs per block instead of 128, four times the blocks
+    dim3 grid(ceil_div(To, CfGeom<2>::BT), ceil_div(Cout, kCfCo), N);
+    KV_CUDA(cudaFuncSetAttribute(disc_conv15_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(CfGeom<2>::SMEM)));
+    disc_conv15_fwd_kernel<2><<<grid, 256, CfGeom<2>::SMEM, st>>>(x, wp, bias, y, Cin, Cout, static_cast<int>(T), To);
+  }
   KV_CUDA(cudaGetLastError());
   g_launches += 2;
   return 0;
@@ -2841,8 +2837,7 @@ int kvae_disc_conv15_bwd(const float* x, const float* gy, const float* w, float*
                                    static_cast<int>(G::SMEM)));                                                           \
       disc_conv15_dgrad_kernel<VQ, CPT><<<grid, 256, G::SMEM, st>>>(gy, wT, gx, Cin, Cout, Ti, To);                        \
     } while (0)
-    if (static_cast<long long>(ceil_div(Ti + kDP, 512)) * ceil_div(Cin, 32) * N >= 2ll * sm_count()) KVAE_DG_LAUNCH(8, 2);
-    else if (!shortl && !narrow) KVAE_DG_LAUNCH(4, 4);
+    if (!shortl && !narrow) KVAE_DG_LAUNCH(4, 4);
     else if (!shortl) KVAE_DG_LAUNCH(4, 2);
     else if (!narrow) KVAE_DG_LAUNCH(1, 4);
     else KVAE_DG_LAUNCH(1, 2);

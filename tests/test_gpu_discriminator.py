@@ -143,7 +143,7 @@ def test_silu_score_hinge_feature_match():
 @pytest.mark.parametrize("generic", [False, True])
 @pytest.mark.parametrize("Cin,Cout,T", [(2, 32, 2999), (32, 64, 751), (96, 64, 70), (128, 256, 47), (256, 1, 12),
                                         (64, 128, 3001), (22, 96, 1030), (33, 65, 517), (128, 256, 1),
-                                        (32, 64, 52001), (64, 128, 40001), (96, 64, 30002), (32, 64, 20001), (64, 64, 9001)])
+                                        (32, 64, 52001), (64, 128, 40001), (96, 64, 30002)])
 def test_strided_k15_conv_fwd_bwd(Cin, Cout, T, generic, monkeypatch):
     """the discriminator's conv geometry (k = 15, stride 4, padding 7; k = 1 for the last layer) forward and all three
     gradients against torch, on the kernels written for it (kvae_disc_conv15_*: full and ragged tiles in every dimension,
