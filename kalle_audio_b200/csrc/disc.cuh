@@ -342,30 +342,33 @@ disc_conv15_fwd_kernel(const float* __restrict__ x, const float* __restrict__ wp
 #pragma unroll
     for (int j = 0; j < TT; ++j) acc[i][j] = 0.f;
 
+  // one warp per input channel of the chunk (8 warps, 8 channels): no index arithmetic beyond an add per copy -- the first
+  // version derived (channel, position) from a flat index with divisions, and a sixth of all issued instructions were
+  // that integer work (ncu: ALU pipe 23 % next to FMA 49 %, profiles/r02_disc_conv15_fwd_msd0_l2_l4.ncu-rep)
+  static_assert(kCfKc == 8, "one warp per channel");
   auto load = [&](int c0, int stage) {
     float* xs = disc_smem + stage * G::STAGE;
     float* ws = xs + G::XS;
-    const int nci = min(kCfKc, Cin - c0);
-    for (int idx = tid; idx < nci * G::SLAB; idx += 256) {
-      const int ci = idx / G::SLAB, j = idx - ci * G::SLAB;
+    if (c0 + warp >= Cin) return;
+    const float* xr = xn + static_cast<size_t>(c0 + warp) * T;
+    float* dst = xs + warp * G::ROW;
+    for (int j = lane; j < G::SLAB; j += 32) {
       const long long u = u0 + j;
       const bool ok = u >= 0 && u < T;
-      cp_async4(xs + ci * G::ROW + j + 4 * (j >> 5), ok ? xn + static_cast<size_t>(c0 + ci) * T + u : xn, ok);
+      cp_async4(dst + j + 4 * (j >> 5), ok ? xr + u : xn, ok);
     }
+    float* wd = ws + warp * kDK * kCfCo;
     if (w16) {
-      for (int idx = tid; idx < nci * kDK * (kCfCo / 4); idx += 256) {
-        const int co = (idx & 15) * 4, r = idx >> 4;        // r = ci * 15 + k
-        const int k = r % kDK, ci = r / kDK;
-        const bool ok = co0 + co < Cout;
-        cp_async16(ws + r * kCfCo + co, ok ? wp + (static_cast<size_t>(k) * Cin + c0 + ci) * Cout + co0 + co : wp, ok);
-      }
+      const int co = (lane & 15) * 4;
+      const bool ok = co0 + co < Cout;
+      for (int k = lane >> 4; k < kDK; k += 2)
+        cp_async16(wd + k * kCfCo + co, ok ? wp + (static_cast<size_t>(k) * Cin + c0 + warp) * Cout + co0 + co : wp, ok);
     } else {
-      for (int idx = tid; idx < nci * kDK * kCfCo; idx += 256) {
-        const int co = idx & (kCfCo - 1), r = idx >> 6;
-        const int k = r % kDK, ci = r / kDK;
-        const bool ok = co0 + co < Cout;
-        cp_async4(ws + r * kCfCo + co, ok ? wp + (static_cast<size_t>(k) * Cin + c0 + ci) * Cout + co0 + co : wp, ok);
-      }
+      for (int k = 0; k < kDK; ++k)
+        for (int co = lane; co < kCfCo; co += 32) {
+          const bool ok = co0 + co < Cout;
+          cp_async4(wd + k * kCfCo + co, ok ? wp + (static_cast<size_t>(k) * Cin + c0 + warp) * Cout + co0 + co : wp, ok);
+        }
     }
   };
 
@@ -451,30 +454,31 @@ disc_conv15_dgrad_kernel(const float* __restrict__ gy, const float* __restrict__
 #pragma unroll
     for (int j = 0; j < G::V; ++j) acc[i][j] = 0.f;
 
-  auto load = [&](int c0, int stage) {
+  static_assert(kDgKc == 8, "one warp per channel");
+  auto load = [&](int c0, int stage) {      // one warp per output channel of the chunk
     float* gs = disc_smem + stage * G::STAGE;
     float* ws = gs + G::GS;
-    const int nco = min(kDgKc, Cout - c0);
-    for (int idx = tid; idx < nco * G::GUSED; idx += 256) {
-      const int co = idx / G::GUSED, i = idx - co * G::GUSED;
+    if (c0 + warp >= Cout) return;
+    const float* gr = gn + static_cast<size_t>(c0 + warp) * To;
+    float* dst = gs + warp * G::GROW;
+    for (int i = lane; i < G::GUSED; i += 32) {
       const int t = qb0 - 4 + i;
       const bool ok = t >= 0 && t < To;
-      cp_async4(gs + co * G::GROW + i, ok ? gn + static_cast<size_t>(c0 + co) * To + t : gn, ok);
+      cp_async4(dst + i, ok ? gr + t : gn, ok);
     }
+    float* wd = ws + warp * kDK * G::CI;
     if (w16) {
-      for (int idx = tid; idx < nco * kDK * (G::CI / 4); idx += 256) {
-        const int ci = (idx % (G::CI / 4)) * 4, r = idx / (G::CI / 4);        // r = co * 15 + k
-        const int k = r % kDK, co = r / kDK;
-        const bool ok = ci0 + ci < Cin;
-        cp_async16(ws + r * G::CI + ci, ok ? wT + (static_cast<size_t>(k) * Cout + c0 + co) * Cin + ci0 + ci : wT, ok);
-      }
+      constexpr int VPR = G::CI / 4;          // 16-byte pieces per (co, k) row
+      const int ci = (lane % VPR) * 4;
+      const bool ok = ci0 + ci < Cin;
+      for (int k = lane / VPR; k < kDK; k += 32 / VPR)
+        cp_async16(wd + k * G::CI + ci, ok ? wT + (static_cast<size_t>(k) * Cout + c0 + warp) * Cin + ci0 + ci : wT, ok);
     } else {
-      for (int idx = tid; idx < nco * kDK * G::CI; idx += 256) {
-        const int ci = idx % G::CI, r = idx / G::CI;
-        const int k = r % kDK, co = r / kDK;
-        const bool ok = ci0 + ci < Cin;
-        cp_async4(ws + r * G::CI + ci, ok ? wT + (static_cast<size_t>(k) * Cout + c0 + co) * Cin + ci0 + ci : wT, ok);
-      }
+      for (int k = 0; k < kDK; ++k)
+        for (int ci = lane; ci < G::CI; ci += 32) {
+          const bool ok = ci0 + ci < Cin;
+          cp_async4(wd + k * G::CI + ci, ok ? wT + (static_cast<size_t>(k) * Cout + c0 + warp) * Cin + ci0 + ci : wT, ok);
+        }
     }
   };
 
@@ -600,23 +604,28 @@ disc_conv15_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ 
 #pragma unroll
     for (int k = 0; k < kDK; ++k) acc[i][k] = 0.f;
 
-  auto load = [&](int item, int stage) {
+  auto load = [&](int item, int stage) {      // warps walk whole rows: an add per copy, no divisions
     float* gs = disc_smem + stage * kWgStage;
     float* xs = gs + kWgGs;
     const int n = item / tiles_t, t0 = (item - n * tiles_t) * kWgTc;
-    for (int idx = tid; idx < kWgCo * kWgTc; idx += 256) {
-      const int row = idx >> 6, col = idx & 63;
-      const int co = co0 + row, t = t0 + col;
-      const bool ok = co < Cout && t < To;
-      cp_async4(gs + row * kWgGRow + col, ok ? gy + (static_cast<size_t>(n) * Cout + co) * To + t : gy, ok);
+    for (int row = warp; row < kWgCo; row += 8) {
+      const int co = co0 + row;
+      const float* gr = gy + (static_cast<size_t>(n) * Cout + min(co, Cout - 1)) * To;
+      for (int col = lane; col < kWgTc; col += 32) {
+        const int t = t0 + col;
+        const bool ok = co < Cout && t < To;
+        cp_async4(gs + row * kWgGRow + col, ok ? gr + t : gy, ok);
+      }
     }
     const long long u0 = static_cast<long long>(kDS) * t0 - kDP;
-    for (int idx = tid; idx < kWgCi * kWgXUsed; idx += 256) {
-      const int ci = idx / kWgXUsed, j = idx - ci * kWgXUsed;
-      const long long u = u0 + j;
+    for (int ci = warp; ci < kWgCi; ci += 8) {
       const int c = ci0 + ci;
-      const bool ok = c < Cin && u >= 0 && u < T;
-      cp_async4(xs + ci * kWgXRow + j, ok ? x + (static_cast<size_t>(n) * Cin + c) * T + u : x, ok);
+      const float* xr = x + (static_cast<size_t>(n) * Cin + min(c, Cin - 1)) * T;
+      for (int j = lane; j < kWgXUsed; j += 32) {
+        const long long u = u0 + j;
+        const bool ok = c < Cin && u >= 0 && u < T;
+        cp_async4(xs + ci * kWgXRow + j, ok ? xr + u : x, ok);
+      }
     }
   };
 
